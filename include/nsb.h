@@ -1,0 +1,198 @@
+/*
+ * nsb.h — C ABI of the B200-native leaf-evaluation executor ("nsb" = nshogi-b200).
+ *
+ * This is the drop-in boundary for nyashiki/nshogi-engine's NN leaf-evaluation path.
+ * The reference selects its executor at compile time behind the C++ virtual class
+ * `nshogi::engine::infer::Infer` (reference src/infer/infer.h:19-32).  The reference has no
+ * C ABI of its own; every entry point below names the reference interface it replaces so
+ * a thin `infer::B200 : Infer` (nshogi-engine_b200/host/infer_b200.h) can forward to it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary
+ *   - every function returns 0 on success or a negative nsb_status; nsb_last_error()
+ *     returns a thread-local human-readable message for the last failure
+ *   - there is NO CPU fallback: if no CUDA device / kernel image is usable the call fails
+ *   - one nsb_ctx per host evaluator thread (reference: one Infer per EvaluationWorker,
+ *     src/mcts/evaluationworker.cc:75-103); a ctx is not thread-safe
+ *   - "host" pointers may be pageable or pinned; pinned (cudaHostRegister'd, as the
+ *     reference's Evaluator does at src/evaluate/evaluator.cc:95-106) makes copies async
+ */
+#ifndef NSB_H
+#define NSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_NUM_SQUARES 81      /* nshogi core::NumSquares                               */
+#define NSB_POLICY_PLANES 27    /* 27 move-type planes (src/mcts/evaluationworker.cc:166) */
+#define NSB_POLICY_SIZE 2187    /* ml::MoveIndexMax = 27 * 81 (src/infer/trt.cc:205)      */
+#define NSB_FEATURE_CHANNELS 86 /* preset::SimpleFeatures (src/evaluate/preset.h:20-66)   */
+#define NSB_MAX_LEGAL_MOVES 593 /* upper bound on legal shogi moves                      */
+#define NSB_CACHE_MAX_MOVES 164 /* EvalCache row width (src/mcts/evalcache.h:26-38)      */
+
+typedef enum nsb_status {
+    NSB_OK = 0,
+    NSB_ERR_INVALID = -1,   /* bad argument / precondition (reference: assert, trt.cc:237-238) */
+    NSB_ERR_CUDA = -2,      /* CUDA runtime error (reference never checks these)               */
+    NSB_ERR_NO_DEVICE = -3, /* no usable sm_100a device: the product path has no CPU fallback  */
+    NSB_ERR_STATE = -4,     /* weights not loaded / ctx busy                                   */
+    NSB_ERR_NOMEM = -5
+} nsb_status;
+
+/* 16-byte packed feature plane == nshogi ml::FeatureBitboard.
+ * Layout pinned by reference src/cuda/extractbit.cu:20-37:
+ *   lo bits 0..62 = squares 0..62; hi bits 0..17 = squares 63..80; hi bit 24 = rotate;
+ *   hi bits 32..63 = IEEE-754 fp32 fill value. */
+typedef struct nsb_feature_bitboard {
+    uint64_t lo;
+    uint64_t hi;
+} nsb_feature_bitboard;
+
+/* ResNet shape.  The reference ships no model (external ONNX, src/context.h:93); only the
+ * tensor contract is pinned (src/infer/trt.cc:144-150,193-227).  DESIGN.md §5 defines the
+ * canonical random-init net: stem conv3x3(in->C) ; blocks x [conv3x3, conv3x3 + skip] ;
+ * policy conv1x1(C->27) ; value conv1x1(C->1) -> FC(81->hidden) -> FC(hidden->2) -> sigmoid. */
+typedef struct nsb_net_desc {
+    int32_t in_channels;  /* 86                                  */
+    int32_t channels;     /* trunk width C (128 or 256)          */
+    int32_t blocks;       /* residual blocks (10, 20, 40)        */
+    int32_t value_hidden; /* hidden units of the value MLP (256) */
+} nsb_net_desc;
+
+/* Compact position record (builder-defined; stage-1 input).
+ * board[sq]: 0 = empty, else 1 + piece_type + 14 * colour, piece_type in
+ *   0..13 = {P,L,N,S,G,K,B,R,+P,+L,+N,+S,+B,+R} (channel order of preset.h:20-33),
+ *   colour 0 = black, 1 = white.  hands[colour][k], k in {P,L,N,S,G,B,R}. */
+typedef struct nsb_position {
+    uint8_t board[81];
+    uint8_t side; /* 0 = black to move, 1 = white to move */
+    uint8_t hands[2][7];
+    uint16_t ply;
+    uint16_t max_ply;
+    float black_draw_value;
+    float white_draw_value;
+} nsb_position; /* 108 bytes */
+
+typedef struct nsb_ctx nsb_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+/* Replaces TensorRT::TensorRT(int GPUId, uint16_t BatchSizeMax, uint16_t NumChannels)
+ * (reference src/infer/trt.cc:52-80): selects the device, allocates device buffers for
+ * `batch_max` samples and `slots` independent in-flight batches (>=1), creates one
+ * non-blocking stream per slot. */
+int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_desc* net);
+
+/* Replaces TensorRT::~TensorRT (trt.cc:82-107). */
+void nsb_destroy(nsb_ctx* ctx);
+
+/* Replaces TensorRT::resetGPU (trt.cc:289-291): cudaSetDevice on the calling thread. */
+int nsb_bind_thread(nsb_ctx* ctx);
+
+/* Number of floats in the canonical fp32 weight blob for `net` (layout: DESIGN.md §5). */
+size_t nsb_weight_blob_floats(const nsb_net_desc* net);
+
+/* Deterministic random init of a canonical blob (He-normal convs, small biases); every
+ * stored value is exactly representable in bf16 so that the CPU oracle and the device see
+ * identical weights.  Host-only helper (no device work). */
+int nsb_weight_blob_random(const nsb_net_desc* net, uint64_t seed, float* blob);
+
+/* Replaces TensorRT::load(path, useCache) (trt.cc:109-232): takes the canonical fp32 blob,
+ * repacks it into the bf16 UMMA tile order the trunk kernel streams, uploads it. */
+int nsb_load_weights(nsb_ctx* ctx, const float* blob, size_t n_floats);
+
+/* ---- the Infer contract (host buffers) ------------------------------------------------- */
+
+/* Replaces Infer::computeNonBlocking (src/infer/infer.h:24-26; TRT impl trt.cc:234-272):
+ * enqueue H2D of n*C feature bitboards, feature expansion + ResNet forward, D2H of
+ * policy[n*2187] raw logits (plane-major), win[n], draw[n] (probabilities).  Returns
+ * immediately; results are valid after nsb_await(ctx, slot).  Precondition: n <= batch_max
+ * and the slot is idle. */
+int nsb_eval_async(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* features, size_t n,
+                   float* policy, float* win, float* draw);
+
+/* Fused-decode variant (replaces trt.cc:234-272 + FeedWorker::feedResult gather/softmax,
+ * src/mcts/feedworker.cc:100-127, or Frame::setEvaluation, src/selfplay/frame.cc:96-118):
+ * the caller supplies CSR legal-move policy indices (move_off[n+1], move_idx[move_off[n]],
+ * values from ml::getMoveIndex) and receives per-move outputs instead of dense logits.
+ *   mode NSB_DECODE_PROBS : softmax over the legal moves (T=1), 1-move rows = 1.0
+ *   mode NSB_DECODE_LOGITS: raw gathered logits (self-play caches logits, frame.cc:110-114)
+ * nan_flag[i] = 1 when any gathered logit / win / draw is NaN (math.h:23-39 semantics). */
+#define NSB_DECODE_PROBS 0
+#define NSB_DECODE_LOGITS 1
+int nsb_eval_decode_async(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* features, size_t n,
+                          const uint32_t* move_off, const uint16_t* move_idx, int mode,
+                          float* legal_out, float* win, float* draw, uint8_t* nan_flag);
+
+/* Same two calls fed from compact position records: stage 1 (position -> 86 feature
+ * bitboards; replaces FeatureStackComptime::constructAt at
+ * src/selfplay/evaluationworker.cc:87-92) also runs on the device. */
+int nsb_eval_positions_async(nsb_ctx* ctx, int slot, const nsb_position* positions, size_t n,
+                             float* policy, float* win, float* draw);
+
+/* Replaces Infer::await (trt.cc:281-283). */
+int nsb_await(nsb_ctx* ctx, int slot);
+/* Replaces Infer::isComputing (trt.cc:285-287): 1 busy, 0 idle, <0 error. */
+int nsb_is_computing(nsb_ctx* ctx, int slot);
+
+/* ---- device-resident entry points (inputs/outputs already in HBM) ----------------------- */
+
+/* Whole path on device pointers, enqueued on the slot's stream (bench `value` leg). */
+int nsb_eval_device(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* d_features, size_t n,
+                    float* d_policy, float* d_win, float* d_draw);
+
+/* Stage 2 alone == cuda::extractBits<ChannelsFirst> (src/cuda/extractbit.h:21-23):
+ * feature bitboards -> fp32 planes, NCHW (channels_first=1) or NHWC (0).  Bit-exact. */
+int nsb_extract_device(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* d_features, size_t n,
+                       int channels, int channels_first, float* d_planes);
+
+/* Stage 1 alone: position records -> feature bitboards (86 per position). */
+int nsb_pack_positions_device(nsb_ctx* ctx, int slot, const nsb_position* d_positions, size_t n,
+                              nsb_feature_bitboard* d_features);
+
+/* Decode alone from dense logits (feedworker.cc:100-127 / frame.cc:96-118). */
+int nsb_decode_device(nsb_ctx* ctx, int slot, const float* d_policy, const float* d_win,
+                      const float* d_draw, size_t n, const uint32_t* d_move_off,
+                      const uint16_t* d_move_idx, int mode, float* d_legal_out,
+                      uint8_t* d_nan_flag);
+
+/* Trunk implementation switch: "tcgen05" (product, default) or "simt" (plain CUDA-core
+ * cross-check used by tests; never the bench path). */
+int nsb_set_trunk_impl(nsb_ctx* ctx, const char* name);
+
+/* Stream of a slot as an opaque cudaStream_t (for event timing from the host side). */
+void* nsb_stream(nsb_ctx* ctx, int slot);
+
+/* Time the most recent trunk launch of the slot with CUDA events (ms); <0 on error. */
+float nsb_last_trunk_ms(nsb_ctx* ctx, int slot);
+
+/* Kernel launches issued by this ctx since creation (bench "gpu_launches"). */
+uint64_t nsb_launch_count(nsb_ctx* ctx);
+
+/* ---- misc ------------------------------------------------------------------------------ */
+
+/* Pinned host allocation helpers (reference pins with cudaHostRegister, evaluator.cc:95-106). */
+int nsb_host_alloc(void** out, size_t bytes);
+int nsb_host_free(void* p);
+int nsb_device_alloc(void** out, size_t bytes);
+int nsb_device_free(void* p);
+int nsb_memcpy_h2d(void* dst, const void* src, size_t bytes);
+int nsb_memcpy_d2h(void* dst, const void* src, size_t bytes);
+int nsb_device_sync(void);
+
+const char* nsb_last_error(void);
+const char* nsb_version(void);
+int nsb_device_count(void);
+
+/* tcgen05 self-test: runs a small UMMA GEMM with the shifted no-swizzle descriptors the
+ * trunk uses and compares on the host; returns 0 when the max error is below tol. */
+int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSB_H */

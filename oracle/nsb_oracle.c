@@ -1,0 +1,447 @@
+/*
+ * nsb_oracle.c — CPU oracle for the leaf-evaluation hot path.  TEST INFRASTRUCTURE ONLY:
+ * loaded by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs; never by the
+ * product library.  See nsb_oracle.h for what is pinned against the reference and what is not.
+ */
+#define _GNU_SOURCE
+#include "nsb_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------------------------------ */
+/* expand: reference src/cuda/extractbit.cu:15-39 (NCHW) and :41-68 (NHWC)                     */
+/* ------------------------------------------------------------------------------------------ */
+
+/* One (plane, output position t) element, exactly the kernel's integer arithmetic:
+ *   Rotate = (hi >> 24) & 1; Value = hi >> 32            (extractbit.cu:20-21)
+ *   TargetSquare = t*(1-2*Rotate) + 80*Rotate            (:26)
+ *   word/shift pick at square 63                         (:30-34)
+ *   out = ((word & mask) >> shift) * Value  as int32     (:36-37) */
+static inline uint32_t expand_one(uint64_t lo, uint64_t hi, int t) {
+    const int rotate = (int)((hi >> 24) & 1u);
+    const uint32_t value = (uint32_t)(hi >> 32);
+    const int sq = t * (1 - 2 * rotate) + 80 * rotate;
+    const int use_hi = sq >= 63;
+    const int sh = sq - 63 * use_hi;
+    const uint64_t word = use_hi ? hi : lo;
+    return (uint32_t)((word >> sh) & 1u) * value;
+}
+
+void nsb_oracle_expand(const nsb_feature_bitboard* fb, size_t n, int channels, int channels_first,
+                       float* planes) {
+    uint32_t* out = (uint32_t*)planes; /* fp32 bit patterns are stored as integers (:80-85) */
+    for (size_t b = 0; b < n; ++b) {
+        for (int c = 0; c < channels; ++c) {
+            const uint64_t lo = fb[b * channels + c].lo, hi = fb[b * channels + c].hi;
+            for (int t = 0; t < 81; ++t) {
+                const uint32_t v = expand_one(lo, hi, t);
+                if (channels_first)
+                    out[(b * channels + c) * 81 + t] = v; /* Dest[Index*81 + BitIndex] (:37) */
+                else
+                    out[(b * 81 + t) * channels + c] = v; /* (:65-66) */
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* pack: position -> 86 feature bitboards (channel order: reference src/evaluate/preset.h:20-66;
+ * plane semantics: SURVEY.md App. A.2, builder-defined — libnshogi is not available)          */
+/* ------------------------------------------------------------------------------------------ */
+
+static const int kStandMax[7] = {6, 4, 4, 4, 4, 2, 2}; /* P L N S G B R: 26 planes per side */
+
+static inline uint32_t f32_bits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+
+static inline void fb_set(nsb_feature_bitboard* f, uint64_t lo, uint64_t hi18, int rotate,
+                          float value) {
+    f->lo = lo;
+    f->hi = hi18 | ((uint64_t)(rotate & 1) << 24) | ((uint64_t)f32_bits(value) << 32);
+}
+
+#define ALL_LO ((1ULL << 63) - 1ULL)
+#define ALL_HI 0x3FFFFULL
+
+void nsb_oracle_pack(const nsb_position* pos, size_t n, nsb_feature_bitboard* fb) {
+    for (size_t b = 0; b < n; ++b) {
+        const nsb_position* p = &pos[b];
+        nsb_feature_bitboard* f = &fb[b * NSB_FEATURE_CHANNELS];
+        const int me = p->side & 1, op = me ^ 1, rot = me; /* white to move => rotate */
+        uint64_t lo[2][14], hi[2][14];
+        memset(lo, 0, sizeof lo);
+        memset(hi, 0, sizeof hi);
+        for (int s = 0; s < 81; ++s) {
+            const int code = p->board[s];
+            if (!code) continue;
+            const int colour = (code - 1) / 14, pt = (code - 1) % 14;
+            if (s < 63)
+                lo[colour][pt] |= 1ULL << s;
+            else
+                hi[colour][pt] |= 1ULL << (s - 63);
+        }
+        int c = 0;
+        for (int pt = 0; pt < 14; ++pt) fb_set(&f[c++], lo[me][pt], hi[me][pt], rot, 1.0f);
+        for (int pt = 0; pt < 14; ++pt) fb_set(&f[c++], lo[op][pt], hi[op][pt], rot, 1.0f);
+        for (int side = 0; side < 2; ++side) {
+            const int col = side == 0 ? me : op;
+            for (int k = 0; k < 7; ++k)
+                for (int j = 1; j <= kStandMax[k]; ++j) {
+                    const int on = p->hands[col][k] >= j;
+                    fb_set(&f[c++], on ? ALL_LO : 0, on ? ALL_HI : 0, rot, 1.0f);
+                }
+        }
+        fb_set(&f[c++], me == 0 ? ALL_LO : 0, me == 0 ? ALL_HI : 0, rot, 1.0f); /* Black */
+        fb_set(&f[c++], me == 1 ? ALL_LO : 0, me == 1 ? ALL_HI : 0, rot, 1.0f); /* White */
+        const float maxply = (float)(p->max_ply ? p->max_ply : 1);
+        fb_set(&f[c++], ALL_LO, ALL_HI, rot, (float)p->ply / maxply); /* Progress      */
+        fb_set(&f[c++], ALL_LO, ALL_HI, rot, 1.0f / maxply);          /* ProgressUnit  */
+        const float bd = p->black_draw_value, wd = p->white_draw_value;
+        fb_set(&f[c++], ALL_LO, ALL_HI, rot, me == 0 ? bd : wd); /* MyDrawValue */
+        fb_set(&f[c++], ALL_LO, ALL_HI, rot, me == 0 ? wd : bd); /* OpDrawValue */
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* decode: reference src/mcts/feedworker.cc:100-136, src/selfplay/frame.cc:96-118               */
+/* ------------------------------------------------------------------------------------------ */
+
+/* reference src/math/math.h:23-39: bit-pattern NaN test (robust under -ffast-math). */
+static inline int isnan_bits(float x) {
+    const uint32_t u = f32_bits(x);
+    return (u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu) != 0;
+}
+
+void nsb_oracle_decode(const float* policy, const float* win, const float* draw, size_t n,
+                       const uint32_t* move_off, const uint16_t* move_idx, int mode,
+                       float* legal_out, uint8_t* nan_flag) {
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t b = move_off[i], e = move_off[i + 1], m = e - b;
+        const float* row = policy + i * NSB_POLICY_SIZE;
+        float* out = legal_out + b;
+        int bad = isnan_bits(win[i]) || isnan_bits(draw[i]);
+        for (uint32_t j = 0; j < m; ++j) { /* gather: feedworker.cc:119-125 / frame.cc:101-106 */
+            out[j] = row[move_idx[b + j]];
+            bad |= isnan_bits(out[j]);
+        }
+        if (nan_flag) nan_flag[i] = (uint8_t)bad;
+        if (mode == NSB_DECODE_LOGITS || m == 0) continue; /* frame.cc:110-114 caches logits */
+        if (m == 1) { /* feedworker.cc:101-103 */
+            out[0] = 1.0f;
+            continue;
+        }
+        if (bad) /* NaN fallback, feedworker.cc:111-118: all-ones before softmax => uniform */
+            for (uint32_t j = 0; j < m; ++j) out[j] = 1.0f;
+        float mx = out[0]; /* softmax_(x, n, T = 1): feedworker.cc:127, frame.cc:117 */
+        for (uint32_t j = 1; j < m; ++j) mx = out[j] > mx ? out[j] : mx;
+        float sum = 0.0f;
+        for (uint32_t j = 0; j < m; ++j) {
+            out[j] = expf(out[j] - mx);
+            sum += out[j];
+        }
+        const float inv = 1.0f / sum;
+        for (uint32_t j = 0; j < m; ++j) out[j] *= inv;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* forward: fp32 definition of the canonical net                                */
+/* ------------------------------------------------------------------------------------------ */
+
+float nsb_oracle_bf16_round(float x) {
+    uint32_t u = f32_bits(x);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x; /* inf / nan unchanged */
+    u += 0x7FFFu + ((u >> 16) & 1u);                /* round to nearest even */
+    u &= 0xFFFF0000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+#define PW 11            /* padded board width  */
+#define PSZ (PW * PW + 8) /* padded plane floats (tail slack for the 99-wide window) */
+
+/* 3x3 conv, pad 1, on [cin][9][9] -> [cout][9][9]; h = t / 9, w = t % 9 (NCHW of
+ * reference src/infer/trt.cc:144-150).  in_pad holds zero-bordered 11x11 planes. */
+static void conv3x3(const float* in_pad, int cin, const float* w, const float* bias, int cout,
+                    float* out /* [cout][81] */) {
+    for (int co = 0; co < cout; ++co) {
+        float acc[9 * PW];
+        for (int o = 0; o < 9 * PW; ++o) acc[o] = bias[co];
+        const float* wc = w + (size_t)co * cin * 9;
+        for (int ci = 0; ci < cin; ++ci) {
+            const float* p = in_pad + (size_t)ci * PSZ;
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float wv = wc[ci * 9 + kh * 3 + kw];
+                    const float* q = p + kh * PW + kw;
+                    for (int o = 0; o < 9 * PW; ++o) acc[o] += wv * q[o];
+                }
+        }
+        for (int h = 0; h < 9; ++h)
+            for (int x = 0; x < 9; ++x) out[co * 81 + h * 9 + x] = acc[h * PW + x];
+    }
+}
+
+static void pad_planes(const float* in /* [c][81] */, int c, float* in_pad) {
+    memset(in_pad, 0, sizeof(float) * (size_t)c * PSZ);
+    for (int ch = 0; ch < c; ++ch)
+        for (int h = 0; h < 9; ++h)
+            for (int x = 0; x < 9; ++x)
+                in_pad[(size_t)ch * PSZ + (h + 1) * PW + (x + 1)] = in[ch * 81 + h * 9 + x];
+}
+
+typedef struct {
+    const nsb_net_desc* net;
+    const float *blob, *planes;
+    size_t n;
+    int emulate_bf16, tid, nthreads;
+    float *policy, *win, *draw;
+} fwd_job;
+
+static void* forward_worker(void* arg) {
+    const fwd_job* J = (const fwd_job*)arg;
+    const nsb_net_desc* net = J->net;
+    const float *blob = J->blob, *planes = J->planes;
+    const int emulate_bf16 = J->emulate_bf16;
+    float *policy = J->policy, *win = J->win, *draw = J->draw;
+    const int IN = net->in_channels, C = net->channels, NB = net->blocks, H = net->value_hidden;
+    const int maxc = C > IN ? C : IN;
+    for (size_t b = (size_t)J->tid; b < J->n; b += (size_t)J->nthreads) {
+        float* x = (float*)malloc(sizeof(float) * (size_t)maxc * 81);
+        float* t = (float*)malloc(sizeof(float) * (size_t)maxc * 81);
+        float* y = (float*)malloc(sizeof(float) * (size_t)maxc * 81);
+        float* pad = (float*)malloc(sizeof(float) * (size_t)maxc * PSZ);
+        const float* w = blob;
+        for (int i = 0; i < IN * 81; ++i) {
+            const float v = planes[(size_t)b * IN * 81 + i];
+            x[i] = emulate_bf16 ? nsb_oracle_bf16_round(v) : v;
+        }
+        /* stem */
+        pad_planes(x, IN, pad);
+        conv3x3(pad, IN, w, w + (size_t)C * IN * 9, C, t);
+        w += (size_t)C * IN * 9 + C;
+        for (int i = 0; i < C * 81; ++i) {
+            float v = t[i] > 0.f ? t[i] : 0.f;
+            x[i] = emulate_bf16 ? nsb_oracle_bf16_round(v) : v;
+        }
+        /* residual blocks */
+        for (int blk = 0; blk < NB; ++blk) {
+            pad_planes(x, C, pad);
+            conv3x3(pad, C, w, w + (size_t)C * C * 9, C, t);
+            w += (size_t)C * C * 9 + C;
+            for (int i = 0; i < C * 81; ++i) {
+                float v = t[i] > 0.f ? t[i] : 0.f;
+                t[i] = emulate_bf16 ? nsb_oracle_bf16_round(v) : v;
+            }
+            pad_planes(t, C, pad);
+            conv3x3(pad, C, w, w + (size_t)C * C * 9, C, y);
+            w += (size_t)C * C * 9 + C;
+            for (int i = 0; i < C * 81; ++i) {
+                float v = y[i] + x[i];
+                v = v > 0.f ? v : 0.f;
+                x[i] = emulate_bf16 ? nsb_oracle_bf16_round(v) : v;
+            }
+        }
+        /* policy head: conv1x1 C -> 27, plane-major logits (ChannelsFirst, globalconfig.h:20) */
+        const float* pw = w;
+        const float* pb = w + (size_t)NSB_POLICY_PLANES * C;
+        w += (size_t)NSB_POLICY_PLANES * C + NSB_POLICY_PLANES;
+        for (int p = 0; p < NSB_POLICY_PLANES; ++p)
+            for (int s = 0; s < 81; ++s) {
+                float acc = pb[p];
+                for (int c = 0; c < C; ++c) acc += pw[p * C + c] * x[c * 81 + s];
+                policy[(size_t)b * NSB_POLICY_SIZE + p * 81 + s] = acc;
+            }
+        /* value head: conv1x1 C -> 1, ReLU, FC 81 -> H, ReLU, FC H -> 2, sigmoid */
+        const float* vw = w;
+        const float vb = w[C];
+        w += C + 1;
+        float v81[81];
+        for (int s = 0; s < 81; ++s) {
+            float acc = vb;
+            for (int c = 0; c < C; ++c) acc += vw[c] * x[c * 81 + s];
+            v81[s] = acc > 0.f ? acc : 0.f;
+        }
+        const float* f1w = w;
+        const float* f1b = w + (size_t)H * 81;
+        w += (size_t)H * 81 + H;
+        const float* f2w = w;
+        const float* f2b = w + 2 * (size_t)H;
+        float o0 = f2b[0], o1 = f2b[1];
+        for (int h = 0; h < H; ++h) {
+            float acc = f1b[h];
+            for (int s = 0; s < 81; ++s) acc += f1w[h * 81 + s] * v81[s];
+            acc = acc > 0.f ? acc : 0.f;
+            o0 += f2w[h] * acc;
+            o1 += f2w[H + h] * acc;
+        }
+        win[b] = 1.0f / (1.0f + expf(-o0));
+        draw[b] = 1.0f / (1.0f + expf(-o1));
+        free(x);
+        free(t);
+        free(y);
+        free(pad);
+    }
+    return NULL;
+}
+
+void nsb_oracle_forward(const nsb_net_desc* net, const float* blob, const float* planes, size_t n,
+                        int emulate_bf16, float* policy, float* win, float* draw) {
+    long nt = sysconf(_SC_NPROCESSORS_ONLN);
+    if (nt < 1) nt = 1;
+    if (nt > 64) nt = 64;
+    if ((size_t)nt > n) nt = (long)(n ? n : 1);
+    pthread_t th[64];
+    fwd_job jobs[64];
+    for (long t = 0; t < nt; ++t) {
+        jobs[t] = (fwd_job){net, blob, planes, n, emulate_bf16, (int)t, (int)nt, policy, win, draw};
+        pthread_create(&th[t], NULL, forward_worker, &jobs[t]);
+    }
+    for (long t = 0; t < nt; ++t) pthread_join(th[t], NULL);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Random executor: reference src/infer/random.cc:28-42                                        */
+/*   std::mt19937_64 Rng(Seed); static std::uniform_real_distribution<float> Distribution(0,1)  */
+/*   (libstdc++ 13 generate_canonical<float,24>: one 64-bit draw, float(u) / 2^64, clamped to   */
+/*   nextafter(1,0) when it rounds to 1).                                                        */
+/* ------------------------------------------------------------------------------------------ */
+
+struct nsb_oracle_rng {
+    uint64_t mt[312];
+    int idx;
+};
+
+nsb_oracle_rng* nsb_oracle_rng_create(uint64_t seed) {
+    nsb_oracle_rng* r = (nsb_oracle_rng*)malloc(sizeof *r);
+    r->mt[0] = seed;
+    for (int i = 1; i < 312; ++i)
+        r->mt[i] = 6364136223846793005ULL * (r->mt[i - 1] ^ (r->mt[i - 1] >> 62)) + (uint64_t)i;
+    r->idx = 312;
+    return r;
+}
+
+void nsb_oracle_rng_destroy(nsb_oracle_rng* r) { free(r); }
+
+static inline uint64_t mt_next(nsb_oracle_rng* r) {
+    if (r->idx >= 312) {
+        const uint64_t UM = 0xFFFFFFFF80000000ULL, LM = 0x7FFFFFFFULL, A = 0xB5026F5AA96619E9ULL;
+        for (int i = 0; i < 312; ++i) {
+            const uint64_t x = (r->mt[i] & UM) | (r->mt[(i + 1) % 312] & LM);
+            r->mt[i] = r->mt[(i + 156) % 312] ^ (x >> 1) ^ ((x & 1ULL) ? A : 0ULL);
+        }
+        r->idx = 0;
+    }
+    uint64_t y = r->mt[r->idx++];
+    y ^= (y >> 29) & 0x5555555555555555ULL;
+    y ^= (y << 17) & 0x71D67FFFEDA60000ULL;
+    y ^= (y << 37) & 0xFFF7EEE000000000ULL;
+    y ^= y >> 43;
+    return y;
+}
+
+static inline float canonical_f32(nsb_oracle_rng* r) {
+    const float sum = (float)mt_next(r);
+    float ret = sum / 18446744073709551616.0f;
+    if (ret >= 1.0f) ret = nextafterf(1.0f, 0.0f);
+    return ret;
+}
+
+void nsb_oracle_random_fill(nsb_oracle_rng* r, size_t n, float* policy, float* win, float* draw) {
+    for (size_t i = 0; i < n; ++i) { /* random.cc:33-41 */
+        for (int j = 0; j < NSB_POLICY_SIZE; ++j) policy[i * NSB_POLICY_SIZE + j] = canonical_f32(r);
+        win[i] = canonical_f32(r);
+        draw[i] = canonical_f32(r);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* CPU path of config 1: pack [+ expand] + Random fill + decode, N threads.    */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct {
+    const nsb_position* pos;
+    size_t n_pos;
+    const uint32_t* move_off;
+    const uint16_t* move_idx;
+    int batch, batches, with_expand, tid;
+    nsb_fill_fn fill;
+    nsb_fill_make_fn mk;
+    double checksum;
+} cpu_job;
+
+static void port_fill(void* h, size_t n, float* p, float* w, float* d) {
+    nsb_oracle_random_fill((nsb_oracle_rng*)h, n, p, w, d);
+}
+static void* port_make(uint64_t seed) { return nsb_oracle_rng_create(seed); }
+
+static void* cpu_worker(void* arg) {
+    cpu_job* j = (cpu_job*)arg;
+    const int B = j->batch;
+    nsb_feature_bitboard* fb = (nsb_feature_bitboard*)malloc(sizeof(*fb) * B * NSB_FEATURE_CHANNELS);
+    float* planes = j->with_expand ? (float*)malloc(sizeof(float) * B * NSB_FEATURE_CHANNELS * 81) : NULL;
+    float* policy = (float*)malloc(sizeof(float) * B * NSB_POLICY_SIZE);
+    float* win = (float*)malloc(sizeof(float) * B);
+    float* draw = (float*)malloc(sizeof(float) * B);
+    float* legal = (float*)malloc(sizeof(float) * B * NSB_MAX_LEGAL_MOVES);
+    uint32_t* off = (uint32_t*)malloc(sizeof(uint32_t) * (B + 1));
+    uint8_t* flag = (uint8_t*)malloc(B);
+    void* h = j->mk((uint64_t)j->tid); /* reference: Random(Seed) per executor */
+    double cs = 0.0;
+    size_t cursor = ((size_t)j->tid * 7919u) % j->n_pos;
+    for (int it = 0; it < j->batches; ++it) {
+        if (cursor + B > j->n_pos) cursor = 0;
+        const size_t s = cursor;
+        cursor += B;
+        nsb_oracle_pack(j->pos + s, B, fb);
+        if (planes) nsb_oracle_expand(fb, B, NSB_FEATURE_CHANNELS, 1, planes);
+        j->fill(h, B, policy, win, draw);
+        const uint32_t base = j->move_off[s];
+        for (int i = 0; i <= B; ++i) off[i] = j->move_off[s + i] - base;
+        nsb_oracle_decode(policy, win, draw, B, off, j->move_idx + base, NSB_DECODE_PROBS, legal, flag);
+        cs += legal[0] + win[B - 1] + (planes ? planes[80] : 0.f);
+    }
+    j->checksum = cs;
+    free(fb);
+    free(planes);
+    free(policy);
+    free(win);
+    free(draw);
+    free(legal);
+    free(off);
+    free(flag);
+    return NULL;
+}
+
+double nsb_oracle_cpu_path(const nsb_position* pos, size_t n_pos, const uint32_t* move_off,
+                           const uint16_t* move_idx, int batch, int threads,
+                           int batches_per_thread, int with_expand, nsb_fill_fn fill,
+                           nsb_fill_make_fn mk, double* seconds_out) {
+    if (threads < 1) threads = 1;
+    if ((size_t)batch > n_pos) return -1.0;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
+    cpu_job* jobs = (cpu_job*)calloc(threads, sizeof(cpu_job));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; ++t) {
+        jobs[t] = (cpu_job){pos, n_pos, move_off, move_idx, batch, batches_per_thread, with_expand,
+                            t, fill ? fill : port_fill, (fill && mk) ? mk : port_make, 0.0};
+        pthread_create(&th[t], NULL, cpu_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double sec = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    if (seconds_out) *seconds_out = sec;
+    free(th);
+    free(jobs);
+    return (double)threads * batches_per_thread * batch / sec;
+}
