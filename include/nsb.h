@@ -26,6 +26,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built -fvisibility=hidden */
+#endif
 
 #define NSB_NUM_SQUARES 81      /* nshogi core::NumSquares                               */
 #define NSB_POLICY_PLANES 27    /* 27 move-type planes (src/mcts/evaluationworker.cc:166) */
@@ -134,6 +137,13 @@ int nsb_eval_decode_async(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* fe
 int nsb_eval_positions_async(nsb_ctx* ctx, int slot, const nsb_position* positions, size_t n,
                              float* policy, float* win, float* draw);
 
+/* Fully fused variant: stage 1 on the device, forward, fused legal-move decode.  This is the
+ * self-play evaluation step (src/selfplay/evaluationworker.cc:87-108) in one call: 108 B up and
+ * ~4 B per legal move down per position instead of 1,376 B up and 8,756 B down. */
+int nsb_eval_positions_decode_async(nsb_ctx* ctx, int slot, const nsb_position* positions, size_t n,
+                                    const uint32_t* move_off, const uint16_t* move_idx, int mode,
+                                    float* legal_out, float* win, float* draw, uint8_t* nan_flag);
+
 /* Replaces Infer::await (trt.cc:281-283). */
 int nsb_await(nsb_ctx* ctx, int slot);
 /* Replaces Infer::isComputing (trt.cc:285-287): 1 busy, 0 idle, <0 error. */
@@ -144,6 +154,12 @@ int nsb_is_computing(nsb_ctx* ctx, int slot);
 /* Whole path on device pointers, enqueued on the slot's stream (bench `value` leg). */
 int nsb_eval_device(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* d_features, size_t n,
                     float* d_policy, float* d_win, float* d_draw);
+
+/* Whole path + fused decode on device pointers; d_policy may be NULL (logits stay on chip). */
+int nsb_eval_decode_device(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* d_features, size_t n,
+                           const uint32_t* d_move_off, const uint16_t* d_move_idx, int mode,
+                           float* d_policy, float* d_legal_out, float* d_win, float* d_draw,
+                           uint8_t* d_nan_flag);
 
 /* Stage 2 alone == cuda::extractBits<ChannelsFirst> (src/cuda/extractbit.h:21-23):
  * feature bitboards -> fp32 planes, NCHW (channels_first=1) or NHWC (0).  Bit-exact. */
@@ -160,15 +176,15 @@ int nsb_decode_device(nsb_ctx* ctx, int slot, const float* d_policy, const float
                       const uint16_t* d_move_idx, int mode, float* d_legal_out,
                       uint8_t* d_nan_flag);
 
-/* Trunk implementation switch: "tcgen05" (product, default) or "simt" (plain CUDA-core
- * cross-check used by tests; never the bench path). */
-int nsb_set_trunk_impl(nsb_ctx* ctx, const char* name);
-
 /* Stream of a slot as an opaque cudaStream_t (for event timing from the host side). */
 void* nsb_stream(nsb_ctx* ctx, int slot);
 
-/* Time the most recent trunk launch of the slot with CUDA events (ms); <0 on error. */
-float nsb_last_trunk_ms(nsb_ctx* ctx, int slot);
+/* Device time of the trunk kernel, measured with CUDA events recorded on the slot's stream
+ * around every trunk launch and harvested in nsb_await(): running sum (ms) and launch count
+ * since creation or the last nsb_trunk_time_reset().  Enabled by nsb_set_timing(ctx, 1). */
+int nsb_set_timing(nsb_ctx* ctx, int enabled);
+int nsb_trunk_time(nsb_ctx* ctx, double* sum_ms, uint64_t* launches);
+int nsb_trunk_time_reset(nsb_ctx* ctx);
 
 /* Kernel launches issued by this ctx since creation (bench "gpu_launches"). */
 uint64_t nsb_launch_count(nsb_ctx* ctx);
@@ -182,16 +198,22 @@ int nsb_device_alloc(void** out, size_t bytes);
 int nsb_device_free(void* p);
 int nsb_memcpy_h2d(void* dst, const void* src, size_t bytes);
 int nsb_memcpy_d2h(void* dst, const void* src, size_t bytes);
+int nsb_memset_device(void* dst, int value, size_t bytes);
 int nsb_device_sync(void);
 
 const char* nsb_last_error(void);
 const char* nsb_version(void);
 int nsb_device_count(void);
 
-/* tcgen05 self-test: runs a small UMMA GEMM with the shifted no-swizzle descriptors the
- * trunk uses and compares on the host; returns 0 when the max error is below tol. */
-int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err);
+/* tcgen05 self-test: one CTA runs D[128 x n_cols] = A * B^T with the K-major SWIZZLE_NONE
+ * descriptors the trunk uses, B's start address moved by shift_rows 16-byte rows, and the host
+ * compares against an fp32 loop.  variant 0 = the convention the trunk uses; variant 1 = LBO/SBO
+ * swapped (diagnostic).  Returns 0 and the max abs error (exact inputs: expect 0). */
+int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, int variant, float* max_err);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

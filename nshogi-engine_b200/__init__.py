@@ -1,0 +1,8 @@
+"""nshogi-engine_b200 — B200-native leaf-evaluation executor for nyashiki/nshogi-engine.
+
+The product is ``libnsb.so`` (csrc/, C ABI in include/nsb.h) plus the C++ host mirror of the
+reference's ``infer::Infer`` / ``evaluate::Evaluator`` (host/).  The Python modules are plumbing
+for tests and benchmarks: ``binding`` (ctypes), ``infer`` (Python twin of the Infer interface),
+``synth`` (seeded synthetic inputs).  There is no CPU fallback anywhere in this package.
+"""
+from . import binding, infer, synth  # noqa: F401

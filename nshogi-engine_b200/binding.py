@@ -1,0 +1,298 @@
+"""ctypes binding of libnsb.so (include/nsb.h) — plumbing only, no compute and NO CPU fallback.
+
+The product is the C-ABI CUDA library; this module lets the tests, ``bench.py`` and
+``__graft_entry__.smoke()`` drive it with numpy host buffers and raw device pointers.  If the
+library is missing or no sm_100a device is present every entry point raises ``NsbError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnsb.so")
+
+NUM_SQUARES = 81
+POLICY_SIZE = 2187
+FEATURE_CHANNELS = 86
+MAX_LEGAL_MOVES = 593
+CACHE_MAX_MOVES = 164
+DECODE_PROBS = 0
+DECODE_LOGITS = 1
+
+# 16-byte packed plane == nshogi ml::FeatureBitboard (reference src/cuda/extractbit.cu:20-37)
+FEATURE_BITBOARD = np.dtype([("lo", "<u8"), ("hi", "<u8")])
+# nsb_position (include/nsb.h), 108 bytes
+POSITION = np.dtype(
+    {
+        "names": ["board", "side", "hands", "ply", "max_ply", "black_draw_value", "white_draw_value"],
+        "formats": [("u1", (81,)), "u1", ("u1", (2, 7)), "<u2", "<u2", "<f4", "<f4"],
+        "offsets": [0, 81, 82, 96, 98, 100, 104],
+        "itemsize": 108,
+    }
+)
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("channels", C.c_int32), ("blocks", C.c_int32),
+                ("value_hidden", C.c_int32)]
+
+
+class NsbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/nsb.h declares
+_P = C.c_void_p
+SIGNATURES = {
+    "nsb_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.POINTER(NetDesc)]),
+    "nsb_destroy": (None, [_P]),
+    "nsb_bind_thread": (C.c_int, [_P]),
+    "nsb_weight_blob_floats": (C.c_size_t, [C.POINTER(NetDesc)]),
+    "nsb_weight_blob_random": (C.c_int, [C.POINTER(NetDesc), C.c_uint64, _P]),
+    "nsb_load_weights": (C.c_int, [_P, _P, C.c_size_t]),
+    "nsb_eval_async": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P]),
+    "nsb_eval_decode_async": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "nsb_eval_positions_async": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P]),
+    "nsb_eval_positions_decode_async": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "nsb_await": (C.c_int, [_P, C.c_int]),
+    "nsb_is_computing": (C.c_int, [_P, C.c_int]),
+    "nsb_eval_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P]),
+    "nsb_eval_decode_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "nsb_extract_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_int, C.c_int, _P]),
+    "nsb_pack_positions_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P]),
+    "nsb_decode_device": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P, _P, C.c_int, _P, _P]),
+    "nsb_stream": (_P, [_P, C.c_int]),
+    "nsb_set_timing": (C.c_int, [_P, C.c_int]),
+    "nsb_trunk_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "nsb_trunk_time_reset": (C.c_int, [_P]),
+    "nsb_launch_count": (C.c_uint64, [_P]),
+    "nsb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "nsb_host_free": (C.c_int, [_P]),
+    "nsb_device_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "nsb_device_free": (C.c_int, [_P]),
+    "nsb_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t]),
+    "nsb_memcpy_d2h": (C.c_int, [_P, _P, C.c_size_t]),
+    "nsb_memset_device": (C.c_int, [_P, C.c_int, C.c_size_t]),
+    "nsb_device_sync": (C.c_int, []),
+    "nsb_last_error": (C.c_char_p, []),
+    "nsb_version": (C.c_char_p, []),
+    "nsb_device_count": (C.c_int, []),
+    "nsb_umma_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libnsb.so (built in-tree by ``__graft_entry__.build()`` / csrc/Makefile)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NsbError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise NsbError(f"{what} failed ({rc}): {lib().nsb_last_error().decode()}")
+
+
+def _ptr(a) -> Optional[int]:
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "host buffers must be C-contiguous"
+        return a.ctypes.data
+    return int(a)
+
+
+def device_count() -> int:
+    return lib().nsb_device_count()
+
+
+def net_desc(channels: int, blocks: int, value_hidden: int = 256, in_channels: int = FEATURE_CHANNELS) -> NetDesc:
+    return NetDesc(in_channels, channels, blocks, value_hidden)
+
+
+def random_blob(desc: NetDesc, seed: int) -> np.ndarray:
+    n = lib().nsb_weight_blob_floats(C.byref(desc))
+    blob = np.empty(n, dtype=np.float32)
+    _check(lib().nsb_weight_blob_random(C.byref(desc), seed, blob.ctypes.data), "nsb_weight_blob_random")
+    return blob
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'ed memory (reference pins with cudaHostRegister,
+    src/evaluate/evaluator.cc:95-106)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape) if isinstance(shape, (tuple, list)) else (int(shape),)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = _P()
+        _check(lib().nsb_host_alloc(C.byref(p), nbytes), "nsb_host_alloc")
+        self._p = p
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            lib().nsb_host_free(self._p)
+            self._p = None
+
+
+class DeviceBuffer:
+    def __init__(self, nbytes: int):
+        p = _P()
+        _check(lib().nsb_device_alloc(C.byref(p), nbytes), "nsb_device_alloc")
+        self.ptr = p.value
+        self.nbytes = nbytes
+
+    @classmethod
+    def from_host(cls, a: np.ndarray) -> "DeviceBuffer":
+        a = np.ascontiguousarray(a)
+        d = cls(max(a.nbytes, 1))
+        if a.nbytes:
+            _check(lib().nsb_memcpy_h2d(d.ptr, a.ctypes.data, a.nbytes), "nsb_memcpy_h2d")
+        return d
+
+    def to_host(self, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        if out.nbytes:
+            _check(lib().nsb_memcpy_d2h(out.ctypes.data, self.ptr, out.nbytes), "nsb_memcpy_d2h")
+        return out
+
+    def fill(self, byte: int):
+        _check(lib().nsb_memset_device(self.ptr, byte, self.nbytes), "nsb_memset_device")
+
+    def free(self):
+        if self.ptr:
+            lib().nsb_device_free(self.ptr)
+            self.ptr = None
+
+
+def device_sync():
+    _check(lib().nsb_device_sync(), "nsb_device_sync")
+
+
+def umma_selftest(n_cols: int, k_elems: int, shift_rows: int, variant: int = 0, gpu: int = 0) -> float:
+    err = C.c_float(-1.0)
+    _check(lib().nsb_umma_selftest(gpu, n_cols, k_elems, shift_rows, variant, C.byref(err)), "nsb_umma_selftest")
+    return float(err.value)
+
+
+class Context:
+    """One nsb_ctx: the C-ABI twin of one reference ``infer::Infer`` instance
+    (reference src/infer/infer.h:19-32), with ``slots`` independent in-flight batches."""
+
+    def __init__(self, desc: NetDesc, batch_max: int, slots: int = 1, gpu: int = 0,
+                 blob: Optional[np.ndarray] = None, seed: Optional[int] = None):
+        self.desc = desc
+        self.batch_max = batch_max
+        self.slots = slots
+        h = _P()
+        _check(lib().nsb_create(C.byref(h), gpu, batch_max, slots, C.byref(desc)), "nsb_create")
+        self._h = h
+        if blob is None and seed is not None:
+            blob = random_blob(desc, seed)
+        if blob is not None:
+            self.load_weights(blob)
+
+    def close(self):
+        if self._h is not None:
+            lib().nsb_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def load_weights(self, blob: np.ndarray):
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        _check(lib().nsb_load_weights(self._h, blob.ctypes.data, blob.size), "nsb_load_weights")
+
+    def bind_thread(self):
+        _check(lib().nsb_bind_thread(self._h), "nsb_bind_thread")
+
+    # -- host-buffer calls (the Infer contract) ------------------------------------------------
+    def eval_async(self, slot, features, n, policy, win, draw):
+        _check(lib().nsb_eval_async(self._h, slot, _ptr(features), n, _ptr(policy), _ptr(win), _ptr(draw)),
+               "nsb_eval_async")
+
+    def eval_decode_async(self, slot, features, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag=None):
+        _check(lib().nsb_eval_decode_async(self._h, slot, _ptr(features), n, _ptr(move_off), _ptr(move_idx), mode,
+                                           _ptr(legal_out), _ptr(win), _ptr(draw), _ptr(nan_flag)),
+               "nsb_eval_decode_async")
+
+    def eval_positions_async(self, slot, positions, n, policy, win, draw):
+        _check(lib().nsb_eval_positions_async(self._h, slot, _ptr(positions), n, _ptr(policy), _ptr(win),
+                                              _ptr(draw)), "nsb_eval_positions_async")
+
+    def eval_positions_decode_async(self, slot, positions, n, move_off, move_idx, mode, legal_out, win, draw,
+                                    nan_flag=None):
+        _check(lib().nsb_eval_positions_decode_async(self._h, slot, _ptr(positions), n, _ptr(move_off),
+                                                     _ptr(move_idx), mode, _ptr(legal_out), _ptr(win), _ptr(draw),
+                                                     _ptr(nan_flag)), "nsb_eval_positions_decode_async")
+
+    def await_(self, slot=0):
+        _check(lib().nsb_await(self._h, slot), "nsb_await")
+
+    def is_computing(self, slot=0) -> bool:
+        rc = lib().nsb_is_computing(self._h, slot)
+        if rc < 0:
+            _check(rc, "nsb_is_computing")
+        return rc == 1
+
+    # -- device-pointer calls -------------------------------------------------------------------
+    def eval_device(self, slot, d_features, n, d_policy, d_win, d_draw):
+        _check(lib().nsb_eval_device(self._h, slot, _ptr(d_features), n, _ptr(d_policy), _ptr(d_win), _ptr(d_draw)),
+               "nsb_eval_device")
+
+    def eval_decode_device(self, slot, d_features, n, d_off, d_idx, mode, d_policy, d_legal, d_win, d_draw, d_flag):
+        _check(lib().nsb_eval_decode_device(self._h, slot, _ptr(d_features), n, _ptr(d_off), _ptr(d_idx), mode,
+                                            _ptr(d_policy), _ptr(d_legal), _ptr(d_win), _ptr(d_draw), _ptr(d_flag)),
+               "nsb_eval_decode_device")
+
+    def extract_device(self, slot, d_features, n, channels, channels_first, d_planes):
+        _check(lib().nsb_extract_device(self._h, slot, _ptr(d_features), n, channels, int(channels_first),
+                                        _ptr(d_planes)), "nsb_extract_device")
+
+    def pack_positions_device(self, slot, d_positions, n, d_features):
+        _check(lib().nsb_pack_positions_device(self._h, slot, _ptr(d_positions), n, _ptr(d_features)),
+               "nsb_pack_positions_device")
+
+    def decode_device(self, slot, d_policy, d_win, d_draw, n, d_off, d_idx, mode, d_legal, d_flag):
+        _check(lib().nsb_decode_device(self._h, slot, _ptr(d_policy), _ptr(d_win), _ptr(d_draw), n, _ptr(d_off),
+                                       _ptr(d_idx), mode, _ptr(d_legal), _ptr(d_flag)), "nsb_decode_device")
+
+    def stream(self, slot=0) -> int:
+        return lib().nsb_stream(self._h, slot) or 0
+
+    def set_timing(self, on: bool):
+        _check(lib().nsb_set_timing(self._h, int(on)), "nsb_set_timing")
+
+    def trunk_time(self):
+        s, n = C.c_double(0), C.c_uint64(0)
+        _check(lib().nsb_trunk_time(self._h, C.byref(s), C.byref(n)), "nsb_trunk_time")
+        return float(s.value), int(n.value)
+
+    def trunk_time_reset(self):
+        _check(lib().nsb_trunk_time_reset(self._h), "nsb_trunk_time_reset")
+
+    def launch_count(self) -> int:
+        return int(lib().nsb_launch_count(self._h))

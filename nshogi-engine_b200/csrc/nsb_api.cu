@@ -1,0 +1,608 @@
+// nsb_api.cu — the C ABI of include/nsb.h: context, per-slot streams and device buffers, weight
+// upload, and the host-buffer / device-buffer entry points of the leaf-evaluation path.
+//
+// Mirrors the life cycle of the reference's TensorRT executor (reference src/infer/trt.cc):
+//   ctor :52-80   -> nsb_create          (cudaSetDevice, device buffers, non-blocking stream)
+//   load :109-232 -> nsb_load_weights    (canonical blob -> bf16 tile stream in HBM)
+//   computeNonBlocking :234-272 -> nsb_eval_async (H2D, kernels, D2H; returns immediately)
+//   await :281-283 / isComputing :285-287 / resetGPU :289-291 / dtor :82-107
+// Unlike the reference, every CUDA return code is checked and surfaced as a status.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "nsb_internal.h"
+
+namespace nsb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    nsb_feature_bitboard* d_feat = nullptr;
+    nsb_position* d_pos = nullptr;
+    float *d_policy = nullptr, *d_win = nullptr, *d_draw = nullptr, *d_legal = nullptr;
+    uint32_t* d_off = nullptr;
+    uint16_t* d_idx = nullptr;
+    uint8_t* d_flag = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed_pending = false;
+};
+
+}  // namespace nsb
+
+struct nsb_ctx {
+    int gpu = 0, batch_max = 0, num_sms = 0;
+    nsb_net_desc desc{};
+    bool loaded = false, timing = false;
+    nsb::DeviceNet net{};
+    void* d_weights[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<nsb::Slot> slots;
+    uint64_t launches = 0;
+    double trunk_ms = 0.0;
+    uint64_t trunk_launches = 0;
+};
+
+using namespace nsb;
+
+#define NSB_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return NSB_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+static int check_ctx(nsb_ctx* c, int slot) {
+    if (!c) {
+        set_error("null ctx");
+        return NSB_ERR_INVALID;
+    }
+    if (slot < 0 || slot >= (int)c->slots.size()) {
+        set_error("slot %d out of range [0,%d)", slot, (int)c->slots.size());
+        return NSB_ERR_INVALID;
+    }
+    return 0;
+}
+
+static int check_batch(nsb_ctx* c, size_t n, bool need_weights) {
+    if (n > (size_t)c->batch_max) {  // reference: assert(BatchSize <= BatchSizeM), trt.cc:237
+        set_error("batch %zu exceeds batch_max %d", n, c->batch_max);
+        return NSB_ERR_INVALID;
+    }
+    if (need_weights && !c->loaded) {
+        set_error("weights not loaded (call nsb_load_weights first)");
+        return NSB_ERR_STATE;
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char* nsb_last_error(void) { return g_err; }
+const char* nsb_version(void) { return "nsb 0.1 (sm_100a, tcgen05 position-stationary trunk)"; }
+
+int nsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_desc* net) {
+    if (!out || !net || batch_max <= 0 || batch_max > 65535 || slots < 1 || slots > 16) {
+        set_error("nsb_create: bad arguments (batch_max 1..65535, slots 1..16)");
+        return NSB_ERR_INVALID;
+    }
+    if ((net->channels != 128 && net->channels != 256) || net->blocks < 1 || net->blocks > 80 ||
+        net->in_channels < 1 || net->in_channels > kStemCin || net->value_hidden < 1 ||
+        net->value_hidden > kMaxHidden) {
+        set_error("nsb_create: unsupported net (channels 128|256, blocks 1..80, in_channels<=%d, hidden<=%d)",
+                  kStemCin, kMaxHidden);
+        return NSB_ERR_INVALID;
+    }
+    if (net->in_channels != NSB_FEATURE_CHANNELS) {
+        set_error("nsb_create: in_channels must be %d (preset::SimpleFeatures)", NSB_FEATURE_CHANNELS);
+        return NSB_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || gpu < 0 || gpu >= ndev) {
+        cudaGetLastError();
+        set_error("nsb_create: no CUDA device %d (found %d); this library has no CPU fallback", gpu, ndev);
+        return NSB_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    NSB_CUDA(cudaGetDeviceProperties(&prop, gpu));
+    if (prop.major != 10) {
+        set_error("nsb_create: device %d is sm_%d%d; the kernels are built for sm_100a only", gpu, prop.major,
+                  prop.minor);
+        return NSB_ERR_NO_DEVICE;
+    }
+    NSB_CUDA(cudaSetDevice(gpu));
+    int rc = trunk_fused_prepare(net->channels);
+    if (rc) return rc;
+    nsb_ctx* c = new (std::nothrow) nsb_ctx();
+    if (!c) {
+        set_error("out of host memory");
+        return NSB_ERR_NOMEM;
+    }
+    c->gpu = gpu;
+    c->batch_max = batch_max;
+    c->num_sms = prop.multiProcessorCount;
+    c->desc = *net;
+    c->slots.resize(slots);
+    const size_t B = (size_t)batch_max;
+    for (auto& s : c->slots) {
+        cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);  // trt.cc:79
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_feat, B * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_pos, B * sizeof(nsb_position));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_policy, B * kPolicySize * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_win, B * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_draw, B * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_legal, B * NSB_MAX_LEGAL_MOVES * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_off, (B + 1) * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_idx, B * NSB_MAX_LEGAL_MOVES * sizeof(uint16_t));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_flag, B);
+        if (e == cudaSuccess) e = cudaEventCreate(&s.ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&s.ev1);
+        if (e != cudaSuccess) {
+            set_error("nsb_create: device allocation failed: %s", cudaGetErrorString(e));
+            nsb_destroy(c);
+            return e == cudaErrorMemoryAllocation ? NSB_ERR_NOMEM : NSB_ERR_CUDA;
+        }
+    }
+    *out = c;
+    return 0;
+}
+
+void nsb_destroy(nsb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->gpu);
+    for (auto& s : c->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_feat); cudaFree(s.d_pos); cudaFree(s.d_policy); cudaFree(s.d_win); cudaFree(s.d_draw);
+        cudaFree(s.d_legal); cudaFree(s.d_off); cudaFree(s.d_idx); cudaFree(s.d_flag);
+        if (s.ev0) cudaEventDestroy(s.ev0);
+        if (s.ev1) cudaEventDestroy(s.ev1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (void* p : c->d_weights) cudaFree(p);
+    delete c;
+}
+
+int nsb_bind_thread(nsb_ctx* c) {
+    if (!c) {
+        set_error("null ctx");
+        return NSB_ERR_INVALID;
+    }
+    NSB_CUDA(cudaSetDevice(c->gpu));
+    return 0;
+}
+
+size_t nsb_weight_blob_floats(const nsb_net_desc* net) { return net ? blob_floats(*net) : 0; }
+
+int nsb_weight_blob_random(const nsb_net_desc* net, uint64_t seed, float* blob) {
+    if (!net || !blob) {
+        set_error("nsb_weight_blob_random: null argument");
+        return NSB_ERR_INVALID;
+    }
+    blob_random(*net, seed, blob);
+    return 0;
+}
+
+int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
+    if (!c || !blob) {
+        set_error("nsb_load_weights: null argument");
+        return NSB_ERR_INVALID;
+    }
+    if (n_floats != blob_floats(c->desc)) {
+        set_error("nsb_load_weights: blob has %zu floats, net needs %zu", n_floats, blob_floats(c->desc));
+        return NSB_ERR_INVALID;
+    }
+    NSB_CUDA(cudaSetDevice(c->gpu));
+    for (auto& s : c->slots) NSB_CUDA(cudaStreamSynchronize(s.stream));
+    const nsb_net_desc& d = c->desc;
+    const int C = d.channels, H = d.value_hidden, NL = 2 * d.blocks + 2;
+    const int stages = stages_per_pass(d);
+    std::vector<uint16_t> tiles((size_t)stages * kStageBytes / 2);
+    std::vector<float> bias((size_t)NL * C), fc1t((size_t)81 * H), fc1b(H), fc2(2 * (size_t)H), fc2b(2);
+    pack_weights(d, blob, tiles.data(), bias.data(), fc1t.data(), fc1b.data(), fc2.data(), fc2b.data());
+    const void* src[6] = {tiles.data(), bias.data(), fc1t.data(), fc1b.data(), fc2.data(), fc2b.data()};
+    const size_t bytes[6] = {tiles.size() * 2, bias.size() * 4, fc1t.size() * 4, fc1b.size() * 4, fc2.size() * 4,
+                             fc2b.size() * 4};
+    for (int i = 0; i < 6; ++i) {
+        if (c->d_weights[i]) {
+            cudaFree(c->d_weights[i]);
+            c->d_weights[i] = nullptr;
+        }
+        NSB_CUDA(cudaMalloc(&c->d_weights[i], bytes[i]));
+        NSB_CUDA(cudaMemcpy(c->d_weights[i], src[i], bytes[i], cudaMemcpyHostToDevice));
+    }
+    DeviceNet& n = c->net;
+    n.channels = C;
+    n.blocks = d.blocks;
+    n.in_channels = d.in_channels;
+    n.hidden = H;
+    n.num_layers = NL;
+    n.stages_per_pass = stages;
+    n.tiles = static_cast<const uint8_t*>(c->d_weights[0]);
+    n.bias = static_cast<const float*>(c->d_weights[1]);
+    n.fc1t = static_cast<const float*>(c->d_weights[2]);
+    n.fc1b = static_cast<const float*>(c->d_weights[3]);
+    n.fc2 = static_cast<const float*>(c->d_weights[4]);
+    n.fc2b = static_cast<const float*>(c->d_weights[5]);
+    c->loaded = true;
+    return 0;
+}
+
+/* ---- shared launch helper ------------------------------------------------------------------ */
+
+static int run_trunk(nsb_ctx* c, Slot& s, const EvalArgs& a) {
+    if (c->timing) {
+        NSB_CUDA(cudaEventRecord(s.ev0, s.stream));
+    }
+    int k = launch_trunk_fused(c->net, a, c->num_sms, s.stream);
+    if (k < 0) return k;
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    if (c->timing) {
+        NSB_CUDA(cudaEventRecord(s.ev1, s.stream));
+        s.timed_pending = true;
+    }
+    return 0;
+}
+
+static int harvest_timing(nsb_ctx* c, Slot& s) {
+    if (s.timed_pending) {
+        float ms = 0.f;
+        NSB_CUDA(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+        c->trunk_ms += ms;
+        c->trunk_launches += 1;
+        s.timed_pending = false;
+    }
+    return 0;
+}
+
+/* ---- the Infer contract -------------------------------------------------------------------- */
+
+int nsb_eval_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, size_t n, float* policy,
+                   float* win, float* draw) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if ((rc = check_batch(c, n, true))) return rc;
+    if (!features || !policy || !win || !draw) {
+        set_error("nsb_eval_async: null buffer");
+        return NSB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    Slot& s = c->slots[slot];
+    NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
+                             cudaMemcpyHostToDevice, s.stream));  // trt.cc:240-242
+    EvalArgs a{};
+    a.features = s.d_feat;
+    a.n = (int)n;
+    a.policy = s.d_policy;
+    a.win = s.d_win;
+    a.draw = s.d_draw;
+    if ((rc = run_trunk(c, s, a))) return rc;
+    NSB_CUDA(cudaMemcpyAsync(policy, s.d_policy, n * kPolicySize * sizeof(float), cudaMemcpyDeviceToHost,
+                             s.stream));  // trt.cc:265-271
+    NSB_CUDA(cudaMemcpyAsync(win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    return 0;
+}
+
+static int eval_decode_common(nsb_ctx* c, Slot& s, size_t n, const uint32_t* move_off, const uint16_t* move_idx,
+                              int mode, float* legal_out, float* win, float* draw, uint8_t* nan_flag) {
+    const size_t total = move_off[n];
+    if (move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) {
+        set_error("eval_decode: move_off must start at 0 and hold at most %d moves per position",
+                  NSB_MAX_LEGAL_MOVES);
+        return NSB_ERR_INVALID;
+    }
+    NSB_CUDA(cudaMemcpyAsync(s.d_off, move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    if (total)
+        NSB_CUDA(cudaMemcpyAsync(s.d_idx, move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
+    EvalArgs a{};
+    a.features = s.d_feat;
+    a.n = (int)n;
+    a.policy = nullptr;  // dense logits never leave the SM
+    a.win = s.d_win;
+    a.draw = s.d_draw;
+    a.move_off = s.d_off;
+    a.move_idx = s.d_idx;
+    a.legal_out = s.d_legal;
+    a.nan_flag = s.d_flag;
+    a.decode_mode = mode;
+    int rc = run_trunk(c, s, a);
+    if (rc) return rc;
+    if (total)
+        NSB_CUDA(cudaMemcpyAsync(legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    if (nan_flag) NSB_CUDA(cudaMemcpyAsync(nan_flag, s.d_flag, n, cudaMemcpyDeviceToHost, s.stream));
+    return 0;
+}
+
+int nsb_eval_decode_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, size_t n,
+                          const uint32_t* move_off, const uint16_t* move_idx, int mode, float* legal_out,
+                          float* win, float* draw, uint8_t* nan_flag) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if ((rc = check_batch(c, n, true))) return rc;
+    if (!features || !move_off || !move_idx || !legal_out || !win || !draw ||
+        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+        set_error("nsb_eval_decode_async: null buffer or bad mode");
+        return NSB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    Slot& s = c->slots[slot];
+    NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
+                             cudaMemcpyHostToDevice, s.stream));
+    return eval_decode_common(c, s, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag);
+}
+
+int nsb_eval_positions_async(nsb_ctx* c, int slot, const nsb_position* positions, size_t n, float* policy,
+                             float* win, float* draw) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if ((rc = check_batch(c, n, true))) return rc;
+    if (!positions || !policy || !win || !draw) {
+        set_error("nsb_eval_positions_async: null buffer");
+        return NSB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    Slot& s = c->slots[slot];
+    NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
+    int k = launch_pack_positions(s.d_pos, n, s.d_feat, s.stream);
+    if (k < 0) return k;
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    EvalArgs a{};
+    a.features = s.d_feat;
+    a.n = (int)n;
+    a.policy = s.d_policy;
+    a.win = s.d_win;
+    a.draw = s.d_draw;
+    if ((rc = run_trunk(c, s, a))) return rc;
+    NSB_CUDA(cudaMemcpyAsync(policy, s.d_policy, n * kPolicySize * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    return 0;
+}
+
+int nsb_eval_positions_decode_async(nsb_ctx* c, int slot, const nsb_position* positions, size_t n,
+                                    const uint32_t* move_off, const uint16_t* move_idx, int mode,
+                                    float* legal_out, float* win, float* draw, uint8_t* nan_flag) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if ((rc = check_batch(c, n, true))) return rc;
+    if (!positions || !move_off || !move_idx || !legal_out || !win || !draw ||
+        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+        set_error("nsb_eval_positions_decode_async: null buffer or bad mode");
+        return NSB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    Slot& s = c->slots[slot];
+    NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
+    int k = launch_pack_positions(s.d_pos, n, s.d_feat, s.stream);
+    if (k < 0) return k;
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    return eval_decode_common(c, s, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag);
+}
+
+int nsb_await(nsb_ctx* c, int slot) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    Slot& s = c->slots[slot];
+    NSB_CUDA(cudaStreamSynchronize(s.stream));  // trt.cc:281-283
+    return harvest_timing(c, s);
+}
+
+int nsb_is_computing(nsb_ctx* c, int slot) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    cudaError_t e = cudaStreamQuery(c->slots[slot].stream);  // trt.cc:285-287
+    if (e == cudaSuccess) return 0;
+    if (e == cudaErrorNotReady) return 1;
+    set_error("cudaStreamQuery failed: %s", cudaGetErrorString(e));
+    return NSB_ERR_CUDA;
+}
+
+/* ---- device-resident entry points ----------------------------------------------------------- */
+
+int nsb_eval_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n, float* d_policy,
+                    float* d_win, float* d_draw) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if (n > 65535u * 64u) {
+        set_error("nsb_eval_device: n too large");
+        return NSB_ERR_INVALID;
+    }
+    if (!c->loaded) {
+        set_error("weights not loaded");
+        return NSB_ERR_STATE;
+    }
+    if (!d_features || !d_win || !d_draw) {
+        set_error("nsb_eval_device: null buffer");
+        return NSB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    EvalArgs a{};
+    a.features = d_features;
+    a.n = (int)n;
+    a.policy = d_policy;
+    a.win = d_win;
+    a.draw = d_draw;
+    return run_trunk(c, c->slots[slot], a);
+}
+
+int nsb_eval_decode_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n,
+                           const uint32_t* d_move_off, const uint16_t* d_move_idx, int mode, float* d_policy,
+                           float* d_legal_out, float* d_win, float* d_draw, uint8_t* d_nan_flag) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if (!c->loaded) {
+        set_error("weights not loaded");
+        return NSB_ERR_STATE;
+    }
+    if (!d_features || !d_win || !d_draw || !d_move_off || !d_move_idx || !d_legal_out) {
+        set_error("nsb_eval_decode_device: null buffer");
+        return NSB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    EvalArgs a{};
+    a.features = d_features;
+    a.n = (int)n;
+    a.policy = d_policy;
+    a.win = d_win;
+    a.draw = d_draw;
+    a.move_off = d_move_off;
+    a.move_idx = d_move_idx;
+    a.legal_out = d_legal_out;
+    a.nan_flag = d_nan_flag;
+    a.decode_mode = mode;
+    return run_trunk(c, c->slots[slot], a);
+}
+
+int nsb_extract_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n, int channels,
+                       int channels_first, float* d_planes) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if (!d_features || !d_planes || channels < 1 || channels > 1024) {
+        set_error("nsb_extract_device: bad arguments");
+        return NSB_ERR_INVALID;
+    }
+    int k = launch_extract(d_features, n, channels, channels_first, d_planes, c->slots[slot].stream);
+    if (k < 0) return k;
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    return 0;
+}
+
+int nsb_pack_positions_device(nsb_ctx* c, int slot, const nsb_position* d_positions, size_t n,
+                              nsb_feature_bitboard* d_features) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if (!d_positions || !d_features) {
+        set_error("nsb_pack_positions_device: null buffer");
+        return NSB_ERR_INVALID;
+    }
+    int k = launch_pack_positions(d_positions, n, d_features, c->slots[slot].stream);
+    if (k < 0) return k;
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    return 0;
+}
+
+int nsb_decode_device(nsb_ctx* c, int slot, const float* d_policy, const float* d_win, const float* d_draw,
+                      size_t n, const uint32_t* d_move_off, const uint16_t* d_move_idx, int mode,
+                      float* d_legal_out, uint8_t* d_nan_flag) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if (!d_policy || !d_win || !d_draw || !d_move_off || !d_move_idx || !d_legal_out ||
+        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+        set_error("nsb_decode_device: null buffer or bad mode");
+        return NSB_ERR_INVALID;
+    }
+    int k = launch_decode(d_policy, d_win, d_draw, n, d_move_off, d_move_idx, mode, d_legal_out, d_nan_flag,
+                          c->slots[slot].stream);
+    if (k < 0) return k;
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    return 0;
+}
+
+void* nsb_stream(nsb_ctx* c, int slot) {
+    if (check_ctx(c, slot)) return nullptr;
+    return c->slots[slot].stream;
+}
+
+int nsb_set_timing(nsb_ctx* c, int enabled) {
+    if (!c) {
+        set_error("null ctx");
+        return NSB_ERR_INVALID;
+    }
+    c->timing = enabled != 0;
+    return 0;
+}
+
+int nsb_trunk_time(nsb_ctx* c, double* sum_ms, uint64_t* launches) {
+    if (!c) {
+        set_error("null ctx");
+        return NSB_ERR_INVALID;
+    }
+    if (sum_ms) *sum_ms = c->trunk_ms;
+    if (launches) *launches = c->trunk_launches;
+    return 0;
+}
+
+int nsb_trunk_time_reset(nsb_ctx* c) {
+    if (!c) {
+        set_error("null ctx");
+        return NSB_ERR_INVALID;
+    }
+    c->trunk_ms = 0.0;
+    c->trunk_launches = 0;
+    return 0;
+}
+
+uint64_t nsb_launch_count(nsb_ctx* c) { return c ? c->launches : 0; }
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+
+int nsb_host_alloc(void** out, size_t bytes) {
+    if (!out) return NSB_ERR_INVALID;
+    NSB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+int nsb_host_free(void* p) {
+    NSB_CUDA(cudaFreeHost(p));
+    return 0;
+}
+int nsb_device_alloc(void** out, size_t bytes) {
+    if (!out) return NSB_ERR_INVALID;
+    NSB_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return 0;
+}
+int nsb_device_free(void* p) {
+    NSB_CUDA(cudaFree(p));
+    return 0;
+}
+int nsb_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+    NSB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int nsb_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+    NSB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int nsb_memset_device(void* dst, int value, size_t bytes) {
+    NSB_CUDA(cudaMemset(dst, value, bytes));
+    return 0;
+}
+int nsb_device_sync(void) {
+    NSB_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, int variant, float* max_err) {
+    return umma_selftest(gpu, n_cols, k_elems, shift_rows, variant, max_err);
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// nsb_internal.h — shared host/device definitions for the leaf-evaluation kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/nsb.h"
+
+namespace nsb {
+
+constexpr int kSquares = NSB_NUM_SQUARES;       // 81
+constexpr int kPolicyPlanes = NSB_POLICY_PLANES; // 27
+constexpr int kPolicySize = NSB_POLICY_SIZE;    // 2187
+constexpr int kStemCin = 128;                   // stem input channels padded 86 -> 128
+constexpr int kStageBytes = 16384;              // one weight tile: 128 Cout x 64 Cin bf16
+constexpr int kMaxHidden = 256;
+
+// Device-side geometry of the position-stationary trunk kernel.
+// A position occupies 100 "slots": slot = 10 * (t / 9) + (t % 9) for board index t, the 10th
+// column and 10th row are permanent zeros, so tap (dh, dw) is the slot offset 10*dh + dw.
+template <int C>
+struct TrunkGeom {
+    static_assert(C == 128 || C == 256, "trunk width must be 128 or 256");
+    static constexpr int KCH = C / 8;                     // 16-byte channel chunks per slot
+    static constexpr int NPOS = (C == 128) ? 2 : 1;       // positions resident per CTA pass
+    static constexpr int NCOLS = NPOS * 96;               // UMMA N: slots [0, NCOLS); last real slot 88 / 188
+    static constexpr int NHALF = C / 128;                 // Cout halves (UMMA M = 128 each)
+    static constexpr int GUARD = 12;                      // zero slots before slot 0 (>= 11)
+    static constexpr int SPITCH = (GUARD + NCOLS + 11) | 1; // slots per channel chunk (odd)
+    static constexpr int BUF_BYTES = ((KCH * SPITCH * 16 + 127) / 128) * 128;
+    static constexpr int NSTAGES = 6;                     // weight ring depth
+    static constexpr int KC64 = C / 64;                   // 64-channel K blocks per tap
+    static constexpr int TMEM_COLS = 256;                 // >= NHALF * NCOLS, power of two
+    static constexpr int SCRATCH_FLOATS = NPOS * kPolicySize;
+    // dynamic shared memory map (byte offsets from a 128-aligned base)
+    static constexpr int OFF_BUF_A = 0;
+    static constexpr int OFF_BUF_B = OFF_BUF_A + BUF_BYTES;
+    static constexpr int OFF_RING = OFF_BUF_B + BUF_BYTES;
+    static constexpr int OFF_SCRATCH = OFF_RING + NSTAGES * kStageBytes;
+    static constexpr int OFF_FEAT = OFF_SCRATCH + ((SCRATCH_FLOATS * 4 + 15) / 16) * 16;
+    static constexpr int OFF_VBUF = OFF_FEAT + NPOS * NSB_FEATURE_CHANNELS * 16;
+    static constexpr int OFF_RED = OFF_VBUF + ((NPOS * 81 * 4 + 15) / 16) * 16;
+    static constexpr int OFF_BARS = OFF_RED + 4 * NPOS * 2 * 4 + 16;
+    static constexpr int SMEM_BYTES = OFF_BARS + (2 * NSTAGES + 2) * 8 + 16 + 128; // + align slack
+    static_assert(NCOLS % 16 == 0 && NCOLS <= 256, "UMMA N");
+    static_assert(NHALF * NCOLS <= TMEM_COLS, "TMEM columns");
+    static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+};
+
+// Device pointers + shape of a loaded net (filled by weights.cc / nsb_api.cu).
+struct DeviceNet {
+    int channels;      // C
+    int blocks;        // residual blocks
+    int in_channels;   // 86
+    int hidden;        // value MLP hidden units (<= 256)
+    int num_layers;    // 1 (stem) + 2*blocks + 1 (heads)
+    int stages_per_pass;
+    const uint8_t* tiles;  // [stages_per_pass][16384] bf16 weight tiles in stream order
+    const float* bias;     // [num_layers][C]  (head row: 27 policy biases, value-conv bias at 27)
+    const float* fc1t;     // [81][hidden]  (transposed for coalesced reads)
+    const float* fc1b;     // [hidden]
+    const float* fc2;      // [2][hidden]
+    const float* fc2b;     // [2]
+};
+
+struct EvalArgs {
+    const nsb_feature_bitboard* features;  // [n][86]
+    int n;
+    float* policy;                // [n][2187] or nullptr (fused decode only)
+    float* win;                   // [n]
+    float* draw;                  // [n]
+    const uint32_t* move_off;     // [n+1] or nullptr
+    const uint16_t* move_idx;
+    float* legal_out;
+    uint8_t* nan_flag;
+    int decode_mode;
+};
+
+// host-side weight handling (weights.cc)
+size_t blob_floats(const nsb_net_desc& d);
+void blob_random(const nsb_net_desc& d, uint64_t seed, float* blob);
+int stages_per_pass(const nsb_net_desc& d);
+// Packs canonical blob -> host images of DeviceNet arrays (tiles as uint16 bf16 bits).
+void pack_weights(const nsb_net_desc& d, const float* blob, uint16_t* tiles, float* bias,
+                  float* fc1t, float* fc1b, float* fc2, float* fc2b);
+
+// kernel launchers (each returns the number of kernels launched or <0 after setting last error)
+int launch_extract(const nsb_feature_bitboard* d_fb, size_t n, int channels, int channels_first,
+                   float* d_planes, cudaStream_t s);
+int launch_pack_positions(const nsb_position* d_pos, size_t n, nsb_feature_bitboard* d_fb,
+                          cudaStream_t s);
+int launch_decode(const float* d_policy, const float* d_win, const float* d_draw, size_t n,
+                  const uint32_t* d_off, const uint16_t* d_idx, int mode, float* d_out,
+                  uint8_t* d_flag, cudaStream_t s);
+int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s);
+int trunk_fused_prepare(int channels);  // sets max dynamic smem attribute
+int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, int variant, float* max_err);
+
+void set_error(const char* fmt, ...);
+
+// shared device code: warp-level gather + softmax over one position's legal moves
+}  // namespace nsb
