@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — leaf evals/sec of the B200 leaf-evaluation path (BASELINE.json metric, config 2).
+
+A step = one batch of 256 synthetic positions through the hot path: feature bitboards ->
+(in-kernel plane expansion) -> 10 x 128 ResNet on tcgen05 -> policy head -> fused legal-move
+gather + softmax + value/draw sigmoids.  One fused kernel launch per step.
+
+  value : device-timed (CUDA events on the launch stream), inputs already resident in HBM,
+          rotating over a pool of input batches larger than L2.
+  e2e   : the same step through the host-buffer C-ABI call (nsb_eval_decode_async + nsb_await):
+          pinned host inputs, H2D + kernel + D2H inside the timed region, several slots in flight.
+  --impl reference : the reference's CPU path for its CPU-runnable config (pack + its own Random
+          executor compiled from /root/reference into oracle/_ref + decode) on all host cores.
+Multi-GPU: one process per GPU (torchrun), independent replicas, weak scaling; NCCL only for the
+barrier, the max-over-ranks of the timed region and the final counter reduction.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "nn_leaf_evals_per_sec_batch256"
+UNIT = "evals/s"
+L2_BYTES = 126 * 1024 * 1024
+FLOPS_PER_SAMPLE = {(128, 10): 0.4944e9, (256, 20): 3.8554e9, (256, 40): 7.6774e9}
+
+
+def workload_name(C, blocks, B):
+    return (f"{blocks}-block {C}-ch ResNet random-init, batch {B} leaf evaluation on 1xB200 per replica "
+            "(feature planes + forward + policy decode)")
+
+
+def trunk_flops_per_sample(C, blocks, in_ch=86):
+    """2*MACs, unpadded channels: stem + 2*blocks convs + policy/value heads + FCs."""
+    conv = lambda ci, co, k: 2.0 * 81 * k * ci * co
+    f = conv(in_ch, C, 9) + 2 * blocks * conv(C, C, 9) + conv(C, 27, 1) + conv(C, 1, 1)
+    f += 2.0 * 81 * 256 + 2.0 * 256 * 2
+    return f
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        load = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(nb, synth, orc_unused, B, pool, seed=20240203):
+    """Pool of `pool` distinct input batches (feature bitboards via the product's own stage-1
+    kernel would need a GPU; here they come from packed synthetic positions uploaded once)."""
+    base_positions = synth.random_positions(min(pool * B, 4096), seed=seed)
+    off1, idx1 = synth.random_legal_moves(B, seed=seed, edge_rows=False)
+    return base_positions, off1, idx1
+
+
+def run_b200(args):
+    pkg = graft.load_package()
+    nb, synth, rep = pkg.binding, pkg.synth, pkg.replica
+    info = rep.RankInfo.from_env()
+    world = info.world
+    if world > 1 or args.gpus > 1:
+        import torch
+        import torch.distributed as dist
+
+        if world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+        torch.cuda.set_device(info.local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", info.local_rank))
+    if nb.device_count() < 1:
+        raise SystemExit("bench: no CUDA device; the product path has no CPU fallback")
+    gpu = info.local_rank
+    B, C, blocks = args.batch, args.channels, args.blocks
+    desc = nb.net_desc(C, blocks)
+    blob = nb.random_blob(desc, 1234)
+    slots = args.slots
+    ctx = nb.Context(desc, batch_max=B, slots=slots, gpu=gpu, blob=blob)
+
+    # ---- synthetic inputs: pool of batches > L2 so no step re-reads a cached input --------------
+    fb_bytes = B * 86 * 16
+    pool = max(4, (L2_BYTES + fb_bytes - 1) // fb_bytes + 8) if not args.small_pool else 8
+    pos = synth.random_positions(2048, seed=20240203 + info.rank)
+    d_pos = nb.DeviceBuffer.from_host(pos)
+    d_fb_unique = nb.DeviceBuffer(len(pos) * 86 * 16)
+    ctx.pack_positions_device(0, d_pos.ptr, len(pos), d_fb_unique.ptr)   # product stage-1 kernel
+    ctx.await_(0)
+    fb_unique = d_fb_unique.to_host((len(pos), 86), nb.FEATURE_BITBOARD)
+    rng = np.random.default_rng(99 + info.rank)
+    off, idx = synth.random_legal_moves(B, seed=20240203, edge_rows=False)
+    n_moves = int(off[-1])
+    # device pool
+    host_pool = fb_unique[rng.integers(0, len(pos), size=pool * B)].reshape(pool, B * 86)
+    d_pool = nb.DeviceBuffer.from_host(host_pool)
+    d_off = nb.DeviceBuffer.from_host(off)
+    d_idx = nb.DeviceBuffer.from_host(idx)
+    n_out = 8
+    d_policy = [nb.DeviceBuffer(B * 2187 * 4) for _ in range(n_out)]
+    d_legal = [nb.DeviceBuffer(max(n_moves, 1) * 4) for _ in range(n_out)]
+    d_win = [nb.DeviceBuffer(B * 4) for _ in range(n_out)]
+    d_draw = [nb.DeviceBuffer(B * 4) for _ in range(n_out)]
+    d_flag = [nb.DeviceBuffer(B) for _ in range(n_out)]
+
+    def dev_step(i):
+        j = i % n_out
+        ctx.eval_decode_device(0, d_pool.ptr + (i % pool) * fb_bytes, B, d_off.ptr, d_idx.ptr, nb.DECODE_PROBS,
+                               d_policy[j].ptr, d_legal[j].ptr, d_win[j].ptr, d_draw[j].ptr, d_flag[j].ptr)
+
+    K, W = args.steps, max(args.warmup, 3)
+    for i in range(W):
+        dev_step(i)
+    ctx.await_(0)
+    ctx.set_timing(True)
+    ctx.trunk_time_reset()
+    sampler = ClockSampler(gpu)
+    sampler.start()
+    time.sleep(0.3)
+    rep.barrier()
+    nb.device_sync()
+    l0 = ctx.launch_count()
+    e0, e1 = nb.Event(), nb.Event()
+    e0.record(ctx, 0)
+    for i in range(K):
+        dev_step(W + i)
+    e1.record(ctx, 0)
+    e1.sync()
+    ctx.await_(0)
+    nb.device_sync()
+    rep.barrier()
+    elapsed_ms = e0.elapsed_ms(e1)
+    launches = ctx.launch_count() - l0
+    trunk_ms_sum, trunk_n = ctx.trunk_time()
+    ctx.set_timing(False)
+    dev_device = None
+    if world > 1:
+        import torch
+        dev_device = torch.device("cuda", info.local_rank)
+    counters, elapsed_max = rep.aggregate({"evals": B * K, "batches": K, "legal_moves": n_moves * K}, elapsed_ms,
+                                          device=dev_device)
+    value = rep.whole_job_rate(counters["evals"], elapsed_max)
+
+    # ---- e2e: host buffers through the C ABI, `slots` batches in flight ---------------------------------
+    h_pool_n = 16
+    h_fb = [nb.PinnedArray((B * 86,), nb.FEATURE_BITBOARD) for _ in range(h_pool_n)]
+    for k, a in enumerate(h_fb):
+        a.array[:] = host_pool[k % pool]
+    h_off = nb.PinnedArray((B + 1,), np.uint32); h_off.array[:] = off
+    h_idx = nb.PinnedArray((max(n_moves, 1),), np.uint16); h_idx.array[:n_moves] = idx
+    h_legal = [nb.PinnedArray((max(n_moves, 1),), np.float32) for _ in range(slots)]
+    h_win = [nb.PinnedArray((B,), np.float32) for _ in range(slots)]
+    h_draw = [nb.PinnedArray((B,), np.float32) for _ in range(slots)]
+    h_flag = [nb.PinnedArray((B,), np.uint8) for _ in range(slots)]
+    h_policy = [nb.PinnedArray((B * 2187,), np.float32) for _ in range(slots)]
+    sink = 0.0
+
+    def e2e_loop(steps, fused):
+        nonlocal sink
+        for i in range(steps):
+            s = i % slots
+            if i >= slots:
+                ctx.await_(s)
+                sink += float(h_win[s].array[0])            # consume the step's result on the host
+            if fused:
+                ctx.eval_decode_async(s, h_fb[i % h_pool_n].array, B, h_off.array, h_idx.array, nb.DECODE_PROBS,
+                                      h_legal[s].array, h_win[s].array, h_draw[s].array, h_flag[s].array)
+            else:
+                ctx.eval_async(s, h_fb[i % h_pool_n].array, B, h_policy[s].array, h_win[s].array, h_draw[s].array)
+        for s in range(slots):
+            ctx.await_(s)
+            sink += float(h_win[s].array[0])
+
+    def time_e2e(fused):
+        e2e_loop(max(W, slots), fused)
+        rep.barrier()
+        nb.device_sync()
+        t0 = time.perf_counter()
+        e2e_loop(K, fused)
+        nb.device_sync()
+        dt = (time.perf_counter() - t0) * 1e3
+        rep.barrier()
+        _, dt_max = rep.aggregate({}, dt, device=dev_device)
+        return rep.whole_job_rate(B * K * world, dt_max)
+
+    e2e_fused = time_e2e(True)
+    e2e_infer = time_e2e(False)
+    clocks = sampler.stop()
+
+    # ---- roofline of the dominant (only) kernel ----------------------------------------------------------
+    tf_burst, tf_sust, hbm, which = peaks()
+    flops_launch = trunk_flops_per_sample(C, blocks) * B
+    avg_launch_ms = trunk_ms_sum / max(trunk_n, 1)
+    achieved = flops_launch / (avg_launch_ms * 1e-3) / 1e12 if avg_launch_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "trunk_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{C}x{blocks}@{B}")
+    roofline = {"bound": "tensor", "kernel": f"trunk_fused_kernel<{C}>", "achieved": round(achieved, 2),
+                "peak": tf_burst, "unit": "TFLOP/s", "frac": round(achieved / tf_burst, 4),
+                "frac_of_sustained_peak": round(achieved / tf_sust, 4), "peak_source": which,
+                "flops_per_launch": flops_launch, "avg_launch_ms": round(avg_launch_ms, 5),
+                "kernel_share_of_step": round(trunk_ms_sum / elapsed_ms, 4) if elapsed_ms > 0 else None,
+                "traffic": traffic}
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(elapsed_max / K, 5), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(C, blocks, B), "launches_per_step": 1,
+                   "batch": B, "channels": C, "blocks": blocks, "legal_moves_per_batch": n_moves,
+                   "l2_policy": f"inputs rotate over a pool of {pool} batches ({pool * fb_bytes >> 20} MiB > L2); "
+                                "weights stay L2-resident as in steady-state serving",
+                   "replicas": world, "slots_in_flight_e2e": slots},
+        "e2e": {"value": round(e2e_fused, 1), "unit": UNIT, "api": "nsb_eval_decode_async + nsb_await (host buffers)",
+                "h2d_bytes_per_step": fb_bytes + (B + 1) * 4 + n_moves * 2,
+                "d2h_bytes_per_step": n_moves * 4 + B * 4 * 2 + B, "clock": "host, device-synchronised both sides"},
+        "e2e_infer_contract": {"value": round(e2e_infer, 1), "unit": UNIT,
+                               "api": "nsb_eval_async + nsb_await == Infer::computeNonBlocking/await (dense logits)",
+                               "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": B * 2187 * 4 + B * 8},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "counters": counters,
+    }
+    if info.rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(synth, B, seconds=args.cpu_seconds)
+    if info.rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return sink
+
+
+def cpu_baseline(synth, B, seconds=12.0, threads=None):
+    """Reference's CPU path for its CPU-runnable config (BASELINE.json configs[0]): stage-1 pack
+    (port; libnshogi absent) + Random executor (the reference's own random.cc compiled into
+    oracle/_ref when present, else the port) + decode (port), one batch of B per thread-iteration."""
+    orc = graft.load_oracle()
+    threads = threads or (os.cpu_count() or 1)
+    pos = synth.random_positions(1024, seed=20240203)
+    off, idx = synth.random_legal_moves(len(pos), seed=20240203, edge_rows=False)
+    use_ref = orc.have_ref_random()
+    v, sec = orc.cpu_path(pos, off, idx, B, threads, 2, False, use_ref)       # calibrate
+    per_thread = max(2, int(seconds / max(sec / 2, 1e-6)))
+    v, sec = orc.cpu_path(pos, off, idx, B, threads, per_thread, False, use_ref)
+    # context: the same net's fp32 forward on the host cores (oracle port, vectorised C, all threads)
+    pkg = graft.load_package()
+    desc = pkg.binding.net_desc(128, 10)
+    blob = pkg.binding.random_blob(desc, 1234)
+    planes = orc.expand(orc.pack(pos[:256]), 256)
+    t0 = time.perf_counter()
+    orc.forward(desc, blob, planes, False)
+    fwd = 256 / (time.perf_counter() - t0)
+    return {"value": round(v, 1), "with_oracle_forward_10x128": {"value": round(fwd, 1), "unit": UNIT,
+            "sample": "256 positions through the oracle's fp32 CPU forward of the 10x128 net, all threads"}, "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
+            "sample": f"{threads} threads x {per_thread} batches of {B}: pack (port of FeatureStackComptime, "
+                      f"builder-defined) + Random executor ({'reference src/infer/random.cc compiled in place' if use_ref else 'port of random.cc'}) "
+                      f"+ decode (port of feedworker.cc:100-136); {sec:.1f} s; NN forward NOT included "
+                      "(the reference's CPU config replaces it with the Random executor)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path on the host cores (see cpu_baseline)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = graft.load_package()
+    synth = pkg.synth
+    orc = graft.load_oracle()
+    B = args.batch
+    threads = os.cpu_count() or 1
+    pos = synth.random_positions(1024, seed=20240203)
+    off, idx = synth.random_legal_moves(len(pos), seed=20240203, edge_rows=False)
+    use_ref = orc.have_ref_random()
+    v, sec = orc.cpu_path(pos, off, idx, B, threads, 2, False, use_ref)
+    K, W = args.steps, max(args.warmup, 1)
+    budget = 120.0                                   # whole run bounded to ~2 minutes
+    per_step = max(1, int((budget / (K + W)) / max(sec / 2, 1e-6)))
+    per_step = min(per_step, 64)
+    for _ in range(W):
+        orc.cpu_path(pos, off, idx, B, threads, per_step, False, use_ref)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(K):
+        orc.cpu_path(pos, off, idx, B, threads, per_step, False, use_ref)
+        total += threads * per_step * B
+    dt = time.perf_counter() - t0
+    value = total / dt
+    sample = (f"each step = {threads} threads x {per_step} batches of {B} through pack (port) + Random executor "
+              f"({'reference random.cc compiled in place' if use_ref else 'port'}) + decode (port); no NN forward on CPU")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": round(dt / K * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.channels, args.blocks, B), "batch": B,
+                       "channels": args.channels, "blocks": args.blocks,
+                       "reference_arm": "the reference has no CPU forward: its CPU-runnable executor (Random, "
+                                        "BASELINE.json configs[0]) stands in for the ResNet"},
+            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": threads,
+                             "kind": "reference" if use_ref else "port", "sample": sample},
+            "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--channels", type=int, default=128)
+    ap.add_argument("--blocks", type=int, default=10)
+    ap.add_argument("--slots", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small-pool", action="store_true", help="8-batch input pool (profiling runs only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

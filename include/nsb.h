@@ -186,6 +186,14 @@ int nsb_set_timing(nsb_ctx* ctx, int enabled);
 int nsb_trunk_time(nsb_ctx* ctx, double* sum_ms, uint64_t* launches);
 int nsb_trunk_time_reset(nsb_ctx* ctx);
 
+/* CUDA events on a slot's stream, for timing a region from the host side of the ABI
+ * (torch.cuda.Event only sees torch's own streams). */
+int nsb_event_create(void** out);
+int nsb_event_destroy(void* ev);
+int nsb_event_record(void* ev, nsb_ctx* ctx, int slot);
+int nsb_event_sync(void* ev);
+int nsb_event_elapsed_ms(void* start, void* stop, float* ms);
+
 /* Kernel launches issued by this ctx since creation (bench "gpu_launches"). */
 uint64_t nsb_launch_count(nsb_ctx* ctx);
 
@@ -207,9 +215,8 @@ int nsb_device_count(void);
 
 /* tcgen05 self-test: one CTA runs D[128 x n_cols] = A * B^T with the K-major SWIZZLE_NONE
  * descriptors the trunk uses, B's start address moved by shift_rows 16-byte rows, and the host
- * compares against an fp32 loop.  variant 0 = the convention the trunk uses; variant 1 = LBO/SBO
- * swapped (diagnostic).  Returns 0 and the max abs error (exact inputs: expect 0). */
-int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, int variant, float* max_err);
+ * compares against an fp32 loop.  Returns 0 and the max abs error (exact inputs: expect 0). */
+int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -83,7 +83,12 @@ SIGNATURES = {
     "nsb_last_error": (C.c_char_p, []),
     "nsb_version": (C.c_char_p, []),
     "nsb_device_count": (C.c_int, []),
-    "nsb_umma_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "nsb_umma_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "nsb_event_create": (C.c_int, [C.POINTER(_P)]),
+    "nsb_event_destroy": (C.c_int, [_P]),
+    "nsb_event_record": (C.c_int, [_P, _P, C.c_int]),
+    "nsb_event_sync": (C.c_int, [_P]),
+    "nsb_event_elapsed_ms": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
 }
 
 
@@ -188,10 +193,35 @@ def device_sync():
     _check(lib().nsb_device_sync(), "nsb_device_sync")
 
 
-def umma_selftest(n_cols: int, k_elems: int, shift_rows: int, variant: int = 0, gpu: int = 0) -> float:
+def umma_selftest(n_cols: int, k_elems: int, shift_rows: int, gpu: int = 0) -> float:
     err = C.c_float(-1.0)
-    _check(lib().nsb_umma_selftest(gpu, n_cols, k_elems, shift_rows, variant, C.byref(err)), "nsb_umma_selftest")
+    _check(lib().nsb_umma_selftest(gpu, n_cols, k_elems, shift_rows, C.byref(err)), "nsb_umma_selftest")
     return float(err.value)
+
+
+class Event:
+    """CUDA event recorded on a slot's stream (timing from the host side of the ABI)."""
+
+    def __init__(self):
+        p = _P()
+        _check(lib().nsb_event_create(C.byref(p)), "nsb_event_create")
+        self._p = p
+
+    def record(self, ctx: "Context", slot: int = 0):
+        _check(lib().nsb_event_record(self._p, ctx._h, slot), "nsb_event_record")
+
+    def sync(self):
+        _check(lib().nsb_event_sync(self._p), "nsb_event_sync")
+
+    def elapsed_ms(self, stop: "Event") -> float:
+        ms = C.c_float(0)
+        _check(lib().nsb_event_elapsed_ms(self._p, stop._p, C.byref(ms)), "nsb_event_elapsed_ms")
+        return float(ms.value)
+
+    def destroy(self):
+        if self._p is not None:
+            lib().nsb_event_destroy(self._p)
+            self._p = None
 
 
 class Context:

@@ -36,8 +36,8 @@ struct Slot {
     uint32_t* d_off = nullptr;
     uint16_t* d_idx = nullptr;
     uint8_t* d_flag = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed_pending = false;
+    std::vector<cudaEvent_t> ev;  // start/stop pairs, one pair per trunk launch since the last await
+    size_t ev_used = 0;
 };
 
 }  // namespace nsb
@@ -157,8 +157,6 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
         if (e == cudaSuccess) e = cudaMalloc(&s.d_off, (B + 1) * sizeof(uint32_t));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_idx, B * NSB_MAX_LEGAL_MOVES * sizeof(uint16_t));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_flag, B);
-        if (e == cudaSuccess) e = cudaEventCreate(&s.ev0);
-        if (e == cudaSuccess) e = cudaEventCreate(&s.ev1);
         if (e != cudaSuccess) {
             set_error("nsb_create: device allocation failed: %s", cudaGetErrorString(e));
             nsb_destroy(c);
@@ -176,8 +174,7 @@ void nsb_destroy(nsb_ctx* c) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_feat); cudaFree(s.d_pos); cudaFree(s.d_policy); cudaFree(s.d_win); cudaFree(s.d_draw);
         cudaFree(s.d_legal); cudaFree(s.d_off); cudaFree(s.d_idx); cudaFree(s.d_flag);
-        if (s.ev0) cudaEventDestroy(s.ev0);
-        if (s.ev1) cudaEventDestroy(s.ev1);
+        for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (void* p : c->d_weights) cudaFree(p);
@@ -253,27 +250,32 @@ int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
 
 static int run_trunk(nsb_ctx* c, Slot& s, const EvalArgs& a) {
     if (c->timing) {
-        NSB_CUDA(cudaEventRecord(s.ev0, s.stream));
+        while (s.ev.size() < s.ev_used + 2) {
+            cudaEvent_t e;
+            NSB_CUDA(cudaEventCreate(&e));
+            s.ev.push_back(e);
+        }
+        NSB_CUDA(cudaEventRecord(s.ev[s.ev_used], s.stream));
     }
     int k = launch_trunk_fused(c->net, a, c->num_sms, s.stream);
     if (k < 0) return k;
     NSB_CUDA(cudaGetLastError());
     c->launches += (uint64_t)k;
     if (c->timing) {
-        NSB_CUDA(cudaEventRecord(s.ev1, s.stream));
-        s.timed_pending = true;
+        NSB_CUDA(cudaEventRecord(s.ev[s.ev_used + 1], s.stream));
+        s.ev_used += 2;
     }
     return 0;
 }
 
 static int harvest_timing(nsb_ctx* c, Slot& s) {
-    if (s.timed_pending) {
+    for (size_t i = 0; i + 1 < s.ev_used; i += 2) {
         float ms = 0.f;
-        NSB_CUDA(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+        NSB_CUDA(cudaEventElapsedTime(&ms, s.ev[i], s.ev[i + 1]));
         c->trunk_ms += ms;
         c->trunk_launches += 1;
-        s.timed_pending = false;
     }
+    s.ev_used = 0;
     return 0;
 }
 
@@ -601,8 +603,35 @@ int nsb_device_sync(void) {
     return 0;
 }
 
-int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, int variant, float* max_err) {
-    return umma_selftest(gpu, n_cols, k_elems, shift_rows, variant, max_err);
+int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err) {
+    return umma_selftest(gpu, n_cols, k_elems, shift_rows, max_err);
+}
+
+int nsb_event_create(void** out) {
+    if (!out) return NSB_ERR_INVALID;
+    cudaEvent_t e;
+    NSB_CUDA(cudaEventCreate(&e));
+    *out = e;
+    return 0;
+}
+int nsb_event_destroy(void* ev) {
+    NSB_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(ev)));
+    return 0;
+}
+int nsb_event_record(void* ev, nsb_ctx* c, int slot) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    NSB_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev), c->slots[slot].stream));
+    return 0;
+}
+int nsb_event_sync(void* ev) {
+    NSB_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(ev)));
+    return 0;
+}
+int nsb_event_elapsed_ms(void* start, void* stop, float* ms) {
+    if (!ms) return NSB_ERR_INVALID;
+    NSB_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+    return 0;
 }
 
 }  // extern "C"

@@ -94,7 +94,7 @@ int launch_decode(const float* d_policy, const float* d_win, const float* d_draw
                   uint8_t* d_flag, cudaStream_t s);
 int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s);
 int trunk_fused_prepare(int channels);  // sets max dynamic smem attribute
-int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, int variant, float* max_err);
+int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err);
 
 void set_error(const char* fmt, ...);
 

@@ -2,8 +2,8 @@
 // K-major SWIZZLE_NONE shared-memory descriptors whose start address is moved by an arbitrary
 // number of 16-byte rows (the zero-copy 3x3 tap shift of trunk_fused.cu).  One CTA computes
 // D[128 x N] = A[128 x K] * B[shift .. shift+N)[K]^T on the tensor core and the host compares it
-// with a plain fp32 loop.  `variant` 1 swaps the LBO/SBO fields, so a failing convention shows
-// up as variant 0 wrong / variant 1 right instead of as a silent garbage network.
+// with a plain fp32 loop, so a wrong descriptor convention shows up here instead of as a silently
+// wrong network.  (First B200 run: max error 0.0 for every shape in tests/test_gpu_parity.py.)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -20,7 +20,7 @@ namespace {
 
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const uint16_t* __restrict__ a /*[128][K]*/, const uint16_t* __restrict__ b /*[rows][K]*/,
-                     int N, int K, int rows, int shift, int variant, float* __restrict__ d /*[128][N]*/) {
+                     int N, int K, int rows, int shift, float* __restrict__ d /*[128][N]*/) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     const int kch = K / 8;
@@ -56,14 +56,8 @@ umma_selftest_kernel(const uint16_t* __restrict__ a /*[128][K]*/, const uint16_t
         for (int k16 = 0; k16 < K / 16; ++k16) {
             const uint32_t a_addr = smem_u32(sa) + (uint32_t)(k16 * 2 * 128 * 16);
             const uint32_t b_addr = smem_u32(sb) + (uint32_t)((k16 * 2 * bp + shift) * 16);
-            uint64_t ad, bd;
-            if (variant == 0) {
-                ad = make_smem_desc(a_addr, 128 * 16, 128);
-                bd = make_smem_desc(b_addr, (uint32_t)bp * 16, 128);
-            } else {
-                ad = make_smem_desc(a_addr, 128, 128 * 16);
-                bd = make_smem_desc(b_addr, 128, (uint32_t)bp * 16);
-            }
+            const uint64_t ad = make_smem_desc(a_addr, 128 * 16, 128);
+            const uint64_t bd = make_smem_desc(b_addr, (uint32_t)bp * 16, 128);
             umma_bf16(tmem_base, ad, bd, idesc, k16 != 0);
         }
         umma_commit(bar);
@@ -84,7 +78,7 @@ umma_selftest_kernel(const uint16_t* __restrict__ a /*[128][K]*/, const uint16_t
 
 }  // namespace
 
-int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, int variant, float* max_err) {
+int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err) {
     if (n_cols % 32 || n_cols < 32 || n_cols > 256 || k_elems % 16 || k_elems <= 0 || shift_rows < 0 ||
         shift_rows > 64) {
         set_error("umma_selftest: need N%%32==0 (32..256), K%%16==0, 0<=shift<=64");
@@ -117,7 +111,7 @@ int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, int variant,
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-        umma_selftest_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, variant, dd);
+        umma_selftest_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, dd);
         e = cudaDeviceSynchronize();
     }
     std::vector<float> hd((size_t)128 * N);

@@ -1,0 +1,280 @@
+"""GPU suite (-m gpu): parity of the CUDA path, called through the C ABI, against the CPU oracle,
+the committed golden vectors and the reference's own extractbit.cu compiled in place."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+# Tolerances (stated here, justified in DESIGN.md §7):
+TOL_LOGIT_VS_BF16_ORACLE = 1e-2   # same bf16 rounding points; fp32 accumulation order differs, so a
+                                  # value on a rounding boundary can flip by one bf16 ulp (2^-8 relative)
+TOL_VALUE_VS_BF16_ORACLE = 2e-3
+TOL_PROB_VS_FP32 = 2e-2           # policy probabilities max-abs-diff, bf16 in / fp32 acc
+TOL_VALUE_VS_FP32 = 1e-2
+TOL_DECODE_REL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def ctx128(nb):
+    desc = nb.net_desc(128, 2)
+    blob = nb.random_blob(desc, 1234)
+    c = nb.Context(desc, batch_max=512, slots=2, blob=blob)
+    yield c, desc, blob
+    c.close()
+
+
+def run_eval(nb, ctx, fb, n, slot=0):
+    policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+    win = np.zeros(n, dtype=np.float32)
+    draw = np.zeros(n, dtype=np.float32)
+    ctx.eval_async(slot, fb, n, policy, win, draw)
+    ctx.await_(slot)
+    return policy, win, draw
+
+
+# ---- tcgen05 building block -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_cols,k,shift", [(192, 64, 0), (192, 64, 11), (96, 128, 1), (192, 128, 22), (256, 16, 5)])
+def test_umma_descriptor_selftest(nb, n_cols, k, shift):
+    assert nb.umma_selftest(n_cols, k, shift) == 0.0
+
+
+# ---- stage 2: extract == reference extractBits<> ----------------------------------------------------------------
+@pytest.mark.parametrize("n,channels", [(1, 86), (3, 86), (256, 86), (37, 93), (5, 1), (4096, 86)])
+@pytest.mark.parametrize("channels_first", [True, False])
+def test_extract_bit_exact(nb, orc, synth, ctx128, n, channels, channels_first):
+    ctx = ctx128[0]
+    fb = synth.random_feature_bitboards(n * channels, seed=n + channels)
+    d_fb = nb.DeviceBuffer.from_host(fb)
+    d_out = nb.DeviceBuffer(n * channels * 81 * 4)
+    d_out.fill(0xFF)
+    ctx.extract_device(0, d_fb.ptr, n, channels, channels_first, d_out.ptr)
+    ctx.await_(0)
+    shape = (n, channels, 81) if channels_first else (n, 81, channels)
+    got = d_out.to_host(shape, np.uint32)
+    want = orc.expand(fb, n, channels, channels_first).view(np.uint32)
+    assert np.array_equal(got, want)
+    if orc.have_ref_extract() and n <= 256:   # the reference's own kernels, compiled from /root/reference
+        d_ref = nb.DeviceBuffer(n * channels * 81 * 4)
+        d_ref.fill(0xFF)
+        assert orc.ref_extract_device(d_ref.ptr, d_fb.ptr, n, channels, channels_first) == 0
+        assert np.array_equal(d_ref.to_host(shape, np.uint32), want)
+        d_ref.free()
+    d_fb.free()
+    d_out.free()
+
+
+def test_extract_golden_and_empty(nb, ctx128, golden_dir):
+    ctx = ctx128[0]
+    g = np.load(os.path.join(golden_dir, "expand_kat.npz"))
+    fb = np.zeros(96, dtype=nb.FEATURE_BITBOARD)
+    fb["lo"], fb["hi"] = g["lo"], g["hi"]
+    d_fb = nb.DeviceBuffer.from_host(fb)
+    d_out = nb.DeviceBuffer(96 * 81 * 4)
+    for cf, key, shape in ((True, "nchw", (2, 48, 81)), (False, "nhwc", (2, 81, 48))):
+        ctx.extract_device(0, d_fb.ptr, 2, 48, cf, d_out.ptr)
+        ctx.await_(0)
+        assert np.array_equal(d_out.to_host(shape, np.uint32), g[key])
+    ctx.extract_device(0, d_fb.ptr, 0, 86, True, d_out.ptr)  # empty batch is a no-op
+    ctx.await_(0)
+    d_fb.free()
+    d_out.free()
+
+
+# ---- stage 1: pack ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 5, 256, 1000])
+def test_pack_bit_exact(nb, orc, synth, ctx128, n):
+    ctx = ctx128[0]
+    pos = synth.random_positions(n, seed=n)
+    d_pos = nb.DeviceBuffer.from_host(pos)
+    d_fb = nb.DeviceBuffer(n * 86 * 16)
+    ctx.pack_positions_device(0, d_pos.ptr, n, d_fb.ptr)
+    ctx.await_(0)
+    got = d_fb.to_host((n * 86,), nb.FEATURE_BITBOARD)
+    want = orc.pack(pos)
+    assert np.array_equal(got["lo"], want["lo"]) and np.array_equal(got["hi"], want["hi"])
+    d_pos.free()
+    d_fb.free()
+
+
+# ---- decode ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 64, 1000])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_decode_matches_oracle(nb, orc, synth, ctx128, n, mode):
+    ctx = ctx128[0]
+    policy, win, draw = synth.random_logits(n, seed=n)
+    off, idx = synth.random_legal_moves(n, seed=n)
+    d = [nb.DeviceBuffer.from_host(a) for a in (policy, win, draw, off, idx)]
+    d_out = nb.DeviceBuffer(max(int(off[-1]), 1) * 4)
+    d_flag = nb.DeviceBuffer(n)
+    ctx.decode_device(0, d[0].ptr, d[1].ptr, d[2].ptr, n, d[3].ptr, d[4].ptr, mode, d_out.ptr, d_flag.ptr)
+    ctx.await_(0)
+    got = d_out.to_host((int(off[-1]),), np.float32)
+    flag = d_flag.to_host((n,), np.uint8)
+    want, wflag = orc.decode(policy, win, draw, off, idx, mode)
+    assert np.array_equal(flag, wflag)
+    if mode == nb.DECODE_LOGITS:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    else:
+        assert np.allclose(got, want, rtol=TOL_DECODE_REL, atol=1e-9)
+    for b in d + [d_out, d_flag]:
+        b.free()
+
+
+# ---- forward ----------------------------------------------------------------------------------------------------
+def test_forward_golden_small_net(nb, orc, golden_dir):
+    g = np.load(os.path.join(golden_dir, "forward_small.npz"))
+    desc = nb.net_desc(128, 1)
+    blob = nb.random_blob(desc, int(g["blob_seed"]))
+    pos = np.frombuffer(g["positions"].tobytes(), dtype=nb.POSITION)
+    n = len(pos)
+    policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+    win = np.zeros(n, dtype=np.float32)
+    draw = np.zeros(n, dtype=np.float32)
+    with nb.Context(desc, batch_max=4, blob=blob) as ctx:
+        ctx.eval_positions_async(0, pos, n, policy, win, draw)
+        ctx.await_(0)
+    assert np.max(np.abs(policy - g["policy_bf16"])) < TOL_LOGIT_VS_BF16_ORACLE
+    assert np.max(np.abs(win - g["win_bf16"])) < TOL_VALUE_VS_BF16_ORACLE
+    assert np.max(np.abs(draw - g["draw_bf16"])) < TOL_VALUE_VS_BF16_ORACLE
+    assert np.max(np.abs(win - g["win_fp32"])) < TOL_VALUE_VS_FP32
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 37])
+def test_forward_matches_oracle_128(nb, orc, synth, ctx128, n):
+    ctx, desc, blob = ctx128
+    pos = synth.random_positions(n, seed=100 + n)
+    fb = orc.pack(pos)
+    policy, win, draw = run_eval(nb, ctx, fb, n)
+    planes = orc.expand(fb, n)
+    op, ow, od = orc.forward(desc, blob, planes, emulate_bf16=True)
+    assert np.max(np.abs(policy - op)) < TOL_LOGIT_VS_BF16_ORACLE
+    assert np.max(np.abs(win - ow)) < TOL_VALUE_VS_BF16_ORACLE and np.max(np.abs(draw - od)) < TOL_VALUE_VS_BF16_ORACLE
+    fp, fw, fd = orc.forward(desc, blob, planes, emulate_bf16=False)
+    off, idx = synth.random_legal_moves(n, seed=n, edge_rows=False)
+    pg, _ = orc.decode(policy, win, draw, off, idx, nb.DECODE_PROBS)
+    pf, _ = orc.decode(fp, fw, fd, off, idx, nb.DECODE_PROBS)
+    assert np.max(np.abs(pg - pf)) < TOL_PROB_VS_FP32
+    assert np.max(np.abs(win - fw)) < TOL_VALUE_VS_FP32 and np.max(np.abs(draw - fd)) < TOL_VALUE_VS_FP32
+
+
+def test_forward_fuzzed_feature_values(nb, orc, synth, ctx128):
+    """Arbitrary FeatureBitboards (random masks, rotate, fractional values, garbage bits): the
+    in-kernel expansion must follow extractbit.cu for any input, not just packed positions."""
+    ctx, desc, blob = ctx128
+    n = 9
+    fb = synth.random_feature_bitboards(n * 86, seed=77)
+    policy, win, draw = run_eval(nb, ctx, fb, n)
+    op, ow, od = orc.forward(desc, blob, orc.expand(fb, n), emulate_bf16=True)
+    assert np.max(np.abs(policy - op)) < 4 * TOL_LOGIT_VS_BF16_ORACLE  # denser inputs, larger activations
+    assert np.max(np.abs(win - ow)) < 4 * TOL_VALUE_VS_BF16_ORACLE
+
+
+def test_forward_matches_oracle_256(nb, orc, synth):
+    desc = nb.net_desc(256, 2)
+    blob = nb.random_blob(desc, 99)
+    n = 5
+    pos = synth.random_positions(n, seed=256)
+    fb = orc.pack(pos)
+    with nb.Context(desc, batch_max=8, blob=blob) as ctx:
+        policy, win, draw = run_eval(nb, ctx, fb, n)
+    op, ow, od = orc.forward(desc, blob, orc.expand(fb, n), emulate_bf16=True)
+    assert np.max(np.abs(policy - op)) < TOL_LOGIT_VS_BF16_ORACLE
+    assert np.max(np.abs(win - ow)) < TOL_VALUE_VS_BF16_ORACLE and np.max(np.abs(draw - od)) < TOL_VALUE_VS_BF16_ORACLE
+
+
+def test_fused_decode_equals_separate_decode(nb, orc, synth, ctx128):
+    """(c): gather + softmax fused into the trunk epilogue == decode of the same launch's logits."""
+    ctx, desc, blob = ctx128
+    n = 45
+    pos = synth.random_positions(n, seed=5)
+    fb = orc.pack(pos)
+    off, idx = synth.random_legal_moves(n, seed=5)
+    policy, win, draw = run_eval(nb, ctx, fb, n)
+    for mode in (nb.DECODE_PROBS, nb.DECODE_LOGITS):
+        legal = np.zeros(int(off[-1]), dtype=np.float32)
+        w2 = np.zeros(n, dtype=np.float32)
+        d2 = np.zeros(n, dtype=np.float32)
+        flag = np.ones(n, dtype=np.uint8)
+        ctx.eval_decode_async(1, fb, n, off, idx, mode, legal, w2, d2, flag)
+        ctx.await_(1)
+        want, wflag = orc.decode(policy, win, draw, off, idx, mode)
+        assert np.array_equal(w2, win) and np.array_equal(d2, draw) and np.array_equal(flag, wflag)
+        if mode == nb.DECODE_LOGITS:
+            assert np.array_equal(legal.view(np.uint32), want.view(np.uint32))
+        else:
+            assert np.allclose(legal, want, rtol=TOL_DECODE_REL, atol=1e-9)
+    # positions-in variant (stage 1 on device too)
+    legal2 = np.zeros(int(off[-1]), dtype=np.float32)
+    ctx.eval_positions_decode_async(0, pos, n, off, idx, nb.DECODE_LOGITS, legal2, w2, d2, flag)
+    ctx.await_(0)
+    assert np.array_equal(legal2.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("batch", [256, 4096])
+def test_full_size_batch_invariance(nb, orc, synth, batch):
+    """BASELINE sizes: every position's result is independent of its batch index, of the batch
+    size and of which CTA / accumulator column evaluates it (bit-exact), and equals the oracle on
+    the distinct positions.  10 x 128 net == config 2."""
+    desc = nb.net_desc(128, 10)
+    blob = nb.random_blob(desc, 1234)
+    base = 16
+    pos = synth.random_positions(base, seed=2024)
+    fb = orc.pack(pos).reshape(base, 86)
+    rng = np.random.default_rng(1)
+    perm = rng.integers(0, base, size=batch)
+    perm[:base] = np.arange(base)
+    big = np.ascontiguousarray(fb[perm].reshape(-1))
+    with nb.Context(desc, batch_max=batch, blob=blob) as ctx:
+        p_small, w_small, d_small = run_eval(nb, ctx, np.ascontiguousarray(fb.reshape(-1)), base)
+        p_big, w_big, d_big = run_eval(nb, ctx, big, batch)
+    assert np.array_equal(p_big.view(np.uint32), p_small[perm].view(np.uint32))
+    assert np.array_equal(w_big, w_small[perm]) and np.array_equal(d_big, d_small[perm])
+    op, ow, od = orc.forward(desc, blob, orc.expand(fb.reshape(-1), base), emulate_bf16=True)
+    assert np.max(np.abs(p_small - op)) < 3 * TOL_LOGIT_VS_BF16_ORACLE   # 21 layers deep
+    assert np.max(np.abs(w_small - ow)) < 3 * TOL_VALUE_VS_BF16_ORACLE
+
+
+# ---- the Infer contract ------------------------------------------------------------------------------------------
+def test_infer_interface_contract(pkg, nb, orc, synth):
+    """Reads like the reference's use of Infer/Evaluator (src/bench/batchsize.cc:47-70)."""
+    B = 128
+    desc = nb.net_desc(128, 2)
+    blob = nb.random_blob(desc, 1234)
+    infer = pkg.infer.B200(0, B, 86, desc, blob=blob)
+    infer.resetGPU()
+    ev = pkg.infer.Evaluator(B, infer)
+    fb = orc.pack(synth.startpos(B))
+    ev.getFeatureBitboards()[:] = fb
+    assert not ev.isComputing()
+    ev.computeNonBlocking(B)
+    ev.await_()
+    assert not ev.isComputing()
+    first = ev.getPolicy().copy()
+    ev.computeBlocking(B)
+    assert np.array_equal(first, ev.getPolicy())
+    pol = first.reshape(B, nb.POLICY_SIZE)
+    assert np.array_equal(pol[0], pol[B - 1])          # startpos x B -> identical rows
+    assert np.all((ev.getWinRate() > 0) & (ev.getWinRate() < 1)) and np.all((ev.getDrawRate() > 0) & (ev.getDrawRate() < 1))
+    op, ow, od = orc.forward(desc, blob, orc.expand(fb[:86], 1), emulate_bf16=True)
+    assert np.max(np.abs(pol[0] - op[0])) < TOL_LOGIT_VS_BF16_ORACLE
+    with pytest.raises(nb.NsbError):                   # BatchSize <= BatchSizeMax (trt.cc:237)
+        infer.ctx.eval_async(0, fb, B + 1, ev.getPolicy(), ev.getWinRate(), ev.getDrawRate())
+    ev.close()
+    infer.close()
+
+
+def test_errors_are_reported_not_swallowed(nb):
+    desc = nb.net_desc(128, 1)
+    with nb.Context(desc, batch_max=4) as ctx:           # no weights loaded
+        z = np.zeros(4 * 86, dtype=nb.FEATURE_BITBOARD)
+        with pytest.raises(nb.NsbError) as e:
+            ctx.eval_async(0, z, 4, np.zeros((4, 2187), np.float32), np.zeros(4, np.float32), np.zeros(4, np.float32))
+        assert "weights not loaded" in str(e.value)
+        with pytest.raises(nb.NsbError):
+            ctx.load_weights(np.zeros(10, dtype=np.float32))
+        with pytest.raises(nb.NsbError):
+            ctx.await_(3)
