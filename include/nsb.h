@@ -194,6 +194,18 @@ int nsb_event_record(void* ev, nsb_ctx* ctx, int slot);
 int nsb_event_sync(void* ev);
 int nsb_event_elapsed_ms(void* start, void* stop, float* ms);
 
+/* Diagnostics: run one trunk launch and return CTA 0's clock64 stamps, 4 per layer
+ * {MMA issue start, MMA issue end, accumulator ready (epilogue start), epilogue end}, then 8 phase
+ * stamps {entry, setup done, features expanded, features loaded, heads read, policy written, value
+ * MLP done, decode done}: 4 * layers + 8 values. */
+int nsb_debug_trunk_timeline(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* d_features, size_t n,
+                             uint64_t* host_stamps, size_t max_stamps);
+
+/* Diagnostics: issue-to-retire rate (cycles per M128 x n_cols x K16 MMA) and numerical check of one
+ * operand layout with a row-shifted B start: layout 0 = SWIZZLE_NONE 16-byte rows, 1 = SWIZZLE_128B. */
+int nsb_debug_umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters,
+                         float* max_err, double* cycles_per_mma);
+
 /* Kernel launches issued by this ctx since creation (bench "gpu_launches"). */
 uint64_t nsb_launch_count(nsb_ctx* ctx);
 
@@ -215,8 +227,10 @@ int nsb_device_count(void);
 
 /* tcgen05 self-test: one CTA runs D[128 x n_cols] = A * B^T with the K-major SWIZZLE_NONE
  * descriptors the trunk uses, B's start address moved by shift_rows 16-byte rows, and the host
- * compares against an fp32 loop.  Returns 0 and the max abs error (exact inputs: expect 0). */
-int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err);
+ * compares against an fp32 loop (max_err), then runs the trunk's epilogue path (16x256b TMEM
+ * fragments + stmatrix.trans, plain and with the skip connection) and compares the bf16 records
+ * (epi_err).  n_cols in {96, 192}.  Inputs are exact in bf16: expect 0 for both. */
+int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err, float* epi_err);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -67,6 +67,9 @@ SIGNATURES = {
     "nsb_extract_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_int, C.c_int, _P]),
     "nsb_pack_positions_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P]),
     "nsb_decode_device": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P, _P, C.c_int, _P, _P]),
+    "nsb_debug_trunk_timeline": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
+    "nsb_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_double)]),
     "nsb_stream": (_P, [_P, C.c_int]),
     "nsb_set_timing": (C.c_int, [_P, C.c_int]),
     "nsb_trunk_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -83,7 +86,7 @@ SIGNATURES = {
     "nsb_last_error": (C.c_char_p, []),
     "nsb_version": (C.c_char_p, []),
     "nsb_device_count": (C.c_int, []),
-    "nsb_umma_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "nsb_umma_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "nsb_event_create": (C.c_int, [C.POINTER(_P)]),
     "nsb_event_destroy": (C.c_int, [_P]),
     "nsb_event_record": (C.c_int, [_P, _P, C.c_int]),
@@ -193,10 +196,19 @@ def device_sync():
     _check(lib().nsb_device_sync(), "nsb_device_sync")
 
 
-def umma_selftest(n_cols: int, k_elems: int, shift_rows: int, gpu: int = 0) -> float:
-    err = C.c_float(-1.0)
-    _check(lib().nsb_umma_selftest(gpu, n_cols, k_elems, shift_rows, C.byref(err)), "nsb_umma_selftest")
-    return float(err.value)
+def umma_selftest(n_cols: int, k_elems: int, shift_rows: int, gpu: int = 0):
+    """Returns (max |D - ref|, max |epilogue record - ref|); both 0.0 when the tcgen05 path is right."""
+    err, epi = C.c_float(-1.0), C.c_float(-1.0)
+    _check(lib().nsb_umma_selftest(gpu, n_cols, k_elems, shift_rows, C.byref(err), C.byref(epi)),
+           "nsb_umma_selftest")
+    return float(err.value), float(epi.value)
+
+
+def umma_probe(n_cols, k_elems, shift_rows, layout, iters=20, gpu=0):
+    err, cyc = C.c_float(-1.0), C.c_double(0)
+    _check(lib().nsb_debug_umma_probe(gpu, n_cols, k_elems, shift_rows, layout, iters, C.byref(err), C.byref(cyc)),
+           "nsb_debug_umma_probe")
+    return float(err.value), float(cyc.value)
 
 
 class Event:
@@ -309,6 +321,13 @@ class Context:
     def decode_device(self, slot, d_policy, d_win, d_draw, n, d_off, d_idx, mode, d_legal, d_flag):
         _check(lib().nsb_decode_device(self._h, slot, _ptr(d_policy), _ptr(d_win), _ptr(d_draw), n, _ptr(d_off),
                                        _ptr(d_idx), mode, _ptr(d_legal), _ptr(d_flag)), "nsb_decode_device")
+
+    def debug_trunk_timeline(self, slot, d_features, n):
+        nl = 2 * self.desc.blocks + 2
+        out = np.zeros(nl * 4 + 16, dtype=np.uint64)
+        _check(lib().nsb_debug_trunk_timeline(self._h, slot, _ptr(d_features), n, out.ctypes.data, out.size),
+               "nsb_debug_trunk_timeline")
+        return out[:nl * 4].reshape(nl, 4), out[nl * 4:]
 
     def stream(self, slot=0) -> int:
         return lib().nsb_stream(self._h, slot) or 0

@@ -482,6 +482,48 @@ int nsb_eval_decode_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_f
     return run_trunk(c, c->slots[slot], a);
 }
 
+int nsb_debug_trunk_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n,
+                             uint64_t* host_stamps, size_t max_stamps) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if (!c->loaded || !d_features || !host_stamps || n == 0) {
+        set_error("nsb_debug_trunk_timeline: bad arguments or weights not loaded");
+        return NSB_ERR_INVALID;
+    }
+    const size_t need = (size_t)c->net.num_layers * 4 + 16;
+    if (max_stamps < need) {
+        set_error("nsb_debug_trunk_timeline: need room for %zu stamps", need);
+        return NSB_ERR_INVALID;
+    }
+    Slot& s = c->slots[slot];
+    unsigned long long* d_t = nullptr;
+    NSB_CUDA(cudaMalloc(&d_t, need * 8));
+    NSB_CUDA(cudaMemsetAsync(d_t, 0, need * 8, s.stream));
+    EvalArgs a{};
+    a.features = d_features;
+    a.n = (int)n;
+    a.policy = s.d_policy;
+    a.win = s.d_win;
+    a.draw = s.d_draw;
+    a.timeline = d_t;
+    if (n > (size_t)c->batch_max) {
+        cudaFree(d_t);
+        set_error("nsb_debug_trunk_timeline: n exceeds batch_max");
+        return NSB_ERR_INVALID;
+    }
+    rc = run_trunk(c, s, a);
+    if (rc == 0) {
+        cudaError_t e = cudaStreamSynchronize(s.stream);
+        if (e == cudaSuccess) e = cudaMemcpy(host_stamps, d_t, need * 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_error("nsb_debug_trunk_timeline: %s", cudaGetErrorString(e));
+            rc = NSB_ERR_CUDA;
+        }
+    }
+    cudaFree(d_t);
+    return rc;
+}
+
 int nsb_extract_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n, int channels,
                        int channels_first, float* d_planes) {
     int rc = check_ctx(c, slot);
@@ -603,8 +645,13 @@ int nsb_device_sync(void) {
     return 0;
 }
 
-int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err) {
-    return umma_selftest(gpu, n_cols, k_elems, shift_rows, max_err);
+int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err, float* epi_err) {
+    return umma_selftest(gpu, n_cols, k_elems, shift_rows, max_err, epi_err);
+}
+
+int nsb_debug_umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters, float* max_err,
+                         double* cycles_per_mma) {
+    return umma_probe(gpu, n_cols, k_elems, shift_rows, layout, iters, max_err, cycles_per_mma);
 }
 
 int nsb_event_create(void** out) {

@@ -40,7 +40,7 @@ struct TrunkGeom {
     static constexpr int OFF_FEAT = OFF_SCRATCH + ((SCRATCH_FLOATS * 4 + 15) / 16) * 16;
     static constexpr int OFF_VBUF = OFF_FEAT + NPOS * NSB_FEATURE_CHANNELS * 16;
     static constexpr int OFF_RED = OFF_VBUF + ((NPOS * 81 * 4 + 15) / 16) * 16;
-    static constexpr int OFF_BARS = OFF_RED + 4 * NPOS * 2 * 4 + 16;
+    static constexpr int OFF_BARS = OFF_RED + ((8 * NPOS * 2 * 4 + NPOS * 2 * 4 + 15) / 16) * 16;
     static constexpr int SMEM_BYTES = OFF_BARS + (2 * NSTAGES + 2) * 8 + 16 + 128; // + align slack
     static_assert(NCOLS % 16 == 0 && NCOLS <= 256, "UMMA N");
     static_assert(NHALF * NCOLS <= TMEM_COLS, "TMEM columns");
@@ -74,6 +74,7 @@ struct EvalArgs {
     float* legal_out;
     uint8_t* nan_flag;
     int decode_mode;
+    unsigned long long* timeline;  // optional (diagnostics): CTA 0 writes 4 clock64 stamps per layer
 };
 
 // host-side weight handling (weights.cc)
@@ -94,7 +95,9 @@ int launch_decode(const float* d_policy, const float* d_win, const float* d_draw
                   uint8_t* d_flag, cudaStream_t s);
 int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s);
 int trunk_fused_prepare(int channels);  // sets max dynamic smem attribute
-int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err);
+int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters, float* max_err,
+               double* cycles_per_mma);
+int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err, float* epi_err);
 
 void set_error(const char* fmt, ...);
 

@@ -15,13 +15,16 @@
 // SAME buffer with the descriptor start address moved by 10*dh + dw rows: im2col costs nothing.
 // Weights stream from L2 through a 6-deep ring of 16 KB tiles filled by the bulk-copy engine.
 //
-// Warp roles (256 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner,
-// warps 4-7 = feature expansion, epilogues (TMEM -> bias/residual/ReLU -> bf16 -> smem), heads.
+// Warp roles (384 threads): warp 0 = weight producer, warp 1 = MMA issuer + TMEM owner,
+// warps 4-11 = feature expansion, epilogues (TMEM -> bias/residual/ReLU -> bf16 -> smem via
+// stmatrix, epilogue.cuh), heads.  Two epilogue warps share each TMEM lane quadrant and split the
+// columns (C = 128: one position each) or the Cout halves (C = 256).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "decode_device.cuh"
+#include "epilogue.cuh"
 #include "nsb_internal.h"
 #include "umma.cuh"
 
@@ -29,23 +32,55 @@ namespace nsb {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kEpiThreads = 128;
-constexpr uint32_t kEpiBar = 1;  // named barrier id for the 4 epilogue warps
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = kEpiThreads / 32;
+constexpr uint32_t kEpiBar = 1;  // named barrier id for the 8 epilogue warps
 
-__host__ __device__ constexpr bool is_real_slot(int n) {
-    // slot n = 100*pos + 10*row + col; column 9 and row 9 are the permanent zero padding
-    return (n % 100) < 90 && ((n % 100) % 10) < 9;
+constexpr int kStemChunks = 12;  // stem K = 96 input channels (86 real), 6 K=16 steps
+
+// One FeatureBitboard (reference src/cuda/extractbit.cu:20-37) -> {w0, w1, w2, value}: bit t of
+// the 81-bit string w2:w1:w0 is the plane's value at output position t (rotation applied), and
+// `value` is the fp32 fill value rounded to bf16 bits.  Squares 0..62 live in lo bits 0..62,
+// squares 63..80 in hi bits 0..17; every other bit of the input is ignored.
+__device__ __forceinline__ uint4 plane_bits(uint4 f) {
+    uint32_t s0 = f.x;
+    uint32_t s1 = (f.y & 0x7FFFFFFFu) | (f.z << 31);
+    uint32_t s2 = (f.z >> 1) & 0x1FFFFu;
+    if ((f.z >> 24) & 1u) {  // rotate: out[t] = in[80 - t]  == (96-bit reversal) >> 15
+        const uint32_t r0 = __brev(s2), r1 = __brev(s1), r2 = __brev(s0);
+        s0 = __funnelshift_r(r0, r1, 15);
+        s1 = __funnelshift_r(r1, r2, 15);
+        s2 = r2 >> 15;
+    }
+    return make_uint4(s0, s1, s2, (uint32_t)f32_to_bf16_bits(__uint_as_float(f.w)));
 }
 
-__device__ __forceinline__ uint32_t expand_bits(uint4 f, int t) {
-    // reference src/cuda/extractbit.cu:20-37 on one (plane, t): fp32 bit pattern or 0
-    const uint64_t lo = ((uint64_t)f.y << 32) | f.x, hi = ((uint64_t)f.w << 32) | f.z;
-    const int rotate = (int)((hi >> 24) & 1ull);
-    const int sq = rotate ? 80 - t : t;
-    const int use_hi = sq >= 63;
-    const uint64_t word = use_hi ? hi : lo;
-    return ((uint32_t)(word >> (sq - 63 * use_hi)) & 1u) * (uint32_t)(hi >> 32);
+constexpr int kFcPrefetch = 27;
+
+// Head accumulator: this warp's lanes 0..6 = head channels hp = 7q + lane (0..26 policy planes,
+// 27 = value conv) for the 96 columns from COL0 (compile-time: slot -> square arithmetic folds).
+template <int COL0>
+__device__ __forceinline__ void head_read(uint32_t taddr, float bias, int hp, float* scratch, float* vbuf, int lane) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        uint32_t v[32];
+        tmem_ld32(taddr + COL0 + j * 32, v);
+        tmem_ld_wait();
+        if (lane < 7) {
+            float* dst = hp < kPolicyPlanes ? scratch + hp * 81 : vbuf;
+            const bool relu = hp == kPolicyPlanes;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int n = COL0 + j * 32 + i;
+                if (is_real_slot(n)) {
+                    const int pos = n / 100, m = n % 100, t = (m / 10) * 9 + (m % 10);
+                    const float x = __uint_as_float(v[i]) + bias;
+                    dst[(relu ? pos * 81 : pos * kPolicySize) + t] = relu ? fmaxf(x, 0.f) : x;  // plane-major logits
+                }
+            }
+        }
+    }
 }
 
 template <int C>
@@ -59,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
     float* scratch = reinterpret_cast<float*>(smem + G::OFF_SCRATCH);
     uint4* featS = reinterpret_cast<uint4*>(smem + G::OFF_FEAT);
     float* vbuf = reinterpret_cast<float*>(smem + G::OFF_VBUF);
-    float* red = reinterpret_cast<float*>(smem + G::OFF_RED);  // [4][NPOS][2] + wd[NPOS][2]
+    float* red = reinterpret_cast<float*>(smem + G::OFF_RED);  // [8][NPOS][2] + wd[NPOS][2]
     const uint32_t bars = sbase + G::OFF_BARS;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_empty = [&](int s) { return bars + 8u * (G::NSTAGES + s); };
@@ -74,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
         (int)blockIdx.x < groups ? (groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int NL = net.num_layers;
 
+    if (a.timeline && blockIdx.x == 0 && threadIdx.x == 128) a.timeline[4 * NL + 0] = clock64();
     // ---- one-time setup ---------------------------------------------------------------------
     for (int i = threadIdx.x; i < 2 * G::BUF_BYTES / 16; i += kThreads)
         reinterpret_cast<uint4*>(smem + G::OFF_BUF_A)[i] = make_uint4(0, 0, 0, 0);
@@ -92,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    if (a.timeline && blockIdx.x == 0 && threadIdx.x == 128) a.timeline[4 * NL + 1] = clock64();
 
     if (warp == 0) {
         // ===== weight producer: linear stream of 16 KB tiles, re-walked once per pass ==========
@@ -108,149 +145,164 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread drives the tensor core ====================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16_f32(128, G::NCOLS);
-            constexpr uint32_t b_lbo = G::SPITCH * 16;
-            uint32_t stage = 0, phase = 0, act_phase = 0;
-            for (int p = 0; p < my_passes; ++p) {
-                for (int L = 0; L < NL; ++L) {
-                    mbar_wait(bar_act, act_phase);
-                    act_phase ^= 1u;
-                    tc_fence_after();
-                    const bool head = (L == NL - 1);
-                    const uint32_t in_buf = (L & 1) ? bufA : bufB;
-                    const int ntaps = head ? 1 : 9;
-                    const int kblocks = (L == 0) ? kStemCin / 64 : G::KC64;
-                    const int nh = head ? 1 : G::NHALF;
-                    for (int tap = 0; tap < ntaps; ++tap) {
-                        const int shift = head ? 0 : (tap / 3 - 1) * 10 + (tap % 3 - 1);
-                        for (int kc = 0; kc < kblocks; ++kc) {
-                            for (int half = 0; half < nh; ++half) {
-                                mbar_wait(bar_full(stage), phase);
-                                tc_fence_after();
+        // ===== MMA issuer: the whole warp walks the loop (warp-uniform control flow and operands),
+        // one elected lane issues the tcgen05 instructions =======================================
+        constexpr uint32_t idesc = make_idesc_bf16_f32(128, G::NCOLS);
+        constexpr uint32_t b_lbo = G::SPITCH * 16;
+        uint32_t stage = 0, phase = 0, act_phase = 0;
+        for (int p = 0; p < my_passes; ++p) {
+            for (int L = 0; L < NL; ++L) {
+                mbar_wait(bar_act, act_phase);
+                act_phase ^= 1u;
+                tc_fence_after();
+                if (a.timeline && blockIdx.x == 0 && p == 0 && lane == 0) a.timeline[4 * L + 0] = clock64();
+                const bool head = (L == NL - 1);
+                const uint32_t in_buf = (L & 1) ? bufA : bufB;
+                const int ntaps = head ? 1 : 9;
+                const int kblocks = (L == 0) ? kStemCin / 64 : G::KC64;
+                const int nh = head ? 1 : G::NHALF;
+                for (int tap = 0; tap < ntaps; ++tap) {
+                    const int shift = head ? 0 : (tap / 3 - 1) * 10 + (tap % 3 - 1);
+                    for (int kc = 0; kc < kblocks; ++kc) {
+                        const uint32_t b_base = in_buf + (uint32_t)((kc * 8 * G::SPITCH + G::GUARD + shift) * 16);
+                        for (int half = 0; half < nh; ++half) {
+                            mbar_wait(bar_full(stage), phase);
+                            tc_fence_after();
+                            const int ksteps = (L == 0 && kc == 1) ? (kStemChunks - 8) / 2 : 4;
+                            if (elect_one()) {
                                 const uint32_t a_base = ring + stage * kStageBytes;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
+                                    if (k >= ksteps) break;
                                     const uint64_t adesc = make_smem_desc(a_base + k * 4096, 2048, 128);
-                                    const uint32_t b_addr =
-                                        in_buf + (uint32_t)(((kc * 8 + 2 * k) * G::SPITCH + G::GUARD + shift) * 16);
-                                    const uint64_t bdesc = make_smem_desc(b_addr, b_lbo, 128);
+                                    const uint64_t bdesc =
+                                        make_smem_desc(b_base + (uint32_t)(2 * k * G::SPITCH * 16), b_lbo, 128);
                                     umma_bf16(tmem_base + half * G::NCOLS, adesc, bdesc, idesc,
                                               (uint32_t)((tap | kc | k) != 0));
                                 }
                                 umma_commit(bar_empty(stage));  // frees the ring slot when the MMAs retire
-                                if (++stage == G::NSTAGES) { stage = 0; phase ^= 1u; }
                             }
+                            __syncwarp();
+                            if (++stage == G::NSTAGES) { stage = 0; phase ^= 1u; }
                         }
                     }
-                    umma_commit(bar_acc);  // accumulator(s) of layer L complete
                 }
+                if (elect_one()) umma_commit(bar_acc);  // accumulator(s) of layer L complete
+                __syncwarp();
+                if (a.timeline && blockIdx.x == 0 && p == 0 && lane == 0) a.timeline[4 * L + 1] = clock64();
             }
         }
     } else if (warp >= 4) {
         // ===== expansion + epilogues + heads =====================================================
-        const int et = threadIdx.x - 128;  // 0..127
-        const int q = warp - 4;            // TMEM lane quadrant (== warp % 4)
+        const int et = threadIdx.x - 128;  // 0..255
+        const int ew = warp - 4;           // 0..7
+        const int q = ew & 3;              // TMEM lane quadrant (== warp % 4)
+        const int part = ew >> 2;          // C=128: column half (= position); C=256: Cout half
+        const int e_col0 = (C == 128) ? 96 * part : 0;
+        const int e_half = (C == 128) ? 0 : part;
+        if (a.timeline && blockIdx.x == 0 && et == 0) a.timeline[4 * NL + 11] = clock64();
+        EpilogueMask<3> realmask;
+        realmask.init(e_col0, lane);
         uint32_t acc_phase = 0;
         for (int p = 0; p < my_passes; ++p) {
             const int b0 = ((int)blockIdx.x + p * (int)gridDim.x) * G::NPOS;
 
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
+            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 8] = clock64();
+            // Per plane: the 81 occupancy bits as one contiguous little-endian bit string with the
+            // rotation (extractbit.cu:20,26) already applied, plus the fill value as bf16 bits.
             for (int i = et; i < G::NPOS * NSB_FEATURE_CHANNELS; i += kEpiThreads) {
                 const int pos = i / NSB_FEATURE_CHANNELS, c = i - pos * NSB_FEATURE_CHANNELS;
                 const int b = b0 + pos;
-                featS[i] = b < a.n ? __ldg(reinterpret_cast<const uint4*>(a.features) +
-                                           (size_t)b * NSB_FEATURE_CHANNELS + c)
-                                   : make_uint4(0, 0, 0, 0);
+                uint4 f = make_uint4(0, 0, 0, 0);
+                if (b < a.n) f = __ldg(reinterpret_cast<const uint4*>(a.features) + (size_t)b * NSB_FEATURE_CHANNELS + c);
+                featS[i] = plane_bits(f);
             }
+            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 9] = clock64();
             named_bar_sync(kEpiBar, kEpiThreads);
-            for (int item = et; item < G::NPOS * (kStemCin / 8) * 81; item += kEpiThreads) {
-                const int pos = item / ((kStemCin / 8) * 81);
-                const int r = item - pos * ((kStemCin / 8) * 81);
-                const int j = r / 81, t = r - j * 81;
-                const int slot = pos * 100 + (t / 9) * 10 + (t % 9);
-                uint32_t w[4];
+            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 3] = clock64();
+            // The stem reads 96 input channels = 12 chunks of 8 (86 real + zero padding).  One work
+            // item = (position, chunk, board row): the 8 planes' bit strings are loaded once, the
+            // row's 9-bit field is cut out with a funnel shift, and 9 records of 16 B are written.
+            for (int item = et; item < G::NPOS * kStemChunks * 9; item += kEpiThreads) {
+                const int pos = item / (kStemChunks * 9);
+                const int r2 = item - pos * (kStemChunks * 9);
+                const int j = r2 / 9, row = r2 - j * 9;
+                const int bit0 = 9 * row, wi = bit0 >> 5, sh = bit0 & 31;
+                uint32_t field[8], val[8];
 #pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                    uint32_t pk = 0;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int c = j * 8 + e2 * 2 + h;
-                        uint32_t bits = 0;
-                        if (c < NSB_FEATURE_CHANNELS)
-                            bits = f32_to_bf16_bits(__uint_as_float(expand_bits(featS[pos * NSB_FEATURE_CHANNELS + c], t)));
-                        pk |= bits << (16 * h);
-                    }
-                    w[e2] = pk;
+                for (int e = 0; e < 8; ++e) {
+                    const int c = j * 8 + e;
+                    uint4 f = make_uint4(0, 0, 0, 0);
+                    if (c < NSB_FEATURE_CHANNELS) f = featS[pos * NSB_FEATURE_CHANNELS + c];
+                    const uint32_t lo = wi == 0 ? f.x : (wi == 1 ? f.y : f.z);
+                    const uint32_t hi = wi == 0 ? f.y : (wi == 1 ? f.z : 0u);
+                    field[e] = __funnelshift_r(lo, hi, sh);
+                    val[e] = f.w;
                 }
-                *reinterpret_cast<uint4*>(smem + G::OFF_BUF_B + (size_t)((j * G::SPITCH + G::GUARD + slot) * 16)) =
-                    make_uint4(w[0], w[1], w[2], w[3]);
+                uint8_t* dst = smem + G::OFF_BUF_B + (size_t)((j * G::SPITCH + G::GUARD + pos * 100 + row * 10) * 16);
+#pragma unroll
+                for (int col = 0; col < 9; ++col) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        const uint32_t a0 = val[2 * e2] & (0u - ((field[2 * e2] >> col) & 1u));
+                        const uint32_t a1 = val[2 * e2 + 1] & (0u - ((field[2 * e2 + 1] >> col) & 1u));
+                        w[e2] = a0 | (a1 << 16);
+                    }
+                    *reinterpret_cast<uint4*>(dst + col * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
             }
+            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 10] = clock64();
             fence_proxy_async_smem();
             mbar_arrive(bar_act);
+            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 2] = clock64();
 
             // -- conv layers: TMEM -> +bias (+skip) -> ReLU -> bf16 -> next layer's B operand ----
             for (int L = 0; L < NL - 1; ++L) {
+                float bias[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    bias[k] = __ldg(net.bias + (size_t)L * C + e_half * 128 + q * 32 + 8 * k + (lane >> 2));
                 mbar_wait(bar_acc, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                uint8_t* out_buf = smem + ((L & 1) ? G::OFF_BUF_B : G::OFF_BUF_A);
+                if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * L + 2] = clock64();
+                const uint32_t out_buf = ((L & 1) ? bufB : bufA) + G::GUARD * 16;
                 const bool residual = (L >= 2) && ((L & 1) == 0);
-#pragma unroll
-                for (int half = 0; half < G::NHALF; ++half) {
-                    const int co = half * 128 + et;
-                    const float bias = __ldg(net.bias + (size_t)L * C + co);
-                    uint8_t* row = out_buf + (size_t)(((co >> 3) * G::SPITCH + G::GUARD) * 16 + (co & 7) * 2);
-#pragma unroll
-                    for (int j = 0; j < G::NCOLS / 32; ++j) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + half * G::NCOLS + j * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int n = j * 32 + i;
-                            if (is_real_slot(n)) {
-                                uint16_t* dst = reinterpret_cast<uint16_t*>(row + n * 16);
-                                float x = __uint_as_float(v[i]) + bias;
-                                if (residual) x += bf16_bits_to_f32(*dst);
-                                *dst = f32_to_bf16_bits(fmaxf(x, 0.f));
-                            }
-                        }
-                    }
-                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + e_half * G::NCOLS + e_col0;
+                const int chunk0 = e_half * 16 + q * 4;
+                if (residual)
+                    epilogue_warp<3, true>(taddr, out_buf, G::SPITCH * 16, chunk0, e_col0, bias, realmask, lane);
+                else
+                    epilogue_warp<3, false>(taddr, out_buf, G::SPITCH * 16, chunk0, e_col0, bias, realmask, lane);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 mbar_arrive(bar_act);
+                if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * L + 3] = clock64();
             }
 
-            // -- heads: rows 0..26 of the accumulator = policy planes, row 27 = value conv --------
+            // -- heads: accumulator row 32*(h/7) + h%7 holds head channel h (0..26 policy planes,
+            //    27 = value conv), i.e. 7 useful lanes in every TMEM quadrant, so all epilogue warps help
+            const int H = net.hidden;
+            const int hp = 7 * q + lane;
+            const float hbias = lane < 7 ? __ldg(net.bias + (size_t)(NL - 1) * C + hp) : 0.f;
+            float wpre[kFcPrefetch];  // first FC1 weights, requested before the accumulator wait
+#pragma unroll
+            for (int t = 0; t < kFcPrefetch; ++t) wpre[t] = et < H ? __ldg(net.fc1t + (size_t)t * H + et) : 0.f;
             mbar_wait(bar_acc, acc_phase);
             acc_phase ^= 1u;
             tc_fence_after();
-            if (q == 0) {
-                const float bias = lane <= kPolicyPlanes ? __ldg(net.bias + (size_t)(NL - 1) * C + lane) : 0.f;
-#pragma unroll
-                for (int j = 0; j < G::NCOLS / 32; ++j) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + j * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int n = j * 32 + i;
-                        if (is_real_slot(n)) {
-                            const int pos = n / 100, m = n % 100, t = (m / 10) * 9 + (m % 10);
-                            const float x = __uint_as_float(v[i]) + bias;
-                            if (lane < kPolicyPlanes)
-                                scratch[pos * kPolicySize + lane * 81 + t] = x;  // plane-major logits
-                            else if (lane == kPolicyPlanes)
-                                vbuf[pos * 81 + t] = fmaxf(x, 0.f);
-                        }
-                    }
-                }
+            if (C == 128 || part == 0) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+                if (part == 0)
+                    head_read<0>(taddr, hbias, hp, scratch, vbuf, lane);
+                else
+                    head_read<96>(taddr, hbias, hp, scratch, vbuf, lane);
                 tc_fence_before();
             }
             named_bar_sync(kEpiBar, kEpiThreads);
+            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 4] = clock64();
 
             if (a.policy != nullptr) {  // dense logits (the Infer contract, trt.cc:265-267)
                 for (int idx = et; idx < G::NPOS * kPolicySize; idx += kEpiThreads) {
@@ -258,27 +310,34 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
                     if (b < a.n) a.policy[(size_t)b * kPolicySize + (idx - pos * kPolicySize)] = scratch[idx];
                 }
             }
-            {   // value MLP: FC(81 -> H) + ReLU, FC(H -> 2), sigmoid
-                const int H = net.hidden;
+            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 5] = clock64();
+            {   // value MLP: FC(81 -> H) + ReLU, FC(H -> 2), sigmoid; one hidden unit per thread
                 float o[G::NPOS][2];
 #pragma unroll
                 for (int pos = 0; pos < G::NPOS; ++pos) o[pos][0] = o[pos][1] = 0.f;
-                for (int h = et; h < H; h += kEpiThreads) {
+                if (et < H) {
+                    const int h = et;
                     float acc[G::NPOS];
                     const float b1 = __ldg(net.fc1b + h);
+                    const float w0 = __ldg(net.fc2 + h), w1 = __ldg(net.fc2 + H + h);
 #pragma unroll
                     for (int pos = 0; pos < G::NPOS; ++pos) acc[pos] = b1;
-                    for (int t = 0; t < 81; ++t) {
-                        const float w = __ldg(net.fc1t + (size_t)t * H + h);
 #pragma unroll
-                        for (int pos = 0; pos < G::NPOS; ++pos) acc[pos] += w * vbuf[pos * 81 + t];
+                    for (int t0 = 0; t0 < 81; t0 += kFcPrefetch) {
+                        float w[kFcPrefetch];
+#pragma unroll
+                        for (int t = 0; t < kFcPrefetch; ++t)
+                            w[t] = t0 == 0 ? wpre[t] : __ldg(net.fc1t + (size_t)(t0 + t) * H + h);
+#pragma unroll
+                        for (int t = 0; t < kFcPrefetch; ++t)
+#pragma unroll
+                            for (int pos = 0; pos < G::NPOS; ++pos) acc[pos] += w[t] * vbuf[pos * 81 + t0 + t];
                     }
-                    const float w0 = __ldg(net.fc2 + h), w1 = __ldg(net.fc2 + H + h);
 #pragma unroll
                     for (int pos = 0; pos < G::NPOS; ++pos) {
                         const float hid = fmaxf(acc[pos], 0.f);
-                        o[pos][0] += w0 * hid;
-                        o[pos][1] += w1 * hid;
+                        o[pos][0] = w0 * hid;
+                        o[pos][1] = w1 * hid;
                     }
                 }
 #pragma unroll
@@ -286,41 +345,46 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const float s = warp_sum(o[pos][k]);
-                        if (lane == 0) red[(q * G::NPOS + pos) * 2 + k] = s;
+                        if (lane == 0) red[(ew * G::NPOS + pos) * 2 + k] = s;
                     }
                 named_bar_sync(kEpiBar, kEpiThreads);
                 if (et < G::NPOS * 2) {
                     const int pos = et >> 1, k = et & 1;
                     float s = __ldg(net.fc2b + k);
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) s += red[(qq * G::NPOS + pos) * 2 + k];
+                    for (int qq = 0; qq < kEpiWarps; ++qq) s += red[(qq * G::NPOS + pos) * 2 + k];
                     const float val = 1.0f / (1.0f + expf(-s));
-                    red[4 * G::NPOS * 2 + pos * 2 + k] = val;
+                    red[kEpiWarps * G::NPOS * 2 + pos * 2 + k] = val;
                     const int b = b0 + pos;
                     if (b < a.n) (k == 0 ? a.win : a.draw)[b] = val;
                 }
             }
+            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 6] = clock64();
             if (a.move_off != nullptr) {  // fused decode on logits that never left shared memory
                 named_bar_sync(kEpiBar, kEpiThreads);
-                if (q < G::NPOS) {
-                    const int b = b0 + q;
+                if (ew < G::NPOS) {
+                    const int b = b0 + ew;
                     if (b < a.n) {
                         const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
-                        const bool bad = warp_decode_row(scratch + q * kPolicySize, a.move_idx + mb, (int)(me - mb),
-                                                         a.decode_mode, red[4 * G::NPOS * 2 + q * 2 + 0],
-                                                         red[4 * G::NPOS * 2 + q * 2 + 1], a.legal_out + mb, lane);
+                        const bool bad = warp_decode_row(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
+                                                         a.decode_mode, red[kEpiWarps * G::NPOS * 2 + ew * 2 + 0],
+                                                         red[kEpiWarps * G::NPOS * 2 + ew * 2 + 1], a.legal_out + mb, lane);
                         if (a.nan_flag && lane == 0) a.nan_flag[b] = bad ? 1 : 0;
                     }
                 }
             }
             named_bar_sync(kEpiBar, kEpiThreads);  // scratch / vbuf / red reusable
+            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 7] = clock64();
         }
     }
 
     // ---- teardown -------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, G::TMEM_COLS);
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, G::TMEM_COLS);
+    }
 }
 
 }  // namespace

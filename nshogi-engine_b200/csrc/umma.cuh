@@ -12,6 +12,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// One lane of the (fully converged) warp; the blessed idiom for single-thread tcgen05 issue: the
+// compiler keeps warp-uniform operands in uniform registers instead of waterfall-looping R2UR.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -134,6 +146,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+}
+// TMEM -> registers, 16 lanes x 32 columns in the mma C-fragment layout (shape .16x256b, x4):
+// for column group g (8 columns each), thread t holds
+//   v[4g+0], v[4g+1] = (lane t/4    , columns 8g + 2(t%4), +1)
+//   v[4g+2], v[4g+3] = (lane t/4 + 8, columns 8g + 2(t%4), +1)
+// which is exactly the fragment stmatrix / ldmatrix (.trans) move to and from shared memory.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// Four 8x8 b16 matrices, transposed on the way: memory row i of matrix k is the 16-byte record
+// at the address supplied by lane 8k+i and receives column i of the register fragment.
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2,
+                                                  uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                 "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+                 : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                                  uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// ReLU fused into the conversion: negative inputs (and NaN) become +0.
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");

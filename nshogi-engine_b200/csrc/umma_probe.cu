@@ -1,0 +1,185 @@
+// umma_probe.cu — microbenchmark + correctness probe for operand layouts of tcgen05.mma
+// (diagnostics, not on the product path): measures the issue-to-retire rate of M128 x N x K16
+// MMAs for (a) the SWIZZLE_NONE 16-byte-row layout with a row-shifted B start and (b) the
+// SWIZZLE_128B layout (128-byte rows) with a row-shifted B start, and checks (b) numerically.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "nsb_internal.h"
+#include "umma.cuh"
+
+namespace nsb {
+namespace {
+
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;            // LBO (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;  // SBO: 8 rows x 128 B
+    d |= 1ull << 46;
+    d |= 2ull << 61;                   // SWIZZLE_128B
+    return d;
+}
+
+// layout 0: [k/8][row][8] (pitch rows), layout 1: [k/64][row][64] with 16-byte chunks XOR (row & 7)
+__device__ __forceinline__ uint32_t elem_off(int layout, int r, int k, int pitch_rows) {
+    if (layout == 0) return (uint32_t)(((k >> 3) * pitch_rows + r) * 16 + (k & 7) * 2);
+    const int kc = k >> 6, c = (k >> 3) & 7;
+    return (uint32_t)(kc * pitch_rows * 128 + r * 128 + ((c ^ (r & 7)) << 4) + (k & 7) * 2);
+}
+
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, int N, int K, int rows,
+                  int shift, int layout, int iters, float* __restrict__ d, unsigned long long* __restrict__ cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int a_rows = 128, b_rows = (rows + 7) & ~7;
+    const size_t a_bytes = (size_t)a_rows * K * 2, b_bytes = (size_t)b_rows * K * 2;
+    uint8_t* sa = smem;
+    uint8_t* sb = sa + ((a_bytes + 1023) & ~(size_t)1023);
+    uint8_t* tail = sb + ((b_bytes + 1023) & ~(size_t)1023);
+    const uint32_t bar = smem_u32(tail);
+    volatile uint32_t* holder = reinterpret_cast<volatile uint32_t*>(tail + 8);
+    for (int i = threadIdx.x; i < 128 * K; i += blockDim.x)
+        *reinterpret_cast<uint16_t*>(sa + elem_off(layout, i / K, i % K, a_rows)) = a[i];
+    for (int i = threadIdx.x; i < rows * K; i += blockDim.x)
+        *reinterpret_cast<uint16_t*>(sb + elem_off(layout, i / K, i % K, b_rows)) = b[i];
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    fence_proxy_async_smem();
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(holder)), 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *holder;
+    if (warp == 0) {   // warp-uniform loop, elected lane issues (same idiom as the trunk)
+        const uint32_t idesc = make_idesc_bf16_f32(128, N);
+        uint32_t parity = 0;
+        const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
+        for (int it = 0; it < iters + 1; ++it) {
+            const unsigned long long t0 = clock64();
+            const int reps = it == 0 ? 1 : 16;
+            for (int rep = 0; rep < reps; ++rep) {
+                if (elect_one()) {
+                    for (int k16 = 0; k16 < K / 16; ++k16) {
+                        uint64_t ad, bd;
+                        if (layout == 0) {
+                            ad = make_smem_desc(a0 + (uint32_t)(k16 * 2 * a_rows * 16), a_rows * 16, 128);
+                            bd = make_smem_desc(b0 + (uint32_t)((k16 * 2 * b_rows + shift) * 16), b_rows * 16, 128);
+                        } else {
+                            const int kc = k16 >> 2, kk = k16 & 3;
+                            ad = make_desc_sw128(a0 + (uint32_t)(kc * a_rows * 128 + kk * 32));
+                            bd = make_desc_sw128(b0 + (uint32_t)(kc * b_rows * 128 + shift * 128 + kk * 32));
+                        }
+                        umma_bf16(tmem_base, ad, bd, idesc, (it == 0 && rep == 0 && k16 == 0) ? 0u : 1u);
+                    }
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(bar);
+            __syncwarp();
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            const unsigned long long t1 = clock64();
+            if (threadIdx.x == 0) {
+                if (it == 1) cycles[0] = 0;
+                if (it >= 1) cycles[0] += t1 - t0;
+            }
+        }
+    }
+    // only the first iteration's result is checked: re-run it cleanly after timing
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16_f32(128, N);
+        for (int k16 = 0; k16 < K / 16; ++k16) {
+            uint64_t ad, bd;
+            if (layout == 0) {
+                ad = make_smem_desc(smem_u32(sa) + (uint32_t)(k16 * 2 * a_rows * 16), a_rows * 16, 128);
+                bd = make_smem_desc(smem_u32(sb) + (uint32_t)((k16 * 2 * b_rows + shift) * 16), b_rows * 16, 128);
+            } else {
+                const int kc = k16 >> 2, kk = k16 & 3;
+                ad = make_desc_sw128(smem_u32(sa) + (uint32_t)(kc * a_rows * 128 + kk * 32));
+                bd = make_desc_sw128(smem_u32(sb) + (uint32_t)(kc * b_rows * 128 + shift * 128 + kk * 32));
+            }
+            umma_bf16(tmem_base, ad, bd, idesc, k16 != 0);
+        }
+        umma_commit(bar);
+        mbar_wait(bar, (uint32_t)((iters + 1) & 1));
+    }
+    __syncthreads();
+    tc_fence_after();
+    for (int j = 0; j < N / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[(size_t)threadIdx.x * N + j * 32 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace
+
+int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters, float* max_err,
+               double* cycles_per_mma) {
+    if (n_cols % 32 || n_cols < 32 || n_cols > 256 || k_elems % 64 || k_elems <= 0 || shift_rows < 0 ||
+        shift_rows > 64 || iters < 1 || (layout != 0 && layout != 1)) {
+        set_error("umma_probe: bad arguments");
+        return NSB_ERR_INVALID;
+    }
+    if (cudaSetDevice(gpu) != cudaSuccess) return NSB_ERR_NO_DEVICE;
+    const int N = n_cols, K = k_elems, rows = N + shift_rows + 8;
+    std::vector<uint16_t> ha((size_t)128 * K), hb((size_t)rows * K);
+    std::vector<float> fa(ha.size()), fb(hb.size());
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (float)((int)(s % 17) - 8) / 8.0f; };
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); };
+    for (size_t i = 0; i < ha.size(); ++i) { fa[i] = rnd(); ha[i] = bits(fa[i]); }
+    for (size_t i = 0; i < hb.size(); ++i) { fb[i] = rnd(); hb[i] = bits(fb[i]); }
+    uint16_t *da = nullptr, *db = nullptr;
+    float* dd = nullptr;
+    unsigned long long* dc = nullptr;
+    cudaError_t e = cudaMalloc(&da, ha.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&db, hb.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&dd, (size_t)128 * N * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dc, 16);
+    if (e == cudaSuccess) e = cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
+    const size_t smem = (size_t)128 * K * 2 + (size_t)((rows + 7) & ~7) * K * 2 + 4096;
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        umma_probe_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, layout, iters, dd, dc);
+        e = cudaDeviceSynchronize();
+    }
+    std::vector<float> hd((size_t)128 * N);
+    unsigned long long hc[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(hd.data(), dd, hd.size() * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(dc);
+    if (e != cudaSuccess) {
+        set_error("umma_probe: CUDA error: %s", cudaGetErrorString(e));
+        return NSB_ERR_CUDA;
+    }
+    float worst = 0.f;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            float acc = 0.f;
+            for (int k = 0; k < K; ++k) acc += fa[(size_t)m * K + k] * fb[(size_t)(n + shift_rows) * K + k];
+            worst = fmaxf(worst, fabsf(acc - hd[(size_t)m * N + n]));
+        }
+    if (max_err) *max_err = worst;
+    if (cycles_per_mma) *cycles_per_mma = (double)hc[0] / ((double)iters * 16.0 * (K / 16));
+    return 0;
+}
+
+}  // namespace nsb

@@ -12,6 +12,7 @@
 
 #include <vector>
 
+#include "epilogue.cuh"
 #include "nsb_internal.h"
 #include "umma.cuh"
 
@@ -20,14 +21,18 @@ namespace {
 
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const uint16_t* __restrict__ a /*[128][K]*/, const uint16_t* __restrict__ b /*[rows][K]*/,
-                     int N, int K, int rows, int shift, float* __restrict__ d /*[128][N]*/) {
+                     int N, int K, int rows, int shift, float* __restrict__ d /*[128][N]*/,
+                     const float* __restrict__ bias /*[128]*/, const uint16_t* __restrict__ xres /*[16][N][8]*/,
+                     uint16_t* __restrict__ e_plain /*[16][N][8]*/, uint16_t* __restrict__ e_res) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     const int kch = K / 8;
     const int bp = rows | 1;  // B row pitch per K chunk (odd, like the trunk's SPITCH)
     uint8_t* sa = smem;                       // [kch][128][16 B]
     uint8_t* sb = sa + (size_t)kch * 128 * 16;  // [kch][bp][16 B]
-    uint8_t* tail = sb + (((size_t)kch * bp * 16 + 15) & ~(size_t)15);
+    uint8_t* so = sb + (((size_t)kch * bp * 16 + 15) & ~(size_t)15);  // epilogue output [16][op][16 B]
+    const int op = N | 1;
+    uint8_t* tail = so + (size_t)16 * op * 16;
     const uint32_t bar = smem_u32(tail);
     volatile uint32_t* holder = reinterpret_cast<volatile uint32_t*>(tail + 8);
 
@@ -71,6 +76,33 @@ umma_selftest_kernel(const uint16_t* __restrict__ a /*[128][K]*/, const uint16_t
 #pragma unroll
         for (int i = 0; i < 32; ++i) d[(size_t)threadIdx.x * N + j * 32 + i] = __uint_as_float(v[i]);
     }
+    // the trunk's epilogue path (epilogue.cuh): 16x256b fragments + stmatrix.trans, plain and residual
+    const int lane = threadIdx.x & 31;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = threadIdx.x; i < 16 * N * 8; i += blockDim.x) {
+            const int c = i / (N * 8), r = (i / 8) % N, e = i % 8;
+            *reinterpret_cast<uint16_t*>(so + ((size_t)c * op + r) * 16 + e * 2) = pass ? xres[i] : (uint16_t)0xFFFFu;
+        }
+        __syncthreads();
+        float b4[4];
+        for (int k = 0; k < 4; ++k) b4[k] = bias[warp * 32 + 8 * k + (lane >> 2)];
+        for (int col0 = 0; col0 < N; col0 += 96) {
+            EpilogueMask<3> mask;
+            mask.init(col0, lane);
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + col0;
+            if (pass)
+                epilogue_warp<3, true>(taddr, smem_u32(so), (uint32_t)op * 16, warp * 4, col0, b4, mask, lane);
+            else
+                epilogue_warp<3, false>(taddr, smem_u32(so), (uint32_t)op * 16, warp * 4, col0, b4, mask, lane);
+        }
+        __syncthreads();
+        uint16_t* dst = pass ? e_res : e_plain;
+        for (int i = threadIdx.x; i < 16 * N * 8; i += blockDim.x) {
+            const int c = i / (N * 8), r = (i / 8) % N, e = i % 8;
+            dst[i] = *reinterpret_cast<uint16_t*>(so + ((size_t)c * op + r) * 16 + e * 2);
+        }
+        __syncthreads();
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -78,10 +110,10 @@ umma_selftest_kernel(const uint16_t* __restrict__ a /*[128][K]*/, const uint16_t
 
 }  // namespace
 
-int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err) {
-    if (n_cols % 32 || n_cols < 32 || n_cols > 256 || k_elems % 16 || k_elems <= 0 || shift_rows < 0 ||
+int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err, float* epi_err) {
+    if (n_cols % 96 || n_cols < 32 || n_cols > 256 || k_elems % 16 || k_elems <= 0 || shift_rows < 0 ||
         shift_rows > 64) {
-        set_error("umma_selftest: need N%%32==0 (32..256), K%%16==0, 0<=shift<=64");
+        set_error("umma_selftest: need N in {96,192}, K%%16==0, 0<=shift<=64");
         return NSB_ERR_INVALID;
     }
     if (cudaSetDevice(gpu) != cudaSuccess) {
@@ -99,24 +131,38 @@ int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_e
     auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); };
     for (size_t i = 0; i < ha.size(); ++i) { fa[i] = rnd(); ha[i] = bits(fa[i]); }
     for (size_t i = 0; i < hb.size(); ++i) { fb[i] = rnd(); hb[i] = bits(fb[i]); }
-    uint16_t *da = nullptr, *db = nullptr;
-    float* dd = nullptr;
+    std::vector<float> hbias(128);
+    std::vector<uint16_t> hx((size_t)16 * N * 8);
+    std::vector<float> fx(hx.size());
+    for (auto& b : hbias) b = rnd();
+    for (size_t i = 0; i < hx.size(); ++i) { fx[i] = rnd(); hx[i] = bits(fx[i]); }
+    uint16_t *da = nullptr, *db = nullptr, *dx = nullptr, *de0 = nullptr, *de1 = nullptr;
+    float *dd = nullptr, *dbias = nullptr;
     cudaError_t e = cudaMalloc(&da, ha.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&dx, hx.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&de0, hx.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&de1, hx.size() * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&dbias, 128 * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dbias, hbias.data(), 128 * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&db, hb.size() * 2);
     if (e == cudaSuccess) e = cudaMalloc(&dd, (size_t)128 * N * 4);
     if (e == cudaSuccess) e = cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
     const int kch = K / 8, bp = rows | 1;
-    const size_t smem = (size_t)kch * 128 * 16 + (size_t)kch * bp * 16 + 64 + 128 + 16;
+    const size_t smem = (size_t)kch * 128 * 16 + (size_t)kch * bp * 16 + (size_t)16 * (N | 1) * 16 + 64 + 128 + 16;
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-        umma_selftest_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, dd);
+        umma_selftest_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, dd, dbias, dx, de0, de1);
         e = cudaDeviceSynchronize();
     }
     std::vector<float> hd((size_t)128 * N);
     if (e == cudaSuccess) e = cudaMemcpy(hd.data(), dd, hd.size() * 4, cudaMemcpyDeviceToHost);
-    cudaFree(da); cudaFree(db); cudaFree(dd);
+    std::vector<uint16_t> he0(hx.size()), he1(hx.size());
+    if (e == cudaSuccess) e = cudaMemcpy(he0.data(), de0, he0.size() * 2, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(he1.data(), de1, he1.size() * 2, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(dx); cudaFree(de0); cudaFree(de1); cudaFree(dbias);
     if (e != cudaSuccess) {
         set_error("umma_selftest: CUDA error: %s", cudaGetErrorString(e));
         return NSB_ERR_CUDA;
@@ -129,6 +175,22 @@ int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_e
             worst = fmaxf(worst, fabsf(acc - hd[(size_t)m * N + n]));
         }
     if (max_err) *max_err = worst;
+    // epilogue: bf16(relu(acc + bias [+ x])) at real slots, 0 at padding slots, layout [chunk][slot][8]
+    auto bf = [](float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7FFFu + ((u >> 16) & 1u); u &= 0xFFFF0000u; float r; memcpy(&r, &u, 4); return r; };
+    auto unbits = [](uint16_t h) { uint32_t u = (uint32_t)h << 16; float r; memcpy(&r, &u, 4); return r; };
+    float worst_e = 0.f;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            float acc = 0.f;
+            for (int k = 0; k < K; ++k) acc += fa[(size_t)m * K + k] * fb[(size_t)(n + shift_rows) * K + k];
+            const size_t idx = ((size_t)(m >> 3) * N + n) * 8 + (m & 7);
+            const bool real = is_real_slot(n);
+            const float w0 = real ? bf(fmaxf(acc + hbias[m], 0.f)) : 0.f;
+            const float w1 = real ? bf(fmaxf(acc + hbias[m] + fx[idx], 0.f)) : 0.f;
+            worst_e = fmaxf(worst_e, fabsf(w0 - unbits(he0[idx])));
+            worst_e = fmaxf(worst_e, fabsf(w1 - unbits(he1[idx])));
+        }
+    if (epi_err) *epi_err = worst_e;
     return 0;
 }
 

@@ -122,7 +122,8 @@ void pack_weights(const nsb_net_desc& d, const float* blob, uint16_t* tiles, flo
         w += C;
         ++layer;
     }
-    // heads: rows 0..26 = policy planes, row 27 = value conv, remaining rows zero
+    // heads: head channel h (0..26 = policy planes, 27 = value conv) sits in tile row 32*(h/7) + h%7
+    // (7 per TMEM lane quadrant, so all epilogue warps share the read-out); remaining rows zero
     const float* pw = w;
     const float* pb = w + (size_t)kPolicyPlanes * C;
     const float* vw = pb + kPolicyPlanes;
@@ -133,8 +134,9 @@ void pack_weights(const nsb_net_desc& d, const float* blob, uint16_t* tiles, flo
                 for (int e = 0; e < 8; ++e) {
                     const int ci = kc * 64 + j * 8 + e;
                     float v = 0.f;
-                    if (row < kPolicyPlanes) v = pw[(size_t)row * C + ci];
-                    else if (row == kPolicyPlanes) v = vw[ci];
+                    const int hc = (row % 32) < 7 ? 7 * (row / 32) + (row % 32) : -1;
+                    if (hc >= 0 && hc < kPolicyPlanes) v = pw[(size_t)hc * C + ci];
+                    else if (hc == kPolicyPlanes) v = vw[ci];
                     t[tile_index(j, row, e)] = bf16_bits_rne(v);
                 }
         t += tile_elems;

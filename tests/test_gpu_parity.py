@@ -37,9 +37,9 @@ def run_eval(nb, ctx, fb, n, slot=0):
 
 
 # ---- tcgen05 building block -----------------------------------------------------------------------------------
-@pytest.mark.parametrize("n_cols,k,shift", [(192, 64, 0), (192, 64, 11), (96, 128, 1), (192, 128, 22), (256, 16, 5)])
-def test_umma_descriptor_selftest(nb, n_cols, k, shift):
-    assert nb.umma_selftest(n_cols, k, shift) == 0.0
+@pytest.mark.parametrize("n_cols,k,shift", [(192, 64, 0), (192, 64, 11), (96, 128, 1), (192, 128, 22), (96, 16, 5)])
+def test_umma_descriptor_and_epilogue_selftest(nb, n_cols, k, shift):
+    assert nb.umma_selftest(n_cols, k, shift) == (0.0, 0.0)
 
 
 # ---- stage 2: extract == reference extractBits<> ----------------------------------------------------------------

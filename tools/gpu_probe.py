@@ -14,7 +14,7 @@ orc = graft.load_oracle()
 nb, synth = pkg.binding, pkg.synth
 print("devices:", nb.device_count(), nb.lib().nsb_version().decode(), flush=True)
 for (n, k, sh) in ((192, 16, 0), (192, 64, 0), (192, 64, 11), (96, 128, 1)):
-    print(f"umma N={n} K={k} shift={sh}: max_err={nb.umma_selftest(n, k, sh)}", flush=True)
+    print(f"umma N={n} K={k} shift={sh}: (mma_err, epilogue_err)={nb.umma_selftest(n, k, sh)}", flush=True)
 for (C, blocks, n) in ((128, 1, 2), (128, 2, 5), (256, 1, 3)):
     desc = nb.net_desc(C, blocks)
     blob = nb.random_blob(desc, 1234)
