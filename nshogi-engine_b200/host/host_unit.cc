@@ -1,0 +1,73 @@
+// host_unit.cc — CPU-only unit checks of the host-side pieces (no GPU, no CUDA calls):
+// EvalCacheB200 behaviour (reference src/mcts/evalcache.cc) and the move-index adaptor.
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <vector>
+
+#include "eval_cache.h"
+#include "move_index.h"
+
+using namespace nshogi::engine;
+
+#define CHECK(c) do { if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+int main() {
+    {   // cache: store/load, 164-move cap, refresh-only on duplicate, LRU eviction within a bundle of 3
+        mcts::EvalCacheB200 C(1);
+        const size_t NB = C.numBundles();
+        CHECK(NB > 0);
+        float P[200];
+        for (int I = 0; I < 200; ++I) P[I] = (float)I;
+        mcts::EvalCacheB200::EvalInfo E;
+        CHECK(!C.load(42, &E));
+        CHECK(!C.store(42, 165, P, 0.5f, 0.1f));            // evalcache.cc:51-53
+        CHECK(C.store(42, 164, P, 0.5f, 0.1f));
+        CHECK(C.load(42, &E) && E.NumMoves == 164 && E.Policy[163] == 163.f && E.WinRate == 0.5f && E.DrawRate == 0.1f);
+        P[0] = 99.f;
+        CHECK(C.store(42, 164, P, 0.9f, 0.9f));             // same (hash, n): recency only, no overwrite (:73-91)
+        CHECK(C.load(42, &E) && E.Policy[0] == 0.f && E.WinRate == 0.5f);
+        const uint64_t H1 = 42 + NB, H2 = 42 + 2 * NB, H3 = 42 + 3 * NB;  // same bundle
+        CHECK(C.store(H1, 3, P, 0.1f, 0.f) && C.store(H2, 3, P, 0.2f, 0.f));
+        CHECK(C.load(42, &E));                               // 42 becomes most recent; H1 is now LRU
+        CHECK(C.store(H3, 3, P, 0.3f, 0.f));                 // evicts H1
+        CHECK(!C.load(H1, &E) && C.load(42, &E) && C.load(H2, &E) && C.load(H3, &E) && E.WinRate == 0.3f);
+        // feed(): CSR rows, > 164 moves skipped
+        const uint32_t Off[4] = {0, 2, 2 + 170, 2 + 170 + 1};
+        std::vector<float> Legal(Off[3], 0.25f);
+        const uint64_t Hs[3] = {1000, 1001, 1002};
+        const float W[3] = {0.1f, 0.2f, 0.3f}, D[3] = {0.f, 0.f, 0.f};
+        CHECK(C.feed(Hs, 3, Off, Legal.data(), W, D) == 2);
+        CHECK(C.load(1000, &E) && E.NumMoves == 2 && !C.load(1001, &E) && C.load(1002, &E) && E.NumMoves == 1);
+    }
+    {   // move index: range, planes, mirroring, no collisions among moves that can be legal together
+        using b200::MoveSpec;
+        auto sq = [](int f, int r) { return 9 * (f - 1) + (r - 1); };
+        CHECK(b200::getMoveIndex(0, MoveSpec{sq(7, 7), sq(7, 6), false, -1}) == 0 * 81 + sq(7, 6));   // N
+        CHECK(b200::getMoveIndex(0, MoveSpec{sq(7, 7), sq(7, 6), true, -1}) == 10 * 81 + sq(7, 6));
+        CHECK(b200::getMoveIndex(0, MoveSpec{sq(2, 9), sq(1, 7), false, -1}) / 81 == 8);               // knight
+        CHECK(b200::getMoveIndex(0, MoveSpec{sq(2, 9), sq(3, 7), false, -1}) / 81 == 9);
+        CHECK(b200::getMoveIndex(0, MoveSpec{0, sq(5, 5), false, 6}) == 26 * 81 + sq(5, 5));            // rook drop
+        // white's mirrored move lands on the mirrored slot of the same plane
+        CHECK(b200::getMoveIndex(1, MoveSpec{80 - sq(7, 7), 80 - sq(7, 6), false, -1}) == 0 * 81 + sq(7, 6));
+        std::set<int> Seen;
+        for (int From = 0; From < 81; ++From)
+            for (int To = 0; To < 81; ++To) {
+                if (From == To) continue;
+                const int Df = To / 9 - From / 9, Dr = To % 9 - From % 9;
+                const bool Line = Df == 0 || Dr == 0 || Df == Dr || Df == -Dr, Knight = Dr == -2 && (Df == 1 || Df == -1);
+                if (!Line && !Knight) continue;
+                for (int Pr = 0; Pr < 2; ++Pr) {
+                    const int I = b200::getMoveIndex(0, MoveSpec{From, To, Pr == 1, -1});
+                    CHECK(I >= 0 && I < 20 * 81 && I % 81 == To);
+                    Seen.insert(I);
+                }
+            }
+        for (int Pc = 0; Pc < 7; ++Pc)
+            for (int To = 0; To < 81; ++To) Seen.insert(b200::getMoveIndex(0, MoveSpec{0, To, false, Pc}));
+        std::printf("reachable policy slots: %zu\n", Seen.size());
+        CHECK(*Seen.rbegin() < 2187 && Seen.size() > 1500);  // most slots are reachable
+    }
+    std::printf("host_unit ok\n");
+    return 0;
+}

@@ -1,0 +1,125 @@
+// infer_b200.h — `infer::B200`, the B200-native executor behind the reference's plug-in interface.
+//
+// Drop-in beside infer::Zero / Nothing / Random / TensorRT (reference src/infer/{zero,nothing,
+// random,trt}.h): same four virtual methods (src/infer/infer.h:19-32), same construction
+// pattern as TensorRT (ctor(GPUId, BatchSizeMax, NumChannels) + load() + resetGPU(),
+// src/infer/trt.cc:52-80,109-232,289-291), same error behaviour (fatal: the reference exits on
+// TensorRT errors, src/infer/trt.h:34-39; load failures throw std::runtime_error, trt.cc:35,130).
+// Everything below the class is the C ABI of include/nsb.h (libnsb.so); there is no CPU path.
+#ifndef NSHOGI_ENGINE_INFER_B200_H
+#define NSHOGI_ENGINE_INFER_B200_H
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "infer/infer.h"  // the reference's header when built in-tree, host/shim otherwise
+#include "nsb.h"
+
+namespace nshogi {
+namespace engine {
+namespace infer {
+
+class B200 : public Infer {
+ public:
+    // NetChannels/NetBlocks select the canonical ResNet; with a weight file they
+    // are read from its header instead (load()).
+    B200(int GPUId, uint16_t BatchSizeMax, uint16_t NumChannels, int NetChannels = 128, int NetBlocks = 10,
+         int Slots = 1)
+        : BatchSizeM(BatchSizeMax), GPUId_(GPUId), Slots_(Slots) {
+        static_assert(sizeof(ml::FeatureBitboard) == sizeof(nsb_feature_bitboard), "FeatureBitboard is 16 bytes");
+        if (NumChannels != NSB_FEATURE_CHANNELS) throw std::runtime_error("B200: NumChannels must be 86");
+        Desc_ = nsb_net_desc{NSB_FEATURE_CHANNELS, NetChannels, NetBlocks, 256};
+        check(nsb_create(&Ctx_, GPUId, BatchSizeMax, Slots, &Desc_), "nsb_create");
+    }
+    ~B200() override {
+        nsb_destroy(Ctx_);
+    }
+    B200(const B200&) = delete;
+    B200& operator=(const B200&) = delete;
+
+    // Weight blob file: "NSBW" u32 version=1, i32 channels, blocks, hidden, in_channels, then the
+    // canonical fp32 blob.  An empty path loads the seeded random-init net, which
+    // is what the benchmarks use (the reference ships no model, src/context.h:93).
+    void load(const std::string& Path, uint64_t Seed = 1234) {
+        std::vector<float> Blob;
+        if (Path.empty()) {
+            Blob.resize(nsb_weight_blob_floats(&Desc_));
+            check(nsb_weight_blob_random(&Desc_, Seed, Blob.data()), "nsb_weight_blob_random");
+        } else {
+            std::ifstream In(Path, std::ios::binary);
+            if (!In) throw std::runtime_error("B200::load: cannot open " + Path);  // trt.cc:35
+            char Magic[4];
+            uint32_t Version = 0;
+            int32_t H[4] = {0, 0, 0, 0};
+            In.read(Magic, 4).read(reinterpret_cast<char*>(&Version), 4).read(reinterpret_cast<char*>(H), 16);
+            if (!In || std::string(Magic, 4) != "NSBW" || Version != 1)
+                throw std::runtime_error("B200::load: not an NSBW v1 weight file: " + Path);
+            if (H[0] != Desc_.channels || H[1] != Desc_.blocks || H[2] != Desc_.value_hidden ||
+                H[3] != Desc_.in_channels)
+                throw std::runtime_error("B200::load: weight file shape differs from the executor's net");
+            Blob.resize(nsb_weight_blob_floats(&Desc_));
+            In.read(reinterpret_cast<char*>(Blob.data()), (std::streamsize)(Blob.size() * sizeof(float)));
+            if (!In) throw std::runtime_error("B200::load: truncated weight file: " + Path);
+        }
+        check(nsb_load_weights(Ctx_, Blob.data(), Blob.size()), "nsb_load_weights");
+    }
+
+    void resetGPU() {  // trt.cc:289-291
+        check(nsb_bind_thread(Ctx_), "nsb_bind_thread");
+    }
+
+    void computeNonBlocking(const ml::FeatureBitboard* Features, std::size_t BatchSize, float* DstPolicy,
+                            float* DstWinRate, float* DstDrawRate) override {
+        check(nsb_eval_async(Ctx_, 0, reinterpret_cast<const nsb_feature_bitboard*>(Features), BatchSize, DstPolicy,
+                             DstWinRate, DstDrawRate),
+              "nsb_eval_async");
+    }
+    void computeBlocking(const ml::FeatureBitboard* Features, std::size_t BatchSize, float* DstPolicy,
+                         float* DstWinRate, float* DstDrawRate) override {
+        computeNonBlocking(Features, BatchSize, DstPolicy, DstWinRate, DstDrawRate);
+        await();
+    }
+    void await() override {
+        check(nsb_await(Ctx_, 0), "nsb_await");
+    }
+    bool isComputing() override {
+        const int R = nsb_is_computing(Ctx_, 0);
+        if (R < 0) check(R, "nsb_is_computing");
+        return R == 1;
+    }
+
+    nsb_ctx* context() {
+        return Ctx_;
+    }
+    int slots() const {
+        return Slots_;
+    }
+    const nsb_net_desc& net() const {
+        return Desc_;
+    }
+
+    static void check(int Status, const char* What) {
+        if (Status != NSB_OK) {  // the reference treats executor errors as fatal (trt.h:34-39)
+            std::fprintf(stderr, "[infer::B200] %s failed (%d): %s\n", What, Status, nsb_last_error());
+            std::exit(1);
+        }
+    }
+
+ private:
+    const uint16_t BatchSizeM;
+    const int GPUId_;
+    const int Slots_;
+    nsb_net_desc Desc_;
+    nsb_ctx* Ctx_ = nullptr;
+};
+
+} // namespace infer
+} // namespace engine
+} // namespace nshogi
+
+#endif // NSHOGI_ENGINE_INFER_B200_H

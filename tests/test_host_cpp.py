@@ -1,0 +1,57 @@
+"""The C++ host mirror (nshogi-engine_b200/host): infer::B200 behind the reference's Infer
+interface, the pinned multi-slot LeafPipeline, the EvalCache restatement and the move-index adaptor."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "nshogi-engine_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def built(pkg):
+    subprocess.check_call(["make", "-C", HOST, "-s", "all"])
+    return HOST
+
+
+def test_host_unit_cpu(built):
+    """EvalCacheB200 == behaviour of reference src/mcts/evalcache.cc (164-move cap, refresh-only
+    duplicates, LRU eviction in bundles of 3, feed() of CSR rows); move-index range / mirroring."""
+    out = subprocess.run([os.path.join(built, "nsb_host_unit")], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "host_unit ok" in out.stdout
+
+
+def test_host_bench_fails_loudly_without_gpu(built, nb):
+    if nb.device_count() > 0:
+        pytest.skip("GPU present")
+    out = subprocess.run([os.path.join(built, "nsb_host_bench")], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "no CPU fallback" in out.stderr
+
+
+def test_host_headers_compile_against_reference_interface(built):
+    """infer_b200.h must also compile against the REFERENCE's own infer.h (not only our shim) when
+    the reference tree is present: that is the drop-in claim of INTEGRATION.md."""
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present on this box")
+    src = '#include "infer_b200.h"\nint main() { return sizeof(nshogi::engine::infer::B200) > 0 ? 0 : 1; }\n'
+    cmd = ["g++", "-std=c++20", "-fsyntax-only", "-x", "c++", "-", f"-I{ref}", f"-I{HOST}",
+           f"-I{os.path.join(ROOT, 'include')}", f"-I{os.path.join(ROOT, 'oracle', 'shim')}"]
+    out = subprocess.run(cmd, input=src, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+
+
+@pytest.mark.gpu
+def test_host_bench_selfcheck_gpu(built):
+    """batchsize.cc-shaped run through infer::B200 (computeBlocking) and through LeafPipeline (4 pinned
+    slots, positions in, fused decode out, EvalCache feed); the two paths must agree."""
+    out = subprocess.run([os.path.join(built, "nsb_host_bench"), "--selfcheck", "--repeat", "50", "--blocks", "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["ok"] and rec["rows_identical"] and rec["cache_hit"]
+    assert rec["max_prob_diff"] < 1e-5 and rec["legal_moves"] >= 28
+    assert rec["pipeline_evals_per_s"] > 0 and rec["infer_blocking_evals_per_s"] > 0
