@@ -111,8 +111,8 @@ int main(int argc, char** argv) {
     evaluate::LeafPipeline Pipe(&Exec, B);
     mcts::EvalCacheB200 Cache(64);
     const std::vector<uint16_t> Moves = startposMoveIndices();
-    std::vector<uint64_t> Hashes(B);
-    auto fill = [&](evaluate::LeafPipeline::Slot& S, uint64_t Salt) {
+    std::vector<std::vector<uint64_t>> SlotHashes(Pipe.numSlots(), std::vector<uint64_t>(B));
+    auto fill = [&](evaluate::LeafPipeline::Slot& S, std::vector<uint64_t>& Hashes, uint64_t Salt) {
         const nsb_position P = startpos();
         for (int I = 0; I < B; ++I) {
             S.Positions[I] = P;
@@ -127,11 +127,17 @@ int main(int argc, char** argv) {
         for (int I = 0; I < Steps; ++I) {
             size_t Idx;
             evaluate::LeafPipeline::Slot& S = Pipe.acquire(&Idx);  // collects the slot's previous batch
-            if (S.Count) Stored += Cache.feed(Hashes.data(), S.Count, S.MoveOffsets, S.Legal, S.WinRate, S.DrawRate);
-            fill(S, (uint64_t)I);
+            if (S.Count)  // the slot's previous batch has landed: decode rows -> evaluation cache
+                Stored += Cache.feed(SlotHashes[Idx].data(), S.Count, S.MoveOffsets, S.Legal, S.WinRate, S.DrawRate);
+            fill(S, SlotHashes[Idx], (uint64_t)I);
             Pipe.submit(Idx, B, /*FromPositions=*/true, NSB_DECODE_PROBS);
         }
         Pipe.drain();
+        for (size_t Idx = 0; Idx < Pipe.numSlots(); ++Idx) {
+            evaluate::LeafPipeline::Slot& S = Pipe.collect(Idx);
+            if (S.Count) Stored += Cache.feed(SlotHashes[Idx].data(), S.Count, S.MoveOffsets, S.Legal, S.WinRate, S.DrawRate);
+            S.Count = 0;
+        }
     };
     run(8);
     T0 = std::chrono::steady_clock::now();
@@ -145,6 +151,7 @@ int main(int argc, char** argv) {
     {
         evaluate::LeafPipeline::Slot& S = Pipe.collect(0);
         const size_t M = Moves.size();
+        S.Count = 0;
         std::vector<double> Ref(M);
         double Mx = -1e30, Sum = 0.0;
         for (size_t J = 0; J < M; ++J) Mx = std::fmax(Mx, (double)Policy[Moves[J]]);
@@ -161,7 +168,7 @@ int main(int argc, char** argv) {
         MaxDiff = std::fmax(MaxDiff, std::fabs((double)S.WinRate[0] - (double)Win[0]));
     }
     mcts::EvalCacheB200::EvalInfo Info;
-    const bool CacheHit = Cache.load(Hashes[B / 2], &Info) && Info.NumMoves == Moves.size();
+    const bool CacheHit = Cache.load(SlotHashes[0][B / 2], &Info) && Info.NumMoves == Moves.size();
     const bool Ok = MaxDiff < 1e-5 && SumErr < 1e-5 && RowsEqual && CacheHit;
     std::printf("{\"batch\": %d, \"net\": \"%dx%d\", \"infer_blocking_evals_per_s\": %.1f, \"pipeline_evals_per_s\": %.1f, "
                 "\"legal_moves\": %zu, \"max_prob_diff\": %.3g, \"row_sum_err\": %.3g, \"rows_identical\": %s, "
