@@ -159,7 +159,6 @@ def run_b200(args):
     d_off = nb.DeviceBuffer.from_host(off)
     d_idx = nb.DeviceBuffer.from_host(idx)
     n_out = 8
-    d_policy = [nb.DeviceBuffer(B * 2187 * 4) for _ in range(n_out)]
     d_legal = [nb.DeviceBuffer(max(n_moves, 1) * 4) for _ in range(n_out)]
     d_win = [nb.DeviceBuffer(B * 4) for _ in range(n_out)]
     d_draw = [nb.DeviceBuffer(B * 4) for _ in range(n_out)]
@@ -167,8 +166,9 @@ def run_b200(args):
 
     def dev_step(i, slot=0):
         j = i % n_out
+        # the production path: legal-move rows out, dense logits never leave the SM (d_policy = NULL)
         ctx.eval_decode_device(slot, d_pool.ptr + (i % pool) * fb_bytes, B, d_off.ptr, d_idx.ptr, nb.DECODE_PROBS,
-                               d_policy[j].ptr, d_legal[j].ptr, d_win[j].ptr, d_draw[j].ptr, d_flag[j].ptr)
+                               None, d_legal[j].ptr, d_win[j].ptr, d_draw[j].ptr, d_flag[j].ptr)
 
     def await_all():
         for s_ in range(slots):

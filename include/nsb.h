@@ -206,6 +206,9 @@ int nsb_debug_trunk_timeline(nsb_ctx* ctx, int slot, const nsb_feature_bitboard*
 int nsb_debug_umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters,
                          float* max_err, double* cycles_per_mma);
 
+/* Diagnostics: sustained cp.async.bulk (L2 -> shared ring) rate per CTA in bytes per SM cycle. */
+int nsb_debug_bulk_rate_probe(int gpu, int ctas, int tile_bytes, int stages, int split, double* bytes_per_cycle);
+
 /* Kernel launches issued by this ctx since creation (bench "gpu_launches"). */
 uint64_t nsb_launch_count(nsb_ctx* ctx);
 

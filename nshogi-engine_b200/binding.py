@@ -70,6 +70,7 @@ SIGNATURES = {
     "nsb_debug_trunk_timeline": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     "nsb_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double)]),
+    "nsb_debug_bulk_rate_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "nsb_stream": (_P, [_P, C.c_int]),
     "nsb_set_timing": (C.c_int, [_P, C.c_int]),
     "nsb_trunk_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -209,6 +210,12 @@ def umma_probe(n_cols, k_elems, shift_rows, layout, iters=20, gpu=0):
     _check(lib().nsb_debug_umma_probe(gpu, n_cols, k_elems, shift_rows, layout, iters, C.byref(err), C.byref(cyc)),
            "nsb_debug_umma_probe")
     return float(err.value), float(cyc.value)
+
+
+def bulk_rate_probe(ctas, tile_bytes, stages, split, gpu=0):
+    v = C.c_double(0)
+    _check(lib().nsb_debug_bulk_rate_probe(gpu, ctas, tile_bytes, stages, split, C.byref(v)), "nsb_debug_bulk_rate_probe")
+    return float(v.value)
 
 
 class Event:

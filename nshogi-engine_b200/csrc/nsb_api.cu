@@ -654,6 +654,10 @@ int nsb_debug_umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int l
     return umma_probe(gpu, n_cols, k_elems, shift_rows, layout, iters, max_err, cycles_per_mma);
 }
 
+int nsb_debug_bulk_rate_probe(int gpu, int ctas, int tile_bytes, int stages, int split, double* bytes_per_cycle) {
+    return bulk_rate_probe(gpu, ctas, tile_bytes, stages, split, bytes_per_cycle);
+}
+
 int nsb_event_create(void** out) {
     if (!out) return NSB_ERR_INVALID;
     cudaEvent_t e;

@@ -97,6 +97,7 @@ int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cud
 int trunk_fused_prepare(int channels);  // sets max dynamic smem attribute
 int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters, float* max_err,
                double* cycles_per_mma);
+int bulk_rate_probe(int gpu, int ctas, int tile_bytes, int stages, int split, double* bytes_per_cycle);
 int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err, float* epi_err);
 
 void set_error(const char* fmt, ...);

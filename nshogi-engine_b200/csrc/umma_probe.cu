@@ -183,3 +183,80 @@ int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int
 }
 
 }  // namespace nsb
+
+// ---- bulk-copy (UBLKCP) stream rate probe: L2-resident source -> shared-memory ring -----------------
+namespace nsb {
+namespace {
+__global__ void __launch_bounds__(64, 1)
+bulk_rate_kernel(const uint8_t* __restrict__ src, int src_bytes, int tile_bytes, int stages, int split, int iters,
+                 unsigned long long* __restrict__ cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t bars = ring + (uint32_t)(stages * tile_bytes);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(bars + 8u * s, 1);
+            mbar_init(bars + 8u * (stages + s), 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int tiles = src_bytes / tile_bytes;
+    const int part = tile_bytes / split;
+    if (threadIdx.x == 0) {            // producer
+        uint32_t stage = 0, phase = 0;
+        for (int it = 0; it < iters; ++it)
+            for (int t = 0; t < tiles; ++t) {
+                mbar_wait(bars + 8u * (stages + stage), phase ^ 1u);
+                mbar_arrive_expect_tx(bars + 8u * stage, (uint32_t)tile_bytes);
+                for (int k = 0; k < split; ++k)
+                    bulk_g2s(ring + stage * tile_bytes + k * part, src + (size_t)t * tile_bytes + k * part, (uint32_t)part,
+                             bars + 8u * stage);
+                if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1u; }
+            }
+    } else if (threadIdx.x == 32) {    // consumer: release each stage as soon as it has landed
+        uint32_t stage = 0, phase = 0;
+        const unsigned long long t0 = clock64();
+        for (int it = 0; it < iters; ++it)
+            for (int t = 0; t < tiles; ++t) {
+                mbar_wait(bars + 8u * stage, phase);
+                mbar_arrive(bars + 8u * (stages + stage));
+                if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1u; }
+            }
+        if (blockIdx.x == 0) cycles[0] = clock64() - t0;
+    }
+}
+}  // namespace
+
+int bulk_rate_probe(int gpu, int ctas, int tile_bytes, int stages, int split, double* bytes_per_cycle) {
+    if (cudaSetDevice(gpu) != cudaSuccess) return NSB_ERR_NO_DEVICE;
+    if (tile_bytes % (16 * split) || stages < 1 || stages * tile_bytes > 200 * 1024 || ctas < 1) {
+        set_error("bulk_rate_probe: bad arguments");
+        return NSB_ERR_INVALID;
+    }
+    const int src_bytes = (288 * 1024 / tile_bytes) * tile_bytes, iters = 20;
+    uint8_t* d = nullptr;
+    unsigned long long* dc = nullptr;
+    cudaError_t e = cudaMalloc(&d, src_bytes);
+    if (e == cudaSuccess) e = cudaMemset(d, 1, src_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dc, 8);
+    const size_t smem = (size_t)stages * tile_bytes + 16 * stages + 256;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bulk_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        bulk_rate_kernel<<<ctas, 64, smem>>>(d, src_bytes, tile_bytes, stages, split, iters, dc);
+        bulk_rate_kernel<<<ctas, 64, smem>>>(d, src_bytes, tile_bytes, stages, split, iters, dc);
+        e = cudaDeviceSynchronize();
+    }
+    unsigned long long hc = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaFree(dc);
+    if (e != cudaSuccess) {
+        set_error("bulk_rate_probe: %s", cudaGetErrorString(e));
+        return NSB_ERR_CUDA;
+    }
+    if (bytes_per_cycle) *bytes_per_cycle = (double)src_bytes * iters / (double)hc;
+    return 0;
+}
+}  // namespace nsb
