@@ -41,52 +41,61 @@ struct EpilogueMask {
     }
 };
 
-// One warp handles its 32 TMEM lanes (= 32 output channels, 4 chunks starting at chunk0) for the
-// 32*NCG columns starting at col0.  `taddr` = TMEM address of (lane quadrant base, column col0 of
-// this accumulator); `buf` = shared address of the output buffer's slot 0 of chunk 0 (guard
-// already added); `pitch` = bytes between channel chunks.  bias[lb*2 + h] is the bias of channel
-// 32q + 16*lb + 8*h + lane/4.  Per element: one FADD (+ unpack and FADD for the skip), half a
-// cvt.rn.relu.bf16x2 and half an AND.
+// One warp handles 16 of its 32 TMEM lanes (lane block lb = 0 / 1 -> 16 output channels = chunks
+// chunk0 + 2*lb, +1) for the 32*NCG columns starting at col0.  `taddr` = TMEM address of (lane
+// quadrant base, column col0 of this accumulator); `buf` = shared address of the output buffer's
+// slot 0 of chunk 0 (guard already added); `pitch` = bytes between channel chunks.
+// bias[lb*2 + h] is the bias of channel 32q + 16*lb + 8*h + lane/4.  Per element: one FADD
+// (+ unpack and FADD for the skip), half a cvt.rn.relu.bf16x2 and half an AND.
 template <int NCG, bool kResidual>
-__device__ __forceinline__ void epilogue_warp(uint32_t taddr, uint32_t buf, uint32_t pitch, int chunk0, int col0,
-                                              const float (&bias)[4], const EpilogueMask<NCG>& mask, int lane) {
+__device__ __forceinline__ void epilogue_half(int lb, uint32_t taddr, uint32_t buf, uint32_t pitch, int chunk0,
+                                              int col0, const float (&bias)[4], const EpilogueMask<NCG>& mask,
+                                              int lane) {
     const int mk = lane >> 3, mi = lane & 7;
+    uint32_t v[NCG][16];
 #pragma unroll
-    for (int lb = 0; lb < 2; ++lb) {
-        uint32_t v[NCG][16];
-#pragma unroll
-        for (int cg = 0; cg < NCG; ++cg) tmem_ld_16x256b_x4(taddr + ((uint32_t)(lb * 16) << 16) + cg * 32, v[cg]);
-        const uint32_t row_addr = buf + (uint32_t)(chunk0 + lb * 2 + (mk & 1)) * pitch +
-                                  (uint32_t)(col0 + 8 * (mk >> 1) + mi) * 16u;
-        uint32_t xr[NCG][2][4];
-        if (kResidual) {
-#pragma unroll
-            for (int cg = 0; cg < NCG; ++cg)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    ldmatrix_x4_trans(row_addr + (uint32_t)(cg * 32 + h * 16) * 16u, xr[cg][h][0], xr[cg][h][1],
-                                      xr[cg][h][2], xr[cg][h][3]);
-        }
-        tmem_ld_wait();
+    for (int cg = 0; cg < NCG; ++cg) tmem_ld_16x256b_x4(taddr + ((uint32_t)(lb * 16) << 16) + cg * 32, v[cg]);
+    const uint32_t row_addr =
+        buf + (uint32_t)(chunk0 + lb * 2 + (mk & 1)) * pitch + (uint32_t)(col0 + 8 * (mk >> 1) + mi) * 16u;
+    uint32_t xr[NCG][2][4];
+    if (kResidual) {
 #pragma unroll
         for (int cg = 0; cg < NCG; ++cg)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t p[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {  // m: bit0 = row half (lane/4 [+8]), bit1 = column group
-                    const int g = 2 * h + (m >> 1), rh = m & 1;
-                    float x0 = __uint_as_float(v[cg][4 * g + 2 * rh + 0]) + bias[lb * 2 + rh];
-                    float x1 = __uint_as_float(v[cg][4 * g + 2 * rh + 1]) + bias[lb * 2 + rh];
-                    if (kResidual) {
-                        x0 += __uint_as_float(xr[cg][h][m] << 16);
-                        x1 += __uint_as_float(xr[cg][h][m] & 0xFFFF0000u);
-                    }
-                    p[m] = pack_relu_bf16x2(x0, x1) & mask.m[cg * 4 + g];
-                }
-                stmatrix_x4_trans(row_addr + (uint32_t)(cg * 32 + h * 16) * 16u, p[0], p[1], p[2], p[3]);
-            }
+            for (int h = 0; h < 2; ++h)
+                ldmatrix_x4_trans(row_addr + (uint32_t)(cg * 32 + h * 16) * 16u, xr[cg][h][0], xr[cg][h][1],
+                                  xr[cg][h][2], xr[cg][h][3]);
     }
+    tmem_ld_wait();
+    const float b0 = lb ? bias[2] : bias[0], b1 = lb ? bias[3] : bias[1];
+#pragma unroll
+    for (int cg = 0; cg < NCG; ++cg)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t p[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {  // m: bit0 = row half (lane/4 [+8]), bit1 = column group
+                const int g = 2 * h + (m >> 1), rh = m & 1;
+                const float bb = rh ? b1 : b0;
+                float x0 = __uint_as_float(v[cg][4 * g + 2 * rh + 0]) + bb;
+                float x1 = __uint_as_float(v[cg][4 * g + 2 * rh + 1]) + bb;
+                if (kResidual) {
+                    x0 += __uint_as_float(xr[cg][h][m] << 16);
+                    x1 += __uint_as_float(xr[cg][h][m] & 0xFFFF0000u);
+                }
+                p[m] = pack_relu_bf16x2(x0, x1) & mask.m[cg * 4 + g];
+            }
+            stmatrix_x4_trans(row_addr + (uint32_t)(cg * 32 + h * 16) * 16u, p[0], p[1], p[2], p[3]);
+        }
+}
+
+// Both lane blocks: the warp's 32 TMEM lanes (= 32 output channels, 4 chunks starting at chunk0).
+template <int NCG, bool kResidual>
+__device__ __forceinline__ void epilogue_warp(uint32_t taddr, uint32_t buf, uint32_t pitch, int chunk0, int col0,
+                                              const float (&bias)[4], const EpilogueMask<NCG>& mask, int lane) {
+#pragma unroll
+    for (int lb = 0; lb < 2; ++lb)
+        epilogue_half<NCG, kResidual>(lb, taddr, buf, pitch, chunk0, col0, bias, mask, lane);
 }
 
 }  // namespace nsb

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -44,6 +45,7 @@ struct Slot {
 
 struct nsb_ctx {
     int gpu = 0, batch_max = 0, num_sms = 0;
+    int max_pairs = 0;  // co-resident CTA pairs of the 256-channel trunk (0: single-CTA kernel)
     nsb_net_desc desc{};
     bool loaded = false, timing = false;
     nsb::DeviceNet net{};
@@ -135,6 +137,13 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     NSB_CUDA(cudaSetDevice(gpu));
     int rc = trunk_fused_prepare(net->channels);
     if (rc) return rc;
+    int max_pairs = 0;
+    // NSB_TRUNK256=single keeps the one-CTA kernel for A/B measurements (diagnostics only)
+    const char* t256 = getenv("NSB_TRUNK256");
+    if (net->channels == 256 && !(t256 && strcmp(t256, "single") == 0)) {
+        if ((rc = trunk_pair_prepare(&max_pairs))) return rc;
+        if (max_pairs > prop.multiProcessorCount / 2) max_pairs = prop.multiProcessorCount / 2;
+    }
     nsb_ctx* c = new (std::nothrow) nsb_ctx();
     if (!c) {
         set_error("out of host memory");
@@ -143,6 +152,7 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     c->gpu = gpu;
     c->batch_max = batch_max;
     c->num_sms = prop.multiProcessorCount;
+    c->max_pairs = max_pairs;
     c->desc = *net;
     c->slots.resize(slots);
     const size_t B = (size_t)batch_max;
@@ -257,7 +267,8 @@ static int run_trunk(nsb_ctx* c, Slot& s, const EvalArgs& a) {
         }
         NSB_CUDA(cudaEventRecord(s.ev[s.ev_used], s.stream));
     }
-    int k = launch_trunk_fused(c->net, a, c->num_sms, s.stream);
+    int k = c->max_pairs > 0 ? launch_trunk_pair(c->net, a, c->max_pairs, s.stream)
+                             : launch_trunk_fused(c->net, a, c->num_sms, s.stream);
     if (k < 0) return k;
     NSB_CUDA(cudaGetLastError());
     c->launches += (uint64_t)k;

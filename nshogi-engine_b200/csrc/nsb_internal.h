@@ -47,6 +47,37 @@ struct TrunkGeom {
     static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 };
 
+// Geometry of the CTA-pair trunk kernel for 256-channel nets (trunk_pair.cu): a
+// cluster of two CTAs owns two positions, CTA r holds position r's activations (all 256 channels)
+// and the weight rows of Cout half r; one cta_group::2 MMA (M = 256, N = 192) per K = 16 step.
+struct PairGeom {
+    static constexpr int C = 256;
+    static constexpr int KCH = C / 8;                     // 32 channel chunks per slot
+    static constexpr int NCOLS = 96;                      // slots of this CTA's position (last real slot 88)
+    static constexpr int NPAIR = 2 * NCOLS;               // UMMA N across the pair
+    static constexpr int GUARD = 12;
+    static constexpr int SPITCH = (GUARD + NCOLS + 11) | 1;
+    static constexpr int BUF_BYTES = ((KCH * SPITCH * 16 + 127) / 128) * 128;
+    static constexpr int XCH = 16;                        // channel chunks of one Cout half
+    static constexpr int XPITCH = NCOLS * 16;             // exchange buffer: [16 chunks][96 slots][16 B]
+    static constexpr int XBUF_BYTES = XCH * XPITCH;
+    static constexpr int NSTAGES = 5;
+    static constexpr int KC64 = C / 64;
+    static constexpr int TMEM_COLS = 256;
+    static constexpr int NBARS = 2 * NSTAGES + 4;         // full[], empty[], act, acc, peer_act, skip
+    static constexpr int OFF_BUF_A = 0;
+    static constexpr int OFF_BUF_B = OFF_BUF_A + BUF_BYTES;
+    static constexpr int OFF_XBUF = OFF_BUF_B + BUF_BYTES;  // also the logits scratch of the tail
+    static constexpr int OFF_RING = OFF_XBUF + XBUF_BYTES;
+    static constexpr int OFF_FEAT = OFF_RING + NSTAGES * kStageBytes;
+    static constexpr int OFF_VBUF = OFF_FEAT + NSB_FEATURE_CHANNELS * 16;
+    static constexpr int OFF_RED = OFF_VBUF + ((81 * 4 + 15) / 16) * 16;
+    static constexpr int OFF_BARS = OFF_RED + ((8 * 2 * 4 + 2 * 4 + 15) / 16) * 16;
+    static constexpr int SMEM_BYTES = OFF_BARS + NBARS * 8 + 16 + 128;
+    static_assert(kPolicySize * 4 <= XBUF_BYTES, "logits scratch aliases the exchange buffer");
+    static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+};
+
 // Device pointers + shape of a loaded net (filled by weights.cc / nsb_api.cu).
 struct DeviceNet {
     int channels;      // C
@@ -95,6 +126,8 @@ int launch_decode(const float* d_policy, const float* d_win, const float* d_draw
                   uint8_t* d_flag, cudaStream_t s);
 int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s);
 int trunk_fused_prepare(int channels);  // sets max dynamic smem attribute
+int trunk_pair_prepare(int* max_pairs);  // same for the CTA-pair kernel; reports co-resident clusters
+int launch_trunk_pair(const DeviceNet& net, const EvalArgs& a, int max_pairs, cudaStream_t s);
 int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters, float* max_err,
                double* cycles_per_mma);
 int bulk_rate_probe(int gpu, int ctas, int tile_bytes, int stages, int split, double* bytes_per_cycle);

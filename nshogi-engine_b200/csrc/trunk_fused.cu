@@ -23,65 +23,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "decode_device.cuh"
-#include "epilogue.cuh"
-#include "nsb_internal.h"
-#include "umma.cuh"
+#include "trunk_common.cuh"
 
 namespace nsb {
 
 namespace {
-
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
-constexpr int kEpiWarps = kEpiThreads / 32;
-constexpr uint32_t kEpiBar = 1;  // named barrier id for the 8 epilogue warps
-
-constexpr int kStemChunks = 12;  // stem K = 96 input channels (86 real), 6 K=16 steps
-
-// One FeatureBitboard (reference src/cuda/extractbit.cu:20-37) -> {w0, w1, w2, value}: bit t of
-// the 81-bit string w2:w1:w0 is the plane's value at output position t (rotation applied), and
-// `value` is the fp32 fill value rounded to bf16 bits.  Squares 0..62 live in lo bits 0..62,
-// squares 63..80 in hi bits 0..17; every other bit of the input is ignored.
-__device__ __forceinline__ uint4 plane_bits(uint4 f) {
-    uint32_t s0 = f.x;
-    uint32_t s1 = (f.y & 0x7FFFFFFFu) | (f.z << 31);
-    uint32_t s2 = (f.z >> 1) & 0x1FFFFu;
-    if ((f.z >> 24) & 1u) {  // rotate: out[t] = in[80 - t]  == (96-bit reversal) >> 15
-        const uint32_t r0 = __brev(s2), r1 = __brev(s1), r2 = __brev(s0);
-        s0 = __funnelshift_r(r0, r1, 15);
-        s1 = __funnelshift_r(r1, r2, 15);
-        s2 = r2 >> 15;
-    }
-    return make_uint4(s0, s1, s2, (uint32_t)f32_to_bf16_bits(__uint_as_float(f.w)));
-}
-
-constexpr int kFcPrefetch = 27;
-
-// Head accumulator: this warp's lanes 0..6 = head channels hp = 7q + lane (0..26 policy planes,
-// 27 = value conv) for the 96 columns from COL0 (compile-time: slot -> square arithmetic folds).
-template <int COL0>
-__device__ __forceinline__ void head_read(uint32_t taddr, float bias, int hp, float* scratch, float* vbuf, int lane) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        uint32_t v[32];
-        tmem_ld32(taddr + COL0 + j * 32, v);
-        tmem_ld_wait();
-        if (lane < 7) {
-            float* dst = hp < kPolicyPlanes ? scratch + hp * 81 : vbuf;
-            const bool relu = hp == kPolicyPlanes;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int n = COL0 + j * 32 + i;
-                if (is_real_slot(n)) {
-                    const int pos = n / 100, m = n % 100, t = (m / 10) * 9 + (m % 10);
-                    const float x = __uint_as_float(v[i]) + bias;
-                    dst[(relu ? pos * 81 : pos * kPolicySize) + t] = relu ? fmaxf(x, 0.f) : x;  // plane-major logits
-                }
-            }
-        }
-    }
-}
 
 template <int C>
 __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNet net, const EvalArgs a) {
@@ -209,51 +155,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
 
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
             if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 8] = clock64();
-            // Per plane: the 81 occupancy bits as one contiguous little-endian bit string with the
-            // rotation (extractbit.cu:20,26) already applied, plus the fill value as bf16 bits.
-            for (int i = et; i < G::NPOS * NSB_FEATURE_CHANNELS; i += kEpiThreads) {
-                const int pos = i / NSB_FEATURE_CHANNELS, c = i - pos * NSB_FEATURE_CHANNELS;
-                const int b = b0 + pos;
-                uint4 f = make_uint4(0, 0, 0, 0);
-                if (b < a.n) f = __ldg(reinterpret_cast<const uint4*>(a.features) + (size_t)b * NSB_FEATURE_CHANNELS + c);
-                featS[i] = plane_bits(f);
-            }
-            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 9] = clock64();
-            named_bar_sync(kEpiBar, kEpiThreads);
-            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 3] = clock64();
-            // The stem reads 96 input channels = 12 chunks of 8 (86 real + zero padding).  One work
-            // item = (position, chunk, board row): the 8 planes' bit strings are loaded once, the
-            // row's 9-bit field is cut out with a funnel shift, and 9 records of 16 B are written.
-            for (int item = et; item < G::NPOS * kStemChunks * 9; item += kEpiThreads) {
-                const int pos = item / (kStemChunks * 9);
-                const int r2 = item - pos * (kStemChunks * 9);
-                const int j = r2 / 9, row = r2 - j * 9;
-                const int bit0 = 9 * row, wi = bit0 >> 5, sh = bit0 & 31;
-                uint32_t field[8], val[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int c = j * 8 + e;
-                    uint4 f = make_uint4(0, 0, 0, 0);
-                    if (c < NSB_FEATURE_CHANNELS) f = featS[pos * NSB_FEATURE_CHANNELS + c];
-                    const uint32_t lo = wi == 0 ? f.x : (wi == 1 ? f.y : f.z);
-                    const uint32_t hi = wi == 0 ? f.y : (wi == 1 ? f.z : 0u);
-                    field[e] = __funnelshift_r(lo, hi, sh);
-                    val[e] = f.w;
-                }
-                uint8_t* dst = smem + G::OFF_BUF_B + (size_t)((j * G::SPITCH + G::GUARD + pos * 100 + row * 10) * 16);
-#pragma unroll
-                for (int col = 0; col < 9; ++col) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        const uint32_t a0 = val[2 * e2] & (0u - ((field[2 * e2] >> col) & 1u));
-                        const uint32_t a1 = val[2 * e2 + 1] & (0u - ((field[2 * e2 + 1] >> col) & 1u));
-                        w[e2] = a0 | (a1 << 16);
-                    }
-                    *reinterpret_cast<uint4*>(dst + col * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
-            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 10] = clock64();
+            unsigned long long* tl = (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) ? a.timeline + 4 * NL : nullptr;
+            expand_features<G::NPOS, G::SPITCH, G::GUARD>(a.features, a.n, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
             mbar_arrive(bar_act);
             if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 2] = clock64();
@@ -284,12 +187,10 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
 
             // -- heads: accumulator row 32*(h/7) + h%7 holds head channel h (0..26 policy planes,
             //    27 = value conv), i.e. 7 useful lanes in every TMEM quadrant, so all epilogue warps help
-            const int H = net.hidden;
             const int hp = 7 * q + lane;
             const float hbias = lane < 7 ? __ldg(net.bias + (size_t)(NL - 1) * C + hp) : 0.f;
             float wpre[kFcPrefetch];  // first FC1 weights, requested before the accumulator wait
-#pragma unroll
-            for (int t = 0; t < kFcPrefetch; ++t) wpre[t] = et < H ? __ldg(net.fc1t + (size_t)t * H + et) : 0.f;
+            fc1_prefetch(net, et, wpre);
             mbar_wait(bar_acc, acc_phase);
             acc_phase ^= 1u;
             tc_fence_after();
@@ -298,83 +199,12 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
                 if (part == 0)
                     head_read<0>(taddr, hbias, hp, scratch, vbuf, lane);
                 else
-                    head_read<96>(taddr, hbias, hp, scratch, vbuf, lane);
+                    head_read<96>(taddr + 96, hbias, hp, scratch, vbuf, lane);
                 tc_fence_before();
             }
             named_bar_sync(kEpiBar, kEpiThreads);
-            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 4] = clock64();
-
-            if (a.policy != nullptr) {  // dense logits (the Infer contract, trt.cc:265-267)
-                for (int idx = et; idx < G::NPOS * kPolicySize; idx += kEpiThreads) {
-                    const int pos = idx / kPolicySize, b = b0 + pos;
-                    if (b < a.n) a.policy[(size_t)b * kPolicySize + (idx - pos * kPolicySize)] = scratch[idx];
-                }
-            }
-            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 5] = clock64();
-            {   // value MLP: FC(81 -> H) + ReLU, FC(H -> 2), sigmoid; one hidden unit per thread
-                float o[G::NPOS][2];
-#pragma unroll
-                for (int pos = 0; pos < G::NPOS; ++pos) o[pos][0] = o[pos][1] = 0.f;
-                if (et < H) {
-                    const int h = et;
-                    float acc[G::NPOS];
-                    const float b1 = __ldg(net.fc1b + h);
-                    const float w0 = __ldg(net.fc2 + h), w1 = __ldg(net.fc2 + H + h);
-#pragma unroll
-                    for (int pos = 0; pos < G::NPOS; ++pos) acc[pos] = b1;
-#pragma unroll
-                    for (int t0 = 0; t0 < 81; t0 += kFcPrefetch) {
-                        float w[kFcPrefetch];
-#pragma unroll
-                        for (int t = 0; t < kFcPrefetch; ++t)
-                            w[t] = t0 == 0 ? wpre[t] : __ldg(net.fc1t + (size_t)(t0 + t) * H + h);
-#pragma unroll
-                        for (int t = 0; t < kFcPrefetch; ++t)
-#pragma unroll
-                            for (int pos = 0; pos < G::NPOS; ++pos) acc[pos] += w[t] * vbuf[pos * 81 + t0 + t];
-                    }
-#pragma unroll
-                    for (int pos = 0; pos < G::NPOS; ++pos) {
-                        const float hid = fmaxf(acc[pos], 0.f);
-                        o[pos][0] = w0 * hid;
-                        o[pos][1] = w1 * hid;
-                    }
-                }
-#pragma unroll
-                for (int pos = 0; pos < G::NPOS; ++pos)
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const float s = warp_sum(o[pos][k]);
-                        if (lane == 0) red[(ew * G::NPOS + pos) * 2 + k] = s;
-                    }
-                named_bar_sync(kEpiBar, kEpiThreads);
-                if (et < G::NPOS * 2) {
-                    const int pos = et >> 1, k = et & 1;
-                    float s = __ldg(net.fc2b + k);
-#pragma unroll
-                    for (int qq = 0; qq < kEpiWarps; ++qq) s += red[(qq * G::NPOS + pos) * 2 + k];
-                    const float val = 1.0f / (1.0f + expf(-s));
-                    red[kEpiWarps * G::NPOS * 2 + pos * 2 + k] = val;
-                    const int b = b0 + pos;
-                    if (b < a.n) (k == 0 ? a.win : a.draw)[b] = val;
-                }
-            }
-            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 6] = clock64();
-            if (a.move_off != nullptr) {  // fused decode on logits that never left shared memory
-                named_bar_sync(kEpiBar, kEpiThreads);
-                if (ew < G::NPOS) {
-                    const int b = b0 + ew;
-                    if (b < a.n) {
-                        const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
-                        const bool bad = warp_decode_row(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
-                                                         a.decode_mode, red[kEpiWarps * G::NPOS * 2 + ew * 2 + 0],
-                                                         red[kEpiWarps * G::NPOS * 2 + ew * 2 + 1], a.legal_out + mb, lane);
-                        if (a.nan_flag && lane == 0) a.nan_flag[b] = bad ? 1 : 0;
-                    }
-                }
-            }
-            named_bar_sync(kEpiBar, kEpiThreads);  // scratch / vbuf / red reusable
-            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 7] = clock64();
+            if (tl) tl[4] = clock64();
+            heads_tail<G::NPOS>(net, a, b0, scratch, vbuf, red, wpre, et, tl);
         }
     }
 

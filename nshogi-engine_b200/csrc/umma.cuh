@@ -208,24 +208,19 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// Remote arrives carry the default .release.cta semantics on purpose: a cluster-scope release or
+// acquire compiles to MEMBAR.ALL.GPU / CCTL.IVALL (hundreds of cycles, measured) and everything these
+// barriers order is either written by the async proxy (bulk copies, tcgen05.commit) or was fenced
+// with fence.proxy.async before a local arrive that the relaying thread has already observed.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
-// wait with cluster-scope acquire (the arrivals may come from the peer CTA)
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait_cluster(bar, parity)) {
-    }
+// remote arrive that also raises the destination barrier's expected transaction count (the bytes a
+// following bulk_s2peer will complete on it)
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t cluster_bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar),
+                 "r"(bytes)
+                 : "memory");
 }
 // shared::cta -> peer's shared memory through the bulk-copy engine; completes (bytes) on an mbarrier
 // that lives in the DESTINATION CTA.  Both destination and barrier are shared::cluster addresses.

@@ -127,18 +127,117 @@ umma_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+
+// The same probe on a CTA pair: one cta_group::2 MMA of M = 256 x N x K16; CTA r holds A rows
+// [128r, 128r + 128) and N/2 rows of B (b_rows rows stored per CTA, start shifted by `shift`).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_pair_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, int N, int K, int rows,
+                       int shift, int layout, int iters, float* __restrict__ d, unsigned long long* __restrict__ cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t rank = cluster_ctarank();
+    const int a_rows = 128, b_rows = (rows + 7) & ~7;
+    const size_t a_bytes = (size_t)a_rows * K * 2, b_bytes = (size_t)b_rows * K * 2;
+    uint8_t* sa = smem;
+    uint8_t* sb = sa + ((a_bytes + 1023) & ~(size_t)1023);
+    uint8_t* tail = sb + ((b_bytes + 1023) & ~(size_t)1023);
+    const uint32_t bar = smem_u32(tail);
+    volatile uint32_t* holder = reinterpret_cast<volatile uint32_t*>(tail + 8);
+    for (int i = threadIdx.x; i < 128 * K; i += blockDim.x)
+        *reinterpret_cast<uint16_t*>(sa + elem_off(layout, i / K, i % K, a_rows)) = a[(size_t)rank * 128 * K + i];
+    for (int i = threadIdx.x; i < rows * K; i += blockDim.x)
+        *reinterpret_cast<uint16_t*>(sb + elem_off(layout, i / K, i % K, b_rows)) = b[(size_t)rank * rows * K + i];
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    fence_proxy_async_smem();
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(holder)), 256);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *holder;
+    const uint32_t idesc = make_idesc_bf16_f32(256, N);
+    const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
+    auto issue_all = [&](bool fresh) {
+        for (int k16 = 0; k16 < K / 16; ++k16) {
+            uint64_t ad, bd;
+            if (layout == 0) {
+                ad = make_smem_desc(a0 + (uint32_t)(k16 * 2 * a_rows * 16), a_rows * 16, 128);
+                bd = make_smem_desc(b0 + (uint32_t)((k16 * 2 * b_rows + shift) * 16), b_rows * 16, 128);
+            } else {
+                const int kc = k16 >> 2, kk = k16 & 3;
+                ad = make_desc_sw128(a0 + (uint32_t)(kc * a_rows * 128 + kk * 32));
+                bd = make_desc_sw128(b0 + (uint32_t)(kc * b_rows * 128 + shift * 128 + kk * 32));
+            }
+            umma_bf16_pair(tmem_base, ad, bd, idesc, (fresh && k16 == 0) ? 0u : 1u);
+        }
+    };
+    uint32_t parity = 0;
+    if (warp == 0) {
+        for (int it = 0; it < iters + 1; ++it) {
+            const unsigned long long t0 = clock64();
+            if (rank == 0) {
+                const int reps = it == 0 ? 1 : 16;
+                for (int rep = 0; rep < reps; ++rep) {
+                    if (elect_one()) issue_all(it == 0 && rep == 0);
+                    __syncwarp();
+                }
+                if (elect_one()) umma_commit_pair(bar, 3);
+                __syncwarp();
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            const unsigned long long t1 = clock64();
+            if (threadIdx.x == 0 && rank == 0) {
+                if (it == 1) cycles[0] = 0;
+                if (it >= 1) cycles[0] += t1 - t0;
+            }
+        }
+        // only a clean single pass is checked
+        if (rank == 0) {
+            if (elect_one()) {
+                issue_all(true);
+                umma_commit_pair(bar, 3);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar, parity);
+    }
+    __syncthreads();
+    tc_fence_after();
+    for (int j = 0; j < N / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            d[((size_t)rank * 128 + threadIdx.x) * N + j * 32 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc_pair(tmem_base, 256);
+}
+
 }  // namespace
 
 int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters, float* max_err,
                double* cycles_per_mma) {
+    // layout: 0 = SWIZZLE_NONE, 1 = SWIZZLE_128B, 2 / 3 = the same on a CTA pair (cta_group::2, M = 256)
+    const bool pair = layout >= 2;
+    const int lay = layout & 1;
     if (n_cols % 32 || n_cols < 32 || n_cols > 256 || k_elems % 64 || k_elems <= 0 || shift_rows < 0 ||
-        shift_rows > 64 || iters < 1 || (layout != 0 && layout != 1)) {
+        shift_rows > 64 || iters < 1 || layout < 0 || layout > 3) {
         set_error("umma_probe: bad arguments");
         return NSB_ERR_INVALID;
     }
     if (cudaSetDevice(gpu) != cudaSuccess) return NSB_ERR_NO_DEVICE;
-    const int N = n_cols, K = k_elems, rows = N + shift_rows + 8;
-    std::vector<uint16_t> ha((size_t)128 * K), hb((size_t)rows * K);
+    const int N = n_cols, K = k_elems, M = pair ? 256 : 128;
+    const int n_cta = pair ? N / 2 : N;            // B rows each CTA contributes
+    const int rows = n_cta + shift_rows + 8;       // B rows each CTA stores
+    const int nct = pair ? 2 : 1;
+    std::vector<uint16_t> ha((size_t)M * K), hb((size_t)nct * rows * K);
     std::vector<float> fa(ha.size()), fb(hb.size());
     uint64_t s = 0x9E3779B97F4A7C15ull;
     auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (float)((int)(s % 17) - 8) / 8.0f; };
@@ -150,18 +249,22 @@ int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int
     unsigned long long* dc = nullptr;
     cudaError_t e = cudaMalloc(&da, ha.size() * 2);
     if (e == cudaSuccess) e = cudaMalloc(&db, hb.size() * 2);
-    if (e == cudaSuccess) e = cudaMalloc(&dd, (size_t)128 * N * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dd, (size_t)M * N * 4);
     if (e == cudaSuccess) e = cudaMalloc(&dc, 16);
     if (e == cudaSuccess) e = cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
     const size_t smem = (size_t)128 * K * 2 + (size_t)((rows + 7) & ~7) * K * 2 + 4096;
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(pair ? (const void*)umma_pair_probe_kernel : (const void*)umma_probe_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-        umma_probe_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, layout, iters, dd, dc);
+        if (pair)
+            umma_pair_probe_kernel<<<2, 128, smem>>>(da, db, N, K, rows, shift_rows, lay, iters, dd, dc);
+        else
+            umma_probe_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, lay, iters, dd, dc);
         e = cudaDeviceSynchronize();
     }
-    std::vector<float> hd((size_t)128 * N);
+    std::vector<float> hd((size_t)M * N);
     unsigned long long hc[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpy(hd.data(), dd, hd.size() * 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost);
@@ -171,10 +274,11 @@ int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int
         return NSB_ERR_CUDA;
     }
     float worst = 0.f;
-    for (int m = 0; m < 128; ++m)
+    for (int m = 0; m < M; ++m)
         for (int n = 0; n < N; ++n) {
+            const int cta = n / n_cta, r = n % n_cta + shift_rows;
             float acc = 0.f;
-            for (int k = 0; k < K; ++k) acc += fa[(size_t)m * K + k] * fb[(size_t)(n + shift_rows) * K + k];
+            for (int k = 0; k < K; ++k) acc += fa[(size_t)m * K + k] * fb[((size_t)cta * rows + r) * K + k];
             worst = fmaxf(worst, fabsf(acc - hd[(size_t)m * N + n]));
         }
     if (max_err) *max_err = worst;
