@@ -14,69 +14,115 @@
 namespace nsb {
 
 // ---------------------------------------------------------------------------------------------
-// extract, channels-first.  The NCHW output is a flat [planes][81] array (plane = b*C + c), so
-// a block owns kPlanesPerBlock consecutive planes: 64 * 81 * 4 B = 20736 B, a multiple of 16, so
-// every block's output window is 16-byte aligned and is written with float4 stores.  The 64
-// feature bitboards (1 KB) are staged in shared memory once; each output element is the
-// reference's integer expression (extractbit.cu:20-37): bit(sq) * value-bits, never converted.
+// extract (stage 2).  Both layouts first turn every feature bitboard into {w0, w1, w2, value}:
+// bit t of the 81-bit string w2:w1:w0 is the plane's occupancy at OUTPUT position t, i.e. the
+// reference's rotation (extractbit.cu:20,26: sq = rotate ? 80 - t : t) and its lo/hi split
+// (:30-34) are resolved once per plane instead of once per element; an output element is then
+// value-bits AND -(bit), the reference's integer expression (:36-37), never converted.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPlanesPerBlock = 64;
 constexpr int kExtractThreads = 256;
 
-__device__ __forceinline__ uint32_t expand_bit(uint64_t lo, uint64_t hi, int t) {
-    const int rotate = (int)((hi >> 24) & 1ull);          // extractbit.cu:20
-    const uint32_t value = (uint32_t)(hi >> 32);          // :21
-    const int sq = rotate ? 80 - t : t;                   // :26
-    const int use_hi = sq >= 63;                          // :30-34
-    const uint64_t word = use_hi ? hi : lo;
-    const int sh = sq - 63 * use_hi;
-    return ((uint32_t)(word >> sh) & 1u) * value;         // :36-37
+__device__ __forceinline__ uint4 plane_string(uint4 f) {
+    uint32_t s0 = f.x;                                   // squares 0..31
+    uint32_t s1 = (f.y & 0x7FFFFFFFu) | (f.z << 31);     // squares 32..63 (63 = hi bit 0)
+    uint32_t s2 = (f.z >> 1) & 0x1FFFFu;                 // squares 64..80
+    if ((f.z >> 24) & 1u) {                              // out[t] = in[80 - t] == (96-bit reversal) >> 15
+        const uint32_t r0 = __brev(s2), r1 = __brev(s1), r2 = __brev(s0);
+        s0 = __funnelshift_r(r0, r1, 15);
+        s1 = __funnelshift_r(r1, r2, 15);
+        s2 = r2 >> 15;
+    }
+    return make_uint4(s0, s1, s2, f.w);
 }
 
+// the 32 bits of the plane string starting at output position t (t < 96)
+__device__ __forceinline__ uint32_t string_bits_from(uint4 p, int t) {
+    const int wi = t >> 5;
+    const uint32_t lo = wi == 0 ? p.x : (wi == 1 ? p.y : p.z);
+    const uint32_t hi = wi == 0 ? p.y : (wi == 1 ? p.z : 0u);
+    return __funnelshift_r(lo, hi, t & 31);
+}
+
+// Channels-first.  The NCHW output is a flat [planes][81] array (plane = b*C + c), so a block owns
+// kPlanesPerBlock consecutive planes: 64 * 81 * 4 B = 20736 B, a multiple of 16, so every block's
+// output window is 16-byte aligned and is written with 16-byte stores (4 consecutive positions of
+// one plane, or the seam between two planes).
 __global__ void __launch_bounds__(kExtractThreads)
 extract_nchw_kernel(const uint4* __restrict__ fb, long long planes_total, uint32_t* __restrict__ out) {
-    __shared__ uint4 s_fb[kPlanesPerBlock];
+    __shared__ uint4 s_pl[kPlanesPerBlock + 1];
     const long long plane0 = (long long)blockIdx.x * kPlanesPerBlock;
     const int nplanes = (int)min((long long)kPlanesPerBlock, planes_total - plane0);
-    if (threadIdx.x < nplanes) s_fb[threadIdx.x] = __ldg(&fb[plane0 + threadIdx.x]);
+    if (threadIdx.x < nplanes) s_pl[threadIdx.x] = plane_string(__ldg(&fb[plane0 + threadIdx.x]));
+    if (threadIdx.x == kPlanesPerBlock) s_pl[kPlanesPerBlock] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const int nelem = nplanes * 81;
     uint32_t* dst = out + plane0 * 81;
     const int nvec = nelem >> 2;
     for (int v = threadIdx.x; v < nvec; v += kExtractThreads) {
-        uint32_t r[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int idx = v * 4 + e;
-            const int pl = idx / 81, t = idx - pl * 81;
-            const uint4 f = s_fb[pl];
-            r[e] = expand_bit(((uint64_t)f.y << 32) | f.x, ((uint64_t)f.w << 32) | f.z, t);
+        const int idx = v * 4;
+        const int pl = idx / 81, t = idx - pl * 81;
+        const uint4 p = s_pl[pl];
+        uint32_t bits = string_bits_from(p, t);      // positions t .. t+3 of this plane (bits past 80 are zero)
+        uint32_t v0 = p.w, v1 = p.w, v2 = p.w, v3 = p.w;
+        if (t > 77) {                                  // seam: the last 81 - t elements are this plane's
+            const uint4 pn = s_pl[pl + 1];
+            const int k = 81 - t;                      // 1..3 elements left in this plane
+            bits |= pn.x << k;
+            v1 = k > 1 ? p.w : pn.w;
+            v2 = k > 2 ? p.w : pn.w;
+            v3 = pn.w;
         }
-        reinterpret_cast<uint4*>(dst)[v] = make_uint4(r[0], r[1], r[2], r[3]);
+        reinterpret_cast<uint4*>(dst)[v] = make_uint4(v0 & (0u - (bits & 1u)), v1 & (0u - ((bits >> 1) & 1u)),
+                                                      v2 & (0u - ((bits >> 2) & 1u)), v3 & (0u - ((bits >> 3) & 1u)));
     }
     for (int idx = (nvec << 2) + threadIdx.x; idx < nelem; idx += kExtractThreads) {  // ragged tail
         const int pl = idx / 81, t = idx - pl * 81;
-        const uint4 f = s_fb[pl];
-        dst[idx] = expand_bit(((uint64_t)f.y << 32) | f.x, ((uint64_t)f.w << 32) | f.z, t);
+        const uint4 p = s_pl[pl];
+        dst[idx] = p.w & (0u - (string_bits_from(p, t) & 1u));
     }
 }
 
-// extract, channels-last (reference extractbit.cu:41-68; dead under the reference's current
-// config, globalconfig.h:20, but part of the extractBits<> API and of test_extractbit.cc).
-// One block per position; the position's C bitboards are staged in shared memory and the
-// [81][C] output window is written with coalesced 4-byte stores.
+// Channels-last (reference extractbit.cu:41-68; dead under the reference's current config,
+// globalconfig.h:20, but part of the extractBits<> API and of test_extractbit.cc).  One block per
+// position; the [81][C] output window is written with coalesced 8-byte stores when C is even
+// (the window is then 8-byte aligned for every position), 4-byte stores otherwise.
 __global__ void __launch_bounds__(256)
 extract_nhwc_kernel(const uint4* __restrict__ fb, int channels, uint32_t* __restrict__ out) {
-    extern __shared__ uint4 s_fbx[];
+    extern __shared__ uint32_t s_x[];   // [3][C] plane-string words (word-major), then [C] values
+    uint32_t* s_w = s_x;
+    uint32_t* s_v = s_x + 3 * channels;
     const long long b = blockIdx.x;
-    for (int c = threadIdx.x; c < channels; c += blockDim.x) s_fbx[c] = __ldg(&fb[b * channels + c]);
+    for (int c = threadIdx.x; c < channels; c += blockDim.x) {
+        const uint4 p = plane_string(__ldg(&fb[b * channels + c]));
+        s_w[c] = p.x;
+        s_w[channels + c] = p.y;
+        s_w[2 * channels + c] = p.z;
+        s_v[c] = p.w;
+    }
     __syncthreads();
     uint32_t* dst = out + b * 81 * channels;
     const int nelem = 81 * channels;
-    for (int idx = threadIdx.x; idx < nelem; idx += blockDim.x) {
-        const int t = idx / channels, c = idx - t * channels;
-        const uint4 f = s_fbx[c];
-        dst[idx] = expand_bit(((uint64_t)f.y << 32) | f.x, ((uint64_t)f.w << 32) | f.z, t);
+    if ((channels & 1) == 0) {
+        const int npair = nelem >> 1, stride = (int)blockDim.x * 2;
+        const int dt = stride / channels, dc = stride - dt * channels;
+        int idx = 2 * (int)threadIdx.x;
+        int t = idx / channels, c = idx - t * channels;
+        for (int v = threadIdx.x; v < npair; v += blockDim.x) {
+            const uint2 w = *reinterpret_cast<const uint2*>(&s_w[(t >> 5) * channels + c]);
+            const uint2 val = *reinterpret_cast<const uint2*>(&s_v[c]);
+            const int sh = t & 31;
+            reinterpret_cast<uint2*>(dst)[v] =
+                make_uint2(val.x & (0u - ((w.x >> sh) & 1u)), val.y & (0u - ((w.y >> sh) & 1u)));
+            c += dc;
+            t += dt;
+            if (c >= channels) { c -= channels; ++t; }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < nelem; idx += blockDim.x) {
+            const int t = idx / channels, c = idx - t * channels;
+            dst[idx] = s_v[c] & (0u - ((s_w[(t >> 5) * channels + c] >> (t & 31)) & 1u));
+        }
     }
 }
 
@@ -93,16 +139,18 @@ int launch_extract(const nsb_feature_bitboard* d_fb, size_t n, int channels, int
         extract_nchw_kernel<<<grid, kExtractThreads, 0, s>>>(reinterpret_cast<const uint4*>(d_fb),
                                                              planes, reinterpret_cast<uint32_t*>(d_planes));
     } else {
-        extract_nhwc_kernel<<<(unsigned)n, 256, (size_t)channels * 16, s>>>(
+        extract_nhwc_kernel<<<(unsigned)n, 256, (size_t)channels * 16 + 16, s>>>(
             reinterpret_cast<const uint4*>(d_fb), channels, reinterpret_cast<uint32_t*>(d_planes));
     }
     return 1;
 }
 
 // ---------------------------------------------------------------------------------------------
-// pack: one warp per position.  Lanes scan the 81-byte board out of shared memory; lane c builds
-// channel c, c+32, c+64 (channel order: reference src/evaluate/preset.h:20-66, semantics
-// SURVEY.md App. A.2 — builder-defined, libnshogi absent).  Output: 86 x 16 B, coalesced.
+// pack: one warp per position.  Board planes: lane s holds the piece code of squares s, s+32, s+64
+// and MATCH.ANY hands every lane the occupancy word of its own piece code in one instruction, so
+// the 28 board planes cost three match instructions per position; lane c then assembles channels
+// c, c+32, c+64 (channel order: reference src/evaluate/preset.h:20-66, semantics SURVEY.md App.
+// A.2 — builder-defined, libnshogi absent).  Output: 86 x 16 B, coalesced.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPackWarps = 4;
 
@@ -121,24 +169,36 @@ __device__ __forceinline__ int stand_piece_of(int k /*0..25*/, int* need) {
 __global__ void __launch_bounds__(kPackWarps * 32)
 pack_positions_kernel(const nsb_position* __restrict__ pos, int n, uint4* __restrict__ fb) {
     __shared__ __align__(16) unsigned char s_pos[kPackWarps][112];
+    __shared__ uint32_t s_occ[kPackWarps][28][3];   // occupancy words of the 28 board planes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kPackWarps + warp;
     if (b >= n) return;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(pos + b);  // 108 B = 27 words
     if (lane < 27) reinterpret_cast<uint32_t*>(s_pos[warp])[lane] = __ldg(src + lane);
+    if (lane < 28) s_occ[warp][lane][0] = s_occ[warp][lane][1] = s_occ[warp][lane][2] = 0u;
     __syncwarp();
     const nsb_position* p = reinterpret_cast<const nsb_position*>(s_pos[warp]);
     const int me = p->side & 1, op = me ^ 1;
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
+        const int sq = blk * 32 + lane;
+        const int code = sq < 81 ? p->board[sq] : 0;              // 0 = empty, else 1 + type + 14 * colour
+        const uint32_t same = __match_any_sync(0xffffffffu, code);
+        if (code >= 1 && code <= 28 && (int)(__ffs(same) - 1) == lane) {
+            const int colour = (code - 1) / 14, pt = (code - 1) % 14;
+            s_occ[warp][(colour == me ? 0 : 14) + pt][blk] = same;
+        }
+    }
+    __syncwarp();
     const uint64_t rot = (uint64_t)me << 24;
     const uint64_t one = (uint64_t)0x3F800000u << 32;
     const uint64_t all_lo = (1ull << 63) - 1ull, all_hi = 0x3FFFFull;
     for (int c = lane; c < NSB_FEATURE_CHANNELS; c += 32) {
         uint64_t lo = 0, hi = 0, val = one;
-        if (c < 28) {
-            const int colour = c < 14 ? me : op, pt = c < 14 ? c : c - 14;
-            const int code = 1 + pt + 14 * colour;
-            for (int s = 0; s < 63; ++s) lo |= (uint64_t)(p->board[s] == code) << s;
-            for (int s = 63; s < 81; ++s) hi |= (uint64_t)(p->board[s] == code) << (s - 63);
+        if (c < 28) {   // squares 0..62 -> lo bits 0..62, squares 63..80 -> hi bits 0..17
+            const uint32_t w0 = s_occ[warp][c][0], w1 = s_occ[warp][c][1], w2 = s_occ[warp][c][2];
+            lo = (uint64_t)w0 | ((uint64_t)(w1 & 0x7FFFFFFFu) << 32);
+            hi = (uint64_t)(w1 >> 31) | ((uint64_t)(w2 & 0x1FFFFu) << 1);
         } else if (c < 80) {
             const int side = (c - 28) / 26, k = (c - 28) % 26;
             int need;
