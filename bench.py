@@ -269,6 +269,7 @@ def run_b200(args):
     e2e_fused = time_e2e(True)
     e2e_infer = time_e2e(False)
     clocks = sampler.stop()
+    selfplay = None if args.no_selfplay else selfplay_leg(args, info, rep, dev_device)
 
     # ---- roofline of the dominant (only) kernel ----------------------------------------------------------
     tf_burst, tf_sust, hbm, which = peaks()
@@ -279,7 +280,7 @@ def run_b200(args):
     tp = os.path.join(ROOT, "profiles", "trunk_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"{C}x{blocks}@{B}")
-    roofline = {"bound": "tensor", "kernel": f"trunk_fused_kernel<{C}>", "achieved": round(achieved, 2),
+    roofline = {"bound": "tensor", "kernel": "trunk_pair_kernel (256 ch, cta_group::2)" if C == 256 else f"trunk_fused_kernel<{C}>", "achieved": round(achieved, 2),
                 "peak": tf_burst, "unit": "TFLOP/s", "frac": round(achieved / tf_burst, 4),
                 "frac_of_sustained_peak": round(achieved / tf_sust, 4), "peak_source": which,
                 "flops_per_launch": flops_launch, "avg_launch_ms": round(avg_launch_ms, 5),
@@ -307,6 +308,8 @@ def run_b200(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "counters": counters,
     }
+    if selfplay is not None:
+        line["selfplay"] = selfplay
     if info.rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(synth, B, seconds=args.cpu_seconds)
     if info.rank == 0:
@@ -316,6 +319,34 @@ def run_b200(args):
         import torch.distributed as dist
         dist.destroy_process_group()
     return sink
+
+
+def selfplay_leg(args, info, rep, device):
+    """BASELINE.json's second metric, "self-play positions/sec" (configs[3]: 20x256 net, 1024 concurrent
+    games per GPU): the C++ self-play loop of nshogi-engine_b200/host/selfplay_sim.cc (frame pool, search
+    workers, pinned multi-slot evaluation worker) against infer::B200, one process per GPU, counters
+    summed over ranks.  Rules are synthetic (libnshogi is not available); the GPU path is the real one."""
+    exe = os.path.join(ROOT, "nshogi-engine_b200", "host", "nsb_selfplay_sim")
+    if not os.path.exists(exe):
+        return {"unavailable": "nsb_selfplay_sim not built"}
+    workers = max(2, min(8, (os.cpu_count() or 4) // max(1, info.world) - 1))
+    cmd = [exe, "--gpu", str(info.local_rank), "--channels", "256", "--blocks", "20", "--batch-size", "512",
+           "--frame-pool-size", "1024", "--num-search-workers", str(workers), "--seconds", str(args.selfplay_seconds),
+           "--warmup", "1.5"]
+    rep.barrier()
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=120 + args.selfplay_seconds)
+    if out.returncode != 0:
+        raise SystemExit(f"selfplay leg failed: {out.stderr[-400:]}")
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    counters, ms_max = rep.aggregate({"records": rec["records"], "games": rec["games"], "evals": rec["evals"],
+                                      "batches": rec["batches"]}, rec["seconds"] * 1e3, device=device)
+    return {"metric": "selfplay_positions_per_sec", "value": round(rep.whole_job_rate(counters["records"], ms_max), 1),
+            "unit": "positions/s", "leaf_evals_per_sec": round(rep.whole_job_rate(counters["evals"], ms_max), 1),
+            "games_per_sec": round(rep.whole_job_rate(counters["games"], ms_max), 2),
+            "avg_batch": round(counters["evals"] / max(counters["batches"], 1), 1), "seconds": rec["seconds"],
+            "config": {"workload": "self-play data generation, 20x256 ResNet, 1024 concurrent games per GPU",
+                       "batch_size": 512, "num_playouts": rec["num_playouts"], "full_search_ratio": rec["full_search_ratio"],
+                       "search_workers_per_gpu": workers, "slots": rec["slots"], "rules": rec["rules"]}}
 
 
 def cpu_baseline(synth, B, seconds=12.0, threads=None):
@@ -401,6 +432,8 @@ def main():
     ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--selfplay-seconds", type=float, default=6.0)
     ap.add_argument("--small-pool", action="store_true", help="8-batch input pool (profiling runs only)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -55,3 +55,26 @@ def test_host_bench_selfcheck_gpu(built):
     assert rec["ok"] and rec["rows_identical"] and rec["cache_hit"]
     assert rec["max_prob_diff"] < 1e-5 and rec["legal_moves"] >= 28
     assert rec["pipeline_evals_per_s"] > 0 and rec["infer_blocking_evals_per_s"] > 0
+
+
+def test_selfplay_sim_fails_loudly_without_gpu(built, nb):
+    if nb.device_count() > 0:
+        pytest.skip("GPU present")
+    out = subprocess.run([os.path.join(built, "nsb_selfplay_sim"), "--seconds", "0.1"], capture_output=True, text=True,
+                         timeout=60)
+    assert out.returncode == 2 and "no CPU fallback" in out.stderr
+
+
+@pytest.mark.gpu
+def test_selfplay_sim_gpu(built):
+    """Self-play loop (frame pool -> search workers -> pinned multi-slot evaluation worker -> back) on a
+    small net: every frame keeps cycling, batches fill up, no NaN rows, records are produced."""
+    out = subprocess.run([os.path.join(built, "nsb_selfplay_sim"), "--channels", "128", "--blocks", "2", "--batch-size", "128",
+                          "--frame-pool-size", "512", "--num-search-workers", "2", "--num-playouts", "8",
+                          "--seconds", "1.0", "--warmup", "0.3"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["nan_rows"] == 0 and rec["evals"] > 10000 and rec["records"] > 1000 and rec["games"] > 0
+    assert 1 <= rec["avg_batch"] <= 128
+    # a move is played every num_playouts (full search) or num_playouts / 4 (reduced search) evaluations
+    assert 2.0 <= rec["evals"] / rec["records"] <= 8.0
