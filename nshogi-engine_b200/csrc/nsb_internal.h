@@ -59,7 +59,9 @@ struct PairGeom {
     static constexpr int SPITCH = (GUARD + NCOLS + 11) | 1;
     static constexpr int BUF_BYTES = ((KCH * SPITCH * 16 + 127) / 128) * 128;
     static constexpr int XCH = 16;                        // channel chunks of one Cout half
-    static constexpr int XPITCH = NCOLS * 16;             // exchange buffer: [16 chunks][96 slots][16 B]
+    static constexpr int XROW = NCOLS * 16;               // bytes of one chunk's 96 slots (one bulk push)
+    static constexpr int XPITCH = (NCOLS + 1) * 16;       // exchange buffer chunk pitch: odd slot count, so that
+                                                          // the two chunks of one stmatrix hit different banks
     static constexpr int XBUF_BYTES = XCH * XPITCH;
     static constexpr int NSTAGES = 5;
     static constexpr int KC64 = C / 64;

@@ -174,12 +174,12 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                 if (residual) {
                     const uint32_t x_buf = bufA;  // == this layer's output buffer (updated in place)
                     const uint32_t dst_bar = map_to_cta(bar_skip, peer);
-                    if (lane == 0) mbar_arrive_expect_tx_remote(dst_bar, G::XBUF_BYTES);
+                    if (lane == 0) mbar_arrive_expect_tx_remote(dst_bar, G::XCH * G::XROW);
                     __syncwarp();
                     if (lane < G::XCH)
                         bulk_s2peer(map_to_cta(xbuf + lane * G::XPITCH, peer),
                                     x_buf + (uint32_t)(((G::XCH * peer + lane) * G::SPITCH + G::GUARD) * 16),
-                                    G::XPITCH, dst_bar);
+                                    G::XROW, dst_bar);
                 }
                 __syncwarp();
             }
@@ -245,13 +245,13 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            mbar_arrive_expect_tx_remote(dst_bar, 2 * G::XPITCH);
+                            mbar_arrive_expect_tx_remote(dst_bar, 2 * G::XROW);
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 const int xc = q * 4 + lb * 2 + j;
                                 bulk_s2peer(map_to_cta(out_base + (uint32_t)(((G::XCH * rank + xc) * G::SPITCH + G::GUARD) * 16),
                                                        peer),
-                                            xbuf + xc * G::XPITCH, G::XPITCH, dst_bar);
+                                            xbuf + xc * G::XPITCH, G::XROW, dst_bar);
                             }
                         }
                     }

@@ -173,10 +173,13 @@ def test_forward_fuzzed_feature_values(nb, orc, synth, ctx128):
     assert np.max(np.abs(win - ow)) < 4 * TOL_VALUE_VS_BF16_ORACLE
 
 
-def test_forward_matches_oracle_256(nb, orc, synth):
+@pytest.mark.parametrize("n", [1, 2, 5])
+def test_forward_matches_oracle_256(nb, orc, synth, n):
+    """256 channels run on the CTA-pair kernel (cta_group::2 MMAs, DSMEM exchange of half of every
+    layer's output and of the skip rows); n = 1 and 5 leave the second CTA of the last pair without
+    a position."""
     desc = nb.net_desc(256, 2)
     blob = nb.random_blob(desc, 99)
-    n = 5
     pos = synth.random_positions(n, seed=256)
     fb = orc.pack(pos)
     with nb.Context(desc, batch_max=8, blob=blob) as ctx:
@@ -184,6 +187,44 @@ def test_forward_matches_oracle_256(nb, orc, synth):
     op, ow, od = orc.forward(desc, blob, orc.expand(fb, n), emulate_bf16=True)
     assert np.max(np.abs(policy - op)) < TOL_LOGIT_VS_BF16_ORACLE
     assert np.max(np.abs(win - ow)) < TOL_VALUE_VS_BF16_ORACLE and np.max(np.abs(draw - od)) < TOL_VALUE_VS_BF16_ORACLE
+
+
+def test_pair_kernel_equals_single_cta_kernel(nb, orc, synth, monkeypatch):
+    """The CTA-pair kernel accumulates every output element in the same K order as the one-CTA
+    kernel, so the two must agree bit for bit - at a size where the pairs run several passes
+    (513 positions -> 257 groups over 74 pairs) and with the fused decode on."""
+    desc = nb.net_desc(256, 3)
+    blob = nb.random_blob(desc, 7)
+    n, base = 513, 24
+    pos = synth.random_positions(base, seed=11)
+    fb = orc.pack(pos).reshape(base, 86)
+    perm = np.random.default_rng(2).integers(0, base, size=n)
+    perm[:base] = np.arange(base)
+    big = np.ascontiguousarray(fb[perm].reshape(-1))
+    off, idx = synth.random_legal_moves(n, seed=5, edge_rows=False)
+
+    def run(single):
+        if single:
+            monkeypatch.setenv("NSB_TRUNK256", "single")
+        else:
+            monkeypatch.delenv("NSB_TRUNK256", raising=False)
+        policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+        win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        legal = np.zeros(int(off[-1]), dtype=np.float32)
+        flag = np.zeros(n, dtype=np.uint8)
+        with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+            ctx.eval_async(0, big, n, policy, win, draw)
+            ctx.await_(0)
+            ctx.eval_decode_async(0, big, n, off, idx, nb.DECODE_PROBS, legal, win, draw, flag)
+            ctx.await_(0)
+        return policy, win, draw, legal
+
+    p1, w1, d1, l1 = run(single=True)
+    p2, w2, d2, l2 = run(single=False)
+    assert np.array_equal(p1.view(np.uint32), p2.view(np.uint32))
+    assert np.array_equal(w1, w2) and np.array_equal(d1, d2) and np.array_equal(l1.view(np.uint32), l2.view(np.uint32))
+    # batch-index invariance across pairs / passes / CTA rank
+    assert np.array_equal(p2.view(np.uint32), p2[:base][perm].view(np.uint32))
 
 
 def test_fused_decode_equals_separate_decode(nb, orc, synth, ctx128):
