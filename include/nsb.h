@@ -176,6 +176,45 @@ int nsb_decode_device(nsb_ctx* ctx, int slot, const float* d_policy, const float
                       const uint16_t* d_move_idx, int mode, float* d_legal_out,
                       uint8_t* d_nan_flag);
 
+/* ---- device-resident evaluation cache --------------------------------- */
+
+/* Replaces EvalCache::EvalCache(MemorySize MiB) (reference src/mcts/evalcache.cc:17-47) with a
+ * table in HBM: rows of <= 164 legal-move values + win + draw keyed by the 64-bit state hash,
+ * bundles of 3 entries in recency order, bundle = hash % NumBundle, try-lock per bundle (a busy
+ * bundle drops the operation, evalcache.cc:58-62,127-131).  One cache per ctx, shared by its slots.
+ * A cache holds whatever the decode mode of the launches that fill it produced (probabilities for
+ * MCTS, feedworker.cc:135; raw logits for self-play, frame.cc:110-114): use one mode per cache. */
+int nsb_cache_create(nsb_ctx* ctx, size_t memory_mb);
+int nsb_cache_clear(nsb_ctx* ctx);
+uint64_t nsb_cache_num_bundles(nsb_ctx* ctx);
+
+/* == EvalCache::store (evalcache.cc:49-121) for a batch of CSR rows on device pointers; rows with
+ * d_skip[i] != 0 (NaN rows, feedworker.cc:134) are not stored; d_stored[i] (optional) = 1 when the
+ * entry is present afterwards. */
+int nsb_cache_store_device(nsb_ctx* ctx, int slot, const uint64_t* d_hashes, size_t n,
+                           const uint32_t* d_move_off, const float* d_legal, const float* d_win,
+                           const float* d_draw, const uint8_t* d_skip, uint8_t* d_stored);
+
+/* == EvalCache::load (evalcache.cc:123-169) + the caller's move-count check
+ * (src/mcts/searchworker.cc:545-556) for a batch: hits get their row / win / draw written and
+ * d_hit[i] = 1; misses are appended (in no particular order) to d_miss_idx[0 .. *d_miss_count). */
+int nsb_cache_probe_device(nsb_ctx* ctx, int slot, const uint64_t* d_hashes, size_t n,
+                           const uint32_t* d_move_off, float* d_legal_out, float* d_win, float* d_draw,
+                           uint8_t* d_hit, int* d_miss_idx, int* d_miss_count);
+
+/* nsb_eval_decode_async behind the cache: probe, evaluate only the misses (the trunk launch works
+ * on the probe's miss list), and store every evaluated row whose nan flag is clear - the sequence
+ * searchworker.cc:540-559 -> evaluation -> feedworker.cc:134-135, in two kernel launches.
+ * hit_flag[i] (optional) = 1 when position i was served from the cache. */
+int nsb_eval_cached_decode_async(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* features, size_t n,
+                                 const uint64_t* hashes, const uint32_t* move_off, const uint16_t* move_idx,
+                                 int mode, float* legal_out, float* win, float* draw, uint8_t* nan_flag,
+                                 uint8_t* hit_flag);
+int nsb_eval_cached_decode_device(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* d_features, size_t n,
+                                  const uint64_t* d_hashes, const uint32_t* d_move_off,
+                                  const uint16_t* d_move_idx, int mode, float* d_legal_out, float* d_win,
+                                  float* d_draw, uint8_t* d_nan_flag, uint8_t* d_hit);
+
 /* Stream of a slot as an opaque cudaStream_t (for event timing from the host side). */
 void* nsb_stream(nsb_ctx* ctx, int slot);
 

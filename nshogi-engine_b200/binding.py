@@ -67,6 +67,13 @@ SIGNATURES = {
     "nsb_extract_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_int, C.c_int, _P]),
     "nsb_pack_positions_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P]),
     "nsb_decode_device": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P, _P, C.c_int, _P, _P]),
+    "nsb_cache_create": (C.c_int, [_P, C.c_size_t]),
+    "nsb_cache_clear": (C.c_int, [_P]),
+    "nsb_cache_num_bundles": (C.c_uint64, [_P]),
+    "nsb_cache_store_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P, _P, _P]),
+    "nsb_cache_probe_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P, _P, _P, _P]),
+    "nsb_eval_cached_decode_async": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "nsb_eval_cached_decode_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "nsb_debug_trunk_timeline": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     "nsb_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double)]),
@@ -328,6 +335,37 @@ class Context:
     def decode_device(self, slot, d_policy, d_win, d_draw, n, d_off, d_idx, mode, d_legal, d_flag):
         _check(lib().nsb_decode_device(self._h, slot, _ptr(d_policy), _ptr(d_win), _ptr(d_draw), n, _ptr(d_off),
                                        _ptr(d_idx), mode, _ptr(d_legal), _ptr(d_flag)), "nsb_decode_device")
+
+    # -- device-resident evaluation cache ------------------------------------------------------------
+    def cache_create(self, memory_mb: int):
+        _check(lib().nsb_cache_create(self._h, memory_mb), "nsb_cache_create")
+
+    def cache_clear(self):
+        _check(lib().nsb_cache_clear(self._h), "nsb_cache_clear")
+
+    def cache_num_bundles(self) -> int:
+        return int(lib().nsb_cache_num_bundles(self._h))
+
+    def cache_store_device(self, slot, d_hashes, n, d_off, d_legal, d_win, d_draw, d_skip=None, d_stored=None):
+        _check(lib().nsb_cache_store_device(self._h, slot, _ptr(d_hashes), n, _ptr(d_off), _ptr(d_legal), _ptr(d_win),
+                                            _ptr(d_draw), _ptr(d_skip), _ptr(d_stored)), "nsb_cache_store_device")
+
+    def cache_probe_device(self, slot, d_hashes, n, d_off, d_legal, d_win, d_draw, d_hit, d_miss_idx, d_miss_count):
+        _check(lib().nsb_cache_probe_device(self._h, slot, _ptr(d_hashes), n, _ptr(d_off), _ptr(d_legal), _ptr(d_win),
+                                            _ptr(d_draw), _ptr(d_hit), _ptr(d_miss_idx), _ptr(d_miss_count)),
+               "nsb_cache_probe_device")
+
+    def eval_cached_decode_async(self, slot, features, n, hashes, move_off, move_idx, mode, legal_out, win, draw,
+                                 nan_flag=None, hit_flag=None):
+        _check(lib().nsb_eval_cached_decode_async(self._h, slot, _ptr(features), n, _ptr(hashes), _ptr(move_off),
+                                                  _ptr(move_idx), mode, _ptr(legal_out), _ptr(win), _ptr(draw),
+                                                  _ptr(nan_flag), _ptr(hit_flag)), "nsb_eval_cached_decode_async")
+
+    def eval_cached_decode_device(self, slot, d_features, n, d_hashes, d_off, d_idx, mode, d_legal, d_win, d_draw,
+                                  d_flag, d_hit):
+        _check(lib().nsb_eval_cached_decode_device(self._h, slot, _ptr(d_features), n, _ptr(d_hashes), _ptr(d_off),
+                                                   _ptr(d_idx), mode, _ptr(d_legal), _ptr(d_win), _ptr(d_draw),
+                                                   _ptr(d_flag), _ptr(d_hit)), "nsb_eval_cached_decode_device")
 
     def debug_trunk_timeline(self, slot, d_features, n):
         nl = 2 * self.desc.blocks + 2

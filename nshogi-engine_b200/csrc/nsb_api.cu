@@ -37,6 +37,11 @@ struct Slot {
     uint32_t* d_off = nullptr;
     uint16_t* d_idx = nullptr;
     uint8_t* d_flag = nullptr;
+    // cached evaluation (allocated by nsb_cache_create)
+    uint64_t* d_hash = nullptr;
+    uint8_t* d_hit = nullptr;
+    int* d_miss_idx = nullptr;
+    int* d_miss_count = nullptr;
     std::vector<cudaEvent_t> ev;  // start/stop pairs, one pair per trunk launch since the last await
     size_t ev_used = 0;
 };
@@ -46,6 +51,7 @@ struct Slot {
 struct nsb_ctx {
     int gpu = 0, batch_max = 0, num_sms = 0;
     int max_pairs = 0;  // co-resident CTA pairs of the 256-channel trunk (0: single-CTA kernel)
+    nsb::DeviceCache cache{};  // device-resident evaluation cache (nsb_cache_create)
     nsb_net_desc desc{};
     bool loaded = false, timing = false;
     nsb::DeviceNet net{};
@@ -184,10 +190,13 @@ void nsb_destroy(nsb_ctx* c) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_feat); cudaFree(s.d_pos); cudaFree(s.d_policy); cudaFree(s.d_win); cudaFree(s.d_draw);
         cudaFree(s.d_legal); cudaFree(s.d_off); cudaFree(s.d_idx); cudaFree(s.d_flag);
+        cudaFree(s.d_hash); cudaFree(s.d_hit); cudaFree(s.d_miss_idx); cudaFree(s.d_miss_count);
         for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (void* p : c->d_weights) cudaFree(p);
+    cudaFree(c->cache.entries);
+    cudaFree(c->cache.meta);
     delete c;
 }
 
@@ -491,6 +500,184 @@ int nsb_eval_decode_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_f
     a.nan_flag = d_nan_flag;
     a.decode_mode = mode;
     return run_trunk(c, c->slots[slot], a);
+}
+
+/* ---- device-resident evaluation cache (reference src/mcts/evalcache.{h,cc}) -------------------- */
+
+int nsb_cache_create(nsb_ctx* c, size_t memory_mb) {
+    int rc = check_ctx(c, 0);
+    if (rc) return rc;
+    if (memory_mb == 0 || memory_mb > 160 * 1024) {
+        set_error("nsb_cache_create: memory_mb must be in 1..163840");
+        return NSB_ERR_INVALID;
+    }
+    if (c->cache.num_bundles) {
+        set_error("nsb_cache_create: this ctx already has a cache");
+        return NSB_ERR_STATE;
+    }
+    NSB_CUDA(cudaSetDevice(c->gpu));
+    // evalcache.cc:17-19: NumBundle = MemorySize MiB / (entry size * bundle size)
+    const unsigned long long bundles = (unsigned long long)memory_mb * 1024ull * 1024ull / (3ull * sizeof(CacheEntry) + 4ull);
+    DeviceCache dc{};
+    dc.num_bundles = bundles;
+    cudaError_t e = cudaMalloc(&dc.entries, bundles * 3ull * sizeof(CacheEntry));
+    if (e == cudaSuccess) e = cudaMalloc(&dc.meta, bundles * sizeof(uint32_t));
+    const size_t B = (size_t)c->batch_max;
+    for (auto& s : c->slots) {
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_hash, B * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_hit, B);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_miss_idx, B * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_miss_count, sizeof(int));
+    }
+    if (e != cudaSuccess) {
+        cudaFree(dc.entries);
+        cudaFree(dc.meta);
+        set_error("nsb_cache_create: device allocation of %zu MiB failed: %s", memory_mb, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? NSB_ERR_NOMEM : NSB_ERR_CUDA;
+    }
+    c->cache = dc;
+    return nsb_cache_clear(c);
+}
+
+int nsb_cache_clear(nsb_ctx* c) {
+    int rc = check_ctx(c, 0);
+    if (rc) return rc;
+    if (!c->cache.num_bundles) {
+        set_error("nsb_cache_clear: no cache (call nsb_cache_create)");
+        return NSB_ERR_STATE;
+    }
+    for (auto& s : c->slots) NSB_CUDA(cudaStreamSynchronize(s.stream));
+    int k = launch_cache_clear(c->cache, c->slots[0].stream);
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    NSB_CUDA(cudaStreamSynchronize(c->slots[0].stream));
+    return 0;
+}
+
+uint64_t nsb_cache_num_bundles(nsb_ctx* c) { return c ? (uint64_t)c->cache.num_bundles : 0; }
+
+static int check_cache(nsb_ctx* c, int slot, const char* who) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if (!c->cache.num_bundles) {
+        set_error("%s: no cache (call nsb_cache_create)", who);
+        return NSB_ERR_STATE;
+    }
+    return 0;
+}
+
+int nsb_cache_store_device(nsb_ctx* c, int slot, const uint64_t* d_hashes, size_t n, const uint32_t* d_move_off,
+                           const float* d_legal, const float* d_win, const float* d_draw, const uint8_t* d_skip,
+                           uint8_t* d_stored) {
+    int rc = check_cache(c, slot, "nsb_cache_store_device");
+    if (rc) return rc;
+    if (!d_hashes || !d_move_off || !d_legal || !d_win || !d_draw) {
+        set_error("nsb_cache_store_device: null buffer");
+        return NSB_ERR_INVALID;
+    }
+    int k = launch_cache_store(c->cache, d_hashes, n, d_move_off, d_legal, d_win, d_draw, d_skip, d_stored,
+                               c->slots[slot].stream);
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    return 0;
+}
+
+int nsb_cache_probe_device(nsb_ctx* c, int slot, const uint64_t* d_hashes, size_t n, const uint32_t* d_move_off,
+                           float* d_legal_out, float* d_win, float* d_draw, uint8_t* d_hit, int* d_miss_idx,
+                           int* d_miss_count) {
+    int rc = check_cache(c, slot, "nsb_cache_probe_device");
+    if (rc) return rc;
+    if (!d_hashes || !d_move_off || !d_legal_out || !d_win || !d_draw || !d_hit || !d_miss_idx || !d_miss_count) {
+        set_error("nsb_cache_probe_device: null buffer");
+        return NSB_ERR_INVALID;
+    }
+    Slot& s = c->slots[slot];
+    NSB_CUDA(cudaMemsetAsync(d_miss_count, 0, sizeof(int), s.stream));
+    int k = launch_cache_probe(c->cache, d_hashes, n, d_move_off, d_legal_out, d_win, d_draw, d_hit, nullptr, d_miss_idx,
+                               d_miss_count, s.stream);
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    return 0;
+}
+
+// probe -> trunk on the misses (fused decode + fused store); everything on the slot's stream
+static int eval_cached_enqueue(nsb_ctx* c, Slot& s, const nsb_feature_bitboard* d_features, size_t n,
+                               const uint64_t* d_hashes, const uint32_t* d_off, const uint16_t* d_idx, int mode,
+                               float* d_legal, float* d_win, float* d_draw, uint8_t* d_nan_flag, uint8_t* d_hit) {
+    NSB_CUDA(cudaMemsetAsync(s.d_miss_count, 0, sizeof(int), s.stream));
+    int k = launch_cache_probe(c->cache, d_hashes, n, d_off, d_legal, d_win, d_draw, d_hit, d_nan_flag, s.d_miss_idx,
+                               s.d_miss_count, s.stream);
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    EvalArgs a{};
+    a.features = d_features;
+    a.n = (int)n;
+    a.win = d_win;
+    a.draw = d_draw;
+    a.move_off = d_off;
+    a.move_idx = d_idx;
+    a.legal_out = d_legal;
+    a.nan_flag = d_nan_flag;
+    a.decode_mode = mode;
+    a.index = s.d_miss_idx;
+    a.count = s.d_miss_count;
+    a.hashes = d_hashes;
+    a.cache = c->cache;
+    return run_trunk(c, s, a);
+}
+
+int nsb_eval_cached_decode_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n,
+                                  const uint64_t* d_hashes, const uint32_t* d_move_off, const uint16_t* d_move_idx,
+                                  int mode, float* d_legal_out, float* d_win, float* d_draw, uint8_t* d_nan_flag,
+                                  uint8_t* d_hit) {
+    int rc = check_cache(c, slot, "nsb_eval_cached_decode_device");
+    if (rc) return rc;
+    if ((rc = check_batch(c, n, true))) return rc;
+    if (!d_features || !d_hashes || !d_move_off || !d_move_idx || !d_legal_out || !d_win || !d_draw || !d_hit ||
+        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+        set_error("nsb_eval_cached_decode_device: null buffer or bad mode");
+        return NSB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    return eval_cached_enqueue(c, c->slots[slot], d_features, n, d_hashes, d_move_off, d_move_idx, mode, d_legal_out, d_win,
+                               d_draw, d_nan_flag, d_hit);
+}
+
+int nsb_eval_cached_decode_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, size_t n,
+                                 const uint64_t* hashes, const uint32_t* move_off, const uint16_t* move_idx, int mode,
+                                 float* legal_out, float* win, float* draw, uint8_t* nan_flag, uint8_t* hit_flag) {
+    int rc = check_cache(c, slot, "nsb_eval_cached_decode_async");
+    if (rc) return rc;
+    if ((rc = check_batch(c, n, true))) return rc;
+    if (!features || !hashes || !move_off || !move_idx || !legal_out || !win || !draw ||
+        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+        set_error("nsb_eval_cached_decode_async: null buffer or bad mode");
+        return NSB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    const size_t total = move_off[n];
+    if (move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) {
+        set_error("nsb_eval_cached_decode_async: move_off must start at 0 and hold at most %d moves per position",
+                  NSB_MAX_LEGAL_MOVES);
+        return NSB_ERR_INVALID;
+    }
+    Slot& s = c->slots[slot];
+    NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
+                             cudaMemcpyHostToDevice, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(s.d_hash, hashes, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(s.d_off, move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    if (total)
+        NSB_CUDA(cudaMemcpyAsync(s.d_idx, move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
+    rc = eval_cached_enqueue(c, s, s.d_feat, n, s.d_hash, s.d_off, s.d_idx, mode, s.d_legal, s.d_win, s.d_draw, s.d_flag,
+                             s.d_hit);
+    if (rc) return rc;
+    if (total)
+        NSB_CUDA(cudaMemcpyAsync(legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    if (nan_flag) NSB_CUDA(cudaMemcpyAsync(nan_flag, s.d_flag, n, cudaMemcpyDeviceToHost, s.stream));
+    if (hit_flag) NSB_CUDA(cudaMemcpyAsync(hit_flag, s.d_hit, n, cudaMemcpyDeviceToHost, s.stream));
+    return 0;
 }
 
 int nsb_debug_trunk_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n,

@@ -96,6 +96,22 @@ struct DeviceNet {
     const float* fc2b;     // [2]
 };
 
+// Device-resident evaluation cache (cache_device.cuh; reference src/mcts/evalcache.h:28-38 rows).
+struct CacheEntry {
+    uint64_t hash;
+    uint32_t n;  // number of legal moves of the row (<= 164)
+    uint32_t pad0;
+    float win, draw;
+    float policy[NSB_CACHE_MAX_MOVES];
+    uint32_t pad1[2];
+};
+static_assert(sizeof(CacheEntry) == 688, "cache entry is 688 bytes (16-byte multiple)");
+struct DeviceCache {
+    CacheEntry* entries;            // [num_bundles][3]
+    uint32_t* meta;                 // [num_bundles]: lock bit 31 | used bits 8..10 | recency order bits 0..5
+    unsigned long long num_bundles; // 0 = no cache
+};
+
 struct EvalArgs {
     const nsb_feature_bitboard* features;  // [n][86]
     int n;
@@ -108,6 +124,12 @@ struct EvalArgs {
     uint8_t* nan_flag;
     int decode_mode;
     unsigned long long* timeline;  // optional (diagnostics): CTA 0 writes 4 clock64 stamps per layer
+    // cached evaluation (optional): the launch works on the positions index[0 .. *count) (the misses
+    // of a preceding cache probe) instead of 0 .. n-1, and stores every decoded row under hashes[b]
+    const int* index;
+    const int* count;
+    const uint64_t* hashes;
+    DeviceCache cache;
 };
 
 // host-side weight handling (weights.cc)
@@ -127,6 +149,13 @@ int launch_decode(const float* d_policy, const float* d_win, const float* d_draw
                   const uint32_t* d_off, const uint16_t* d_idx, int mode, float* d_out,
                   uint8_t* d_flag, cudaStream_t s);
 int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s);
+int launch_cache_probe(const DeviceCache& c, const uint64_t* d_hashes, size_t n, const uint32_t* d_off, float* d_legal,
+                       float* d_win, float* d_draw, uint8_t* d_hit, uint8_t* d_nan_flag, int* d_miss_idx, int* d_miss_count,
+                       cudaStream_t s);
+int launch_cache_store(const DeviceCache& c, const uint64_t* d_hashes, size_t n, const uint32_t* d_off,
+                       const float* d_legal, const float* d_win, const float* d_draw, const uint8_t* d_skip,
+                       uint8_t* d_stored, cudaStream_t s);
+int launch_cache_clear(const DeviceCache& c, cudaStream_t s);
 int trunk_fused_prepare(int channels);  // sets max dynamic smem attribute
 int trunk_pair_prepare(int* max_pairs);  // same for the CTA-pair kernel; reports co-resident clusters
 int launch_trunk_pair(const DeviceNet& net, const EvalArgs& a, int max_pairs, cudaStream_t s);

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "cache_device.cuh"
 #include "decode_device.cuh"
 #include "epilogue.cuh"
 #include "nsb_internal.h"
@@ -39,21 +40,27 @@ __device__ __forceinline__ uint4 plane_bits(uint4 f) {
     return make_uint4(s0, s1, s2, (uint32_t)f32_to_bf16_bits(__uint_as_float(f.w)));
 }
 
-// Stage 2 of feature extraction for the NPOS positions starting at batch index b0, executed by
+// A launch works on n positions, or - behind a cache probe - on the *count misses listed in index[].
+__device__ __forceinline__ int eval_count(const EvalArgs& a) { return a.count ? __ldg(a.count) : a.n; }
+// batch index of work-list entry li, -1 past the end
+__device__ __forceinline__ int eval_index(const EvalArgs& a, int li, int n_eff) {
+    return li < n_eff ? (a.index ? __ldg(a.index + li) : li) : -1;
+}
+
+// Stage 2 of feature extraction for the NPOS work-list entries starting at li0, executed by
 // the 256 epilogue threads (et = 0..255): bitboards -> featS (bit strings) -> 16-byte records
 // [chunk j][slot][8 channels] of the stem's B operand at `stem_buf` (generic pointer to slot 0 of
 // chunk 0 minus the guard, i.e. the buffer base).  `tl` (optional) receives clock64 stamps.
 template <int NPOS, int SPITCH, int GUARD>
-__device__ __forceinline__ void expand_features(const nsb_feature_bitboard* __restrict__ features, int n, int b0,
-                                                uint4* featS, uint8_t* stem_buf, int et,
-                                                unsigned long long* tl) {
+__device__ __forceinline__ void expand_features(const EvalArgs& a, int n_eff, int li0, uint4* featS, uint8_t* stem_buf,
+                                                int et, unsigned long long* tl) {
     // Per plane: the 81 occupancy bits as one contiguous little-endian bit string with the
     // rotation (extractbit.cu:20,26) already applied, plus the fill value as bf16 bits.
     for (int i = et; i < NPOS * NSB_FEATURE_CHANNELS; i += kEpiThreads) {
         const int pos = i / NSB_FEATURE_CHANNELS, c = i - pos * NSB_FEATURE_CHANNELS;
-        const int b = b0 + pos;
+        const int b = eval_index(a, li0 + pos, n_eff);
         uint4 f = make_uint4(0, 0, 0, 0);
-        if (b < n) f = __ldg(reinterpret_cast<const uint4*>(features) + (size_t)b * NSB_FEATURE_CHANNELS + c);
+        if (b >= 0) f = __ldg(reinterpret_cast<const uint4*>(a.features) + (size_t)b * NSB_FEATURE_CHANNELS + c);
         featS[i] = plane_bits(f);
     }
     if (tl) tl[9] = clock64();
@@ -127,22 +134,23 @@ __device__ __forceinline__ void fc1_prefetch(const DeviceNet& net, int et, float
     for (int t = 0; t < kFcPrefetch; ++t) wpre[t] = et < H ? __ldg(net.fc1t + (size_t)t * H + et) : 0.f;
 }
 
-// Tail of a pass for the NPOS positions at b0, executed by the 256 epilogue threads after the
+// Tail of a pass for the NPOS work-list entries at li0, executed by the 256 epilogue threads after the
 // logits (scratch[pos][2187], plane-major) and the value-conv plane (vbuf[pos][81], ReLU applied)
 // are in shared memory and a kEpiBar barrier has been passed: dense logits (the Infer contract,
 // trt.cc:265-267), value MLP FC(81 -> H) + ReLU, FC(H -> 2), sigmoid (one hidden unit per thread),
-// fused legal-move decode on logits that never left shared memory.  Ends with a kEpiBar barrier
-// (scratch / vbuf / red reusable).
+// fused legal-move decode on logits that never left shared memory and, when the launch carries a
+// cache, the store of the decoded row (feedworker.cc:134-135: rows with NaNs are not stored).  Ends
+// with a kEpiBar barrier (scratch / vbuf / red reusable).
 template <int NPOS>
-__device__ __forceinline__ void heads_tail(const DeviceNet& net, const EvalArgs& a, int b0, const float* scratch,
+__device__ __forceinline__ void heads_tail(const DeviceNet& net, const EvalArgs& a, int n_eff, int li0, const float* scratch,
                                            const float* vbuf, float* red, const float (&wpre)[kFcPrefetch], int et,
                                            unsigned long long* tl) {
     const int ew = et >> 5, lane = et & 31;
     const int H = net.hidden;
     if (a.policy != nullptr) {
         for (int idx = et; idx < NPOS * kPolicySize; idx += kEpiThreads) {
-            const int pos = idx / kPolicySize, b = b0 + pos;
-            if (b < a.n) a.policy[(size_t)b * kPolicySize + (idx - pos * kPolicySize)] = scratch[idx];
+            const int pos = idx / kPolicySize, b = eval_index(a, li0 + pos, n_eff);
+            if (b >= 0) a.policy[(size_t)b * kPolicySize + (idx - pos * kPolicySize)] = scratch[idx];
         }
     }
     if (tl) tl[5] = clock64();
@@ -190,21 +198,25 @@ __device__ __forceinline__ void heads_tail(const DeviceNet& net, const EvalArgs&
             for (int qq = 0; qq < kEpiWarps; ++qq) s += red[(qq * NPOS + pos) * 2 + k];
             const float val = 1.0f / (1.0f + expf(-s));
             red[kEpiWarps * NPOS * 2 + pos * 2 + k] = val;
-            const int b = b0 + pos;
-            if (b < a.n) (k == 0 ? a.win : a.draw)[b] = val;
+            const int b = eval_index(a, li0 + pos, n_eff);
+            if (b >= 0) (k == 0 ? a.win : a.draw)[b] = val;
         }
     }
     if (tl) tl[6] = clock64();
     if (a.move_off != nullptr) {
         named_bar_sync(kEpiBar, kEpiThreads);
         if (ew < NPOS) {
-            const int b = b0 + ew;
-            if (b < a.n) {
+            const int b = eval_index(a, li0 + ew, n_eff);
+            if (b >= 0) {
                 const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
+                const float w = red[kEpiWarps * NPOS * 2 + ew * 2 + 0], d = red[kEpiWarps * NPOS * 2 + ew * 2 + 1];
                 const bool bad = warp_decode_row(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
-                                                 a.decode_mode, red[kEpiWarps * NPOS * 2 + ew * 2 + 0],
-                                                 red[kEpiWarps * NPOS * 2 + ew * 2 + 1], a.legal_out + mb, lane);
+                                                 a.decode_mode, w, d, a.legal_out + mb, lane);
                 if (a.nan_flag && lane == 0) a.nan_flag[b] = bad ? 1 : 0;
+                if (a.hashes != nullptr && !bad) {  // every lane re-reads exactly the row elements it wrote
+                    __syncwarp();
+                    cache_store_warp(a.cache, __ldg(a.hashes + b), (int)(me - mb), a.legal_out + mb, w, d, lane);
+                }
             }
         }
     }

@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
         reinterpret_cast<volatile uint32_t*>(smem + G::OFF_BARS + 8 * (2 * G::NSTAGES + 2));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int groups = (a.n + G::NPOS - 1) / G::NPOS;
+    const int n_eff = eval_count(a);
+    const int groups = (n_eff + G::NPOS - 1) / G::NPOS;
     const int my_passes =
         (int)blockIdx.x < groups ? (groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int NL = net.num_layers;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
             if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 8] = clock64();
             unsigned long long* tl = (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) ? a.timeline + 4 * NL : nullptr;
-            expand_features<G::NPOS, G::SPITCH, G::GUARD>(a.features, a.n, b0, featS, smem + G::OFF_BUF_B, et, tl);
+            expand_features<G::NPOS, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
             mbar_arrive(bar_act);
             if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 2] = clock64();
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
             }
             named_bar_sync(kEpiBar, kEpiThreads);
             if (tl) tl[4] = clock64();
-            heads_tail<G::NPOS>(net, a, b0, scratch, vbuf, red, wpre, et, tl);
+            heads_tail<G::NPOS>(net, a, n_eff, b0, scratch, vbuf, red, wpre, et, tl);
         }
     }
 

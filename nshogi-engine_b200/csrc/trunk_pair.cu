@@ -57,7 +57,8 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
     const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
-    const int groups = (a.n + 1) / 2;
+    const int n_eff = eval_count(a);
+    const int groups = (n_eff + 1) / 2;
     const int my_passes = pair < groups ? (groups - pair + npairs - 1) / npairs : 0;
     const int NL = net.num_layers;
     const bool stamp = a.timeline && blockIdx.x == 0;
@@ -200,7 +201,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
             unsigned long long* tl = (stamp && p == 0 && et == 0) ? a.timeline + 4 * NL : nullptr;
             if (tl) tl[8] = clock64();
-            expand_features<1, G::SPITCH, G::GUARD>(a.features, a.n, b0, featS, smem + G::OFF_BUF_B, et, tl);
+            expand_features<1, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
             mbar_arrive(bar_act);
             if (et < kPushes) mbar_arrive_remote(map_to_cta(bar_act, peer));  // nothing to exchange for the stem input
@@ -276,7 +277,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
             }
             named_bar_sync(kEpiBar, kEpiThreads);
             if (tl) tl[4] = clock64();
-            heads_tail<1>(net, a, b0, scratch, vbuf, red, wpre, et, tl);
+            heads_tail<1>(net, a, n_eff, b0, scratch, vbuf, red, wpre, et, tl);
         }
     }
 
@@ -314,7 +315,7 @@ int trunk_pair_prepare(int* max_pairs) {
 
 int launch_trunk_pair(const DeviceNet& net, const EvalArgs& a, int max_pairs, cudaStream_t s) {
     if (a.n <= 0) return 0;
-    const int groups = (a.n + 1) / 2;
+    const int groups = (a.n + 1) / 2;  // upper bound when the launch works on a miss list
     const int pairs = groups < max_pairs ? groups : max_pairs;
     trunk_pair_kernel<<<2 * pairs, kThreads, PairGeom::SMEM_BYTES, s>>>(net, a);
     return 1;

@@ -1,13 +1,20 @@
 // eval_cache.h — the consumer of the decode step: an evaluation cache with the reference's
 // observable behaviour (reference src/mcts/evalcache.{h,cc}): rows of at most 164 legal-move
 // values + win rate + draw rate keyed by the 64-bit state hash; `Hash % NumBundle` picks a bundle
-// of 3 entries kept in most-recently-used order; store() and load() give up (return false) when
-// the bundle is busy instead of waiting (try_lock, evalcache.cc:60-66,135-139); store() of a
-// (hash, move-count) pair that is already present only refreshes its recency (:73-91); a full
-// bundle evicts its least recently used entry (:99-121).  Whether the row holds probabilities
-// (MCTS, src/mcts/feedworker.cc:135) or raw logits (self-play, src/selfplay/frame.cc:110-114) is the
-// caller's choice of decode mode.  Layout differs from the reference (flat bundles with an order
-// permutation instead of linked CacheData nodes); behaviour does not.
+// of 3 entries kept on a recency list; store() and load() give up (return false) when the bundle
+// is busy instead of waiting (try_lock, evalcache.cc:60-66,135-139); store() of a (hash, move-count)
+// pair that is already present only refreshes its recency (:73-91); a full bundle overwrites the
+// LAST entry of the list (:90-121).  Whether the row holds probabilities (MCTS,
+// src/mcts/feedworker.cc:135) or raw logits (self-play, src/selfplay/frame.cc:110-114) is the
+// caller's choice of decode mode.
+//
+// The recency list is the reference's, quirk included: its "move to front" (evalcache.cc:75-86)
+// never repairs the old head's Prev pointer, so an element that has been the head keeps
+// Prev == nullptr and the guard `Prev != nullptr` then refuses to move it again until its
+// predecessor is moved away.  Layout differs (flat bundles, an order permutation and one "Prev is
+// null" flag per list position instead of linked CacheData nodes); behaviour does not - it is
+// checked operation by operation against the reference's own evalcache.cc compiled in place
+// (tests/test_evalcache.py).
 #ifndef NSHOGI_ENGINE_MCTS_EVAL_CACHE_B200_H
 #define NSHOGI_ENGINE_MCTS_EVAL_CACHE_B200_H
 
@@ -109,13 +116,25 @@ class EvalCacheB200 {
     };
     struct Bundle {
         std::atomic_flag Busy = ATOMIC_FLAG_INIT;
-        uint8_t Order[BUNDLE_WAYS] = {0, 1, 2};  // way indices, most recently used first
+        uint8_t Order[BUNDLE_WAYS] = {0, 1, 2};  // way indices in list order (head first)
+        bool PrevNull[BUNDLE_WAYS] = {true, false, false};  // by list position: the element's Prev == nullptr
         Way Ways[BUNDLE_WAYS];
     };
-    static void touch(Bundle& B, int Pos) {  // move Order[Pos] to the front
-        const uint8_t W = B.Order[Pos];
-        for (int K = Pos; K > 0; --K) B.Order[K] = B.Order[K - 1];
-        B.Order[0] = W;
+    // evalcache.cc:75-86 on the list position Pos: nothing happens when the element's Prev is null;
+    // otherwise it becomes the head, the old head keeps its null Prev (now at position 1), and the
+    // element that followed the moved one inherits the moved one's (valid) Prev.
+    static void touch(Bundle& B, int Pos) {
+        if (B.PrevNull[Pos]) return;
+        const uint8_t O0 = B.Order[0], O1 = B.Order[1], O2 = B.Order[2];
+        if (Pos == 1) {
+            B.Order[0] = O1; B.Order[1] = O0; B.Order[2] = O2;
+            B.PrevNull[1] = true;
+            B.PrevNull[2] = false;
+        } else {
+            B.Order[0] = O2; B.Order[1] = O0; B.Order[2] = O1;
+            B.PrevNull[2] = B.PrevNull[1];
+            B.PrevNull[1] = true;
+        }
     }
 
     const std::size_t NumBundle;

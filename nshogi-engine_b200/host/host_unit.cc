@@ -1,6 +1,10 @@
 // host_unit.cc — CPU-only unit checks of the host-side pieces (no GPU, no CUDA calls):
 // EvalCacheB200 behaviour (reference src/mcts/evalcache.cc) and the move-index adaptor.
+// `--cache-trace NUM_BUNDLES_MIB` replays "s hash n win draw" / "l hash n" lines from stdin through
+// EvalCacheB200 and prints one result line per operation (tests/test_evalcache.py compares them
+// with the oracle and with the reference's own evalcache.cc).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <vector>
@@ -12,8 +16,32 @@ using namespace nshogi::engine;
 
 #define CHECK(c) do { if (!(c)) { std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 
-int main() {
-    {   // cache: store/load, 164-move cap, refresh-only on duplicate, LRU eviction within a bundle of 3
+static int cacheTrace(std::size_t MiB) {
+    mcts::EvalCacheB200 C(MiB);
+    std::printf("bundles %zu\n", C.numBundles());
+    char Op;
+    unsigned long long H;
+    unsigned N;
+    while (std::scanf(" %c %llu %u", &Op, &H, &N) == 3) {
+        if (Op == 's') {
+            float W, D;
+            if (std::scanf("%f %f", &W, &D) != 2) return 1;
+            std::vector<float> Row(N);
+            for (unsigned J = 0; J < N; ++J) Row[J] = W + (float)J;  // the row is a function of (win, j)
+            std::printf("%d\n", C.store(H, (uint16_t)N, Row.data(), W, D) ? 1 : 0);
+        } else {
+            mcts::EvalCacheB200::EvalInfo E;
+            const bool Hit = C.load(H, &E) && E.NumMoves == N;  // searchworker.cc:545-556
+            if (Hit) std::printf("1 %.9g %.9g %.9g\n", E.WinRate, E.DrawRate, N ? E.Policy[N - 1] : 0.f);
+            else std::printf("0\n");
+        }
+    }
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 3 && std::strcmp(argv[1], "--cache-trace") == 0) return cacheTrace((std::size_t)std::atoi(argv[2]));
+    {   // cache: store/load, 164-move cap, refresh-only on duplicate, the reference's replacement order
         mcts::EvalCacheB200 C(1);
         const size_t NB = C.numBundles();
         CHECK(NB > 0);
@@ -29,9 +57,11 @@ int main() {
         CHECK(C.load(42, &E) && E.Policy[0] == 0.f && E.WinRate == 0.5f);
         const uint64_t H1 = 42 + NB, H2 = 42 + 2 * NB, H3 = 42 + 3 * NB;  // same bundle
         CHECK(C.store(H1, 3, P, 0.1f, 0.f) && C.store(H2, 3, P, 0.2f, 0.f));
-        CHECK(C.load(42, &E));                               // 42 becomes most recent; H1 is now LRU
-        CHECK(C.store(H3, 3, P, 0.3f, 0.f));                 // evicts H1
-        CHECK(!C.load(H1, &E) && C.load(42, &E) && C.load(H2, &E) && C.load(H3, &E) && E.WinRate == 0.3f);
+        // list is now H2, H1, 42 and both H1 and 42 have been heads: their Prev is null, so this hit
+        // does NOT move 42 to the front (evalcache.cc:146 guard) ...
+        CHECK(C.load(42, &E));
+        CHECK(C.store(H3, 3, P, 0.3f, 0.f));                 // ... and the full bundle overwrites its last entry: 42
+        CHECK(!C.load(42, &E) && C.load(H1, &E) && C.load(H2, &E) && C.load(H3, &E) && E.WinRate == 0.3f);
         // feed(): CSR rows, > 164 moves skipped
         const uint32_t Off[4] = {0, 2, 2 + 170, 2 + 170 + 1};
         std::vector<float> Legal(Off[3], 0.25f);

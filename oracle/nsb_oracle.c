@@ -445,3 +445,102 @@ double nsb_oracle_cpu_path(const nsb_position* pos, size_t n_pos, const uint32_t
     free(jobs);
     return (double)threads * batches_per_thread * batch / sec;
 }
+
+
+/* ---- evaluation cache: restatement of reference src/mcts/evalcache.{h,cc} ---------------------- */
+#define NSB_ORACLE_CACHE_ROW 164 /* evalcache.h:26 MAX_CACHE_MOVES_COUNT */
+#define NSB_ORACLE_BUNDLE 3      /* evalcache.h:44 CACHE_BUNDLE_SIZE     */
+
+typedef struct cache_elem {
+    int used;
+    uint64_t hash;
+    uint32_t n;
+    float row[NSB_ORACLE_CACHE_ROW];
+    float win, draw;
+    struct cache_elem *next, *prev;
+} cache_elem;
+
+struct nsb_oracle_cache {
+    uint64_t num_bundles;
+    cache_elem* mem;
+    cache_elem** head;
+};
+
+nsb_oracle_cache* nsb_oracle_cache_create(uint64_t num_bundles) { /* evalcache.cc:17-47 */
+    nsb_oracle_cache* c = (nsb_oracle_cache*)calloc(1, sizeof *c);
+    c->num_bundles = num_bundles;
+    c->mem = (cache_elem*)calloc((size_t)num_bundles * NSB_ORACLE_BUNDLE, sizeof(cache_elem));
+    c->head = (cache_elem**)calloc((size_t)num_bundles, sizeof(cache_elem*));
+    for (uint64_t b = 0; b < num_bundles; ++b) {
+        cache_elem* e = c->mem + b * NSB_ORACLE_BUNDLE;
+        c->head[b] = e;
+        for (int j = 0; j < NSB_ORACLE_BUNDLE; ++j) {
+            e[j].used = 0;
+            e[j].prev = j ? &e[j - 1] : NULL;
+            e[j].next = j + 1 < NSB_ORACLE_BUNDLE ? &e[j + 1] : NULL;
+        }
+    }
+    return c;
+}
+
+void nsb_oracle_cache_destroy(nsb_oracle_cache* c) {
+    if (!c) return;
+    free(c->mem);
+    free(c->head);
+    free(c);
+}
+
+/* The "Reorder" blocks of evalcache.cc:75-86,96-107,146-157, statement for statement.  Note what they
+ * do NOT do: the old head's Prev is left NULL.  An element that has been the head therefore looks
+ * like the head forever after (its Prev is only repaired when its predecessor is moved away), and
+ * `Prev != nullptr` - the guard of every reorder - keeps it where it is.  This is the reference's
+ * observable replacement policy, so it is restated, not repaired. */
+static void cache_to_front(cache_elem** head, cache_elem* e) {
+    if (e->prev == NULL) return;
+    e->prev->next = e->next;
+    if (e->next) e->next->prev = e->prev;
+    e->next = *head;
+    e->prev = NULL;
+    *head = e;
+}
+
+int nsb_oracle_cache_store(nsb_oracle_cache* c, uint64_t hash, uint32_t n, const float* row, float win, float draw) {
+    if (n > NSB_ORACLE_CACHE_ROW) return 0; /* :51-53 */
+    cache_elem** head = &c->head[hash % c->num_bundles];
+    cache_elem* e = *head;
+    for (;;) {
+        if (!e->used) break;                    /* :66-68 */
+        if (e->hash == hash && e->n == n) {     /* :70-88: already there, refresh recency only */
+            cache_to_front(head, e);
+            return 1;
+        }
+        if (e->next == NULL) break;             /* :90-92: overwrite the least recent entry */
+        e = e->next;
+    }
+    cache_to_front(head, e);
+    e->used = 1;
+    e->hash = hash;
+    e->n = n;
+    memcpy(e->row, row, sizeof(float) * n);
+    e->win = win;
+    e->draw = draw;
+    return 1;
+}
+
+int nsb_oracle_cache_load(nsb_oracle_cache* c, uint64_t hash, uint32_t expected_n, float* row, float* win, float* draw) {
+    cache_elem** head = &c->head[hash % c->num_bundles];
+    for (cache_elem* e = *head; e != NULL; e = e->next) {
+        if (!e->used) break;                    /* :136-138 */
+        if (e->hash == hash) {                  /* :140-160 */
+            const int usable = e->n == expected_n; /* searchworker.cc:546 */
+            if (usable) {
+                memcpy(row, e->row, sizeof(float) * e->n);
+                *win = e->win;
+                *draw = e->draw;
+            }
+            cache_to_front(head, e);
+            return usable;
+        }
+    }
+    return 0;
+}

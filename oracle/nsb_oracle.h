@@ -69,6 +69,16 @@ double nsb_oracle_cpu_path(const nsb_position* pos, size_t n_pos, const uint32_t
                            int batches_per_thread, int with_expand, nsb_fill_fn fill,
                            nsb_fill_make_fn mk, double* seconds_out);
 
+/* reference src/mcts/evalcache.{h,cc}: bundles of 3 entries on a recency list, bundle = hash %
+ * num_bundles; store (:49-121) and load (:123-169; the caller's move-count check of
+ * src/mcts/searchworker.cc:545-556 is applied by `expected_n`).  Single-threaded, so the try-lock
+ * never fails.  load returns 1 on a usable hit (row / win / draw filled), 0 otherwise. */
+typedef struct nsb_oracle_cache nsb_oracle_cache;
+nsb_oracle_cache* nsb_oracle_cache_create(uint64_t num_bundles);
+void nsb_oracle_cache_destroy(nsb_oracle_cache* c);
+int nsb_oracle_cache_store(nsb_oracle_cache* c, uint64_t hash, uint32_t n, const float* row, float win, float draw);
+int nsb_oracle_cache_load(nsb_oracle_cache* c, uint64_t hash, uint32_t expected_n, float* row, float* win, float* draw);
+
 float nsb_oracle_bf16_round(float x);
 
 #ifdef __cplusplus

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libnsb_oracle.so")
 REF_RANDOM = os.path.join(HERE, "_ref", "libnsb_ref_random.so")
 REF_EXTRACT = os.path.join(HERE, "_ref", "libnsb_ref_extractbit.so")
+REF_EVALCACHE = os.path.join(HERE, "_ref", "libnsb_ref_evalcache.so")
 
 POLICY_SIZE = 2187
 FEATURE_CHANNELS = 86
@@ -172,3 +173,67 @@ def cpu_path(pos, off, idx, batch: int, threads: int, batches_per_thread: int, w
     v = lib().nsb_oracle_cpu_path(pos.ctypes.data, len(pos), off.ctypes.data, idx.ctypes.data, batch, threads,
                                   batches_per_thread, int(with_expand), fill, mk, C.byref(sec))
     return float(v), float(sec.value)
+
+
+class Cache:
+    """Restatement of reference src/mcts/evalcache.{h,cc} (single-threaded)."""
+
+    def __init__(self, num_bundles: int):
+        l = lib()
+        l.nsb_oracle_cache_create.restype = _P
+        l.nsb_oracle_cache_create.argtypes = [C.c_uint64]
+        l.nsb_oracle_cache_destroy.argtypes = [_P]
+        l.nsb_oracle_cache_store.argtypes = [_P, C.c_uint64, C.c_uint32, _P, C.c_float, C.c_float]
+        l.nsb_oracle_cache_load.argtypes = [_P, C.c_uint64, C.c_uint32, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        self._h = l.nsb_oracle_cache_create(num_bundles)
+
+    def store(self, h: int, row: np.ndarray, win: float, draw: float) -> bool:
+        row = np.ascontiguousarray(row, dtype=np.float32)
+        return bool(lib().nsb_oracle_cache_store(self._h, h, len(row), row.ctypes.data, win, draw))
+
+    def load(self, h: int, expected_n: int):
+        row = np.zeros(max(expected_n, 1), dtype=np.float32)
+        w, d = C.c_float(0), C.c_float(0)
+        ok = bool(lib().nsb_oracle_cache_load(self._h, h, expected_n, row.ctypes.data, C.byref(w), C.byref(d)))
+        return ok, row[:expected_n], float(w.value), float(d.value)
+
+    def close(self):
+        if self._h:
+            lib().nsb_oracle_cache_destroy(self._h)
+            self._h = None
+
+
+def have_ref_evalcache() -> bool:
+    return os.path.exists(REF_EVALCACHE)
+
+
+class RefCache:
+    """The reference's own EvalCache (src/mcts/evalcache.cc compiled in place into oracle/_ref)."""
+
+    def __init__(self, memory_mb: int):
+        l = C.CDLL(REF_EVALCACHE)
+        l.nsb_ref_evalcache_make.restype = _P
+        l.nsb_ref_evalcache_make.argtypes = [C.c_size_t]
+        l.nsb_ref_evalcache_free.argtypes = [_P]
+        l.nsb_ref_evalcache_num_bundles.restype = C.c_uint64
+        l.nsb_ref_evalcache_num_bundles.argtypes = [_P]
+        l.nsb_ref_evalcache_store.argtypes = [_P, C.c_uint64, C.c_uint32, _P, C.c_float, C.c_float]
+        l.nsb_ref_evalcache_load.argtypes = [_P, C.c_uint64, C.c_uint32, _P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        self._l = l
+        self._h = l.nsb_ref_evalcache_make(memory_mb)
+        self.num_bundles = int(l.nsb_ref_evalcache_num_bundles(self._h))
+
+    def store(self, h: int, row: np.ndarray, win: float, draw: float) -> bool:
+        row = np.ascontiguousarray(row, dtype=np.float32)
+        return bool(self._l.nsb_ref_evalcache_store(self._h, h, len(row), row.ctypes.data, win, draw))
+
+    def load(self, h: int, expected_n: int):
+        row = np.zeros(max(expected_n, 164), dtype=np.float32)
+        w, d = C.c_float(0), C.c_float(0)
+        ok = bool(self._l.nsb_ref_evalcache_load(self._h, h, expected_n, row.ctypes.data, C.byref(w), C.byref(d)))
+        return ok, row[:expected_n], float(w.value), float(d.value)
+
+    def close(self):
+        if self._h:
+            self._l.nsb_ref_evalcache_free(self._h)
+            self._h = None

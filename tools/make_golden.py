@@ -59,3 +59,33 @@ np.savez_compressed(os.path.join(out, "forward_small.npz"), positions=pos.view(n
                                                                        dtype=np.uint8),
                     policy_fp32=p32, win_fp32=w32, draw_fp32=d32, policy_bf16=p16, win_bf16=w16, draw_bf16=d16)
 print("golden written to", out, {f: os.path.getsize(os.path.join(out, f)) for f in os.listdir(out)})
+
+# 4. evaluation-cache trace from the REFERENCE's own src/mcts/evalcache.cc (compiled in place):
+#    4000 operations over 18 keys that collide in 3 bundles, rows are a function of (win, j)
+assert orc.have_ref_evalcache(), "oracle/_ref/libnsb_ref_evalcache.so missing (needs /root/reference)"
+ref = orc.RefCache(1)
+NB = ref.num_bundles
+rng = np.random.default_rng(20240203)
+keys = np.array([b + k * NB for b in (3, 4, 5) for k in range(6)], dtype=np.uint64)
+n_ops = 4000
+op = (rng.random(n_ops) < 0.5).astype(np.uint8)                       # 1 = store, 0 = load
+key = keys[rng.integers(0, len(keys), size=n_ops)]
+cnt = rng.choice(np.array([1, 3, 3, 3, 5, 164, 165], dtype=np.uint32), size=n_ops)
+win = rng.random(n_ops).astype(np.float32)
+draw = rng.random(n_ops).astype(np.float32)
+res = np.zeros(n_ops, dtype=np.uint8)
+got_win = np.zeros(n_ops, dtype=np.float32)
+got_last = np.zeros(n_ops, dtype=np.float32)
+for i in range(n_ops):
+    if op[i]:
+        row = (win[i] + np.arange(cnt[i], dtype=np.float32)).astype(np.float32)
+        res[i] = ref.store(int(key[i]), row, float(win[i]), float(draw[i]))
+    else:
+        ok, row, w, d = ref.load(int(key[i]), int(cnt[i]))
+        res[i] = ok
+        if ok:
+            got_win[i], got_last[i] = w, row[-1]
+ref.close()
+np.savez_compressed(os.path.join(out, "evalcache_trace.npz"), num_bundles=np.uint64(NB), op=op, key=key, cnt=cnt, win=win,
+                    draw=draw, res=res, got_win=got_win, got_last=got_last)
+print("evalcache trace:", n_ops, "ops,", int(res[op == 0].sum()), "hits of", int((op == 0).sum()), "loads")
