@@ -210,6 +210,13 @@ int nsb_eval_cached_decode_async(nsb_ctx* ctx, int slot, const nsb_feature_bitbo
                                  const uint64_t* hashes, const uint32_t* move_off, const uint16_t* move_idx,
                                  int mode, float* legal_out, float* win, float* draw, uint8_t* nan_flag,
                                  uint8_t* hit_flag);
+/* The same from compact position records (stage 1 on the device first): the self-play evaluation
+ * step of src/selfplay/evaluationworker.cc:87-108 behind Frame's evaluation cache
+ * (src/selfplay/frame.cc:89-114). */
+int nsb_eval_positions_cached_decode_async(nsb_ctx* ctx, int slot, const nsb_position* positions, size_t n,
+                                           const uint64_t* hashes, const uint32_t* move_off,
+                                           const uint16_t* move_idx, int mode, float* legal_out, float* win,
+                                           float* draw, uint8_t* nan_flag, uint8_t* hit_flag);
 int nsb_eval_cached_decode_device(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* d_features, size_t n,
                                   const uint64_t* d_hashes, const uint32_t* d_move_off,
                                   const uint16_t* d_move_idx, int mode, float* d_legal_out, float* d_win,

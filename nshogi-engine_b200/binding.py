@@ -73,6 +73,8 @@ SIGNATURES = {
     "nsb_cache_store_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P, _P, _P]),
     "nsb_cache_probe_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P, _P, _P, _P]),
     "nsb_eval_cached_decode_async": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "nsb_eval_positions_cached_decode_async": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, C.c_int, _P, _P, _P, _P,
+                                                         _P]),
     "nsb_eval_cached_decode_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "nsb_debug_trunk_timeline": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     "nsb_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
@@ -360,6 +362,13 @@ class Context:
         _check(lib().nsb_eval_cached_decode_async(self._h, slot, _ptr(features), n, _ptr(hashes), _ptr(move_off),
                                                   _ptr(move_idx), mode, _ptr(legal_out), _ptr(win), _ptr(draw),
                                                   _ptr(nan_flag), _ptr(hit_flag)), "nsb_eval_cached_decode_async")
+
+    def eval_positions_cached_decode_async(self, slot, positions, n, hashes, move_off, move_idx, mode, legal_out, win,
+                                           draw, nan_flag=None, hit_flag=None):
+        _check(lib().nsb_eval_positions_cached_decode_async(self._h, slot, _ptr(positions), n, _ptr(hashes),
+                                                            _ptr(move_off), _ptr(move_idx), mode, _ptr(legal_out),
+                                                            _ptr(win), _ptr(draw), _ptr(nan_flag), _ptr(hit_flag)),
+               "nsb_eval_positions_cached_decode_async")
 
     def eval_cached_decode_device(self, slot, d_features, n, d_hashes, d_off, d_idx, mode, d_legal, d_win, d_draw,
                                   d_flag, d_hit):

@@ -52,10 +52,18 @@ __device__ __forceinline__ uint32_t cache_move_to_front(uint32_t meta, int i) {
 }
 
 // Warp-uniform try-lock of the bundle word; on success *meta is its content without the lock bit.
-__device__ __forceinline__ bool cache_try_lock_warp(uint32_t* word, uint32_t* meta, int lane) {
-    uint32_t old = 0;
-    if (lane == 0) old = atomicOr(word, kCacheLockBit);
-    old = __shfl_sync(0xffffffffu, old, 0);
+// `tries` = 1 is the reference's try_lock (a busy bundle drops the operation).  The batch probe uses
+// a short bounded retry instead: batches of concurrent streams tend to touch the same bundles within
+// the same microsecond, and a dropped load costs a whole network evaluation, while the holder (one
+// warp, a few hundred nanoseconds, never waiting on anything) is certain to release.
+__device__ __forceinline__ bool cache_try_lock_warp(uint32_t* word, uint32_t* meta, int lane, int tries = 1) {
+    uint32_t old = kCacheLockBit;
+    for (int t = 0; t < tries; ++t) {
+        if (lane == 0) old = atomicOr(word, kCacheLockBit);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (!(old & kCacheLockBit)) break;
+        if (t + 1 < tries) __nanosleep(200);
+    }
     if (old & kCacheLockBit) return false;
     __threadfence();  // acquire: entry reads below must not be satisfied before the lock is held
     *meta = old;
@@ -107,12 +115,13 @@ __device__ __forceinline__ bool cache_store_warp(const DeviceCache& c, uint64_t 
 // evalcache.cc:123-169 + the caller's move-count check (searchworker.cc:545-556): returns true and
 // fills row[0..expected_n), *win, *draw when an entry with this hash exists AND has expected_n moves.
 // A hash match with a different move count still refreshes the entry's recency, as in the reference.
+constexpr int kCacheProbeTries = 64;
 __device__ __forceinline__ bool cache_load_warp(const DeviceCache& c, uint64_t hash, int expected_n, float* row, float* win,
                                                 float* draw, int lane) {
     const unsigned long long bundle = hash % c.num_bundles;
     uint32_t* word = c.meta + bundle;
     uint32_t meta;
-    if (!cache_try_lock_warp(word, &meta, lane)) return false;
+    if (!cache_try_lock_warp(word, &meta, lane, kCacheProbeTries)) return false;
     const CacheEntry* base = c.entries + bundle * 3;
     bool match = false;
     uint32_t n_e = 0, slot = 0;

@@ -680,6 +680,47 @@ int nsb_eval_cached_decode_async(nsb_ctx* c, int slot, const nsb_feature_bitboar
     return 0;
 }
 
+int nsb_eval_positions_cached_decode_async(nsb_ctx* c, int slot, const nsb_position* positions, size_t n,
+                                           const uint64_t* hashes, const uint32_t* move_off, const uint16_t* move_idx,
+                                           int mode, float* legal_out, float* win, float* draw, uint8_t* nan_flag,
+                                           uint8_t* hit_flag) {
+    int rc = check_cache(c, slot, "nsb_eval_positions_cached_decode_async");
+    if (rc) return rc;
+    if ((rc = check_batch(c, n, true))) return rc;
+    if (!positions || !hashes || !move_off || !move_idx || !legal_out || !win || !draw ||
+        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+        set_error("nsb_eval_positions_cached_decode_async: null buffer or bad mode");
+        return NSB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    const size_t total = move_off[n];
+    if (move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) {
+        set_error("nsb_eval_positions_cached_decode_async: move_off must start at 0 and hold at most %d moves per position",
+                  NSB_MAX_LEGAL_MOVES);
+        return NSB_ERR_INVALID;
+    }
+    Slot& s = c->slots[slot];
+    NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(s.d_hash, hashes, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(s.d_off, move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    if (total)
+        NSB_CUDA(cudaMemcpyAsync(s.d_idx, move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
+    int k = launch_pack_positions(s.d_pos, n, s.d_feat, s.stream);
+    if (k < 0) return k;
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    rc = eval_cached_enqueue(c, s, s.d_feat, n, s.d_hash, s.d_off, s.d_idx, mode, s.d_legal, s.d_win, s.d_draw, s.d_flag,
+                             s.d_hit);
+    if (rc) return rc;
+    if (total)
+        NSB_CUDA(cudaMemcpyAsync(legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    if (nan_flag) NSB_CUDA(cudaMemcpyAsync(nan_flag, s.d_flag, n, cudaMemcpyDeviceToHost, s.stream));
+    if (hit_flag) NSB_CUDA(cudaMemcpyAsync(hit_flag, s.d_hit, n, cudaMemcpyDeviceToHost, s.stream));
+    return 0;
+}
+
 int nsb_debug_trunk_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n,
                              uint64_t* host_stamps, size_t max_stamps) {
     int rc = check_ctx(c, slot);

@@ -69,6 +69,16 @@ class B200 : public Infer {
         check(nsb_load_weights(Ctx_, Blob.data(), Blob.size()), "nsb_load_weights");
     }
 
+    // Device-resident evaluation cache shared by this executor's slots (reference: one EvalCache per
+    // Manager, src/mcts/manager.cc:202-206; here it lives in HBM next to the kernels that fill it).
+    void enableCache(std::size_t MemoryMiB) {
+        check(nsb_cache_create(Ctx_, MemoryMiB), "nsb_cache_create");
+        HasCache_ = true;
+    }
+    bool hasCache() const {
+        return HasCache_;
+    }
+
     void resetGPU() {  // trt.cc:289-291
         check(nsb_bind_thread(Ctx_), "nsb_bind_thread");
     }
@@ -116,6 +126,7 @@ class B200 : public Infer {
     const int Slots_;
     nsb_net_desc Desc_;
     nsb_ctx* Ctx_ = nullptr;
+    bool HasCache_ = false;
 };
 
 } // namespace infer

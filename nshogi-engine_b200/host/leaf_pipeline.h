@@ -28,11 +28,13 @@ class LeafPipeline {
         nsb_position* Positions = nullptr;         // [BatchMax]       (packed-position mode)
         uint32_t* MoveOffsets = nullptr;           // [BatchMax + 1]   CSR of legal-move policy indices
         uint16_t* MoveIndices = nullptr;           // [BatchMax * 593] values of ml::getMoveIndex
+        uint64_t* Hashes = nullptr;                // [BatchMax]       state hashes (only read when the executor has a cache)
         // outputs, valid after collect()
         float* Legal = nullptr;                    // per legal move: probabilities or raw logits
         float* WinRate = nullptr;
         float* DrawRate = nullptr;
         uint8_t* NanFlag = nullptr;
+        uint8_t* HitFlag = nullptr;                // 1 = served from the device-resident cache
         std::size_t Count = 0;
         bool InFlight = false;
     };
@@ -48,6 +50,8 @@ class LeafPipeline {
             alloc(S.WinRate, BatchMax);
             alloc(S.DrawRate, BatchMax);
             alloc(S.NanFlag, BatchMax);
+            alloc(S.Hashes, BatchMax);
+            alloc(S.HitFlag, BatchMax);
         }
     }
     ~LeafPipeline() {
@@ -75,11 +79,27 @@ class LeafPipeline {
         return Slots[I];
     }
 
-    // Enqueue H2D + stage 1 (if FromPositions) + expansion + forward + fused decode + D2H.
-    void submit(std::size_t Index, std::size_t Count, bool FromPositions, int DecodeMode = NSB_DECODE_PROBS) {
+    // Enqueue H2D + stage 1 (if FromPositions) + expansion + forward + fused decode + D2H.  With
+    // UseCache (executor built with enableCache) the batch goes through the device-resident cache:
+    // hits are served from HBM, only the misses are evaluated, evaluated rows are stored.
+    void submit(std::size_t Index, std::size_t Count, bool FromPositions, int DecodeMode = NSB_DECODE_PROBS,
+                bool UseCache = false) {
         Slot& S = Slots[Index];
         S.Count = Count;
         if (Count == 0) return;
+        if (UseCache) {
+            const int R =
+                FromPositions
+                    ? nsb_eval_positions_cached_decode_async(Ex->context(), (int)Index, S.Positions, Count, S.Hashes,
+                                                             S.MoveOffsets, S.MoveIndices, DecodeMode, S.Legal, S.WinRate,
+                                                             S.DrawRate, S.NanFlag, S.HitFlag)
+                    : nsb_eval_cached_decode_async(Ex->context(), (int)Index, S.Features, Count, S.Hashes, S.MoveOffsets,
+                                                   S.MoveIndices, DecodeMode, S.Legal, S.WinRate, S.DrawRate, S.NanFlag,
+                                                   S.HitFlag);
+            infer::B200::check(R, "LeafPipeline::submit (cached)");
+            S.InFlight = true;
+            return;
+        }
         const int R = FromPositions
                           ? nsb_eval_positions_decode_async(Ex->context(), (int)Index, S.Positions, Count, S.MoveOffsets,
                                                             S.MoveIndices, DecodeMode, S.Legal, S.WinRate, S.DrawRate,

@@ -11,8 +11,10 @@
 // What is SYNTHETIC, because libnshogi (rules, move generation, repetition, declaration) is not
 // available in this build: tree descent is replaced by a few random piece relocations of the root
 // position, legal moves by a random set of distinct policy slots (count ~ N(80, 35) clipped to
-// [1, 593]), game length by U[80, 200] plies.  --descent-ns adds a busy wait per leaf to model the
-// CPU cost of a real descent.  Records are counted, not written (saveworker.cc writes one teacher
+// [1, 593], a function of the position), game length by U[80, 200] plies.  --descent-ns adds a busy
+// wait per leaf to model the CPU cost of a real descent; --revisit-ratio makes that fraction of the
+// descents end in a recently visited leaf (transpositions) and --cache-mb puts the device-resident
+// evaluation cache (Frame::setEvaluationCache, frame.cc:89-114) in front of the network.  Records are counted, not written (saveworker.cc writes one teacher
 // record per played position).
 #include <atomic>
 #include <chrono>
@@ -44,6 +46,10 @@ struct Frame {  // reference src/selfplay/frame.h: one game in flight
     uint32_t PlayoutsLeft = 0, Ply = 0, GameLen = 0;
     float Win = 0.f, Draw = 0.f, PolicyMass = 0.f;
     Phase P = Phase::LeafSelection;
+    uint64_t Hash = 0;         // state hash of the leaf (key of the evaluation cache)
+    nsb_position Recent[4];    // leaves visited lately: --revisit-ratio re-descends to one of them
+    uint32_t RecentCount = 0;
+    bool CacheHit = false;
 };
 
 inline uint64_t next(uint64_t& S) {  // xorshift64*
@@ -87,8 +93,15 @@ class FrameQueue {  // reference src/selfplay/framequeue.h
 };
 
 struct Info {  // reference src/selfplay/selfplayinfo.h
-    std::atomic<uint64_t> Evals{0}, Batches{0}, Records{0}, Games{0}, NanRows{0};
+    std::atomic<uint64_t> Evals{0}, Batches{0}, Records{0}, Games{0}, NanRows{0}, CacheHits{0};
 };
+
+inline uint64_t hashPosition(const nsb_position& P) {  // stand-in for core::State::getHash(): FNV-1a of the record
+    const unsigned char* B = reinterpret_cast<const unsigned char*>(&P);
+    uint64_t H = 0xCBF29CE484222325ull;
+    for (std::size_t I = 0; I < sizeof(nsb_position); ++I) H = (H ^ B[I]) * 0x100000001B3ull;
+    return H;
+}
 
 nsb_position startpos() {  // hirate; squares s = 9 * (file - 1) + (rank - 1)
     nsb_position P;
@@ -131,8 +144,8 @@ void newGame(Frame& F, uint32_t Playouts) {
 
 struct Options {
     int Channels = 256, Blocks = 20, Batch = 512, Frames = 1024, SearchWorkers = 4, Slots = 3, GPU = 0;
-    int Playouts = 200, DescentNs = 0;
-    double FullSearchRatio = 0.25, Seconds = 5.0, Warmup = 1.0;
+    int Playouts = 200, DescentNs = 0, CacheMiB = 0;
+    double FullSearchRatio = 0.25, Seconds = 5.0, Warmup = 1.0, RevisitRatio = 0.0;
 };
 
 uint32_t playoutsFor(const Options& O, uint64_t& Rng) {  // worker.cc:184-197
@@ -160,17 +173,27 @@ void searchWorker(const Options& O, FrameQueue* SearchQueue, FrameQueue* Evaluat
                     }
                 }
             }
-            // LeafSelection: descend (synthetic), list the leaf's legal moves as policy slots
-            F->Leaf = F->Root;
-            const int Depth = 1 + (int)(next(F->Rng) % 6);
-            for (int D = 0; D < Depth; ++D) relocate(F->Leaf, F->Rng);
+            // LeafSelection: descend (synthetic) - or, with --revisit-ratio, reach a leaf seen lately
+            // (a transposition) - and list the leaf's legal moves as policy slots.  The move list is a
+            // function of the position, as it is with a real move generator.
+            const double U = (double)(next(F->Rng) >> 11) * (1.0 / 9007199254740992.0);
+            if (F->RecentCount > 0 && U < O.RevisitRatio) {
+                F->Leaf = F->Recent[next(F->Rng) % F->RecentCount];
+            } else {
+                F->Leaf = F->Root;
+                const int Depth = 1 + (int)(next(F->Rng) % 6);
+                for (int D = 0; D < Depth; ++D) relocate(F->Leaf, F->Rng);
+                F->Recent[F->RecentCount < 4 ? F->RecentCount++ : next(F->Rng) % 4] = F->Leaf;
+            }
+            F->Hash = hashPosition(F->Leaf);
+            uint64_t MoveRng = F->Hash | 1ull;
             // n ~ N(80, 35) by the sum of 4 uniforms, clipped to [1, 593]
             double Z = 0.0;
-            for (int K = 0; K < 4; ++K) Z += (double)(next(F->Rng) >> 11) * (1.0 / 9007199254740992.0);
+            for (int K = 0; K < 4; ++K) Z += (double)(next(MoveRng) >> 11) * (1.0 / 9007199254740992.0);
             int N = (int)(80.0 + 35.0 * (Z - 2.0) * 1.7320508);
             N = N < 1 ? 1 : (N > NSB_MAX_LEGAL_MOVES ? NSB_MAX_LEGAL_MOVES : N);
-            const uint32_t Start = (uint32_t)(next(F->Rng) % NSB_POLICY_SIZE);
-            uint32_t Stride = 1 + (uint32_t)(next(F->Rng) % (NSB_POLICY_SIZE - 1));
+            const uint32_t Start = (uint32_t)(next(MoveRng) % NSB_POLICY_SIZE);
+            uint32_t Stride = 1 + (uint32_t)(next(MoveRng) % (NSB_POLICY_SIZE - 1));
             if (Stride % 3 == 0) ++Stride;  // 2187 = 3^7: any stride not divisible by 3 visits distinct slots
             for (int J = 0; J < N; ++J) F->MoveIdx[J] = (uint16_t)((Start + (uint64_t)J * Stride) % NSB_POLICY_SIZE);
             F->NumMoves = (uint32_t)N;
@@ -209,6 +232,7 @@ void evaluationWorker(const Options& O, infer::B200* Exec, FrameQueue* Evaluatio
             for (uint32_t J = 0; J < F->NumMoves; ++J) Mass += Row[J];
             F->PolicyMass = Mass;
             if (S.NanFlag[I]) SI->NanRows.fetch_add(1, std::memory_order_relaxed);
+            if (O.CacheMiB > 0 && S.HitFlag[I]) SI->CacheHits.fetch_add(1, std::memory_order_relaxed);
             F->P = Phase::Backpropagation;
         }
         SI->Evals.fetch_add(Fs.size(), std::memory_order_relaxed);
@@ -235,13 +259,15 @@ void evaluationWorker(const Options& O, infer::B200* Exec, FrameQueue* Evaluatio
         for (std::size_t I = 0; I < Tasks.size(); ++I) {
             const Frame* F = Tasks[I];
             S.Positions[I] = F->Leaf;
+            S.Hashes[I] = F->Hash;
             S.MoveOffsets[I] = Off;
             std::memcpy(S.MoveIndices + Off, F->MoveIdx, F->NumMoves * sizeof(uint16_t));
             Off += F->NumMoves;
         }
         S.MoveOffsets[Tasks.size()] = Off;
         SlotTasks[Idx].swap(Tasks);
-        Pipe.submit(Idx, SlotTasks[Idx].size(), /*FromPositions=*/true, NSB_DECODE_LOGITS);  // frame.cc:110-114
+        Pipe.submit(Idx, SlotTasks[Idx].size(), /*FromPositions=*/true, NSB_DECODE_LOGITS,  // frame.cc:110-114
+                    /*UseCache=*/O.CacheMiB > 0);
         InFlight.push_back(Idx);
     }
     while (!InFlight.empty()) {  // Worker::stop contract: drain before returning
@@ -268,6 +294,8 @@ int main(int argc, char** argv) {
         else if (A == "--num-playouts") O.Playouts = nextI();
         else if (A == "--full-search-ratio") O.FullSearchRatio = nextD();
         else if (A == "--descent-ns") O.DescentNs = nextI();
+        else if (A == "--cache-mb") O.CacheMiB = nextI();
+        else if (A == "--revisit-ratio") O.RevisitRatio = nextD();
         else if (A == "--seconds") O.Seconds = nextD();
         else if (A == "--warmup") O.Warmup = nextD();
         else {
@@ -281,6 +309,7 @@ int main(int argc, char** argv) {
     }
     infer::B200 Exec(O.GPU, (uint16_t)O.Batch, NSB_FEATURE_CHANNELS, O.Channels, O.Blocks, O.Slots);
     Exec.load("");
+    if (O.CacheMiB > 0) Exec.enableCache((std::size_t)O.CacheMiB);  // Frame::setEvaluationCache, frame.cc:89
 
     std::vector<Frame> Pool((std::size_t)O.Frames);
     FrameQueue SearchQueue, EvaluationQueue;
@@ -302,9 +331,11 @@ int main(int argc, char** argv) {
 
     std::this_thread::sleep_for(std::chrono::duration<double>(O.Warmup));
     const uint64_t E0 = SI.Evals.load(), B0 = SI.Batches.load(), R0 = SI.Records.load(), G0 = SI.Games.load();
+    const uint64_t H0 = SI.CacheHits.load();
     const auto T0 = Clock::now();
     std::this_thread::sleep_for(std::chrono::duration<double>(O.Seconds));
     const uint64_t E1 = SI.Evals.load(), B1 = SI.Batches.load(), R1 = SI.Records.load(), G1 = SI.Games.load();
+    const uint64_t H1 = SI.CacheHits.load();
     const double Sec = std::chrono::duration<double>(Clock::now() - T0).count();
     Running.store(false);
     SearchQueue.close();
@@ -315,12 +346,13 @@ int main(int argc, char** argv) {
     std::printf("{\"metric\": \"selfplay_positions_per_sec\", \"value\": %.1f, \"unit\": \"positions/s\", "
                 "\"leaf_evals_per_sec\": %.1f, \"games_per_sec\": %.3f, \"avg_batch\": %.1f, \"seconds\": %.3f, "
                 "\"records\": %llu, \"evals\": %llu, \"batches\": %llu, \"games\": %llu, "
+                "\"cache_mb\": %d, \"revisit_ratio\": %.2f, \"cache_hit_rate\": %.4f, "
                 "\"net\": \"%dx%d\", \"batch_size\": %d, \"frame_pool\": %d, \"search_workers\": %d, \"slots\": %d, "
                 "\"num_playouts\": %d, \"full_search_ratio\": %.2f, \"descent_ns\": %d, \"nan_rows\": %llu, "
                 "\"rules\": \"synthetic (libnshogi absent): random relocations, random legal-move slots\"}\n",
                 (double)(R1 - R0) / Sec, Evals / Sec, (double)(G1 - G0) / Sec, Batches > 0 ? Evals / Batches : 0.0, Sec,
                 (unsigned long long)(R1 - R0), (unsigned long long)(E1 - E0), (unsigned long long)(B1 - B0),
-                (unsigned long long)(G1 - G0),
+                (unsigned long long)(G1 - G0), O.CacheMiB, O.RevisitRatio, Evals > 0 ? (double)(H1 - H0) / Evals : 0.0,
                 O.Blocks, O.Channels, O.Batch, O.Frames, O.SearchWorkers, O.Slots, O.Playouts, O.FullSearchRatio,
                 O.DescentNs, (unsigned long long)SI.NanRows.load());
     return 0;

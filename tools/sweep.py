@@ -137,9 +137,90 @@ def hbm_sweep(batches, out):
     ctx.close()
 
 
+def cache_sweep(out):
+    """Device-resident evaluation cache: probe / store kernels (GB/s of entry + row traffic) and the
+    cached evaluation path (probe -> trunk on the misses -> fused store) at several hit rates."""
+    _, _, hbm, _ = bench.peaks()
+    B = 4096
+    desc = nb.net_desc(128, 10)
+    ctx = nb.Context(desc, batch_max=B, slots=4, seed=1234)
+    ctx.cache_create(8192)                       # 8 GiB, like the reference's default (src/context.h:89)
+    nbund = ctx.cache_num_bundles()
+    rng = np.random.default_rng(3)
+    off, idx = synth.random_legal_moves(B, seed=9, edge_rows=False)
+    cnt = np.diff(off)
+    n_moves = int(off[-1])
+    pos = synth.random_positions(2048, seed=20240203)
+    d_pos = nb.DeviceBuffer.from_host(pos)
+    d_fbu = nb.DeviceBuffer(len(pos) * 86 * 16)
+    ctx.pack_positions_device(0, d_pos.ptr, len(pos), d_fbu.ptr)
+    ctx.await_(0)
+    fbu = d_fbu.to_host((len(pos), 86), nb.FEATURE_BITBOARD)
+    d_feat = nb.DeviceBuffer.from_host(fbu[rng.integers(0, len(pos), size=B)].reshape(-1))
+    d_off, d_idx = nb.DeviceBuffer.from_host(off), nb.DeviceBuffer.from_host(idx)
+    d_rows = nb.DeviceBuffer.from_host(rng.random(n_moves).astype(np.float32))
+    d_win = nb.DeviceBuffer.from_host(np.full(B, 0.5, np.float32))
+    d_legal, d_flag, d_hit = nb.DeviceBuffer(n_moves * 4), nb.DeviceBuffer(B), nb.DeviceBuffer(B)
+    d_miss, d_cnt = nb.DeviceBuffer(4 * B), nb.DeviceBuffer(4)
+    nsets = 24                                    # distinct key sets so that no launch re-touches warm lines
+    keysets = [(rng.integers(1, 2**62, size=B, dtype=np.int64).astype(np.uint64)) for _ in range(nsets)]
+    d_keys = [nb.DeviceBuffer.from_host(k) for k in keysets]
+    cacheable = cnt <= 164
+    row_bytes = float((cnt[cacheable] * 4).sum())
+    # store: hash + 3 headers (24 B) + meta RMW (8 B) read, row read + row/entry written
+    store_bytes = B * (8 + 72 + 8) + cacheable.sum() * 24 + 2 * row_bytes
+    ms = time_launches(ctx, lambda i, s: ctx.cache_store_device(0, d_keys[i % nsets].ptr, B, d_off.ptr, d_rows.ptr, d_win.ptr,
+                                                                d_win.ptr), nsets - 3, slots=1)
+    out({"kind": "hbm", "kernel": "cache_store_kernel", "batch": B, "reps": nsets - 3, "us_per_launch": round(ms * 1e3, 2),
+         "algorithmic_bytes": int(store_bytes), "gb_per_s": round(store_bytes / ms / 1e6, 1),
+         "frac_hbm_peak": round(store_bytes / ms / 1e6 / hbm, 4), "hbm_peak_gbs": hbm})
+    for k in range(nsets):                        # make sure every set is resident
+        ctx.cache_store_device(0, d_keys[k].ptr, B, d_off.ptr, d_rows.ptr, d_win.ptr, d_win.ptr)
+    ctx.await_(0)
+    probe_bytes = B * (8 + 72 + 8 + 8) + 2 * row_bytes + cacheable.sum() * 8
+    ms = time_launches(ctx, lambda i, s: ctx.cache_probe_device(0, d_keys[i % nsets].ptr, B, d_off.ptr, d_legal.ptr, d_win.ptr,
+                                                                d_win.ptr, d_hit.ptr, d_miss.ptr, d_cnt.ptr), nsets - 3, slots=1)
+    out({"kind": "hbm", "kernel": "cache_probe_kernel (all hits)", "batch": B, "reps": nsets - 3,
+         "us_per_launch": round(ms * 1e3, 2), "algorithmic_bytes": int(probe_bytes),
+         "gb_per_s": round(probe_bytes / ms / 1e6, 1), "frac_hbm_peak": round(probe_bytes / ms / 1e6 / hbm, 4),
+         "hbm_peak_gbs": hbm})
+    # cached evaluation at a given hit rate: a fraction of the batch reuses resident keys
+    Bc = 256
+    offc, idxc = synth.random_legal_moves(Bc, seed=20240203, edge_rows=False)
+    d_offc, d_idxc = nb.DeviceBuffer.from_host(offc), nb.DeviceBuffer.from_host(idxc)
+    d_rowsc = nb.DeviceBuffer.from_host(rng.random(int(offc[-1])).astype(np.float32))
+    resident = rng.integers(1, 2**62, size=Bc, dtype=np.int64).astype(np.uint64)
+    d_res = nb.DeviceBuffer.from_host(resident)
+    ctx.cache_store_device(0, d_res.ptr, Bc, d_offc.ptr, d_rowsc.ptr, d_win.ptr, d_win.ptr)
+    ctx.await_(0)
+    outs = [(nb.DeviceBuffer(int(offc[-1]) * 4), nb.DeviceBuffer(Bc * 4), nb.DeviceBuffer(Bc * 4), nb.DeviceBuffer(Bc),
+             nb.DeviceBuffer(Bc)) for _ in range(4)]
+    reps = 400
+    for rate in (0.0, 0.25, 0.5, 0.9):
+        nhit = int(round(rate * Bc))
+        keybufs = []
+        for _ in range(reps + 8):                # fresh miss keys every launch (they get stored by the launch)
+            k = rng.integers(1, 2**62, size=Bc, dtype=np.int64).astype(np.uint64)
+            k[:nhit] = resident[:nhit]
+            keybufs.append(nb.DeviceBuffer.from_host(k))
+
+        def launch(i, slot):
+            o = outs[slot]
+            ctx.eval_cached_decode_device(slot, d_feat.ptr, Bc, keybufs[i].ptr, d_offc.ptr, d_idxc.ptr, nb.DECODE_PROBS,
+                                          o[0].ptr, o[1].ptr, o[2].ptr, o[3].ptr, o[4].ptr)
+
+        ms4 = time_launches(ctx, launch, reps, slots=4, warm=4)
+        hits = int(outs[0][4].to_host((Bc,), np.uint8).sum())
+        out({"kind": "cached_eval", "net": "10x128", "batch": Bc, "hit_rate_target": rate, "hits_in_last_batch": hits,
+             "ms_per_batch_4streams": round(ms4, 5), "positions_per_s": round(Bc / ms4 * 1e3, 1)})
+        for b in keybufs:
+            b.free()
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="all", choices=["all", "trunk", "hbm"])
+    ap.add_argument("--what", default="all", choices=["all", "trunk", "hbm", "cache"])
     ap.add_argument("--nets", default="10x128,20x256,40x256")
     ap.add_argument("--batches", default="64,128,256,512,1024,2048,4096")
     ap.add_argument("--hbm-batches", default="256,1024,4096,16384")
@@ -153,6 +234,8 @@ def main():
 
     if args.what in ("all", "hbm"):
         hbm_sweep([int(x) for x in args.hbm_batches.split(",")], out)
+    if args.what in ("all", "cache"):
+        cache_sweep(out)
     if args.what in ("all", "trunk"):
         nets = [(int(s.split("x")[1]), int(s.split("x")[0])) for s in args.nets.split(",")]
         trunk_sweep(nets, [int(x) for x in args.batches.split(",")], out)
@@ -172,6 +255,13 @@ def main():
                 if r["kind"] == "hbm":
                     f.write(f"| {r['kernel']} | {r['batch']} | {r['us_per_launch']:.2f} | {r['algorithmic_bytes'] / 1e6:.2f} | "
                             f"{r['gb_per_s']:.0f} | {100 * r['frac_hbm_peak']:.1f} |\n")
+            if any(r["kind"] == "cached_eval" for r in rows):
+                f.write("\n## Cached evaluation (probe -> trunk on the misses -> fused store), 4 streams\n\n")
+                f.write("| net | batch | target hit rate | hits in last batch | ms / batch | positions/s |\n|---|---|---|---|---|---|\n")
+                for r in rows:
+                    if r["kind"] == "cached_eval":
+                        f.write(f"| {r['net']} | {r['batch']} | {r['hit_rate_target']:.2f} | {r['hits_in_last_batch']} | "
+                                f"{r['ms_per_batch_4streams']:.4f} | {r['positions_per_s']:.0f} |\n")
 
 
 if __name__ == "__main__":
