@@ -78,3 +78,17 @@ def test_selfplay_sim_gpu(built):
     assert 1 <= rec["avg_batch"] <= 128
     # a move is played every num_playouts (full search) or num_playouts / 4 (reduced search) evaluations
     assert 2.0 <= rec["evals"] / rec["records"] <= 8.0
+
+
+@pytest.mark.gpu
+def test_selfplay_sim_with_device_cache_gpu(built):
+    """The same loop behind the device-resident evaluation cache: half of the descents revisit a recent
+    leaf, so about half of the evaluations must be served from the cache."""
+    out = subprocess.run([os.path.join(built, "nsb_selfplay_sim"), "--channels", "128", "--blocks", "2", "--batch-size", "128",
+                          "--frame-pool-size", "512", "--num-search-workers", "2", "--num-playouts", "8", "--cache-mb", "64",
+                          "--revisit-ratio", "0.5", "--seconds", "1.0", "--warmup", "0.3"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["nan_rows"] == 0 and rec["evals"] > 10000 and rec["records"] > 1000
+    assert 0.35 <= rec["cache_hit_rate"] <= 0.6, rec["cache_hit_rate"]
