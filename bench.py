@@ -287,7 +287,13 @@ def run_b200(args):
                 "kernel_share_of_step": round(trunk_ms_sum / seq_elapsed_ms, 4) if seq_elapsed_ms > 0 else None,
                 "timing": f"{trunk_n} launches back to back on one stream, one CUDA event pair per launch; "
                           f"that sub-run: {seq_elapsed_ms / max(K2, 1):.5f} ms/step",
-                "traffic": traffic}
+                "traffic": traffic,
+                # the same kernel with `slots` launches in flight (the `value` leg): whole-job useful FLOP/s
+                "in_flight": {"achieved": round(value / max(world, 1) * trunk_flops_per_sample(C, blocks) / 1e12, 2),
+                              "frac": round(value / max(world, 1) * trunk_flops_per_sample(C, blocks) / 1e12 / tf_burst, 4),
+                              "frac_of_sustained_peak": round(value / max(world, 1) * trunk_flops_per_sample(C, blocks)
+                                                              / 1e12 / tf_sust, 4),
+                              "streams": slots, "per": "GPU"}}
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -334,12 +340,21 @@ def selfplay_leg(args, info, rep, device):
            "--frame-pool-size", "1024", "--num-search-workers", str(workers), "--seconds", str(args.selfplay_seconds),
            "--warmup", "1.5"]
     rep.barrier()
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=120 + args.selfplay_seconds)
-    if out.returncode != 0:
-        raise SystemExit(f"selfplay leg failed: {out.stderr[-400:]}")
-    rec = json.loads(out.stdout.strip().splitlines()[-1])
-    counters, ms_max = rep.aggregate({"records": rec["records"], "games": rec["games"], "evals": rec["evals"],
-                                      "batches": rec["batches"]}, rec["seconds"] * 1e3, device=device)
+    rec, err = None, None
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=120 + args.selfplay_seconds)
+        if out.returncode == 0:
+            rec = json.loads(out.stdout.strip().splitlines()[-1])
+        else:
+            err = out.stderr.strip()[-300:] or f"exit code {out.returncode}"
+    except (OSError, subprocess.SubprocessError, ValueError, IndexError) as e:
+        err = repr(e)
+    # every rank takes part in the reduction, also one whose harness failed (it contributes zeros)
+    mine = {"records": rec["records"], "games": rec["games"], "evals": rec["evals"], "batches": rec["batches"],
+            "nan_rows": 0 if rec else 1} if rec else {"nan_rows": 1}
+    counters, ms_max = rep.aggregate(mine, rec["seconds"] * 1e3 if rec else 0.0, device=device)
+    if counters["nan_rows"] or rec is None:      # "nan_rows" doubles as the count of failed ranks in this reduction
+        return {"unavailable": f"self-play harness failed on {counters['nan_rows']} rank(s): {err}"}
     return {"metric": "selfplay_positions_per_sec", "value": round(rep.whole_job_rate(counters["records"], ms_max), 1),
             "unit": "positions/s", "leaf_evals_per_sec": round(rep.whole_job_rate(counters["evals"], ms_max), 1),
             "games_per_sec": round(rep.whole_job_rate(counters["games"], ms_max), 2),
