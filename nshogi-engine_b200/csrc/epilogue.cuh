@@ -68,6 +68,7 @@ __device__ __forceinline__ void epilogue_half(int lb, uint32_t taddr, uint32_t b
     }
     tmem_ld_wait();
     const float b0 = lb ? bias[2] : bias[0], b1 = lb ? bias[3] : bias[1];
+    const uint64_t bb0 = pack_f32x2(b0, b0), bb1 = pack_f32x2(b1, b1);
 #pragma unroll
     for (int cg = 0; cg < NCG; ++cg)
 #pragma unroll
@@ -76,14 +77,10 @@ __device__ __forceinline__ void epilogue_half(int lb, uint32_t taddr, uint32_t b
 #pragma unroll
             for (int m = 0; m < 4; ++m) {  // m: bit0 = row half (lane/4 [+8]), bit1 = column group
                 const int g = 2 * h + (m >> 1), rh = m & 1;
-                const float bb = rh ? b1 : b0;
-                float x0 = __uint_as_float(v[cg][4 * g + 2 * rh + 0]) + bb;
-                float x1 = __uint_as_float(v[cg][4 * g + 2 * rh + 1]) + bb;
-                if (kResidual) {
-                    x0 += __uint_as_float(xr[cg][h][m] << 16);
-                    x1 += __uint_as_float(xr[cg][h][m] & 0xFFFF0000u);
-                }
-                p[m] = pack_relu_bf16x2(x0, x1) & mask.m[cg * 4 + g];
+                // the accumulator pair (two adjacent slots of one channel) goes through packed adds
+                uint64_t x = add_f32x2(pack_u32x2(v[cg][4 * g + 2 * rh + 0], v[cg][4 * g + 2 * rh + 1]), rh ? bb1 : bb0);
+                if (kResidual) x = add_f32x2(x, pack_u32x2(xr[cg][h][m] << 16, xr[cg][h][m] & 0xFFFF0000u));
+                p[m] = pack_relu_bf16x2(x) & mask.m[cg * 4 + g];
             }
             stmatrix_x4_trans(row_addr + (uint32_t)(cg * 32 + h * 16) * 16u, p[0], p[1], p[2], p[3]);
         }

@@ -188,6 +188,32 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
+// Packed fp32 pair arithmetic (SASS FADD2): one issue slot for two adds.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// cvt.rn.relu.bf16x2 of a packed pair (low half of the result = low element)
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(uint64_t v) {
+    uint32_t d;
+    asm("{\n\t.reg .f32 lo, hi;\n\t"
+        "mov.b64 {lo, hi}, %1;\n\t"
+        "cvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}"
+        : "=r"(d)
+        : "l"(v));
+    return d;
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
