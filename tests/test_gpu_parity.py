@@ -319,3 +319,53 @@ def test_errors_are_reported_not_swallowed(nb):
             ctx.load_weights(np.zeros(10, dtype=np.float32))
         with pytest.raises(nb.NsbError):
             ctx.await_(3)
+
+
+# ---- edge cases ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,channels", [(2, 2), (7, 64), (1, 128), (33, 31)])
+def test_extract_other_channel_counts(nb, orc, synth, ctx128, n, channels):
+    """extractBits<> is generic in the channel count (src/cuda/extractbit.cu:76-96): even counts take the
+    8-byte NHWC path, odd ones the scalar path, and the NCHW blocks end in a ragged tail."""
+    ctx = ctx128[0]
+    fb = synth.random_feature_bitboards(n * channels, seed=1000 + channels)
+    fb["hi"][::3] |= np.uint64(1 << 24)                    # plenty of rotated planes
+    d_fb = nb.DeviceBuffer.from_host(fb)
+    d_out = nb.DeviceBuffer(n * channels * 81 * 4)
+    for cf in (True, False):
+        d_out.fill(0xAB)
+        ctx.extract_device(0, d_fb.ptr, n, channels, cf, d_out.ptr)
+        ctx.await_(0)
+        shape = (n, channels, 81) if cf else (n, 81, channels)
+        assert np.array_equal(d_out.to_host(shape, np.uint32), orc.expand(fb, n, channels, cf).view(np.uint32))
+    d_fb.free()
+    d_out.free()
+
+
+def test_empty_batch_and_empty_rows(nb, orc, synth, ctx128):
+    """n = 0 is a no-op on every entry point; a position without legal moves (an empty CSR row) produces
+    no output and does not disturb its neighbours."""
+    ctx, desc, blob = ctx128
+    z = np.zeros(1, dtype=np.float32)
+    ctx.eval_async(0, np.zeros(1, dtype=nb.FEATURE_BITBOARD), 0, z, z, z)
+    ctx.eval_decode_async(0, np.zeros(1, dtype=nb.FEATURE_BITBOARD), 0, np.zeros(1, dtype=np.uint32),
+                          np.zeros(1, dtype=np.uint16), nb.DECODE_PROBS, z, z, z, None)
+    ctx.await_(0)
+    n = 6
+    pos = synth.random_positions(n, seed=5)
+    fb = orc.pack(pos)
+    cnt = np.array([3, 0, 1, 0, 40, 2], dtype=np.uint32)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    off[1:] = np.cumsum(cnt)
+    idx = np.random.default_rng(1).choice(nb.POLICY_SIZE, size=int(off[-1]), replace=False).astype(np.uint16)
+    legal = np.full(int(off[-1]), -7.0, dtype=np.float32)
+    win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    flag = np.zeros(n, dtype=np.uint8)
+    ctx.eval_decode_async(0, fb, n, off, idx, nb.DECODE_PROBS, legal, win, draw, flag)
+    ctx.await_(0)
+    policy, w2, d2 = run_eval(nb, ctx, fb, n)
+    want, wflag = orc.decode(policy, w2, d2, off, idx, nb.DECODE_PROBS)
+    assert np.allclose(legal, want, rtol=1e-5, atol=1e-7) and np.array_equal(flag, wflag)
+    assert np.array_equal(win, w2) and legal[off[2]] == 1.0          # 1-move row (feedworker.cc:101-103)
+    for i in range(n):
+        if cnt[i] > 1:
+            assert abs(legal[off[i]:off[i + 1]].sum() - 1.0) < 1e-5
