@@ -64,6 +64,7 @@ static T* pinned(size_t N) {
 int main(int argc, char** argv) {
     int Channels = 128, Blocks = 10, B = 256, Repeat = 300, Slots = 4;
     bool SelfCheck = false;
+    std::string Weights;  // NSBW file (nshogi-engine_b200/weights_io.py); empty = seeded random-init net
     for (int I = 1; I < argc; ++I) {
         const std::string A = argv[I];
         auto next = [&]() { return I + 1 < argc ? std::atoi(argv[++I]) : 0; };
@@ -73,13 +74,14 @@ int main(int argc, char** argv) {
         else if (A == "--repeat") Repeat = next();
         else if (A == "--slots") Slots = next();
         else if (A == "--selfcheck") SelfCheck = true;
+        else if (A == "--weights" && I + 1 < argc) Weights = argv[++I];
     }
     if (nsb_device_count() < 1) {
         std::fprintf(stderr, "nsb_host_bench: no CUDA device; infer::B200 has no CPU fallback\n");
         return 2;
     }
     infer::B200 Exec(0, (uint16_t)B, NSB_FEATURE_CHANNELS, Channels, Blocks, Slots);
-    Exec.load("");  // seeded random-init net (the reference ships no model)
+    Exec.load(Weights);  // "" = seeded random-init net (the reference ships no model)
     Exec.resetGPU();
 
     // --- Evaluator-style pinned batch buffers (reference src/evaluate/evaluator.cc:85-106) -----------
