@@ -59,7 +59,8 @@ struct PairGeom {
     static constexpr int SPITCH = (GUARD + NCOLS + 11) | 1;
     static constexpr int BUF_BYTES = ((KCH * SPITCH * 16 + 127) / 128) * 128;
     static constexpr int XCH = 16;                        // channel chunks of one Cout half
-    static constexpr int XROW = NCOLS * 16;               // bytes of one chunk's 96 slots (one bulk push)
+    static constexpr int XROW = 89 * 16;                  // bytes one bulk push moves per chunk: slots 0..88 (the rest
+                                                          // of the 96 are padding that is zero on both sides already)
     static constexpr int XPITCH = (NCOLS + 1) * 16;       // exchange buffer chunk pitch: odd slot count, so that
                                                           // the two chunks of one stmatrix hit different banks
     static constexpr int XBUF_BYTES = XCH * XPITCH;

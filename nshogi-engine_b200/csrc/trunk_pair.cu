@@ -245,15 +245,14 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                             epilogue_half<3, false>(lb, taddr, xbuf, G::XPITCH, q * 4, 0, bias, realmask, lane);
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
-                            mbar_arrive_expect_tx_remote(dst_bar, 2 * G::XROW);
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const int xc = q * 4 + lb * 2 + j;
-                                bulk_s2peer(map_to_cta(out_base + (uint32_t)(((G::XCH * rank + xc) * G::SPITCH + G::GUARD) * 16),
-                                                       peer),
-                                            xbuf + xc * G::XPITCH, G::XROW, dst_bar);
-                            }
+                        // one bulk copy costs its issuing thread ~290 cycles (tools/bulk_probe.py): two lanes, one chunk each
+                        if (lane == 0) mbar_arrive_expect_tx_remote(dst_bar, 2 * G::XROW);
+                        __syncwarp();
+                        if (lane < 2) {
+                            const int xc = q * 4 + lb * 2 + lane;
+                            bulk_s2peer(map_to_cta(out_base + (uint32_t)(((G::XCH * rank + xc) * G::SPITCH + G::GUARD) * 16),
+                                                   peer),
+                                        xbuf + xc * G::XPITCH, G::XROW, dst_bar);
                         }
                     }
                     tc_fence_before();
