@@ -15,7 +15,8 @@
 //
 // Warp roles per CTA (384 threads): warp 0 = weight producer (its Cout half of every tile pair),
 // warp 1 = MMA issuer in the leader CTA / ring-full relay in the peer, warp 2 = activation relay +
-// skip push, warps 4-11 = expansion, epilogues (4 warps own position, 4 warps peer's), heads, tail.
+// skip push, warp 3 = exchange push, warps 4-11 = expansion, epilogues (each warp: 16 of my Cout rows, first for the peer's
+// position - pushed at once - then for my own), heads, tail.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,7 +28,7 @@ namespace nsb {
 
 namespace {
 
-constexpr int kPushes = 8;  // exchange pushes per layer and direction: 4 warps x 2 halves of 2 chunks
+constexpr uint32_t kPushBar = 2;  // named barrier: 8 epilogue warps arrive, the push warp (warp 3) waits
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
@@ -72,7 +73,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
             mbar_init(bar_full(s), rank == 0 ? 2 : 1);  // leader: own producer + the peer's relay
             mbar_init(bar_empty(s), 1);
         }
-        mbar_init(bar_act, kEpiThreads + kPushes);  // 256 local epilogue threads + the peer's pushes
+        mbar_init(bar_act, kEpiThreads + 1);  // 256 local epilogue threads + the peer's push warp
         mbar_init(bar_acc, 1);
         mbar_init(bar_peer_act, 1);
         mbar_init(bar_skip, 1);
@@ -184,13 +185,29 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                 }
                 __syncwarp();
             }
+    } else if (warp == 3) {
+        // ===== push warp: the exchange buffer -> the peer's activation buffer, once per conv layer =====
+        // The epilogue warps write the peer position's rows first and arrive on kPushBar without
+        // waiting; this warp then issues the 16 bulk copies (one lane each: a copy costs its issuing
+        // thread ~290 cycles, tools/bulk_probe.py) while they go on with their own position.
+        for (int p = 0; p < my_passes; ++p)
+            for (int L = 0; L < NL - 1; ++L) {
+                named_bar_sync(kPushBar, kEpiThreads + 32);
+                const uint32_t out_base = (L & 1) ? bufB : bufA;
+                const uint32_t dst_bar = map_to_cta(bar_act, peer);
+                if (lane == 0) mbar_arrive_expect_tx_remote(dst_bar, G::XCH * G::XROW);
+                __syncwarp();
+                if (lane < G::XCH)
+                    bulk_s2peer(map_to_cta(out_base + (uint32_t)(((G::XCH * rank + lane) * G::SPITCH + G::GUARD) * 16), peer),
+                                xbuf + lane * G::XPITCH, G::XROW, dst_bar);
+                __syncwarp();
+            }
     } else if (warp >= 4) {
         // ===== expansion + epilogues + heads =====================================================
         const int et = threadIdx.x - 128;  // 0..255
         const int ew = warp - 4;           // 0..7
         const int q = ew & 3;              // TMEM lane quadrant (== warp % 4): 32 of my 128 Cout
-        const int part = ew >> 2;          // which position's 96 columns
-        const bool own = (uint32_t)part == rank;
+        const int lbw = ew >> 2;           // the 16-lane block of that quadrant this warp owns (both positions)
         if (stamp && et == 0) a.timeline[4 * NL + 11] = clock64();
         EpilogueMask<3> realmask;
         realmask.init(0, lane);
@@ -204,7 +221,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
             expand_features<1, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
             mbar_arrive(bar_act);
-            if (et < kPushes) mbar_arrive_remote(map_to_cta(bar_act, peer));  // nothing to exchange for the stem input
+            if (et == 0) mbar_arrive_remote(map_to_cta(bar_act, peer));  // nothing to exchange for the stem input
             if (tl) tl[2] = clock64();
 
             // -- conv layers: TMEM -> +bias (+skip) -> ReLU -> bf16 -> next layer's B operand ----
@@ -219,43 +236,30 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                 if (stamp && p == 0 && et == 0) a.timeline[4 * L + 2] = clock64();
                 const uint32_t out_base = (L & 1) ? bufB : bufA;
                 const bool residual = (L >= 2) && ((L & 1) == 0);
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + part * G::NCOLS;
-                if (own) {
+                const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+                // First the PEER's position: its rows go through the exchange buffer and are pushed into
+                // the peer's activation buffer the moment this warp's two chunks are written, so that the
+                // DSMEM transfer and the barrier relay to the leader run under the second half below.
+                if (residual) {  // the peer's x rows for my channels, pushed during the MMA phase
+                    mbar_wait(bar_skip, skip_phase);
+                    skip_phase ^= 1u;
+                }
+                if (residual)
+                    epilogue_half<3, true>(lbw, tq + peer * G::NCOLS, xbuf, G::XPITCH, q * 4, 0, bias, realmask, lane);
+                else
+                    epilogue_half<3, false>(lbw, tq + peer * G::NCOLS, xbuf, G::XPITCH, q * 4, 0, bias, realmask, lane);
+                fence_proxy_async_smem();
+                named_bar_arrive(kPushBar, kEpiThreads + 32);  // hand the exchange buffer to the push warp, do not wait
+                // then my own position, in place in my activation buffer
+                {
                     const uint32_t out_buf = out_base + G::GUARD * 16;
                     const int chunk0 = (int)rank * G::XCH + q * 4;
                     if (residual)
-                        epilogue_warp<3, true>(taddr, out_buf, G::SPITCH * 16, chunk0, 0, bias, realmask, lane);
+                        epilogue_half<3, true>(lbw, tq + rank * G::NCOLS, out_buf, G::SPITCH * 16, chunk0, 0, bias, realmask, lane);
                     else
-                        epilogue_warp<3, false>(taddr, out_buf, G::SPITCH * 16, chunk0, 0, bias, realmask, lane);
+                        epilogue_half<3, false>(lbw, tq + rank * G::NCOLS, out_buf, G::SPITCH * 16, chunk0, 0, bias, realmask, lane);
                     tc_fence_before();
                     fence_proxy_async_smem();
-                } else {
-                    // the other position's rows go through the exchange buffer; each half (2 chunks
-                    // = 3 KB) is pushed into the peer's activation buffer as soon as it is written
-                    if (residual) {  // the peer's x rows for my channels, pushed during the MMA phase
-                        mbar_wait(bar_skip, skip_phase);
-                        skip_phase ^= 1u;
-                    }
-                    const uint32_t dst_bar = map_to_cta(bar_act, peer);
-#pragma unroll
-                    for (int lb = 0; lb < 2; ++lb) {
-                        if (residual)
-                            epilogue_half<3, true>(lb, taddr, xbuf, G::XPITCH, q * 4, 0, bias, realmask, lane);
-                        else
-                            epilogue_half<3, false>(lb, taddr, xbuf, G::XPITCH, q * 4, 0, bias, realmask, lane);
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        // one bulk copy costs its issuing thread ~290 cycles (tools/bulk_probe.py): two lanes, one chunk each
-                        if (lane == 0) mbar_arrive_expect_tx_remote(dst_bar, 2 * G::XROW);
-                        __syncwarp();
-                        if (lane < 2) {
-                            const int xc = q * 4 + lb * 2 + lane;
-                            bulk_s2peer(map_to_cta(out_base + (uint32_t)(((G::XCH * rank + xc) * G::SPITCH + G::GUARD) * 16),
-                                                   peer),
-                                        xbuf + xc * G::XPITCH, G::XROW, dst_bar);
-                        }
-                    }
-                    tc_fence_before();
                 }
                 mbar_arrive(bar_act);
                 if (stamp && p == 0 && et == 0) a.timeline[4 * L + 3] = clock64();
@@ -270,7 +274,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
             mbar_wait(bar_acc, acc_phase);
             acc_phase ^= 1u;
             tc_fence_after();
-            if (part == 0) {
+            if (lbw == 0) {
                 head_read<0>(tmem_base + ((uint32_t)(q * 32) << 16) + rank * G::NCOLS, hbias, hp, scratch, vbuf, lane);
                 tc_fence_before();
             }
