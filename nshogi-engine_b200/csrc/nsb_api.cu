@@ -100,7 +100,7 @@ static int check_batch(nsb_ctx* c, size_t n, bool need_weights) {
 extern "C" {
 
 const char* nsb_last_error(void) { return g_err; }
-const char* nsb_version(void) { return "nsb 0.1 (sm_100a, tcgen05 position-stationary trunk)"; }
+const char* nsb_version(void) { return "nsb 0.2 (sm_100a: tcgen05 position-stationary trunk, cta_group::2 pair trunk, device-resident eval cache)"; }
 
 int nsb_device_count(void) {
     int n = 0;
