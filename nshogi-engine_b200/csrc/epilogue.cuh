@@ -47,7 +47,9 @@ struct EpilogueMask {
 // slot 0 of chunk 0 (guard already added); `pitch` = bytes between channel chunks.
 // bias[lb*2 + h] is the bias of channel 32q + 16*lb + 8*h + lane/4.  Per element: one FADD
 // (+ unpack and FADD for the skip), half a cvt.rn.relu.bf16x2 and half an AND.
-template <int NCG, bool kResidual>
+// LBS = chunk distance between the two lane blocks (2: channels in accumulator-row order; 8: the
+// TS kernel's row permutation, where lane block lb holds K block lb of the output channels).
+template <int NCG, bool kResidual, int LBS = 2>
 __device__ __forceinline__ void epilogue_half(int lb, uint32_t taddr, uint32_t buf, uint32_t pitch, int chunk0,
                                               int col0, const float (&bias)[4], const EpilogueMask<NCG>& mask,
                                               int lane) {
@@ -56,7 +58,7 @@ __device__ __forceinline__ void epilogue_half(int lb, uint32_t taddr, uint32_t b
 #pragma unroll
     for (int cg = 0; cg < NCG; ++cg) tmem_ld_16x256b_x4(taddr + ((uint32_t)(lb * 16) << 16) + cg * 32, v[cg]);
     const uint32_t row_addr =
-        buf + (uint32_t)(chunk0 + lb * 2 + (mk & 1)) * pitch + (uint32_t)(col0 + 8 * (mk >> 1) + mi) * 16u;
+        buf + (uint32_t)(chunk0 + lb * LBS + (mk & 1)) * pitch + (uint32_t)(col0 + 8 * (mk >> 1) + mi) * 16u;
     uint32_t xr[NCG][2][4];
     if (kResidual) {
 #pragma unroll

@@ -51,6 +51,7 @@ struct Slot {
 struct nsb_ctx {
     int gpu = 0, batch_max = 0, num_sms = 0;
     int max_pairs = 0;  // co-resident CTA pairs of the 256-channel trunk (0: single-CTA kernel)
+    bool use_ts = false;       // 128-channel trunk with the weights fed through tensor memory (trunk_ts.cu)
     nsb::DeviceCache cache{};  // device-resident evaluation cache (nsb_cache_create)
     nsb_net_desc desc{};
     bool loaded = false, timing = false;
@@ -150,6 +151,11 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
         if ((rc = trunk_pair_prepare(&max_pairs))) return rc;
         if (max_pairs > prop.multiProcessorCount / 2) max_pairs = prop.multiProcessorCount / 2;
     }
+    // NSB_TRUNK128=ts selects the experimental kernel that feeds the weights through tensor memory
+    // (trunk_ts.cu; parity-tested, measured 0-7 % slower than the default)
+    const char* t128 = getenv("NSB_TRUNK128");
+    const bool use_ts = net->channels == 128 && t128 && strcmp(t128, "ts") == 0;
+    if (use_ts && (rc = trunk_ts_prepare())) return rc;
     nsb_ctx* c = new (std::nothrow) nsb_ctx();
     if (!c) {
         set_error("out of host memory");
@@ -159,6 +165,7 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     c->batch_max = batch_max;
     c->num_sms = prop.multiProcessorCount;
     c->max_pairs = max_pairs;
+    c->use_ts = use_ts;
     c->desc = *net;
     c->slots.resize(slots);
     const size_t B = (size_t)batch_max;
@@ -233,10 +240,15 @@ int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
     for (auto& s : c->slots) NSB_CUDA(cudaStreamSynchronize(s.stream));
     const nsb_net_desc& d = c->desc;
     const int C = d.channels, H = d.value_hidden, NL = 2 * d.blocks + 2;
-    const int stages = stages_per_pass(d);
+    int stages = stages_per_pass(d);
     std::vector<uint16_t> tiles((size_t)stages * kStageBytes / 2);
     std::vector<float> bias((size_t)NL * C), fc1t((size_t)81 * H), fc1b(H), fc2(2 * (size_t)H), fc2b(2);
     pack_weights(d, blob, tiles.data(), bias.data(), fc1t.data(), fc1b.data(), fc2.data(), fc2b.data());
+    if (c->use_ts) {  // same bias / FC arrays; the conv weights as a stream of 4 KB K = 16 steps
+        stages = ts_steps_per_pass(d);
+        tiles.assign((size_t)stages * 2048, 0);
+        pack_weights_ts(d, blob, tiles.data());
+    }
     const void* src[6] = {tiles.data(), bias.data(), fc1t.data(), fc1b.data(), fc2.data(), fc2b.data()};
     const size_t bytes[6] = {tiles.size() * 2, bias.size() * 4, fc1t.size() * 4, fc1b.size() * 4, fc2.size() * 4,
                              fc2b.size() * 4};
@@ -277,6 +289,7 @@ static int run_trunk(nsb_ctx* c, Slot& s, const EvalArgs& a) {
         NSB_CUDA(cudaEventRecord(s.ev[s.ev_used], s.stream));
     }
     int k = c->max_pairs > 0 ? launch_trunk_pair(c->net, a, c->max_pairs, s.stream)
+            : c->use_ts      ? launch_trunk_ts(c->net, a, c->num_sms, s.stream)
                              : launch_trunk_fused(c->net, a, c->num_sms, s.stream);
     if (k < 0) return k;
     NSB_CUDA(cudaGetLastError());

@@ -88,8 +88,8 @@ struct DeviceNet {
     int in_channels;   // 86
     int hidden;        // value MLP hidden units (<= 256)
     int num_layers;    // 1 (stem) + 2*blocks + 1 (heads)
-    int stages_per_pass;
-    const uint8_t* tiles;  // [stages_per_pass][16384] bf16 weight tiles in stream order
+    int stages_per_pass;   // classic stream: 16 KB tiles per pass; TS stream: 4 KB K = 16 steps per pass
+    const uint8_t* tiles;  // [stages_per_pass][16384] bf16 weight tiles in stream order (or the TS stream)
     const float* bias;     // [num_layers][C]  (head row: 27 policy biases, value-conv bias at 27)
     const float* fc1t;     // [81][hidden]  (transposed for coalesced reads)
     const float* fc1b;     // [hidden]
@@ -137,6 +137,8 @@ struct EvalArgs {
 size_t blob_floats(const nsb_net_desc& d);
 void blob_random(const nsb_net_desc& d, uint64_t seed, float* blob);
 int stages_per_pass(const nsb_net_desc& d);
+int ts_steps_per_pass(const nsb_net_desc& d);
+void pack_weights_ts(const nsb_net_desc& d, const float* blob, uint16_t* stream);  // trunk_ts.cu's weight stream
 // Packs canonical blob -> host images of DeviceNet arrays (tiles as uint16 bf16 bits).
 void pack_weights(const nsb_net_desc& d, const float* blob, uint16_t* tiles, float* bias,
                   float* fc1t, float* fc1b, float* fc2, float* fc2b);
@@ -158,6 +160,8 @@ int launch_cache_store(const DeviceCache& c, const uint64_t* d_hashes, size_t n,
                        uint8_t* d_stored, cudaStream_t s);
 int launch_cache_clear(const DeviceCache& c, cudaStream_t s);
 int trunk_fused_prepare(int channels);  // sets max dynamic smem attribute
+int trunk_ts_prepare();  // 128-channel trunk with the weights fed through tensor memory (trunk_ts.cu)
+int launch_trunk_ts(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s);
 int trunk_pair_prepare(int* max_pairs);  // same for the CTA-pair kernel; reports co-resident clusters
 int launch_trunk_pair(const DeviceNet& net, const EvalArgs& a, int max_pairs, cudaStream_t s);
 int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters, float* max_err,

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
         }
-        mbar_init(bar_act, kEpiThreads);
+        mbar_init(bar_act, kEpiWarps);  // one arrival per epilogue warp (256 arrivals on one word serialise)
         mbar_init(bar_acc, 1);
         fence_mbar_init();
     }
@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
             unsigned long long* tl = (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) ? a.timeline + 4 * NL : nullptr;
             expand_features<G::NPOS, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
-            mbar_arrive(bar_act);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_act);
             if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 2] = clock64();
 
             // -- conv layers: TMEM -> +bias (+skip) -> ReLU -> bf16 -> next layer's B operand ----
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
                     epilogue_warp<3, false>(taddr, out_buf, G::SPITCH * 16, chunk0, e_col0, bias, realmask, lane);
                 tc_fence_before();
                 fence_proxy_async_smem();
-                mbar_arrive(bar_act);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_act);
                 if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * L + 3] = clock64();
             }
 

@@ -73,7 +73,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
             mbar_init(bar_full(s), rank == 0 ? 2 : 1);  // leader: own producer + the peer's relay
             mbar_init(bar_empty(s), 1);
         }
-        mbar_init(bar_act, kEpiThreads + 1);  // 256 local epilogue threads + the peer's push warp
+        mbar_init(bar_act, kEpiWarps + 1);  // one arrival per local epilogue warp + the peer's push warp
         mbar_init(bar_acc, 1);
         mbar_init(bar_peer_act, 1);
         mbar_init(bar_skip, 1);
@@ -220,7 +220,8 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
             if (tl) tl[8] = clock64();
             expand_features<1, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
-            mbar_arrive(bar_act);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_act);
             if (et == 0) mbar_arrive_remote(map_to_cta(bar_act, peer));  // nothing to exchange for the stem input
             if (tl) tl[2] = clock64();
 
@@ -261,7 +262,8 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                     tc_fence_before();
                     fence_proxy_async_smem();
                 }
-                mbar_arrive(bar_act);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_act);
                 if (stamp && p == 0 && et == 0) a.timeline[4 * L + 3] = clock64();
             }
 

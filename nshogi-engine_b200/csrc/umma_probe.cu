@@ -50,6 +50,7 @@ umma_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b
         *reinterpret_cast<uint16_t*>(sb + elem_off(layout, i / K, i % K, b_rows)) = b[i];
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 16, 1);
         fence_mbar_init();
     }
     fence_proxy_async_smem();
@@ -79,6 +80,8 @@ umma_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b
                             bd = make_desc_sw128(b0 + (uint32_t)(kc * b_rows * 128 + shift * 128 + kk * 32));
                         }
                         umma_bf16(tmem_base, ad, bd, idesc, (it == 0 && rep == 0 && k16 == 0) ? 0u : 1u);
+                        // odd iteration counts: a tcgen05.commit after every 4th MMA, like the trunk's ring
+                        if ((iters & 1) && (k16 & 3) == 3) umma_commit(bar + 16);
                     }
                 }
                 __syncwarp();
@@ -127,6 +130,112 @@ umma_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+
+// The same probe with the A operand in TENSOR MEMORY (layout 4): every thread stores its row's K
+// elements into TMEM columns [256, 256 + K/2) with tcgen05.st; the MMAs then read A from TMEM and
+// only B from shared memory.  `smem_noise` > 0 makes warps 1-3 stream 16-byte stores through a
+// scratch area of shared memory during the timed loop (the traffic a weight ring would add).
+__global__ void __launch_bounds__(128, 1)
+umma_ts_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, int N, int K, int rows,
+                     int shift, int smem_noise, int iters, float* __restrict__ d, unsigned long long* __restrict__ cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_rows = (rows + 7) & ~7;
+    const size_t b_bytes = (size_t)b_rows * K * 2;
+    uint8_t* sb = smem;
+    uint8_t* noise = sb + ((b_bytes + 1023) & ~(size_t)1023);   // 32 KB scratch
+    uint8_t* tail = noise + 32768;
+    const uint32_t bar = smem_u32(tail);
+    volatile uint32_t* holder = reinterpret_cast<volatile uint32_t*>(tail + 8);
+    volatile int* stop = reinterpret_cast<volatile int*>(tail + 16);
+    for (int i = threadIdx.x; i < rows * K; i += blockDim.x)
+        *reinterpret_cast<uint16_t*>(sb + elem_off(0, i / K, i % K, b_rows)) = b[i];
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        *stop = 0;
+    }
+    fence_proxy_async_smem();
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(holder)), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *holder;
+    const uint32_t a_tmem = tmem_base + 256;
+    {   // my row of A -> TMEM, 8 columns per K = 16 step
+        const uint32_t lane_addr = a_tmem + ((uint32_t)(warp * 32) << 16);
+        for (int k16 = 0; k16 < K / 16; ++k16) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = (uint32_t)a[(size_t)threadIdx.x * K + k16 * 16 + 2 * j] |
+                       ((uint32_t)a[(size_t)threadIdx.x * K + k16 * 16 + 2 * j + 1] << 16);
+            tmem_st_32x32b_x8(lane_addr + k16 * 8, v);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16_f32(128, N);
+    const uint32_t b0 = smem_u32(sb);
+    auto issue_all = [&](bool fresh) {
+        for (int k16 = 0; k16 < K / 16; ++k16) {
+            const uint64_t bd = make_smem_desc(b0 + (uint32_t)((k16 * 2 * b_rows + shift) * 16), b_rows * 16, 128);
+            umma_bf16_ts(tmem_base, a_tmem + k16 * 8, bd, idesc, (fresh && k16 == 0) ? 0u : 1u);
+        }
+    };
+    if (warp == 0) {
+        uint32_t parity = 0;
+        for (int it = 0; it < iters + 1; ++it) {
+            const unsigned long long t0 = clock64();
+            const int reps = it == 0 ? 1 : 16;
+            for (int rep = 0; rep < reps; ++rep) {
+                if (elect_one()) issue_all(it == 0 && rep == 0);
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(bar);
+            __syncwarp();
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            const unsigned long long t1 = clock64();
+            if (threadIdx.x == 0) {
+                if (it == 1) cycles[0] = 0;
+                if (it >= 1) cycles[0] += t1 - t0;
+            }
+        }
+        if (elect_one()) {
+            issue_all(true);
+            umma_commit(bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, parity);
+        if (threadIdx.x == 0) *stop = 1;
+    } else if (smem_noise > 0) {
+        uint4* dst = reinterpret_cast<uint4*>(noise);
+        unsigned k = threadIdx.x;
+        while (*stop == 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                dst[k & 2047] = make_uint4(k, k, k, k);
+                k += 96;
+            }
+        }
+    }
+    __syncthreads();
+    tc_fence_after();
+    for (int j = 0; j < N / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[(size_t)threadIdx.x * N + j * 32 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
 
 // The same probe on a CTA pair: one cta_group::2 MMA of M = 256 x N x K16; CTA r holds A rows
 // [128r, 128r + 128) and N/2 rows of B (b_rows rows stored per CTA, start shifted by `shift`).
@@ -224,11 +333,13 @@ umma_pair_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restric
 
 int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters, float* max_err,
                double* cycles_per_mma) {
-    // layout: 0 = SWIZZLE_NONE, 1 = SWIZZLE_128B, 2 / 3 = the same on a CTA pair (cta_group::2, M = 256)
-    const bool pair = layout >= 2;
-    const int lay = layout & 1;
+    // layout: 0 = SWIZZLE_NONE, 1 = SWIZZLE_128B, 2 / 3 = the same on a CTA pair (cta_group::2, M = 256),
+    //         4 = A operand in tensor memory (B SWIZZLE_NONE), 5 = the same with concurrent shared-memory stores
+    const bool ts = layout >= 4;
+    const bool pair = layout == 2 || layout == 3;
+    const int lay = ts ? 0 : (layout & 1);
     if (n_cols % 32 || n_cols < 32 || n_cols > 256 || k_elems % 64 || k_elems <= 0 || shift_rows < 0 ||
-        shift_rows > 64 || iters < 1 || layout < 0 || layout > 3) {
+        shift_rows > 64 || iters < 1 || layout < 0 || layout > 5) {
         set_error("umma_probe: bad arguments");
         return NSB_ERR_INVALID;
     }
@@ -253,12 +364,15 @@ int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int
     if (e == cudaSuccess) e = cudaMalloc(&dc, 16);
     if (e == cudaSuccess) e = cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
-    const size_t smem = (size_t)128 * K * 2 + (size_t)((rows + 7) & ~7) * K * 2 + 4096;
+    const size_t smem = (size_t)128 * K * 2 + (size_t)((rows + 7) & ~7) * K * 2 + 4096 + (ts ? 32768 : 0);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(pair ? (const void*)umma_pair_probe_kernel : (const void*)umma_probe_kernel,
+        e = cudaFuncSetAttribute(ts ? (const void*)umma_ts_probe_kernel
+                                    : (pair ? (const void*)umma_pair_probe_kernel : (const void*)umma_probe_kernel),
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
-        if (pair)
+        if (ts)
+            umma_ts_probe_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, layout == 5 ? 1 : 0, iters, dd, dc);
+        else if (pair)
             umma_pair_probe_kernel<<<2, 128, smem>>>(da, db, N, K, rows, shift_rows, lay, iters, dd, dc);
         else
             umma_probe_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, lay, iters, dd, dc);

@@ -156,4 +156,60 @@ void pack_weights(const nsb_net_desc& d, const float* blob, uint16_t* tiles, flo
     std::memcpy(fc2b, w, sizeof(float) * 2);
 }
 
+
+// ---- "TS" weight stream (trunk_ts.cu: the A operand goes global -> registers -> tensor memory) ------
+// One 4 KB block per K = 16 MMA step, [128 accumulator rows][16 input channels] bf16 (a row's 32
+// bytes are exactly what one producer thread stores into its TMEM lane), in issue order:
+//   layer, K block kc (64 input channels; the previous epilogue finishes them in this order),
+//   tap, step k (16 channels).
+// Accumulator row 32q + 16lb + r holds output channel 64lb + 16q + r, so that lane block lb of every
+// TMEM quadrant - one half of the epilogue - is exactly K block lb of the next layer.  The head
+// layer keeps its own row assignment (head channel h in row 32*(h/7) + h%7).
+int ts_steps_per_pass(const nsb_net_desc& d) {
+    const int kc64 = d.channels / 64;
+    return 9 * 6 + 2 * d.blocks * 9 * kc64 * 4 + kc64 * 4;  // stem: 96 input channels = 6 steps per tap
+}
+
+void pack_weights_ts(const nsb_net_desc& d, const float* blob, uint16_t* stream) {
+    const int C = d.channels, IN = d.in_channels, NB = d.blocks;
+    const int kc64 = C / 64;
+    const float* w = blob;
+    uint16_t* t = stream;
+    auto row_channel = [](int row) { return 64 * ((row >> 4) & 1) + 16 * (row >> 5) + (row & 15); };
+    auto pack_conv = [&](const float* cw, int cin_real, int kblocks, int last_block_steps) {
+        for (int kc = 0; kc < kblocks; ++kc)
+            for (int tap = 0; tap < 9; ++tap)
+                for (int k = 0; k < (kc + 1 == kblocks ? last_block_steps : 4); ++k) {
+                    for (int row = 0; row < 128; ++row)
+                        for (int e = 0; e < 16; ++e) {
+                            const int co = row_channel(row), ci = kc * 64 + k * 16 + e;
+                            const float v = ci < cin_real ? cw[((size_t)co * cin_real + ci) * 9 + tap] : 0.f;
+                            t[row * 16 + e] = bf16_bits_rne(v);
+                        }
+                    t += 128 * 16;
+                }
+    };
+    pack_conv(w, IN, 2, 2);  // stem: channels 0..63, then 64..95 (86 real)
+    w += (size_t)C * IN * 9 + C;
+    for (int b = 0; b < 2 * NB; ++b) {
+        pack_conv(w, C, kc64, 4);
+        w += (size_t)C * C * 9 + C;
+    }
+    const float* pw = w;
+    const float* vw = w + (size_t)kPolicyPlanes * C + kPolicyPlanes;
+    for (int kc = 0; kc < kc64; ++kc)
+        for (int k = 0; k < 4; ++k) {
+            for (int row = 0; row < 128; ++row)
+                for (int e = 0; e < 16; ++e) {
+                    const int ci = kc * 64 + k * 16 + e;
+                    const int hc = (row % 32) < 7 ? 7 * (row / 32) + (row % 32) : -1;
+                    float v = 0.f;
+                    if (hc >= 0 && hc < kPolicyPlanes) v = pw[(size_t)hc * C + ci];
+                    else if (hc == kPolicyPlanes) v = vw[ci];
+                    t[row * 16 + e] = bf16_bits_rne(v);
+                }
+            t += 128 * 16;
+        }
+}
+
 }  // namespace nsb

@@ -380,3 +380,37 @@ def test_pair_kernel_stress_over_streams():
                                                        "pair_stress.py"), "8"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "mismatching launches: 0" in out.stdout
+
+
+def test_ts_kernel_matches_oracle_and_default_kernel(nb, orc, synth, monkeypatch):
+    """trunk_ts.cu (NSB_TRUNK128=ts: weights through tensor memory, A operand of tcgen05.mma read from
+    TMEM, K-block-pipelined layers): same results as the oracle within the logit tolerance and the same
+    decoded probabilities as the default kernel within float noise (the K order differs)."""
+    desc = nb.net_desc(128, 4)
+    blob = nb.random_blob(desc, 77)
+    n = 301                                                  # 151 groups over 148 CTAs: two passes on some
+    pos = synth.random_positions(n, seed=12)
+    fb = orc.pack(pos)
+    off, idx = synth.random_legal_moves(n, seed=6, edge_rows=False)
+
+    def run(ts):
+        if ts:
+            monkeypatch.setenv("NSB_TRUNK128", "ts")
+        else:
+            monkeypatch.delenv("NSB_TRUNK128", raising=False)
+        policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+        win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        legal = np.zeros(int(off[-1]), dtype=np.float32)
+        with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+            ctx.eval_async(0, fb, n, policy, win, draw)
+            ctx.await_(0)
+            ctx.eval_decode_async(0, fb, n, off, idx, nb.DECODE_PROBS, legal, win, draw, None)
+            ctx.await_(0)
+        return policy, win, draw, legal
+
+    p_ts, w_ts, d_ts, l_ts = run(True)
+    p_df, w_df, d_df, l_df = run(False)
+    op, ow, od = orc.forward(desc, blob, orc.expand(fb[:32 * 86], 32), emulate_bf16=True)
+    assert np.max(np.abs(p_ts[:32] - op)) < 2 * TOL_LOGIT_VS_BF16_ORACLE
+    assert np.max(np.abs(w_ts[:32] - ow)) < 2 * TOL_VALUE_VS_BF16_ORACLE
+    assert np.max(np.abs(l_ts - l_df)) < 5e-3 and np.max(np.abs(w_ts - w_df)) < 2e-3

@@ -37,3 +37,5 @@ print("phase stamps relative to kernel entry (cycles):")
 for k in order:
     print(f"  {names[k]:20s} {ph[k] - ph[0]:9d}")
 print("  layer-0 MMA start    ", t0 - ph[0], "   last MMA issued", t[-1, 1] - ph[0])
+if len(ph) > 12 and ph[12]:
+    print("  MMA warp: cycles spent waiting for weight stages (whole launch):", ph[12])

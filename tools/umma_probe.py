@@ -5,10 +5,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as graft
 nb = graft.load_package().binding
-names = {0: "cta1/none", 1: "cta1/sw128", 2: "pair/none", 3: "pair/sw128"}
-for layout in (0, 1, 2, 3):
+names = {0: "cta1/none", 1: "cta1/sw128", 2: "pair/none", 3: "pair/sw128", 4: "cta1/A-in-TMEM", 5: "cta1/A-in-TMEM + smem stores"}
+layouts = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else list(names)
+for layout in layouts:
     for N in (96, 192, 256):
-        if layout >= 2 and N == 96:
+        if layout in (2, 3) and N == 96:
             N = 128
         for shift in (0, 11):
             try:
