@@ -279,21 +279,27 @@ def run_b200(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "trunk_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(f"{C}x{blocks}@{B}")
-    roofline = {"bound": "tensor", "kernel": "trunk_pair_kernel (256 ch, cta_group::2)" if C == 256 else f"trunk_fused_kernel<{C}>", "achieved": round(achieved, 2),
-                "peak": tf_burst, "unit": "TFLOP/s", "frac": round(achieved / tf_burst, 4),
-                "frac_of_sustained_peak": round(achieved / tf_sust, 4), "peak_source": which,
-                "flops_per_launch": flops_launch, "avg_launch_ms": round(avg_launch_ms, 5),
-                "kernel_share_of_step": round(trunk_ms_sum / seq_elapsed_ms, 4) if seq_elapsed_ms > 0 else None,
-                "timing": f"{trunk_n} launches back to back on one stream, one CUDA event pair per launch; "
-                          f"that sub-run: {seq_elapsed_ms / max(K2, 1):.5f} ms/step",
-                "traffic": traffic,
-                # the same kernel with `slots` launches in flight (the `value` leg): whole-job useful FLOP/s
-                "in_flight": {"achieved": round(value / max(world, 1) * trunk_flops_per_sample(C, blocks) / 1e12, 2),
-                              "frac": round(value / max(world, 1) * trunk_flops_per_sample(C, blocks) / 1e12 / tf_burst, 4),
-                              "frac_of_sustained_peak": round(value / max(world, 1) * trunk_flops_per_sample(C, blocks)
-                                                              / 1e12 / tf_sust, 4),
-                              "streams": slots, "per": "GPU"}}
+        kname = ctx.trunk_kernel_name()
+        tag = ":duo" if "duo" in kname else ""
+        traffic = json.load(open(tp)).get(f"{C}x{blocks}@{B}{tag}")
+    # `achieved`: the timed region itself.  Its launches overlap (`slots` streams), so a launch's duration
+    # there is the steady-state time per launch, elapsed / launches; the same kernel launched alone
+    # (one stream, back to back, an event pair per launch) is reported beside it.
+    step_ms = elapsed_max / K
+    achieved_ss = flops_launch / (step_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": ctx.trunk_kernel_name(), "achieved": round(achieved_ss, 2),
+                "peak": tf_burst, "unit": "TFLOP/s", "frac": round(achieved_ss / tf_burst, 4),
+                "frac_of_sustained_peak": round(achieved_ss / tf_sust, 4), "peak_source": which,
+                "flops_per_launch": flops_launch, "avg_launch_ms": round(step_ms, 5),
+                "timing": f"timed region: {K} launches over {slots} streams, CUDA events on the streams, "
+                          "duration per launch = elapsed / launches (launches overlap); per GPU",
+                "isolated_launch": {"avg_launch_ms": round(avg_launch_ms, 5), "achieved": round(achieved, 2),
+                                    "frac": round(achieved / tf_burst, 4),
+                                    "frac_of_sustained_peak": round(achieved / tf_sust, 4),
+                                    "kernel_share_of_step": round(trunk_ms_sum / seq_elapsed_ms, 4) if seq_elapsed_ms > 0 else None,
+                                    "timing": f"{trunk_n} launches back to back on one stream, one CUDA event pair per "
+                                              f"launch; that sub-run: {seq_elapsed_ms / max(K2, 1):.5f} ms/step"},
+                "traffic": traffic}
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

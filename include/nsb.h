@@ -255,6 +255,11 @@ int nsb_debug_umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int l
 /* Diagnostics: sustained cp.async.bulk (L2 -> shared ring) rate per CTA in bytes per SM cycle. */
 int nsb_debug_bulk_rate_probe(int gpu, int ctas, int tile_bytes, int stages, int split, double* bytes_per_cycle);
 
+/* Which trunk kernel this ctx launches (chosen at nsb_create from the net width and the number of
+ * slots: a one-slot ctx gets the kernel with the shortest launch, a multi-slot ctx the one with the
+ * highest throughput when several batches are in flight). */
+const char* nsb_trunk_kernel_name(nsb_ctx* ctx);
+
 /* Kernel launches issued by this ctx since creation (bench "gpu_launches"). */
 uint64_t nsb_launch_count(nsb_ctx* ctx);
 

@@ -85,6 +85,7 @@ SIGNATURES = {
     "nsb_trunk_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "nsb_trunk_time_reset": (C.c_int, [_P]),
     "nsb_launch_count": (C.c_uint64, [_P]),
+    "nsb_trunk_kernel_name": (C.c_char_p, [_P]),
     "nsb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "nsb_host_free": (C.c_int, [_P]),
     "nsb_device_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
@@ -396,6 +397,9 @@ class Context:
 
     def trunk_time_reset(self):
         _check(lib().nsb_trunk_time_reset(self._h), "nsb_trunk_time_reset")
+
+    def trunk_kernel_name(self) -> str:
+        return lib().nsb_trunk_kernel_name(self._h).decode()
 
     def launch_count(self) -> int:
         return int(lib().nsb_launch_count(self._h))

@@ -52,6 +52,7 @@ struct nsb_ctx {
     int gpu = 0, batch_max = 0, num_sms = 0;
     int max_pairs = 0;  // co-resident CTA pairs of the 256-channel trunk (0: single-CTA kernel)
     bool use_ts = false;       // 128-channel trunk with the weights fed through tensor memory (trunk_ts.cu)
+    int duo_ctas = 0;          // > 0: the two-CTAs-per-SM 128-channel trunk (trunk_duo.cu), co-resident CTAs per SM
     nsb::DeviceCache cache{};  // device-resident evaluation cache (nsb_cache_create)
     nsb_net_desc desc{};
     bool loaded = false, timing = false;
@@ -151,11 +152,17 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
         if ((rc = trunk_pair_prepare(&max_pairs))) return rc;
         if (max_pairs > prop.multiProcessorCount / 2) max_pairs = prop.multiProcessorCount / 2;
     }
-    // NSB_TRUNK128=ts selects the experimental kernel that feeds the weights through tensor memory
-    // (trunk_ts.cu; parity-tested, measured 0-7 % slower than the default)
+    // 128 channels: a context with several slots is a throughput pipeline (batches in flight on
+    // several streams) and gets the two-CTAs-per-SM kernel (trunk_duo.cu: +6 % throughput, measured);
+    // a one-slot context evaluates one batch at a time and gets the kernel with the shorter launch
+    // (trunk_fused.cu).  NSB_TRUNK128 = classic | duo | ts forces one (ts: experimental trunk_ts.cu).
     const char* t128 = getenv("NSB_TRUNK128");
-    const bool use_ts = net->channels == 128 && t128 && strcmp(t128, "ts") == 0;
+    const bool is128 = net->channels == 128;
+    const bool use_ts = is128 && t128 && strcmp(t128, "ts") == 0;
+    const bool want_duo = is128 && !use_ts && (t128 ? strcmp(t128, "duo") == 0 : slots >= 2);
     if (use_ts && (rc = trunk_ts_prepare())) return rc;
+    int duo_ctas = 0;
+    if (want_duo && (rc = trunk_duo_prepare(&duo_ctas))) return rc;
     nsb_ctx* c = new (std::nothrow) nsb_ctx();
     if (!c) {
         set_error("out of host memory");
@@ -166,6 +173,7 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     c->num_sms = prop.multiProcessorCount;
     c->max_pairs = max_pairs;
     c->use_ts = use_ts;
+    c->duo_ctas = duo_ctas;
     c->desc = *net;
     c->slots.resize(slots);
     const size_t B = (size_t)batch_max;
@@ -244,7 +252,7 @@ int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
     std::vector<uint16_t> tiles((size_t)stages * kStageBytes / 2);
     std::vector<float> bias((size_t)NL * C), fc1t((size_t)81 * H), fc1b(H), fc2(2 * (size_t)H), fc2b(2);
     pack_weights(d, blob, tiles.data(), bias.data(), fc1t.data(), fc1b.data(), fc2.data(), fc2b.data());
-    if (c->use_ts) {  // same bias / FC arrays; the conv weights as a stream of 4 KB K = 16 steps
+    if (c->use_ts || c->duo_ctas > 0) {  // same bias / FC arrays; the conv weights as a stream of 4 KB K = 16 steps
         stages = ts_steps_per_pass(d);
         tiles.assign((size_t)stages * 2048, 0);
         pack_weights_ts(d, blob, tiles.data());
@@ -289,6 +297,7 @@ static int run_trunk(nsb_ctx* c, Slot& s, const EvalArgs& a) {
         NSB_CUDA(cudaEventRecord(s.ev[s.ev_used], s.stream));
     }
     int k = c->max_pairs > 0 ? launch_trunk_pair(c->net, a, c->max_pairs, s.stream)
+            : c->duo_ctas > 0 ? launch_trunk_duo(c->net, a, c->num_sms, c->duo_ctas, s.stream)
             : c->use_ts      ? launch_trunk_ts(c->net, a, c->num_sms, s.stream)
                              : launch_trunk_fused(c->net, a, c->num_sms, s.stream);
     if (k < 0) return k;
@@ -565,6 +574,14 @@ int nsb_cache_clear(nsb_ctx* c) {
     c->launches += (uint64_t)k;
     NSB_CUDA(cudaStreamSynchronize(c->slots[0].stream));
     return 0;
+}
+
+const char* nsb_trunk_kernel_name(nsb_ctx* c) {
+    if (!c) return "";
+    if (c->max_pairs > 0) return "trunk_pair_kernel (256 ch, cta_group::2 CTA pair)";
+    if (c->duo_ctas > 0) return "trunk_duo_kernel (128 ch, weights via TMEM, 2 CTAs per SM)";
+    if (c->use_ts) return "trunk_ts_kernel (128 ch, weights via TMEM, experimental)";
+    return c->desc.channels == 128 ? "trunk_fused_kernel<128>" : "trunk_fused_kernel<256>";
 }
 
 uint64_t nsb_cache_num_bundles(nsb_ctx* c) { return c ? (uint64_t)c->cache.num_bundles : 0; }

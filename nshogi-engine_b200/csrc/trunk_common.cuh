@@ -51,12 +51,13 @@ __device__ __forceinline__ int eval_index(const EvalArgs& a, int li, int n_eff) 
 // the 256 epilogue threads (et = 0..255): bitboards -> featS (bit strings) -> 16-byte records
 // [chunk j][slot][8 channels] of the stem's B operand at `stem_buf` (generic pointer to slot 0 of
 // chunk 0 minus the guard, i.e. the buffer base).  `tl` (optional) receives clock64 stamps.
-template <int NPOS, int SPITCH, int GUARD>
+// NT = number of threads doing the expansion (the kEpiBar named barrier is used with NT threads).
+template <int NPOS, int SPITCH, int GUARD, int NT = kEpiThreads>
 __device__ __forceinline__ void expand_features(const EvalArgs& a, int n_eff, int li0, uint4* featS, uint8_t* stem_buf,
                                                 int et, unsigned long long* tl) {
     // Per plane: the 81 occupancy bits as one contiguous little-endian bit string with the
     // rotation (extractbit.cu:20,26) already applied, plus the fill value as bf16 bits.
-    for (int i = et; i < NPOS * NSB_FEATURE_CHANNELS; i += kEpiThreads) {
+    for (int i = et; i < NPOS * NSB_FEATURE_CHANNELS; i += NT) {
         const int pos = i / NSB_FEATURE_CHANNELS, c = i - pos * NSB_FEATURE_CHANNELS;
         const int b = eval_index(a, li0 + pos, n_eff);
         uint4 f = make_uint4(0, 0, 0, 0);
@@ -64,12 +65,12 @@ __device__ __forceinline__ void expand_features(const EvalArgs& a, int n_eff, in
         featS[i] = plane_bits(f);
     }
     if (tl) tl[9] = clock64();
-    named_bar_sync(kEpiBar, kEpiThreads);
+    named_bar_sync(kEpiBar, NT);
     if (tl) tl[3] = clock64();
     // The stem reads 96 input channels = 12 chunks of 8 (86 real + zero padding).  One work
     // item = (position, chunk, board row): the 8 planes' bit strings are loaded once, the
     // row's 9-bit field is cut out with a funnel shift, and 9 records of 16 B are written.
-    for (int item = et; item < NPOS * kStemChunks * 9; item += kEpiThreads) {
+    for (int item = et; item < NPOS * kStemChunks * 9; item += NT) {
         const int pos = item / (kStemChunks * 9);
         const int r2 = item - pos * (kStemChunks * 9);
         const int j = r2 / 9, row = r2 - j * 9;

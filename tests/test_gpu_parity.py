@@ -414,3 +414,47 @@ def test_ts_kernel_matches_oracle_and_default_kernel(nb, orc, synth, monkeypatch
     assert np.max(np.abs(p_ts[:32] - op)) < 2 * TOL_LOGIT_VS_BF16_ORACLE
     assert np.max(np.abs(w_ts[:32] - ow)) < 2 * TOL_VALUE_VS_BF16_ORACLE
     assert np.max(np.abs(l_ts - l_df)) < 5e-3 and np.max(np.abs(w_ts - w_df)) < 2e-3
+
+
+def test_duo_kernel_selected_for_multi_slot_contexts_and_matches(nb, orc, synth, monkeypatch):
+    """A 128-channel ctx with >= 2 slots launches trunk_duo.cu (two CTAs per SM, weights through tensor
+    memory), a one-slot ctx trunk_fused.cu; both agree with the oracle, and with each other within float
+    noise (different K order).  1,000 positions: 500 groups over 296 co-resident CTAs, two passes."""
+    monkeypatch.delenv("NSB_TRUNK128", raising=False)
+    desc = nb.net_desc(128, 3)
+    blob = nb.random_blob(desc, 21)
+    n = 1000
+    pos = synth.random_positions(n, seed=4)
+    fb = orc.pack(pos)
+    off, idx = synth.random_legal_moves(n, seed=8, edge_rows=False)
+
+    def run(slots):
+        policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+        win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        legal = np.zeros(int(off[-1]), dtype=np.float32)
+        with nb.Context(desc, batch_max=n, slots=slots, blob=blob) as ctx:
+            name = ctx.trunk_kernel_name()
+            ctx.eval_async(0, fb, n, policy, win, draw)
+            ctx.await_(0)
+            ctx.eval_decode_async(slots - 1, fb, n, off, idx, nb.DECODE_PROBS, legal, win, draw, None)
+            ctx.await_(slots - 1)
+        return name, policy, win, legal
+
+    n1, p1, w1, l1 = run(1)
+    n2, p2, w2, l2 = run(2)
+    assert "trunk_fused_kernel<128>" in n1 and "trunk_duo_kernel" in n2
+    op, ow, od = orc.forward(desc, blob, orc.expand(fb[:24 * 86], 24), emulate_bf16=True)
+    for p, w in ((p1, w1), (p2, w2)):
+        assert np.max(np.abs(p[:24] - op)) < 2 * TOL_LOGIT_VS_BF16_ORACLE and np.max(np.abs(w[:24] - ow)) < 2 * TOL_VALUE_VS_BF16_ORACLE
+    assert np.max(np.abs(l1 - l2)) < 5e-3 and np.max(np.abs(w1 - w2)) < 2e-3
+    # batch-index invariance inside the duo kernel: identical positions give identical bits
+    same = np.random.default_rng(0).integers(0, 8, size=n)
+    fb8 = np.ascontiguousarray(fb.reshape(n, 86)[same].reshape(-1))
+    policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+    win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    with nb.Context(desc, batch_max=n, slots=2, blob=blob) as ctx:
+        ctx.eval_async(0, fb8, n, policy, win, draw)
+        ctx.await_(0)
+    first = {int(k): int(np.argmax(same == k)) for k in np.unique(same)}
+    ref_rows = np.array([first[int(k)] for k in same])
+    assert np.array_equal(policy.view(np.uint32), policy[ref_rows].view(np.uint32)) and np.array_equal(win, win[ref_rows])
