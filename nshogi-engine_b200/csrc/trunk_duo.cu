@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
     const int my_passes =
         (int)blockIdx.x < groups ? (groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int NL = net.num_layers;
+    const bool stamp = a.timeline && blockIdx.x == 0;  // diagnostics: tools/timeline.py
 
     // ---- one-time setup ---------------------------------------------------------------------
     for (int i = threadIdx.x; i < 2 * G::BUF_BYTES / 16; i += G::THREADS)
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                     mbar_wait(bar_act, act_phase);
                     act_phase ^= 1u;
                     tc_fence_after();
+                    if (stamp && p == 0 && lane == 0) a.timeline[4 * L + 0] = clock64();
                     const bool head = (L == NL - 1);
                     const uint32_t in_buf = (L & 1) ? bufA : bufB;
                     const int ntaps = head ? 1 : 9;
@@ -257,12 +259,11 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                                 if (elect_one()) {
                                     const uint32_t a_base = tmem_base + G::A_COL0 + slot * G::A_STAGE_COLS;
 #pragma unroll
-                                    for (int k2 = 0; k2 < 2; ++k2) {
-                                        const int k = 2 * h + k2;
-                                        const uint64_t bdesc =
-                                            make_smem_desc(b_base + (uint32_t)(2 * k * G::SPITCH * 16), b_lbo, 128);
-                                        umma_bf16_ts(tmem_base, a_base + k2 * 8, bdesc, idesc, (uint32_t)((kc | tap | k) != 0));
-                                    }
+                                    const uint32_t b_lo = smem_desc_lo(b_base, b_lbo) + (uint32_t)(4 * h * G::SPITCH);
+#pragma unroll
+                                    for (int k2 = 0; k2 < 2; ++k2)
+                                        umma_bf16_ts(tmem_base, a_base + k2 * 8, smem_desc_from(b_lo + (uint32_t)(2 * k2 * G::SPITCH), 128),
+                                                     idesc, (uint32_t)((kc | tap | h | k2) != 0));
                                     umma_commit(bar_aempty(slot));
                                 }
                                 __syncwarp();
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                     }
                     if (elect_one()) umma_commit(bar_acc);
                     __syncwarp();
+                    if (stamp && p == 0 && lane == 0) a.timeline[4 * L + 1] = clock64();
                 }
             }
         }
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                 mbar_wait(bar_acc, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
+                if (stamp && p == 0 && et == 0) a.timeline[4 * L + 2] = clock64();
                 const uint32_t out_buf = ((L & 1) ? bufB : bufA) + G::GUARD * 16;
                 const bool residual = (L >= 2) && ((L & 1) == 0);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -323,6 +326,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_act);
+                if (stamp && p == 0 && et == 0) a.timeline[4 * L + 3] = clock64();
             }
 
             // -- heads: row 32*(h/7) + h%7 of the accumulator holds head channel h

@@ -77,18 +77,24 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
     const uint32_t tmem_base = *tmem_holder;
     if (a.timeline && blockIdx.x == 0 && threadIdx.x == 128) a.timeline[4 * NL + 1] = clock64();
 
-    if (warp == 0) {
-        // ===== weight producer: linear stream of 16 KB tiles, re-walked once per pass ==========
+    if (warp == 0 || warp == 2) {
+        // ===== weight producers: linear stream of 16 KB tiles, re-walked once per pass ==========
+        // TWO of them, on alternate tiles: one thread cannot issue more than one bulk copy per ~290
+        // cycles (tools/bulk_probe.py), and with its waits that is one tile per ~410 cycles - slower
+        // than the 392 cycles the four MMAs of a tile take.  The ring position of tile t (tiles since
+        // kernel start) is t % NSTAGES, its use number t / NSTAGES.
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int p = 0; p < my_passes; ++p) {
-                const uint8_t* src = net.tiles;
-                for (int s = 0; s < net.stages_per_pass; ++s, src += kStageBytes) {
-                    mbar_wait(bar_empty(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(bar_full(stage), kStageBytes);
-                    bulk_g2s(ring + stage * kStageBytes, src, kStageBytes, bar_full(stage));
-                    if (++stage == G::NSTAGES) { stage = 0; phase ^= 1u; }
-                }
+            const uint32_t me = warp >> 1;
+            const uint32_t total = (uint32_t)my_passes * (uint32_t)net.stages_per_pass;
+            uint32_t s_in_pass = me % (uint32_t)net.stages_per_pass;
+            for (uint32_t t = me; t < total; t += 2) {
+                const uint32_t stage = t % G::NSTAGES, phase = (t / G::NSTAGES) & 1u;
+                mbar_wait(bar_empty(stage), phase ^ 1u);
+                mbar_arrive_expect_tx(bar_full(stage), kStageBytes);
+                bulk_g2s(ring + stage * kStageBytes, net.tiles + (size_t)s_in_pass * kStageBytes, kStageBytes,
+                         bar_full(stage));
+                s_in_pass += 2;
+                if (s_in_pass >= (uint32_t)net.stages_per_pass) s_in_pass -= (uint32_t)net.stages_per_pass;
             }
         }
     } else if (warp == 1) {
@@ -117,14 +123,13 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
                             tc_fence_after();
                             const int ksteps = (L == 0 && kc == 1) ? (kStemChunks - 8) / 2 : 4;
                             if (elect_one()) {
-                                const uint32_t a_base = ring + stage * kStageBytes;
+                                const uint32_t a_lo = smem_desc_lo(ring + stage * kStageBytes, 2048);
+                                const uint32_t b_lo = smem_desc_lo(b_base, b_lbo);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     if (k >= ksteps) break;
-                                    const uint64_t adesc = make_smem_desc(a_base + k * 4096, 2048, 128);
-                                    const uint64_t bdesc =
-                                        make_smem_desc(b_base + (uint32_t)(2 * k * G::SPITCH * 16), b_lbo, 128);
-                                    umma_bf16(tmem_base + half * G::NCOLS, adesc, bdesc, idesc,
+                                    umma_bf16(tmem_base + half * G::NCOLS, smem_desc_from(a_lo + k * (4096 >> 4), 128),
+                                              smem_desc_from(b_lo + (uint32_t)(2 * k * G::SPITCH), 128), idesc,
                                               (uint32_t)((tap | kc | k) != 0));
                                 }
                                 umma_commit(bar_empty(stage));  // frees the ring slot when the MMAs retire

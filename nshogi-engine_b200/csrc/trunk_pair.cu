@@ -139,14 +139,14 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                         tc_fence_after();
                         const int ksteps = (L == 0 && kc == 1) ? (kStemChunks - 8) / 2 : 4;
                         if (elect_one()) {
-                            const uint32_t a_base = ring + stage * kStageBytes;
+                            const uint32_t a_lo = smem_desc_lo(ring + stage * kStageBytes, 2048);
+                            const uint32_t b_lo = smem_desc_lo(b_base, b_lbo);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 if (k >= ksteps) break;
-                                const uint64_t adesc = make_smem_desc(a_base + k * 4096, 2048, 128);
-                                const uint64_t bdesc =
-                                    make_smem_desc(b_base + (uint32_t)(2 * k * G::SPITCH * 16), b_lbo, 128);
-                                umma_bf16_pair(tmem_base, adesc, bdesc, idesc, (uint32_t)((tap | kc | k) != 0));
+                                umma_bf16_pair(tmem_base, smem_desc_from(a_lo + k * (4096 >> 4), 128),
+                                               smem_desc_from(b_lo + (uint32_t)(2 * k * G::SPITCH), 128), idesc,
+                                               (uint32_t)((tap | kc | k) != 0));
                             }
                             umma_commit_pair(bar_empty(stage), 3);  // frees the stage in BOTH rings
                         }

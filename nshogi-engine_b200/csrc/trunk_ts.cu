@@ -200,12 +200,12 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint32_t a_base = tmem_base + G::A_COL0 + slot * G::A_STAGE_COLS;
+                                const uint32_t b_lo = smem_desc_lo(b_base, b_lbo);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     if (k >= nk) break;
-                                    const uint64_t bdesc =
-                                        make_smem_desc(b_base + (uint32_t)(2 * k * G::SPITCH * 16), b_lbo, 128);
-                                    umma_bf16_ts(acc, a_base + k * 8, bdesc, idesc, (uint32_t)((kc | tap | k) != 0));
+                                    umma_bf16_ts(acc, a_base + k * 8, smem_desc_from(b_lo + (uint32_t)(2 * k * G::SPITCH), 128), idesc,
+                                                 (uint32_t)((kc | tap | k) != 0));
                                 }
                                 umma_commit(bar_aempty(slot));  // frees the ring stage when the MMAs retire
                             }

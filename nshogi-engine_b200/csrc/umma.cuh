@@ -112,6 +112,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 
+// The same descriptor split into its halves for issue loops: shared-memory addresses are below 256 KB,
+// so (addr >> 4) needs no mask, and consecutive K steps differ by a constant in the low word only -
+// one integer add per descriptor instead of a shift and two logic ops on the (narrow) uniform datapath.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (smem_addr >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t smem_desc_from(uint32_t lo, uint32_t sbo_bytes) {
+    return ((uint64_t)(((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14)) << 32) | lo;
+}
+
 // Instruction descriptor for kind::f16, A/B = bf16 K-major, D = fp32.
 //   [4,6) c_format=1 (f32) | [7,10) a_format=1 (bf16) | [10,13) b_format=1 | [15] a_major=0 (K)
 //   [16] b_major=0 (K) | [17,23) N>>3 | [24,29) M>>4

@@ -186,12 +186,38 @@ umma_ts_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict_
             umma_bf16_ts(tmem_base, a_tmem + k16 * 8, bd, idesc, (fresh && k16 == 0) ? 0u : 1u);
         }
     };
+    // smem_noise == 2: the trunk's ring protocol around every `ring_mmas` MMAs (odd iters: 2, even: 4): a
+    // wait on an already complete mbarrier, tcgen05.fence, elect, the MMAs, a commit, __syncwarp
+    const int ring_mmas = (iters & 1) ? 2 : 4;
+    if (threadIdx.x == 0) {
+        mbar_init(bar + 32, 1);
+        mbar_init(bar + 40, 1);
+        fence_mbar_init();
+        mbar_arrive(bar + 40);  // phase 0 of this one is complete for good
+    }
+    __syncthreads();
     if (warp == 0) {
         uint32_t parity = 0;
         for (int it = 0; it < iters + 1; ++it) {
             const unsigned long long t0 = clock64();
             const int reps = it == 0 ? 1 : 16;
             for (int rep = 0; rep < reps; ++rep) {
+                if (smem_noise == 2) {
+                    for (int k0 = 0; k0 < K / 16; k0 += ring_mmas) {
+                        mbar_wait(bar + 40, 0);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            for (int k16 = k0; k16 < k0 + ring_mmas; ++k16) {
+                                const uint64_t bd =
+                                    make_smem_desc(b0 + (uint32_t)((k16 * 2 * b_rows + shift) * 16), b_rows * 16, 128);
+                                umma_bf16_ts(tmem_base, a_tmem + k16 * 8, bd, idesc, (it == 0 && rep == 0 && k16 == 0) ? 0u : 1u);
+                            }
+                            umma_commit(bar + 32);
+                        }
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 if (elect_one()) issue_all(it == 0 && rep == 0);
                 __syncwarp();
             }
@@ -212,7 +238,7 @@ umma_ts_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict_
         __syncwarp();
         mbar_wait(bar, parity);
         if (threadIdx.x == 0) *stop = 1;
-    } else if (smem_noise > 0) {
+    } else if (smem_noise == 1) {
         uint4* dst = reinterpret_cast<uint4*>(noise);
         unsigned k = threadIdx.x;
         while (*stop == 0) {
@@ -339,7 +365,7 @@ int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int
     const bool pair = layout == 2 || layout == 3;
     const int lay = ts ? 0 : (layout & 1);
     if (n_cols % 32 || n_cols < 32 || n_cols > 256 || k_elems % 64 || k_elems <= 0 || shift_rows < 0 ||
-        shift_rows > 64 || iters < 1 || layout < 0 || layout > 5) {
+        shift_rows > 64 || iters < 1 || layout < 0 || layout > 6) {
         set_error("umma_probe: bad arguments");
         return NSB_ERR_INVALID;
     }
@@ -371,7 +397,7 @@ int umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
         if (ts)
-            umma_ts_probe_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, layout == 5 ? 1 : 0, iters, dd, dc);
+            umma_ts_probe_kernel<<<1, 128, smem>>>(da, db, N, K, rows, shift_rows, layout - 4, iters, dd, dc);
         else if (pair)
             umma_pair_probe_kernel<<<2, 128, smem>>>(da, db, N, K, rows, shift_rows, lay, iters, dd, dc);
         else
