@@ -253,12 +253,35 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                         for (int tap = 0; tap < ntaps; ++tap) {
                             const int shift = head ? 0 : (tap / 3 - 1) * 10 + (tap % 3 - 1);
                             const uint32_t b_base = in_buf + (uint32_t)((kc * 8 * G::SPITCH + G::GUARD + shift) * 16);
+                            if (halves == 2) {
+                                // both ring stages of the tap in one round of the issue protocol (wait, fence,
+                                // elect, commit, warp sync cost ~190 cycles a round): 4 MMAs per round
+                                const uint32_t s0 = slot, s1 = (slot + 1) % G::A_STAGES;
+                                const uint32_t ph1 = s1 == 0 ? phase ^ 1u : phase;
+                                mbar_wait(bar_afull(s0), phase);
+                                mbar_wait(bar_afull(s1), ph1);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const uint32_t b_lo = smem_desc_lo(b_base, b_lbo);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const uint32_t a_base = tmem_base + G::A_COL0 + ((k < 2) ? s0 : s1) * G::A_STAGE_COLS;
+                                        umma_bf16_ts(tmem_base, a_base + (k & 1) * 8, smem_desc_from(b_lo + (uint32_t)(2 * k * G::SPITCH), 128),
+                                                     idesc, (uint32_t)((kc | tap | k) != 0));
+                                        if (k == 1) umma_commit(bar_aempty(s0));
+                                    }
+                                    umma_commit(bar_aempty(s1));
+                                }
+                                __syncwarp();
+                                slot = (slot + 2) % G::A_STAGES;
+                                if (slot < 2) phase ^= 1u;
+                                continue;
+                            }
                             for (int h = 0; h < halves; ++h) {
                                 mbar_wait(bar_afull(slot), phase);
                                 tc_fence_after();
                                 if (elect_one()) {
                                     const uint32_t a_base = tmem_base + G::A_COL0 + slot * G::A_STAGE_COLS;
-#pragma unroll
                                     const uint32_t b_lo = smem_desc_lo(b_base, b_lbo) + (uint32_t)(4 * h * G::SPITCH);
 #pragma unroll
                                     for (int k2 = 0; k2 < 2; ++k2)
