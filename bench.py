@@ -268,6 +268,38 @@ def run_b200(args):
 
     e2e_fused = time_e2e(True)
     e2e_infer = time_e2e(False)
+
+    # packed positions in (108 B instead of 1,376 B per position over PCIe): stage 1 runs in the trunk
+    # kernel's prologue, still one launch per batch
+    h_pos = [nb.PinnedArray((B,), nb.POSITION) for _ in range(h_pool_n)]
+    for k, a_ in enumerate(h_pos):
+        a_.array[:] = pos[rng.integers(0, len(pos), size=B)]
+
+    def e2e_positions_loop(steps):
+        nonlocal sink
+        for i in range(steps):
+            s = i % slots
+            if i >= slots:
+                ctx.await_(s)
+                sink += float(h_win[s].array[0])
+            ctx.eval_positions_decode_async(s, h_pos[i % h_pool_n].array, B, h_off.array, h_idx.array, nb.DECODE_PROBS,
+                                            h_legal[s].array, h_win[s].array, h_draw[s].array, h_flag[s].array)
+        for s in range(slots):
+            ctx.await_(s)
+            sink += float(h_win[s].array[0])
+
+    e2e_positions_loop(max(W, slots))
+    rep.barrier()
+    nb.device_sync()
+    lp0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    e2e_positions_loop(K)
+    nb.device_sync()
+    dt = (time.perf_counter() - t0) * 1e3
+    pos_launches = ctx.launch_count() - lp0
+    rep.barrier()
+    _, dt_max = rep.aggregate({}, dt, device=dev_device)
+    e2e_positions = rep.whole_job_rate(B * K * world, dt_max)
     clocks = sampler.stop()
     selfplay = None if args.no_selfplay else selfplay_leg(args, info, rep, dev_device)
 
@@ -317,6 +349,10 @@ def run_b200(args):
         "e2e_infer_contract": {"value": round(e2e_infer, 1), "unit": UNIT,
                                "api": "nsb_eval_async + nsb_await == Infer::computeNonBlocking/await (dense logits)",
                                "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": B * 2187 * 4 + B * 8},
+        "e2e_positions": {"value": round(e2e_positions, 1), "unit": UNIT,
+                          "api": "nsb_eval_positions_decode_async + nsb_await (packed positions in, stage 1 in the trunk prologue)",
+                          "h2d_bytes_per_step": B * 108 + (B + 1) * 4 + n_moves * 2,
+                          "d2h_bytes_per_step": n_moves * 4 + B * 4 * 2 + B, "launches_per_step": pos_launches / K},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "counters": counters,
     }

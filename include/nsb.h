@@ -246,6 +246,9 @@ int nsb_event_elapsed_ms(void* start, void* stop, float* ms);
  * MLP done, decode done}: 4 * layers + 8 values. */
 int nsb_debug_trunk_timeline(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* d_features, size_t n,
                              uint64_t* host_stamps, size_t max_stamps);
+/* Same launch fed with packed positions (stage 1 in the kernel's prologue). */
+int nsb_debug_trunk_timeline_positions(nsb_ctx* ctx, int slot, const nsb_position* d_positions, size_t n,
+                                       uint64_t* host_stamps, size_t max_stamps);
 
 /* Diagnostics: issue-to-retire rate (cycles per M128 x n_cols x K16 MMA) and numerical check of one
  * operand layout with a row-shifted B start: layout 0 = SWIZZLE_NONE 16-byte rows, 1 = SWIZZLE_128B. */

@@ -77,6 +77,7 @@ SIGNATURES = {
                                                          _P]),
     "nsb_eval_cached_decode_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "nsb_debug_trunk_timeline": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
+    "nsb_debug_trunk_timeline_positions": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
     "nsb_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double)]),
     "nsb_debug_bulk_rate_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
@@ -377,11 +378,11 @@ class Context:
                                                    _ptr(d_idx), mode, _ptr(d_legal), _ptr(d_win), _ptr(d_draw),
                                                    _ptr(d_flag), _ptr(d_hit)), "nsb_eval_cached_decode_device")
 
-    def debug_trunk_timeline(self, slot, d_features, n):
+    def debug_trunk_timeline(self, slot, d_features, n, positions=False):
         nl = 2 * self.desc.blocks + 2
         out = np.zeros(nl * 4 + 16, dtype=np.uint64)
-        _check(lib().nsb_debug_trunk_timeline(self._h, slot, _ptr(d_features), n, out.ctypes.data, out.size),
-               "nsb_debug_trunk_timeline")
+        fn = lib().nsb_debug_trunk_timeline_positions if positions else lib().nsb_debug_trunk_timeline
+        _check(fn(self._h, slot, _ptr(d_features), n, out.ctypes.data, out.size), "nsb_debug_trunk_timeline")
         return out[:nl * 4].reshape(nl, 4), out[nl * 4:]
 
     def stream(self, slot=0) -> int:

@@ -52,6 +52,7 @@ struct nsb_ctx {
     int gpu = 0, batch_max = 0, num_sms = 0;
     int max_pairs = 0;  // co-resident CTA pairs of the 256-channel trunk (0: single-CTA kernel)
     bool use_ts = false;       // 128-channel trunk with the weights fed through tensor memory (trunk_ts.cu)
+    bool fuse_pack = true;     // packed positions are expanded in the trunk prologue (NSB_FUSE_PACK=0: separate pack kernel)
     int duo_ctas = 0;          // > 0: the two-CTAs-per-SM 128-channel trunk (trunk_duo.cu), co-resident CTAs per SM
     nsb::DeviceCache cache{};  // device-resident evaluation cache (nsb_cache_create)
     nsb_net_desc desc{};
@@ -174,6 +175,7 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     c->max_pairs = max_pairs;
     c->use_ts = use_ts;
     c->duo_ctas = duo_ctas;
+    if (const char* fp = getenv("NSB_FUSE_PACK")) c->fuse_pack = strcmp(fp, "0") != 0;
     c->desc = *net;
     c->slots.resize(slots);
     const size_t B = (size_t)batch_max;
@@ -350,8 +352,25 @@ int nsb_eval_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, s
     return 0;
 }
 
-static int eval_decode_common(nsb_ctx* c, Slot& s, size_t n, const uint32_t* move_off, const uint16_t* move_idx,
-                              int mode, float* legal_out, float* win, float* draw, uint8_t* nan_flag) {
+// Stage 1 for a batch whose packed positions are already in s.d_pos: either it is left to the trunk
+// kernel's prologue (*fused = s.d_pos; the bitboards never exist in HBM), or the
+// standalone pack kernel fills s.d_feat (*fused = nullptr).
+static int stage1(nsb_ctx* c, Slot& s, size_t n, const nsb_position** fused) {
+    if (c->fuse_pack) {
+        *fused = s.d_pos;
+        return 0;
+    }
+    *fused = nullptr;
+    int k = launch_pack_positions(s.d_pos, n, s.d_feat, s.stream);
+    if (k < 0) return k;
+    NSB_CUDA(cudaGetLastError());
+    c->launches += (uint64_t)k;
+    return 0;
+}
+
+static int eval_decode_common(nsb_ctx* c, Slot& s, const nsb_position* d_positions, size_t n, const uint32_t* move_off,
+                              const uint16_t* move_idx, int mode, float* legal_out, float* win, float* draw,
+                              uint8_t* nan_flag) {
     const size_t total = move_off[n];
     if (move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) {
         set_error("eval_decode: move_off must start at 0 and hold at most %d moves per position",
@@ -363,6 +382,7 @@ static int eval_decode_common(nsb_ctx* c, Slot& s, size_t n, const uint32_t* mov
         NSB_CUDA(cudaMemcpyAsync(s.d_idx, move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
     EvalArgs a{};
     a.features = s.d_feat;
+    a.positions = d_positions;
     a.n = (int)n;
     a.policy = nullptr;  // dense logits never leave the SM
     a.win = s.d_win;
@@ -397,7 +417,7 @@ int nsb_eval_decode_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* feat
     Slot& s = c->slots[slot];
     NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
                              cudaMemcpyHostToDevice, s.stream));
-    return eval_decode_common(c, s, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag);
+    return eval_decode_common(c, s, nullptr, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag);
 }
 
 int nsb_eval_positions_async(nsb_ctx* c, int slot, const nsb_position* positions, size_t n, float* policy,
@@ -412,12 +432,11 @@ int nsb_eval_positions_async(nsb_ctx* c, int slot, const nsb_position* positions
     if (n == 0) return 0;
     Slot& s = c->slots[slot];
     NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
-    int k = launch_pack_positions(s.d_pos, n, s.d_feat, s.stream);
-    if (k < 0) return k;
-    NSB_CUDA(cudaGetLastError());
-    c->launches += (uint64_t)k;
+    const nsb_position* fused = nullptr;
+    if ((rc = stage1(c, s, n, &fused))) return rc;
     EvalArgs a{};
     a.features = s.d_feat;
+    a.positions = fused;
     a.n = (int)n;
     a.policy = s.d_policy;
     a.win = s.d_win;
@@ -443,11 +462,9 @@ int nsb_eval_positions_decode_async(nsb_ctx* c, int slot, const nsb_position* po
     if (n == 0) return 0;
     Slot& s = c->slots[slot];
     NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
-    int k = launch_pack_positions(s.d_pos, n, s.d_feat, s.stream);
-    if (k < 0) return k;
-    NSB_CUDA(cudaGetLastError());
-    c->launches += (uint64_t)k;
-    return eval_decode_common(c, s, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag);
+    const nsb_position* fused = nullptr;
+    if ((rc = stage1(c, s, n, &fused))) return rc;
+    return eval_decode_common(c, s, fused, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag);
 }
 
 int nsb_await(nsb_ctx* c, int slot) {
@@ -631,7 +648,8 @@ int nsb_cache_probe_device(nsb_ctx* c, int slot, const uint64_t* d_hashes, size_
 }
 
 // probe -> trunk on the misses (fused decode + fused store); everything on the slot's stream
-static int eval_cached_enqueue(nsb_ctx* c, Slot& s, const nsb_feature_bitboard* d_features, size_t n,
+static int eval_cached_enqueue(nsb_ctx* c, Slot& s, const nsb_feature_bitboard* d_features,
+                               const nsb_position* d_positions, size_t n,
                                const uint64_t* d_hashes, const uint32_t* d_off, const uint16_t* d_idx, int mode,
                                float* d_legal, float* d_win, float* d_draw, uint8_t* d_nan_flag, uint8_t* d_hit) {
     NSB_CUDA(cudaMemsetAsync(s.d_miss_count, 0, sizeof(int), s.stream));
@@ -641,6 +659,7 @@ static int eval_cached_enqueue(nsb_ctx* c, Slot& s, const nsb_feature_bitboard* 
     c->launches += (uint64_t)k;
     EvalArgs a{};
     a.features = d_features;
+    a.positions = d_positions;  // set: stage 1 runs in the trunk prologue, for the misses only
     a.n = (int)n;
     a.win = d_win;
     a.draw = d_draw;
@@ -669,7 +688,7 @@ int nsb_eval_cached_decode_device(nsb_ctx* c, int slot, const nsb_feature_bitboa
         return NSB_ERR_INVALID;
     }
     if (n == 0) return 0;
-    return eval_cached_enqueue(c, c->slots[slot], d_features, n, d_hashes, d_move_off, d_move_idx, mode, d_legal_out, d_win,
+    return eval_cached_enqueue(c, c->slots[slot], d_features, nullptr, n, d_hashes, d_move_off, d_move_idx, mode, d_legal_out, d_win,
                                d_draw, d_nan_flag, d_hit);
 }
 
@@ -698,8 +717,8 @@ int nsb_eval_cached_decode_async(nsb_ctx* c, int slot, const nsb_feature_bitboar
     NSB_CUDA(cudaMemcpyAsync(s.d_off, move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
     if (total)
         NSB_CUDA(cudaMemcpyAsync(s.d_idx, move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
-    rc = eval_cached_enqueue(c, s, s.d_feat, n, s.d_hash, s.d_off, s.d_idx, mode, s.d_legal, s.d_win, s.d_draw, s.d_flag,
-                             s.d_hit);
+    rc = eval_cached_enqueue(c, s, s.d_feat, nullptr, n, s.d_hash, s.d_off, s.d_idx, mode, s.d_legal, s.d_win, s.d_draw,
+                             s.d_flag, s.d_hit);
     if (rc) return rc;
     if (total)
         NSB_CUDA(cudaMemcpyAsync(legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
@@ -735,12 +754,10 @@ int nsb_eval_positions_cached_decode_async(nsb_ctx* c, int slot, const nsb_posit
     NSB_CUDA(cudaMemcpyAsync(s.d_off, move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
     if (total)
         NSB_CUDA(cudaMemcpyAsync(s.d_idx, move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
-    int k = launch_pack_positions(s.d_pos, n, s.d_feat, s.stream);
-    if (k < 0) return k;
-    NSB_CUDA(cudaGetLastError());
-    c->launches += (uint64_t)k;
-    rc = eval_cached_enqueue(c, s, s.d_feat, n, s.d_hash, s.d_off, s.d_idx, mode, s.d_legal, s.d_win, s.d_draw, s.d_flag,
-                             s.d_hit);
+    const nsb_position* fused = nullptr;
+    if ((rc = stage1(c, s, n, &fused))) return rc;
+    rc = eval_cached_enqueue(c, s, s.d_feat, fused, n, s.d_hash, s.d_off, s.d_idx, mode, s.d_legal, s.d_win, s.d_draw,
+                             s.d_flag, s.d_hit);
     if (rc) return rc;
     if (total)
         NSB_CUDA(cudaMemcpyAsync(legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
@@ -751,11 +768,11 @@ int nsb_eval_positions_cached_decode_async(nsb_ctx* c, int slot, const nsb_posit
     return 0;
 }
 
-int nsb_debug_trunk_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n,
-                             uint64_t* host_stamps, size_t max_stamps) {
+static int debug_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, const nsb_position* d_positions,
+                          size_t n, uint64_t* host_stamps, size_t max_stamps) {
     int rc = check_ctx(c, slot);
     if (rc) return rc;
-    if (!c->loaded || !d_features || !host_stamps || n == 0) {
+    if (!c->loaded || (!d_features && !d_positions) || !host_stamps || n == 0) {
         set_error("nsb_debug_trunk_timeline: bad arguments or weights not loaded");
         return NSB_ERR_INVALID;
     }
@@ -770,6 +787,7 @@ int nsb_debug_trunk_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d
     NSB_CUDA(cudaMemsetAsync(d_t, 0, need * 8, s.stream));
     EvalArgs a{};
     a.features = d_features;
+    a.positions = d_positions;
     a.n = (int)n;
     a.policy = s.d_policy;
     a.win = s.d_win;
@@ -791,6 +809,16 @@ int nsb_debug_trunk_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d
     }
     cudaFree(d_t);
     return rc;
+}
+
+int nsb_debug_trunk_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n,
+                             uint64_t* host_stamps, size_t max_stamps) {
+    return debug_timeline(c, slot, d_features, nullptr, n, host_stamps, max_stamps);
+}
+
+int nsb_debug_trunk_timeline_positions(nsb_ctx* c, int slot, const nsb_position* d_positions, size_t n,
+                                       uint64_t* host_stamps, size_t max_stamps) {
+    return debug_timeline(c, slot, nullptr, d_positions, n, host_stamps, max_stamps);
 }
 
 int nsb_extract_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n, int channels,

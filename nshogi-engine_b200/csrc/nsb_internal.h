@@ -115,6 +115,8 @@ struct DeviceCache {
 
 struct EvalArgs {
     const nsb_feature_bitboard* features;  // [n][86]
+    const nsb_position* positions;         // [n] or nullptr; when set, stage 1 runs in the kernel's prologue
+                                           // and `features` is not read
     int n;
     float* policy;                // [n][2187] or nullptr (fused decode only)
     float* win;                   // [n]

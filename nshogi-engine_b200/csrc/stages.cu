@@ -10,6 +10,7 @@
 
 #include "decode_device.cuh"
 #include "nsb_internal.h"
+#include "pack_device.cuh"
 
 namespace nsb {
 
@@ -146,85 +147,19 @@ int launch_extract(const nsb_feature_bitboard* d_fb, size_t n, int channels, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// pack: one warp per position.  Board planes: lane s holds the piece code of squares s, s+32, s+64
-// and MATCH.ANY hands every lane the occupancy word of its own piece code in one instruction, so
-// the 28 board planes cost three match instructions per position; lane c then assembles channels
-// c, c+32, c+64 (channel order: reference src/evaluate/preset.h:20-66, semantics SURVEY.md App.
-// A.2 — builder-defined, libnshogi absent).  Output: 86 x 16 B, coalesced.
+// pack: one warp per position (pack_device.cuh holds the warp routine, which the trunk kernels also
+// run in their prologue when they are handed packed positions).  Output: 86 x 16 B, coalesced.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPackWarps = 4;
 
-__device__ __forceinline__ int stand_piece_of(int k /*0..25*/, int* need) {
-    // P1-6 L1-4 N1-4 S1-4 G1-4 B1-2 R1-2
-    if (k < 6) { *need = k + 1; return 0; }
-    if (k < 10) { *need = k - 5; return 1; }
-    if (k < 14) { *need = k - 9; return 2; }
-    if (k < 18) { *need = k - 13; return 3; }
-    if (k < 22) { *need = k - 17; return 4; }
-    if (k < 24) { *need = k - 21; return 5; }
-    *need = k - 23;
-    return 6;
-}
-
 __global__ void __launch_bounds__(kPackWarps * 32)
 pack_positions_kernel(const nsb_position* __restrict__ pos, int n, uint4* __restrict__ fb) {
-    __shared__ __align__(16) unsigned char s_pos[kPackWarps][112];
-    __shared__ uint32_t s_occ[kPackWarps][28][3];   // occupancy words of the 28 board planes
+    __shared__ uint4 s_occ[kPackWarps][28];   // occupancy words of the 28 board planes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kPackWarps + warp;
     if (b >= n) return;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(pos + b);  // 108 B = 27 words
-    if (lane < 27) reinterpret_cast<uint32_t*>(s_pos[warp])[lane] = __ldg(src + lane);
-    if (lane < 28) s_occ[warp][lane][0] = s_occ[warp][lane][1] = s_occ[warp][lane][2] = 0u;
-    __syncwarp();
-    const nsb_position* p = reinterpret_cast<const nsb_position*>(s_pos[warp]);
-    const int me = p->side & 1, op = me ^ 1;
-#pragma unroll
-    for (int blk = 0; blk < 3; ++blk) {
-        const int sq = blk * 32 + lane;
-        const int code = sq < 81 ? p->board[sq] : 0;              // 0 = empty, else 1 + type + 14 * colour
-        const uint32_t same = __match_any_sync(0xffffffffu, code);
-        if (code >= 1 && code <= 28 && (int)(__ffs(same) - 1) == lane) {
-            const int colour = (code - 1) / 14, pt = (code - 1) % 14;
-            s_occ[warp][(colour == me ? 0 : 14) + pt][blk] = same;
-        }
-    }
-    __syncwarp();
-    const uint64_t rot = (uint64_t)me << 24;
-    const uint64_t one = (uint64_t)0x3F800000u << 32;
-    const uint64_t all_lo = (1ull << 63) - 1ull, all_hi = 0x3FFFFull;
-    for (int c = lane; c < NSB_FEATURE_CHANNELS; c += 32) {
-        uint64_t lo = 0, hi = 0, val = one;
-        if (c < 28) {   // squares 0..62 -> lo bits 0..62, squares 63..80 -> hi bits 0..17
-            const uint32_t w0 = s_occ[warp][c][0], w1 = s_occ[warp][c][1], w2 = s_occ[warp][c][2];
-            lo = (uint64_t)w0 | ((uint64_t)(w1 & 0x7FFFFFFFu) << 32);
-            hi = (uint64_t)(w1 >> 31) | ((uint64_t)(w2 & 0x1FFFFu) << 1);
-        } else if (c < 80) {
-            const int side = (c - 28) / 26, k = (c - 28) % 26;
-            int need;
-            const int piece = stand_piece_of(k, &need);
-            const int on = p->hands[side == 0 ? me : op][piece] >= need;
-            lo = on ? all_lo : 0;
-            hi = on ? all_hi : 0;
-        } else if (c < 82) {
-            const int on = (c - 80) == me;
-            lo = on ? all_lo : 0;
-            hi = on ? all_hi : 0;
-        } else {
-            lo = all_lo;
-            hi = all_hi;
-            const float maxply = (float)(p->max_ply ? p->max_ply : 1);
-            float v;
-            if (c == 82) v = (float)p->ply / maxply;
-            else if (c == 83) v = 1.0f / maxply;
-            else if (c == 84) v = me == 0 ? p->black_draw_value : p->white_draw_value;
-            else v = me == 0 ? p->white_draw_value : p->black_draw_value;
-            val = (uint64_t)__float_as_uint(v) << 32;
-        }
-        hi |= rot | val;
-        fb[(long long)b * NSB_FEATURE_CHANNELS + c] =
-            make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
-    }
+    uint4* dst = fb + (long long)b * NSB_FEATURE_CHANNELS;
+    pack_position_warp(pos + b, lane, s_occ[warp], [&](int c, uint4 f) { dst[c] = f; });
 }
 
 int launch_pack_positions(const nsb_position* d_pos, size_t n, nsb_feature_bitboard* d_fb,

@@ -11,6 +11,7 @@
 #include "decode_device.cuh"
 #include "epilogue.cuh"
 #include "nsb_internal.h"
+#include "pack_device.cuh"
 #include "umma.cuh"
 
 namespace nsb {
@@ -57,12 +58,28 @@ __device__ __forceinline__ void expand_features(const EvalArgs& a, int n_eff, in
                                                 int et, unsigned long long* tl) {
     // Per plane: the 81 occupancy bits as one contiguous little-endian bit string with the
     // rotation (extractbit.cu:20,26) already applied, plus the fill value as bf16 bits.
-    for (int i = et; i < NPOS * NSB_FEATURE_CHANNELS; i += NT) {
-        const int pos = i / NSB_FEATURE_CHANNELS, c = i - pos * NSB_FEATURE_CHANNELS;
-        const int b = eval_index(a, li0 + pos, n_eff);
-        uint4 f = make_uint4(0, 0, 0, 0);
-        if (b >= 0) f = __ldg(reinterpret_cast<const uint4*>(a.features) + (size_t)b * NSB_FEATURE_CHANNELS + c);
-        featS[i] = plane_bits(f);
+    if (a.positions != nullptr) {
+        // stage 1 fused in: warp `pos` builds the position's 86 bitboards from its 108-byte record; they
+        // go straight into featS and never exist in HBM.  The occupancy scratch is the position's own
+        // first 28 featS slots (pack_device.cuh).
+        const int pos = et >> 5, lane = et & 31;
+        if (pos < NPOS) {
+            uint4* mine = featS + pos * NSB_FEATURE_CHANNELS;
+            const int b = eval_index(a, li0 + pos, n_eff);
+            if (b >= 0) {
+                pack_position_warp(a.positions + b, lane, mine, [&](int c, uint4 f) { mine[c] = plane_bits(f); });
+            } else {
+                for (int c = lane; c < NSB_FEATURE_CHANNELS; c += 32) mine[c] = make_uint4(0, 0, 0, 0);
+            }
+        }
+    } else {
+        for (int i = et; i < NPOS * NSB_FEATURE_CHANNELS; i += NT) {
+            const int pos = i / NSB_FEATURE_CHANNELS, c = i - pos * NSB_FEATURE_CHANNELS;
+            const int b = eval_index(a, li0 + pos, n_eff);
+            uint4 f = make_uint4(0, 0, 0, 0);
+            if (b >= 0) f = __ldg(reinterpret_cast<const uint4*>(a.features) + (size_t)b * NSB_FEATURE_CHANNELS + c);
+            featS[i] = plane_bits(f);
+        }
     }
     if (tl) tl[9] = clock64();
     named_bar_sync(kEpiBar, NT);

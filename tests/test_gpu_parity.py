@@ -458,3 +458,53 @@ def test_duo_kernel_selected_for_multi_slot_contexts_and_matches(nb, orc, synth,
     first = {int(k): int(np.argmax(same == k)) for k in np.unique(same)}
     ref_rows = np.array([first[int(k)] for k in same])
     assert np.array_equal(policy.view(np.uint32), policy[ref_rows].view(np.uint32)) and np.array_equal(win, win[ref_rows])
+
+
+@pytest.mark.parametrize("channels,slots", [(128, 1), (128, 2), (256, 1)])
+def test_stage1_fused_into_trunk_prologue(nb, orc, synth, monkeypatch, channels, slots):
+    """packed positions -> stem operand inside the trunk kernel (no bitboards in HBM).  For
+    each trunk kernel (classic, duo, pair) the positions-in calls must give the bits of the bitboards-in
+    calls fed with the oracle's stage 1, for dense logits, fused decode (odd n: a padded position in the
+    last group) and the separate pack kernel (NSB_FUSE_PACK=0)."""
+    monkeypatch.delenv("NSB_TRUNK128", raising=False)
+    monkeypatch.delenv("NSB_TRUNK256", raising=False)
+    desc = nb.net_desc(channels, 2)
+    blob = nb.random_blob(desc, 77)
+    n = 301
+    pos = synth.random_positions(n, seed=31)
+    pos["max_ply"][7] = 0  # guarded division (SURVEY App. A.2)
+    fb = orc.pack(pos)
+    off, idx = synth.random_legal_moves(n, seed=3)
+
+    def run(fused):
+        if fused:
+            monkeypatch.delenv("NSB_FUSE_PACK", raising=False)
+        else:
+            monkeypatch.setenv("NSB_FUSE_PACK", "0")
+        out = {}
+        with nb.Context(desc, batch_max=n, slots=slots, blob=blob) as ctx:
+            for name, src in (("bb", fb), ("pos", pos)):
+                policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+                win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+                legal = np.zeros(int(off[-1]), dtype=np.float32)
+                w2, d2 = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+                flag = np.ones(n, dtype=np.uint8)
+                launches0 = ctx.launch_count()
+                if name == "bb":
+                    ctx.eval_async(0, src, n, policy, win, draw)
+                    ctx.await_(0)
+                    ctx.eval_decode_async(slots - 1, src, n, off, idx, nb.DECODE_LOGITS, legal, w2, d2, flag)
+                else:
+                    ctx.eval_positions_async(0, src, n, policy, win, draw)
+                    ctx.await_(0)
+                    ctx.eval_positions_decode_async(slots - 1, src, n, off, idx, nb.DECODE_LOGITS, legal, w2, d2, flag)
+                ctx.await_(slots - 1)
+                out[name] = (policy, win, draw, legal, w2, d2, flag, ctx.launch_count() - launches0)
+        return out
+
+    for fused in (True, False):
+        o = run(fused)
+        for a, b in zip(o["bb"][:7], o["pos"][:7]):
+            assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
+        # one kernel per call when fused, two (pack + trunk) otherwise
+        assert o["bb"][7] == 2 and o["pos"][7] == (2 if fused else 4)

@@ -16,10 +16,11 @@ blocks = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 desc = nb.net_desc(C, blocks)
 ctx = nb.Context(desc, batch_max=B, seed=1234)
-fb = synth.random_feature_bitboards(B * 86, seed=1)
+POSITIONS = os.environ.get("NSB_TIMELINE_POSITIONS") == "1"   # feed packed positions: stage 1 in the prologue
+fb = synth.random_positions(B, seed=1) if POSITIONS else synth.random_feature_bitboards(B * 86, seed=1)
 d_fb = nb.DeviceBuffer.from_host(fb)
 for _ in range(3):
-    t, ph = ctx.debug_trunk_timeline(0, d_fb.ptr, B)
+    t, ph = ctx.debug_trunk_timeline(0, d_fb.ptr, B, positions=POSITIONS)
     t, ph = t.astype(np.int64), ph.astype(np.int64)
 t0 = t[0, 0]
 print(f"C={C} blocks={blocks} B={B}  (cycles; CTA 0, pass 0)")
