@@ -268,9 +268,31 @@ uint64_t nsb_launch_count(nsb_ctx* ctx);
 
 /* ---- misc ------------------------------------------------------------------------------ */
 
-/* Pinned host allocation helpers (reference pins with cudaHostRegister, evaluator.cc:95-106). */
+/* Pinned host allocation helpers (reference pins with cudaHostRegister, evaluator.cc:95-106).
+ * Memory from nsb_host_alloc is page-locked AND mapped into the device's address space. */
 int nsb_host_alloc(void** out, size_t bytes);
 int nsb_host_free(void* p);
+/* Page-lock (or adopt, if the caller already did: cudaHostRegister in evaluator.cc:95-106) a buffer the
+ * caller owns, so that calls using it qualify for NSB_IO_DIRECT below. */
+int nsb_host_register(void* p, size_t bytes);
+int nsb_host_unregister(void* p);
+
+/* How the host-buffer entry points (nsb_eval_async, nsb_eval_decode_async and their nsb_eval_positions_*
+ * twins) move data.
+ *   NSB_IO_STAGED: copy nodes on the slot's stream around the kernel (H2D inputs, D2H results), the
+ *                  reference's scheme (trt.cc:240-242,265-271).  Default for contexts with >= 2 slots:
+ *                  the copies of one batch overlap the kernels of the others.
+ *   NSB_IO_DIRECT: when every buffer of the call lies in nsb_host_alloc memory, the one trunk launch
+ *                  reads its inputs from and writes its results into those buffers itself over PCIe:
+ *                  no copy nodes, one stream operation per batch.  Default for one-slot contexts,
+ *                  where every copy node is serial latency.  Calls with other buffers fall back to
+ *                  the staged path.  Results are complete after nsb_await() either way; the inputs
+ *                  must stay untouched until then (the Infer contract, evaluationworker.cc:158-180).
+ * Environment override at nsb_create: NSB_IO=direct|staged. */
+#define NSB_IO_STAGED 0
+#define NSB_IO_DIRECT 1
+int nsb_set_io_mode(nsb_ctx* ctx, int mode);
+int nsb_io_mode(nsb_ctx* ctx);
 int nsb_device_alloc(void** out, size_t bytes);
 int nsb_device_free(void* p);
 int nsb_memcpy_h2d(void* dst, const void* src, size_t bytes);

@@ -87,6 +87,10 @@ SIGNATURES = {
     "nsb_trunk_time_reset": (C.c_int, [_P]),
     "nsb_launch_count": (C.c_uint64, [_P]),
     "nsb_trunk_kernel_name": (C.c_char_p, [_P]),
+    "nsb_host_register": (C.c_int, [_P, C.c_size_t]),
+    "nsb_host_unregister": (C.c_int, [_P]),
+    "nsb_set_io_mode": (C.c_int, [_P, C.c_int]),
+    "nsb_io_mode": (C.c_int, [_P]),
     "nsb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "nsb_host_free": (C.c_int, [_P]),
     "nsb_device_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
@@ -171,6 +175,14 @@ class PinnedArray:
             self.array = None
             lib().nsb_host_free(self._p)
             self._p = None
+
+
+def host_register(arr: np.ndarray):
+    _check(lib().nsb_host_register(arr.ctypes.data, arr.nbytes), "nsb_host_register")
+
+
+def host_unregister(arr: np.ndarray):
+    _check(lib().nsb_host_unregister(arr.ctypes.data), "nsb_host_unregister")
 
 
 class DeviceBuffer:
@@ -384,6 +396,12 @@ class Context:
         fn = lib().nsb_debug_trunk_timeline_positions if positions else lib().nsb_debug_trunk_timeline
         _check(fn(self._h, slot, _ptr(d_features), n, out.ctypes.data, out.size), "nsb_debug_trunk_timeline")
         return out[:nl * 4].reshape(nl, 4), out[nl * 4:]
+
+    def set_io_mode(self, direct: bool):
+        _check(lib().nsb_set_io_mode(self._h, 1 if direct else 0), "nsb_set_io_mode")
+
+    def io_mode(self) -> str:
+        return "direct" if lib().nsb_io_mode(self._h) == 1 else "staged"
 
     def stream(self, slot=0) -> int:
         return lib().nsb_stream(self._h, slot) or 0

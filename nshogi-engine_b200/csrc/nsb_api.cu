@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -27,6 +29,22 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
+}
+
+// Page-locked allocations made through nsb_host_alloc.  With unified addressing they are mapped into
+// every device's address space at their host address, so a kernel can read its inputs from them and
+// write its results into them over PCIe without a copy node on the stream ("direct" I/O mode).
+static std::mutex g_host_mu;
+static std::map<uintptr_t, size_t> g_host_allocs;  // base -> bytes
+
+static bool host_mapped(const void* p, size_t bytes) {
+    if (p == nullptr) return false;
+    const uintptr_t a = (uintptr_t)p;
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    auto it = g_host_allocs.upper_bound(a);
+    if (it == g_host_allocs.begin()) return false;
+    --it;
+    return a + bytes <= it->first + it->second;
 }
 
 struct Slot {
@@ -52,6 +70,7 @@ struct nsb_ctx {
     int gpu = 0, batch_max = 0, num_sms = 0;
     int max_pairs = 0;  // co-resident CTA pairs of the 256-channel trunk (0: single-CTA kernel)
     bool use_ts = false;       // 128-channel trunk with the weights fed through tensor memory (trunk_ts.cu)
+    bool direct_io = false;    // kernels read / write the caller's page-locked buffers themselves (no copy nodes)
     bool fuse_pack = true;     // packed positions are expanded in the trunk prologue (NSB_FUSE_PACK=0: separate pack kernel)
     int duo_ctas = 0;          // > 0: the two-CTAs-per-SM 128-channel trunk (trunk_duo.cu), co-resident CTAs per SM
     nsb::DeviceCache cache{};  // device-resident evaluation cache (nsb_cache_create)
@@ -98,6 +117,11 @@ static int check_batch(nsb_ctx* c, size_t n, bool need_weights) {
         return NSB_ERR_STATE;
     }
     return 0;
+}
+
+static bool dense_outputs_mapped(size_t n, const float* policy, const float* win, const float* draw) {
+    return host_mapped(policy, n * kPolicySize * sizeof(float)) && host_mapped(win, n * sizeof(float)) &&
+           host_mapped(draw, n * sizeof(float));
 }
 
 extern "C" {
@@ -176,6 +200,11 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     c->use_ts = use_ts;
     c->duo_ctas = duo_ctas;
     if (const char* fp = getenv("NSB_FUSE_PACK")) c->fuse_pack = strcmp(fp, "0") != 0;
+    // A one-slot context is the latency configuration (one batch at a time: every copy node is serial
+    // time) and defaults to direct I/O; a multi-slot pipeline overlaps its copies with other batches'
+    // kernels and keeps them.  NSB_IO = direct | staged or nsb_set_io_mode() override.
+    c->direct_io = slots == 1;
+    if (const char* io = getenv("NSB_IO")) c->direct_io = strcmp(io, "direct") == 0;
     c->desc = *net;
     c->slots.resize(slots);
     const size_t B = (size_t)batch_max;
@@ -336,6 +365,16 @@ int nsb_eval_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, s
     }
     if (n == 0) return 0;
     Slot& s = c->slots[slot];
+    if (c->direct_io && host_mapped(features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard)) &&
+        dense_outputs_mapped(n, policy, win, draw)) {
+        EvalArgs a{};
+        a.features = features;
+        a.n = (int)n;
+        a.policy = policy;
+        a.win = win;
+        a.draw = draw;
+        return run_trunk(c, s, a);
+    }
     NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
                              cudaMemcpyHostToDevice, s.stream));  // trt.cc:240-242
     EvalArgs a{};
@@ -350,6 +389,42 @@ int nsb_eval_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, s
     NSB_CUDA(cudaMemcpyAsync(win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     NSB_CUDA(cudaMemcpyAsync(draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     return 0;
+}
+
+static bool decode_buffers_mapped(size_t n, size_t total, const uint32_t* move_off, const uint16_t* move_idx,
+                                  const float* legal_out, const float* win, const float* draw, const uint8_t* nan_flag) {
+    return host_mapped(move_off, (n + 1) * sizeof(uint32_t)) && host_mapped(move_idx, (total ? total : 1) * sizeof(uint16_t)) &&
+           host_mapped(legal_out, (total ? total : 1) * sizeof(float)) && host_mapped(win, n * sizeof(float)) &&
+           host_mapped(draw, n * sizeof(float)) && (nan_flag == nullptr || host_mapped(nan_flag, n));
+}
+
+// Direct I/O (c->direct_io and every buffer of the call lies in nsb_host_alloc memory): the one trunk
+// launch reads the inputs from and writes the legal-move rows into the caller's page-locked buffers.
+// Exactly one of features / positions is set.  Returns 1 if the launch was enqueued, 0 if the call
+// has to take the staged path, < 0 on error.
+static int eval_decode_direct(nsb_ctx* c, Slot& s, const nsb_feature_bitboard* features, const nsb_position* positions,
+                              size_t n, const uint32_t* move_off, const uint16_t* move_idx, int mode, float* legal_out,
+                              float* win, float* draw, uint8_t* nan_flag) {
+    if (!c->direct_io) return 0;
+    const size_t total = move_off[n];
+    if (move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) return 0;  // the staged path reports it
+    if (features ? !host_mapped(features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard))
+                 : !host_mapped(positions, n * sizeof(nsb_position)))
+        return 0;
+    if (!decode_buffers_mapped(n, total, move_off, move_idx, legal_out, win, draw, nan_flag)) return 0;
+    EvalArgs a{};
+    a.features = features;
+    a.positions = positions;
+    a.n = (int)n;
+    a.win = win;
+    a.draw = draw;
+    a.move_off = move_off;
+    a.move_idx = move_idx;
+    a.legal_out = legal_out;
+    a.nan_flag = nan_flag;
+    a.decode_mode = mode;
+    const int rc = run_trunk(c, s, a);
+    return rc ? rc : 1;
 }
 
 // Stage 1 for a batch whose packed positions are already in s.d_pos: either it is left to the trunk
@@ -415,6 +490,8 @@ int nsb_eval_decode_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* feat
     }
     if (n == 0) return 0;
     Slot& s = c->slots[slot];
+    if ((rc = eval_decode_direct(c, s, features, nullptr, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag)))
+        return rc < 0 ? rc : 0;
     NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
                              cudaMemcpyHostToDevice, s.stream));
     return eval_decode_common(c, s, nullptr, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag);
@@ -431,6 +508,16 @@ int nsb_eval_positions_async(nsb_ctx* c, int slot, const nsb_position* positions
     }
     if (n == 0) return 0;
     Slot& s = c->slots[slot];
+    if (c->direct_io && c->fuse_pack && host_mapped(positions, n * sizeof(nsb_position)) &&
+        dense_outputs_mapped(n, policy, win, draw)) {
+        EvalArgs a{};
+        a.positions = positions;
+        a.n = (int)n;
+        a.policy = policy;
+        a.win = win;
+        a.draw = draw;
+        return run_trunk(c, s, a);
+    }
     NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
     const nsb_position* fused = nullptr;
     if ((rc = stage1(c, s, n, &fused))) return rc;
@@ -461,6 +548,9 @@ int nsb_eval_positions_decode_async(nsb_ctx* c, int slot, const nsb_position* po
     }
     if (n == 0) return 0;
     Slot& s = c->slots[slot];
+    if (c->fuse_pack &&
+        (rc = eval_decode_direct(c, s, nullptr, positions, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag)))
+        return rc < 0 ? rc : 0;
     NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
     const nsb_position* fused = nullptr;
     if ((rc = stage1(c, s, n, &fused))) return rc;
@@ -909,13 +999,59 @@ uint64_t nsb_launch_count(nsb_ctx* c) { return c ? c->launches : 0; }
 
 int nsb_host_alloc(void** out, size_t bytes) {
     if (!out) return NSB_ERR_INVALID;
-    NSB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    NSB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    g_host_allocs[(uintptr_t)*out] = bytes ? bytes : 1;
     return 0;
 }
 int nsb_host_free(void* p) {
+    {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        g_host_allocs.erase((uintptr_t)p);
+    }
     NSB_CUDA(cudaFreeHost(p));
     return 0;
 }
+int nsb_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) {
+        set_error("nsb_host_register: bad arguments");
+        return NSB_ERR_INVALID;
+    }
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);  // evaluator.cc:95-106
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();  // the caller pinned it (the reference's Evaluator does): adopt it
+    } else if (e != cudaSuccess) {
+        set_error("cudaHostRegister failed: %s", cudaGetErrorString(e));
+        return NSB_ERR_CUDA;
+    }
+    // direct I/O needs the device to reach the range at its host address (true on unified-addressing
+    // x86 hosts); otherwise the range stays page-locked but calls using it take the staged path
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, p, 0) == cudaSuccess && dp == p) {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        g_host_allocs[(uintptr_t)p] = bytes;
+    } else {
+        cudaGetLastError();
+    }
+    return 0;
+}
+int nsb_host_unregister(void* p) {
+    {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        g_host_allocs.erase((uintptr_t)p);
+    }
+    NSB_CUDA(cudaHostUnregister(p));
+    return 0;
+}
+int nsb_set_io_mode(nsb_ctx* c, int mode) {
+    if (!c || (mode != NSB_IO_STAGED && mode != NSB_IO_DIRECT)) {
+        set_error("nsb_set_io_mode: bad arguments");
+        return NSB_ERR_INVALID;
+    }
+    c->direct_io = mode == NSB_IO_DIRECT;
+    return 0;
+}
+int nsb_io_mode(nsb_ctx* c) { return c && c->direct_io ? NSB_IO_DIRECT : NSB_IO_STAGED; }
 int nsb_device_alloc(void** out, size_t bytes) {
     if (!out) return NSB_ERR_INVALID;
     NSB_CUDA(cudaMalloc(out, bytes ? bytes : 1));

@@ -508,3 +508,98 @@ def test_stage1_fused_into_trunk_prologue(nb, orc, synth, monkeypatch, channels,
             assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
         # one kernel per call when fused, two (pack + trunk) otherwise
         assert o["bb"][7] == 2 and o["pos"][7] == (2 if fused else 4)
+
+
+@pytest.mark.parametrize("channels,slots", [(128, 1), (128, 2), (256, 1)])
+def test_direct_io_equals_staged(nb, orc, synth, monkeypatch, channels, slots):
+    """NSB_IO_DIRECT: the trunk launch reads and writes the caller's mapped page-locked buffers itself (no copy
+    nodes).  Same bits as the staged path for every host-buffer entry point; pageable buffers in direct mode
+    silently take the staged path; a one-slot ctx defaults to direct, a pipeline to staged."""
+    monkeypatch.delenv("NSB_IO", raising=False)
+    monkeypatch.delenv("NSB_FUSE_PACK", raising=False)
+    desc = nb.net_desc(channels, 2)
+    blob = nb.random_blob(desc, 5)
+    n = 203
+    pos = synth.random_positions(n, seed=8)
+    fb = orc.pack(pos)
+    off, idx = synth.random_legal_moves(n, seed=9)
+    total = int(off[-1])
+    P = nb.PinnedArray
+    h_fb, h_pos = P((n * 86,), nb.FEATURE_BITBOARD), P((n,), nb.POSITION)
+    h_fb.array[:] = fb
+    h_pos.array[:] = pos
+    h_off, h_idx = P((n + 1,), np.uint32), P((total,), np.uint16)
+    h_off.array[:] = off
+    h_idx.array[:] = idx
+    h_policy, h_win, h_draw = P((n, nb.POLICY_SIZE), np.float32), P((n,), np.float32), P((n,), np.float32)
+    h_legal, h_flag = P((total,), np.float32), P((n,), np.uint8)
+
+    def calls(ctx):
+        out = []
+        for src, dense, dec in ((h_fb, ctx.eval_async, ctx.eval_decode_async),
+                                (h_pos, ctx.eval_positions_async, ctx.eval_positions_decode_async)):
+            for a in (h_policy, h_win, h_draw, h_legal):
+                a.array[...] = -7.0
+            h_flag.array[:] = 9
+            l0 = ctx.launch_count()
+            dense(0, src.array, n, h_policy.array, h_win.array, h_draw.array)
+            ctx.await_(0)
+            out += [h_policy.array.copy(), h_win.array.copy(), h_draw.array.copy()]
+            h_win.array[:] = -7.0
+            dec(slots - 1, src.array, n, h_off.array, h_idx.array, nb.DECODE_PROBS, h_legal.array, h_win.array, h_draw.array,
+                h_flag.array)
+            ctx.await_(slots - 1)
+            out += [h_legal.array.copy(), h_win.array.copy(), h_draw.array.copy(), h_flag.array.copy()]
+            assert ctx.launch_count() - l0 == 2
+        return out
+
+    with nb.Context(desc, batch_max=n, slots=slots, blob=blob) as ctx:
+        assert ctx.io_mode() == ("direct" if slots == 1 else "staged")
+        ctx.set_io_mode(False)
+        staged = calls(ctx)
+        ctx.set_io_mode(True)
+        assert ctx.io_mode() == "direct"
+        direct = calls(ctx)
+        # pageable numpy arrays in direct mode: staged fallback, same results
+        policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+        win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        ctx.eval_async(0, fb, n, policy, win, draw)
+        ctx.await_(0)
+    assert np.all(staged[0] != -7.0) and np.all(staged[3] != -7.0)
+    for a, b in zip(staged, direct):
+        assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
+    assert np.array_equal(policy.view(np.uint32), staged[0].view(np.uint32)) and np.array_equal(win, staged[1])
+    for a in (h_fb, h_pos, h_off, h_idx, h_policy, h_win, h_draw, h_legal, h_flag):
+        a.free()
+
+
+def test_direct_io_on_caller_registered_buffers(nb, orc, synth, monkeypatch):
+    """The Infer contract with buffers the caller owns and pins (reference src/evaluate/evaluator.cc:95-106):
+    nsb_host_register makes them eligible for direct I/O - one stream operation per computeNonBlocking."""
+    monkeypatch.delenv("NSB_IO", raising=False)
+    desc = nb.net_desc(128, 1)
+    blob = nb.random_blob(desc, 3)
+    n = 64
+    fb = orc.pack(synth.random_positions(n, seed=2))
+    feat = np.zeros(n * 86 + 256, dtype=nb.FEATURE_BITBOARD)[:n * 86]
+    feat[:] = fb
+    policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+    win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+        assert ctx.io_mode() == "direct"
+        ctx.eval_async(0, feat, n, policy, win, draw)   # pageable: staged fallback
+        ctx.await_(0)
+        want = (policy.copy(), win.copy(), draw.copy())
+        bufs = (feat, policy, win, draw)
+        for a in bufs:
+            nb.host_register(a)
+        try:
+            for a in bufs[1:]:
+                a[...] = 0
+            ctx.eval_async(0, feat, n, policy, win, draw)
+            ctx.await_(0)
+        finally:
+            for a in bufs:
+                nb.host_unregister(a)
+    for a, b in zip(want, (policy, win, draw)):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

@@ -2,6 +2,8 @@
 """A/B of the two host-buffer entry points, alternating so that clock / power drift hits both alike:
    bb  : nsb_eval_decode_async            (1,376 B per position over PCIe, bitboards in)
    pos : nsb_eval_positions_decode_async  (108 B per position, stage 1 in the trunk prologue)
+Each is run with staged I/O (copy nodes around the kernel) and direct I/O (the kernel reads / writes the mapped
+page-locked buffers itself).
 usage: e2e_ab.py [channels blocks batch slots steps rounds]"""
 import os
 import sys
@@ -58,13 +60,18 @@ def loop(steps, positions):
 
 
 print(f"{ctx.trunk_kernel_name()}  B={B} slots={slots} fuse_pack={os.environ.get('NSB_FUSE_PACK', '1')}")
-loop(200, False)
-loop(200, True)
+for direct in (False, True):
+    ctx.set_io_mode(direct)
+    loop(100, False)
+    loop(100, True)
 for r in range(rounds):
-    for positions in (False, True):
-        nb.device_sync()
-        t0 = time.perf_counter()
-        loop(K, positions)
-        nb.device_sync()
-        dt = time.perf_counter() - t0
-        print(f"round {r} {'pos' if positions else 'bb '}: {B * K / dt / 1e6:.3f} M evals/s  ({dt / K * 1e6:.1f} us/step)")
+    for direct in (False, True):
+        ctx.set_io_mode(direct)
+        for positions in (False, True):
+            nb.device_sync()
+            t0 = time.perf_counter()
+            loop(K, positions)
+            nb.device_sync()
+            dt = time.perf_counter() - t0
+            print(f"round {r} {ctx.io_mode():6s} {'pos' if positions else 'bb '}: {B * K / dt / 1e6:.3f} M evals/s  "
+                  f"({dt / K * 1e6:.1f} us/step)")
