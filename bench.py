@@ -300,6 +300,33 @@ def run_b200(args):
     rep.barrier()
     _, dt_max = rep.aggregate({}, dt, device=dev_device)
     e2e_positions = rep.whole_job_rate(B * K * world, dt_max)
+
+    # one batch at a time (the reference executor's usage: computeNonBlocking -> await per evaluator thread,
+    # src/mcts/evaluationworker.cc:158-180): a one-slot context = classic kernel + direct I/O (the kernel
+    # reads / writes the page-locked host buffers itself), against the same context with staged copies
+    latency = None
+    if not args.no_latency_leg:
+        ctx1 = nb.Context(desc, batch_max=B, slots=1, gpu=gpu, blob=blob)
+        KL = min(K, 500)
+
+        def one_at_a_time(steps):
+            nonlocal sink
+            t0 = time.perf_counter()
+            for i in range(steps):
+                ctx1.eval_decode_async(0, h_fb[i % h_pool_n].array, B, h_off.array, h_idx.array, nb.DECODE_PROBS,
+                                       h_legal[0].array, h_win[0].array, h_draw[0].array, h_flag[0].array)
+                ctx1.await_(0)
+                sink += float(h_win[0].array[0])
+            return (time.perf_counter() - t0) * 1e6 / steps
+
+        latency = {"kernel": ctx1.trunk_kernel_name(), "batch": B, "steps": KL,
+                   "api": "nsb_eval_decode_async + nsb_await, one batch in flight, host buffers"}
+        for mode in ("staged", "direct"):
+            ctx1.set_io_mode(mode == "direct")
+            one_at_a_time(50)
+            latency[f"{mode}_us_per_batch"] = round(one_at_a_time(KL), 2)
+        latency["default_io"] = "direct"
+        ctx1.close()
     clocks = sampler.stop()
     selfplay = None if args.no_selfplay else selfplay_leg(args, info, rep, dev_device)
 
@@ -353,6 +380,7 @@ def run_b200(args):
                           "api": "nsb_eval_positions_decode_async + nsb_await (packed positions in, stage 1 in the trunk prologue)",
                           "h2d_bytes_per_step": B * 108 + (B + 1) * 4 + n_moves * 2,
                           "d2h_bytes_per_step": n_moves * 4 + B * 4 * 2 + B, "launches_per_step": pos_launches / K},
+        "latency_one_batch_in_flight": latency,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "counters": counters,
     }
@@ -490,6 +518,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--no-latency-leg", action="store_true")
     ap.add_argument("--selfplay-seconds", type=float, default=6.0)
     ap.add_argument("--small-pool", action="store_true", help="8-batch input pool (profiling runs only)")
     args = ap.parse_args()
