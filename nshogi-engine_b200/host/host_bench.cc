@@ -175,7 +175,7 @@ int main(int argc, char** argv) {
     std::printf("{\"batch\": %d, \"net\": \"%dx%d\", \"infer_blocking_evals_per_s\": %.1f, \"pipeline_evals_per_s\": %.1f, "
                 "\"legal_moves\": %zu, \"max_prob_diff\": %.3g, \"row_sum_err\": %.3g, \"rows_identical\": %s, "
                 "\"cache_rows_stored\": %zu, \"cache_hit\": %s, \"ok\": %s}\n",
-                B, Blocks, Channels, BlockingRate, PipeRate, Moves.size(), MaxDiff, SumErr, RowsEqual ? "true" : "false",
+                B, Exec.net().blocks, Exec.net().channels, BlockingRate, PipeRate, Moves.size(), MaxDiff, SumErr, RowsEqual ? "true" : "false",
                 Stored, CacheHit ? "true" : "false", Ok ? "true" : "false");
     nsb_host_free(Features); nsb_host_free(Policy); nsb_host_free(Win); nsb_host_free(Draw);
     return (SelfCheck && !Ok) ? 1 : 0;

@@ -3,14 +3,21 @@
 // `--cache-trace NUM_BUNDLES_MIB` replays "s hash n win draw" / "l hash n" lines from stdin through
 // EvalCacheB200 and prints one result line per operation (tests/test_evalcache.py compares them
 // with the oracle and with the reference's own evalcache.cc).
+// `--onnx-blob IN.onnx OUT.bin` runs the model-file reader of infer::B200::load (onnx_import.h) and writes
+// i32 in_channels, channels, blocks, hidden + the canonical fp32 blob (tests/test_onnx_io.py compares it with
+// the Python reader bit for bit); a graph it rejects prints the reason and exits 3.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <set>
 #include <vector>
 
+#include <fstream>
+#include <iterator>
+
 #include "eval_cache.h"
 #include "move_index.h"
+#include "onnx_import.h"
 
 using namespace nshogi::engine;
 
@@ -39,7 +46,29 @@ static int cacheTrace(std::size_t MiB) {
     return 0;
 }
 
+static int onnxBlob(const char* InPath, const char* OutPath) {
+    std::ifstream In(InPath, std::ios::binary);
+    if (!In) return 2;
+    std::vector<uint8_t> Bytes((std::istreambuf_iterator<char>(In)), std::istreambuf_iterator<char>());
+    std::vector<float> Blob;
+    infer::onnx::NetShape S;
+    try {
+        infer::onnx::Graph G = infer::onnx::parseModel(Bytes);
+        S = infer::onnx::toBlob(G, &Blob);
+    } catch (const infer::onnx::Error& E) {
+        std::printf("rejected: %s\n", E.what());
+        return 3;
+    }
+    const int32_t Head[4] = {S.InChannels, S.Channels, S.Blocks, S.Hidden};
+    std::ofstream Out(OutPath, std::ios::binary);
+    Out.write(reinterpret_cast<const char*>(Head), sizeof Head);
+    Out.write(reinterpret_cast<const char*>(Blob.data()), (std::streamsize)(Blob.size() * sizeof(float)));
+    std::printf("ok %d %d %d %d %zu\n", S.InChannels, S.Channels, S.Blocks, S.Hidden, Blob.size());
+    return Out ? 0 : 2;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 4 && std::strcmp(argv[1], "--onnx-blob") == 0) return onnxBlob(argv[2], argv[3]);
     if (argc >= 3 && std::strcmp(argv[1], "--cache-trace") == 0) return cacheTrace((std::size_t)std::atoi(argv[2]));
     {   // cache: store/load, 164-move cap, refresh-only on duplicate, the reference's replacement order
         mcts::EvalCacheB200 C(1);

@@ -12,13 +12,16 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
+#include <iterator>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "infer/infer.h"  // the reference's header when built in-tree, host/shim otherwise
 #include "nsb.h"
+#include "onnx_import.h"
 
 namespace nshogi {
 namespace engine {
@@ -42,9 +45,12 @@ class B200 : public Infer {
     B200(const B200&) = delete;
     B200& operator=(const B200&) = delete;
 
-    // Weight blob file: "NSBW" u32 version=1, i32 channels, blocks, hidden, in_channels, then the
-    // canonical fp32 blob.  An empty path loads the seeded random-init net, which
-    // is what the benchmarks use (the reference ships no model, src/context.h:93).
+    // Loads the net.  `Path` is either the reference's ONNX model file (what TensorRT::load takes,
+    // trt.cc:109-232; read by onnx_import.h, no engine build step) or an NSBW blob file ("NSBW", u32
+    // version=1, i32 channels, blocks, hidden, in_channels, then the canonical fp32 blob of DESIGN.md §5;
+    // written by weights_io.py).  The file decides the net's shape, as it does for the reference: if it
+    // differs from the constructor's, the context is rebuilt for it.  An empty path loads the seeded
+    // random-init net, which is what the benchmarks use (the reference ships no model, src/context.h:93).
     void load(const std::string& Path, uint64_t Seed = 1234) {
         std::vector<float> Blob;
         if (Path.empty()) {
@@ -53,18 +59,35 @@ class B200 : public Infer {
         } else {
             std::ifstream In(Path, std::ios::binary);
             if (!In) throw std::runtime_error("B200::load: cannot open " + Path);  // trt.cc:35
-            char Magic[4];
-            uint32_t Version = 0;
-            int32_t H[4] = {0, 0, 0, 0};
-            In.read(Magic, 4).read(reinterpret_cast<char*>(&Version), 4).read(reinterpret_cast<char*>(H), 16);
-            if (!In || std::string(Magic, 4) != "NSBW" || Version != 1)
-                throw std::runtime_error("B200::load: not an NSBW v1 weight file: " + Path);
-            if (H[0] != Desc_.channels || H[1] != Desc_.blocks || H[2] != Desc_.value_hidden ||
-                H[3] != Desc_.in_channels)
-                throw std::runtime_error("B200::load: weight file shape differs from the executor's net");
-            Blob.resize(nsb_weight_blob_floats(&Desc_));
-            In.read(reinterpret_cast<char*>(Blob.data()), (std::streamsize)(Blob.size() * sizeof(float)));
-            if (!In) throw std::runtime_error("B200::load: truncated weight file: " + Path);
+            std::vector<uint8_t> Bytes((std::istreambuf_iterator<char>(In)), std::istreambuf_iterator<char>());
+            nsb_net_desc FileDesc{};
+            if (Bytes.size() >= 24 && std::memcmp(Bytes.data(), "NSBW", 4) == 0) {
+                uint32_t Version = 0;
+                int32_t H[4] = {0, 0, 0, 0};
+                std::memcpy(&Version, Bytes.data() + 4, 4);
+                std::memcpy(H, Bytes.data() + 8, 16);
+                if (Version != 1) throw std::runtime_error("B200::load: not an NSBW v1 weight file: " + Path);
+                FileDesc = nsb_net_desc{H[3], H[0], H[1], H[2]};
+                const std::size_t Floats = nsb_weight_blob_floats(&FileDesc);
+                if (Floats == 0 || Bytes.size() != 24 + Floats * sizeof(float))
+                    throw std::runtime_error("B200::load: truncated or oversized weight file: " + Path);
+                Blob.resize(Floats);
+                std::memcpy(Blob.data(), Bytes.data() + 24, Floats * sizeof(float));
+            } else {
+                onnx::Graph G = onnx::parseModel(Bytes);  // throws onnx::Error (a std::runtime_error)
+                const onnx::NetShape S = onnx::toBlob(G, &Blob);
+                FileDesc = nsb_net_desc{S.InChannels, S.Channels, S.Blocks, S.Hidden};
+                if (Blob.size() != nsb_weight_blob_floats(&FileDesc))
+                    throw std::runtime_error("B200::load: " + Path + ": the executor does not support this net shape");
+            }
+            if (FileDesc.channels != Desc_.channels || FileDesc.blocks != Desc_.blocks ||
+                FileDesc.value_hidden != Desc_.value_hidden || FileDesc.in_channels != Desc_.in_channels) {
+                if (HasCache_) throw std::runtime_error("B200::load: net shape changes after enableCache()");
+                nsb_destroy(Ctx_);
+                Ctx_ = nullptr;
+                Desc_ = FileDesc;
+                check(nsb_create(&Ctx_, GPUId_, BatchSizeM, Slots_, &Desc_), "nsb_create");
+            }
         }
         check(nsb_load_weights(Ctx_, Blob.data(), Blob.size()), "nsb_load_weights");
     }

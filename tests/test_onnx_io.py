@@ -136,3 +136,43 @@ def test_unsupported_graphs_fail_loudly(oi):
     g.initializers[stem.inputs[1]] = np.zeros((8, 86, 5, 5), dtype=np.float32)
     with pytest.raises(ValueError, match="3x3"):
         oi.blob_from_graph(g)
+
+
+def _cpp_blob(path, tmp_path):
+    import subprocess
+    unit = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nshogi-engine_b200", "host", "nsb_host_unit")
+    out = str(tmp_path / "blob.bin")
+    r = subprocess.run([unit, "--onnx-blob", path, out], capture_output=True, text=True, timeout=60)
+    if r.returncode != 0:
+        return r.returncode, r.stdout, None, None
+    raw = open(out, "rb").read()
+    head = np.frombuffer(raw[:16], dtype="<i4")
+    return 0, r.stdout, {"in_channels": int(head[0]), "channels": int(head[1]), "blocks": int(head[2]),
+                         "value_hidden": int(head[3])}, np.frombuffer(raw[16:], dtype="<f4")
+
+
+def test_cpp_reader_of_infer_b200_load_matches_python(pkg, oi, nb, golden_dir, tmp_path):
+    """host/onnx_import.h (what infer::B200::load runs on a .onnx path) == onnx_io.py, bit for bit: on the
+    torch-exported file, on a graph with BatchNormalization / MatMul / Split, on a written 128-channel net; and it
+    rejects what the Python reader rejects."""
+    cases = [os.path.join(golden_dir, "resnet_torch_export.onnx")]
+    model, _ = _bn_graph(oi, np.random.default_rng(5))
+    p = str(tmp_path / "bn.onnx")
+    open(p, "wb").write(model)
+    cases.append(p)
+    p = str(tmp_path / "w128.onnx")
+    oi.write_onnx(p, nb.random_blob(nb.net_desc(128, 1), 9), 128, 1)
+    cases.append(p)
+    for path in cases:
+        meta, blob = oi.read_onnx(path)
+        rc, out, cmeta, cblob = _cpp_blob(path, tmp_path)
+        assert rc == 0, out
+        assert cmeta == meta
+        assert np.array_equal(cblob.view(np.uint32), blob.view(np.uint32))
+    bad, _ = _bn_graph(oi, np.random.default_rng(6), extra=oi._node("Relu", ["x1"], ["dangling"]))
+    p = str(tmp_path / "bad.onnx")
+    open(p, "wb").write(bad)
+    rc, out, _, _ = _cpp_blob(p, tmp_path)
+    assert rc == 3 and "trunk output must feed" in out
+    open(p, "wb").write(b"\x0a\x03abc")
+    assert _cpp_blob(p, tmp_path)[0] == 3

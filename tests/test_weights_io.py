@@ -149,3 +149,12 @@ def test_imported_net_matches_torch_on_gpu(pkg, nb, orc, synth, C, tmp_path):
                          timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert json.loads(out.stdout.strip().splitlines()[-1])["ok"]
+    # ... and as the reference's own model format: an ONNX file handed to load(), as TensorRT::load takes it
+    # (trt.cc:109-232).  The executor is constructed for the default 10 x 128 net; the file decides the shape.
+    onnx_path = str(tmp_path / "net.onnx")
+    pkg.onnx_io.write_onnx(onnx_path, blob, C, blocks)
+    out = subprocess.run([os.path.join(HOST, "nsb_host_bench"), "--selfcheck", "--repeat", "20", "--batch", "64",
+                          "--weights", onnx_path], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["ok"] and line["net"] == f"{blocks}x{C}"
