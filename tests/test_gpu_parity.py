@@ -560,6 +560,16 @@ def test_direct_io_equals_staged(nb, orc, synth, monkeypatch, channels, slots):
         ctx.set_io_mode(True)
         assert ctx.io_mode() == "direct"
         direct = calls(ctx)
+        # the caller refills the SAME buffers between batches (evaluationworker.cc:124-154): a launch must see the
+        # new contents, not lines cached from the previous launch's reads of host memory
+        h_fb.array[:] = fb.reshape(n, 86)[::-1].reshape(-1)
+        h_pos.array[:] = pos[::-1]
+        rev = calls(ctx)
+        ctx.set_io_mode(False)
+        rev_staged = calls(ctx)
+        ctx.set_io_mode(True)
+        h_fb.array[:] = fb
+        h_pos.array[:] = pos
         # pageable numpy arrays in direct mode: staged fallback, same results
         policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
         win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
@@ -569,6 +579,9 @@ def test_direct_io_equals_staged(nb, orc, synth, monkeypatch, channels, slots):
     for a, b in zip(staged, direct):
         assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
     assert np.array_equal(policy.view(np.uint32), staged[0].view(np.uint32)) and np.array_equal(win, staged[1])
+    for a, b in zip(rev_staged, rev):
+        assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
+    assert np.array_equal(rev[0].view(np.uint32), staged[0][::-1].view(np.uint32)) and not np.array_equal(rev[1], staged[1])
     for a in (h_fb, h_pos, h_off, h_idx, h_policy, h_win, h_draw, h_legal, h_flag):
         a.free()
 
