@@ -801,6 +801,12 @@ int nsb_eval_cached_decode_async(nsb_ctx* c, int slot, const nsb_feature_bitboar
         return NSB_ERR_INVALID;
     }
     Slot& s = c->slots[slot];
+    if (c->direct_io && host_mapped(features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard)) &&
+        host_mapped(hashes, n * sizeof(uint64_t)) &&
+        decode_buffers_mapped(n, total, move_off, move_idx, legal_out, win, draw, nan_flag) &&
+        (hit_flag == nullptr || host_mapped(hit_flag, n)))  // probe + trunk work on the caller's buffers: no copy nodes
+        return eval_cached_enqueue(c, s, features, nullptr, n, hashes, move_off, move_idx, mode, legal_out, win, draw,
+                                   nan_flag ? nan_flag : s.d_flag, hit_flag ? hit_flag : s.d_hit);
     NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
                              cudaMemcpyHostToDevice, s.stream));
     NSB_CUDA(cudaMemcpyAsync(s.d_hash, hashes, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
@@ -839,6 +845,12 @@ int nsb_eval_positions_cached_decode_async(nsb_ctx* c, int slot, const nsb_posit
         return NSB_ERR_INVALID;
     }
     Slot& s = c->slots[slot];
+    if (c->direct_io && c->fuse_pack && host_mapped(positions, n * sizeof(nsb_position)) &&
+        host_mapped(hashes, n * sizeof(uint64_t)) &&
+        decode_buffers_mapped(n, total, move_off, move_idx, legal_out, win, draw, nan_flag) &&
+        (hit_flag == nullptr || host_mapped(hit_flag, n)))
+        return eval_cached_enqueue(c, s, nullptr, positions, n, hashes, move_off, move_idx, mode, legal_out, win, draw,
+                                   nan_flag ? nan_flag : s.d_flag, hit_flag ? hit_flag : s.d_hit);
     NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
     NSB_CUDA(cudaMemcpyAsync(s.d_hash, hashes, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
     NSB_CUDA(cudaMemcpyAsync(s.d_off, move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));

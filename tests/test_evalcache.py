@@ -207,11 +207,13 @@ def test_device_cache_same_bundle_in_one_batch(nb):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("channels", [128, 256])
-def test_eval_cached_serves_hits_and_evaluates_misses(nb, orc, synth, channels):
+@pytest.mark.parametrize("channels,direct", [(128, False), (256, False), (128, True), (256, True)])
+def test_eval_cached_serves_hits_and_evaluates_misses(nb, orc, synth, channels, direct):
     """nsb_eval_cached_decode_async: first call evaluates everything and fills the cache, the second call
     is served from it bit for bit, a mixed batch evaluates only the new positions (trunk launch on the
-    probe's miss list), and a changed move count is a miss (searchworker.cc:546)."""
+    probe's miss list), and a changed move count is a miss (searchworker.cc:546).  `direct`: every buffer
+    of the cached calls is mapped page-locked memory and the packed positions go in, so the probe and the
+    trunk work on the caller's buffers themselves (NSB_IO_DIRECT, stage 1 in the prologue, misses only)."""
     desc = nb.net_desc(channels, 2)
     blob = nb.random_blob(desc, 5)
     n = 37
@@ -234,6 +236,21 @@ def test_eval_cached_serves_hits_and_evaluates_misses(nb, orc, synth, channels):
         win, draw = np.zeros(m, dtype=np.float32), np.zeros(m, dtype=np.float32)
         flag, hit = np.zeros(m, dtype=np.uint8), np.zeros(m, dtype=np.uint8)
         f = np.ascontiguousarray(fb[sel].reshape(-1))
+        if cached and direct:
+            host = [np.ascontiguousarray(pos[sel]), np.ascontiguousarray(hashes[sel]), off, idx, legal, win, draw, flag, hit]
+            pins = []
+            for h in host:
+                p = nb.PinnedArray(h.shape, h.dtype)
+                p.array[...] = h
+                pins.append(p)
+            arrs = [p.array for p in pins]
+            ctx.eval_positions_cached_decode_async(0, arrs[0], m, arrs[1], arrs[2], arrs[3], nb.DECODE_PROBS, *arrs[4:])
+            ctx.await_(0)
+            for h, p in zip(host[4:], pins[4:]):
+                h[...] = p.array
+            for p in pins:
+                p.free()
+            return legal, win, draw, hit, off
         if cached:
             ctx.eval_cached_decode_async(0, f, m, np.ascontiguousarray(hashes[sel]), off, idx, nb.DECODE_PROBS, legal, win,
                                          draw, flag, hit)
@@ -244,6 +261,7 @@ def test_eval_cached_serves_hits_and_evaluates_misses(nb, orc, synth, channels):
 
     with nb.Context(desc, batch_max=2 * n, blob=blob) as ctx:
         ctx.cache_create(4)
+        assert ctx.io_mode() == "direct"                                   # one-slot ctx
         first = list(range(n))
         base = run(ctx, first, cached=False)
         l0 = ctx.launch_count()
