@@ -69,6 +69,22 @@ umma_probe_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b
             const int reps = it == 0 ? 1 : 16;
             for (int rep = 0; rep < reps; ++rep) {
                 if (elect_one()) {
+                    if (layout == 0) {
+                        // the trunk kernels' issue loop: descriptor low words advance by one integer add per
+                        // K step (building both descriptors from scratch costs more than a small-N MMA takes)
+                        const uint32_t a_lo = smem_desc_lo(a0, a_rows * 16);
+                        const uint32_t b_lo = smem_desc_lo(b0 + (uint32_t)(shift * 16), b_rows * 16);
+                        for (int k4 = 0; k4 < K / 64; ++k4) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const int k16 = k4 * 4 + kk;
+                                umma_bf16(tmem_base, smem_desc_from(a_lo + (uint32_t)(k16 * 2 * a_rows), 128),
+                                          smem_desc_from(b_lo + (uint32_t)(k16 * 2 * b_rows), 128), idesc,
+                                          (it == 0 && rep == 0 && k16 == 0) ? 0u : 1u);
+                            }
+                            if (iters & 1) umma_commit(bar + 16);
+                        }
+                    } else
                     for (int k16 = 0; k16 < K / 16; ++k16) {
                         uint64_t ad, bd;
                         if (layout == 0) {
