@@ -144,6 +144,37 @@ int nsb_eval_positions_decode_async(nsb_ctx* ctx, int slot, const nsb_position* 
                                     const uint32_t* move_off, const uint16_t* move_idx, int mode,
                                     float* legal_out, float* win, float* draw, uint8_t* nan_flag);
 
+/* The general form of the fused path; every nsb_eval_*decode_async call is this request with some
+ * fields left NULL.
+ *   features / positions : exactly one is set (bitboards in, or packed positions with stage 1 in the
+ *                          trunk kernel's prologue)
+ *   hashes               : non-NULL -> through the device-resident cache (nsb_cache_create): hits are
+ *                          served from HBM, misses evaluated and stored; hit_flag[i] = 1 for a hit
+ *   order_out (optional) : per position the RANK ORDER of its decoded row: order_out[move_off[i] + r] =
+ *                          index within the row (0 .. n_i-1) of the move with the r-th largest value,
+ *                          ties by lower index first; identity for a row flagged NaN.  This is the
+ *                          permutation the reference applies with Node::sort() - std::sort of the edges by
+ *                          decreasing probability, src/mcts/node.h:163-168, on a feed thread for every leaf
+ *                          (feedworker.cc:129) - so the caller writes its edges in search order in one
+ *                          pass instead of sorting them (std::sort leaves the order of ties unspecified;
+ *                          here it is defined).  Rows served from the cache are ranked too. */
+typedef struct nsb_decode_request {
+    const nsb_feature_bitboard* features; /* [n][86] or NULL                      */
+    const nsb_position* positions;        /* [n]     or NULL                      */
+    size_t n;
+    const uint64_t* hashes;               /* [n] or NULL (no cache)               */
+    const uint32_t* move_off;             /* [n+1] CSR offsets                    */
+    const uint16_t* move_idx;             /* [move_off[n]] policy slots           */
+    int mode;                             /* NSB_DECODE_PROBS / NSB_DECODE_LOGITS */
+    float* legal_out;                     /* [move_off[n]]                        */
+    uint16_t* order_out;                  /* [move_off[n]] or NULL                */
+    float* win;                           /* [n]                                  */
+    float* draw;                          /* [n]                                  */
+    uint8_t* nan_flag;                    /* [n] or NULL                          */
+    uint8_t* hit_flag;                    /* [n] or NULL (cached requests only)   */
+} nsb_decode_request;
+int nsb_eval_request_async(nsb_ctx* ctx, int slot, const nsb_decode_request* request);
+
 /* Replaces Infer::await (trt.cc:281-283). */
 int nsb_await(nsb_ctx* ctx, int slot);
 /* Replaces Infer::isComputing (trt.cc:285-287): 1 busy, 0 idle, <0 error. */

@@ -89,6 +89,7 @@ SIGNATURES = {
     "nsb_trunk_kernel_name": (C.c_char_p, [_P]),
     "nsb_host_register": (C.c_int, [_P, C.c_size_t]),
     "nsb_host_unregister": (C.c_int, [_P]),
+    "nsb_eval_request_async": (C.c_int, [_P, C.c_int, _P]),
     "nsb_set_io_mode": (C.c_int, [_P, C.c_int]),
     "nsb_io_mode": (C.c_int, [_P]),
     "nsb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
@@ -175,6 +176,13 @@ class PinnedArray:
             self.array = None
             lib().nsb_host_free(self._p)
             self._p = None
+
+
+class DecodeRequest(C.Structure):
+    """include/nsb.h nsb_decode_request"""
+    _fields_ = [("features", _P), ("positions", _P), ("n", C.c_size_t), ("hashes", _P), ("move_off", _P), ("move_idx", _P),
+                ("mode", C.c_int), ("legal_out", _P), ("order_out", _P), ("win", _P), ("draw", _P), ("nan_flag", _P),
+                ("hit_flag", _P)]
 
 
 def host_register(arr: np.ndarray):
@@ -396,6 +404,13 @@ class Context:
         fn = lib().nsb_debug_trunk_timeline_positions if positions else lib().nsb_debug_trunk_timeline
         _check(fn(self._h, slot, _ptr(d_features), n, out.ctypes.data, out.size), "nsb_debug_trunk_timeline")
         return out[:nl * 4].reshape(nl, 4), out[nl * 4:]
+
+    def eval_request_async(self, slot, n, move_off, move_idx, mode, legal_out, win, draw, features=None, positions=None,
+                           hashes=None, order_out=None, nan_flag=None, hit_flag=None):
+        """nsb_eval_request_async: the general fused call (cache when `hashes`, rank order when `order_out`)."""
+        r = DecodeRequest(_ptr(features), _ptr(positions), n, _ptr(hashes), _ptr(move_off), _ptr(move_idx), mode,
+                          _ptr(legal_out), _ptr(order_out), _ptr(win), _ptr(draw), _ptr(nan_flag), _ptr(hit_flag))
+        _check(lib().nsb_eval_request_async(self._h, slot, C.byref(r)), "nsb_eval_request_async")
 
     def set_io_mode(self, direct: bool):
         _check(lib().nsb_set_io_mode(self._h, 1 if direct else 0), "nsb_set_io_mode")

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "cache_device.cuh"
+#include "decode_device.cuh"
 #include "nsb_internal.h"
 
 namespace nsb {
@@ -18,13 +19,17 @@ __global__ void __launch_bounds__(kCacheWarps * 32)
 cache_probe_kernel(const DeviceCache c, const uint64_t* __restrict__ hashes, int n, const uint32_t* __restrict__ off,
                    float* __restrict__ legal, float* __restrict__ win, float* __restrict__ draw,
                    uint8_t* __restrict__ hit, uint8_t* __restrict__ nan_flag, int* __restrict__ miss_idx,
-                   int* __restrict__ miss_count) {
+                   int* __restrict__ miss_count, uint16_t* __restrict__ order) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kCacheWarps + warp;
     if (b >= n) return;
     const uint32_t mb = off[b], me = off[b + 1];
     float w = 0.f, d = 0.f;
-    const bool found = cache_load_warp(c, hashes[b], (int)(me - mb), legal + mb, &w, &d, lane);
+    float v[kDecodePerLane];
+#pragma unroll
+    for (int k = 0; k < kDecodePerLane; ++k) v[k] = 0.f;
+    const bool found = cache_load_warp(c, hashes[b], (int)(me - mb), legal + mb, &w, &d, lane, order ? v : nullptr);
+    if (found && order != nullptr) warp_rank_row(v, (int)(me - mb), lane, order + mb);  // a hit is ranked like an evaluated row
     if (lane == 0) {
         hit[b] = found ? 1 : 0;
         if (found) {
@@ -61,11 +66,11 @@ __global__ void cache_clear_kernel(const DeviceCache c) {
 
 int launch_cache_probe(const DeviceCache& c, const uint64_t* d_hashes, size_t n, const uint32_t* d_off, float* d_legal,
                        float* d_win, float* d_draw, uint8_t* d_hit, uint8_t* d_nan_flag, int* d_miss_idx, int* d_miss_count,
-                       cudaStream_t s) {
+                       cudaStream_t s, uint16_t* d_order) {
     if (n == 0) return 0;
     const unsigned grid = (unsigned)((n + kCacheWarps - 1) / kCacheWarps);
     cache_probe_kernel<<<grid, kCacheWarps * 32, 0, s>>>(c, d_hashes, (int)n, d_off, d_legal, d_win, d_draw, d_hit,
-                                                         d_nan_flag, d_miss_idx, d_miss_count);
+                                                         d_nan_flag, d_miss_idx, d_miss_count, d_order);
     return 1;
 }
 

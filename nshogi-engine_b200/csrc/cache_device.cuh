@@ -116,8 +116,11 @@ __device__ __forceinline__ bool cache_store_warp(const DeviceCache& c, uint64_t 
 // fills row[0..expected_n), *win, *draw when an entry with this hash exists AND has expected_n moves.
 // A hash match with a different move count still refreshes the entry's recency, as in the reference.
 constexpr int kCacheProbeTries = 64;
+constexpr int kCacheRowPerLane = (NSB_CACHE_MAX_MOVES + 31) / 32;  // 6 row elements per lane at most
+
+// `vals` (optional): lane l also keeps row element l + 32 k in vals[k] (for ranking the row without re-reading it)
 __device__ __forceinline__ bool cache_load_warp(const DeviceCache& c, uint64_t hash, int expected_n, float* row, float* win,
-                                                float* draw, int lane) {
+                                                float* draw, int lane, float* vals = nullptr) {
     const unsigned long long bundle = hash % c.num_bundles;
     uint32_t* word = c.meta + bundle;
     uint32_t meta;
@@ -142,7 +145,16 @@ __device__ __forceinline__ bool cache_load_warp(const DeviceCache& c, uint64_t h
     const bool ok = (int)n_e == expected_n;
     if (ok) {
         const CacheEntry* e = base + slot;
-        for (int j = lane; j < expected_n; j += 32) row[j] = __ldcg(&e->policy[j]);
+        if (vals != nullptr) {
+#pragma unroll
+            for (int k = 0; k < kCacheRowPerLane; ++k) {
+                const int j = lane + 32 * k;
+                vals[k] = 0.f;
+                if (j < expected_n) row[j] = vals[k] = __ldcg(&e->policy[j]);
+            }
+        } else {
+            for (int j = lane; j < expected_n; j += 32) row[j] = __ldcg(&e->policy[j]);
+        }
         *win = __ldcg(&e->win);
         *draw = __ldcg(&e->draw);
     }

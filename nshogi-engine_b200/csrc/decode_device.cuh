@@ -30,11 +30,45 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// One warp decodes one position.  `logits` may point to shared or global memory.
+// Rank order of a decoded row: order[r] = index (within the row) of the move with the r-th largest value, ties
+// by lower index first - the permutation that the reference's Node::sort() (std::sort of the edges by decreasing
+// probability, src/mcts/node.h:163-168, run on a feed thread for every leaf, feedworker.cc:129) applies, made
+// deterministic.  Lane l holds v[k] = value of move l + 32 k.  Rank counting with warp shuffles: m^2 / 32
+// comparisons per lane, ~1.6 k cycles for the typical 80 moves; nothing leaves registers.
+__device__ __forceinline__ void warp_rank_row(const float (&v)[kDecodePerLane], int m, int lane,
+                                              uint16_t* __restrict__ order) {
+    int rank[kDecodePerLane];
+#pragma unroll
+    for (int k = 0; k < kDecodePerLane; ++k) rank[k] = 0;
+#pragma unroll
+    for (int kp = 0; kp < kDecodePerLane; ++kp) {
+        if (32 * kp >= m) break;
+        const float mine = v[kp];
+        const int lim = m - 32 * kp < 32 ? m - 32 * kp : 32;
+        for (int src = 0; src < lim; ++src) {
+            const float x = __shfl_sync(0xffffffffu, mine, src);
+            const int j = 32 * kp + src;
+#pragma unroll
+            for (int k = 0; k < kDecodePerLane; ++k) {
+                if (32 * k >= m) break;
+                rank[k] += (x > v[k] || (x == v[k] && j < lane + 32 * k)) ? 1 : 0;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kDecodePerLane; ++k) {
+        const int i = lane + 32 * k;
+        if (i < m) order[rank[k]] = (uint16_t)i;
+    }
+}
+
+// One warp decodes one position.  `logits` may point to shared or global memory.  `order` (optional):
+// the row's rank order (warp_rank_row) of the values written to `out`; identity for a row with NaNs.
 // Returns the row's NaN flag (uniform across the warp).
 __device__ __forceinline__ bool warp_decode_row(const float* logits, const uint16_t* __restrict__ idx,
                                                 int m, int mode, float win, float draw,
-                                                float* __restrict__ out, int lane) {
+                                                float* __restrict__ out, int lane,
+                                                uint16_t* __restrict__ order = nullptr) {
     if (m > NSB_MAX_LEGAL_MOVES) m = NSB_MAX_LEGAL_MOVES;
     float v[kDecodePerLane];
     bool bad = isnan_bits(win) || isnan_bits(draw);
@@ -56,11 +90,21 @@ __device__ __forceinline__ bool warp_decode_row(const float* logits, const uint1
             const int j = lane + 32 * k;
             if (j < m) out[j] = v[k];
         }
+        if (order != nullptr) {
+            if (bad) {
+                for (int j = lane; j < m; j += 32) order[j] = (uint16_t)j;
+            } else {
+                warp_rank_row(v, m, lane, order);
+            }
+        }
         return bad;
     }
     if (m <= 0) return bad;
     if (m == 1) {  // feedworker.cc:101-103
-        if (lane == 0) out[0] = 1.0f;
+        if (lane == 0) {
+            out[0] = 1.0f;
+            if (order != nullptr) order[0] = 0;
+        }
         return bad;
     }
     if (bad) {  // NaN fallback: every legal logit := 1 before the softmax (feedworker.cc:111-118)
@@ -85,6 +129,16 @@ __device__ __forceinline__ bool warp_decode_row(const float* logits, const uint1
     for (int k = 0; k < kDecodePerLane; ++k) {
         const int j = lane + 32 * k;
         if (j < m) out[j] = v[k] * inv;
+    }
+    if (order != nullptr) {
+        if (bad) {  // uniform probabilities: keep the generation order
+            for (int j = lane; j < m; j += 32) order[j] = (uint16_t)j;
+        } else {    // exp is monotonic and `inv` positive: ranking the unnormalised values ranks the probabilities,
+                    // except where two different exponentials round to one probability - rank what was written
+#pragma unroll
+            for (int k = 0; k < kDecodePerLane; ++k) v[k] *= inv;
+            warp_rank_row(v, m, lane, order);
+        }
     }
     return bad;
 }

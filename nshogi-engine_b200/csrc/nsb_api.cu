@@ -54,6 +54,7 @@ struct Slot {
     float *d_policy = nullptr, *d_win = nullptr, *d_draw = nullptr, *d_legal = nullptr;
     uint32_t* d_off = nullptr;
     uint16_t* d_idx = nullptr;
+    uint16_t* d_order = nullptr;  // rank order of the decoded rows (optional output)
     uint8_t* d_flag = nullptr;
     // cached evaluation (allocated by nsb_cache_create)
     uint64_t* d_hash = nullptr;
@@ -218,6 +219,7 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
         if (e == cudaSuccess) e = cudaMalloc(&s.d_legal, B * NSB_MAX_LEGAL_MOVES * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_off, (B + 1) * sizeof(uint32_t));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_idx, B * NSB_MAX_LEGAL_MOVES * sizeof(uint16_t));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_order, B * NSB_MAX_LEGAL_MOVES * sizeof(uint16_t));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_flag, B);
         if (e != cudaSuccess) {
             set_error("nsb_create: device allocation failed: %s", cudaGetErrorString(e));
@@ -235,7 +237,7 @@ void nsb_destroy(nsb_ctx* c) {
     for (auto& s : c->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_feat); cudaFree(s.d_pos); cudaFree(s.d_policy); cudaFree(s.d_win); cudaFree(s.d_draw);
-        cudaFree(s.d_legal); cudaFree(s.d_off); cudaFree(s.d_idx); cudaFree(s.d_flag);
+        cudaFree(s.d_legal); cudaFree(s.d_off); cudaFree(s.d_idx); cudaFree(s.d_order); cudaFree(s.d_flag);
         cudaFree(s.d_hash); cudaFree(s.d_hit); cudaFree(s.d_miss_idx); cudaFree(s.d_miss_count);
         for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -398,35 +400,6 @@ static bool decode_buffers_mapped(size_t n, size_t total, const uint32_t* move_o
            host_mapped(draw, n * sizeof(float)) && (nan_flag == nullptr || host_mapped(nan_flag, n));
 }
 
-// Direct I/O (c->direct_io and every buffer of the call lies in nsb_host_alloc memory): the one trunk
-// launch reads the inputs from and writes the legal-move rows into the caller's page-locked buffers.
-// Exactly one of features / positions is set.  Returns 1 if the launch was enqueued, 0 if the call
-// has to take the staged path, < 0 on error.
-static int eval_decode_direct(nsb_ctx* c, Slot& s, const nsb_feature_bitboard* features, const nsb_position* positions,
-                              size_t n, const uint32_t* move_off, const uint16_t* move_idx, int mode, float* legal_out,
-                              float* win, float* draw, uint8_t* nan_flag) {
-    if (!c->direct_io) return 0;
-    const size_t total = move_off[n];
-    if (move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) return 0;  // the staged path reports it
-    if (features ? !host_mapped(features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard))
-                 : !host_mapped(positions, n * sizeof(nsb_position)))
-        return 0;
-    if (!decode_buffers_mapped(n, total, move_off, move_idx, legal_out, win, draw, nan_flag)) return 0;
-    EvalArgs a{};
-    a.features = features;
-    a.positions = positions;
-    a.n = (int)n;
-    a.win = win;
-    a.draw = draw;
-    a.move_off = move_off;
-    a.move_idx = move_idx;
-    a.legal_out = legal_out;
-    a.nan_flag = nan_flag;
-    a.decode_mode = mode;
-    const int rc = run_trunk(c, s, a);
-    return rc ? rc : 1;
-}
-
 // Stage 1 for a batch whose packed positions are already in s.d_pos: either it is left to the trunk
 // kernel's prologue (*fused = s.d_pos; the bitboards never exist in HBM), or the
 // standalone pack kernel fills s.d_feat (*fused = nullptr).
@@ -443,58 +416,34 @@ static int stage1(nsb_ctx* c, Slot& s, size_t n, const nsb_position** fused) {
     return 0;
 }
 
-static int eval_decode_common(nsb_ctx* c, Slot& s, const nsb_position* d_positions, size_t n, const uint32_t* move_off,
-                              const uint16_t* move_idx, int mode, float* legal_out, float* win, float* draw,
-                              uint8_t* nan_flag) {
-    const size_t total = move_off[n];
-    if (move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) {
-        set_error("eval_decode: move_off must start at 0 and hold at most %d moves per position",
-                  NSB_MAX_LEGAL_MOVES);
+static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const char* who);
+
+int nsb_eval_request_async(nsb_ctx* c, int slot, const nsb_decode_request* request) {
+    if (!request) {
+        set_error("nsb_eval_request_async: null request");
         return NSB_ERR_INVALID;
     }
-    NSB_CUDA(cudaMemcpyAsync(s.d_off, move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
-    if (total)
-        NSB_CUDA(cudaMemcpyAsync(s.d_idx, move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
-    EvalArgs a{};
-    a.features = s.d_feat;
-    a.positions = d_positions;
-    a.n = (int)n;
-    a.policy = nullptr;  // dense logits never leave the SM
-    a.win = s.d_win;
-    a.draw = s.d_draw;
-    a.move_off = s.d_off;
-    a.move_idx = s.d_idx;
-    a.legal_out = s.d_legal;
-    a.nan_flag = s.d_flag;
-    a.decode_mode = mode;
-    int rc = run_trunk(c, s, a);
-    if (rc) return rc;
-    if (total)
-        NSB_CUDA(cudaMemcpyAsync(legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    if (nan_flag) NSB_CUDA(cudaMemcpyAsync(nan_flag, s.d_flag, n, cudaMemcpyDeviceToHost, s.stream));
-    return 0;
+    return eval_request(c, slot, *request, "nsb_eval_request_async");
 }
 
 int nsb_eval_decode_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, size_t n,
                           const uint32_t* move_off, const uint16_t* move_idx, int mode, float* legal_out,
                           float* win, float* draw, uint8_t* nan_flag) {
-    int rc = check_ctx(c, slot);
-    if (rc) return rc;
-    if ((rc = check_batch(c, n, true))) return rc;
-    if (!features || !move_off || !move_idx || !legal_out || !win || !draw ||
-        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+    nsb_decode_request r{};
+    r.features = features;
+    r.n = n;
+    r.move_off = move_off;
+    r.move_idx = move_idx;
+    r.mode = mode;
+    r.legal_out = legal_out;
+    r.win = win;
+    r.draw = draw;
+    r.nan_flag = nan_flag;
+    if (!features) {
         set_error("nsb_eval_decode_async: null buffer or bad mode");
         return NSB_ERR_INVALID;
     }
-    if (n == 0) return 0;
-    Slot& s = c->slots[slot];
-    if ((rc = eval_decode_direct(c, s, features, nullptr, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag)))
-        return rc < 0 ? rc : 0;
-    NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
-                             cudaMemcpyHostToDevice, s.stream));
-    return eval_decode_common(c, s, nullptr, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag);
+    return eval_request(c, slot, r, "nsb_eval_decode_async");
 }
 
 int nsb_eval_positions_async(nsb_ctx* c, int slot, const nsb_position* positions, size_t n, float* policy,
@@ -538,23 +487,21 @@ int nsb_eval_positions_async(nsb_ctx* c, int slot, const nsb_position* positions
 int nsb_eval_positions_decode_async(nsb_ctx* c, int slot, const nsb_position* positions, size_t n,
                                     const uint32_t* move_off, const uint16_t* move_idx, int mode,
                                     float* legal_out, float* win, float* draw, uint8_t* nan_flag) {
-    int rc = check_ctx(c, slot);
-    if (rc) return rc;
-    if ((rc = check_batch(c, n, true))) return rc;
-    if (!positions || !move_off || !move_idx || !legal_out || !win || !draw ||
-        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+    nsb_decode_request r{};
+    r.positions = positions;
+    r.n = n;
+    r.move_off = move_off;
+    r.move_idx = move_idx;
+    r.mode = mode;
+    r.legal_out = legal_out;
+    r.win = win;
+    r.draw = draw;
+    r.nan_flag = nan_flag;
+    if (!positions) {
         set_error("nsb_eval_positions_decode_async: null buffer or bad mode");
         return NSB_ERR_INVALID;
     }
-    if (n == 0) return 0;
-    Slot& s = c->slots[slot];
-    if (c->fuse_pack &&
-        (rc = eval_decode_direct(c, s, nullptr, positions, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag)))
-        return rc < 0 ? rc : 0;
-    NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
-    const nsb_position* fused = nullptr;
-    if ((rc = stage1(c, s, n, &fused))) return rc;
-    return eval_decode_common(c, s, fused, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag);
+    return eval_request(c, slot, r, "nsb_eval_positions_decode_async");
 }
 
 int nsb_await(nsb_ctx* c, int slot) {
@@ -785,88 +732,137 @@ int nsb_eval_cached_decode_device(nsb_ctx* c, int slot, const nsb_feature_bitboa
 int nsb_eval_cached_decode_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, size_t n,
                                  const uint64_t* hashes, const uint32_t* move_off, const uint16_t* move_idx, int mode,
                                  float* legal_out, float* win, float* draw, uint8_t* nan_flag, uint8_t* hit_flag) {
+    nsb_decode_request r{};
+    r.features = features;
+    r.n = n;
+    r.hashes = hashes;
+    r.move_off = move_off;
+    r.move_idx = move_idx;
+    r.mode = mode;
+    r.legal_out = legal_out;
+    r.win = win;
+    r.draw = draw;
+    r.nan_flag = nan_flag;
+    r.hit_flag = hit_flag;
     int rc = check_cache(c, slot, "nsb_eval_cached_decode_async");
     if (rc) return rc;
-    if ((rc = check_batch(c, n, true))) return rc;
-    if (!features || !hashes || !move_off || !move_idx || !legal_out || !win || !draw ||
-        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+    if (!features || !hashes) {
         set_error("nsb_eval_cached_decode_async: null buffer or bad mode");
         return NSB_ERR_INVALID;
     }
-    if (n == 0) return 0;
-    const size_t total = move_off[n];
-    if (move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) {
-        set_error("nsb_eval_cached_decode_async: move_off must start at 0 and hold at most %d moves per position",
-                  NSB_MAX_LEGAL_MOVES);
-        return NSB_ERR_INVALID;
-    }
-    Slot& s = c->slots[slot];
-    if (c->direct_io && host_mapped(features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard)) &&
-        host_mapped(hashes, n * sizeof(uint64_t)) &&
-        decode_buffers_mapped(n, total, move_off, move_idx, legal_out, win, draw, nan_flag) &&
-        (hit_flag == nullptr || host_mapped(hit_flag, n)))  // probe + trunk work on the caller's buffers: no copy nodes
-        return eval_cached_enqueue(c, s, features, nullptr, n, hashes, move_off, move_idx, mode, legal_out, win, draw,
-                                   nan_flag ? nan_flag : s.d_flag, hit_flag ? hit_flag : s.d_hit);
-    NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
-                             cudaMemcpyHostToDevice, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(s.d_hash, hashes, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(s.d_off, move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
-    if (total)
-        NSB_CUDA(cudaMemcpyAsync(s.d_idx, move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
-    rc = eval_cached_enqueue(c, s, s.d_feat, nullptr, n, s.d_hash, s.d_off, s.d_idx, mode, s.d_legal, s.d_win, s.d_draw,
-                             s.d_flag, s.d_hit);
-    if (rc) return rc;
-    if (total)
-        NSB_CUDA(cudaMemcpyAsync(legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    if (nan_flag) NSB_CUDA(cudaMemcpyAsync(nan_flag, s.d_flag, n, cudaMemcpyDeviceToHost, s.stream));
-    if (hit_flag) NSB_CUDA(cudaMemcpyAsync(hit_flag, s.d_hit, n, cudaMemcpyDeviceToHost, s.stream));
-    return 0;
+    return eval_request(c, slot, r, "nsb_eval_cached_decode_async");
 }
 
 int nsb_eval_positions_cached_decode_async(nsb_ctx* c, int slot, const nsb_position* positions, size_t n,
                                            const uint64_t* hashes, const uint32_t* move_off, const uint16_t* move_idx,
                                            int mode, float* legal_out, float* win, float* draw, uint8_t* nan_flag,
                                            uint8_t* hit_flag) {
+    nsb_decode_request r{};
+    r.positions = positions;
+    r.n = n;
+    r.hashes = hashes;
+    r.move_off = move_off;
+    r.move_idx = move_idx;
+    r.mode = mode;
+    r.legal_out = legal_out;
+    r.win = win;
+    r.draw = draw;
+    r.nan_flag = nan_flag;
+    r.hit_flag = hit_flag;
     int rc = check_cache(c, slot, "nsb_eval_positions_cached_decode_async");
     if (rc) return rc;
-    if ((rc = check_batch(c, n, true))) return rc;
-    if (!positions || !hashes || !move_off || !move_idx || !legal_out || !win || !draw ||
-        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+    if (!positions || !hashes) {
         set_error("nsb_eval_positions_cached_decode_async: null buffer or bad mode");
         return NSB_ERR_INVALID;
     }
+    return eval_request(c, slot, r, "nsb_eval_positions_cached_decode_async");
+}
+
+// The one implementation behind every host-buffer entry point of the fused path (include/nsb.h,
+// nsb_decode_request): bitboards or packed positions in; through the device cache when hashes are given;
+// rank order out when asked for.  Direct I/O: when every buffer of the request is mapped page-locked memory
+// the kernels work on the caller's buffers themselves; otherwise copy nodes around them (trt.cc:240-242,265-271).
+static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const char* who) {
+    int rc = r.hashes ? check_cache(c, slot, who) : check_ctx(c, slot);
+    if (rc) return rc;
+    const size_t n = r.n;
+    if ((rc = check_batch(c, n, true))) return rc;
+    if ((r.features != nullptr) == (r.positions != nullptr) || !r.move_off || !r.move_idx || !r.legal_out || !r.win || !r.draw ||
+        (r.mode != NSB_DECODE_PROBS && r.mode != NSB_DECODE_LOGITS)) {
+        set_error("%s: null buffer or bad mode", who);
+        return NSB_ERR_INVALID;
+    }
     if (n == 0) return 0;
-    const size_t total = move_off[n];
-    if (move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) {
-        set_error("nsb_eval_positions_cached_decode_async: move_off must start at 0 and hold at most %d moves per position",
-                  NSB_MAX_LEGAL_MOVES);
+    const size_t total = r.move_off[n];
+    if (r.move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) {
+        set_error("%s: move_off must start at 0 and hold at most %d moves per position", who, NSB_MAX_LEGAL_MOVES);
         return NSB_ERR_INVALID;
     }
     Slot& s = c->slots[slot];
-    if (c->direct_io && c->fuse_pack && host_mapped(positions, n * sizeof(nsb_position)) &&
-        host_mapped(hashes, n * sizeof(uint64_t)) &&
-        decode_buffers_mapped(n, total, move_off, move_idx, legal_out, win, draw, nan_flag) &&
-        (hit_flag == nullptr || host_mapped(hit_flag, n)))
-        return eval_cached_enqueue(c, s, nullptr, positions, n, hashes, move_off, move_idx, mode, legal_out, win, draw,
-                                   nan_flag ? nan_flag : s.d_flag, hit_flag ? hit_flag : s.d_hit);
-    NSB_CUDA(cudaMemcpyAsync(s.d_pos, positions, n * sizeof(nsb_position), cudaMemcpyHostToDevice, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(s.d_hash, hashes, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(s.d_off, move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
-    if (total)
-        NSB_CUDA(cudaMemcpyAsync(s.d_idx, move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
-    const nsb_position* fused = nullptr;
-    if ((rc = stage1(c, s, n, &fused))) return rc;
-    rc = eval_cached_enqueue(c, s, s.d_feat, fused, n, s.d_hash, s.d_off, s.d_idx, mode, s.d_legal, s.d_win, s.d_draw,
-                             s.d_flag, s.d_hit);
-    if (rc) return rc;
-    if (total)
-        NSB_CUDA(cudaMemcpyAsync(legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    NSB_CUDA(cudaMemcpyAsync(draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    if (nan_flag) NSB_CUDA(cudaMemcpyAsync(nan_flag, s.d_flag, n, cudaMemcpyDeviceToHost, s.stream));
-    if (hit_flag) NSB_CUDA(cudaMemcpyAsync(hit_flag, s.d_hit, n, cudaMemcpyDeviceToHost, s.stream));
+    const size_t in_bytes = r.features ? n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard) : n * sizeof(nsb_position);
+    const void* in = r.features ? (const void*)r.features : (const void*)r.positions;
+
+    EvalArgs a{};
+    a.n = (int)n;
+    a.decode_mode = r.mode;
+    const bool direct = c->direct_io && (r.features || c->fuse_pack) && host_mapped(in, in_bytes) &&
+                        decode_buffers_mapped(n, total, r.move_off, r.move_idx, r.legal_out, r.win, r.draw, r.nan_flag) &&
+                        (!r.hashes || host_mapped(r.hashes, n * sizeof(uint64_t))) && (!r.hit_flag || host_mapped(r.hit_flag, n)) &&
+                        (!r.order_out || host_mapped(r.order_out, (total ? total : 1) * sizeof(uint16_t)));
+    const uint64_t* hashes = r.hashes;
+    uint8_t* hit = r.hit_flag ? r.hit_flag : s.d_hit;
+    if (direct) {
+        a.features = r.features;
+        a.positions = r.positions;
+        a.win = r.win;
+        a.draw = r.draw;
+        a.move_off = r.move_off;
+        a.move_idx = r.move_idx;
+        a.legal_out = r.legal_out;
+        a.order_out = r.order_out;
+        a.nan_flag = r.nan_flag ? r.nan_flag : (r.hashes ? s.d_flag : nullptr);
+    } else {
+        NSB_CUDA(cudaMemcpyAsync(r.features ? (void*)s.d_feat : (void*)s.d_pos, in, in_bytes, cudaMemcpyHostToDevice, s.stream));
+        a.features = s.d_feat;
+        if (r.positions && (rc = stage1(c, s, n, &a.positions))) return rc;
+        if (r.hashes) {
+            NSB_CUDA(cudaMemcpyAsync(s.d_hash, r.hashes, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+            hashes = s.d_hash;
+            hit = s.d_hit;
+        }
+        NSB_CUDA(cudaMemcpyAsync(s.d_off, r.move_off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+        if (total)
+            NSB_CUDA(cudaMemcpyAsync(s.d_idx, r.move_idx, total * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
+        a.win = s.d_win;
+        a.draw = s.d_draw;
+        a.move_off = s.d_off;
+        a.move_idx = s.d_idx;
+        a.legal_out = s.d_legal;
+        a.order_out = r.order_out ? s.d_order : nullptr;
+        a.nan_flag = s.d_flag;
+    }
+    if (r.hashes) {
+        NSB_CUDA(cudaMemsetAsync(s.d_miss_count, 0, sizeof(int), s.stream));
+        int k = launch_cache_probe(c->cache, hashes, n, a.move_off, a.legal_out, a.win, a.draw, hit, a.nan_flag, s.d_miss_idx,
+                                   s.d_miss_count, s.stream, a.order_out);
+        NSB_CUDA(cudaGetLastError());
+        c->launches += (uint64_t)k;
+        a.index = s.d_miss_idx;   // the trunk launch works on the probe's miss list and stores what it decodes
+        a.count = s.d_miss_count;
+        a.hashes = hashes;
+        a.cache = c->cache;
+    }
+    if ((rc = run_trunk(c, s, a))) return rc;
+    if (direct) return 0;
+    if (total) {
+        NSB_CUDA(cudaMemcpyAsync(r.legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        if (r.order_out)
+            NSB_CUDA(cudaMemcpyAsync(r.order_out, s.d_order, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
+    }
+    NSB_CUDA(cudaMemcpyAsync(r.win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    NSB_CUDA(cudaMemcpyAsync(r.draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    if (r.nan_flag) NSB_CUDA(cudaMemcpyAsync(r.nan_flag, s.d_flag, n, cudaMemcpyDeviceToHost, s.stream));
+    if (r.hashes && r.hit_flag) NSB_CUDA(cudaMemcpyAsync(r.hit_flag, s.d_hit, n, cudaMemcpyDeviceToHost, s.stream));
     return 0;
 }
 

@@ -124,6 +124,7 @@ struct EvalArgs {
     const uint32_t* move_off;     // [n+1] or nullptr
     const uint16_t* move_idx;
     float* legal_out;
+    uint16_t* order_out;          // optional: per position the rank order of its decoded row (decode_device.cuh)
     uint8_t* nan_flag;
     int decode_mode;
     unsigned long long* timeline;  // optional (diagnostics): CTA 0 writes 4 clock64 stamps per layer
@@ -156,7 +157,7 @@ int launch_decode(const float* d_policy, const float* d_win, const float* d_draw
 int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s);
 int launch_cache_probe(const DeviceCache& c, const uint64_t* d_hashes, size_t n, const uint32_t* d_off, float* d_legal,
                        float* d_win, float* d_draw, uint8_t* d_hit, uint8_t* d_nan_flag, int* d_miss_idx, int* d_miss_count,
-                       cudaStream_t s);
+                       cudaStream_t s, uint16_t* d_order = nullptr);
 int launch_cache_store(const DeviceCache& c, const uint64_t* d_hashes, size_t n, const uint32_t* d_off,
                        const float* d_legal, const float* d_win, const float* d_draw, const uint8_t* d_skip,
                        uint8_t* d_stored, cudaStream_t s);

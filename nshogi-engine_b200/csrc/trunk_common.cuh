@@ -229,7 +229,8 @@ __device__ __forceinline__ void heads_tail(const DeviceNet& net, const EvalArgs&
                 const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
                 const float w = red[kEpiWarps * NPOS * 2 + ew * 2 + 0], d = red[kEpiWarps * NPOS * 2 + ew * 2 + 1];
                 const bool bad = warp_decode_row(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
-                                                 a.decode_mode, w, d, a.legal_out + mb, lane);
+                                                 a.decode_mode, w, d, a.legal_out + mb, lane,
+                                                 a.order_out ? a.order_out + mb : nullptr);
                 if (a.nan_flag && lane == 0) a.nan_flag[b] = bad ? 1 : 0;
                 if (a.hashes != nullptr && !bad) {  // every lane re-reads exactly the row elements it wrote
                     __syncwarp();

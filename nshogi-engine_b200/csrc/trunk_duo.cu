@@ -124,7 +124,7 @@ __device__ __forceinline__ void heads_tail_small(const DeviceNet& net, const Eva
                 const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
                 const float w = red[NW * NPOS * 2 + ew * 2 + 0], d = red[NW * NPOS * 2 + ew * 2 + 1];
                 const bool bad = warp_decode_row(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb), a.decode_mode,
-                                                 w, d, a.legal_out + mb, lane);
+                                                 w, d, a.legal_out + mb, lane, a.order_out ? a.order_out + mb : nullptr);
                 if (a.nan_flag && lane == 0) a.nan_flag[b] = bad ? 1 : 0;
                 if (a.hashes != nullptr && !bad) {
                     __syncwarp();

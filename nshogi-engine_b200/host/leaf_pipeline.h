@@ -31,6 +31,9 @@ class LeafPipeline {
         uint64_t* Hashes = nullptr;                // [BatchMax]       state hashes (only read when the executor has a cache)
         // outputs, valid after collect()
         float* Legal = nullptr;                    // per legal move: probabilities or raw logits
+        uint16_t* Order = nullptr;                 // per position the rank order of its row (submit(..., Ranked)):
+                                                   // Order[off + r] = row index of the r-th most probable move, the
+                                                   // permutation of Node::sort() (src/mcts/node.h:163-168)
         float* WinRate = nullptr;
         float* DrawRate = nullptr;
         uint8_t* NanFlag = nullptr;
@@ -47,6 +50,7 @@ class LeafPipeline {
             alloc(S.MoveOffsets, BatchMax + 1);
             alloc(S.MoveIndices, BatchMax * NSB_MAX_LEGAL_MOVES);
             alloc(S.Legal, BatchMax * NSB_MAX_LEGAL_MOVES);
+            alloc(S.Order, BatchMax * NSB_MAX_LEGAL_MOVES);
             alloc(S.WinRate, BatchMax);
             alloc(S.DrawRate, BatchMax);
             alloc(S.NanFlag, BatchMax);
@@ -79,34 +83,30 @@ class LeafPipeline {
         return Slots[I];
     }
 
-    // Enqueue H2D + stage 1 (if FromPositions) + expansion + forward + fused decode + D2H.  With
-    // UseCache (executor built with enableCache) the batch goes through the device-resident cache:
-    // hits are served from HBM, only the misses are evaluated, evaluated rows are stored.
+    // Enqueue stage 1 (if FromPositions) + expansion + forward + fused decode, with the copies around them or, in
+    // a one-slot executor, directly on these page-locked arrays (NSB_IO_DIRECT).  With UseCache (executor built
+    // with enableCache) the batch goes through the device-resident cache: hits are served from HBM, only the
+    // misses are evaluated, evaluated rows are stored.  With Ranked, Order[] receives every row's rank order.
     void submit(std::size_t Index, std::size_t Count, bool FromPositions, int DecodeMode = NSB_DECODE_PROBS,
-                bool UseCache = false) {
+                bool UseCache = false, bool Ranked = false) {
         Slot& S = Slots[Index];
         S.Count = Count;
         if (Count == 0) return;
-        if (UseCache) {
-            const int R =
-                FromPositions
-                    ? nsb_eval_positions_cached_decode_async(Ex->context(), (int)Index, S.Positions, Count, S.Hashes,
-                                                             S.MoveOffsets, S.MoveIndices, DecodeMode, S.Legal, S.WinRate,
-                                                             S.DrawRate, S.NanFlag, S.HitFlag)
-                    : nsb_eval_cached_decode_async(Ex->context(), (int)Index, S.Features, Count, S.Hashes, S.MoveOffsets,
-                                                   S.MoveIndices, DecodeMode, S.Legal, S.WinRate, S.DrawRate, S.NanFlag,
-                                                   S.HitFlag);
-            infer::B200::check(R, "LeafPipeline::submit (cached)");
-            S.InFlight = true;
-            return;
-        }
-        const int R = FromPositions
-                          ? nsb_eval_positions_decode_async(Ex->context(), (int)Index, S.Positions, Count, S.MoveOffsets,
-                                                            S.MoveIndices, DecodeMode, S.Legal, S.WinRate, S.DrawRate,
-                                                            S.NanFlag)
-                          : nsb_eval_decode_async(Ex->context(), (int)Index, S.Features, Count, S.MoveOffsets,
-                                                  S.MoveIndices, DecodeMode, S.Legal, S.WinRate, S.DrawRate, S.NanFlag);
-        infer::B200::check(R, "LeafPipeline::submit");
+        nsb_decode_request R{};
+        if (FromPositions) R.positions = S.Positions;
+        else R.features = S.Features;
+        R.n = Count;
+        R.hashes = UseCache ? S.Hashes : nullptr;
+        R.move_off = S.MoveOffsets;
+        R.move_idx = S.MoveIndices;
+        R.mode = DecodeMode;
+        R.legal_out = S.Legal;
+        R.order_out = Ranked ? S.Order : nullptr;
+        R.win = S.WinRate;
+        R.draw = S.DrawRate;
+        R.nan_flag = S.NanFlag;
+        R.hit_flag = UseCache ? S.HitFlag : nullptr;
+        infer::B200::check(nsb_eval_request_async(Ex->context(), (int)Index, &R), "LeafPipeline::submit");
         S.InFlight = true;
     }
 

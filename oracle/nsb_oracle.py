@@ -90,6 +90,23 @@ def decode(policy, win, draw, off, idx, mode: int):
     return out, flag
 
 
+def rank_rows(legal, off, flags=None):
+    """Edge order after reference src/mcts/node.h:163-168 (Node::sort: std::sort of a node's edges by decreasing
+    probability, called from feedworker.cc:129): per CSR row the permutation `order` with legal[order] non-increasing.
+    std::sort leaves the order of equal elements unspecified; the restatement fixes it (lower index first = a stable
+    sort), which is one of the results std::sort may produce.  Rows flagged NaN keep the generation order."""
+    legal = np.asarray(legal, dtype=np.float32)
+    off = np.asarray(off, dtype=np.int64)
+    order = np.zeros(int(off[-1]), dtype=np.uint16)
+    for b in range(len(off) - 1):
+        row = legal[off[b]:off[b + 1]]
+        if flags is not None and flags[b]:
+            order[off[b]:off[b + 1]] = np.arange(len(row), dtype=np.uint16)
+        else:
+            order[off[b]:off[b + 1]] = np.argsort(-row.astype(np.float64), kind="stable").astype(np.uint16)
+    return order
+
+
 def forward(desc, blob: np.ndarray, planes: np.ndarray, emulate_bf16: bool):
     """fp32 definition of the canonical net; planes [n][in_channels][81] fp32."""
     d = NetDesc(desc.in_channels, desc.channels, desc.blocks, desc.value_hidden)

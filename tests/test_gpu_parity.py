@@ -616,3 +616,90 @@ def test_direct_io_on_caller_registered_buffers(nb, orc, synth, monkeypatch):
                 nb.host_unregister(a)
     for a, b in zip(want, (policy, win, draw)):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("channels,slots", [(128, 1), (128, 2), (256, 1)])
+def test_rank_order_of_decoded_rows(nb, orc, synth, monkeypatch, channels, slots):
+    """order_out of nsb_eval_request_async: per position the permutation that sorts its decoded row by decreasing
+    value (the reference's Node::sort(), src/mcts/node.h:163-168, called per leaf at feedworker.cc:129), ties by
+    lower index.  Bit-exact against the oracle's restatement applied to the GPU's own rows, for every trunk
+    kernel, both decode modes, edge rows (1, 164, 165, 593 moves), duplicated policy slots (exact ties), NaN rows
+    (identity), staged and direct I/O; the other outputs are unchanged by asking for the order."""
+    monkeypatch.delenv("NSB_IO", raising=False)
+    desc = nb.net_desc(channels, 2)
+    blob = nb.random_blob(desc, 17)
+    n = 70
+    pos = synth.random_positions(n, seed=6)
+    off, idx = synth.random_legal_moves(n, seed=6)          # edge rows included
+    idx = idx.copy()
+    r = 5                                                   # exact ties: one row gathers the same slot many times
+    idx[off[r]:off[r + 1]] = idx[off[r]]
+    idx[off[r + 1]:off[r + 1] + 4] = idx[off[r + 1]]
+    total = int(off[-1])
+    P = nb.PinnedArray
+    h_pos, h_off, h_idx = P((n,), nb.POSITION), P((n + 1,), np.uint32), P((total,), np.uint16)
+    h_pos.array[:], h_off.array[:], h_idx.array[:] = pos, off, idx
+    h_legal, h_order = P((total,), np.float32), P((total,), np.uint16)
+    h_win, h_draw, h_flag = P((n,), np.float32), P((n,), np.float32), P((n,), np.uint8)
+    with nb.Context(desc, batch_max=n, slots=slots, blob=blob) as ctx:
+        for direct in (False, True):
+            ctx.set_io_mode(direct)
+            for mode in (nb.DECODE_PROBS, nb.DECODE_LOGITS):
+                h_order.array[:] = 0xFFFF
+                ctx.eval_request_async(0, n, h_off.array, h_idx.array, mode, h_legal.array, h_win.array, h_draw.array,
+                                       positions=h_pos.array, order_out=h_order.array, nan_flag=h_flag.array)
+                ctx.await_(0)
+                legal, order, flag = h_legal.array.copy(), h_order.array.copy(), h_flag.array.copy()
+                assert not flag.any()
+                assert np.array_equal(order, orc.rank_rows(legal, off, flag))
+                for b in range(n):
+                    row, o = legal[off[b]:off[b + 1]], order[off[b]:off[b + 1]].astype(np.int64)
+                    assert np.array_equal(np.sort(o), np.arange(len(row)))            # a permutation
+                    assert np.all(np.diff(row[o]) <= 0)                               # sortedness
+                assert np.array_equal(order[off[r]:off[r + 1]], np.arange(off[r + 1] - off[r]))   # all tied: identity
+                # same call without the order: identical rows
+                plain = np.zeros(total, dtype=np.float32)
+                w2, d2 = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+                ctx.eval_positions_decode_async(slots - 1, pos, n, off, idx, mode, plain, w2, d2, None)
+                ctx.await_(slots - 1)
+                assert np.array_equal(plain.view(np.uint32), legal.view(np.uint32)) and np.array_equal(w2, h_win.array)
+    for a in (h_pos, h_off, h_idx, h_legal, h_order, h_win, h_draw, h_flag):
+        a.free()
+
+
+def test_rank_order_nan_rows_and_cache_hits(nb, orc, synth):
+    """A NaN row keeps the generation order (its probabilities are uniform, feedworker.cc:111-118); rows served from
+    the device cache are ranked like evaluated ones."""
+    desc = nb.net_desc(128, 1)
+    blob = nb.random_blob(desc, 17)
+    blob_nan = blob.copy()
+    blob_nan[-1] = np.nan                                   # draw-rate bias: every row is flagged
+    n = 33
+    pos = synth.random_positions(n, seed=9)
+    off, idx = synth.random_legal_moves(n, seed=9, edge_rows=False)
+    total = int(off[-1])
+    hashes = np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(7)
+
+    def call(ctx, use_cache):
+        legal, order = np.zeros(total, dtype=np.float32), np.full(total, 0xFFFF, dtype=np.uint16)
+        win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        flag, hit = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+        ctx.eval_request_async(0, n, off, idx, nb.DECODE_PROBS, legal, win, draw, positions=pos, order_out=order,
+                               nan_flag=flag, hashes=hashes if use_cache else None, hit_flag=hit if use_cache else None)
+        ctx.await_(0)
+        return legal, order, flag, hit
+
+    with nb.Context(desc, batch_max=n, blob=blob_nan) as ctx:
+        legal, order, flag, _ = call(ctx, False)
+        assert flag.all()
+        assert np.array_equal(order, orc.rank_rows(legal, off, flag))
+        for b in range(n):
+            assert np.array_equal(order[off[b]:off[b + 1]], np.arange(off[b + 1] - off[b]))
+    with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+        ctx.cache_create(4)
+        first = call(ctx, True)
+        again = call(ctx, True)
+        cacheable = np.diff(off) <= 164
+        assert first[3].sum() == 0 and np.array_equal(again[3].astype(bool), cacheable)
+        assert np.array_equal(again[0].view(np.uint32), first[0].view(np.uint32))
+        assert np.array_equal(again[1], first[1]) and np.array_equal(first[1], orc.rank_rows(first[0], off, first[2]))

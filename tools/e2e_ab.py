@@ -42,6 +42,8 @@ h_legal = [nb.PinnedArray((n_moves,), np.float32) for _ in range(slots)]
 h_win = [nb.PinnedArray((B,), np.float32) for _ in range(slots)]
 h_draw = [nb.PinnedArray((B,), np.float32) for _ in range(slots)]
 h_flag = [nb.PinnedArray((B,), np.uint8) for _ in range(slots)]
+RANKED = os.environ.get("E2E_RANKED") == "1"     # also ask for every row's rank order (Node::sort on the GPU)
+h_order = [nb.PinnedArray((n_moves,), np.uint16) for _ in range(slots)]
 
 
 def loop(steps, positions):
@@ -49,7 +51,12 @@ def loop(steps, positions):
         s = i % slots
         if i >= slots:
             ctx.await_(s)
-        if positions:
+        if RANKED:
+            ctx.eval_request_async(s, B, h_off.array, h_idx.array, nb.DECODE_PROBS, h_legal[s].array, h_win[s].array,
+                                   h_draw[s].array, positions=h_pos[i % NP].array if positions else None,
+                                   features=None if positions else h_fb[i % NP].array, order_out=h_order[s].array,
+                                   nan_flag=h_flag[s].array)
+        elif positions:
             ctx.eval_positions_decode_async(s, h_pos[i % NP].array, B, h_off.array, h_idx.array, nb.DECODE_PROBS,
                                             h_legal[s].array, h_win[s].array, h_draw[s].array, h_flag[s].array)
         else:
@@ -59,7 +66,7 @@ def loop(steps, positions):
         ctx.await_(s)
 
 
-print(f"{ctx.trunk_kernel_name()}  B={B} slots={slots} fuse_pack={os.environ.get('NSB_FUSE_PACK', '1')}")
+print(f"{ctx.trunk_kernel_name()}  B={B} slots={slots} ranked={RANKED} fuse_pack={os.environ.get('NSB_FUSE_PACK', '1')}")
 for direct in (False, True):
     ctx.set_io_mode(direct)
     loop(100, False)
