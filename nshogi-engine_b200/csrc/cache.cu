@@ -25,11 +25,15 @@ cache_probe_kernel(const DeviceCache c, const uint64_t* __restrict__ hashes, int
     if (b >= n) return;
     const uint32_t mb = off[b], me = off[b + 1];
     float w = 0.f, d = 0.f;
-    float v[kDecodePerLane];
-#pragma unroll
-    for (int k = 0; k < kDecodePerLane; ++k) v[k] = 0.f;
+    __shared__ float s_row[kCacheWarps][kCacheRowPerLane * 32];
+    float v[kCacheRowPerLane];
     const bool found = cache_load_warp(c, hashes[b], (int)(me - mb), legal + mb, &w, &d, lane, order ? v : nullptr);
-    if (found && order != nullptr) warp_rank_row(v, (int)(me - mb), lane, order + mb);  // a hit is ranked like an evaluated row
+    if (found && order != nullptr) {  // a hit is ranked like an evaluated row
+#pragma unroll
+        for (int k = 0; k < kCacheRowPerLane; ++k) s_row[warp][lane + 32 * k] = v[k];
+        __syncwarp();
+        rank_row_coop(s_row[warp], (int)(me - mb), 0, 1, lane, order + mb);
+    }
     if (lane == 0) {
         hit[b] = found ? 1 : 0;
         if (found) {

@@ -33,52 +33,65 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Rank order of a decoded row: order[r] = index (within the row) of the move with the r-th largest value, ties
 // by lower index first - the permutation that the reference's Node::sort() (std::sort of the edges by decreasing
 // probability, src/mcts/node.h:163-168, run on a feed thread for every leaf, feedworker.cc:129) applies, made
-// deterministic.  Lane l holds v[k] = value of move l + 32 k.  Rank counting with warp shuffles: m^2 / 32
-// comparisons per lane, ~1.6 k cycles for the typical 80 moves; nothing leaves registers.
-__device__ __forceinline__ void warp_rank_row(const float (&v)[kDecodePerLane], int m, int lane,
+// deterministic.  Rank counting over a row staged in shared memory: warp `part` of the `nparts` warps that share
+// the row ranks the 32-move slices part, part + nparts, ...; each lane compares its move with all m values
+// (broadcast shared-memory reads), ~4 m cycles per slice.
+__device__ __forceinline__ void rank_row_coop(const float* vals, int m, int part, int nparts, int lane,
                                               uint16_t* __restrict__ order) {
-    int rank[kDecodePerLane];
-#pragma unroll
-    for (int k = 0; k < kDecodePerLane; ++k) rank[k] = 0;
-#pragma unroll
-    for (int kp = 0; kp < kDecodePerLane; ++kp) {
-        if (32 * kp >= m) break;
-        const float mine = v[kp];
-        const int lim = m - 32 * kp < 32 ? m - 32 * kp : 32;
-        for (int src = 0; src < lim; ++src) {
-            const float x = __shfl_sync(0xffffffffu, mine, src);
-            const int j = 32 * kp + src;
-#pragma unroll
-            for (int k = 0; k < kDecodePerLane; ++k) {
-                if (32 * k >= m) break;
-                rank[k] += (x > v[k] || (x == v[k] && j < lane + 32 * k)) ? 1 : 0;
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kDecodePerLane; ++k) {
+    if (m > NSB_MAX_LEGAL_MOVES) m = NSB_MAX_LEGAL_MOVES;
+    for (int k = part; 32 * k < m; k += nparts) {
         const int i = lane + 32 * k;
-        if (i < m) order[rank[k]] = (uint16_t)i;
+        const float mine = i < m ? vals[i] : 0.f;
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < m; ++j) {
+            const float x = vals[j];
+            rank += (x > mine || (x == mine && j < i)) ? 1 : 0;
+        }
+        if (i < m) order[rank] = (uint16_t)i;
     }
 }
 
-// One warp decodes one position.  `logits` may point to shared or global memory.  `order` (optional):
-// the row's rank order (warp_rank_row) of the values written to `out`; identity for a row with NaNs.
+// Copies a row's rank order from its shared-memory staging to `dst` (global or mapped host memory) with one
+// 2-byte store per lane and consecutive addresses across the warp, slices shared like in rank_row_coop (the
+// scattered stores of the ranking itself would each be a PCIe transaction when dst is host memory).
+__device__ __forceinline__ void rank_row_copy_out(const uint16_t* staged, int m, int part, int nparts, int lane,
+                                                  uint16_t* __restrict__ dst) {
+    if (m > NSB_MAX_LEGAL_MOVES) m = NSB_MAX_LEGAL_MOVES;
+    for (int i = lane + 32 * part; i < m; i += 32 * nparts) dst[i] = staged[i];
+}
+
+// One warp decodes one position.  `logits` may point to shared or global memory.  `stage` (kStage only,
+// shared memory, may alias the row's own logits): receives a copy of the m values written to `out` for
+// rank_row_coop - all equal for a row with NaNs, so that its rank order is the identity.
 // Returns the row's NaN flag (uniform across the warp).
+template <bool kStage = false>
 __device__ __forceinline__ bool warp_decode_row(const float* logits, const uint16_t* __restrict__ idx,
                                                 int m, int mode, float win, float draw,
-                                                float* __restrict__ out, int lane,
-                                                uint16_t* __restrict__ order = nullptr) {
+                                                float* __restrict__ out, int lane, float* stage = nullptr) {
     if (m > NSB_MAX_LEGAL_MOVES) m = NSB_MAX_LEGAL_MOVES;
     float v[kDecodePerLane];
     bool bad = isnan_bits(win) || isnan_bits(draw);
     float mx = -CUDART_INF_F;
+    // all index loads first, back to back: with direct I/O they cross PCIe, and one round trip per 32-move
+    // slice (a load, then the gather that depends on it, then the next load) costs microseconds
+    uint32_t id[kDecodePerLane];
+#pragma unroll
+    for (int k = 0; k < kDecodePerLane; ++k) {
+        const int j = lane + 32 * k;
+        id[k] = j < m ? (uint32_t)__ldg(idx + j) : 0u;
+    }
+    // (keeps the compiler from sinking each load down to its gather: it did, one register for all of them)
+    asm volatile("" : "+r"(id[0]), "+r"(id[1]), "+r"(id[2]), "+r"(id[3]), "+r"(id[4]), "+r"(id[5]), "+r"(id[6]), "+r"(id[7]),
+                      "+r"(id[8]), "+r"(id[9]), "+r"(id[10]), "+r"(id[11]), "+r"(id[12]), "+r"(id[13]), "+r"(id[14]),
+                      "+r"(id[15]), "+r"(id[16]), "+r"(id[17]), "+r"(id[18]));
+    static_assert(kDecodePerLane == 19, "operand list above");
 #pragma unroll
     for (int k = 0; k < kDecodePerLane; ++k) {
         const int j = lane + 32 * k;
         v[k] = 0.f;
         if (j < m) {  // gather: feedworker.cc:119-125, frame.cc:101-106
-            v[k] = logits[idx[j]];
+            v[k] = logits[id[k]];
             bad |= isnan_bits(v[k]);
             mx = fmaxf(mx, v[k]);
         }
@@ -90,11 +103,12 @@ __device__ __forceinline__ bool warp_decode_row(const float* logits, const uint1
             const int j = lane + 32 * k;
             if (j < m) out[j] = v[k];
         }
-        if (order != nullptr) {
-            if (bad) {
-                for (int j = lane; j < m; j += 32) order[j] = (uint16_t)j;
-            } else {
-                warp_rank_row(v, m, lane, order);
+        if (kStage) {
+            __syncwarp();  // every lane has gathered: the logits may be overwritten
+#pragma unroll
+            for (int k = 0; k < kDecodePerLane; ++k) {
+                const int j = lane + 32 * k;
+                if (j < m) stage[j] = bad ? 0.f : v[k];
             }
         }
         return bad;
@@ -103,7 +117,7 @@ __device__ __forceinline__ bool warp_decode_row(const float* logits, const uint1
     if (m == 1) {  // feedworker.cc:101-103
         if (lane == 0) {
             out[0] = 1.0f;
-            if (order != nullptr) order[0] = 0;
+            if (kStage) stage[0] = 1.0f;
         }
         return bad;
     }
@@ -130,14 +144,11 @@ __device__ __forceinline__ bool warp_decode_row(const float* logits, const uint1
         const int j = lane + 32 * k;
         if (j < m) out[j] = v[k] * inv;
     }
-    if (order != nullptr) {
-        if (bad) {  // uniform probabilities: keep the generation order
-            for (int j = lane; j < m; j += 32) order[j] = (uint16_t)j;
-        } else {    // exp is monotonic and `inv` positive: ranking the unnormalised values ranks the probabilities,
-                    // except where two different exponentials round to one probability - rank what was written
+    if (kStage) {  // (a NaN row is uniform here: all ties, identity order)
 #pragma unroll
-            for (int k = 0; k < kDecodePerLane; ++k) v[k] *= inv;
-            warp_rank_row(v, m, lane, order);
+        for (int k = 0; k < kDecodePerLane; ++k) {
+            const int j = lane + 32 * k;
+            if (j < m) stage[j] = v[k] * inv;
         }
     }
     return bad;

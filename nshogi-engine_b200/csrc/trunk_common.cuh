@@ -160,7 +160,7 @@ __device__ __forceinline__ void fc1_prefetch(const DeviceNet& net, int et, float
 // cache, the store of the decoded row (feedworker.cc:134-135: rows with NaNs are not stored).  Ends
 // with a kEpiBar barrier (scratch / vbuf / red reusable).
 template <int NPOS>
-__device__ __forceinline__ void heads_tail(const DeviceNet& net, const EvalArgs& a, int n_eff, int li0, const float* scratch,
+__device__ __forceinline__ void heads_tail(const DeviceNet& net, const EvalArgs& a, int n_eff, int li0, float* scratch,
                                            const float* vbuf, float* red, const float (&wpre)[kFcPrefetch], int et,
                                            unsigned long long* tl) {
     const int ew = et >> 5, lane = et & 31;
@@ -228,14 +228,34 @@ __device__ __forceinline__ void heads_tail(const DeviceNet& net, const EvalArgs&
             if (b >= 0) {
                 const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
                 const float w = red[kEpiWarps * NPOS * 2 + ew * 2 + 0], d = red[kEpiWarps * NPOS * 2 + ew * 2 + 1];
-                const bool bad = warp_decode_row(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
-                                                 a.decode_mode, w, d, a.legal_out + mb, lane,
-                                                 a.order_out ? a.order_out + mb : nullptr);
+                // (two instantiations: the staging keeps the row's values live longer, which costs the plain
+                // path microseconds if it is only predicated off)
+                const bool bad = a.order_out
+                                     ? warp_decode_row<true>(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
+                                                             a.decode_mode, w, d, a.legal_out + mb, lane, scratch + ew * kPolicySize)
+                                     : warp_decode_row<false>(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
+                                                              a.decode_mode, w, d, a.legal_out + mb, lane);
                 if (a.nan_flag && lane == 0) a.nan_flag[b] = bad ? 1 : 0;
                 if (a.hashes != nullptr && !bad) {  // every lane re-reads exactly the row elements it wrote
                     __syncwarp();
                     cache_store_warp(a.cache, __ldg(a.hashes + b), (int)(me - mb), a.legal_out + mb, w, d, lane);
                 }
+            }
+        }
+        if (a.order_out != nullptr) {  // rank order of the rows (Node::sort): all epilogue warps share the work
+            named_bar_sync(kEpiBar, kEpiThreads);
+            const int pos = ew % NPOS;
+            const int b = eval_index(a, li0 + pos, n_eff);
+            // the order is staged behind the row's values in the position's (dead) logits scratch
+            uint16_t* ostage = reinterpret_cast<uint16_t*>(scratch + pos * kPolicySize + 608);
+            if (b >= 0) {
+                const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
+                rank_row_coop(scratch + pos * kPolicySize, (int)(me - mb), ew / NPOS, kEpiWarps / NPOS, lane, ostage);
+            }
+            named_bar_sync(kEpiBar, kEpiThreads);
+            if (b >= 0) {
+                const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
+                rank_row_copy_out(ostage, (int)(me - mb), ew / NPOS, kEpiWarps / NPOS, lane, a.order_out + mb);
             }
         }
     }
