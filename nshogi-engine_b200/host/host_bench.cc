@@ -132,7 +132,7 @@ int main(int argc, char** argv) {
             if (S.Count)  // the slot's previous batch has landed: decode rows -> evaluation cache
                 Stored += Cache.feed(SlotHashes[Idx].data(), S.Count, S.MoveOffsets, S.Legal, S.WinRate, S.DrawRate);
             fill(S, SlotHashes[Idx], (uint64_t)I);
-            Pipe.submit(Idx, B, /*FromPositions=*/true, NSB_DECODE_PROBS);
+            Pipe.submit(Idx, B, /*FromPositions=*/true, NSB_DECODE_PROBS, /*UseCache=*/false, /*Ranked=*/true);
         }
         Pipe.drain();
         for (size_t Idx = 0; Idx < Pipe.numSlots(); ++Idx) {
@@ -149,7 +149,7 @@ int main(int argc, char** argv) {
 
     // --- self-check: fused probabilities == softmax of the Infer contract's logits at the same slots -----
     double MaxDiff = 0.0, SumErr = 0.0;
-    bool RowsEqual = true;
+    bool RowsEqual = true, OrderOk = true;
     {
         evaluate::LeafPipeline::Slot& S = Pipe.collect(0);
         const size_t M = Moves.size();
@@ -168,15 +168,21 @@ int main(int argc, char** argv) {
             RowsEqual = RowsEqual && std::memcmp(S.Legal, S.Legal + I * M, M * sizeof(float)) == 0 &&
                         std::memcmp(Policy, Policy + (size_t)I * NSB_POLICY_SIZE, NSB_POLICY_SIZE * sizeof(float)) == 0;
         MaxDiff = std::fmax(MaxDiff, std::fabs((double)S.WinRate[0] - (double)Win[0]));
+        // the rank order replaces Node::sort() (src/mcts/node.h:163-168): a permutation with non-increasing values
+        std::vector<int> Seen(M, 0);
+        for (size_t R = 0; R < M; ++R) {
+            const uint16_t J = S.Order[R];
+            OrderOk = OrderOk && J < M && !Seen[J]++ && (R == 0 || S.Legal[S.Order[R - 1]] >= S.Legal[J]);
+        }
     }
     mcts::EvalCacheB200::EvalInfo Info;
     const bool CacheHit = Cache.load(SlotHashes[0][B / 2], &Info) && Info.NumMoves == Moves.size();
-    const bool Ok = MaxDiff < 1e-5 && SumErr < 1e-5 && RowsEqual && CacheHit;
+    const bool Ok = MaxDiff < 1e-5 && SumErr < 1e-5 && RowsEqual && CacheHit && OrderOk;
     std::printf("{\"batch\": %d, \"net\": \"%dx%d\", \"infer_blocking_evals_per_s\": %.1f, \"pipeline_evals_per_s\": %.1f, "
                 "\"legal_moves\": %zu, \"max_prob_diff\": %.3g, \"row_sum_err\": %.3g, \"rows_identical\": %s, "
-                "\"cache_rows_stored\": %zu, \"cache_hit\": %s, \"ok\": %s}\n",
+                "\"cache_rows_stored\": %zu, \"cache_hit\": %s, \"order_ok\": %s, \"ok\": %s}\n",
                 B, Exec.net().blocks, Exec.net().channels, BlockingRate, PipeRate, Moves.size(), MaxDiff, SumErr, RowsEqual ? "true" : "false",
-                Stored, CacheHit ? "true" : "false", Ok ? "true" : "false");
+                Stored, CacheHit ? "true" : "false", OrderOk ? "true" : "false", Ok ? "true" : "false");
     nsb_host_free(Features); nsb_host_free(Policy); nsb_host_free(Win); nsb_host_free(Draw);
     return (SelfCheck && !Ok) ? 1 : 0;
 }
