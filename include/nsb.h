@@ -217,6 +217,11 @@ int nsb_decode_device(nsb_ctx* ctx, int slot, const float* d_policy, const float
  * MCTS, feedworker.cc:135; raw logits for self-play, frame.cc:110-114): use one mode per cache. */
 int nsb_cache_create(nsb_ctx* ctx, size_t memory_mb);
 int nsb_cache_clear(nsb_ctx* ctx);
+/* The reference has ONE EvalCache per Manager, shared by all evaluation workers (src/mcts/manager.cc:202-206)
+ * - by default two executors per GPU (context.h:75).  nsb_cache_attach lets `ctx` use the table `owner`
+ * created (same device): launches of both contexts probe and fill it concurrently, the bundles' lock words
+ * arbitrate.  The owner must outlive every ctx attached to it. */
+int nsb_cache_attach(nsb_ctx* ctx, nsb_ctx* owner);
 uint64_t nsb_cache_num_bundles(nsb_ctx* ctx);
 
 /* == EvalCache::store (evalcache.cc:49-121) for a batch of CSR rows on device pointers; rows with

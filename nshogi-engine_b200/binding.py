@@ -90,6 +90,7 @@ SIGNATURES = {
     "nsb_host_register": (C.c_int, [_P, C.c_size_t]),
     "nsb_host_unregister": (C.c_int, [_P]),
     "nsb_eval_request_async": (C.c_int, [_P, C.c_int, _P]),
+    "nsb_cache_attach": (C.c_int, [_P, _P]),
     "nsb_set_io_mode": (C.c_int, [_P, C.c_int]),
     "nsb_io_mode": (C.c_int, [_P]),
     "nsb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
@@ -411,6 +412,9 @@ class Context:
         r = DecodeRequest(_ptr(features), _ptr(positions), n, _ptr(hashes), _ptr(move_off), _ptr(move_idx), mode,
                           _ptr(legal_out), _ptr(order_out), _ptr(win), _ptr(draw), _ptr(nan_flag), _ptr(hit_flag))
         _check(lib().nsb_eval_request_async(self._h, slot, C.byref(r)), "nsb_eval_request_async")
+
+    def cache_attach(self, owner: "Context"):
+        _check(lib().nsb_cache_attach(self._h, owner._h), "nsb_cache_attach")
 
     def set_io_mode(self, direct: bool):
         _check(lib().nsb_set_io_mode(self._h, 1 if direct else 0), "nsb_set_io_mode")

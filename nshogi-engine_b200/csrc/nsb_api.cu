@@ -74,7 +74,8 @@ struct nsb_ctx {
     bool direct_io = false;    // kernels read / write the caller's page-locked buffers themselves (no copy nodes)
     bool fuse_pack = true;     // packed positions are expanded in the trunk prologue (NSB_FUSE_PACK=0: separate pack kernel)
     int duo_ctas = 0;          // > 0: the two-CTAs-per-SM 128-channel trunk (trunk_duo.cu), co-resident CTAs per SM
-    nsb::DeviceCache cache{};  // device-resident evaluation cache (nsb_cache_create)
+    nsb::DeviceCache cache{};  // device-resident evaluation cache (nsb_cache_create / nsb_cache_attach)
+    bool cache_owned = false;  // false: the table belongs to another ctx of the same device (nsb_cache_attach)
     nsb_net_desc desc{};
     bool loaded = false, timing = false;
     nsb::DeviceNet net{};
@@ -243,8 +244,10 @@ void nsb_destroy(nsb_ctx* c) {
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (void* p : c->d_weights) cudaFree(p);
-    cudaFree(c->cache.entries);
-    cudaFree(c->cache.meta);
+    if (c->cache_owned) {
+        cudaFree(c->cache.entries);
+        cudaFree(c->cache.meta);
+    }
     delete c;
 }
 
@@ -612,7 +615,37 @@ int nsb_cache_create(nsb_ctx* c, size_t memory_mb) {
         return e == cudaErrorMemoryAllocation ? NSB_ERR_NOMEM : NSB_ERR_CUDA;
     }
     c->cache = dc;
+    c->cache_owned = true;
     return nsb_cache_clear(c);
+}
+
+int nsb_cache_attach(nsb_ctx* c, nsb_ctx* owner) {
+    int rc = check_ctx(c, 0);
+    if (rc) return rc;
+    if (!owner || owner == c || !owner->cache.num_bundles || owner->gpu != c->gpu) {
+        set_error("nsb_cache_attach: the owner must be another ctx of the same device that has a cache");
+        return NSB_ERR_INVALID;
+    }
+    if (c->cache.num_bundles) {
+        set_error("nsb_cache_attach: this ctx already has a cache");
+        return NSB_ERR_STATE;
+    }
+    NSB_CUDA(cudaSetDevice(c->gpu));
+    const size_t B = (size_t)c->batch_max;
+    cudaError_t e = cudaSuccess;
+    for (auto& s : c->slots) {
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_hash, B * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_hit, B);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_miss_idx, B * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_miss_count, sizeof(int));
+    }
+    if (e != cudaSuccess) {
+        set_error("nsb_cache_attach: device allocation failed: %s", cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? NSB_ERR_NOMEM : NSB_ERR_CUDA;
+    }
+    c->cache = owner->cache;  // the bundles' lock words make concurrent kernels of several contexts safe
+    c->cache_owned = false;
+    return 0;
 }
 
 int nsb_cache_clear(nsb_ctx* c) {

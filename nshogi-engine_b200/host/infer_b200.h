@@ -98,6 +98,11 @@ class B200 : public Infer {
         check(nsb_cache_create(Ctx_, MemoryMiB), "nsb_cache_create");
         HasCache_ = true;
     }
+    // Share another executor's cache (same GPU): the reference's evaluation workers all feed one EvalCache.
+    void attachCache(B200& Owner) {
+        check(nsb_cache_attach(Ctx_, Owner.Ctx_), "nsb_cache_attach");
+        HasCache_ = true;
+    }
     bool hasCache() const {
         return HasCache_;
     }

@@ -295,3 +295,43 @@ def test_eval_cached_serves_hits_and_evaluates_misses(nb, orc, synth, channels, 
                                      off3, idx3, nb.DECODE_PROBS, legal, win, draw, None, hit)
         ctx.await_(0)
         assert hit[victim] == 0 and abs(legal[off3[victim]:off3[victim + 1]].sum() - 1.0) < 1e-5
+
+
+@pytest.mark.gpu
+def test_two_executors_share_one_cache(nb, orc, synth):
+    """nsb_cache_attach: the reference's evaluation workers (two executors per GPU by default, context.h:75) feed ONE
+    EvalCache (manager.cc:202-206).  What executor A evaluated is a hit for executor B, bit for bit, and both can
+    run at once."""
+    desc = nb.net_desc(128, 1)
+    blob = nb.random_blob(desc, 5)
+    n = 48
+    pos = synth.random_positions(n, seed=3)
+    off, idx = synth.random_legal_moves(n, seed=3, edge_rows=False)
+    total = int(off[-1])
+    hashes = np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(99)
+
+    def call(ctx, start=True):
+        legal = np.zeros(total, dtype=np.float32)
+        win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+        hit = np.zeros(n, dtype=np.uint8)
+        ctx.eval_positions_cached_decode_async(0, pos, n, hashes, off, idx, nb.DECODE_PROBS, legal, win, draw, None, hit)
+        return legal, win, draw, hit
+
+    with nb.Context(desc, batch_max=n, blob=blob) as a, nb.Context(desc, batch_max=n, blob=blob) as b:
+        a.cache_create(4)
+        b.cache_attach(a)
+        assert b.cache_num_bundles() == a.cache_num_bundles()
+        ra = call(a)
+        a.await_(0)
+        rb = call(b)
+        b.await_(0)
+        cacheable = np.diff(off) <= 164
+        assert ra[3].sum() == 0 and np.array_equal(rb[3].astype(bool), cacheable)
+        assert np.array_equal(rb[0].view(np.uint32), ra[0].view(np.uint32)) and np.array_equal(rb[1], ra[1])
+        a.cache_clear()
+        ra, rb = call(a), call(b)        # both in flight on the same table
+        a.await_(0)
+        b.await_(0)
+        assert np.array_equal(rb[0].view(np.uint32), ra[0].view(np.uint32))
+        with pytest.raises(Exception):
+            a.cache_attach(a)
