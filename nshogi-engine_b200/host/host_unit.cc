@@ -15,7 +15,12 @@
 #include <fstream>
 #include <iterator>
 
+#include <algorithm>
+#include <cmath>
+#include <random>
+
 #include "eval_cache.h"
+#include "mcts_feed.h"
 #include "move_index.h"
 #include "onnx_import.h"
 
@@ -65,6 +70,76 @@ static int onnxBlob(const char* InPath, const char* OutPath) {
     Out.write(reinterpret_cast<const char*>(Blob.data()), (std::streamsize)(Blob.size() * sizeof(float)));
     std::printf("ok %d %d %d %d %zu\n", S.InChannels, S.Channels, S.Blocks, S.Hidden, Blob.size());
     return Out ? 0 : 2;
+}
+
+// ---- mock of the reference's mcts::Node / Edge surface that feedRanked touches (src/mcts/node.h, edge.h) ----
+struct MockEdge {
+    uint16_t Move = 0;
+    float Probability = 0.f;
+    uint16_t getMove() const { return Move; }
+    void setMove(uint16_t M) { Move = M; }
+    void setProbability(float P) { Probability = P; }
+    float getProbability() const { return Probability; }
+};
+struct MockNode {
+    static constexpr uint64_t VisitMask = (1ull << 32) - 1;
+    std::vector<MockEdge> Edges;
+    MockNode* Parent = nullptr;
+    double WinAcc = 0.0, DrawAcc = 0.0;
+    uint64_t Visits = 0;
+    float WinPred = -1.f, DrawPred = -1.f, BackedWin = -1.f, BackedDraw = -1.f;
+    uint16_t getNumChildren() const { return (uint16_t)Edges.size(); }
+    MockEdge* getEdge() { return Edges.data(); }
+    const MockNode* getParent() const { return Parent; }
+    double getWinRateAccumulated() const { return WinAcc; }
+    double getDrawRateAccumulated() const { return DrawAcc; }
+    uint64_t getVisitsAndVirtualLoss() const { return Visits; }
+    void setEvaluation(const float* Policy, float W, float D) {  // node.h:150-160
+        if (Policy) for (size_t I = 0; I < Edges.size(); ++I) Edges[I].setProbability(Policy[I]);
+        WinPred = W;
+        DrawPred = D;
+    }
+    void sort() {  // node.h:163-168 (stable here: the tie order the GPU rank defines)
+        std::stable_sort(Edges.begin(), Edges.end(), [](const MockEdge& A, const MockEdge& B) { return A.Probability > B.Probability; });
+    }
+    void updateAncestors(float W, float D) { BackedWin = W; BackedDraw = D; }
+};
+
+static int feedChecks() {
+    std::mt19937_64 Rng(7);
+    for (int Trial = 0; Trial < 200; ++Trial) {
+        const uint16_t N = (uint16_t)(Trial < 3 ? Trial + 1 : 2 + Rng() % 300);
+        std::vector<float> Legal(N);
+        double Sum = 0.0;
+        for (auto& P : Legal) Sum += (P = (float)((Rng() % 1000) + 1));
+        for (auto& P : Legal) P = (float)(P / Sum);
+        if (Trial % 5 == 0 && N > 4) Legal[1] = Legal[3] = Legal[0];  // exact ties
+        std::vector<uint16_t> Order(N);
+        for (uint16_t I = 0; I < N; ++I) Order[I] = I;
+        std::stable_sort(Order.begin(), Order.end(), [&](uint16_t A, uint16_t B) { return Legal[A] > Legal[B]; });  // == the GPU's rank order
+        MockNode Parent, A, B;
+        Parent.WinAcc = 30.0; Parent.DrawAcc = 5.0; Parent.Visits = 100;
+        A.Edges.resize(N);
+        for (uint16_t I = 0; I < N; ++I) A.Edges[I].Move = (uint16_t)(1000 + I);
+        B = A;
+        A.Parent = B.Parent = (Trial % 2) ? &Parent : nullptr;
+        const bool NanW = Trial % 7 == 0, NanD = Trial % 11 == 0;
+        const float W = NanW ? std::nanf("") : 0.625f, D = NanD ? std::nanf("") : 0.125f;
+        // the reference's sequence (feedworker.cc:58-131) on node A
+        float RW = W, RD = D;
+        if (NanW) RW = A.Parent ? (float)(1.0 - 30.0 / 100.0) : 0.5f;
+        if (NanD) RD = A.Parent ? (float)(5.0 / 100.0) : 0.0f;
+        if (N == 1) { float One = 1.0f; A.setEvaluation(&One, RW, RD); }
+        else { A.setEvaluation(Legal.data(), RW, RD); A.sort(); }
+        A.updateAncestors(RW, RD);
+        // feedRanked on node B
+        const mcts::LeafRow Row{Legal.data(), Order.data(), N, W, D};
+        const bool Nan = mcts::feedRanked(&B, Row);
+        CHECK(Nan == (NanW || NanD));
+        CHECK(B.WinPred == A.WinPred && B.DrawPred == A.DrawPred && B.BackedWin == A.BackedWin && B.BackedDraw == A.BackedDraw);
+        for (uint16_t I = 0; I < N; ++I) CHECK(B.Edges[I].Move == A.Edges[I].Move && B.Edges[I].Probability == A.Edges[I].Probability);
+    }
+    return 0;
 }
 
 int main(int argc, char** argv) {
@@ -127,6 +202,7 @@ int main(int argc, char** argv) {
         std::printf("reachable policy slots: %zu\n", Seen.size());
         CHECK(*Seen.rbegin() < 2187 && Seen.size() > 1500);  // most slots are reachable
     }
+    if (feedChecks()) return 1;  // mcts_feed.h == setEvaluation + sort + updateAncestors of the reference
     std::printf("host_unit ok\n");
     return 0;
 }
