@@ -13,6 +13,7 @@
 #include "eval_cache.h"
 #include "infer_b200.h"
 #include "leaf_pipeline.h"
+#include "leaf_queue.h"
 #include "move_index.h"
 
 using namespace nshogi::engine;
@@ -62,7 +63,7 @@ static T* pinned(size_t N) {
 }
 
 int main(int argc, char** argv) {
-    int Channels = 128, Blocks = 10, B = 256, Repeat = 300, Slots = 4;
+    int Channels = 128, Blocks = 10, B = 256, Repeat = 300, Slots = 4, QueueThreads = 4;
     bool SelfCheck = false;
     std::string Weights;  // NSBW file (nshogi-engine_b200/weights_io.py); empty = seeded random-init net
     for (int I = 1; I < argc; ++I) {
@@ -73,6 +74,7 @@ int main(int argc, char** argv) {
         else if (A == "--batch") B = next();
         else if (A == "--repeat") Repeat = next();
         else if (A == "--slots") Slots = next();
+        else if (A == "--queue-threads") QueueThreads = next();
         else if (A == "--selfcheck") SelfCheck = true;
         else if (A == "--weights" && I + 1 < argc) Weights = argv[++I];
     }
@@ -147,6 +149,61 @@ int main(int argc, char** argv) {
     Ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
     const double PipeRate = (double)B * Repeat / Ms * 1000.0;
 
+    // --- the MCTS-side assembly: QueueThreads search threads write their leaves straight into the open pinned
+    //     batch (leaf_queue.h: one CAS per leaf, no mutex / allocation / copy; replaces evaluationqueue.cc +
+    //     EvaluationWorker::getBatch), this thread seals, submits and feeds ----------------------------------------
+    double QueueRate = 0.0;
+    bool QueueOk = true;
+    std::size_t QueueFed = 0;
+    if (QueueThreads > 0) {
+        evaluate::LeafQueue Queue(&Pipe);
+        const std::size_t Target = (std::size_t)B * Repeat;
+        std::atomic<std::size_t> Pushed{0};
+        std::atomic<bool> Stop{false};
+        const nsb_position P0 = startpos();
+        auto feed = [&](evaluate::LeafPipeline::Slot& S, std::size_t Row, void* User) {
+            const uint32_t Bg = S.MoveOffsets[Row], En = S.MoveOffsets[Row + 1];
+            // every leaf is the start position: the most probable move's row index must be the same everywhere,
+            // and the handle must be the one pushed with the row
+            QueueOk = QueueOk && En - Bg == Moves.size() && S.Order[Bg] == S.Order[0] && User == (void*)(uintptr_t)(Row + 1);
+            ++QueueFed;
+        };
+        Queue.open(feed);
+        std::vector<std::thread> Search;
+        for (int T = 0; T < QueueThreads; ++T)
+            Search.emplace_back([&]() {
+                evaluate::LeafQueue::Ticket Tk;
+                while (!Stop.load(std::memory_order_relaxed)) {
+                    if (Pushed.load(std::memory_order_relaxed) >= Target) break;
+                    if (!Queue.reserve((uint16_t)Moves.size(), nullptr, &Tk)) {
+                        std::this_thread::yield();
+                        continue;
+                    }
+                    Tk.S->Positions[Tk.Row] = P0;
+                    std::memcpy(Tk.S->MoveIndices + Tk.MoveBegin, Moves.data(), Moves.size() * sizeof(uint16_t));
+                    Tk.S->Hashes[Tk.Row] = (uint64_t)Tk.Row;
+                    Queue.setUser(Tk, (void*)(uintptr_t)(Tk.Row + 1));
+                    Queue.publish(Tk);
+                    Pushed.fetch_add(1, std::memory_order_relaxed);
+                }
+            });
+        T0 = std::chrono::steady_clock::now();
+        std::size_t Submitted = 0;
+        while (Submitted < Target) {
+            if (Queue.openRows() < (std::size_t)B && Pushed.load(std::memory_order_relaxed) < Target) {
+                std::this_thread::yield();
+                continue;
+            }
+            Submitted += Queue.submitOpen(/*FromPositions=*/true, NSB_DECODE_PROBS, /*UseCache=*/false, /*Ranked=*/true, feed);
+        }
+        Stop.store(true);
+        for (auto& Th : Search) Th.join();
+        Queue.drain(true, NSB_DECODE_PROBS, false, true, feed);
+        Ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+        QueueRate = (double)QueueFed / Ms * 1000.0;
+        QueueOk = QueueOk && QueueFed >= Target;
+    }
+
     // --- self-check: fused probabilities == softmax of the Infer contract's logits at the same slots -----
     double MaxDiff = 0.0, SumErr = 0.0;
     bool RowsEqual = true, OrderOk = true;
@@ -177,11 +234,11 @@ int main(int argc, char** argv) {
     }
     mcts::EvalCacheB200::EvalInfo Info;
     const bool CacheHit = Cache.load(SlotHashes[0][B / 2], &Info) && Info.NumMoves == Moves.size();
-    const bool Ok = MaxDiff < 1e-5 && SumErr < 1e-5 && RowsEqual && CacheHit && OrderOk;
+    const bool Ok = MaxDiff < 1e-5 && SumErr < 1e-5 && RowsEqual && CacheHit && OrderOk && QueueOk;
     std::printf("{\"batch\": %d, \"net\": \"%dx%d\", \"infer_blocking_evals_per_s\": %.1f, \"pipeline_evals_per_s\": %.1f, "
-                "\"legal_moves\": %zu, \"max_prob_diff\": %.3g, \"row_sum_err\": %.3g, \"rows_identical\": %s, "
+                "\"queue_evals_per_s\": %.1f, \"queue_threads\": %d, \"queue_ok\": %s, \"legal_moves\": %zu, \"max_prob_diff\": %.3g, \"row_sum_err\": %.3g, \"rows_identical\": %s, "
                 "\"cache_rows_stored\": %zu, \"cache_hit\": %s, \"order_ok\": %s, \"ok\": %s}\n",
-                B, Exec.net().blocks, Exec.net().channels, BlockingRate, PipeRate, Moves.size(), MaxDiff, SumErr, RowsEqual ? "true" : "false",
+                B, Exec.net().blocks, Exec.net().channels, BlockingRate, PipeRate, QueueRate, QueueThreads, QueueOk ? "true" : "false", Moves.size(), MaxDiff, SumErr, RowsEqual ? "true" : "false",
                 Stored, CacheHit ? "true" : "false", OrderOk ? "true" : "false", Ok ? "true" : "false");
     nsb_host_free(Features); nsb_host_free(Policy); nsb_host_free(Win); nsb_host_free(Draw);
     return (SelfCheck && !Ok) ? 1 : 0;
