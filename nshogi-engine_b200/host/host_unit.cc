@@ -19,7 +19,11 @@
 #include <cmath>
 #include <random>
 
+#include <atomic>
+#include <thread>
+
 #include "eval_cache.h"
+#include "leaf_queue.h"
 #include "mcts_feed.h"
 #include "move_index.h"
 #include "onnx_import.h"
@@ -105,6 +109,76 @@ struct MockNode {
     void updateAncestors(float W, float D) { BackedWin = W; BackedDraw = D; }
 };
 
+// ---- LeafQueue protocol on plain memory: `--queue-stress THREADS LEAVES` (built with -fsanitize=thread by
+//      tests/test_host_cpp.py).  Every pushed leaf must come back exactly once, in a batch whose CSR is consistent.
+struct FakePipeline {
+    struct Slot {
+        std::vector<uint32_t> MoveOffsets;
+        std::vector<uint16_t> MoveIndices;
+        std::vector<uint64_t> Hashes;
+        std::size_t Count = 0;
+    };
+    std::vector<Slot> Slots;
+    std::size_t BatchMax, Next = 0, Batches = 0;
+    FakePipeline(std::size_t NumSlots, std::size_t B) : Slots(NumSlots), BatchMax(B) {
+        for (auto& S : Slots) {
+            S.MoveOffsets.resize(B + 1);
+            S.MoveIndices.resize(B * NSB_MAX_LEGAL_MOVES);
+            S.Hashes.resize(B);
+        }
+    }
+    std::size_t numSlots() const { return Slots.size(); }
+    std::size_t batchMax() const { return BatchMax; }
+    Slot& acquire(std::size_t* K) { *K = Next; Next = (Next + 1) % Slots.size(); return Slots[*K]; }
+    void submit(std::size_t K, std::size_t Rows, bool, int, bool, bool) { Slots[K].Count = Rows; ++Batches; }
+    Slot& collect(std::size_t K) { return Slots[K]; }
+};
+
+static int queueStress(int Threads, std::size_t Leaves) {
+    FakePipeline Pipe(3, 64);
+    evaluate::BasicLeafQueue<FakePipeline> Queue(&Pipe);
+    std::vector<uint8_t> SeenLeaf(Leaves, 0);
+    std::size_t Fed = 0;
+    bool Ok = true;
+    auto feed = [&](FakePipeline::Slot& S, std::size_t Row, void* User) {
+        const std::size_t Id = (std::size_t)(uintptr_t)User - 1;
+        const uint32_t Bg = S.MoveOffsets[Row], En = S.MoveOffsets[Row + 1];
+        Ok = Ok && Id < Leaves && !SeenLeaf[Id] && S.Hashes[Row] == Id * 2654435761ull && En - Bg == 1 + Id % 7;
+        for (uint32_t J = Bg; Ok && J < En; ++J) Ok = S.MoveIndices[J] == (uint16_t)(Id + J - Bg);
+        if (Id < Leaves) SeenLeaf[Id] = 1;
+        ++Fed;
+    };
+    Queue.open(feed);
+    std::atomic<std::size_t> NextLeaf{0};
+    std::vector<std::thread> Search;
+    for (int T = 0; T < Threads; ++T)
+        Search.emplace_back([&]() {
+            for (;;) {
+                const std::size_t Id = NextLeaf.fetch_add(1);
+                if (Id >= Leaves) return;
+                const uint16_t N = (uint16_t)(1 + Id % 7);
+                evaluate::BasicLeafQueue<FakePipeline>::Ticket Tk;
+                while (!Queue.reserve(N, (void*)(uintptr_t)(Id + 1), &Tk)) std::this_thread::yield();
+                for (uint16_t J = 0; J < N; ++J) Tk.S->MoveIndices[Tk.MoveBegin + J] = (uint16_t)(Id + J);
+                Tk.S->Hashes[Tk.Row] = Id * 2654435761ull;
+                Queue.publish(Tk);
+            }
+        });
+    std::size_t Submitted = 0;
+    while (Submitted < Leaves) {
+        if (Queue.openRows() < 48 && NextLeaf.load() < Leaves + (std::size_t)Threads) {  // partial batches too
+            std::this_thread::yield();
+            continue;
+        }
+        Submitted += Queue.submitOpen(true, 0, false, true, feed);
+    }
+    for (auto& Th : Search) Th.join();
+    Queue.drain(true, 0, false, true, feed);
+    std::printf("queue stress: %zu leaves fed in %zu batches by %d threads: %s\n", Fed, Pipe.Batches, Threads,
+                Ok && Fed == Leaves ? "ok" : "FAIL");
+    return Ok && Fed == Leaves ? 0 : 1;
+}
+
 static int feedChecks() {
     std::mt19937_64 Rng(7);
     for (int Trial = 0; Trial < 200; ++Trial) {
@@ -143,6 +217,7 @@ static int feedChecks() {
 }
 
 int main(int argc, char** argv) {
+    if (argc >= 4 && std::strcmp(argv[1], "--queue-stress") == 0) return queueStress(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]));
     if (argc >= 4 && std::strcmp(argv[1], "--onnx-blob") == 0) return onnxBlob(argv[2], argv[3]);
     if (argc >= 3 && std::strcmp(argv[1], "--cache-trace") == 0) return cacheTrace((std::size_t)std::atoi(argv[2]));
     {   // cache: store/load, 164-move cap, refresh-only on duplicate, the reference's replacement order

@@ -27,9 +27,12 @@ namespace nshogi {
 namespace engine {
 namespace evaluate {
 
-class LeafQueue {
+// PipelineT: LeafPipeline, or anything with its Slot / numSlots / batchMax / acquire / submit / collect surface
+// (host_unit.cc runs the protocol on plain memory under ThreadSanitizer).
+template <typename PipelineT>
+class BasicLeafQueue {
  public:
-    using Slot = LeafPipeline::Slot;
+    using Slot = typename PipelineT::Slot;
 
     struct Ticket {
         Slot* S = nullptr;
@@ -37,7 +40,7 @@ class LeafQueue {
         uint32_t MoveBegin = 0;  // fill S->MoveIndices[MoveBegin .. MoveBegin + NumMoves)
     };
 
-    explicit LeafQueue(LeafPipeline* P) : Pipe(P), Users(P->numSlots()), Counts(P->numSlots(), 0) {
+    explicit BasicLeafQueue(PipelineT* P) : Pipe(P), Users(P->numSlots()), Counts(P->numSlots(), 0) {
         for (auto& U : Users) U.resize(P->batchMax(), nullptr);
     }
 
@@ -116,7 +119,7 @@ class LeafQueue {
         Counts[K] = 0;
     }
 
-    LeafPipeline* Pipe;
+    PipelineT* Pipe;
     std::vector<std::vector<void*>> Users;  // per slot, per row: the caller's handle (the reference queues Node*)
     std::vector<std::size_t> Counts;        // rows of the batch each slot holds (0 once fed)
     std::size_t OpenIndex = 0;
@@ -125,6 +128,8 @@ class LeafQueue {
     std::atomic<uint64_t> Cursor{1ull << 63};  // sealed until open()
     std::atomic<uint32_t> Published{0};
 };
+
+using LeafQueue = BasicLeafQueue<LeafPipeline>;
 
 } // namespace evaluate
 } // namespace engine

@@ -92,3 +92,25 @@ def test_selfplay_sim_with_device_cache_gpu(built):
     rec = json.loads(out.stdout.strip().splitlines()[-1])
     assert rec["nan_rows"] == 0 and rec["evals"] > 10000 and rec["records"] > 1000
     assert 0.35 <= rec["cache_hit_rate"] <= 0.6, rec["cache_hit_rate"]
+
+
+def test_leaf_queue_protocol_under_thread_sanitizer(built, tmp_path):
+    """leaf_queue.h (lock-free in-place batch assembly, replaces reference src/mcts/evaluationqueue.cc + getBatch):
+    6 filling threads, 60,000 leaves through 3 slots of 64 rows on plain memory - every leaf comes back exactly once
+    with its handle, hash and CSR span - built with -fsanitize=thread (the reference's own race-detection practice,
+    SURVEY.md §5), which must stay silent."""
+    inc = ["-I" + HOST, "-I" + os.path.join(HOST, "shim"), "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "oracle", "shim")]
+    exe = str(tmp_path / "unit_tsan")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", *inc, "-o", exe,
+                        os.path.join(HOST, "host_unit.cc"), "-lpthread"], capture_output=True, text=True, timeout=300)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe, "--queue-stress", "6", "60000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "60000 leaves fed" in out.stdout and ": ok" in out.stdout
+    assert "ThreadSanitizer" not in out.stderr
+    out = subprocess.run([os.path.join(built, "nsb_host_unit"), "--queue-stress", "8", "300000"], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0 and ": ok" in out.stdout
