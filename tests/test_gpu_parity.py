@@ -703,3 +703,9 @@ def test_rank_order_nan_rows_and_cache_hits(nb, orc, synth):
         assert first[3].sum() == 0 and np.array_equal(again[3].astype(bool), cacheable)
         assert np.array_equal(again[0].view(np.uint32), first[0].view(np.uint32))
         assert np.array_equal(again[1], first[1]) and np.array_equal(first[1], orc.rank_rows(first[0], off, first[2]))
+
+
+def test_graft_entry_smoke():
+    """The driver's smoke() entry point itself (it pins the launch count of the fused path)."""
+    import __graft_entry__ as graft
+    graft.smoke()
