@@ -709,3 +709,47 @@ def test_graft_entry_smoke():
     """The driver's smoke() entry point itself (it pins the launch count of the fused path)."""
     import __graft_entry__ as graft
     graft.smoke()
+
+
+def test_maximum_batch_size(nb, orc, synth):
+    """batch_max = 65,535 (the reference's uint16_t BatchSizeMax, src/infer/trt.cc:52) in one call: 32,768 position
+    pairs over 148 CTAs = 222 passes.  Checksum-of-rows property: every position is one of 16 base positions with
+    one of 16 move lists, so every output row must equal, bit for bit, the row of its (position, list) pair from a
+    16 x 16 reference batch; rank orders included."""
+    desc = nb.net_desc(128, 1)
+    blob = nb.random_blob(desc, 3)
+    n, base = 65535, 16
+    pos16 = synth.random_positions(base, seed=77)
+    off16, idx16 = synth.random_legal_moves(base, seed=77, edge_rows=False)
+    rng = np.random.default_rng(5)
+
+    def build(which_pos, which_list):
+        cnt = np.diff(off16)[which_list].astype(np.int64)
+        off = np.zeros(len(which_pos) + 1, dtype=np.uint32)
+        off[1:] = np.cumsum(cnt)
+        src = np.repeat(off16[:-1][which_list].astype(np.int64), cnt) + (np.arange(int(off[-1])) - np.repeat(off[:-1].astype(np.int64), cnt))
+        return np.ascontiguousarray(pos16[which_pos]), off, np.ascontiguousarray(idx16[src])
+
+    def run(ctx, p, off, idx):
+        m = len(p)
+        legal, order = np.zeros(int(off[-1]), dtype=np.float32), np.zeros(int(off[-1]), dtype=np.uint16)
+        win, draw, flag = np.zeros(m, dtype=np.float32), np.zeros(m, dtype=np.float32), np.ones(m, dtype=np.uint8)
+        ctx.eval_request_async(0, m, off, idx, nb.DECODE_PROBS, legal, win, draw, positions=p, order_out=order, nan_flag=flag)
+        ctx.await_(0)
+        return legal, order, win, draw, flag
+
+    with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+        gp, gl = np.divmod(np.arange(base * base), base)
+        ref_p, ref_off, ref_idx = build(gp, gl)
+        r_legal, r_order, r_win, r_draw, _ = run(ctx, ref_p, ref_off, ref_idx)
+        wp, wl = rng.integers(0, base, size=n), rng.integers(0, base, size=n)
+        p, off, idx = build(wp, wl)
+        legal, order, win, draw, flag = run(ctx, p, off, idx)
+    assert not flag.any()
+    pair = wp * base + wl
+    assert np.array_equal(win, r_win[pair]) and np.array_equal(draw, r_draw[pair])
+    cnt = np.diff(off).astype(np.int64)
+    src = np.repeat(ref_off[:-1][pair].astype(np.int64), cnt) + (np.arange(int(off[-1])) - np.repeat(off[:-1].astype(np.int64), cnt))
+    assert np.array_equal(legal.view(np.uint32), r_legal[src].view(np.uint32))
+    assert np.array_equal(order, r_order[src])
+    assert np.array_equal(r_order, orc.rank_rows(r_legal, ref_off))
