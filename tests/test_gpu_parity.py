@@ -711,12 +711,15 @@ def test_graft_entry_smoke():
     graft.smoke()
 
 
-def test_maximum_batch_size(nb, orc, synth):
+@pytest.mark.parametrize("channels,slots", [(128, 1), (128, 2), (256, 1)])
+def test_maximum_batch_size(nb, orc, synth, monkeypatch, channels, slots):
     """batch_max = 65,535 (the reference's uint16_t BatchSizeMax, src/infer/trt.cc:52) in one call: 32,768 position
     pairs over 148 CTAs = 222 passes.  Checksum-of-rows property: every position is one of 16 base positions with
     one of 16 move lists, so every output row must equal, bit for bit, the row of its (position, list) pair from a
-    16 x 16 reference batch; rank orders included."""
-    desc = nb.net_desc(128, 1)
+    16 x 16 reference batch; rank orders included.  All three trunk kernels (classic, duo, pair)."""
+    monkeypatch.delenv("NSB_TRUNK128", raising=False)
+    monkeypatch.delenv("NSB_TRUNK256", raising=False)
+    desc = nb.net_desc(channels, 1)
     blob = nb.random_blob(desc, 3)
     n, base = 65535, 16
     pos16 = synth.random_positions(base, seed=77)
@@ -738,7 +741,7 @@ def test_maximum_batch_size(nb, orc, synth):
         ctx.await_(0)
         return legal, order, win, draw, flag
 
-    with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+    with nb.Context(desc, batch_max=n, slots=slots, blob=blob) as ctx:
         gp, gl = np.divmod(np.arange(base * base), base)
         ref_p, ref_off, ref_idx = build(gp, gl)
         r_legal, r_order, r_win, r_draw, _ = run(ctx, ref_p, ref_off, ref_idx)
