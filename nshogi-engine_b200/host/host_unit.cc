@@ -62,8 +62,7 @@ static int onnxBlob(const char* InPath, const char* OutPath) {
     std::vector<float> Blob;
     infer::onnx::NetShape S;
     try {
-        infer::onnx::Graph G = infer::onnx::parseModel(Bytes);
-        S = infer::onnx::toBlob(G, &Blob);
+        S = infer::onnx::importModel(Bytes, &Blob);
     } catch (const infer::onnx::Error& E) {
         std::printf("rejected: %s\n", E.what());
         return 3;

@@ -74,8 +74,7 @@ class B200 : public Infer {
                 Blob.resize(Floats);
                 std::memcpy(Blob.data(), Bytes.data() + 24, Floats * sizeof(float));
             } else {
-                onnx::Graph G = onnx::parseModel(Bytes);  // throws onnx::Error (a std::runtime_error)
-                const onnx::NetShape S = onnx::toBlob(G, &Blob);
+                const onnx::NetShape S = onnx::importModel(Bytes, &Blob);  // throws onnx::Error (a std::runtime_error)
                 FileDesc = nsb_net_desc{S.InChannels, S.Channels, S.Blocks, S.Hidden};
                 if (Blob.size() != nsb_weight_blob_floats(&FileDesc))
                     throw std::runtime_error("B200::load: " + Path + ": the executor does not support this net shape");

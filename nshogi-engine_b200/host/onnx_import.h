@@ -627,6 +627,19 @@ inline NetShape toBlob(Graph& G, std::vector<float>* Blob) {
     return S;
 }
 
+// parseModel + toBlob for a file image; whatever a damaged file trips (a missing node input, an absurd length)
+// surfaces as onnx::Error like an unsupported graph does.
+inline NetShape importModel(const std::vector<uint8_t>& Data, std::vector<float>* Blob) {
+    try {
+        Graph G = parseModel(Data);
+        return toBlob(G, Blob);
+    } catch (const Error&) {
+        throw;
+    } catch (const std::exception& E) {
+        throw Error(std::string("onnx: malformed file: ") + E.what());
+    }
+}
+
 } // namespace onnx
 } // namespace infer
 } // namespace engine

@@ -70,6 +70,12 @@ def _fields(buf: bytes):
         yield fno, wt, v
 
 
+def _s(v) -> str:
+    """Names are matched, never interpreted: bytes that are not UTF-8 survive as surrogates (the C++ reader compares
+    raw bytes)."""
+    return v.decode("utf-8", "surrogateescape")
+
+
 def _signed(v: int) -> int:
     return v - (1 << 64) if v >= (1 << 63) else v
 
@@ -146,7 +152,7 @@ def _parse_tensor(buf: bytes) -> Tuple[str, np.ndarray]:
         elif fno == 2:
             dtype = v
         elif fno == 8:
-            name = v.decode()
+            name = _s(v)
         elif fno == 9:
             raw = v
         elif fno == 4:
@@ -187,7 +193,7 @@ def _parse_attr(buf: bytes) -> Tuple[str, object]:
     ints: List[int] = []
     for fno, wt, v in _fields(buf):
         if fno == 1:
-            name = v.decode()
+            name = _s(v)
         elif fno == 20:
             atype = v
         elif fno == 2:
@@ -221,25 +227,25 @@ def _parse_node(buf: bytes) -> Node:
     n = Node("", [], [])
     for fno, _, v in _fields(buf):
         if fno == 1:
-            n.inputs.append(v.decode())
+            n.inputs.append(_s(v))
         elif fno == 2:
-            n.outputs.append(v.decode())
+            n.outputs.append(_s(v))
         elif fno == 3:
-            n.name = v.decode()
+            n.name = _s(v)
         elif fno == 4:
-            n.op = v.decode()
+            n.op = _s(v)
         elif fno == 5:
             k, val = _parse_attr(v)
             n.attrs[k] = val
         elif fno == 7 and v not in (b"", b"ai.onnx"):
-            raise ValueError(f"node {n.name!r}: operator domain {v.decode()!r} is not supported")
+            raise ValueError(f"node {n.name!r}: operator domain {_s(v)!r} is not supported")
     return n
 
 
 def _value_info_name(buf: bytes) -> str:
     for fno, _, v in _fields(buf):
         if fno == 1:
-            return v.decode()
+            return _s(v)
     return ""
 
 
@@ -252,7 +258,7 @@ def parse_model(data: bytes) -> Graph:
             dom, ver = "", 0
             for f2, _, v2 in _fields(v):
                 if f2 == 1:
-                    dom = v2.decode()
+                    dom = _s(v2)
                 elif f2 == 2:
                     ver = v2
             if dom in ("", "ai.onnx"):
@@ -511,9 +517,20 @@ def blob_from_graph(g: Graph) -> Tuple[dict, np.ndarray]:
     return {"channels": C, "blocks": blocks, "value_hidden": H, "in_channels": cin}, blob
 
 
+def blob_from_bytes(data: bytes) -> Tuple[dict, np.ndarray]:
+    """parse_model + blob_from_graph; a damaged file is a ValueError like an unsupported one, never a stray
+    IndexError / struct.error from the decoder."""
+    try:
+        return blob_from_graph(parse_model(data))
+    except ValueError:
+        raise
+    except (IndexError, KeyError, AttributeError, struct.error, UnicodeDecodeError, OverflowError, MemoryError, TypeError) as e:
+        raise ValueError(f"malformed ONNX file: {type(e).__name__}: {e}") from e
+
+
 def read_onnx(path: str) -> Tuple[dict, np.ndarray]:
     with open(path, "rb") as f:
-        return blob_from_graph(parse_model(f.read()))
+        return blob_from_bytes(f.read())
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -142,7 +142,7 @@ def _cpp_blob(path, tmp_path):
     import subprocess
     unit = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nshogi-engine_b200", "host", "nsb_host_unit")
     out = str(tmp_path / "blob.bin")
-    r = subprocess.run([unit, "--onnx-blob", path, out], capture_output=True, text=True, timeout=60)
+    r = subprocess.run([unit, "--onnx-blob", path, out], capture_output=True, text=True, errors="replace", timeout=60)
     if r.returncode != 0:
         return r.returncode, r.stdout, None, None
     raw = open(out, "rb").read()
@@ -176,3 +176,37 @@ def test_cpp_reader_of_infer_b200_load_matches_python(pkg, oi, nb, golden_dir, t
     assert rc == 3 and "trunk output must feed" in out
     open(p, "wb").write(b"\x0a\x03abc")
     assert _cpp_blob(p, tmp_path)[0] == 3
+
+
+def test_damaged_files_are_rejected_not_crashing(oi, golden_dir, tmp_path):
+    """Byte-level fuzz of the torch-exported file: truncations, flipped bytes, spliced garbage.  Both readers must
+    either load the file (a flipped weight byte is still a valid model) or reject it with their error type -
+    ValueError / exit code 3 - never crash, hang or raise something else."""
+    data = open(os.path.join(golden_dir, "resnet_torch_export.onnx"), "rb").read()
+    rng = np.random.default_rng(11)
+    cases = [data[:k] for k in (0, 1, 7, 100, 5000, len(data) - 1)]
+    for _ in range(40):
+        b = bytearray(data)
+        # mutate the structural part (the graph's nodes sit at the front of the file) and anywhere
+        for _ in range(int(rng.integers(1, 6))):
+            k = int(rng.integers(0, 4000 if rng.random() < 0.7 else len(b)))
+            b[k] = int(rng.integers(0, 256))
+        cases.append(bytes(b))
+    for _ in range(10):
+        k = int(rng.integers(0, len(data)))
+        cases.append(data[:k] + bytes(rng.integers(0, 256, size=64, dtype=np.uint8)) + data[k:])
+    loaded = rejected = 0
+    for i, c in enumerate(cases):
+        try:
+            oi.blob_from_bytes(c)
+            py_ok = True
+        except ValueError:
+            py_ok = False
+        p = str(tmp_path / "fuzz.onnx")
+        open(p, "wb").write(c)
+        rc, out, _, _ = _cpp_blob(p, tmp_path)
+        assert rc in (0, 3), (i, rc, out)
+        assert (rc == 0) == py_ok, (i, rc, py_ok, out)      # the two readers agree on what is loadable
+        loaded += py_ok
+        rejected += not py_ok
+    assert rejected >= 10
