@@ -756,3 +756,13 @@ def test_maximum_batch_size(nb, orc, synth, monkeypatch, channels, slots):
     assert np.array_equal(legal.view(np.uint32), r_legal[src].view(np.uint32))
     assert np.array_equal(order, r_order[src])
     assert np.array_equal(r_order, orc.rank_rows(r_legal, ref_off))
+
+
+def test_concurrent_contexts_soak_short():
+    """tools/soak.py for 8 s: four host threads, four contexts (classic + shared cache, an executor attached to it, duo
+    with 4 slots, the 256-channel pair kernel) on one GPU at once, every result bit-identical to its first."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "soak.py"), "8"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "soak ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
