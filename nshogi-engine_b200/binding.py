@@ -401,7 +401,7 @@ class Context:
 
     def debug_trunk_timeline(self, slot, d_features, n, positions=False):
         nl = 2 * self.desc.blocks + 2
-        out = np.zeros(nl * 4 + 16, dtype=np.uint64)
+        out = np.zeros(nl * 4 + 16 + 3 * 1024, dtype=np.uint64)
         fn = lib().nsb_debug_trunk_timeline_positions if positions else lib().nsb_debug_trunk_timeline
         _check(fn(self._h, slot, _ptr(d_features), n, out.ctypes.data, out.size), "nsb_debug_trunk_timeline")
         return out[:nl * 4].reshape(nl, 4), out[nl * 4:]

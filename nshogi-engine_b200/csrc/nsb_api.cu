@@ -73,7 +73,10 @@ struct nsb_ctx {
     bool use_ts = false;       // 128-channel trunk with the weights fed through tensor memory (trunk_ts.cu)
     bool direct_io = false;    // kernels read / write the caller's page-locked buffers themselves (no copy nodes)
     bool fuse_pack = true;     // packed positions are expanded in the trunk prologue (NSB_FUSE_PACK=0: separate pack kernel)
-    int duo_ctas = 0;          // > 0: the two-CTAs-per-SM 128-channel trunk (trunk_duo.cu), co-resident CTAs per SM
+    int duo_ctas = 0;          // > 0: the two-CTAs-per-SM 128-channel trunk (trunk_duo.cu) is available, co-resident CTAs per SM
+    bool duo_always = false;   // every launch uses it (multi-slot pipeline, or forced); otherwise it is chosen per batch size
+    nsb::DeviceNet net_duo{};  // the same net with the weight stream in trunk_duo.cu's order (when both kernels are loaded)
+    void* d_duo_tiles = nullptr;
     nsb::DeviceCache cache{};  // device-resident evaluation cache (nsb_cache_create / nsb_cache_attach)
     bool cache_owned = false;  // false: the table belongs to another ctx of the same device (nsb_cache_attach)
     nsb_net_desc desc{};
@@ -186,7 +189,11 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     const char* t128 = getenv("NSB_TRUNK128");
     const bool is128 = net->channels == 128;
     const bool use_ts = is128 && t128 && strcmp(t128, "ts") == 0;
-    const bool want_duo = is128 && !use_ts && (t128 ? strcmp(t128, "duo") == 0 : slots >= 2);
+    // Unforced, a 128-channel context loads BOTH kernels: a multi-slot pipeline always launches the duo kernel; a
+    // one-slot context picks per batch - trunk_fused.cu while the batch fits one wave of one CTA per SM (shortest
+    // launch), trunk_duo.cu (two co-resident CTAs per SM share the tensor pipe) where that is faster (use_duo()).
+    const bool want_duo = is128 && !use_ts && (t128 ? strcmp(t128, "duo") == 0 : true);
+    const bool duo_always = want_duo && (t128 ? true : slots >= 2);
     if (use_ts && (rc = trunk_ts_prepare())) return rc;
     int duo_ctas = 0;
     if (want_duo && (rc = trunk_duo_prepare(&duo_ctas))) return rc;
@@ -201,6 +208,8 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     c->max_pairs = max_pairs;
     c->use_ts = use_ts;
     c->duo_ctas = duo_ctas;
+    c->duo_always = duo_always;
+    if (const char* dc = getenv("NSB_DUO_CTAS")) c->duo_ctas = duo_ctas > 0 ? atoi(dc) : 0;  // diagnostics: force the grid cap
     if (const char* fp = getenv("NSB_FUSE_PACK")) c->fuse_pack = strcmp(fp, "0") != 0;
     // A one-slot context is the latency configuration (one batch at a time: every copy node is serial
     // time) and defaults to direct I/O; a multi-slot pipeline overlaps its copies with other batches'
@@ -244,6 +253,7 @@ void nsb_destroy(nsb_ctx* c) {
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (void* p : c->d_weights) cudaFree(p);
+    cudaFree(c->d_duo_tiles);
     if (c->cache_owned) {
         cudaFree(c->cache.entries);
         cudaFree(c->cache.meta);
@@ -288,10 +298,17 @@ int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
     std::vector<uint16_t> tiles((size_t)stages * kStageBytes / 2);
     std::vector<float> bias((size_t)NL * C), fc1t((size_t)81 * H), fc1b(H), fc2(2 * (size_t)H), fc2b(2);
     pack_weights(d, blob, tiles.data(), bias.data(), fc1t.data(), fc1b.data(), fc2.data(), fc2b.data());
+    const bool ts_only = c->use_ts || (c->duo_ctas > 0 && c->duo_always);
+    std::vector<uint16_t> ts_tiles;
+    int ts_stages = 0;
     if (c->use_ts || c->duo_ctas > 0) {  // same bias / FC arrays; the conv weights as a stream of 4 KB K = 16 steps
-        stages = ts_steps_per_pass(d);
-        tiles.assign((size_t)stages * 2048, 0);
-        pack_weights_ts(d, blob, tiles.data());
+        ts_stages = ts_steps_per_pass(d);
+        ts_tiles.assign((size_t)ts_stages * 2048, 0);
+        pack_weights_ts(d, blob, ts_tiles.data());
+        if (ts_only) {
+            stages = ts_stages;
+            tiles.swap(ts_tiles);
+        }
     }
     const void* src[6] = {tiles.data(), bias.data(), fc1t.data(), fc1b.data(), fc2.data(), fc2b.data()};
     const size_t bytes[6] = {tiles.size() * 2, bias.size() * 4, fc1t.size() * 4, fc1b.size() * 4, fc2.size() * 4,
@@ -317,8 +334,31 @@ int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
     n.fc1b = static_cast<const float*>(c->d_weights[3]);
     n.fc2 = static_cast<const float*>(c->d_weights[4]);
     n.fc2b = static_cast<const float*>(c->d_weights[5]);
+    if (c->duo_ctas > 0 && !c->duo_always) {  // both kernels: a second weight stream beside the first
+        cudaFree(c->d_duo_tiles);
+        c->d_duo_tiles = nullptr;
+        NSB_CUDA(cudaMalloc(&c->d_duo_tiles, ts_tiles.size() * 2));
+        NSB_CUDA(cudaMemcpy(c->d_duo_tiles, ts_tiles.data(), ts_tiles.size() * 2, cudaMemcpyHostToDevice));
+        c->net_duo = n;
+        c->net_duo.stages_per_pass = ts_stages;
+        c->net_duo.tiles = static_cast<const uint8_t*>(c->d_duo_tiles);
+    } else {
+        c->net_duo = n;
+    }
     c->loaded = true;
     return 0;
+}
+
+// One-slot 128-channel contexts hold both trunk kernels and choose per batch.  Launch durations measured on B200
+// (tools/residency.py, tools/sweep.py): trunk_fused.cu 0.129 ms per wave of 148 CTAs (2 positions each);
+// trunk_duo.cu 0.157 ms while at most one CTA per SM is resident, 0.215 ms per wave of 296 co-resident CTAs.
+static bool use_duo(const nsb_ctx* c, int n) {
+    if (c->duo_ctas <= 0) return false;
+    if (c->duo_always) return true;
+    const int groups = (n + 1) / 2, sms = c->num_sms;
+    const double classic = 0.129 * ((groups + sms - 1) / sms);
+    const double duo = groups <= sms ? 0.157 : 0.215 * ((groups + 2 * sms - 1) / (2 * sms));
+    return duo < classic;
 }
 
 /* ---- shared launch helper ------------------------------------------------------------------ */
@@ -333,7 +373,7 @@ static int run_trunk(nsb_ctx* c, Slot& s, const EvalArgs& a) {
         NSB_CUDA(cudaEventRecord(s.ev[s.ev_used], s.stream));
     }
     int k = c->max_pairs > 0 ? launch_trunk_pair(c->net, a, c->max_pairs, s.stream)
-            : c->duo_ctas > 0 ? launch_trunk_duo(c->net, a, c->num_sms, c->duo_ctas, s.stream)
+            : use_duo(c, a.n) ? launch_trunk_duo(c->net_duo, a, c->num_sms, c->duo_ctas, s.stream)
             : c->use_ts      ? launch_trunk_ts(c->net, a, c->num_sms, s.stream)
                              : launch_trunk_fused(c->net, a, c->num_sms, s.stream);
     if (k < 0) return k;
@@ -666,7 +706,13 @@ int nsb_cache_clear(nsb_ctx* c) {
 const char* nsb_trunk_kernel_name(nsb_ctx* c) {
     if (!c) return "";
     if (c->max_pairs > 0) return "trunk_pair_kernel (256 ch, cta_group::2 CTA pair)";
-    if (c->duo_ctas > 0) return "trunk_duo_kernel (128 ch, weights via TMEM, 2 CTAs per SM)";
+    if (c->duo_ctas > 0 && c->duo_always) {
+        static thread_local char name[96];
+        snprintf(name, sizeof name, "trunk_duo_kernel (128 ch, weights via TMEM, %d CTA%s per SM)", c->duo_ctas,
+                 c->duo_ctas == 1 ? "" : "s");
+        return name;
+    }
+    if (c->duo_ctas > 0) return "trunk_fused_kernel<128> (trunk_duo_kernel for batches where two CTAs per SM are faster)";
     if (c->use_ts) return "trunk_ts_kernel (128 ch, weights via TMEM, experimental)";
     return c->desc.channels == 128 ? "trunk_fused_kernel<128>" : "trunk_fused_kernel<256>";
 }
@@ -907,7 +953,8 @@ static int debug_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_fe
         set_error("nsb_debug_trunk_timeline: bad arguments or weights not loaded");
         return NSB_ERR_INVALID;
     }
-    const size_t need = (size_t)c->net.num_layers * 4 + 16;
+    // 4 per layer + 16 phase stamps + per CTA {SM id, globaltimer at start, at end} for up to 1,024 CTAs (trunk_duo.cu)
+    const size_t need = (size_t)c->net.num_layers * 4 + 16 + 3 * 1024;
     if (max_stamps < need) {
         set_error("nsb_debug_trunk_timeline: need room for %zu stamps", need);
         return NSB_ERR_INVALID;

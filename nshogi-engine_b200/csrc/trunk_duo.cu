@@ -180,6 +180,16 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
         (int)blockIdx.x < groups ? (groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int NL = net.num_layers;
     const bool stamp = a.timeline && blockIdx.x == 0;  // diagnostics: tools/timeline.py
+    // diagnostics: where and when every CTA ran (co-residency of the two CTAs of an SM: tools/residency.py)
+    unsigned long long* cta_rec = (a.timeline && blockIdx.x < 1024) ? a.timeline + 4 * NL + 16 + 3 * blockIdx.x : nullptr;
+    if (cta_rec && threadIdx.x == 0) {
+        unsigned smid;
+        unsigned long long t;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        cta_rec[0] = smid;
+        cta_rec[1] = t;
+    }
 
     // ---- one-time setup ---------------------------------------------------------------------
     for (int i = threadIdx.x; i < 2 * G::BUF_BYTES / 16; i += G::THREADS)
@@ -396,6 +406,11 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
     // ---- teardown -------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    if (cta_rec && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        cta_rec[2] = t;
+    }
     if (warp == 8) {
         __syncwarp();
         tmem_dealloc(tmem_base, G::TMEM_COLS);
@@ -415,7 +430,11 @@ int trunk_duo_prepare(int* ctas_per_sm) {
         set_error("trunk duo: cannot configure the kernel: %s (is this an sm_100a device?)", cudaGetErrorString(e));
         return NSB_ERR_NO_DEVICE;
     }
-    if (ctas_per_sm) *ctas_per_sm = nb;
+    // The occupancy calculator answers 1 for this kernel, the hardware co-schedules 2 (tools/residency.py: 296 CTAs on
+    // 148 SMs, lifetimes overlapping 99 %): the footprint is built for two - 2 x (111 KB + 1 KB) of shared memory,
+    // 2 x 256 TMEM columns, 2 x 30 K registers (static_asserts in DuoGeom).  An oversized grid would only cost a
+    // second wave, an undersized one halves the kernel's reason to exist.
+    if (ctas_per_sm) *ctas_per_sm = nb < 2 ? 2 : nb;
     return 0;
 }
 
