@@ -80,7 +80,7 @@ while "classic+cache" not in handles:
     time.sleep(0.01)
 threads = [t1,
            threading.Thread(target=worker, args=("classic+attached", 128, 10, 1, 130), kwargs=dict(cached_with=handles["classic+cache"], ranked=True)),
-           threading.Thread(target=worker, args=("duo", 128, 10, 4, 256), kwargs=dict(ranked=True)),
+           threading.Thread(target=worker, args=("duo", 128, 10, 4, int(sys.argv[2]) if len(sys.argv) > 2 else 700), kwargs=dict(ranked=True)),
            threading.Thread(target=worker, args=("pair", 256, 6, 2, 301))]
 for t in threads[1:]:
     t.start()
