@@ -788,3 +788,15 @@ def test_concurrent_contexts_soak_short():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "soak.py"), "8"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "soak ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_api_modes_differential_fuzz_short():
+    """tools/fuzz_modes.py for 10 s: random nets / batch sizes / move lists (rows of 0, 1, 164, 165, 593 moves); bitboards in
+    (staged) == packed positions in (direct, ranked) == through the cache (misses) == from the cache (hits), bit for bit,
+    rank orders equal to the oracle's.  (2,708 configurations in a 150 s run while developing.)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_modes.py"), "10", "7"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
