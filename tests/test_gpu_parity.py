@@ -800,3 +800,39 @@ def test_api_modes_differential_fuzz_short():
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_modes.py"), "10", "7"], capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_request_validation(nb, synth):
+    """nsb_eval_request_async reports malformed requests instead of launching: both / neither input kind, a cache request
+    without a cache, a bad decode mode, offsets that do not start at 0 or exceed 593 moves per position."""
+    desc = nb.net_desc(128, 1)
+    n = 4
+    pos = synth.random_positions(n, seed=1)
+    fb = np.zeros(n * 86, dtype=nb.FEATURE_BITBOARD)
+    off, idx = synth.random_legal_moves(n, seed=1, edge_rows=False)
+    legal = np.zeros(int(off[-1]), dtype=np.float32)
+    win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    hashes = np.arange(n, dtype=np.uint64)
+    with nb.Context(desc, batch_max=n, seed=1) as ctx:
+        ok = dict(positions=pos)
+        ctx.eval_request_async(0, n, off, idx, nb.DECODE_PROBS, legal, win, draw, **ok)
+        ctx.await_(0)
+        l0 = ctx.launch_count()
+        for bad in (dict(positions=pos, features=fb), dict(), dict(positions=pos, hashes=hashes)):
+            with pytest.raises(nb.NsbError):
+                ctx.eval_request_async(0, n, off, idx, nb.DECODE_PROBS, legal, win, draw, **bad)
+        with pytest.raises(nb.NsbError):
+            ctx.eval_request_async(0, n, off, idx, 7, legal, win, draw, **ok)
+        off_bad = off.copy()
+        off_bad[0] = 1
+        with pytest.raises(nb.NsbError):
+            ctx.eval_request_async(0, n, off_bad, idx, nb.DECODE_PROBS, legal, win, draw, **ok)
+        off_big = np.array([0, 594, 594, 594, 594], dtype=np.uint32) * np.uint32(n)   # > n * 593 moves in total
+        with pytest.raises(nb.NsbError):
+            ctx.eval_request_async(0, n, off_big, np.zeros(int(off_big[-1]), dtype=np.uint16), nb.DECODE_PROBS,
+                                   np.zeros(int(off_big[-1]), dtype=np.float32), win, draw, **ok)
+        with pytest.raises(nb.NsbError):
+            ctx.eval_request_async(0, n + 1, off, idx, nb.DECODE_PROBS, legal, win, draw, **ok)    # > batch_max
+        assert ctx.launch_count() == l0                                                            # nothing was launched
+        ctx.eval_request_async(0, 0, off, idx, nb.DECODE_PROBS, legal, win, draw, **ok)            # n = 0 is a no-op
+        assert ctx.launch_count() == l0
