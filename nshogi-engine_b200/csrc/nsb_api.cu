@@ -357,8 +357,9 @@ static bool use_duo(const nsb_ctx* c, int n) {
     if (c->duo_always) return true;
     const int groups = (n + 1) / 2, sms = c->num_sms;
     const double classic = 0.129 * ((groups + sms - 1) / sms);
-    const double duo = groups <= sms ? 0.157 : 0.215 * ((groups + 2 * sms - 1) / (2 * sms));
-    return duo < classic;
+    const int full = groups / (2 * sms), rest = groups % (2 * sms);  // waves of co-resident pairs, then the remainder
+    const double duo = 0.215 * full + (rest == 0 ? 0.0 : rest <= sms ? 0.157 : 0.215);
+    return duo < classic;  // in effect: more than one CTA per SM worth of position pairs
 }
 
 /* ---- shared launch helper ------------------------------------------------------------------ */
