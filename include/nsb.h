@@ -309,7 +309,11 @@ uint64_t nsb_launch_count(nsb_ctx* ctx);
 int nsb_host_alloc(void** out, size_t bytes);
 int nsb_host_free(void* p);
 /* Page-lock (or adopt, if the caller already did: cudaHostRegister in evaluator.cc:95-106) a buffer the
- * caller owns, so that calls using it qualify for NSB_IO_DIRECT below. */
+ * caller owns, so that calls using it qualify for NSB_IO_DIRECT below.  Returns NSB_OK when this call locked the
+ * range (undo with nsb_host_unregister), NSB_HOST_ALREADY_LOCKED (> 0, not an error) when it already was - by the
+ * caller or by an earlier call - and < 0 on failure (the buffer still works, through the staged path).
+ * nsb_host_unregister forgets the range and unlocks it only if nsb_host_register locked it. */
+#define NSB_HOST_ALREADY_LOCKED 1
 int nsb_host_register(void* p, size_t bytes);
 int nsb_host_unregister(void* p);
 

@@ -186,8 +186,12 @@ class DecodeRequest(C.Structure):
                 ("hit_flag", _P)]
 
 
-def host_register(arr: np.ndarray):
-    _check(lib().nsb_host_register(arr.ctypes.data, arr.nbytes), "nsb_host_register")
+def host_register(arr: np.ndarray) -> bool:
+    """True if this call page-locked the array, False if it already was (NSB_HOST_ALREADY_LOCKED)."""
+    rc = lib().nsb_host_register(arr.ctypes.data, arr.nbytes)
+    if rc < 0:
+        _check(rc, "nsb_host_register")
+    return rc == 0
 
 
 def host_unregister(arr: np.ndarray):

@@ -35,7 +35,12 @@ void set_error(const char* fmt, ...) {
 // every device's address space at their host address, so a kernel can read its inputs from them and
 // write its results into them over PCIe without a copy node on the stream ("direct" I/O mode).
 static std::mutex g_host_mu;
-static std::map<uintptr_t, size_t> g_host_allocs;  // base -> bytes
+struct HostRange {
+    size_t bytes = 0;
+    bool direct = true;       // mapped at its host address: kernels may dereference the host pointer
+    bool registered = false;  // page-locked by nsb_host_register (cudaHostUnregister is ours to call)
+};
+static std::map<uintptr_t, HostRange> g_host_allocs;  // base -> range
 
 static bool host_mapped(const void* p, size_t bytes) {
     if (p == nullptr) return false;
@@ -44,7 +49,7 @@ static bool host_mapped(const void* p, size_t bytes) {
     auto it = g_host_allocs.upper_bound(a);
     if (it == g_host_allocs.begin()) return false;
     --it;
-    return a + bytes <= it->first + it->second;
+    return it->second.direct && a + bytes <= it->first + it->second.bytes;
 }
 
 struct Slot {
@@ -1090,7 +1095,7 @@ int nsb_host_alloc(void** out, size_t bytes) {
     if (!out) return NSB_ERR_INVALID;
     NSB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
     std::lock_guard<std::mutex> lock(g_host_mu);
-    g_host_allocs[(uintptr_t)*out] = bytes ? bytes : 1;
+    g_host_allocs[(uintptr_t)*out] = HostRange{bytes ? bytes : 1, true, false};
     return 0;
 }
 int nsb_host_free(void* p) {
@@ -1106,30 +1111,38 @@ int nsb_host_register(void* p, size_t bytes) {
         set_error("nsb_host_register: bad arguments");
         return NSB_ERR_INVALID;
     }
-    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);  // evaluator.cc:95-106
-    if (e == cudaErrorHostMemoryAlreadyRegistered) {
-        cudaGetLastError();  // the caller pinned it (the reference's Evaluator does): adopt it
+    if (host_mapped(p, bytes)) return NSB_HOST_ALREADY_LOCKED;  // nsb_host_alloc memory, or registered before
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);  // evaluator.cc:95-106
+    const bool adopted = e == cudaErrorHostMemoryAlreadyRegistered;  // the caller pinned it (the reference's Evaluator does)
+    if (adopted) {
+        cudaGetLastError();
     } else if (e != cudaSuccess) {
+        cudaGetLastError();
         set_error("cudaHostRegister failed: %s", cudaGetErrorString(e));
         return NSB_ERR_CUDA;
     }
     // direct I/O needs the device to reach the range at its host address (true on unified-addressing
     // x86 hosts); otherwise the range stays page-locked but calls using it take the staged path
     void* dp = nullptr;
-    if (cudaHostGetDevicePointer(&dp, p, 0) == cudaSuccess && dp == p) {
+    const bool direct = cudaHostGetDevicePointer(&dp, p, 0) == cudaSuccess && dp == p;
+    if (!direct) cudaGetLastError();
+    if (direct || !adopted) {
         std::lock_guard<std::mutex> lock(g_host_mu);
-        g_host_allocs[(uintptr_t)p] = bytes;
-    } else {
-        cudaGetLastError();
+        g_host_allocs[(uintptr_t)p] = HostRange{bytes, direct, !adopted};
     }
-    return 0;
+    return adopted ? NSB_HOST_ALREADY_LOCKED : NSB_OK;
 }
 int nsb_host_unregister(void* p) {
+    bool ours = false;
     {
         std::lock_guard<std::mutex> lock(g_host_mu);
-        g_host_allocs.erase((uintptr_t)p);
+        auto it = g_host_allocs.find((uintptr_t)p);
+        if (it != g_host_allocs.end()) {
+            ours = it->second.registered;
+            g_host_allocs.erase(it);
+        }
     }
-    NSB_CUDA(cudaHostUnregister(p));
+    if (ours) NSB_CUDA(cudaHostUnregister(p));  // an adopted range stays locked: its owner unlocks it
     return 0;
 }
 int nsb_set_io_mode(nsb_ctx* c, int mode) {

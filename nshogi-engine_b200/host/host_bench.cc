@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "eval_cache.h"
@@ -64,7 +65,7 @@ static T* pinned(size_t N) {
 
 int main(int argc, char** argv) {
     int Channels = 128, Blocks = 10, B = 256, Repeat = 300, Slots = 4, QueueThreads = 4;
-    bool SelfCheck = false;
+    bool SelfCheck = false, MallocBuffers = false;
     std::string Weights;  // NSBW file (nshogi-engine_b200/weights_io.py); empty = seeded random-init net
     for (int I = 1; I < argc; ++I) {
         const std::string A = argv[I];
@@ -76,6 +77,7 @@ int main(int argc, char** argv) {
         else if (A == "--slots") Slots = next();
         else if (A == "--queue-threads") QueueThreads = next();
         else if (A == "--selfcheck") SelfCheck = true;
+        else if (A == "--malloc-buffers") MallocBuffers = true;  // plain page-aligned memory: infer::B200 page-locks it itself
         else if (A == "--weights" && I + 1 < argc) Weights = argv[++I];
     }
     if (nsb_device_count() < 1) {
@@ -87,10 +89,15 @@ int main(int argc, char** argv) {
     Exec.resetGPU();
 
     // --- Evaluator-style pinned batch buffers (reference src/evaluate/evaluator.cc:85-106) -----------
-    auto* Features = pinned<nshogi::ml::FeatureBitboard>((size_t)B * NSB_FEATURE_CHANNELS);
-    float* Policy = pinned<float>((size_t)B * NSB_POLICY_SIZE);
-    float* Win = pinned<float>(B);
-    float* Draw = pinned<float>(B);
+    auto buffer = [&](auto* Tag, std::size_t N) {
+        using T = std::remove_pointer_t<decltype(Tag)>;
+        if (!MallocBuffers) return pinned<T>(N);
+        return static_cast<T*>(std::aligned_alloc(4096, ((N * sizeof(T) + 4095) / 4096) * 4096));
+    };
+    auto* Features = buffer((nshogi::ml::FeatureBitboard*)nullptr, (size_t)B * NSB_FEATURE_CHANNELS);
+    float* Policy = buffer((float*)nullptr, (size_t)B * NSB_POLICY_SIZE);
+    float* Win = buffer((float*)nullptr, (size_t)B);
+    float* Draw = buffer((float*)nullptr, (size_t)B);
     {   // startpos x B (batchsize.cc:47-59); stage 1 runs on the device, features come back once
         std::vector<nsb_position> Pos(B, startpos());
         void *DPos = nullptr, *DFeat = nullptr;
@@ -236,10 +243,12 @@ int main(int argc, char** argv) {
     const bool CacheHit = Cache.load(SlotHashes[0][B / 2], &Info) && Info.NumMoves == Moves.size();
     const bool Ok = MaxDiff < 1e-5 && SumErr < 1e-5 && RowsEqual && CacheHit && OrderOk && QueueOk;
     std::printf("{\"batch\": %d, \"net\": \"%dx%d\", \"infer_blocking_evals_per_s\": %.1f, \"pipeline_evals_per_s\": %.1f, "
-                "\"queue_evals_per_s\": %.1f, \"queue_threads\": %d, \"queue_ok\": %s, \"legal_moves\": %zu, \"max_prob_diff\": %.3g, \"row_sum_err\": %.3g, \"rows_identical\": %s, "
+                "\"queue_evals_per_s\": %.1f, \"queue_threads\": %d, \"queue_ok\": %s, \"io_mode\": \"%s\", \"legal_moves\": %zu, \"max_prob_diff\": %.3g, \"row_sum_err\": %.3g, \"rows_identical\": %s, "
                 "\"cache_rows_stored\": %zu, \"cache_hit\": %s, \"order_ok\": %s, \"ok\": %s}\n",
-                B, Exec.net().blocks, Exec.net().channels, BlockingRate, PipeRate, QueueRate, QueueThreads, QueueOk ? "true" : "false", Moves.size(), MaxDiff, SumErr, RowsEqual ? "true" : "false",
+                B, Exec.net().blocks, Exec.net().channels, BlockingRate, PipeRate, QueueRate, QueueThreads, QueueOk ? "true" : "false", nsb_io_mode(Exec.context()) == NSB_IO_DIRECT ? "direct" : "staged", Moves.size(), MaxDiff, SumErr, RowsEqual ? "true" : "false",
                 Stored, CacheHit ? "true" : "false", OrderOk ? "true" : "false", Ok ? "true" : "false");
-    nsb_host_free(Features); nsb_host_free(Policy); nsb_host_free(Win); nsb_host_free(Draw);
+    if (!MallocBuffers) {
+        nsb_host_free(Features); nsb_host_free(Policy); nsb_host_free(Win); nsb_host_free(Draw);
+    }  // (malloc'ed buffers are released at exit, after the executor has unlocked them in its destructor)
     return (SelfCheck && !Ok) ? 1 : 0;
 }

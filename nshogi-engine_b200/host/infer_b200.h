@@ -40,6 +40,8 @@ class B200 : public Infer {
         check(nsb_create(&Ctx_, GPUId, BatchSizeMax, Slots, &Desc_), "nsb_create");
     }
     ~B200() override {
+        if (Ctx_) nsb_await(Ctx_, 0);
+        for (void* P : Registered_) nsb_host_unregister(P);
         nsb_destroy(Ctx_);
     }
     B200(const B200&) = delete;
@@ -110,8 +112,27 @@ class B200 : public Infer {
         check(nsb_bind_thread(Ctx_), "nsb_bind_thread");
     }
 
+    // The Infer contract gives the executor four caller-owned arrays that stay the same for its lifetime and are
+    // sized for BatchSizeMax (src/evaluate/evaluator.cc:85-106).  The first time a set of arrays is seen it is
+    // page-locked - or adopted, if the caller's Evaluator already did that - so that a one-slot executor works on
+    // them directly (NSB_IO_DIRECT: no copy nodes).  Arrays that cannot be registered simply take the staged path.
+    void setAutoRegister(bool On) {
+        AutoRegister_ = On;
+    }
+
     void computeNonBlocking(const ml::FeatureBitboard* Features, std::size_t BatchSize, float* DstPolicy,
                             float* DstWinRate, float* DstDrawRate) override {
+        if (AutoRegister_ && (Features != Seen_[0] || DstPolicy != Seen_[1] || DstWinRate != Seen_[2] || DstDrawRate != Seen_[3])) {
+            Seen_[0] = Features;
+            Seen_[1] = DstPolicy;
+            Seen_[2] = DstWinRate;
+            Seen_[3] = DstDrawRate;
+            const std::size_t B = BatchSizeM;
+            const std::size_t Bytes[4] = {B * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard), B * NSB_POLICY_SIZE * sizeof(float),
+                                          B * sizeof(float), B * sizeof(float)};
+            for (int I = 0; I < 4; ++I)
+                if (nsb_host_register(const_cast<void*>(Seen_[I]), Bytes[I]) == NSB_OK) Registered_.push_back(const_cast<void*>(Seen_[I]));
+        }
         check(nsb_eval_async(Ctx_, 0, reinterpret_cast<const nsb_feature_bitboard*>(Features), BatchSize, DstPolicy,
                              DstWinRate, DstDrawRate),
               "nsb_eval_async");
@@ -154,6 +175,9 @@ class B200 : public Infer {
     nsb_net_desc Desc_;
     nsb_ctx* Ctx_ = nullptr;
     bool HasCache_ = false;
+    bool AutoRegister_ = true;
+    const void* Seen_[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<void*> Registered_;
 };
 
 } // namespace infer

@@ -114,3 +114,19 @@ def test_leaf_queue_protocol_under_thread_sanitizer(built, tmp_path):
     out = subprocess.run([os.path.join(built, "nsb_host_unit"), "--queue-stress", "8", "300000"], capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0 and ": ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_infer_contract_on_plain_buffers_is_page_locked_by_the_executor(built):
+    """The unmodified Infer contract with buffers the executor has never seen (plain page-aligned malloc, as an
+    Evaluator built without CUDA_ENABLED would hand over): infer::B200 page-locks them on first sight, a one-slot
+    executor then runs direct I/O on them; same self-check as with nsb_host_alloc memory, and faster than staged."""
+    rates = {}
+    for flag in ([], ["--malloc-buffers"]):
+        out = subprocess.run([os.path.join(built, "nsb_host_bench"), "--selfcheck", "--slots", "1", "--repeat", "200", *flag],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        assert line["ok"] and line["io_mode"] == "direct"
+        rates[bool(flag)] = line["infer_blocking_evals_per_s"]
+    assert rates[True] > 0.9 * rates[False]      # page-locked by the executor == allocated page-locked
