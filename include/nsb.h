@@ -122,11 +122,31 @@ int nsb_eval_async(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* features,
  * src/mcts/feedworker.cc:100-127, or Frame::setEvaluation, src/selfplay/frame.cc:96-118):
  * the caller supplies CSR legal-move policy indices (move_off[n+1], move_idx[move_off[n]],
  * values from ml::getMoveIndex) and receives per-move outputs instead of dense logits.
- *   mode NSB_DECODE_PROBS : softmax over the legal moves (T=1), 1-move rows = 1.0
- *   mode NSB_DECODE_LOGITS: raw gathered logits (self-play caches logits, frame.cc:110-114)
- * nan_flag[i] = 1 when any gathered logit / win / draw is NaN (math.h:23-39 semantics). */
+ *   mode NSB_DECODE_PROBS : MCTS flavour (FeedWorker::feedResult, feedworker.cc:100-136): softmax over the
+ *                           legal moves (T=1); a 1-move row is 1.0 without a gather (:101-103); with a
+ *                           cache the PROBABILITIES are stored (:134-135)
+ *   mode NSB_DECODE_LOGITS: raw gathered logits only (the first half of Frame::setEvaluation, frame.cc:96-114)
+ *   mode NSB_DECODE_BOTH  : self-play flavour, the whole of Frame::setEvaluation<false> (frame.cc:93-118) in one
+ *                           launch: gather -> the RAW LOGITS go to the cache (:110-114) -> softmax (no 1-move
+ *                           shortcut; skipped for rows flagged NSB_ROW_SKIP_SOFTMAX = the Gumbel root, :116-118)
+ *                           -> legal_out; nsb_decode_request::logits_out (optional) also returns the raw logits.
+ *                           Rows served from the cache take the same route from the stored logits.  The
+ *                           Dirichlet mix at the AlphaZero root (:121-133) is host/selfplay_feed.h.
+ *   | NSB_DECODE_NAN_FALLBACK : feedResult<NaNFallbackEnabled = true>.  The reference ships it OFF
+ *                           (src/context.h:103), and so does mode & 0x100 == 0: NaNs flow through the softmax,
+ *                           nan_flag[i] = 0, rows are stored in the cache whatever they hold.  With the bit set:
+ *                             - a NaN among the gathered logits of a row with >= 2 moves replaces every legal
+ *                               logit by 1 before the softmax, i.e. a uniform row (feedworker.cc:106-118);
+ *                             - a NaN win / draw rate leaves the row's softmax alone (:58-85: the caller replaces
+ *                               the value from the parent node, host/mcts_feed.h) and is returned as is;
+ *                             - nan_flag[i] = 1 for either (NaNFound), and such rows are not stored (:134).
+ *                           NaN test: bit pattern, src/math/math.h:23-39. */
 #define NSB_DECODE_PROBS 0
 #define NSB_DECODE_LOGITS 1
+#define NSB_DECODE_BOTH 2
+#define NSB_DECODE_MODE_MASK 0xFF
+#define NSB_DECODE_NAN_FALLBACK 0x100
+#define NSB_ROW_SKIP_SOFTMAX 1 /* nsb_decode_request::row_flags bit: Gumbel root (frame.cc:116-118) */
 int nsb_eval_decode_async(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* features, size_t n,
                           const uint32_t* move_off, const uint16_t* move_idx, int mode,
                           float* legal_out, float* win, float* draw, uint8_t* nan_flag);
@@ -157,7 +177,8 @@ int nsb_eval_positions_decode_async(nsb_ctx* ctx, int slot, const nsb_position* 
  *                          decreasing probability, src/mcts/node.h:163-168, on a feed thread for every leaf
  *                          (feedworker.cc:129) - so the caller writes its edges in search order in one
  *                          pass instead of sorting them (std::sort leaves the order of ties unspecified;
- *                          here it is defined).  Rows served from the cache are ranked too. */
+ *                          here it is defined).  Rows served from the cache are ranked too.  A row whose
+ *                          values contain a NaN (possible without NSB_DECODE_NAN_FALLBACK) gets the identity. */
 typedef struct nsb_decode_request {
     const nsb_feature_bitboard* features; /* [n][86] or NULL                      */
     const nsb_position* positions;        /* [n]     or NULL                      */
@@ -165,13 +186,15 @@ typedef struct nsb_decode_request {
     const uint64_t* hashes;               /* [n] or NULL (no cache)               */
     const uint32_t* move_off;             /* [n+1] CSR offsets                    */
     const uint16_t* move_idx;             /* [move_off[n]] policy slots           */
-    int mode;                             /* NSB_DECODE_PROBS / NSB_DECODE_LOGITS */
+    int mode;                             /* NSB_DECODE_* [| NSB_DECODE_NAN_FALLBACK] */
     float* legal_out;                     /* [move_off[n]]                        */
     uint16_t* order_out;                  /* [move_off[n]] or NULL                */
     float* win;                           /* [n]                                  */
     float* draw;                          /* [n]                                  */
     uint8_t* nan_flag;                    /* [n] or NULL                          */
     uint8_t* hit_flag;                    /* [n] or NULL (cached requests only)   */
+    const uint8_t* row_flags;             /* [n] or NULL: NSB_ROW_* bits (NSB_DECODE_BOTH)            */
+    float* logits_out;                    /* [move_off[n]] or NULL: raw logits too (NSB_DECODE_BOTH) */
 } nsb_decode_request;
 int nsb_eval_request_async(nsb_ctx* ctx, int slot, const nsb_decode_request* request);
 
@@ -207,14 +230,22 @@ int nsb_decode_device(nsb_ctx* ctx, int slot, const float* d_policy, const float
                       const uint16_t* d_move_idx, int mode, float* d_legal_out,
                       uint8_t* d_nan_flag);
 
+/* The same with the per-row flags and the second output of NSB_DECODE_BOTH (d_row_flags, d_logits_out optional). */
+int nsb_decode_device_ex(nsb_ctx* ctx, int slot, const float* d_policy, const float* d_win, const float* d_draw,
+                         size_t n, const uint32_t* d_move_off, const uint16_t* d_move_idx, int mode,
+                         const uint8_t* d_row_flags, float* d_legal_out, float* d_logits_out, uint8_t* d_nan_flag);
+
 /* ---- device-resident evaluation cache --------------------------------- */
 
 /* Replaces EvalCache::EvalCache(MemorySize MiB) (reference src/mcts/evalcache.cc:17-47) with a
  * table in HBM: rows of <= 164 legal-move values + win + draw keyed by the 64-bit state hash,
  * bundles of 3 entries in recency order, bundle = hash % NumBundle, try-lock per bundle (a busy
  * bundle drops the operation, evalcache.cc:58-62,127-131).  One cache per ctx, shared by its slots.
- * A cache holds whatever the decode mode of the launches that fill it produced (probabilities for
- * MCTS, feedworker.cc:135; raw logits for self-play, frame.cc:110-114): use one mode per cache. */
+ * A cache holds what the decode mode of the launches that fill it stores: probabilities for NSB_DECODE_PROBS
+ * (MCTS, feedworker.cc:135), raw logits for NSB_DECODE_LOGITS / NSB_DECODE_BOTH (self-play, frame.cc:110-114);
+ * a hit is post-processed by the mode of the request that probes (BOTH: softmax of the stored logits), so a
+ * cache is filled and probed with one mode - as in the reference, where the MCTS manager and the self-play
+ * frames each own theirs. */
 int nsb_cache_create(nsb_ctx* ctx, size_t memory_mb);
 int nsb_cache_clear(nsb_ctx* ctx);
 /* The reference has ONE EvalCache per Manager, shared by all evaluation workers (src/mcts/manager.cc:202-206)
@@ -312,7 +343,12 @@ int nsb_host_free(void* p);
  * caller owns, so that calls using it qualify for NSB_IO_DIRECT below.  Returns NSB_OK when this call locked the
  * range (undo with nsb_host_unregister), NSB_HOST_ALREADY_LOCKED (> 0, not an error) when it already was - by the
  * caller or by an earlier call - and < 0 on failure (the buffer still works, through the staged path).
- * nsb_host_unregister forgets the range and unlocks it only if nsb_host_register locked it. */
+ * nsb_host_unregister forgets the range and unlocks it only if nsb_host_register locked it (nsb_host_alloc
+ * memory is left alone).  A registered or adopted range must outlive every call that uses it; whoever made the
+ * library know a range calls nsb_host_unregister before the memory is unlocked / freed by its owner, or at the
+ * latest when the executor goes (infer::B200 does both for the Infer contract's arrays).  An adopted range is
+ * re-validated with the driver whenever it is registered again, so an address the caller has freed and the
+ * allocator has reused is never taken for page-locked memory. */
 #define NSB_HOST_ALREADY_LOCKED 1
 int nsb_host_register(void* p, size_t bytes);
 int nsb_host_unregister(void* p);

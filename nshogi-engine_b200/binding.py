@@ -22,6 +22,9 @@ MAX_LEGAL_MOVES = 593
 CACHE_MAX_MOVES = 164
 DECODE_PROBS = 0
 DECODE_LOGITS = 1
+DECODE_BOTH = 2            # self-play: raw logits to the cache, probabilities out (frame.cc:93-118)
+DECODE_NAN_FALLBACK = 0x100  # feedResult<NaNFallbackEnabled = true>; off by default like src/context.h:103
+ROW_SKIP_SOFTMAX = 1       # row flag: Gumbel root (frame.cc:116-118)
 
 # 16-byte packed plane == nshogi ml::FeatureBitboard (reference src/cuda/extractbit.cu:20-37)
 FEATURE_BITBOARD = np.dtype([("lo", "<u8"), ("hi", "<u8")])
@@ -67,6 +70,7 @@ SIGNATURES = {
     "nsb_extract_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_int, C.c_int, _P]),
     "nsb_pack_positions_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P]),
     "nsb_decode_device": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P, _P, C.c_int, _P, _P]),
+    "nsb_decode_device_ex": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_size_t, _P, _P, C.c_int, _P, _P, _P, _P]),
     "nsb_cache_create": (C.c_int, [_P, C.c_size_t]),
     "nsb_cache_clear": (C.c_int, [_P]),
     "nsb_cache_num_bundles": (C.c_uint64, [_P]),
@@ -183,7 +187,7 @@ class DecodeRequest(C.Structure):
     """include/nsb.h nsb_decode_request"""
     _fields_ = [("features", _P), ("positions", _P), ("n", C.c_size_t), ("hashes", _P), ("move_off", _P), ("move_idx", _P),
                 ("mode", C.c_int), ("legal_out", _P), ("order_out", _P), ("win", _P), ("draw", _P), ("nan_flag", _P),
-                ("hit_flag", _P)]
+                ("hit_flag", _P), ("row_flags", _P), ("logits_out", _P)]
 
 
 def host_register(arr: np.ndarray) -> bool:
@@ -365,6 +369,11 @@ class Context:
         _check(lib().nsb_decode_device(self._h, slot, _ptr(d_policy), _ptr(d_win), _ptr(d_draw), n, _ptr(d_off),
                                        _ptr(d_idx), mode, _ptr(d_legal), _ptr(d_flag)), "nsb_decode_device")
 
+    def decode_device_ex(self, slot, d_policy, d_win, d_draw, n, d_off, d_idx, mode, d_row_flags, d_legal, d_logits, d_flag):
+        _check(lib().nsb_decode_device_ex(self._h, slot, _ptr(d_policy), _ptr(d_win), _ptr(d_draw), n, _ptr(d_off),
+                                          _ptr(d_idx), mode, _ptr(d_row_flags), _ptr(d_legal), _ptr(d_logits), _ptr(d_flag)),
+               "nsb_decode_device_ex")
+
     # -- device-resident evaluation cache ------------------------------------------------------------
     def cache_create(self, memory_mb: int):
         _check(lib().nsb_cache_create(self._h, memory_mb), "nsb_cache_create")
@@ -411,10 +420,12 @@ class Context:
         return out[:nl * 4].reshape(nl, 4), out[nl * 4:]
 
     def eval_request_async(self, slot, n, move_off, move_idx, mode, legal_out, win, draw, features=None, positions=None,
-                           hashes=None, order_out=None, nan_flag=None, hit_flag=None):
-        """nsb_eval_request_async: the general fused call (cache when `hashes`, rank order when `order_out`)."""
+                           hashes=None, order_out=None, nan_flag=None, hit_flag=None, row_flags=None, logits_out=None):
+        """nsb_eval_request_async: the general fused call (cache when `hashes`, rank order when `order_out`,
+        per-row flags and raw logits beside the probabilities for DECODE_BOTH)."""
         r = DecodeRequest(_ptr(features), _ptr(positions), n, _ptr(hashes), _ptr(move_off), _ptr(move_idx), mode,
-                          _ptr(legal_out), _ptr(order_out), _ptr(win), _ptr(draw), _ptr(nan_flag), _ptr(hit_flag))
+                          _ptr(legal_out), _ptr(order_out), _ptr(win), _ptr(draw), _ptr(nan_flag), _ptr(hit_flag),
+                          _ptr(row_flags), _ptr(logits_out))
         _check(lib().nsb_eval_request_async(self._h, slot, C.byref(r)), "nsb_eval_request_async")
 
     def cache_attach(self, owner: "Context"):

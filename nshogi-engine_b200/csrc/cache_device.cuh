@@ -75,10 +75,14 @@ __device__ __forceinline__ void cache_unlock_warp(uint32_t* word, uint32_t meta,
     if (lane == 0) atomicExch(word, meta & ~kCacheLockBit);
 }
 
-// evalcache.cc:49-121.  `row` = n values (global or shared memory).  Returns true when the entry is
-// present afterwards (stored or refreshed), false when dropped (n > 164 or bundle busy).
-__device__ __forceinline__ bool cache_store_warp(const DeviceCache& c, uint64_t hash, int n, const float* row, float win,
-                                                 float draw, int lane) {
+// evalcache.cc:49-121.  The row's n values come from `get(k)` = element lane + 32 k (k < 6: n <= 164), so that
+// a decode can store from its registers.  Returns true when the entry is present afterwards (stored or
+// refreshed), false when dropped (n > 164 or bundle busy).
+constexpr int kCacheRowPerLane = (NSB_CACHE_MAX_MOVES + 31) / 32;  // 6 row elements per lane at most
+
+template <typename Get>
+__device__ __forceinline__ bool cache_store_warp_from(const DeviceCache& c, uint64_t hash, int n, Get get, float win,
+                                                      float draw, int lane) {
     if (n > NSB_CACHE_MAX_MOVES) return false;
     const unsigned long long bundle = hash % c.num_bundles;
     uint32_t* word = c.meta + bundle;
@@ -101,7 +105,11 @@ __device__ __forceinline__ bool cache_store_warp(const DeviceCache& c, uint64_t 
     const int target = free_mask ? __ffs(free_mask) - 1 : 2;  // first unused entry, else the last one of the list
     const uint32_t slot = cache_order_slot(meta, target);
     CacheEntry* e = base + slot;
-    for (int j = lane; j < n; j += 32) e->policy[j] = row[j];
+#pragma unroll
+    for (int k = 0; k < kCacheRowPerLane; ++k) {
+        const int j = lane + 32 * k;
+        if (j < n) e->policy[j] = get(k);
+    }
     if (lane == 0) {
         e->hash = hash;
         e->n = (uint32_t)n;
@@ -112,15 +120,20 @@ __device__ __forceinline__ bool cache_store_warp(const DeviceCache& c, uint64_t 
     return true;
 }
 
+// the same with the row in (global or shared) memory
+__device__ __forceinline__ bool cache_store_warp(const DeviceCache& c, uint64_t hash, int n, const float* row, float win,
+                                                 float draw, int lane) {
+    return cache_store_warp_from(c, hash, n, [&](int k) { return row[lane + 32 * k]; }, win, draw, lane);
+}
+
 // evalcache.cc:123-169 + the caller's move-count check (searchworker.cc:545-556): returns true and
 // fills row[0..expected_n), *win, *draw when an entry with this hash exists AND has expected_n moves.
 // A hash match with a different move count still refreshes the entry's recency, as in the reference.
 constexpr int kCacheProbeTries = 64;
-constexpr int kCacheRowPerLane = (NSB_CACHE_MAX_MOVES + 31) / 32;  // 6 row elements per lane at most
 
-// `vals` (optional): lane l also keeps row element l + 32 k in vals[k] (for ranking the row without re-reading it)
-__device__ __forceinline__ bool cache_load_warp(const DeviceCache& c, uint64_t hash, int expected_n, float* row, float* win,
-                                                float* draw, int lane, float* vals = nullptr) {
+// The row comes back in registers: lane l holds element l + 32 k in vals[k] (0 beyond expected_n).
+__device__ __forceinline__ bool cache_load_warp(const DeviceCache& c, uint64_t hash, int expected_n, float (&vals)[kCacheRowPerLane],
+                                                float* win, float* draw, int lane) {
     const unsigned long long bundle = hash % c.num_bundles;
     uint32_t* word = c.meta + bundle;
     uint32_t meta;
@@ -145,15 +158,10 @@ __device__ __forceinline__ bool cache_load_warp(const DeviceCache& c, uint64_t h
     const bool ok = (int)n_e == expected_n;
     if (ok) {
         const CacheEntry* e = base + slot;
-        if (vals != nullptr) {
 #pragma unroll
-            for (int k = 0; k < kCacheRowPerLane; ++k) {
-                const int j = lane + 32 * k;
-                vals[k] = 0.f;
-                if (j < expected_n) row[j] = vals[k] = __ldcg(&e->policy[j]);
-            }
-        } else {
-            for (int j = lane; j < expected_n; j += 32) row[j] = __ldcg(&e->policy[j]);
+        for (int k = 0; k < kCacheRowPerLane; ++k) {
+            const int j = lane + 32 * k;
+            vals[k] = j < expected_n ? __ldcg(&e->policy[j]) : 0.f;
         }
         *win = __ldcg(&e->win);
         *draw = __ldcg(&e->draw);

@@ -35,10 +35,14 @@ void set_error(const char* fmt, ...) {
 // every device's address space at their host address, so a kernel can read its inputs from them and
 // write its results into them over PCIe without a copy node on the stream ("direct" I/O mode).
 static std::mutex g_host_mu;
+enum class HostKind { Alloc, Registered, Adopted };
 struct HostRange {
     size_t bytes = 0;
-    bool direct = true;       // mapped at its host address: kernels may dereference the host pointer
-    bool registered = false;  // page-locked by nsb_host_register (cudaHostUnregister is ours to call)
+    bool direct = true;  // mapped at its host address: kernels may dereference the host pointer
+    // Alloc: nsb_host_alloc (cudaFreeHost in nsb_host_free); Registered: page-locked by nsb_host_register
+    // (cudaHostUnregister is ours to call); Adopted: page-locked by the caller before we saw it (the reference's
+    // Evaluator, evaluator.cc:95-106) - the caller unlocks it, we only forget it (nsb_host_unregister)
+    HostKind kind = HostKind::Alloc;
 };
 static std::map<uintptr_t, HostRange> g_host_allocs;  // base -> range
 
@@ -61,6 +65,8 @@ struct Slot {
     uint16_t* d_idx = nullptr;
     uint16_t* d_order = nullptr;  // rank order of the decoded rows (optional output)
     uint8_t* d_flag = nullptr;
+    uint8_t* d_rowflags = nullptr;  // NSB_ROW_* bits of a NSB_DECODE_BOTH request
+    float* d_logits = nullptr;      // raw logits beside the probabilities (allocated on first use)
     // cached evaluation (allocated by nsb_cache_create)
     uint64_t* d_hash = nullptr;
     uint8_t* d_hit = nullptr;
@@ -125,6 +131,29 @@ static int check_batch(nsb_ctx* c, size_t n, bool need_weights) {
     if (need_weights && !c->loaded) {
         set_error("weights not loaded (call nsb_load_weights first)");
         return NSB_ERR_STATE;
+    }
+    return 0;
+}
+
+static bool mode_ok(int mode) {
+    const int kind = mode & NSB_DECODE_MODE_MASK;
+    return (mode & ~(NSB_DECODE_MODE_MASK | NSB_DECODE_NAN_FALLBACK)) == 0 &&
+           (kind == NSB_DECODE_PROBS || kind == NSB_DECODE_LOGITS || kind == NSB_DECODE_BOTH);
+}
+
+// CSR offsets of a request: start at 0, never decrease, at most 593 moves per row (the reference asserts these;
+// here they would index the decode's registers, the cache rows and the rank staging).  O(n) on the host.
+static int check_offsets(const uint32_t* off, size_t n, const char* who) {
+    if (off[0] != 0) {
+        set_error("%s: move_off must start at 0", who);
+        return NSB_ERR_INVALID;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        if (off[i + 1] < off[i] || off[i + 1] - off[i] > (uint32_t)NSB_MAX_LEGAL_MOVES) {
+            set_error("%s: move_off[%zu..%zu] = %u..%u: rows must hold 0..%d moves", who, i, i + 1, off[i], off[i + 1],
+                      NSB_MAX_LEGAL_MOVES);
+            return NSB_ERR_INVALID;
+        }
     }
     return 0;
 }
@@ -236,6 +265,7 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
         if (e == cudaSuccess) e = cudaMalloc(&s.d_idx, B * NSB_MAX_LEGAL_MOVES * sizeof(uint16_t));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_order, B * NSB_MAX_LEGAL_MOVES * sizeof(uint16_t));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_flag, B);
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_rowflags, B);
         if (e != cudaSuccess) {
             set_error("nsb_create: device allocation failed: %s", cudaGetErrorString(e));
             nsb_destroy(c);
@@ -252,7 +282,7 @@ void nsb_destroy(nsb_ctx* c) {
     for (auto& s : c->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_feat); cudaFree(s.d_pos); cudaFree(s.d_policy); cudaFree(s.d_win); cudaFree(s.d_draw);
-        cudaFree(s.d_legal); cudaFree(s.d_off); cudaFree(s.d_idx); cudaFree(s.d_order); cudaFree(s.d_flag);
+        cudaFree(s.d_legal); cudaFree(s.d_off); cudaFree(s.d_idx); cudaFree(s.d_order); cudaFree(s.d_flag); cudaFree(s.d_rowflags); cudaFree(s.d_logits);
         cudaFree(s.d_hash); cudaFree(s.d_hit); cudaFree(s.d_miss_idx); cudaFree(s.d_miss_count);
         for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -297,6 +327,7 @@ int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
     }
     NSB_CUDA(cudaSetDevice(c->gpu));
     for (auto& s : c->slots) NSB_CUDA(cudaStreamSynchronize(s.stream));
+    c->loaded = false;  // a reload that fails half-way must not leave launches on freed weight buffers possible
     const nsb_net_desc& d = c->desc;
     const int C = d.channels, H = d.value_hidden, NL = 2 * d.blocks + 2;
     int stages = stages_per_pass(d);
@@ -608,8 +639,8 @@ int nsb_eval_decode_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_f
         set_error("weights not loaded");
         return NSB_ERR_STATE;
     }
-    if (!d_features || !d_win || !d_draw || !d_move_off || !d_move_idx || !d_legal_out) {
-        set_error("nsb_eval_decode_device: null buffer");
+    if (!d_features || !d_win || !d_draw || !d_move_off || !d_move_idx || !d_legal_out || !mode_ok(mode)) {
+        set_error("nsb_eval_decode_device: null buffer or bad mode");
         return NSB_ERR_INVALID;
     }
     if (n == 0) return 0;
@@ -776,7 +807,7 @@ static int eval_cached_enqueue(nsb_ctx* c, Slot& s, const nsb_feature_bitboard* 
                                float* d_legal, float* d_win, float* d_draw, uint8_t* d_nan_flag, uint8_t* d_hit) {
     NSB_CUDA(cudaMemsetAsync(s.d_miss_count, 0, sizeof(int), s.stream));
     int k = launch_cache_probe(c->cache, d_hashes, n, d_off, d_legal, d_win, d_draw, d_hit, d_nan_flag, s.d_miss_idx,
-                               s.d_miss_count, s.stream);
+                               s.d_miss_count, s.stream, nullptr, mode);
     NSB_CUDA(cudaGetLastError());
     c->launches += (uint64_t)k;
     EvalArgs a{};
@@ -805,7 +836,7 @@ int nsb_eval_cached_decode_device(nsb_ctx* c, int slot, const nsb_feature_bitboa
     if (rc) return rc;
     if ((rc = check_batch(c, n, true))) return rc;
     if (!d_features || !d_hashes || !d_move_off || !d_move_idx || !d_legal_out || !d_win || !d_draw || !d_hit ||
-        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+        !mode_ok(mode)) {
         set_error("nsb_eval_cached_decode_device: null buffer or bad mode");
         return NSB_ERR_INVALID;
     }
@@ -873,16 +904,16 @@ static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const
     const size_t n = r.n;
     if ((rc = check_batch(c, n, true))) return rc;
     if ((r.features != nullptr) == (r.positions != nullptr) || !r.move_off || !r.move_idx || !r.legal_out || !r.win || !r.draw ||
-        (r.mode != NSB_DECODE_PROBS && r.mode != NSB_DECODE_LOGITS)) {
+        !mode_ok(r.mode)) {
         set_error("%s: null buffer or bad mode", who);
         return NSB_ERR_INVALID;
     }
     if (n == 0) return 0;
+    if ((rc = check_offsets(r.move_off, n, who))) return rc;
     const size_t total = r.move_off[n];
-    if (r.move_off[0] != 0 || total > n * (size_t)NSB_MAX_LEGAL_MOVES) {
-        set_error("%s: move_off must start at 0 and hold at most %d moves per position", who, NSB_MAX_LEGAL_MOVES);
-        return NSB_ERR_INVALID;
-    }
+    const bool both = (r.mode & NSB_DECODE_MODE_MASK) == NSB_DECODE_BOTH;
+    const uint8_t* row_flags = both ? r.row_flags : nullptr;  // the other modes have no per-row variants
+    float* logits_out = both ? r.logits_out : nullptr;
     Slot& s = c->slots[slot];
     const size_t in_bytes = r.features ? n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard) : n * sizeof(nsb_position);
     const void* in = r.features ? (const void*)r.features : (const void*)r.positions;
@@ -893,7 +924,9 @@ static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const
     const bool direct = c->direct_io && (r.features || c->fuse_pack) && host_mapped(in, in_bytes) &&
                         decode_buffers_mapped(n, total, r.move_off, r.move_idx, r.legal_out, r.win, r.draw, r.nan_flag) &&
                         (!r.hashes || host_mapped(r.hashes, n * sizeof(uint64_t))) && (!r.hit_flag || host_mapped(r.hit_flag, n)) &&
-                        (!r.order_out || host_mapped(r.order_out, (total ? total : 1) * sizeof(uint16_t)));
+                        (!r.order_out || host_mapped(r.order_out, (total ? total : 1) * sizeof(uint16_t))) &&
+                        (!row_flags || host_mapped(row_flags, n)) &&
+                        (!logits_out || host_mapped(logits_out, (total ? total : 1) * sizeof(float)));
     const uint64_t* hashes = r.hashes;
     uint8_t* hit = r.hit_flag ? r.hit_flag : s.d_hit;
     if (direct) {
@@ -906,6 +939,8 @@ static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const
         a.legal_out = r.legal_out;
         a.order_out = r.order_out;
         a.nan_flag = r.nan_flag ? r.nan_flag : (r.hashes ? s.d_flag : nullptr);
+        a.row_flags = row_flags;
+        a.logits_out = logits_out;
     } else {
         NSB_CUDA(cudaMemcpyAsync(r.features ? (void*)s.d_feat : (void*)s.d_pos, in, in_bytes, cudaMemcpyHostToDevice, s.stream));
         a.features = s.d_feat;
@@ -925,11 +960,19 @@ static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const
         a.legal_out = s.d_legal;
         a.order_out = r.order_out ? s.d_order : nullptr;
         a.nan_flag = s.d_flag;
+        if (row_flags) {
+            NSB_CUDA(cudaMemcpyAsync(s.d_rowflags, row_flags, n, cudaMemcpyHostToDevice, s.stream));
+            a.row_flags = s.d_rowflags;
+        }
+        if (logits_out) {
+            if (!s.d_logits) NSB_CUDA(cudaMalloc(&s.d_logits, (size_t)c->batch_max * NSB_MAX_LEGAL_MOVES * sizeof(float)));
+            a.logits_out = s.d_logits;
+        }
     }
     if (r.hashes) {
         NSB_CUDA(cudaMemsetAsync(s.d_miss_count, 0, sizeof(int), s.stream));
         int k = launch_cache_probe(c->cache, hashes, n, a.move_off, a.legal_out, a.win, a.draw, hit, a.nan_flag, s.d_miss_idx,
-                                   s.d_miss_count, s.stream, a.order_out);
+                                   s.d_miss_count, s.stream, a.order_out, r.mode, a.row_flags, a.logits_out);
         NSB_CUDA(cudaGetLastError());
         c->launches += (uint64_t)k;
         a.index = s.d_miss_idx;   // the trunk launch works on the probe's miss list and stores what it decodes
@@ -943,6 +986,8 @@ static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const
         NSB_CUDA(cudaMemcpyAsync(r.legal_out, s.d_legal, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
         if (r.order_out)
             NSB_CUDA(cudaMemcpyAsync(r.order_out, s.d_order, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
+        if (logits_out)
+            NSB_CUDA(cudaMemcpyAsync(logits_out, s.d_logits, total * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     }
     NSB_CUDA(cudaMemcpyAsync(r.win, s.d_win, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     NSB_CUDA(cudaMemcpyAsync(r.draw, s.d_draw, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
@@ -1040,13 +1085,21 @@ int nsb_decode_device(nsb_ctx* c, int slot, const float* d_policy, const float* 
                       float* d_legal_out, uint8_t* d_nan_flag) {
     int rc = check_ctx(c, slot);
     if (rc) return rc;
-    if (!d_policy || !d_win || !d_draw || !d_move_off || !d_move_idx || !d_legal_out ||
-        (mode != NSB_DECODE_PROBS && mode != NSB_DECODE_LOGITS)) {
+    return nsb_decode_device_ex(c, slot, d_policy, d_win, d_draw, n, d_move_off, d_move_idx, mode, nullptr, d_legal_out,
+                                nullptr, d_nan_flag);
+}
+
+int nsb_decode_device_ex(nsb_ctx* c, int slot, const float* d_policy, const float* d_win, const float* d_draw,
+                         size_t n, const uint32_t* d_move_off, const uint16_t* d_move_idx, int mode,
+                         const uint8_t* d_row_flags, float* d_legal_out, float* d_logits_out, uint8_t* d_nan_flag) {
+    int rc = check_ctx(c, slot);
+    if (rc) return rc;
+    if (!d_policy || !d_win || !d_draw || !d_move_off || !d_move_idx || !d_legal_out || !mode_ok(mode)) {
         set_error("nsb_decode_device: null buffer or bad mode");
         return NSB_ERR_INVALID;
     }
     int k = launch_decode(d_policy, d_win, d_draw, n, d_move_off, d_move_idx, mode, d_legal_out, d_nan_flag,
-                          c->slots[slot].stream);
+                          c->slots[slot].stream, d_row_flags, d_logits_out);
     if (k < 0) return k;
     NSB_CUDA(cudaGetLastError());
     c->launches += (uint64_t)k;
@@ -1095,7 +1148,7 @@ int nsb_host_alloc(void** out, size_t bytes) {
     if (!out) return NSB_ERR_INVALID;
     NSB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
     std::lock_guard<std::mutex> lock(g_host_mu);
-    g_host_allocs[(uintptr_t)*out] = HostRange{bytes ? bytes : 1, true, false};
+    g_host_allocs[(uintptr_t)*out] = HostRange{bytes ? bytes : 1, true, HostKind::Alloc};
     return 0;
 }
 int nsb_host_free(void* p) {
@@ -1106,12 +1159,33 @@ int nsb_host_free(void* p) {
     NSB_CUDA(cudaFreeHost(p));
     return 0;
 }
+// The registry entry that covers [p, p + bytes), if any (caller holds g_host_mu).
+static std::map<uintptr_t, HostRange>::iterator host_find_locked(const void* p, size_t bytes) {
+    const uintptr_t a = (uintptr_t)p;
+    auto it = g_host_allocs.upper_bound(a);
+    if (it == g_host_allocs.begin()) return g_host_allocs.end();
+    --it;
+    return a + bytes <= it->first + it->second.bytes ? it : g_host_allocs.end();
+}
+
 int nsb_host_register(void* p, size_t bytes) {
     if (!p || bytes == 0) {
         set_error("nsb_host_register: bad arguments");
         return NSB_ERR_INVALID;
     }
-    if (host_mapped(p, bytes)) return NSB_HOST_ALREADY_LOCKED;  // nsb_host_alloc memory, or registered before
+    {
+        std::lock_guard<std::mutex> lock(g_host_mu);
+        auto it = host_find_locked(p, bytes);
+        if (it != g_host_allocs.end()) {
+            if (it->second.kind != HostKind::Adopted) return NSB_HOST_ALREADY_LOCKED;  // nsb_host_alloc memory, or registered before
+            // An adopted range belongs to the caller, who may have unlocked and freed it since (the reference's
+            // ~Evaluator runs before ~Infer): trust the entry only if the driver still knows the range.
+            void* dp = nullptr;
+            if (cudaHostGetDevicePointer(&dp, p, 0) == cudaSuccess && dp == p) return NSB_HOST_ALREADY_LOCKED;
+            cudaGetLastError();
+            g_host_allocs.erase(it);  // stale: the address has been reused; register it afresh below
+        }
+    }
     const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);  // evaluator.cc:95-106
     const bool adopted = e == cudaErrorHostMemoryAlreadyRegistered;  // the caller pinned it (the reference's Evaluator does)
     if (adopted) {
@@ -1128,7 +1202,7 @@ int nsb_host_register(void* p, size_t bytes) {
     if (!direct) cudaGetLastError();
     if (direct || !adopted) {
         std::lock_guard<std::mutex> lock(g_host_mu);
-        g_host_allocs[(uintptr_t)p] = HostRange{bytes, direct, !adopted};
+        g_host_allocs[(uintptr_t)p] = HostRange{bytes, direct, adopted ? HostKind::Adopted : HostKind::Registered};
     }
     return adopted ? NSB_HOST_ALREADY_LOCKED : NSB_OK;
 }
@@ -1137,8 +1211,8 @@ int nsb_host_unregister(void* p) {
     {
         std::lock_guard<std::mutex> lock(g_host_mu);
         auto it = g_host_allocs.find((uintptr_t)p);
-        if (it != g_host_allocs.end()) {
-            ours = it->second.registered;
+        if (it != g_host_allocs.end() && it->second.kind != HostKind::Alloc) {  // nsb_host_alloc memory goes with nsb_host_free
+            ours = it->second.kind == HostKind::Registered;
             g_host_allocs.erase(it);
         }
     }

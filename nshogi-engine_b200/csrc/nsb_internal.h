@@ -126,7 +126,9 @@ struct EvalArgs {
     float* legal_out;
     uint16_t* order_out;          // optional: per position the rank order of its decoded row (decode_device.cuh)
     uint8_t* nan_flag;
-    int decode_mode;
+    int decode_mode;              // NSB_DECODE_* [| NSB_DECODE_NAN_FALLBACK]
+    const uint8_t* row_flags;     // [n] or nullptr: NSB_ROW_* bits (NSB_DECODE_BOTH)
+    float* logits_out;            // optional (NSB_DECODE_BOTH): the raw gathered logits beside legal_out
     unsigned long long* timeline;  // optional (diagnostics): CTA 0 writes 4 clock64 stamps per layer
     // cached evaluation (optional): the launch works on the positions index[0 .. *count) (the misses
     // of a preceding cache probe) instead of 0 .. n-1, and stores every decoded row under hashes[b]
@@ -153,11 +155,12 @@ int launch_pack_positions(const nsb_position* d_pos, size_t n, nsb_feature_bitbo
                           cudaStream_t s);
 int launch_decode(const float* d_policy, const float* d_win, const float* d_draw, size_t n,
                   const uint32_t* d_off, const uint16_t* d_idx, int mode, float* d_out,
-                  uint8_t* d_flag, cudaStream_t s);
+                  uint8_t* d_flag, cudaStream_t s, const uint8_t* d_row_flags = nullptr, float* d_logits_out = nullptr);
 int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s);
 int launch_cache_probe(const DeviceCache& c, const uint64_t* d_hashes, size_t n, const uint32_t* d_off, float* d_legal,
                        float* d_win, float* d_draw, uint8_t* d_hit, uint8_t* d_nan_flag, int* d_miss_idx, int* d_miss_count,
-                       cudaStream_t s, uint16_t* d_order = nullptr);
+                       cudaStream_t s, uint16_t* d_order = nullptr, int mode = 0, const uint8_t* d_row_flags = nullptr,
+                       float* d_logits_out = nullptr);
 int launch_cache_store(const DeviceCache& c, const uint64_t* d_hashes, size_t n, const uint32_t* d_off,
                        const float* d_legal, const float* d_win, const float* d_draw, const uint8_t* d_skip,
                        uint8_t* d_stored, cudaStream_t s);

@@ -181,23 +181,24 @@ __global__ void __launch_bounds__(kDecodeWarps * 32)
 decode_kernel(const float* __restrict__ policy, const float* __restrict__ win,
               const float* __restrict__ draw, int n, const uint32_t* __restrict__ off,
               const uint16_t* __restrict__ idx, int mode, float* __restrict__ out,
-              uint8_t* __restrict__ flag) {
+              uint8_t* __restrict__ flag, const uint8_t* __restrict__ row_flags, float* __restrict__ logits_out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * kDecodeWarps + warp;
     if (i >= n) return;
     const uint32_t b = off[i], e = off[i + 1];
     const bool bad = warp_decode_row(policy + (size_t)i * kPolicySize, idx + b, (int)(e - b), mode,
-                                     win[i], draw[i], out + b, lane);
+                                     row_flags ? (int)row_flags[i] : 0, win[i], draw[i], out + b,
+                                     logits_out ? logits_out + b : nullptr, lane);
     if (flag && lane == 0) flag[i] = bad ? 1 : 0;
 }
 
 int launch_decode(const float* d_policy, const float* d_win, const float* d_draw, size_t n,
                   const uint32_t* d_off, const uint16_t* d_idx, int mode, float* d_out,
-                  uint8_t* d_flag, cudaStream_t s) {
+                  uint8_t* d_flag, cudaStream_t s, const uint8_t* d_row_flags, float* d_logits_out) {
     if (n == 0) return 0;
     const unsigned grid = (unsigned)((n + kDecodeWarps - 1) / kDecodeWarps);
     decode_kernel<<<grid, kDecodeWarps * 32, 0, s>>>(d_policy, d_win, d_draw, (int)n, d_off, d_idx,
-                                                     mode, d_out, d_flag);
+                                                     mode, d_out, d_flag, d_row_flags, d_logits_out);
     return 1;
 }
 

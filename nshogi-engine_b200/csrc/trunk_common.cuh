@@ -152,6 +152,61 @@ __device__ __forceinline__ void fc1_prefetch(const DeviceNet& net, int et, float
     for (int t = 0; t < kFcPrefetch; ++t) wpre[t] = et < H ? __ldg(net.fc1t + (size_t)t * H + et) : 0.f;
 }
 
+// The decode part of a pass's tail, shared by all trunk kernels: NT epilogue threads, the logits of the NPOS
+// positions in scratch[pos][2187], their win / draw rates in wd[pos * 2 + {0, 1}] (shared memory).  Warp `pos`
+// decodes position pos (gather + softmax on logits that never left shared memory, decode_device.cuh) and, when
+// the launch carries a cache, stores the row from its registers - probabilities for NSB_DECODE_PROBS
+// (feedworker.cc:134-135), raw logits for LOGITS / BOTH (frame.cc:110-114), nothing for a row with NaNFound -;
+// then all warps rank the rows (Node::sort) when the request asks for the order.  The caller has passed a
+// kEpiBar barrier after writing scratch / wd and passes one before reusing them.
+template <int NPOS, int NT>
+__device__ __forceinline__ void decode_tail(const EvalArgs& a, int n_eff, int li0, float* scratch, const float* wd, int et) {
+    constexpr int NW = NT / 32;
+    const int ew = et >> 5, lane = et & 31;
+    if (ew < NPOS) {
+        const int b = eval_index(a, li0 + ew, n_eff);
+        if (b >= 0) {
+            const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
+            const int m = (int)(me - mb);
+            const float w = wd[ew * 2 + 0], d = wd[ew * 2 + 1];
+            const int rf = a.row_flags ? (int)__ldg(a.row_flags + b) : 0;
+            float* row = scratch + ew * kPolicySize;
+            float* lout = a.logits_out ? a.logits_out + mb : nullptr;
+            bool nan_found;
+            // (instantiations kept apart: the staging keeps the row's values live longer and the store drags the
+            // cache code in, which costs the plain path microseconds if they are only predicated off)
+            if (a.hashes != nullptr) {
+                const uint64_t hash = __ldg(a.hashes + b);
+                auto store = [&](const float (&v)[kDecodePerLane]) {
+                    cache_store_warp_from(a.cache, hash, m, [&](int k) { return v[k]; }, w, d, lane);
+                };
+                nan_found = a.order_out ? warp_decode_row<true>(row, a.move_idx + mb, m, a.decode_mode, rf, w, d, a.legal_out + mb, lout, lane, row, store)
+                                        : warp_decode_row<false>(row, a.move_idx + mb, m, a.decode_mode, rf, w, d, a.legal_out + mb, lout, lane, nullptr, store);
+            } else {
+                nan_found = a.order_out ? warp_decode_row<true>(row, a.move_idx + mb, m, a.decode_mode, rf, w, d, a.legal_out + mb, lout, lane, row)
+                                        : warp_decode_row<false>(row, a.move_idx + mb, m, a.decode_mode, rf, w, d, a.legal_out + mb, lout, lane);
+            }
+            if (a.nan_flag && lane == 0) a.nan_flag[b] = nan_found ? 1 : 0;
+        }
+    }
+    if (a.order_out != nullptr) {  // rank order of the rows (Node::sort): all epilogue warps share the work
+        named_bar_sync(kEpiBar, NT);
+        const int pos = ew % NPOS;
+        const int b = eval_index(a, li0 + pos, n_eff);
+        // the order is staged behind the row's values in the position's (dead) logits scratch
+        uint16_t* ostage = reinterpret_cast<uint16_t*>(scratch + pos * kPolicySize + 608);
+        if (b >= 0) {
+            const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
+            rank_row_coop(scratch + pos * kPolicySize, (int)(me - mb), ew / NPOS, NW / NPOS, lane, ostage);
+        }
+        named_bar_sync(kEpiBar, NT);
+        if (b >= 0) {
+            const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
+            rank_row_copy_out(ostage, (int)(me - mb), ew / NPOS, NW / NPOS, lane, a.order_out + mb);
+        }
+    }
+}
+
 // Tail of a pass for the NPOS work-list entries at li0, executed by the 256 epilogue threads after the
 // logits (scratch[pos][2187], plane-major) and the value-conv plane (vbuf[pos][81], ReLU applied)
 // are in shared memory and a kEpiBar barrier has been passed: dense logits (the Infer contract,
@@ -223,41 +278,7 @@ __device__ __forceinline__ void heads_tail(const DeviceNet& net, const EvalArgs&
     if (tl) tl[6] = clock64();
     if (a.move_off != nullptr) {
         named_bar_sync(kEpiBar, kEpiThreads);
-        if (ew < NPOS) {
-            const int b = eval_index(a, li0 + ew, n_eff);
-            if (b >= 0) {
-                const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
-                const float w = red[kEpiWarps * NPOS * 2 + ew * 2 + 0], d = red[kEpiWarps * NPOS * 2 + ew * 2 + 1];
-                // (two instantiations: the staging keeps the row's values live longer, which costs the plain
-                // path microseconds if it is only predicated off)
-                const bool bad = a.order_out
-                                     ? warp_decode_row<true>(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
-                                                             a.decode_mode, w, d, a.legal_out + mb, lane, scratch + ew * kPolicySize)
-                                     : warp_decode_row<false>(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
-                                                              a.decode_mode, w, d, a.legal_out + mb, lane);
-                if (a.nan_flag && lane == 0) a.nan_flag[b] = bad ? 1 : 0;
-                if (a.hashes != nullptr && !bad) {  // every lane re-reads exactly the row elements it wrote
-                    __syncwarp();
-                    cache_store_warp(a.cache, __ldg(a.hashes + b), (int)(me - mb), a.legal_out + mb, w, d, lane);
-                }
-            }
-        }
-        if (a.order_out != nullptr) {  // rank order of the rows (Node::sort): all epilogue warps share the work
-            named_bar_sync(kEpiBar, kEpiThreads);
-            const int pos = ew % NPOS;
-            const int b = eval_index(a, li0 + pos, n_eff);
-            // the order is staged behind the row's values in the position's (dead) logits scratch
-            uint16_t* ostage = reinterpret_cast<uint16_t*>(scratch + pos * kPolicySize + 608);
-            if (b >= 0) {
-                const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
-                rank_row_coop(scratch + pos * kPolicySize, (int)(me - mb), ew / NPOS, kEpiWarps / NPOS, lane, ostage);
-            }
-            named_bar_sync(kEpiBar, kEpiThreads);
-            if (b >= 0) {
-                const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
-                rank_row_copy_out(ostage, (int)(me - mb), ew / NPOS, kEpiWarps / NPOS, lane, a.order_out + mb);
-            }
-        }
+        decode_tail<NPOS, kEpiThreads>(a, n_eff, li0, scratch, red + kEpiWarps * NPOS * 2, et);
     }
     named_bar_sync(kEpiBar, kEpiThreads);
     if (tl) tl[7] = clock64();

@@ -118,39 +118,7 @@ __device__ __forceinline__ void heads_tail_small(const DeviceNet& net, const Eva
     }
     if (a.move_off != nullptr) {
         named_bar_sync(kEpiBar, NT);
-        if (ew < NPOS) {
-            const int b = eval_index(a, li0 + ew, n_eff);
-            if (b >= 0) {
-                const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
-                const float w = red[NW * NPOS * 2 + ew * 2 + 0], d = red[NW * NPOS * 2 + ew * 2 + 1];
-                const bool bad = a.order_out
-                                     ? warp_decode_row<true>(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
-                                                             a.decode_mode, w, d, a.legal_out + mb, lane, scratch + ew * kPolicySize)
-                                     : warp_decode_row<false>(scratch + ew * kPolicySize, a.move_idx + mb, (int)(me - mb),
-                                                              a.decode_mode, w, d, a.legal_out + mb, lane);
-                if (a.nan_flag && lane == 0) a.nan_flag[b] = bad ? 1 : 0;
-                if (a.hashes != nullptr && !bad) {
-                    __syncwarp();
-                    cache_store_warp(a.cache, __ldg(a.hashes + b), (int)(me - mb), a.legal_out + mb, w, d, lane);
-                }
-            }
-        }
-        if (a.order_out != nullptr) {  // rank order of the rows (Node::sort): the epilogue warps share the work
-            named_bar_sync(kEpiBar, NT);
-            const int pos = ew % NPOS;
-            const int b = eval_index(a, li0 + pos, n_eff);
-            // the order is staged behind the row's values in the position's (dead) logits scratch
-            uint16_t* ostage = reinterpret_cast<uint16_t*>(scratch + pos * kPolicySize + 608);
-            if (b >= 0) {
-                const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
-                rank_row_coop(scratch + pos * kPolicySize, (int)(me - mb), ew / NPOS, NW / NPOS, lane, ostage);
-            }
-            named_bar_sync(kEpiBar, NT);
-            if (b >= 0) {
-                const uint32_t mb = __ldg(a.move_off + b), me = __ldg(a.move_off + b + 1);
-                rank_row_copy_out(ostage, (int)(me - mb), ew / NPOS, NW / NPOS, lane, a.order_out + mb);
-            }
-        }
+        decode_tail<NPOS, NT>(a, n_eff, li0, scratch, red + NW * NPOS * 2, et);
     }
     named_bar_sync(kEpiBar, NT);
 }

@@ -25,6 +25,7 @@
 #include "eval_cache.h"
 #include "leaf_queue.h"
 #include "mcts_feed.h"
+#include "selfplay_feed.h"
 #include "move_index.h"
 #include "onnx_import.h"
 
@@ -205,12 +206,49 @@ static int feedChecks() {
         if (N == 1) { float One = 1.0f; A.setEvaluation(&One, RW, RD); }
         else { A.setEvaluation(Legal.data(), RW, RD); A.sort(); }
         A.updateAncestors(RW, RD);
-        // feedRanked on node B
+        // feedRanked<true> on node B
         const mcts::LeafRow Row{Legal.data(), Order.data(), N, W, D};
-        const bool Nan = mcts::feedRanked(&B, Row);
+        const bool Nan = mcts::feedRanked<true>(&B, Row);
         CHECK(Nan == (NanW || NanD));
         CHECK(B.WinPred == A.WinPred && B.DrawPred == A.DrawPred && B.BackedWin == A.BackedWin && B.BackedDraw == A.BackedDraw);
         for (uint16_t I = 0; I < N; ++I) CHECK(B.Edges[I].Move == A.Edges[I].Move && B.Edges[I].Probability == A.Edges[I].Probability);
+        // feedResult<false>, the reference's default build (context.h:103): nothing is replaced, nothing is found
+        MockNode C2;
+        C2.Edges.resize(N);
+        C2.Parent = A.Parent;
+        const bool Nan2 = mcts::feedRanked<false>(&C2, Row);
+        CHECK(!Nan2);
+        CHECK(NanW ? std::isnan(C2.WinPred) : C2.WinPred == W);
+        CHECK(NanD ? std::isnan(C2.DrawPred) : C2.DrawPred == D);
+    }
+    return 0;
+}
+
+// selfplay_feed.h == the tail of Frame::setEvaluation (frame.cc:116-135) written out literally
+static int selfplayFeedChecks() {
+    std::mt19937_64 Rng(11);
+    std::gamma_distribution<double> Gamma(0.15, 1.0);
+    for (int Trial = 0; Trial < 64; ++Trial) {
+        const std::size_t N = 1 + Rng() % 400;
+        std::vector<float> P(N);
+        double Sum = 0.0;
+        for (auto& X : P) Sum += (X = (float)((Rng() % 1000) + 1));
+        for (auto& X : P) X = (float)(X / Sum);
+        std::vector<double> Noise(600);
+        double NS = 0.0;
+        for (auto& X : Noise) NS += (X = Gamma(Rng));
+        for (auto& X : Noise) X /= NS;
+        const bool Gumbel = Trial & 1, Root = Trial & 2, Full = Trial & 4;
+        std::vector<float> Want = P;
+        if (!Gumbel && Root && Full)  // frame.cc:121-133
+            for (std::size_t I = 0; I < N; ++I) Want[I] = (float)((1 - 0.25) * (double)Want[I] + 0.25 * Noise[I]);
+        MockNode Nd;
+        Nd.Edges.resize(N);
+        std::vector<float> Row = P;
+        selfplay::setEvaluationDecoded(&Nd, Row.data(), N, 0.5f, 0.25f, Gumbel, Root, Full, Noise.data());
+        for (std::size_t I = 0; I < N; ++I) CHECK(std::memcmp(&Nd.Edges[I].Probability, &Want[I], 4) == 0);
+        CHECK(Nd.WinPred == 0.5f && Nd.DrawPred == 0.25f);
+        CHECK(selfplay::rowFlags(Gumbel, Root) == ((Gumbel && Root) ? NSB_ROW_SKIP_SOFTMAX : 0));
     }
     return 0;
 }
@@ -277,6 +315,7 @@ int main(int argc, char** argv) {
         CHECK(*Seen.rbegin() < 2187 && Seen.size() > 1500);  // most slots are reachable
     }
     if (feedChecks()) return 1;  // mcts_feed.h == setEvaluation + sort + updateAncestors of the reference
+    if (selfplayFeedChecks()) return 1;
     std::printf("host_unit ok\n");
     return 0;
 }

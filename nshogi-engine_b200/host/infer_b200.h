@@ -130,8 +130,11 @@ class B200 : public Infer {
             const std::size_t B = BatchSizeM;
             const std::size_t Bytes[4] = {B * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard), B * NSB_POLICY_SIZE * sizeof(float),
                                           B * sizeof(float), B * sizeof(float)};
+            // Every range the library now knows - locked by this call OR adopted from the caller's Evaluator - is
+            // remembered and forgotten again in ~B200 (nsb_host_unregister unlocks only what the library locked and
+            // leaves nsb_host_alloc memory alone), so that no entry outlives the executor that made it.
             for (int I = 0; I < 4; ++I)
-                if (nsb_host_register(const_cast<void*>(Seen_[I]), Bytes[I]) == NSB_OK) Registered_.push_back(const_cast<void*>(Seen_[I]));
+                if (nsb_host_register(const_cast<void*>(Seen_[I]), Bytes[I]) >= 0) Registered_.push_back(const_cast<void*>(Seen_[I]));
         }
         check(nsb_eval_async(Ctx_, 0, reinterpret_cast<const nsb_feature_bitboard*>(Features), BatchSize, DstPolicy,
                              DstWinRate, DstDrawRate),

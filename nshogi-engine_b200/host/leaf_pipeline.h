@@ -12,6 +12,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "infer_b200.h"
@@ -29,6 +30,7 @@ class LeafPipeline {
         uint32_t* MoveOffsets = nullptr;           // [BatchMax + 1]   CSR of legal-move policy indices
         uint16_t* MoveIndices = nullptr;           // [BatchMax * 593] values of ml::getMoveIndex
         uint64_t* Hashes = nullptr;                // [BatchMax]       state hashes (only read when the executor has a cache)
+        uint8_t* RowFlags = nullptr;               // [BatchMax]       NSB_ROW_* bits (read by NSB_DECODE_BOTH requests)
         // outputs, valid after collect()
         float* Legal = nullptr;                    // per legal move: probabilities or raw logits
         uint16_t* Order = nullptr;                 // per position the rank order of its row (submit(..., Ranked)):
@@ -56,6 +58,8 @@ class LeafPipeline {
             alloc(S.NanFlag, BatchMax);
             alloc(S.Hashes, BatchMax);
             alloc(S.HitFlag, BatchMax);
+            alloc(S.RowFlags, BatchMax);
+            std::memset(S.RowFlags, 0, BatchMax);
         }
     }
     ~LeafPipeline() {
@@ -87,6 +91,9 @@ class LeafPipeline {
     // a one-slot executor, directly on these page-locked arrays (NSB_IO_DIRECT).  With UseCache (executor built
     // with enableCache) the batch goes through the device-resident cache: hits are served from HBM, only the
     // misses are evaluated, evaluated rows are stored.  With Ranked, Order[] receives every row's rank order.
+    // DecodeMode: NSB_DECODE_PROBS (MCTS, feedworker.cc:100-136), NSB_DECODE_BOTH (self-play, frame.cc:93-118: the
+    // cache keeps raw logits, Legal receives probabilities, RowFlags marks Gumbel roots), optionally
+    // | NSB_DECODE_NAN_FALLBACK (Context::isNaNFallbackEnabled()).
     void submit(std::size_t Index, std::size_t Count, bool FromPositions, int DecodeMode = NSB_DECODE_PROBS,
                 bool UseCache = false, bool Ranked = false) {
         Slot& S = Slots[Index];
@@ -106,6 +113,7 @@ class LeafPipeline {
         R.draw = S.DrawRate;
         R.nan_flag = S.NanFlag;
         R.hit_flag = UseCache ? S.HitFlag : nullptr;
+        R.row_flags = (DecodeMode & NSB_DECODE_MODE_MASK) == NSB_DECODE_BOTH ? S.RowFlags : nullptr;
         infer::B200::check(nsb_eval_request_async(Ex->context(), (int)Index, &R), "LeafPipeline::submit");
         S.InFlight = true;
     }

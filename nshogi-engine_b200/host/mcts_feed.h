@@ -4,9 +4,10 @@
 // The reference, per leaf and on a feed thread: NaN fallback for win / draw rate from the parent's statistics
 // (:58-85), gather of the legal logits + softmax (:100-127), Node::setEvaluation, Node::sort() (std::sort of the
 // edges by decreasing probability, src/mcts/node.h:163-168), updateAncestors, EvalCache::store (:134-135).  With
-// the executor's fused decode the gather, the softmax, the NaN handling of the policy, the cache store and the
-// sort's permutation are already done on the GPU; what is left is O(n): write the edges in rank order, apply the
-// win / draw fallback, back-propagate.
+// the executor's fused decode the gather, the softmax, the NaN handling of the policy row (:105-118, only with
+// NSB_DECODE_NAN_FALLBACK, as in the reference's two builds of feedResult), the cache store and the sort's
+// permutation are already done on the GPU; what is left is O(n): write the edges in rank order, apply the
+// win / draw fallback (:58-85), back-propagate.
 //
 // Templated on the node type so that it compiles against the reference's mcts::Node (getNumChildren, getEdge,
 // setEvaluation, getParent, getWinRateAccumulated, getDrawRateAccumulated, getVisitsAndVirtualLoss, VisitMask,
@@ -42,20 +43,23 @@ inline LeafRow leafRow(const evaluate::LeafPipeline::Slot& S, std::size_t I) {
     return LeafRow{S.Legal + B, S.Order + B, (uint16_t)(E - B), S.WinRate[I], S.DrawRate[I]};
 }
 
-// feedResult<NaNFallbackEnabled = true> for a ranked row.  Returns true if a NaN was replaced (the reference
-// then skips the cache store; the device cache never stores such rows either).
-template <typename NodeT>
+// feedResult<NaNFallbackEnabled> for a ranked row; the batch must have been submitted with (true) or without
+// (false, the reference's default: src/context.h:103) NSB_DECODE_NAN_FALLBACK accordingly.  The policy half of
+// the fallback (a NaN logit makes the row uniform, :105-118) has happened on the GPU; the value half (:58-85)
+// is here, because it needs the parent node.  Returns NaNFound (the reference then skips the cache store; the
+// device cache has skipped it already: the flag of the GPU row covers logits, win and draw rate).
+template <bool NaNFallbackEnabled = false, typename NodeT>
 bool feedRanked(NodeT* N, const LeafRow& R) {
     float WinRate = R.WinRate, DrawRate = R.DrawRate;
     bool NaNFound = false;
-    if (isNaNBits(WinRate)) {  // feedworker.cc:61-72
+    if (NaNFallbackEnabled && isNaNBits(WinRate)) {  // feedworker.cc:61-72
         NaNFound = true;
         const NodeT* Parent = N->getParent();
         WinRate = Parent == nullptr
                       ? 0.5f
                       : (float)(1.0 - Parent->getWinRateAccumulated() / (double)(Parent->getVisitsAndVirtualLoss() & NodeT::VisitMask));
     }
-    if (isNaNBits(DrawRate)) {  // feedworker.cc:73-84
+    if (NaNFallbackEnabled && isNaNBits(DrawRate)) {  // feedworker.cc:73-84
         NaNFound = true;
         const NodeT* Parent = N->getParent();
         DrawRate = Parent == nullptr

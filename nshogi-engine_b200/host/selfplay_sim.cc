@@ -22,14 +22,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <deque>
+#include <limits>
 #include <mutex>
+#include <random>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "infer_b200.h"
 #include "leaf_pipeline.h"
+#include "selfplay_feed.h"
 
 using namespace nshogi::engine;
 using Clock = std::chrono::steady_clock;
@@ -47,6 +51,9 @@ struct Frame {  // reference src/selfplay/frame.h: one game in flight
     float Win = 0.f, Draw = 0.f, PolicyMass = 0.f;
     Phase P = Phase::LeafSelection;
     uint64_t Hash = 0;         // state hash of the leaf (key of the evaluation cache)
+    bool AtRoot = true;        // the next leaf is the root itself (first evaluation after a move, worker.cc:159-160)
+    bool FullSearch = true;    // getDidFullSearch().back() (worker.cc:184-197)
+    double Noise[600];         // Dirichlet (or Gumbel) noise sampled at root preparation (frame.cc:26, worker.cc:166-177)
     nsb_position Recent[4];    // leaves visited lately: --revisit-ratio re-descends to one of them
     uint32_t RecentCount = 0;
     bool CacheHit = false;
@@ -145,18 +152,36 @@ void newGame(Frame& F, uint32_t Playouts) {
 struct Options {
     int Channels = 256, Blocks = 20, Batch = 512, Frames = 1024, SearchWorkers = 4, Slots = 3, GPU = 0;
     int Playouts = 200, DescentNs = 0, CacheMiB = 0;
+    bool Gumbel = false;  // main.cc --gumbel
     double FullSearchRatio = 0.25, Seconds = 5.0, Warmup = 1.0, RevisitRatio = 0.0;
 };
 
-uint32_t playoutsFor(const Options& O, uint64_t& Rng) {  // worker.cc:184-197
+uint32_t playoutsFor(const Options& O, uint64_t& Rng, bool* FullSearch) {  // worker.cc:184-197
     const double U = (double)(next(Rng) >> 11) * (1.0 / 9007199254740992.0);
-    return U < O.FullSearchRatio ? (uint32_t)O.Playouts : (uint32_t)std::max(1, O.Playouts / 4);
+    *FullSearch = U < O.FullSearchRatio;
+    return *FullSearch ? (uint32_t)O.Playouts : (uint32_t)std::max(1, O.Playouts / 4);
+}
+
+// Worker::prepareRoot, worker.cc:166-177 + sampleNoise :640-655: 600 noise values per root - Gumbel
+// -log(-log U), or Gamma(0.15, 1) normalised to a Dirichlet sample for the AlphaZero style.
+void prepareRoot(const Options& O, Frame& F, std::mt19937_64& MT) {
+    F.AtRoot = true;
+    if (O.Gumbel) {
+        std::uniform_real_distribution<double> D(std::numeric_limits<double>::min(), 1.0);
+        for (double& X : F.Noise) X = -std::log(-std::log(D(MT)));
+    } else {
+        std::gamma_distribution<double> D(0.15, 1.0);
+        double Sum = 0.0;
+        for (double& X : F.Noise) Sum += (X = D(MT));
+        for (double& X : F.Noise) X /= Sum;
+    }
 }
 
 // reference src/selfplay/worker.cc: LeafSelection / Backpropagation / Transition on the CPU
 void searchWorker(const Options& O, FrameQueue* SearchQueue, FrameQueue* EvaluationQueue, Info* SI,
                   std::atomic<bool>* Running) {
     std::vector<Frame*> In, Out;
+    std::mt19937_64 MT(0x5EED5EEDull + (uint64_t)(uintptr_t)&In);  // worker.cc: one generator per search worker
     while (Running->load(std::memory_order_relaxed)) {
         In.clear();
         SearchQueue->get(64, true, In);
@@ -167,17 +192,20 @@ void searchWorker(const Options& O, FrameQueue* SearchQueue, FrameQueue* Evaluat
                     SI->Records.fetch_add(1, std::memory_order_relaxed);
                     if (++F->Ply >= F->GameLen) {
                         SI->Games.fetch_add(1, std::memory_order_relaxed);
-                        newGame(*F, playoutsFor(O, F->Rng));
+                        newGame(*F, playoutsFor(O, F->Rng, &F->FullSearch));
                     } else {
-                        F->PlayoutsLeft = playoutsFor(O, F->Rng);
+                        F->PlayoutsLeft = playoutsFor(O, F->Rng, &F->FullSearch);
                     }
+                    prepareRoot(O, *F, MT);
                 }
             }
             // LeafSelection: descend (synthetic) - or, with --revisit-ratio, reach a leaf seen lately
             // (a transposition) - and list the leaf's legal moves as policy slots.  The move list is a
             // function of the position, as it is with a real move generator.
             const double U = (double)(next(F->Rng) >> 11) * (1.0 / 9007199254740992.0);
-            if (F->RecentCount > 0 && U < O.RevisitRatio) {
+            if (F->AtRoot) {  // RootPreparation: the first leaf after a move is the root position itself
+                F->Leaf = F->Root;
+            } else if (F->RecentCount > 0 && U < O.RevisitRatio) {
                 F->Leaf = F->Recent[next(F->Rng) % F->RecentCount];
             } else {
                 F->Leaf = F->Root;
@@ -228,7 +256,11 @@ void evaluationWorker(const Options& O, infer::B200* Exec, FrameQueue* Evaluatio
             F->Win = S.WinRate[I];
             F->Draw = S.DrawRate[I];
             float Mass = 0.f;
-            const float* Row = S.Legal + S.MoveOffsets[I];
+            float* Row = S.Legal + S.MoveOffsets[I];
+            // the gather, the cache store of the raw logits and the softmax (or its skip at a Gumbel root) happened
+            // on the GPU (NSB_DECODE_BOTH); the Dirichlet mix of an AlphaZero root of a full search is left
+            if (!O.Gumbel && F->AtRoot && F->FullSearch) selfplay::mixDirichletNoise(Row, F->Noise, F->NumMoves);  // frame.cc:121-133
+            F->AtRoot = false;
             for (uint32_t J = 0; J < F->NumMoves; ++J) Mass += Row[J];
             F->PolicyMass = Mass;
             if (S.NanFlag[I]) SI->NanRows.fetch_add(1, std::memory_order_relaxed);
@@ -260,14 +292,16 @@ void evaluationWorker(const Options& O, infer::B200* Exec, FrameQueue* Evaluatio
             const Frame* F = Tasks[I];
             S.Positions[I] = F->Leaf;
             S.Hashes[I] = F->Hash;
+            S.RowFlags[I] = selfplay::rowFlags(O.Gumbel, F->AtRoot);  // frame.cc:116-118
             S.MoveOffsets[I] = Off;
             std::memcpy(S.MoveIndices + Off, F->MoveIdx, F->NumMoves * sizeof(uint16_t));
             Off += F->NumMoves;
         }
         S.MoveOffsets[Tasks.size()] = Off;
         SlotTasks[Idx].swap(Tasks);
-        Pipe.submit(Idx, SlotTasks[Idx].size(), /*FromPositions=*/true, NSB_DECODE_LOGITS,  // frame.cc:110-114
-                    /*UseCache=*/O.CacheMiB > 0);
+        // Frame::setEvaluation<false> in one launch: the cache keeps raw logits (frame.cc:110-114), the frames
+        // receive probabilities (frame.cc:116-118) - for rows served from the cache too
+        Pipe.submit(Idx, SlotTasks[Idx].size(), /*FromPositions=*/true, NSB_DECODE_BOTH, /*UseCache=*/O.CacheMiB > 0);
         InFlight.push_back(Idx);
     }
     while (!InFlight.empty()) {  // Worker::stop contract: drain before returning
@@ -295,6 +329,7 @@ int main(int argc, char** argv) {
         else if (A == "--full-search-ratio") O.FullSearchRatio = nextD();
         else if (A == "--descent-ns") O.DescentNs = nextI();
         else if (A == "--cache-mb") O.CacheMiB = nextI();
+        else if (A == "--gumbel") O.Gumbel = true;
         else if (A == "--revisit-ratio") O.RevisitRatio = nextD();
         else if (A == "--seconds") O.Seconds = nextD();
         else if (A == "--warmup") O.Warmup = nextD();
@@ -318,6 +353,10 @@ int main(int argc, char** argv) {
     for (std::size_t I = 0; I < Pool.size(); ++I) {
         Pool[I].Rng = 0x9E3779B97F4A7C15ull * (I + 1) + (uint64_t)O.GPU * 0xD1B54A32D192ED03ull;
         newGame(Pool[I], (uint32_t)O.Playouts);
+        {
+            std::mt19937_64 MT(Pool[I].Rng);
+            prepareRoot(O, Pool[I], MT);
+        }
         Pool[I].Ply = (uint32_t)(next(Pool[I].Rng) % Pool[I].GameLen);  // games start staggered
         Init.push_back(&Pool[I]);
     }
@@ -349,11 +388,13 @@ int main(int argc, char** argv) {
                 "\"cache_mb\": %d, \"revisit_ratio\": %.2f, \"cache_hit_rate\": %.4f, "
                 "\"net\": \"%dx%d\", \"batch_size\": %d, \"frame_pool\": %d, \"search_workers\": %d, \"slots\": %d, "
                 "\"num_playouts\": %d, \"full_search_ratio\": %.2f, \"descent_ns\": %d, \"nan_rows\": %llu, "
+                "\"decode\": \"NSB_DECODE_BOTH (logits cached, probabilities out; %s)\", "
                 "\"rules\": \"synthetic (libnshogi absent): random relocations, random legal-move slots\"}\n",
                 (double)(R1 - R0) / Sec, Evals / Sec, (double)(G1 - G0) / Sec, Batches > 0 ? Evals / Batches : 0.0, Sec,
                 (unsigned long long)(R1 - R0), (unsigned long long)(E1 - E0), (unsigned long long)(B1 - B0),
                 (unsigned long long)(G1 - G0), O.CacheMiB, O.RevisitRatio, Evals > 0 ? (double)(H1 - H0) / Evals : 0.0,
                 O.Blocks, O.Channels, O.Batch, O.Frames, O.SearchWorkers, O.Slots, O.Playouts, O.FullSearchRatio,
-                O.DescentNs, (unsigned long long)SI.NanRows.load());
+                O.DescentNs, (unsigned long long)SI.NanRows.load(),
+                O.Gumbel ? "Gumbel roots skip the softmax" : "Dirichlet mix at full-search roots on the host");
     return 0;
 }

@@ -111,7 +111,7 @@ void nsb_oracle_pack(const nsb_position* pos, size_t n, nsb_feature_bitboard* fb
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* decode: reference src/mcts/feedworker.cc:100-136, src/selfplay/frame.cc:96-118               */
+/* decode: reference src/mcts/feedworker.cc:56-136, src/selfplay/frame.cc:93-136                */
 /* ------------------------------------------------------------------------------------------ */
 
 /* reference src/math/math.h:23-39: bit-pattern NaN test (robust under -ffast-math). */
@@ -120,36 +120,118 @@ static inline int isnan_bits(float x) {
     return (u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu) != 0;
 }
 
+/* ml::math::softmax_(x, n, T = 1) (libnshogi, UNPINNED: assumed max-subtracted exp / sum).  Called at
+ * feedworker.cc:127 and frame.cc:117. */
+static void softmax_inplace(float* x, uint32_t m) {
+    if (m == 0) return;
+    float mx = x[0];
+    for (uint32_t j = 1; j < m; ++j) mx = x[j] > mx ? x[j] : mx;
+    float sum = 0.0f;
+    for (uint32_t j = 0; j < m; ++j) {
+        x[j] = expf(x[j] - mx);
+        sum += x[j];
+    }
+    const float inv = 1.0f / sum;
+    for (uint32_t j = 0; j < m; ++j) x[j] *= inv;
+}
+
+/* One leaf, MCTS flavour = FeedWorker::feedResult<NaNFallbackEnabled> (feedworker.cc:56-137) as far as the
+ * policy row, NaNFound and the cache decision go.  Three separate pieces of the reference:
+ *   :58-85   win / draw NaN  -> NaNFound = true; the VALUE is replaced from the parent (restated in
+ *            nsb_oracle_value_fallback below); the policy row is NOT touched
+ *   :100-103 one child       -> LegalPolicy[0] = 1, no gather, no NaN test of the logit
+ *   :105-118 fallback build  -> gather; the first NaN logit sets NaNFound and makes EVERY legal logit 1
+ *   :119-126 default build   -> plain gather (NaNs flow into the softmax; NaNFound stays false)
+ *   :127     softmax_        :134 cache store iff !NaNFound
+ * Returns NaNFound. */
+static int feed_result_row(const float* row, const uint16_t* idx, uint32_t m, int fallback, float win, float draw,
+                           float* out) {
+    int nan_found = 0;
+    if (fallback && (isnan_bits(win) || isnan_bits(draw))) nan_found = 1; /* :61-62, :73-74 */
+    if (m == 1) {                                                          /* :100-103 */
+        out[0] = 1.0f;
+        return nan_found;
+    }
+    if (fallback) { /* :105-118 */
+        for (uint32_t j = 0; j < m; ++j) {
+            out[j] = row[idx[j]];
+            if (isnan_bits(out[j])) {
+                nan_found = 1;
+                for (uint32_t k = 0; k < m; ++k) out[k] = 1.0f;
+                break;
+            }
+        }
+    } else { /* :119-126 */
+        for (uint32_t j = 0; j < m; ++j) out[j] = row[idx[j]];
+    }
+    softmax_inplace(out, m); /* :127 */
+    return nan_found;
+}
+
+/* One leaf, self-play flavour = Frame::setEvaluation<false> (frame.cc:93-136) up to the Dirichlet mix:
+ *   :96-107  gather the raw logits      :110-114 EvalCache->store(raw logits), unconditional
+ *   :116-118 softmax_ unless (Gumbel && root): the caller passes that as NSB_ROW_SKIP_SOFTMAX
+ * There is no NaN handling in this function of the reference; with the NSB_DECODE_NAN_FALLBACK bit the
+ * executor (and this restatement) only REPORT a NaN among logits / win / draw and keep such a row out of the
+ * cache - an extension, off by default like the reference's own switch (src/context.h:103). */
+static int set_evaluation_row(const float* row, const uint16_t* idx, uint32_t m, int fallback, int row_flags,
+                              float win, float draw, float* out, float* logits_out) {
+    int any_nan = isnan_bits(win) || isnan_bits(draw);
+    for (uint32_t j = 0; j < m; ++j) { /* :96-107 */
+        out[j] = row[idx[j]];
+        any_nan |= isnan_bits(out[j]);
+        if (logits_out) logits_out[j] = out[j];
+    }
+    if (!(row_flags & NSB_ROW_SKIP_SOFTMAX)) softmax_inplace(out, m); /* :116-118 */
+    return fallback && any_nan;
+}
+
+void nsb_oracle_decode_ex(const float* policy, const float* win, const float* draw, size_t n,
+                          const uint32_t* move_off, const uint16_t* move_idx, int mode, const uint8_t* row_flags,
+                          float* legal_out, float* logits_out, uint8_t* nan_flag) {
+    const int fallback = (mode & NSB_DECODE_NAN_FALLBACK) != 0, kind = mode & NSB_DECODE_MODE_MASK;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t b = move_off[i], m = move_off[i + 1] - b;
+        const float* row = policy + i * NSB_POLICY_SIZE;
+        int flag;
+        if (kind == NSB_DECODE_PROBS)
+            flag = feed_result_row(row, move_idx + b, m, fallback, win[i], draw[i], legal_out + b);
+        else if (kind == NSB_DECODE_LOGITS) /* the gather alone: frame.cc:96-107 */
+            flag = set_evaluation_row(row, move_idx + b, m, fallback, NSB_ROW_SKIP_SOFTMAX, win[i], draw[i],
+                                      legal_out + b, NULL);
+        else
+            flag = set_evaluation_row(row, move_idx + b, m, fallback, row_flags ? row_flags[i] : 0, win[i], draw[i],
+                                      legal_out + b, logits_out ? logits_out + b : NULL);
+        if (nan_flag) nan_flag[i] = (uint8_t)flag;
+    }
+}
+
 void nsb_oracle_decode(const float* policy, const float* win, const float* draw, size_t n,
                        const uint32_t* move_off, const uint16_t* move_idx, int mode,
                        float* legal_out, uint8_t* nan_flag) {
-    for (size_t i = 0; i < n; ++i) {
-        const uint32_t b = move_off[i], e = move_off[i + 1], m = e - b;
-        const float* row = policy + i * NSB_POLICY_SIZE;
-        float* out = legal_out + b;
-        int bad = isnan_bits(win[i]) || isnan_bits(draw[i]);
-        for (uint32_t j = 0; j < m; ++j) { /* gather: feedworker.cc:119-125 / frame.cc:101-106 */
-            out[j] = row[move_idx[b + j]];
-            bad |= isnan_bits(out[j]);
-        }
-        if (nan_flag) nan_flag[i] = (uint8_t)bad;
-        if (mode == NSB_DECODE_LOGITS || m == 0) continue; /* frame.cc:110-114 caches logits */
-        if (m == 1) { /* feedworker.cc:101-103 */
-            out[0] = 1.0f;
-            continue;
-        }
-        if (bad) /* NaN fallback, feedworker.cc:111-118: all-ones before softmax => uniform */
-            for (uint32_t j = 0; j < m; ++j) out[j] = 1.0f;
-        float mx = out[0]; /* softmax_(x, n, T = 1): feedworker.cc:127, frame.cc:117 */
-        for (uint32_t j = 1; j < m; ++j) mx = out[j] > mx ? out[j] : mx;
-        float sum = 0.0f;
-        for (uint32_t j = 0; j < m; ++j) {
-            out[j] = expf(out[j] - mx);
-            sum += out[j];
-        }
-        const float inv = 1.0f / sum;
-        for (uint32_t j = 0; j < m; ++j) out[j] *= inv;
+    nsb_oracle_decode_ex(policy, win, draw, n, move_off, move_idx, mode, NULL, legal_out, NULL, nan_flag);
+}
+
+/* feedworker.cc:58-85: the NaN fallback of the leaf's VALUE from its parent's running statistics
+ * (has_parent == 0: the root, :64-65, :76-77).  Returns NaNFound. */
+int nsb_oracle_value_fallback(float* win, float* draw, int has_parent, double parent_win_acc,
+                              double parent_draw_acc, uint64_t parent_visits) {
+    int nan_found = 0;
+    if (isnan_bits(*win)) {
+        nan_found = 1;
+        *win = has_parent ? (float)(1.0 - parent_win_acc / (double)parent_visits) : 0.5f;
     }
+    if (isnan_bits(*draw)) {
+        nan_found = 1;
+        *draw = has_parent ? (float)(parent_draw_acc / (double)parent_visits) : 0.0f;
+    }
+    return nan_found;
+}
+
+/* frame.cc:121-133: Dirichlet noise at the AlphaZero root of a full search, in double, rounded once. */
+void nsb_oracle_dirichlet_mix(float* probs, const double* noise, uint32_t m) {
+    const double EPS = 0.25;
+    for (uint32_t j = 0; j < m; ++j) probs[j] = (float)((1 - EPS) * (double)probs[j] + EPS * noise[j]);
 }
 
 /* ------------------------------------------------------------------------------------------ */

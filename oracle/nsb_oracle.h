@@ -13,9 +13,12 @@
  *   pack       : UNPINNED — FeatureStackComptime lives in libnshogi (un-vendored, unpinned,
  *                           absent); channel order follows src/evaluate/preset.h:20-66, plane
  *                           semantics follow SURVEY.md App. A.2 and are builder-defined.
- *   decode     : order of operations pinned by src/mcts/feedworker.cc:100-136 and
- *                src/selfplay/frame.cc:93-118; ml::math::softmax_ itself is libnshogi
- *                (UNPINNED, assumed max-subtracted exp / sum, T = 1).
+ *   decode     : order of operations and NaN semantics pinned by src/mcts/feedworker.cc:56-136
+ *                (three pieces: :58-85 value fallback, :100-103 one-move shortcut, :105-127 gather
+ *                + logit fallback + softmax) and src/selfplay/frame.cc:93-136; ml::math::softmax_
+ *                itself is libnshogi (UNPINNED, assumed max-subtracted exp / sum, T = 1).
+ *   cache      : PINNED   — restates src/mcts/evalcache.cc:17-169; checked operation by operation
+ *                           against the reference's evalcache.cc compiled here (oracle/_ref).
  *   forward    : UNPINNED — the reference's forward is TensorRT on an external ONNX (neither
  *                           present); the oracle is the fp32 definition of OUR canonical net.
  */
@@ -38,7 +41,17 @@ void nsb_oracle_expand(const nsb_feature_bitboard* fb, size_t n, int channels, i
 /* position -> 86 feature bitboards, channel order of reference src/evaluate/preset.h:20-66. */
 void nsb_oracle_pack(const nsb_position* pos, size_t n, nsb_feature_bitboard* fb);
 
-/* reference src/mcts/feedworker.cc:100-136 (mode PROBS) / src/selfplay/frame.cc:96-114 (LOGITS). */
+/* reference src/mcts/feedworker.cc:56-136 (mode PROBS; | NSB_DECODE_NAN_FALLBACK = feedResult<true>, the
+ * default is the reference's: off, src/context.h:103) / src/selfplay/frame.cc:93-118 (LOGITS = the gather,
+ * BOTH = the whole of setEvaluation<false> before the Dirichlet mix; row_flags: NSB_ROW_SKIP_SOFTMAX). */
+void nsb_oracle_decode_ex(const float* policy, const float* win, const float* draw, size_t n,
+                          const uint32_t* move_off, const uint16_t* move_idx, int mode, const uint8_t* row_flags,
+                          float* legal_out, float* logits_out, uint8_t* nan_flag);
+/* feedworker.cc:58-85: NaN win / draw rate replaced from the parent's statistics; returns NaNFound. */
+int nsb_oracle_value_fallback(float* win, float* draw, int has_parent, double parent_win_acc,
+                              double parent_draw_acc, uint64_t parent_visits);
+/* frame.cc:121-133: p = (float)(0.75 * (double)p + 0.25 * noise) at the AlphaZero root of a full search. */
+void nsb_oracle_dirichlet_mix(float* probs, const double* noise, uint32_t m);
 void nsb_oracle_decode(const float* policy, const float* win, const float* draw, size_t n,
                        const uint32_t* move_off, const uint16_t* move_idx, int mode,
                        float* legal_out, uint8_t* nan_flag);

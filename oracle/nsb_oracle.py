@@ -44,6 +44,13 @@ def lib() -> C.CDLL:
         l.nsb_oracle_pack.restype = None
         l.nsb_oracle_decode.argtypes = [_P, _P, _P, C.c_size_t, _P, _P, C.c_int, _P, _P]
         l.nsb_oracle_decode.restype = None
+        l.nsb_oracle_decode_ex.argtypes = [_P, _P, _P, C.c_size_t, _P, _P, C.c_int, _P, _P, _P, _P]
+        l.nsb_oracle_decode_ex.restype = None
+        l.nsb_oracle_value_fallback.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_double, C.c_double,
+                                                C.c_uint64]
+        l.nsb_oracle_value_fallback.restype = C.c_int
+        l.nsb_oracle_dirichlet_mix.argtypes = [_P, _P, C.c_uint32]
+        l.nsb_oracle_dirichlet_mix.restype = None
         l.nsb_oracle_forward.argtypes = [C.POINTER(NetDesc), _P, _P, C.c_size_t, C.c_int, _P, _P, _P]
         l.nsb_oracle_forward.restype = None
         l.nsb_oracle_rng_create.argtypes = [C.c_uint64]
@@ -90,17 +97,54 @@ def decode(policy, win, draw, off, idx, mode: int):
     return out, flag
 
 
+def decode_ex(policy, win, draw, off, idx, mode: int, row_flags=None, want_logits: bool = False):
+    """nsb_oracle_decode_ex: returns (legal, logits or None, nan_flag)."""
+    policy = np.ascontiguousarray(policy, dtype=np.float32)
+    win = np.ascontiguousarray(win, dtype=np.float32)
+    draw = np.ascontiguousarray(draw, dtype=np.float32)
+    off = np.ascontiguousarray(off, dtype=np.uint32)
+    idx = np.ascontiguousarray(idx, dtype=np.uint16)
+    n = len(win)
+    out = np.zeros(int(off[n]), dtype=np.float32)
+    logits = np.zeros(int(off[n]), dtype=np.float32) if want_logits else None
+    flag = np.zeros(n, dtype=np.uint8)
+    rf = None if row_flags is None else np.ascontiguousarray(row_flags, dtype=np.uint8)
+    lib().nsb_oracle_decode_ex(policy.ctypes.data, win.ctypes.data, draw.ctypes.data, n, off.ctypes.data, idx.ctypes.data,
+                               mode, None if rf is None else rf.ctypes.data, out.ctypes.data,
+                               None if logits is None else logits.ctypes.data, flag.ctypes.data)
+    return out, logits, flag
+
+
+def value_fallback(win: float, draw: float, has_parent: bool, parent_win_acc: float = 0.0, parent_draw_acc: float = 0.0,
+                   parent_visits: int = 1):
+    """feedworker.cc:58-85; returns (win, draw, NaNFound)."""
+    w, d = C.c_float(win), C.c_float(draw)
+    f = lib().nsb_oracle_value_fallback(C.byref(w), C.byref(d), int(has_parent), parent_win_acc, parent_draw_acc,
+                                        parent_visits)
+    return float(w.value), float(d.value), bool(f)
+
+
+def dirichlet_mix(probs, noise):
+    """frame.cc:121-133."""
+    p = np.ascontiguousarray(probs, dtype=np.float32).copy()
+    nz = np.ascontiguousarray(noise, dtype=np.float64)
+    assert len(nz) >= len(p)
+    lib().nsb_oracle_dirichlet_mix(p.ctypes.data, nz.ctypes.data, len(p))
+    return p
+
+
 def rank_rows(legal, off, flags=None):
     """Edge order after reference src/mcts/node.h:163-168 (Node::sort: std::sort of a node's edges by decreasing
     probability, called from feedworker.cc:129): per CSR row the permutation `order` with legal[order] non-increasing.
     std::sort leaves the order of equal elements unspecified; the restatement fixes it (lower index first = a stable
-    sort), which is one of the results std::sort may produce.  Rows flagged NaN keep the generation order."""
+    sort), which is one of the results std::sort may produce.  A uniform row (the NaN-logit fallback) therefore keeps
+    the generation order, and so does - by definition of the executor - a row that contains NaNs."""
     legal = np.asarray(legal, dtype=np.float32)
     off = np.asarray(off, dtype=np.int64)
     order = np.zeros(int(off[-1]), dtype=np.uint16)
     for b in range(len(off) - 1):
         row = legal[off[b]:off[b + 1]]
-        if flags is not None and flags[b]:
+        if np.isnan(row).any():     # std::sort over NaNs is undefined in the reference; the executor defines: identity
             order[off[b]:off[b + 1]] = np.arange(len(row), dtype=np.uint16)
         else:
             order[off[b]:off[b + 1]] = np.argsort(-row.astype(np.float64), kind="stable").astype(np.uint16)

@@ -72,3 +72,36 @@ def softmax_rows(policy, off, idx):
         e = np.exp(g - g.max())
         out[off[i]:off[i + 1]] = e / e.sum()
     return out
+
+
+def drift_metrics(nb, orc, desc, blob, fb, n, got, off, idx):
+    """Drift of an executor result `got` = (logits [n,2187], win, draw) against the oracle at both precisions, on the
+    bitboards `fb`: the numbers of DESIGN.md §4's drift table and of tests/test_depth_parity.py.
+      *_vs_bf16 : against oracle.forward(emulate_bf16=True) - same rounding points as the kernels (bf16 inputs, weights
+                  and activations, fp32 accumulation); what is left is accumulation order
+      *_vs_fp32 : against oracle.forward(emulate_bf16=False) - the precision bar of the north star (the reference's
+                  TensorRT path has fp32 I/O with TF32 allowed, src/infer/trt.cc:144-161): decoded probabilities,
+                  KL(fp32 || got) per row, win / draw rate
+      oracle_*  : the bf16-emulating oracle against the fp32 oracle, i.e. the share of the drift that is bf16 itself"""
+    planes = orc.expand(fb, n)
+    pb, wb, db = orc.forward(desc, blob, planes, emulate_bf16=True)
+    pf, wf, df = orc.forward(desc, blob, planes, emulate_bf16=False)
+    gp, gw, gd = got
+    qg, _ = orc.decode(gp, gw, gd, off, idx, nb.DECODE_PROBS)
+    qb, _ = orc.decode(pb, wb, db, off, idx, nb.DECODE_PROBS)
+    qf, _ = orc.decode(pf, wf, df, off, idx, nb.DECODE_PROBS)
+    kl = 0.0
+    for i in range(n):
+        a, b = qf[off[i]:off[i + 1]].astype(np.float64), qg[off[i]:off[i + 1]].astype(np.float64)
+        m = a > 0
+        kl = max(kl, float(np.sum(a[m] * np.log(a[m] / np.maximum(b[m], 1e-300)))))
+    f = lambda x: float(np.max(np.abs(x))) if x.size else 0.0
+    return {
+        "layers": 2 * desc.blocks + 2, "n": n, "logit_rms_fp32": float(np.sqrt(np.mean(pf.astype(np.float64) ** 2))),
+        "logit_vs_bf16": f(gp - pb), "logit_vs_bf16_mean": float(np.mean(np.abs(gp - pb))),
+        "value_vs_bf16": max(f(gw - wb), f(gd - db)),
+        "logit_vs_fp32": f(gp - pf), "prob_vs_fp32": f(qg - qf), "kl_vs_fp32": kl,
+        "win_vs_fp32": f(gw - wf), "draw_vs_fp32": f(gd - df),
+        "oracle_prob_bf16_vs_fp32": f(qb - qf), "oracle_value_bf16_vs_fp32": max(f(wb - wf), f(db - df)),
+        "win_spread_fp32": float(np.ptp(wf)) if n > 1 else 0.0, "max_prob_fp32": float(qf.max()) if qf.size else 0.0,
+    }

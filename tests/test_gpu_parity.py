@@ -102,26 +102,40 @@ def test_pack_bit_exact(nb, orc, synth, ctx128, n):
 
 # ---- decode ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 64, 1000])
-@pytest.mark.parametrize("mode", [0, 1])
-def test_decode_matches_oracle(nb, orc, synth, ctx128, n, mode):
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("fallback", [False, True])
+def test_decode_matches_oracle(nb, orc, synth, ctx128, n, kind, fallback):
+    """Standalone decode kernel vs the oracle for every mode (PROBS = feedworker.cc:100-136, LOGITS / BOTH =
+    frame.cc:93-118), with and without the NaN fallback (feedResult<true> / the reference's default <false>), Gumbel
+    root rows (softmax skipped) and raw logits beside the probabilities.  synth.random_logits plants an all-NaN
+    logit row (5), a partly-NaN one (6), -inf logits (7), a NaN win rate (8) and a NaN draw rate (9)."""
     ctx = ctx128[0]
+    mode = kind | (nb.DECODE_NAN_FALLBACK if fallback else 0)
     policy, win, draw = synth.random_logits(n, seed=n)
     off, idx = synth.random_legal_moves(n, seed=n)
-    d = [nb.DeviceBuffer.from_host(a) for a in (policy, win, draw, off, idx)]
-    d_out = nb.DeviceBuffer(max(int(off[-1]), 1) * 4)
-    d_flag = nb.DeviceBuffer(n)
-    ctx.decode_device(0, d[0].ptr, d[1].ptr, d[2].ptr, n, d[3].ptr, d[4].ptr, mode, d_out.ptr, d_flag.ptr)
+    rf = (np.arange(n) % 5 == 2).astype(np.uint8) * nb.ROW_SKIP_SOFTMAX
+    total = int(off[-1])
+    d = [nb.DeviceBuffer.from_host(a) for a in (policy, win, draw, off, idx, rf)]
+    d_out, d_log, d_flag = nb.DeviceBuffer(max(total, 1) * 4), nb.DeviceBuffer(max(total, 1) * 4), nb.DeviceBuffer(n)
+    d_log.fill(0)
+    ctx.decode_device_ex(0, d[0].ptr, d[1].ptr, d[2].ptr, n, d[3].ptr, d[4].ptr, mode, d[5].ptr, d_out.ptr, d_log.ptr, d_flag.ptr)
     ctx.await_(0)
-    got = d_out.to_host((int(off[-1]),), np.float32)
-    flag = d_flag.to_host((n,), np.uint8)
-    want, wflag = orc.decode(policy, win, draw, off, idx, mode)
+    got, got_log, flag = d_out.to_host((total,), np.float32), d_log.to_host((total,), np.float32), d_flag.to_host((n,), np.uint8)
+    want, want_log, wflag = orc.decode_ex(policy, win, draw, off, idx, mode, row_flags=rf, want_logits=True)
     assert np.array_equal(flag, wflag)
-    if mode == nb.DECODE_LOGITS:
+    if n >= 64:
+        assert list(np.nonzero(flag)[0]) == ([5, 6, 8, 9] if fallback else [])
+    if kind == nb.DECODE_LOGITS:
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     else:
-        assert np.allclose(got, want, rtol=TOL_DECODE_REL, atol=1e-9)
-    for b in d + [d_out, d_flag]:
-        b.free()
+        assert np.array_equal(np.isnan(got), np.isnan(want))          # NaN rows: the same rows, whatever the payload
+        assert np.allclose(got, want, rtol=TOL_DECODE_REL, atol=1e-9, equal_nan=True)
+        if kind == nb.DECODE_BOTH:
+            assert np.array_equal(got_log.view(np.uint32), want_log.view(np.uint32))
+            for i in np.nonzero(rf)[0]:                                # Gumbel root: the raw logits, bit for bit
+                assert np.array_equal(got[off[i]:off[i + 1]].view(np.uint32), want_log[off[i]:off[i + 1]].view(np.uint32))
+    for b_ in d + [d_out, d_log, d_flag]:
+        b_.free()
 
 
 # ---- forward ----------------------------------------------------------------------------------------------------
@@ -688,42 +702,171 @@ def test_rank_order_of_decoded_rows(nb, orc, synth, monkeypatch, channels, slots
         a.free()
 
 
-def test_rank_order_nan_rows_and_cache_hits(nb, orc, synth):
-    """A NaN row keeps the generation order (its probabilities are uniform, feedworker.cc:111-118); rows served from
-    the device cache are ranked like evaluated ones."""
-    desc = nb.net_desc(128, 1)
+def _nan_case_blobs(nb, desc, blob):
+    """Three nets that produce NaNs in different places: the draw-rate bias (every position's draw rate is NaN, its
+    logits are fine), the bias of policy plane 3 (a NaN logit in every row that gathers a slot of that plane, values
+    fine), and both."""
+    out = {}
+    for name in ("draw", "logit", "both"):
+        b = blob.copy()
+        w = helpers.split_blob(desc, b)      # views into b
+        if name in ("draw", "both"):
+            w["fc2_b"][1] = np.nan
+        if name in ("logit", "both"):
+            w["pol_b"][3] = np.nan
+        out[name] = b
+    return out
+
+
+@pytest.mark.parametrize("channels,slots", [(128, 1), (128, 2), (256, 1)])
+def test_nan_semantics_follow_feedworker(nb, orc, synth, monkeypatch, channels, slots):
+    """The four cases of FeedWorker::feedResult<NaNFallbackEnabled> (src/mcts/feedworker.cc:56-137) on every trunk
+    kernel, fused decode with rank order:
+      fallback on,  NaN draw rate  (:58-85)  -> nan_flag, the row keeps its ORDINARY softmax and rank order
+      fallback on,  NaN logit      (:105-118)-> nan_flag, uniform row, identity order; 1-move rows untouched (:100-103)
+      fallback off (reference default, src/context.h:103): nan_flag stays 0; NaN logits flow through the softmax
+                    (the whole row is NaN, identity order); a NaN draw rate changes nothing
+    and the reference's cache rule (:134: store iff !NaNFound): flagged rows are evaluated again, unflagged ones hit."""
+    monkeypatch.delenv("NSB_TRUNK128", raising=False)
+    monkeypatch.delenv("NSB_IO", raising=False)
+    desc = nb.net_desc(channels, 1)
     blob = nb.random_blob(desc, 17)
-    blob_nan = blob.copy()
-    blob_nan[-1] = np.nan                                   # draw-rate bias: every row is flagged
+    blobs = _nan_case_blobs(nb, desc, blob)
     n = 33
     pos = synth.random_positions(n, seed=9)
-    off, idx = synth.random_legal_moves(n, seed=9, edge_rows=False)
+    off, idx = synth.random_legal_moves(n, seed=9)          # edge rows: 1, 164, 165, 593, 2 moves
     total = int(off[-1])
     hashes = np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(7)
+    touches = np.array([np.any(idx[off[b]:off[b + 1]] // 81 == 3) for b in range(n)])   # rows that gather plane 3
+    one_move = np.diff(off) == 1
+    assert touches.sum() > 5 and (~touches).sum() >= 1 and one_move[0]
 
-    def call(ctx, use_cache):
+    def call(ctx, mode, use_cache=False):
         legal, order = np.zeros(total, dtype=np.float32), np.full(total, 0xFFFF, dtype=np.uint16)
         win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
-        flag, hit = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
-        ctx.eval_request_async(0, n, off, idx, nb.DECODE_PROBS, legal, win, draw, positions=pos, order_out=order,
+        flag, hit = np.full(n, 9, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+        ctx.eval_request_async(slots - 1, n, off, idx, mode, legal, win, draw, positions=pos, order_out=order,
                                nan_flag=flag, hashes=hashes if use_cache else None, hit_flag=hit if use_cache else None)
-        ctx.await_(0)
-        return legal, order, flag, hit
+        ctx.await_(slots - 1)
+        return legal, order, flag, hit, win, draw
 
-    with nb.Context(desc, batch_max=n, blob=blob_nan) as ctx:
-        legal, order, flag, _ = call(ctx, False)
-        assert flag.all()
-        assert np.array_equal(order, orc.rank_rows(legal, off, flag))
-        for b in range(n):
-            assert np.array_equal(order[off[b]:off[b + 1]], np.arange(off[b + 1] - off[b]))
-    with nb.Context(desc, batch_max=n, blob=blob) as ctx:
-        ctx.cache_create(4)
-        first = call(ctx, True)
-        again = call(ctx, True)
-        cacheable = np.diff(off) <= 164
-        assert first[3].sum() == 0 and np.array_equal(again[3].astype(bool), cacheable)
-        assert np.array_equal(again[0].view(np.uint32), first[0].view(np.uint32))
-        assert np.array_equal(again[1], first[1]) and np.array_equal(first[1], orc.rank_rows(first[0], off, first[2]))
+    with nb.Context(desc, batch_max=n, slots=slots, blob=blob) as ctx:
+        clean = call(ctx, nb.DECODE_PROBS)
+    assert not clean[2].any() and np.array_equal(clean[1], orc.rank_rows(clean[0], off))
+    F = nb.DECODE_NAN_FALLBACK
+    for case, bl in blobs.items():
+        with nb.Context(desc, batch_max=n, slots=slots, blob=bl) as ctx:
+            dense = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+            dw, dd = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+            ctx.eval_positions_async(0, pos, n, dense, dw, dd)
+            ctx.await_(0)
+            assert np.isnan(dd).all() == (case != "logit") and np.isnan(dense[:, 3 * 81:4 * 81]).all() == (case != "draw")
+            for mode in (nb.DECODE_PROBS | F, nb.DECODE_PROBS):
+                legal, order, flag, _, win, draw = call(ctx, mode)
+                want, wflag = orc.decode(dense, dw, dd, off, idx, mode)           # the oracle on the GPU's own logits
+                assert np.array_equal(flag, wflag), (case, mode)
+                assert np.array_equal(np.isnan(legal), np.isnan(want)), (case, mode)
+                assert np.allclose(legal, want, rtol=TOL_DECODE_REL, atol=1e-9, equal_nan=True), (case, mode)
+                assert np.array_equal(order, orc.rank_rows(legal, off)), (case, mode)
+                assert np.array_equal(np.isnan(draw), np.isnan(dd)) and np.array_equal(win, dw)   # values come back as they are
+                logit_rows = touches & ~one_move if case != "draw" else np.zeros(n, dtype=bool)
+                if mode & F:
+                    assert np.array_equal(flag.astype(bool), logit_rows if case == "logit" else np.ones(n, dtype=bool))
+                else:
+                    assert not flag.any()
+                for b in range(n):
+                    row, o = legal[off[b]:off[b + 1]], order[off[b]:off[b + 1]]
+                    if logit_rows[b]:
+                        assert np.array_equal(o, np.arange(len(row)))                      # uniform or all-NaN: identity
+                        if mode & F:
+                            assert np.allclose(row, 1.0 / len(row), rtol=1e-6)            # feedworker.cc:111-118
+                        else:
+                            assert np.isnan(row).all()
+                    elif case == "draw":                                                   # policy untouched: the clean net's row
+                        assert np.array_equal(row.view(np.uint32), clean[0][off[b]:off[b + 1]].view(np.uint32))
+                        assert np.array_equal(o, clean[1][off[b]:off[b + 1]])
+            # the cache follows NaNFound (feedworker.cc:134)
+            for mode in (nb.DECODE_PROBS | F, nb.DECODE_PROBS):
+                ctx.cache_create(4) if mode & F else ctx.cache_clear()
+                first = call(ctx, mode, use_cache=True)
+                again = call(ctx, mode, use_cache=True)
+                cacheable = (np.diff(off) <= 164) & ~first[2].astype(bool)
+                assert first[3].sum() == 0 and np.array_equal(again[3].astype(bool), cacheable), (case, mode)
+                assert np.array_equal(np.isnan(again[0]), np.isnan(first[0]))
+                assert np.array_equal(again[1], first[1])                                  # hits are ranked like evaluated rows
+
+
+def test_selfplay_decode_in_one_launch(nb, orc, synth, monkeypatch):
+    """NSB_DECODE_BOTH = Frame::setEvaluation<false> (src/selfplay/frame.cc:93-118) in one evaluation: the raw logits
+    go to the device cache (:110-114), the caller receives probabilities (:116-118) - raw logits at Gumbel roots
+    (NSB_ROW_SKIP_SOFTMAX) - and, if asked, the raw logits as well; rows served from the cache take the same route and
+    give the same bits as evaluated ones.  Against the oracle's restatement on the GPU's own dense logits; the
+    Dirichlet mix of the AlphaZero root (:121-133) is host code, checked in nsb_host_unit."""
+    monkeypatch.delenv("NSB_IO", raising=False)
+    for channels, slots in ((128, 1), (128, 2), (256, 1)):
+        desc = nb.net_desc(channels, 2)
+        blob = nb.random_blob(desc, 5)
+        n = 61
+        pos = synth.random_positions(n, seed=12)
+        off, idx = synth.random_legal_moves(n, seed=12)
+        total = int(off[-1])
+        rf = (np.arange(n) % 7 == 1).astype(np.uint8) * nb.ROW_SKIP_SOFTMAX
+        rf[1] = nb.ROW_SKIP_SOFTMAX                       # a cacheable 164-move row that is a Gumbel root
+        hashes = np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(11)
+        P = nb.PinnedArray
+        hp = {k: P(a.shape, a.dtype) for k, a in dict(pos=pos, off=off, idx=idx, rf=rf, hashes=hashes).items()}
+        for k, a in dict(pos=pos, off=off, idx=idx, rf=rf, hashes=hashes).items():
+            hp[k].array[...] = a
+        o = dict(legal=P((total,), np.float32), logits=P((total,), np.float32), order=P((total,), np.uint16),
+                 win=P((n,), np.float32), draw=P((n,), np.float32), flag=P((n,), np.uint8), hit=P((n,), np.uint8))
+
+        def call(ctx, direct, use_cache, row_flags=True, want_logits=True):
+            for a in o.values():
+                a.array[...] = 0
+            ctx.set_io_mode(direct)
+            ctx.eval_request_async(slots - 1, n, hp["off"].array, hp["idx"].array, nb.DECODE_BOTH, o["legal"].array, o["win"].array,
+                                   o["draw"].array, positions=hp["pos"].array, order_out=o["order"].array, nan_flag=o["flag"].array,
+                                   hashes=hp["hashes"].array if use_cache else None, hit_flag=o["hit"].array if use_cache else None,
+                                   row_flags=hp["rf"].array if row_flags else None, logits_out=o["logits"].array if want_logits else None)
+            ctx.await_(slots - 1)
+            return {k: a.array.copy() for k, a in o.items()}
+
+        with nb.Context(desc, batch_max=n, slots=slots, blob=blob) as ctx:
+            dense = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+            dw, dd = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+            ctx.eval_positions_async(0, pos, n, dense, dw, dd)
+            ctx.await_(0)
+            want, want_log, _ = orc.decode_ex(dense, dw, dd, off, idx, nb.DECODE_BOTH, row_flags=rf, want_logits=True)
+            ctx.cache_create(8)
+            plain = call(ctx, False, False)
+            assert np.array_equal(plain["logits"].view(np.uint32), want_log.view(np.uint32))      # gather: bit-exact
+            assert np.allclose(plain["legal"], want, rtol=TOL_DECODE_REL, atol=1e-9)
+            for b in np.nonzero(rf)[0]:
+                assert np.array_equal(plain["legal"][off[b]:off[b + 1]].view(np.uint32), want_log[off[b]:off[b + 1]].view(np.uint32))
+            assert np.array_equal(plain["order"], orc.rank_rows(plain["legal"], off)) and not plain["flag"].any()
+            miss = call(ctx, True, True)                  # fills the cache with RAW LOGITS
+            hit = call(ctx, False, True)                  # served from it: softmax of the stored logits
+            hit_direct = call(ctx, True, True, want_logits=False)
+            cacheable = np.diff(off) <= 164
+            assert miss["hit"].sum() == 0 and np.array_equal(hit["hit"].astype(bool), cacheable)
+            for r in (miss, hit, hit_direct):
+                for k in ("legal", "win", "draw", "order"):
+                    assert np.array_equal(r[k].view(np.uint32) if r[k].dtype == np.float32 else r[k],
+                                          plain[k].view(np.uint32) if plain[k].dtype == np.float32 else plain[k]), k
+            assert np.array_equal(hit["logits"].view(np.uint32), plain["logits"].view(np.uint32))
+            # what the cache holds is the raw logits (frame.cc:110-114): a LOGITS-mode probe returns them unchanged
+            for a in o.values():
+                a.array[...] = 0
+            ctx.eval_request_async(slots - 1, n, hp["off"].array, hp["idx"].array, nb.DECODE_LOGITS, o["legal"].array, o["win"].array,
+                                   o["draw"].array, positions=hp["pos"].array, hashes=hp["hashes"].array, hit_flag=o["hit"].array)
+            ctx.await_(slots - 1)
+            assert np.array_equal(o["legal"].array.view(np.uint32), plain["logits"].view(np.uint32)) and o["hit"].array.sum() == cacheable.sum()
+            # without row flags every row is softmaxed
+            noflags = call(ctx, False, False, row_flags=False)
+            want2, _, _ = orc.decode_ex(dense, dw, dd, off, idx, nb.DECODE_BOTH)
+            assert np.allclose(noflags["legal"], want2, rtol=TOL_DECODE_REL, atol=1e-9)
+        for a in list(hp.values()) + list(o.values()):
+            a.free()
 
 
 def test_graft_entry_smoke():
@@ -804,7 +947,8 @@ def test_api_modes_differential_fuzz_short():
 
 def test_request_validation(nb, synth):
     """nsb_eval_request_async reports malformed requests instead of launching: both / neither input kind, a cache request
-    without a cache, a bad decode mode, offsets that do not start at 0 or exceed 593 moves per position."""
+    without a cache, a bad decode mode, offsets that do not start at 0, decrease, or give a row more than 593 moves;
+    a policy slot beyond 2186 (a caller's bug the reference would assert on) reads the last slot instead of faulting."""
     desc = nb.net_desc(128, 1)
     n = 4
     pos = synth.random_positions(n, seed=1)
@@ -831,8 +975,29 @@ def test_request_validation(nb, synth):
         with pytest.raises(nb.NsbError):
             ctx.eval_request_async(0, n, off_big, np.zeros(int(off_big[-1]), dtype=np.uint16), nb.DECODE_PROBS,
                                    np.zeros(int(off_big[-1]), dtype=np.float32), win, draw, **ok)
+        off_dec = off.copy()
+        off_dec[2] = off_dec[1] - 1                                                               # decreasing offsets
+        with pytest.raises(nb.NsbError):
+            ctx.eval_request_async(0, n, off_dec, idx, nb.DECODE_PROBS, legal, win, draw, **ok)
+        off_row = np.array([0, 594, 595, 596, 597], dtype=np.uint32)                               # one row of 594 moves
+        with pytest.raises(nb.NsbError):
+            ctx.eval_request_async(0, n, off_row, np.zeros(597, dtype=np.uint16), nb.DECODE_PROBS, np.zeros(597, dtype=np.float32),
+                                   win, draw, **ok)
+        for bad_mode in (3, 0x200, nb.DECODE_NAN_FALLBACK | 3):
+            with pytest.raises(nb.NsbError):
+                ctx.eval_request_async(0, n, off, idx, bad_mode, legal, win, draw, **ok)
         with pytest.raises(nb.NsbError):
             ctx.eval_request_async(0, n + 1, off, idx, nb.DECODE_PROBS, legal, win, draw, **ok)    # > batch_max
         assert ctx.launch_count() == l0                                                            # nothing was launched
         ctx.eval_request_async(0, 0, off, idx, nb.DECODE_PROBS, legal, win, draw, **ok)            # n = 0 is a no-op
         assert ctx.launch_count() == l0
+        idx_oob = idx.copy()
+        idx_oob[:3] = [2187, 40000, 65535]                                                         # clamped to slot 2186
+        idx_ref = idx.copy()
+        idx_ref[:3] = 2186
+        l_oob, l_ref = np.zeros_like(legal), np.zeros_like(legal)
+        ctx.eval_request_async(0, n, off, idx_oob, nb.DECODE_LOGITS, l_oob, win, draw, **ok)
+        ctx.await_(0)
+        ctx.eval_request_async(0, n, off, idx_ref, nb.DECODE_LOGITS, l_ref, win, draw, **ok)
+        ctx.await_(0)
+        assert np.array_equal(l_oob.view(np.uint32), l_ref.view(np.uint32))

@@ -39,7 +39,7 @@ def test_host_headers_compile_against_reference_interface(built):
         pytest.skip("reference tree not present on this box")
     src = '#include "infer_b200.h"\nint main() { return sizeof(nshogi::engine::infer::B200) > 0 ? 0 : 1; }\n'
     cmd = ["g++", "-std=c++20", "-fsyntax-only", "-x", "c++", "-", f"-I{ref}", f"-I{HOST}",
-           f"-I{os.path.join(ROOT, 'include')}", f"-I{os.path.join(ROOT, 'oracle', 'shim')}"]
+           f"-I{os.path.join(ROOT, 'include')}", f"-I{os.path.join(HOST, 'shim')}"]
     out = subprocess.run(cmd, input=src, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
 
@@ -100,7 +100,7 @@ def test_leaf_queue_protocol_under_thread_sanitizer(built, tmp_path):
     with its handle, hash and CSR span - built with -fsanitize=thread (the reference's own race-detection practice,
     SURVEY.md §5), which must stay silent."""
     inc = ["-I" + HOST, "-I" + os.path.join(HOST, "shim"), "-I" + os.path.join(ROOT, "include"),
-           "-I" + os.path.join(ROOT, "oracle", "shim")]
+           "-I" + os.path.join(HOST, "shim")]
     exe = str(tmp_path / "unit_tsan")
     r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", *inc, "-o", exe,
                         os.path.join(HOST, "host_unit.cc"), "-lpthread"], capture_output=True, text=True, timeout=300)

@@ -132,27 +132,90 @@ def test_startpos_has_40_pieces(orc, synth):
     assert planes[0, :28].sum() == 40 and planes[0, 28:80].sum() == 0
 
 
-# ---- decode (reference src/mcts/feedworker.cc:100-136, src/selfplay/frame.cc:93-118) -----------------------
+# ---- decode (reference src/mcts/feedworker.cc:56-136, src/selfplay/frame.cc:93-136) ------------------------
 def test_decode_properties(orc, nb, synth):
+    """synth.random_logits: row 5 all-NaN logits, row 6 some NaN logits, row 7 -inf logits, row 8 NaN win rate,
+    row 9 NaN draw rate.  The four cases of FeedWorker::feedResult<NaNFallbackEnabled>:
+      fallback on,  NaN logit (:105-118)  -> uniform row, NaNFound
+      fallback on,  NaN win/draw (:58-85) -> NaNFound, the row keeps its normal softmax
+      fallback off (the reference's default, context.h:103), NaN logit -> NaNs flow through softmax_, no flag
+      fallback off, NaN win/draw          -> nothing happens to the row, no flag"""
     n = 64
     policy, win, draw = synth.random_logits(n, seed=1)
     off, idx = synth.random_legal_moves(n, seed=1)
-    probs, flag = orc.decode(policy, win, draw, off, idx, nb.DECODE_PROBS)
-    logits, flag2 = orc.decode(policy, win, draw, off, idx, nb.DECODE_LOGITS)
-    assert np.array_equal(flag, flag2)
-    assert flag[5] == 1 and flag[8] == 1 and flag[9] == 1 and flag[0] == 0
-    assert probs[off[0]] == 1.0 and off[1] - off[0] == 1      # 1-move shortcut (feedworker.cc:101-103)
+    ref = helpers.softmax_rows(np.nan_to_num(policy, nan=0.0), off, idx)
+    rows = lambda a, i: a[off[i]:off[i + 1]]
+    for fallback in (True, False):
+        mode = nb.DECODE_PROBS | (nb.DECODE_NAN_FALLBACK if fallback else 0)
+        probs, flag = orc.decode(policy, win, draw, off, idx, mode)
+        logits, flag2 = orc.decode(policy, win, draw, off, idx, nb.DECODE_LOGITS | (mode & nb.DECODE_NAN_FALLBACK))
+        assert probs[off[0]] == 1.0 and off[1] - off[0] == 1      # 1-move shortcut (feedworker.cc:101-103)
+        if fallback:
+            assert list(np.nonzero(flag)[0]) == [5, 6, 8, 9] and np.array_equal(flag, flag2)
+        else:
+            assert not flag.any() and not flag2.any()
+        for i in range(n):
+            row, m = rows(probs, i), int(off[i + 1] - off[i])
+            g = policy[i, idx[off[i]:off[i + 1]]]
+            assert np.array_equal(rows(logits, i).view(np.uint32), g.view(np.uint32))   # raw gather
+            if i in (5, 6) and m > 1:
+                if fallback:     # NaN logit -> every legal logit := 1 -> uniform (feedworker.cc:111-118)
+                    assert np.allclose(row, 1.0 / m, rtol=1e-6)
+                elif np.isnan(g).any():
+                    assert np.isnan(row).all()
+                continue
+            # rows 8 / 9 (NaN win / draw): the policy is the ordinary softmax either way
+            assert abs(row.sum() - 1.0) < 1e-5
+            if m > 1:
+                assert np.allclose(row, rows(ref, i), rtol=2e-6, atol=1e-9)
+    # a 1-move row never looks at its logit (:100-103), even when it is NaN and the fallback is on
+    policy1 = policy.copy()
+    policy1[0, :] = np.nan
+    probs, flag = orc.decode(policy1, win, draw, off, idx, nb.DECODE_PROBS | nb.DECODE_NAN_FALLBACK)
+    assert probs[off[0]] == 1.0 and flag[0] == 0
+
+
+def test_decode_selfplay_flavour(orc, nb, synth):
+    """Frame::setEvaluation<false> (frame.cc:93-136): raw logits (what the cache keeps) + softmax; no 1-move shortcut;
+    the Gumbel root skips the softmax; no NaN handling unless the reporting bit is set."""
+    n = 40
+    policy, win, draw = synth.random_logits(n, seed=3)
+    off, idx = synth.random_legal_moves(n, seed=3)
+    rf = np.zeros(n, dtype=np.uint8)
+    rf[[2, 11]] = nb.ROW_SKIP_SOFTMAX
+    probs, logits, flag = orc.decode_ex(policy, win, draw, off, idx, nb.DECODE_BOTH, row_flags=rf, want_logits=True)
+    raw, _ = orc.decode(policy, win, draw, off, idx, nb.DECODE_LOGITS)
+    assert np.array_equal(logits.view(np.uint32), raw.view(np.uint32)) and not flag.any()
     ref = helpers.softmax_rows(np.nan_to_num(policy, nan=0.0), off, idx)
     for i in range(n):
-        row = probs[off[i]:off[i + 1]]
-        assert abs(row.sum() - 1.0) < 1e-5
-        m = off[i + 1] - off[i]
-        if flag[i] and m > 1:      # NaN fallback -> uniform (feedworker.cc:111-118)
-            assert np.allclose(row, 1.0 / m, rtol=1e-6)
-        elif m > 1:
+        row, g = probs[off[i]:off[i + 1]], raw[off[i]:off[i + 1]]
+        if rf[i]:
+            assert np.array_equal(row.view(np.uint32), g.view(np.uint32))
+        elif np.isnan(g).any():
+            assert np.isnan(row).all()
+        else:
             assert np.allclose(row, ref[off[i]:off[i + 1]], rtol=2e-6, atol=1e-9)
-        g = policy[i, idx[off[i]:off[i + 1]]]
-        assert np.array_equal(logits[off[i]:off[i + 1]].view(np.uint32), g.view(np.uint32))  # raw gather
+    assert probs[off[0]] == 1.0                                   # softmax of one finite logit
+    _, _, flag = orc.decode_ex(policy, win, draw, off, idx, nb.DECODE_BOTH | nb.DECODE_NAN_FALLBACK, row_flags=rf)
+    assert list(np.nonzero(flag)[0]) == [5, 6, 8, 9]
+
+
+def test_value_fallback_and_dirichlet_mix(orc):
+    """feedworker.cc:58-85 and frame.cc:121-133, against hand-computed values."""
+    nan = float("nan")
+    assert orc.value_fallback(0.3, 0.1, True, 5.0, 1.0, 10) == (np.float32(0.3), np.float32(0.1), False)
+    w, d, f = orc.value_fallback(nan, 0.1, True, 6.0, 1.0, 8)
+    assert f and w == np.float32(1.0 - 6.0 / 8.0) and d == np.float32(0.1)
+    w, d, f = orc.value_fallback(0.3, nan, True, 6.0, 1.0, 8)
+    assert f and w == np.float32(0.3) and d == np.float32(1.0 / 8.0)
+    assert orc.value_fallback(nan, nan, False) == (0.5, 0.0, True)
+    rng = np.random.default_rng(4)
+    p = rng.random(50).astype(np.float32)
+    noise = rng.gamma(0.15, 1.0, size=600)
+    noise /= noise.sum()                                          # worker.cc:170-176
+    mixed = orc.dirichlet_mix(p, noise)
+    want = (0.75 * p.astype(np.float64) + 0.25 * noise[:50]).astype(np.float32)
+    assert np.array_equal(mixed.view(np.uint32), want.view(np.uint32))
 
 
 # ---- forward oracle vs PyTorch fp32 ----------------------------------------------------------------------

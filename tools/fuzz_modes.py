@@ -35,7 +35,9 @@ while time.time() < t_end:
     blocks = int(rng.integers(1, 3))
     slots = int(rng.integers(1, 3))
     n = int(rng.choice([1, 2, 3, int(rng.integers(4, 64)), int(rng.integers(64, 700))]))
-    mode = int(rng.choice([nb.DECODE_PROBS, nb.DECODE_LOGITS]))
+    mode = int(rng.choice([nb.DECODE_PROBS, nb.DECODE_LOGITS, nb.DECODE_BOTH]))
+    both = mode == nb.DECODE_BOTH
+    row_flags = (rng.random(n) < 0.2).astype(np.uint8) * nb.ROW_SKIP_SOFTMAX   # Gumbel roots (read in BOTH mode only)
     desc = nb.net_desc(channels, blocks)
     key = (channels, blocks)
     if key not in blobs:
@@ -53,10 +55,10 @@ while time.time() < t_end:
 
     def outs():
         return dict(legal=P((max(total, 1),), np.float32), order=P((max(total, 1),), np.uint16), win=P((n,), np.float32),
-                    draw=P((n,), np.float32), flag=P((n,), np.uint8), hit=P((n,), np.uint8))
+                    draw=P((n,), np.float32), flag=P((n,), np.uint8), hit=P((n,), np.uint8), logits=P((max(total, 1),), np.float32))
 
     h = dict(fb=pinned(fb), pos=pinned(pos), off=pinned(off), idx=pinned(idx if total else np.zeros(1, dtype=np.uint16)),
-             hashes=pinned(hashes))
+             hashes=pinned(hashes), rf=pinned(row_flags))
     res = {}
     with nb.Context(desc, batch_max=n, slots=slots, blob=blob) as ctx:
         ctx.cache_create(8)
@@ -68,7 +70,8 @@ while time.time() < t_end:
                 a.array[...] = 0
             ctx.set_io_mode(direct)
             ctx.eval_request_async(s_last, n, h["off"].array, h["idx"].array, mode, o["legal"].array, o["win"].array, o["draw"].array,
-                                   nan_flag=o["flag"].array, **{k: (v(o) if callable(v) else v) for k, v in kw.items()})
+                                   nan_flag=o["flag"].array, row_flags=h["rf"].array if both else None,
+                                   logits_out=o["logits"].array if both else None, **{k: (v(o) if callable(v) else v) for k, v in kw.items()})
             ctx.await_(s_last)
             res[name] = {k: a.array.copy() for k, a in o.items()}
             for a in o.values():
@@ -85,9 +88,18 @@ while time.time() < t_end:
         r = res[name]
         assert np.array_equal(r["legal"][:total].view(np.uint32), base["legal"][:total].view(np.uint32)), (tag, name, "legal")
         assert np.array_equal(r["win"], base["win"]) and np.array_equal(r["draw"], base["draw"]), (tag, name, "win/draw")
+        assert np.array_equal(r["logits"][:total].view(np.uint32), base["logits"][:total].view(np.uint32)), (tag, name, "logits")
         want = orc.rank_rows(base["legal"][:total], off, base["flag"])
         assert np.array_equal(r["order"][:total], want), (tag, name, "order")
     assert not base["flag"].any(), tag
+    if both:   # Frame::setEvaluation: softmax of the raw logits, skipped at Gumbel roots (frame.cc:116-118)
+        for b in range(n):
+            lg, pr = base["logits"][off[b]:off[b + 1]], base["legal"][off[b]:off[b + 1]]
+            if row_flags[b]:
+                assert np.array_equal(lg.view(np.uint32), pr.view(np.uint32)), (tag, b, "skip")
+            elif len(lg):
+                e = np.exp(lg.astype(np.float64) - lg.max())
+                assert np.allclose(pr, e / e.sum(), rtol=2e-6, atol=1e-9), (tag, b, "softmax")
     assert res["cached_miss"]["hit"].sum() == 0, tag
     # rows of more than 164 moves are never stored; the others are hits the second time unless their store was dropped
     # because another warp held the bundle's lock at that moment (the reference's try_lock semantics, evalcache.cc:58-62)
