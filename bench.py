@@ -1,18 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — leaf evals/sec of the B200 leaf-evaluation path (BASELINE.json metric, config 2).
+"""bench.py — leaf evals/sec of the B200 leaf-evaluation path (BASELINE.json metric).
 
-A step = one batch of 256 synthetic positions through the hot path: feature bitboards ->
-(in-kernel plane expansion) -> 10 x 128 ResNet on tcgen05 -> policy head -> fused legal-move
-gather + softmax + value/draw sigmoids.  One fused kernel launch per step.
+A STEP is a fixed bundle of `config.batches_per_step` batches (so that the timed region is about a second under the
+driver's `--steps 20`, long enough for the board to reach its steady clocks and for the clock sampler to see it); a
+batch is one pass of the hot path over B synthetic positions: feature bitboards -> (in-kernel plane expansion) -> ResNet
+on tcgen05 -> policy head -> fused legal-move gather + softmax + value/draw sigmoids.  One kernel launch per batch.
 
-  value : device-timed (CUDA events on the launch stream), inputs already resident in HBM,
-          rotating over a pool of input batches larger than L2.
-  e2e   : the same step through the host-buffer C-ABI call (nsb_eval_decode_async + nsb_await):
-          pinned host inputs, H2D + kernel + D2H inside the timed region, several slots in flight.
-  --impl reference : the reference's CPU path for its CPU-runnable config (pack + its own Random
-          executor compiled from /root/reference into oracle/_ref + decode) on all host cores.
-Multi-GPU: one process per GPU (torchrun), independent replicas, weak scaling; NCCL only for the
-barrier, the max-over-ranks of the timed region and the final counter reduction.
+  --config 2 (default): 10 x 128 net, B = 256        the configuration BASELINE.json's metric is quoted on
+  --config 3          : 20 x 256 net, B = 512        (USI `go`: executor-side evals/s + one-batch-in-flight latency;
+                                                      the search itself needs libnshogi's rules)
+  --config 4          : 20 x 256 net, B = 512        + the self-play loop (1024 concurrent games per GPU)
+  --config 5          : 40 x 256 net, B = 1024       + the batch sweep 64 .. 4096 (TFLOP/s, % of burst / sustained peak)
+
+  value : device-timed (CUDA events on the launch streams), inputs already resident in HBM, rotating over a pool of
+          input batches larger than L2, `streams_in_flight` batches in flight.
+  e2e   : the same step through the host-buffer C-ABI call (nsb_eval_decode_async + nsb_await): pinned host inputs,
+          H2D + kernel + D2H inside the timed region; e2e.infer_contract is the unmodified Infer contract (dense logits).
+  --impl reference : the reference's CPU path for its CPU-runnable config (pack + its own Random executor compiled from
+          /root/reference into oracle/_ref + decode) on all host cores.
+Multi-GPU: one process per GPU (torchrun), independent replicas, weak scaling; NCCL only for the barrier, the
+max-over-ranks of the timed region and the final counter reduction.
 """
 from __future__ import annotations
 
@@ -31,15 +38,34 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
 
-METRIC = "nn_leaf_evals_per_sec_batch256"
 UNIT = "evals/s"
 L2_BYTES = 126 * 1024 * 1024
-FLOPS_PER_SAMPLE = {(128, 10): 0.4944e9, (256, 20): 3.8554e9, (256, 40): 7.6774e9}
+
+# channels, blocks, batch, batches per step, weight seed (seeds with a live value head, tests/test_depth_parity.py)
+CONFIGS = {
+    2: dict(channels=128, blocks=10, batch=256, batches_per_step=512, seed=1,
+            name="bench: 10-block 128-ch ResNet random-init, batch 256 leaf evaluation on 1xB200"),
+    3: dict(channels=256, blocks=20, batch=512, batches_per_step=32, seed=1234,
+            name="USI go, 20-block 256-ch ResNet, batch 512, 1xB200: executor-side leaf evals/s (search needs libnshogi)"),
+    4: dict(channels=256, blocks=20, batch=512, batches_per_step=32, seed=1234,
+            name="self-play data generation, 20x256 ResNet, 1024 concurrent games per GPU"),
+    5: dict(channels=256, blocks=40, batch=1024, batches_per_step=8, seed=5,
+            name="large-batch sweep 64-4096 on 40-block 256-ch ResNet, tensor-pipe roofline report"),
+}
 
 
-def workload_name(C, blocks, B):
-    return (f"{blocks}-block {C}-ch ResNet random-init, batch {B} leaf evaluation on 1xB200 per replica "
-            "(feature planes + forward + policy decode)")
+def metric_name(B):
+    return f"nn_leaf_evals_per_sec_batch{B}"
+
+
+def make_config(args):
+    """The `config` object of the JSON line: identical for the b200 arm and the reference arm of one --config."""
+    c = CONFIGS[args.config]
+    return {"workload": f"{c['name']} (feature planes + forward + policy decode), per replica", "config": args.config,
+            "batch": args.batch, "channels": args.channels, "blocks": args.blocks, "batches_per_step": args.batches_per_step,
+            "launches_per_batch": 1, "streams_in_flight": args.slots,
+            "l2_policy": "inputs rotate over a pool of batches larger than L2 (126 MiB); weights stay L2-resident as in "
+                         "steady-state serving"}
 
 
 def trunk_flops_per_sample(C, blocks, in_ch=86):
@@ -59,64 +85,204 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  NVML in
+    a thread of this process (every 20 ms, time-stamped, so that the samples inside a window can be picked out exactly);
+    falls back to `nvidia-smi -lms 100` when NVML cannot be loaded."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    SMI_Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []          # (t, sm_mhz, power_w, reasons bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._smi = None
+        self._smi_lines = []
+        self.source = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.gpu
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    phys = int(ids[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons_fn(h))))
+                    except pynvml.NVMLError:
+                        pass
+                    self._stop.wait(0.02)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+            self.source = "nvml, 20 ms"
+        except Exception:  # noqa: BLE001 - any NVML problem: use the command-line tool
+            try:
+                self._smi = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.SMI_Q}",
+                                              "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                threading.Thread(target=self._pump, daemon=True).start()
+                self.source = "nvidia-smi -lms 100"
+            except OSError:
+                self._smi = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        for line in self._smi.stdout:
+            self._smi_lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
-        if self.proc is None:
-            return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        if self._smi is not None:
+            self._smi.terminate()
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+                self._smi.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self._smi.kill()
+            for t, ln in self._smi_lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    mask = 0
+                    for bit, v in zip((0x8, 0x40, 0x20, 0x4), f[5:9]):   # NVML's bit values for the same four reasons
+                        if v.lower().startswith("active"):
+                            mask |= bit
+                    self.samples.append((t, float(f[1]), float(f[3]), mask))
+                    self.max_mhz = float(f[2])
+                except ValueError:
+                    continue
+
+    def window(self, t0: float, t1: float):
+        """Summary of the samples taken in [t0, t1] (perf_counter times)."""
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not inside:
             return None
-        load = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
-        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = sorted({nm for s in inside for bit, nm in names.items() if s[3] & bit})
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_mhz_min": min(s[1] for s in inside),
+                "sm_max_mhz": self.max_mhz, "power_w_max": round(max(s[2] for s in inside), 1),
+                "power_w_median": round(statistics.median(s[2] for s in inside), 1), "samples": len(inside),
+                "reasons": reasons, "window_s": round(t1 - t0, 3), "source": self.source,
+                "window": "the timed region of `value` only"}
 
 
-def build_workload(nb, synth, orc_unused, B, pool, seed=20240203):
-    """Pool of `pool` distinct input batches (feature bitboards via the product's own stage-1
-    kernel would need a GPU; here they come from packed synthetic positions uploaded once)."""
-    base_positions = synth.random_positions(min(pool * B, 4096), seed=seed)
-    off1, idx1 = synth.random_legal_moves(B, seed=seed, edge_rows=False)
-    return base_positions, off1, idx1
+class Workload:
+    """Synthetic inputs of one (net, batch): a device pool of feature-bitboard batches larger than L2 (built with the
+    product's own stage-1 kernel from packed synthetic positions), CSR legal-move lists, output buffers."""
+
+    def __init__(self, nb, synth, ctx, B, rank, small_pool=False):
+        self.nb, self.B = nb, B
+        self.fb_bytes = B * 86 * 16
+        self.pool = max(4, (L2_BYTES + self.fb_bytes - 1) // self.fb_bytes + 8) if not small_pool else 8
+        self.pos = synth.random_positions(2048, seed=20240203 + rank)
+        d_pos = nb.DeviceBuffer.from_host(self.pos)
+        d_fb_unique = nb.DeviceBuffer(len(self.pos) * 86 * 16)
+        ctx.pack_positions_device(0, d_pos.ptr, len(self.pos), d_fb_unique.ptr)   # product stage-1 kernel
+        ctx.await_(0)
+        fb_unique = d_fb_unique.to_host((len(self.pos), 86), nb.FEATURE_BITBOARD)
+        d_pos.free()
+        d_fb_unique.free()
+        self.rng = np.random.default_rng(99 + rank)
+        self.off, self.idx = synth.random_legal_moves(B, seed=20240203, edge_rows=False)
+        self.n_moves = int(self.off[-1])
+        self.host_pool = fb_unique[self.rng.integers(0, len(self.pos), size=self.pool * B)].reshape(self.pool, B * 86)
+        self.d_pool = nb.DeviceBuffer.from_host(self.host_pool)
+        self.d_off = nb.DeviceBuffer.from_host(self.off)
+        self.d_idx = nb.DeviceBuffer.from_host(self.idx)
+        self.n_out = 8
+        self.d_legal = [nb.DeviceBuffer(max(self.n_moves, 1) * 4) for _ in range(self.n_out)]
+        self.d_win = [nb.DeviceBuffer(B * 4) for _ in range(self.n_out)]
+        self.d_draw = [nb.DeviceBuffer(B * 4) for _ in range(self.n_out)]
+        self.d_flag = [nb.DeviceBuffer(B) for _ in range(self.n_out)]
+
+    def dev_step(self, ctx, i, slot=0):
+        j = i % self.n_out
+        # the production path: legal-move rows out, dense logits never leave the SM (d_policy = NULL)
+        ctx.eval_decode_device(slot, self.d_pool.ptr + (i % self.pool) * self.fb_bytes, self.B, self.d_off.ptr, self.d_idx.ptr,
+                               self.nb.DECODE_PROBS, None, self.d_legal[j].ptr, self.d_win[j].ptr, self.d_draw[j].ptr,
+                               self.d_flag[j].ptr)
+
+    def free(self):
+        for b in [self.d_pool, self.d_off, self.d_idx] + self.d_legal + self.d_win + self.d_draw + self.d_flag:
+            b.free()
+
+
+def device_leg(nb, rep, ctx, wl, slots, batches, warm_batches, step_batches=None):
+    """`batches` launches round-robin over `slots` streams, device-resident inputs / outputs, CUDA events on the streams.
+    Returns (elapsed ms, per-step ms list or None, perf_counter window)."""
+    S = slots
+    assert wl.n_out % S == 0           # an output buffer is only ever reused on the stream that wrote it last
+    for i in range(warm_batches):
+        wl.dev_step(ctx, i, i % S)
+    for s_ in range(S):
+        ctx.await_(s_)
+    rep.barrier()
+    nb.device_sync()
+    e0 = nb.Event()
+    marks = []                          # per step boundary: one event per stream
+    t0 = time.perf_counter()
+    e0.record(ctx, 0)
+    for i in range(batches):
+        wl.dev_step(ctx, warm_batches + i, i % S)
+        if step_batches and (i + 1) % step_batches == 0:
+            evs = [nb.Event() for _ in range(S)]
+            for s_ in range(S):
+                evs[s_].record(ctx, s_)
+            marks.append(evs)
+    if not marks or batches % (step_batches or batches):
+        evs = [nb.Event() for _ in range(S)]
+        for s_ in range(S):
+            evs[s_].record(ctx, s_)
+        marks.append(evs)
+    for e in marks[-1]:
+        e.sync()
+    for s_ in range(S):
+        ctx.await_(s_)
+    nb.device_sync()
+    t1 = time.perf_counter()
+    rep.barrier()
+    ends = [max(e0.elapsed_ms(e) for e in evs) for evs in marks]
+    per_step = [b - a for a, b in zip([0.0] + ends[:-1], ends)] if step_batches else None
+    for evs in marks:
+        for e in evs:
+            e.destroy()
+    e0.destroy()
+    return ends[-1], per_step, (t0, t1)
+
+
+def isolated_leg(nb, ctx, wl, launches, warm=20):
+    """The trunk kernel launched alone: back to back on ONE stream (no overlap between launches), one CUDA event pair
+    around each launch, harvested in nsb_await.  Returns (avg launch ms, ms per step of that sub-run, launches)."""
+    for i in range(warm):
+        wl.dev_step(ctx, i, 0)
+    ctx.await_(0)
+    ctx.set_timing(True)
+    ctx.trunk_time_reset()
+    es0, es1 = nb.Event(), nb.Event()
+    es0.record(ctx, 0)
+    for i in range(launches):
+        wl.dev_step(ctx, warm + i, 0)
+    es1.record(ctx, 0)
+    es1.sync()
+    ctx.await_(0)
+    seq_ms = es0.elapsed_ms(es1)
+    ms_sum, n = ctx.trunk_time()
+    ctx.set_timing(False)
+    return ms_sum / max(n, 1), seq_ms / max(launches, 1), n, ms_sum / seq_ms if seq_ms > 0 else None
 
 
 def run_b200(args):
@@ -124,6 +290,7 @@ def run_b200(args):
     nb, synth, rep = pkg.binding, pkg.synth, pkg.replica
     info = rep.RankInfo.from_env()
     world = info.world
+    dev_device = None
     if world > 1 or args.gpus > 1:
         import torch
         import torch.distributed as dist
@@ -132,284 +299,225 @@ def run_b200(args):
             raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
         torch.cuda.set_device(info.local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", info.local_rank))
+        dev_device = torch.device("cuda", info.local_rank)
     if nb.device_count() < 1:
         raise SystemExit("bench: no CUDA device; the product path has no CPU fallback")
     gpu = info.local_rank
-    B, C, blocks = args.batch, args.channels, args.blocks
+    B, C, blocks, slots, bps = args.batch, args.channels, args.blocks, args.slots, args.batches_per_step
     desc = nb.net_desc(C, blocks)
-    blob = nb.random_blob(desc, 1234)
-    slots = args.slots
+    blob = nb.random_blob(desc, args.seed)
     ctx = nb.Context(desc, batch_max=B, slots=slots, gpu=gpu, blob=blob)
-
-    # ---- synthetic inputs: pool of batches > L2 so no step re-reads a cached input --------------
-    fb_bytes = B * 86 * 16
-    pool = max(4, (L2_BYTES + fb_bytes - 1) // fb_bytes + 8) if not args.small_pool else 8
-    pos = synth.random_positions(2048, seed=20240203 + info.rank)
-    d_pos = nb.DeviceBuffer.from_host(pos)
-    d_fb_unique = nb.DeviceBuffer(len(pos) * 86 * 16)
-    ctx.pack_positions_device(0, d_pos.ptr, len(pos), d_fb_unique.ptr)   # product stage-1 kernel
-    ctx.await_(0)
-    fb_unique = d_fb_unique.to_host((len(pos), 86), nb.FEATURE_BITBOARD)
-    rng = np.random.default_rng(99 + info.rank)
-    off, idx = synth.random_legal_moves(B, seed=20240203, edge_rows=False)
-    n_moves = int(off[-1])
-    # device pool
-    host_pool = fb_unique[rng.integers(0, len(pos), size=pool * B)].reshape(pool, B * 86)
-    d_pool = nb.DeviceBuffer.from_host(host_pool)
-    d_off = nb.DeviceBuffer.from_host(off)
-    d_idx = nb.DeviceBuffer.from_host(idx)
-    n_out = 8
-    d_legal = [nb.DeviceBuffer(max(n_moves, 1) * 4) for _ in range(n_out)]
-    d_win = [nb.DeviceBuffer(B * 4) for _ in range(n_out)]
-    d_draw = [nb.DeviceBuffer(B * 4) for _ in range(n_out)]
-    d_flag = [nb.DeviceBuffer(B) for _ in range(n_out)]
-
-    def dev_step(i, slot=0):
-        j = i % n_out
-        # the production path: legal-move rows out, dense logits never leave the SM (d_policy = NULL)
-        ctx.eval_decode_device(slot, d_pool.ptr + (i % pool) * fb_bytes, B, d_off.ptr, d_idx.ptr, nb.DECODE_PROBS,
-                               None, d_legal[j].ptr, d_win[j].ptr, d_draw[j].ptr, d_flag[j].ptr)
-
-    def await_all():
-        for s_ in range(slots):
-            ctx.await_(s_)
-
+    wl = Workload(nb, synth, ctx, B, info.rank, args.small_pool)
     K, W = args.steps, max(args.warmup, 3)
-    S = slots                       # launches round-robin over S streams (n_out % S == 0: an output
-    assert n_out % S == 0           # buffer is only ever reused on the stream that wrote it last)
-    for i in range(W):
-        dev_step(i, i % S)
-    await_all()
+    tf_burst, tf_sust, hbm, which = peaks()
+    flops_batch = trunk_flops_per_sample(C, blocks) * B
+
+    # ---- value: K steps of `bps` batches, device-resident, `slots` streams ------------------------------------------
     sampler = ClockSampler(gpu)
     sampler.start()
-    time.sleep(0.3)
-    rep.barrier()
-    nb.device_sync()
     l0 = ctx.launch_count()
-    e0 = nb.Event()
-    e_end = [nb.Event() for _ in range(S)]
-    e0.record(ctx, 0)
-    for i in range(K):
-        dev_step(W + i, i % S)
-    for s_ in range(S):
-        e_end[s_].record(ctx, s_)
-    for s_ in range(S):
-        e_end[s_].sync()
-    await_all()
-    nb.device_sync()
-    rep.barrier()
-    elapsed_ms = max(e0.elapsed_ms(e) for e in e_end)
-    launches = ctx.launch_count() - l0
-
-    # per-launch duration of the trunk kernel: the same launches issued back to back on ONE stream
-    # (no overlap between launches), a CUDA event pair around each, harvested in nsb_await
-    K2 = min(K, 500)
-    ctx.set_timing(True)
-    ctx.trunk_time_reset()
-    es0, es1 = nb.Event(), nb.Event()
-    es0.record(ctx, 0)
-    for i in range(K2):
-        dev_step(W + K + i, 0)
-    es1.record(ctx, 0)
-    es1.sync()
-    ctx.await_(0)
-    seq_elapsed_ms = es0.elapsed_ms(es1)
-    trunk_ms_sum, trunk_n = ctx.trunk_time()
-    ctx.set_timing(False)
-    dev_device = None
-    if world > 1:
-        import torch
-        dev_device = torch.device("cuda", info.local_rank)
-    counters, elapsed_max = rep.aggregate({"evals": B * K, "batches": K, "legal_moves": n_moves * K}, elapsed_ms,
-                                          device=dev_device)
+    elapsed_ms, per_step, (tw0, tw1) = device_leg(nb, rep, ctx, wl, slots, K * bps, W * bps, step_batches=bps)
+    launches = ctx.launch_count() - l0 - W * bps
+    clocks = sampler.window(tw0, tw1)
+    counters, elapsed_max = rep.aggregate({"evals": B * K * bps, "batches": K * bps, "legal_moves": wl.n_moves * K * bps},
+                                          elapsed_ms, device=dev_device)
     value = rep.whole_job_rate(counters["evals"], elapsed_max)
+    batch_ms = elapsed_max / (K * bps)
+    achieved_ss = flops_batch / (batch_ms * 1e-3) / 1e12
+    # burst (first step after the warm-up's idle gap) against steady state (second half of the run), this rank
+    steady = per_step[len(per_step) // 2:] if per_step and len(per_step) >= 4 else per_step
+    ss_batch_ms = (sum(steady) / len(steady) / bps) if steady else batch_ms
+    best_step_ms = min(per_step) if per_step else elapsed_ms / K
 
-    # ---- e2e: host buffers through the C ABI, `slots` batches in flight ---------------------------------
+    # ---- the kernel alone -------------------------------------------------------------------------------------------
+    iso_n = min(max(K * bps // 4, 100), 1000)
+    iso_ms, iso_step_ms, iso_launches, iso_share = isolated_leg(nb, ctx, wl, iso_n)
+    isolated = {"kernel": ctx.trunk_kernel_name(), "avg_launch_ms": round(iso_ms, 5),
+                "achieved": round(flops_batch / (iso_ms * 1e-3) / 1e12, 2),
+                "frac": round(flops_batch / (iso_ms * 1e-3) / 1e12 / tf_burst, 4),
+                "frac_of_sustained_peak": round(flops_batch / (iso_ms * 1e-3) / 1e12 / tf_sust, 4),
+                "kernel_share_of_step": round(iso_share, 4) if iso_share else None,
+                "timing": f"{iso_launches} launches back to back on one stream, one CUDA event pair per launch; "
+                          f"that sub-run: {iso_step_ms:.5f} ms per batch"}
+    one_slot = None
+    if C == 128 and not args.no_latency_leg:
+        # what a ONE-slot executor (the reference's usage: one batch per evaluator thread) launches for this batch size
+        ctx1 = nb.Context(desc, batch_max=B, slots=1, gpu=gpu, blob=blob)
+        ms1, step1, n1, share1 = isolated_leg(nb, ctx1, wl, iso_n)
+        one_slot = {"kernel": ctx1.trunk_kernel_name(), "avg_launch_ms": round(ms1, 5),
+                    "achieved": round(flops_batch / (ms1 * 1e-3) / 1e12, 2),
+                    "frac": round(flops_batch / (ms1 * 1e-3) / 1e12 / tf_burst, 4),
+                    "frac_of_sustained_peak": round(flops_batch / (ms1 * 1e-3) / 1e12 / tf_sust, 4)}
+        ctx1.close()
+
+    # ---- e2e: host buffers through the C ABI, `slots` batches in flight ----------------------------------------------
     h_pool_n = 16
+    n_moves, fb_bytes = wl.n_moves, wl.fb_bytes
     h_fb = [nb.PinnedArray((B * 86,), nb.FEATURE_BITBOARD) for _ in range(h_pool_n)]
     for k, a in enumerate(h_fb):
-        a.array[:] = host_pool[k % pool]
-    h_off = nb.PinnedArray((B + 1,), np.uint32); h_off.array[:] = off
-    h_idx = nb.PinnedArray((max(n_moves, 1),), np.uint16); h_idx.array[:n_moves] = idx
+        a.array[:] = wl.host_pool[k % wl.pool]
+    h_off = nb.PinnedArray((B + 1,), np.uint32); h_off.array[:] = wl.off
+    h_idx = nb.PinnedArray((max(n_moves, 1),), np.uint16); h_idx.array[:n_moves] = wl.idx
     h_legal = [nb.PinnedArray((max(n_moves, 1),), np.float32) for _ in range(slots)]
     h_win = [nb.PinnedArray((B,), np.float32) for _ in range(slots)]
     h_draw = [nb.PinnedArray((B,), np.float32) for _ in range(slots)]
     h_flag = [nb.PinnedArray((B,), np.uint8) for _ in range(slots)]
     h_policy = [nb.PinnedArray((B * 2187,), np.float32) for _ in range(slots)]
+    h_pos = [nb.PinnedArray((B,), nb.POSITION) for _ in range(h_pool_n)]
+    for a_ in h_pos:
+        a_.array[:] = wl.pos[wl.rng.integers(0, len(wl.pos), size=B)]
     sink = 0.0
 
-    def e2e_loop(steps, fused):
+    def e2e_loop(batches, kind):
         nonlocal sink
-        for i in range(steps):
+        for i in range(batches):
             s = i % slots
             if i >= slots:
                 ctx.await_(s)
-                sink += float(h_win[s].array[0])            # consume the step's result on the host
-            if fused:
+                sink += float(h_win[s].array[0])            # consume the batch's result on the host
+            if kind == "fused":
                 ctx.eval_decode_async(s, h_fb[i % h_pool_n].array, B, h_off.array, h_idx.array, nb.DECODE_PROBS,
                                       h_legal[s].array, h_win[s].array, h_draw[s].array, h_flag[s].array)
-            else:
+            elif kind == "infer":
                 ctx.eval_async(s, h_fb[i % h_pool_n].array, B, h_policy[s].array, h_win[s].array, h_draw[s].array)
-        for s in range(slots):
+            else:   # packed positions in: stage 1 in the trunk kernel's prologue
+                ctx.eval_positions_decode_async(s, h_pos[i % h_pool_n].array, B, h_off.array, h_idx.array, nb.DECODE_PROBS,
+                                                h_legal[s].array, h_win[s].array, h_draw[s].array, h_flag[s].array)
+        for s in range(min(slots, batches)):
             ctx.await_(s)
             sink += float(h_win[s].array[0])
 
-    def time_e2e(fused):
-        e2e_loop(max(W, slots), fused)
+    def time_e2e(kind, batches):
+        e2e_loop(max(bps // 4, slots), kind)
         rep.barrier()
         nb.device_sync()
         t0 = time.perf_counter()
-        e2e_loop(K, fused)
+        e2e_loop(batches, kind)
         nb.device_sync()
         dt = (time.perf_counter() - t0) * 1e3
         rep.barrier()
         _, dt_max = rep.aggregate({}, dt, device=dev_device)
-        return rep.whole_job_rate(B * K * world, dt_max)
+        return rep.whole_job_rate(B * batches * world, dt_max)
 
-    e2e_fused = time_e2e(True)
-    e2e_infer = time_e2e(False)
-
-    # packed positions in (108 B instead of 1,376 B per position over PCIe): stage 1 runs in the trunk
-    # kernel's prologue, still one launch per batch
-    h_pos = [nb.PinnedArray((B,), nb.POSITION) for _ in range(h_pool_n)]
-    for k, a_ in enumerate(h_pos):
-        a_.array[:] = pos[rng.integers(0, len(pos), size=B)]
-
-    def e2e_positions_loop(steps):
-        nonlocal sink
-        for i in range(steps):
-            s = i % slots
-            if i >= slots:
-                ctx.await_(s)
-                sink += float(h_win[s].array[0])
-            ctx.eval_positions_decode_async(s, h_pos[i % h_pool_n].array, B, h_off.array, h_idx.array, nb.DECODE_PROBS,
-                                            h_legal[s].array, h_win[s].array, h_draw[s].array, h_flag[s].array)
-        for s in range(slots):
-            ctx.await_(s)
-            sink += float(h_win[s].array[0])
-
-    def timed(loop, steps):
-        rep.barrier()
-        nb.device_sync()
-        t0 = time.perf_counter()
-        loop(steps)
-        nb.device_sync()
-        dt = (time.perf_counter() - t0) * 1e3
-        rep.barrier()
-        _, dt_max = rep.aggregate({}, dt, device=dev_device)
-        return dt_max
-
-    # By now the board sits at its power cap and clocks have dropped since the first leg, so the positions-in leg
-    # is timed interleaved with the bitboards-in call in the same window (two halves each): that pair compares.
-    e2e_positions_loop(max(W, slots))
-    lp0 = ctx.launch_count()
-    half = max(K // 2, slots)
-    ms_pos = ms_bb = 0.0
-    for _ in range(2):
-        ms_pos += timed(e2e_positions_loop, half)
-        ms_bb += timed(lambda n_: e2e_loop(n_, True), half)
-    pos_launches = (ctx.launch_count() - lp0) / 2          # both legs launch one kernel per step
-    e2e_positions = rep.whole_job_rate(B * 2 * half * world, ms_pos)
-    e2e_bb_same_window = rep.whole_job_rate(B * 2 * half * world, ms_bb)
-    K_pos = 2 * half
+    e2e_fused = time_e2e("fused", K * bps)
+    e2e_infer = time_e2e("infer", K * bps)
+    e2e_positions = time_e2e("positions", K * bps)
 
     # one batch at a time (the reference executor's usage: computeNonBlocking -> await per evaluator thread,
-    # src/mcts/evaluationworker.cc:158-180): a one-slot context = classic kernel + direct I/O (the kernel
-    # reads / writes the page-locked host buffers itself), against the same context with staged copies
+    # src/mcts/evaluationworker.cc:158-180): a one-slot context = direct I/O (the kernel reads / writes the
+    # page-locked host buffers itself), against the same context with staged copies
     latency = None
     if not args.no_latency_leg:
         ctx1 = nb.Context(desc, batch_max=B, slots=1, gpu=gpu, blob=blob)
-        KL = min(K, 500)
+        KL = min(K * bps, 500)
 
-        def one_at_a_time(steps):
+        def one_at_a_time(n_batches):
             nonlocal sink
             t0 = time.perf_counter()
-            for i in range(steps):
+            for i in range(n_batches):
                 ctx1.eval_decode_async(0, h_fb[i % h_pool_n].array, B, h_off.array, h_idx.array, nb.DECODE_PROBS,
                                        h_legal[0].array, h_win[0].array, h_draw[0].array, h_flag[0].array)
                 ctx1.await_(0)
                 sink += float(h_win[0].array[0])
-            return (time.perf_counter() - t0) * 1e6 / steps
+            return (time.perf_counter() - t0) * 1e6 / n_batches
 
-        latency = {"kernel": ctx1.trunk_kernel_name(), "batch": B, "steps": KL,
+        latency = {"kernel": ctx1.trunk_kernel_name(), "batch": B, "batches": KL,
                    "api": "nsb_eval_decode_async + nsb_await, one batch in flight, host buffers"}
         for mode in ("staged", "direct"):
             ctx1.set_io_mode(mode == "direct")
             one_at_a_time(50)
             latency[f"{mode}_us_per_batch"] = round(one_at_a_time(KL), 2)
         latency["default_io"] = "direct"
+        latency["evals_per_s_one_in_flight"] = round(B / (latency["direct_us_per_batch"] * 1e-6), 1)
         ctx1.close()
-    clocks = sampler.stop()
-    selfplay = None if args.no_selfplay else selfplay_leg(args, info, rep, dev_device)
+    sampler.stop()
+
+    sweep = batch_sweep(args, nb, synth, rep, desc, blob, gpu, info, tf_burst, tf_sust) if args.config == 5 and not args.no_sweep else None
+    selfplay = selfplay_leg(args, info, rep, dev_device) if args.config in (2, 4) and not args.no_selfplay else None
 
     # ---- roofline of the dominant (only) kernel ----------------------------------------------------------
-    tf_burst, tf_sust, hbm, which = peaks()
-    flops_launch = trunk_flops_per_sample(C, blocks) * B
-    avg_launch_ms = trunk_ms_sum / max(trunk_n, 1)
-    achieved = flops_launch / (avg_launch_ms * 1e-3) / 1e12 if avg_launch_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "trunk_traffic.json")
     if os.path.exists(tp):
-        kname = ctx.trunk_kernel_name()
-        tag = ":duo" if "duo" in kname else ""
+        tag = ":duo" if "duo" in ctx.trunk_kernel_name() else ""
         traffic = json.load(open(tp)).get(f"{C}x{blocks}@{B}{tag}")
-    # `achieved`: the timed region itself.  Its launches overlap (`slots` streams), so a launch's duration
-    # there is the steady-state time per launch, elapsed / launches; the same kernel launched alone
-    # (one stream, back to back, an event pair per launch) is reported beside it.
-    step_ms = elapsed_max / K
-    achieved_ss = flops_launch / (step_ms * 1e-3) / 1e12
+    # `achieved`: the timed region itself.  Its launches overlap (`slots` streams, CTAs of different launches share
+    # the SMs), so the duration of a launch there is the steady-state time per launch, elapsed / launches; the same
+    # kernel launched alone is reported beside it (isolated_launch), and so is the kernel a one-slot executor runs.
     roofline = {"bound": "tensor", "kernel": ctx.trunk_kernel_name(), "achieved": round(achieved_ss, 2),
                 "peak": tf_burst, "unit": "TFLOP/s", "frac": round(achieved_ss / tf_burst, 4),
                 "frac_of_sustained_peak": round(achieved_ss / tf_sust, 4), "peak_source": which,
-                "flops_per_launch": flops_launch, "avg_launch_ms": round(step_ms, 5),
-                "timing": f"timed region: {K} launches over {slots} streams, CUDA events on the streams, "
+                "flops_per_launch": flops_batch, "avg_launch_ms": round(batch_ms, 5),
+                "timing": f"timed region: {K * bps} launches over {slots} streams, CUDA events on the streams, "
                           "duration per launch = elapsed / launches (launches overlap); per GPU",
-                "isolated_launch": {"avg_launch_ms": round(avg_launch_ms, 5), "achieved": round(achieved, 2),
-                                    "frac": round(achieved / tf_burst, 4),
-                                    "frac_of_sustained_peak": round(achieved / tf_sust, 4),
-                                    "kernel_share_of_step": round(trunk_ms_sum / seq_elapsed_ms, 4) if seq_elapsed_ms > 0 else None,
-                                    "timing": f"{trunk_n} launches back to back on one stream, one CUDA event pair per "
-                                              f"launch; that sub-run: {seq_elapsed_ms / max(K2, 1):.5f} ms/step"},
-                "traffic": traffic}
+                "steady_state": {"avg_launch_ms": round(ss_batch_ms, 5),
+                                 "frac": round(flops_batch / (ss_batch_ms * 1e-3) / 1e12 / tf_burst, 4),
+                                 "what": "second half of the timed steps (this rank): the board has reached its power-capped clock"},
+                "best_step": {"avg_launch_ms": round(best_step_ms / bps, 5),
+                              "frac": round(flops_batch / (best_step_ms / bps * 1e-3) / 1e12 / tf_burst, 4)},
+                "isolated_launch": isolated, "one_slot_executor_launch": one_slot, "traffic": traffic}
+    if sweep is not None:
+        roofline["sweep"] = sweep
 
     line = {
-        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": metric_name(B), "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(elapsed_max / K, 5), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(C, blocks, B), "launches_per_step": 1,
-                   "batch": B, "channels": C, "blocks": blocks, "legal_moves_per_batch": n_moves,
-                   "l2_policy": f"inputs rotate over a pool of {pool} batches ({pool * fb_bytes >> 20} MiB > L2); "
-                                "weights stay L2-resident as in steady-state serving",
-                   "replicas": world, "streams_in_flight": slots,
-                   "value_leg": f"{slots} streams round-robin, device-resident inputs/outputs, events on the streams"},
+        "config": make_config(args),
         "e2e": {"value": round(e2e_fused, 1), "unit": UNIT, "api": "nsb_eval_decode_async + nsb_await (host buffers)",
-                "h2d_bytes_per_step": fb_bytes + (B + 1) * 4 + n_moves * 2,
-                "d2h_bytes_per_step": n_moves * 4 + B * 4 * 2 + B, "clock": "host, device-synchronised both sides"},
-        "e2e_infer_contract": {"value": round(e2e_infer, 1), "unit": UNIT,
-                               "api": "nsb_eval_async + nsb_await == Infer::computeNonBlocking/await (dense logits)",
-                               "h2d_bytes_per_step": fb_bytes, "d2h_bytes_per_step": B * 2187 * 4 + B * 8},
-        "e2e_positions": {"value": round(e2e_positions, 1), "unit": UNIT,
-                          "api": "nsb_eval_positions_decode_async + nsb_await (packed positions in, stage 1 in the trunk prologue)",
-                          "h2d_bytes_per_step": B * 108 + (B + 1) * 4 + n_moves * 2,
-                          "d2h_bytes_per_step": n_moves * 4 + B * 4 * 2 + B, "launches_per_step": pos_launches / K_pos,
-                          "bitboards_in_same_window": round(e2e_bb_same_window, 1),
-                          "note": "timed in alternating half-windows with the bitboards-in call, late in the run "
-                                  "(board at its power cap): compare with bitboards_in_same_window, not with e2e"},
-        "latency_one_batch_in_flight": latency,
+                "h2d_bytes_per_step": (fb_bytes + (B + 1) * 4 + n_moves * 2) * bps,
+                "d2h_bytes_per_step": (n_moves * 4 + B * 4 * 2 + B) * bps, "clock": "host, device-synchronised both sides",
+                "infer_contract": {"value": round(e2e_infer, 1), "unit": UNIT,
+                                   "api": "nsb_eval_async + nsb_await == Infer::computeNonBlocking/await (dense logits)",
+                                   "h2d_bytes_per_step": fb_bytes * bps, "d2h_bytes_per_step": (B * 2187 * 4 + B * 8) * bps,
+                                   "d2h_gbs_per_gpu": round(e2e_infer / world * (2187 * 4 + 8) / 1e9, 2)},
+                "positions_in": {"value": round(e2e_positions, 1), "unit": UNIT,
+                                 "api": "nsb_eval_positions_decode_async + nsb_await (packed positions in, stage 1 in the trunk prologue)",
+                                 "h2d_bytes_per_step": (B * 108 + (B + 1) * 4 + n_moves * 2) * bps,
+                                 "d2h_bytes_per_step": (n_moves * 4 + B * 4 * 2 + B) * bps},
+                "one_batch_in_flight": latency},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "per_step_ms": [round(x, 3) for x in per_step] if per_step and len(per_step) <= 64 else None,
         "counters": counters,
     }
+    if args.config == 3 and latency:
+        # USI nps (src/protocol/usilogger.cc:46) = visited nodes / s; the executor bounds it from above by
+        # evals/s / (1 - cache-hit fraction - terminal fraction); the search needs libnshogi
+        line["usi_nps_estimate"] = {"leaf_evals_per_s": round(value, 1), "one_batch_in_flight_evals_per_s": latency["evals_per_s_one_in_flight"],
+                                    "formula": "nps ~= evals/s / (1 - cache_hit - terminal); not measured: no rules library"}
     if selfplay is not None:
         line["selfplay"] = selfplay
     if info.rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(synth, B, seconds=args.cpu_seconds)
     if info.rank == 0:
         print(json.dumps(line), flush=True)
+    wl.free()
     ctx.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
     return sink
+
+
+def batch_sweep(args, nb, synth, rep, desc, blob, gpu, info, tf_burst, tf_sust):
+    """BASELINE configs[4]: B = 64 .. 4096 on the 40 x 256 net: evals/s, TFLOP/s and % of burst / sustained peak per B,
+    `slots` streams in flight and one launch alone."""
+    rows = []
+    for Bs in (64, 128, 256, 512, 1024, 2048, 4096):
+        ctx = nb.Context(desc, batch_max=Bs, slots=args.slots, gpu=gpu, blob=blob)
+        wl = Workload(nb, synth, ctx, Bs, info.rank, small_pool=False)
+        flops = trunk_flops_per_sample(args.channels, args.blocks) * Bs
+        est_ms = flops / (0.75 * tf_burst * 1e9)
+        n = int(min(max(600.0 / est_ms, 8), 4000))           # ~0.6 s per point
+        ms, _, _ = device_leg(nb, rep, ctx, wl, args.slots, n, max(n // 8, args.slots))
+        iso_ms, _, _, _ = isolated_leg(nb, ctx, wl, max(n // 4, 4), warm=4)
+        tf = flops * n / (ms * 1e-3) / 1e12
+        rows.append({"batch": Bs, "launches": n, "evals_per_s": round(Bs * n / (ms * 1e-3), 1), "tflops": round(tf, 1),
+                     "frac_burst": round(tf / tf_burst, 4), "frac_sustained": round(tf / tf_sust, 4),
+                     "alone_launch_ms": round(iso_ms, 4), "alone_frac_burst": round(flops / (iso_ms * 1e-3) / 1e12 / tf_burst, 4)})
+        wl.free()
+        ctx.close()
+    return rows
 
 
 def selfplay_leg(args, info, rep, device):
@@ -446,39 +554,52 @@ def selfplay_leg(args, info, rep, device):
             "avg_batch": round(counters["evals"] / max(counters["batches"], 1), 1), "seconds": rec["seconds"],
             "config": {"workload": "self-play data generation, 20x256 ResNet, 1024 concurrent games per GPU",
                        "batch_size": 512, "num_playouts": rec["num_playouts"], "full_search_ratio": rec["full_search_ratio"],
-                       "search_workers_per_gpu": workers, "slots": rec["slots"], "rules": rec["rules"]}}
+                       "search_workers_per_gpu": workers, "slots": rec["slots"], "rules": rec["rules"],
+                       "decode": rec.get("decode")}}
 
 
-def cpu_baseline(synth, B, seconds=12.0, threads=None):
-    """Reference's CPU path for its CPU-runnable config (BASELINE.json configs[0]): stage-1 pack
-    (port; libnshogi absent) + Random executor (the reference's own random.cc compiled into
-    oracle/_ref when present, else the port) + decode (port), one batch of B per thread-iteration."""
-    orc = graft.load_oracle()
-    threads = threads or (os.cpu_count() or 1)
+def cpu_path_rate(orc, synth, B, threads, seconds):
     pos = synth.random_positions(1024, seed=20240203)
     off, idx = synth.random_legal_moves(len(pos), seed=20240203, edge_rows=False)
     use_ref = orc.have_ref_random()
     v, sec = orc.cpu_path(pos, off, idx, B, threads, 2, False, use_ref)       # calibrate
     per_thread = max(2, int(seconds / max(sec / 2, 1e-6)))
     v, sec = orc.cpu_path(pos, off, idx, B, threads, per_thread, False, use_ref)
+    return v, sec, per_thread, use_ref
+
+
+def cpu_baseline(synth, B, seconds=12.0):
+    """The reference's CPU path for its CPU-runnable config (BASELINE.json configs[0]): stage-1 pack (port; libnshogi
+    absent) + Random executor (the reference's own random.cc compiled into oracle/_ref when present, else the port) +
+    decode (port), one batch per thread-iteration.  Reported twice: on every host core at this run's batch size (the
+    headline `value`), and exactly as configs[0] states it - 8 threads, batch 128."""
+    orc = graft.load_oracle()
+    cores = os.cpu_count() or 1
+    v, sec, per_thread, use_ref = cpu_path_rate(orc, synth, B, cores, seconds * 0.6)
+    v0, sec0, per0, _ = cpu_path_rate(orc, synth, 128, 8, seconds * 0.4)
     # context: the same net's fp32 forward on the host cores (oracle port, vectorised C, all threads)
     pkg = graft.load_package()
     desc = pkg.binding.net_desc(128, 10)
-    blob = pkg.binding.random_blob(desc, 1234)
-    planes = orc.expand(orc.pack(pos[:256]), 256)
+    blob = pkg.binding.random_blob(desc, 1)
+    pos = synth.random_positions(256, seed=20240203)
+    planes = orc.expand(orc.pack(pos), 256)
     t0 = time.perf_counter()
     orc.forward(desc, blob, planes, False)
     fwd = 256 / (time.perf_counter() - t0)
-    return {"value": round(v, 1), "with_oracle_forward_10x128": {"value": round(fwd, 1), "unit": UNIT,
-            "sample": "256 positions through the oracle's fp32 CPU forward of the 10x128 net, all threads"}, "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
-            "sample": f"{threads} threads x {per_thread} batches of {B}: pack (port of FeatureStackComptime, "
-                      f"builder-defined) + Random executor ({'reference src/infer/random.cc compiled in place' if use_ref else 'port of random.cc'}) "
-                      f"+ decode (port of feedworker.cc:100-136); {sec:.1f} s; NN forward NOT included "
-                      "(the reference's CPU config replaces it with the Random executor)"}
+    rand = "reference src/infer/random.cc compiled in place" if use_ref else "port of random.cc"
+    return {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "kind_detail": f"Random executor: {rand}; stage-1 pack and decode: ports (libnshogi absent)",
+            "sample": f"{cores} threads x {per_thread} batches of {B}: pack (port of FeatureStackComptime, builder-defined) + "
+                      f"Random executor ({rand}) + decode (port of feedworker.cc:100-136); {sec:.1f} s; NN forward NOT "
+                      "included (the reference's CPU config replaces it with the Random executor)",
+            "configs0_8_threads_batch128": {"value": round(v0, 1), "unit": UNIT, "cores": 8,
+                                            "sample": f"8 threads x {per0} batches of 128, same three stages; {sec0:.1f} s"},
+            "with_oracle_forward_10x128": {"value": round(fwd, 1), "unit": UNIT,
+                                           "sample": "256 positions through the oracle's fp32 CPU forward of the 10x128 net, all threads"}}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path on the host cores (see cpu_baseline)."""
+    """--impl reference: the reference's CPU path on the host cores (see cpu_baseline), every core, same config object."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -504,17 +625,17 @@ def run_reference(args):
         total += threads * per_step * B
     dt = time.perf_counter() - t0
     value = total / dt
-    sample = (f"each step = {threads} threads x {per_step} batches of {B} through pack (port) + Random executor "
-              f"({'reference random.cc compiled in place' if use_ref else 'port'}) + decode (port); no NN forward on CPU")
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
+    rand = "reference random.cc compiled in place" if use_ref else "port"
+    sample = (f"each step = {threads} threads x {per_step} batches of {B} (a bounded sample of the step's "
+              f"{args.batches_per_step} batches) through pack (port) + Random executor ({rand}) + decode (port); no NN forward "
+              "on the CPU: the reference has none, its CPU-runnable executor (Random, BASELINE.json configs[0]) stands in")
+    line = {"impl": "reference", "metric": metric_name(B), "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
             "steps": K, "warmup": W, "ms_per_step": round(dt / K * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.channels, args.blocks, B), "batch": B,
-                       "channels": args.channels, "blocks": args.blocks,
-                       "reference_arm": "the reference has no CPU forward: its CPU-runnable executor (Random, "
-                                        "BASELINE.json configs[0]) stands in for the ResNet"},
-            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": threads,
-                             "kind": "reference" if use_ref else "port", "sample": sample},
+            "config": make_config(args),
+            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": threads, "kind": "port",
+                             "kind_detail": f"Random executor: {rand}; stage-1 pack and decode: ports (libnshogi absent)",
+                             "sample": sample},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -523,20 +644,29 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--channels", type=int, default=128)
-    ap.add_argument("--blocks", type=int, default=10)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--channels", type=int, default=None)
+    ap.add_argument("--blocks", type=int, default=None)
+    ap.add_argument("--batches-per-step", type=int, default=None)
+    ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--no-latency-leg", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--selfplay-seconds", type=float, default=6.0)
     ap.add_argument("--small-pool", action="store_true", help="8-batch input pool (profiling runs only)")
     args = ap.parse_args()
+    c = CONFIGS[args.config]
+    for k_arg, k_cfg in (("batch", "batch"), ("channels", "channels"), ("blocks", "blocks"), ("batches_per_step", "batches_per_step"),
+                         ("seed", "seed")):
+        if getattr(args, k_arg) is None:
+            setattr(args, k_arg, c[k_cfg])
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -91,7 +91,7 @@ def test_selfplay_sim_with_device_cache_gpu(built):
     assert out.returncode == 0, out.stdout + out.stderr
     rec = json.loads(out.stdout.strip().splitlines()[-1])
     assert rec["nan_rows"] == 0 and rec["evals"] > 10000 and rec["records"] > 1000
-    assert 0.35 <= rec["cache_hit_rate"] <= 0.6, rec["cache_hit_rate"]
+    assert 0.28 <= rec["cache_hit_rate"] <= 0.6, rec["cache_hit_rate"]
 
 
 def test_leaf_queue_protocol_under_thread_sanitizer(built, tmp_path):
