@@ -307,24 +307,6 @@ int nsb_event_record(void* ev, nsb_ctx* ctx, int slot);
 int nsb_event_sync(void* ev);
 int nsb_event_elapsed_ms(void* start, void* stop, float* ms);
 
-/* Diagnostics: run one trunk launch and return CTA 0's clock64 stamps, 4 per layer
- * {MMA issue start, MMA issue end, accumulator ready (epilogue start), epilogue end}, then 8 phase
- * stamps {entry, setup done, features expanded, features loaded, heads read, policy written, value
- * MLP done, decode done}: 4 * layers + 8 values. */
-int nsb_debug_trunk_timeline(nsb_ctx* ctx, int slot, const nsb_feature_bitboard* d_features, size_t n,
-                             uint64_t* host_stamps, size_t max_stamps);
-/* Same launch fed with packed positions (stage 1 in the kernel's prologue). */
-int nsb_debug_trunk_timeline_positions(nsb_ctx* ctx, int slot, const nsb_position* d_positions, size_t n,
-                                       uint64_t* host_stamps, size_t max_stamps);
-
-/* Diagnostics: issue-to-retire rate (cycles per M128 x n_cols x K16 MMA) and numerical check of one
- * operand layout with a row-shifted B start: layout 0 = SWIZZLE_NONE 16-byte rows, 1 = SWIZZLE_128B. */
-int nsb_debug_umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters,
-                         float* max_err, double* cycles_per_mma);
-
-/* Diagnostics: sustained cp.async.bulk (L2 -> shared ring) rate per CTA in bytes per SM cycle. */
-int nsb_debug_bulk_rate_probe(int gpu, int ctas, int tile_bytes, int stages, int split, double* bytes_per_cycle);
-
 /* Which trunk kernel this ctx launches (chosen at nsb_create from the net width and the number of
  * slots: a one-slot ctx gets the kernel with the shortest launch, a multi-slot ctx the one with the
  * highest throughput when several batches are in flight). */

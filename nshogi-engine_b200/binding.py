@@ -80,11 +80,6 @@ SIGNATURES = {
     "nsb_eval_positions_cached_decode_async": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, C.c_int, _P, _P, _P, _P,
                                                          _P]),
     "nsb_eval_cached_decode_device": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
-    "nsb_debug_trunk_timeline": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
-    "nsb_debug_trunk_timeline_positions": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
-    "nsb_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
-                                       C.POINTER(C.c_double)]),
-    "nsb_debug_bulk_rate_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "nsb_stream": (_P, [_P, C.c_int]),
     "nsb_set_timing": (C.c_int, [_P, C.c_int]),
     "nsb_trunk_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -117,6 +112,34 @@ SIGNATURES = {
 }
 
 
+# the additional symbols of the diagnostic build (include/nsb_diag.h, libnsb_diag.so)
+DIAG_SIGNATURES = {
+    "nsb_debug_trunk_timeline": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
+    "nsb_debug_trunk_timeline_positions": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, C.c_size_t]),
+    "nsb_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_double)]),
+    "nsb_debug_bulk_rate_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+}
+DIAG_LIB_PATH = os.path.join(HERE, "libnsb_diag.so")
+_diag = None
+
+
+def diag_lib() -> C.CDLL:
+    """The diagnostic build of the library (-DNSB_DIAG): every product symbol plus include/nsb_diag.h.  Tools and the
+    tests that compare against the superseded kernels load it; the product path never does."""
+    global _diag
+    if _diag is None:
+        if not os.path.exists(DIAG_LIB_PATH):
+            raise NsbError(f"{DIAG_LIB_PATH} not built")
+        l = C.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in {**SIGNATURES, **DIAG_SIGNATURES}.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _diag = l
+    return _diag
+
+
 def lib() -> C.CDLL:
     """Load libnsb.so (built in-tree by ``__graft_entry__.build()`` / csrc/Makefile)."""
     global _lib
@@ -135,7 +158,10 @@ def lib() -> C.CDLL:
 
 def _check(rc: int, what: str) -> None:
     if rc != 0:
-        raise NsbError(f"{what} failed ({rc}): {lib().nsb_last_error().decode()}")
+        msg = lib().nsb_last_error().decode()
+        if _diag is not None and _diag.nsb_last_error():   # the call may have gone to the diagnostic build
+            msg = msg or _diag.nsb_last_error().decode()
+        raise NsbError(f"{what} failed ({rc}): {msg}")
 
 
 def _ptr(a) -> Optional[int]:
@@ -247,14 +273,14 @@ def umma_selftest(n_cols: int, k_elems: int, shift_rows: int, gpu: int = 0):
 
 def umma_probe(n_cols, k_elems, shift_rows, layout, iters=20, gpu=0):
     err, cyc = C.c_float(-1.0), C.c_double(0)
-    _check(lib().nsb_debug_umma_probe(gpu, n_cols, k_elems, shift_rows, layout, iters, C.byref(err), C.byref(cyc)),
+    _check(diag_lib().nsb_debug_umma_probe(gpu, n_cols, k_elems, shift_rows, layout, iters, C.byref(err), C.byref(cyc)),
            "nsb_debug_umma_probe")
     return float(err.value), float(cyc.value)
 
 
 def bulk_rate_probe(ctas, tile_bytes, stages, split, gpu=0):
     v = C.c_double(0)
-    _check(lib().nsb_debug_bulk_rate_probe(gpu, ctas, tile_bytes, stages, split, C.byref(v)), "nsb_debug_bulk_rate_probe")
+    _check(diag_lib().nsb_debug_bulk_rate_probe(gpu, ctas, tile_bytes, stages, split, C.byref(v)), "nsb_debug_bulk_rate_probe")
     return float(v.value)
 
 
@@ -267,7 +293,7 @@ class Event:
         self._p = p
 
     def record(self, ctx: "Context", slot: int = 0):
-        _check(lib().nsb_event_record(self._p, ctx._h, slot), "nsb_event_record")
+        _check(ctx._l.nsb_event_record(self._p, ctx._h, slot), "nsb_event_record")
 
     def sync(self):
         _check(lib().nsb_event_sync(self._p), "nsb_event_sync")
@@ -288,12 +314,13 @@ class Context:
     (reference src/infer/infer.h:19-32), with ``slots`` independent in-flight batches."""
 
     def __init__(self, desc: NetDesc, batch_max: int, slots: int = 1, gpu: int = 0,
-                 blob: Optional[np.ndarray] = None, seed: Optional[int] = None):
+                 blob: Optional[np.ndarray] = None, seed: Optional[int] = None, diag: bool = False):
         self.desc = desc
         self.batch_max = batch_max
         self.slots = slots
+        self._l = diag_lib() if diag else lib()   # diag: the -DNSB_DIAG build (timeline stamps, superseded kernels)
         h = _P()
-        _check(lib().nsb_create(C.byref(h), gpu, batch_max, slots, C.byref(desc)), "nsb_create")
+        _check(self._l.nsb_create(C.byref(h), gpu, batch_max, slots, C.byref(desc)), "nsb_create")
         self._h = h
         if blob is None and seed is not None:
             blob = random_blob(desc, seed)
@@ -302,7 +329,7 @@ class Context:
 
     def close(self):
         if self._h is not None:
-            lib().nsb_destroy(self._h)
+            self._l.nsb_destroy(self._h)
             self._h = None
 
     def __enter__(self):
@@ -313,109 +340,109 @@ class Context:
 
     def load_weights(self, blob: np.ndarray):
         blob = np.ascontiguousarray(blob, dtype=np.float32)
-        _check(lib().nsb_load_weights(self._h, blob.ctypes.data, blob.size), "nsb_load_weights")
+        _check(self._l.nsb_load_weights(self._h, blob.ctypes.data, blob.size), "nsb_load_weights")
 
     def bind_thread(self):
-        _check(lib().nsb_bind_thread(self._h), "nsb_bind_thread")
+        _check(self._l.nsb_bind_thread(self._h), "nsb_bind_thread")
 
     # -- host-buffer calls (the Infer contract) ------------------------------------------------
     def eval_async(self, slot, features, n, policy, win, draw):
-        _check(lib().nsb_eval_async(self._h, slot, _ptr(features), n, _ptr(policy), _ptr(win), _ptr(draw)),
+        _check(self._l.nsb_eval_async(self._h, slot, _ptr(features), n, _ptr(policy), _ptr(win), _ptr(draw)),
                "nsb_eval_async")
 
     def eval_decode_async(self, slot, features, n, move_off, move_idx, mode, legal_out, win, draw, nan_flag=None):
-        _check(lib().nsb_eval_decode_async(self._h, slot, _ptr(features), n, _ptr(move_off), _ptr(move_idx), mode,
+        _check(self._l.nsb_eval_decode_async(self._h, slot, _ptr(features), n, _ptr(move_off), _ptr(move_idx), mode,
                                            _ptr(legal_out), _ptr(win), _ptr(draw), _ptr(nan_flag)),
                "nsb_eval_decode_async")
 
     def eval_positions_async(self, slot, positions, n, policy, win, draw):
-        _check(lib().nsb_eval_positions_async(self._h, slot, _ptr(positions), n, _ptr(policy), _ptr(win),
+        _check(self._l.nsb_eval_positions_async(self._h, slot, _ptr(positions), n, _ptr(policy), _ptr(win),
                                               _ptr(draw)), "nsb_eval_positions_async")
 
     def eval_positions_decode_async(self, slot, positions, n, move_off, move_idx, mode, legal_out, win, draw,
                                     nan_flag=None):
-        _check(lib().nsb_eval_positions_decode_async(self._h, slot, _ptr(positions), n, _ptr(move_off),
+        _check(self._l.nsb_eval_positions_decode_async(self._h, slot, _ptr(positions), n, _ptr(move_off),
                                                      _ptr(move_idx), mode, _ptr(legal_out), _ptr(win), _ptr(draw),
                                                      _ptr(nan_flag)), "nsb_eval_positions_decode_async")
 
     def await_(self, slot=0):
-        _check(lib().nsb_await(self._h, slot), "nsb_await")
+        _check(self._l.nsb_await(self._h, slot), "nsb_await")
 
     def is_computing(self, slot=0) -> bool:
-        rc = lib().nsb_is_computing(self._h, slot)
+        rc = self._l.nsb_is_computing(self._h, slot)
         if rc < 0:
             _check(rc, "nsb_is_computing")
         return rc == 1
 
     # -- device-pointer calls -------------------------------------------------------------------
     def eval_device(self, slot, d_features, n, d_policy, d_win, d_draw):
-        _check(lib().nsb_eval_device(self._h, slot, _ptr(d_features), n, _ptr(d_policy), _ptr(d_win), _ptr(d_draw)),
+        _check(self._l.nsb_eval_device(self._h, slot, _ptr(d_features), n, _ptr(d_policy), _ptr(d_win), _ptr(d_draw)),
                "nsb_eval_device")
 
     def eval_decode_device(self, slot, d_features, n, d_off, d_idx, mode, d_policy, d_legal, d_win, d_draw, d_flag):
-        _check(lib().nsb_eval_decode_device(self._h, slot, _ptr(d_features), n, _ptr(d_off), _ptr(d_idx), mode,
+        _check(self._l.nsb_eval_decode_device(self._h, slot, _ptr(d_features), n, _ptr(d_off), _ptr(d_idx), mode,
                                             _ptr(d_policy), _ptr(d_legal), _ptr(d_win), _ptr(d_draw), _ptr(d_flag)),
                "nsb_eval_decode_device")
 
     def extract_device(self, slot, d_features, n, channels, channels_first, d_planes):
-        _check(lib().nsb_extract_device(self._h, slot, _ptr(d_features), n, channels, int(channels_first),
+        _check(self._l.nsb_extract_device(self._h, slot, _ptr(d_features), n, channels, int(channels_first),
                                         _ptr(d_planes)), "nsb_extract_device")
 
     def pack_positions_device(self, slot, d_positions, n, d_features):
-        _check(lib().nsb_pack_positions_device(self._h, slot, _ptr(d_positions), n, _ptr(d_features)),
+        _check(self._l.nsb_pack_positions_device(self._h, slot, _ptr(d_positions), n, _ptr(d_features)),
                "nsb_pack_positions_device")
 
     def decode_device(self, slot, d_policy, d_win, d_draw, n, d_off, d_idx, mode, d_legal, d_flag):
-        _check(lib().nsb_decode_device(self._h, slot, _ptr(d_policy), _ptr(d_win), _ptr(d_draw), n, _ptr(d_off),
+        _check(self._l.nsb_decode_device(self._h, slot, _ptr(d_policy), _ptr(d_win), _ptr(d_draw), n, _ptr(d_off),
                                        _ptr(d_idx), mode, _ptr(d_legal), _ptr(d_flag)), "nsb_decode_device")
 
     def decode_device_ex(self, slot, d_policy, d_win, d_draw, n, d_off, d_idx, mode, d_row_flags, d_legal, d_logits, d_flag):
-        _check(lib().nsb_decode_device_ex(self._h, slot, _ptr(d_policy), _ptr(d_win), _ptr(d_draw), n, _ptr(d_off),
+        _check(self._l.nsb_decode_device_ex(self._h, slot, _ptr(d_policy), _ptr(d_win), _ptr(d_draw), n, _ptr(d_off),
                                           _ptr(d_idx), mode, _ptr(d_row_flags), _ptr(d_legal), _ptr(d_logits), _ptr(d_flag)),
                "nsb_decode_device_ex")
 
     # -- device-resident evaluation cache ------------------------------------------------------------
     def cache_create(self, memory_mb: int):
-        _check(lib().nsb_cache_create(self._h, memory_mb), "nsb_cache_create")
+        _check(self._l.nsb_cache_create(self._h, memory_mb), "nsb_cache_create")
 
     def cache_clear(self):
-        _check(lib().nsb_cache_clear(self._h), "nsb_cache_clear")
+        _check(self._l.nsb_cache_clear(self._h), "nsb_cache_clear")
 
     def cache_num_bundles(self) -> int:
-        return int(lib().nsb_cache_num_bundles(self._h))
+        return int(self._l.nsb_cache_num_bundles(self._h))
 
     def cache_store_device(self, slot, d_hashes, n, d_off, d_legal, d_win, d_draw, d_skip=None, d_stored=None):
-        _check(lib().nsb_cache_store_device(self._h, slot, _ptr(d_hashes), n, _ptr(d_off), _ptr(d_legal), _ptr(d_win),
+        _check(self._l.nsb_cache_store_device(self._h, slot, _ptr(d_hashes), n, _ptr(d_off), _ptr(d_legal), _ptr(d_win),
                                             _ptr(d_draw), _ptr(d_skip), _ptr(d_stored)), "nsb_cache_store_device")
 
     def cache_probe_device(self, slot, d_hashes, n, d_off, d_legal, d_win, d_draw, d_hit, d_miss_idx, d_miss_count):
-        _check(lib().nsb_cache_probe_device(self._h, slot, _ptr(d_hashes), n, _ptr(d_off), _ptr(d_legal), _ptr(d_win),
+        _check(self._l.nsb_cache_probe_device(self._h, slot, _ptr(d_hashes), n, _ptr(d_off), _ptr(d_legal), _ptr(d_win),
                                             _ptr(d_draw), _ptr(d_hit), _ptr(d_miss_idx), _ptr(d_miss_count)),
                "nsb_cache_probe_device")
 
     def eval_cached_decode_async(self, slot, features, n, hashes, move_off, move_idx, mode, legal_out, win, draw,
                                  nan_flag=None, hit_flag=None):
-        _check(lib().nsb_eval_cached_decode_async(self._h, slot, _ptr(features), n, _ptr(hashes), _ptr(move_off),
+        _check(self._l.nsb_eval_cached_decode_async(self._h, slot, _ptr(features), n, _ptr(hashes), _ptr(move_off),
                                                   _ptr(move_idx), mode, _ptr(legal_out), _ptr(win), _ptr(draw),
                                                   _ptr(nan_flag), _ptr(hit_flag)), "nsb_eval_cached_decode_async")
 
     def eval_positions_cached_decode_async(self, slot, positions, n, hashes, move_off, move_idx, mode, legal_out, win,
                                            draw, nan_flag=None, hit_flag=None):
-        _check(lib().nsb_eval_positions_cached_decode_async(self._h, slot, _ptr(positions), n, _ptr(hashes),
+        _check(self._l.nsb_eval_positions_cached_decode_async(self._h, slot, _ptr(positions), n, _ptr(hashes),
                                                             _ptr(move_off), _ptr(move_idx), mode, _ptr(legal_out),
                                                             _ptr(win), _ptr(draw), _ptr(nan_flag), _ptr(hit_flag)),
                "nsb_eval_positions_cached_decode_async")
 
     def eval_cached_decode_device(self, slot, d_features, n, d_hashes, d_off, d_idx, mode, d_legal, d_win, d_draw,
                                   d_flag, d_hit):
-        _check(lib().nsb_eval_cached_decode_device(self._h, slot, _ptr(d_features), n, _ptr(d_hashes), _ptr(d_off),
+        _check(self._l.nsb_eval_cached_decode_device(self._h, slot, _ptr(d_features), n, _ptr(d_hashes), _ptr(d_off),
                                                    _ptr(d_idx), mode, _ptr(d_legal), _ptr(d_win), _ptr(d_draw),
                                                    _ptr(d_flag), _ptr(d_hit)), "nsb_eval_cached_decode_device")
 
     def debug_trunk_timeline(self, slot, d_features, n, positions=False):
         nl = 2 * self.desc.blocks + 2
         out = np.zeros(nl * 4 + 16 + 3 * 1024, dtype=np.uint64)
-        fn = lib().nsb_debug_trunk_timeline_positions if positions else lib().nsb_debug_trunk_timeline
+        fn = self._l.nsb_debug_trunk_timeline_positions if positions else self._l.nsb_debug_trunk_timeline
         _check(fn(self._h, slot, _ptr(d_features), n, out.ctypes.data, out.size), "nsb_debug_trunk_timeline")
         return out[:nl * 4].reshape(nl, 4), out[nl * 4:]
 
@@ -426,33 +453,33 @@ class Context:
         r = DecodeRequest(_ptr(features), _ptr(positions), n, _ptr(hashes), _ptr(move_off), _ptr(move_idx), mode,
                           _ptr(legal_out), _ptr(order_out), _ptr(win), _ptr(draw), _ptr(nan_flag), _ptr(hit_flag),
                           _ptr(row_flags), _ptr(logits_out))
-        _check(lib().nsb_eval_request_async(self._h, slot, C.byref(r)), "nsb_eval_request_async")
+        _check(self._l.nsb_eval_request_async(self._h, slot, C.byref(r)), "nsb_eval_request_async")
 
     def cache_attach(self, owner: "Context"):
-        _check(lib().nsb_cache_attach(self._h, owner._h), "nsb_cache_attach")
+        _check(self._l.nsb_cache_attach(self._h, owner._h), "nsb_cache_attach")
 
     def set_io_mode(self, direct: bool):
-        _check(lib().nsb_set_io_mode(self._h, 1 if direct else 0), "nsb_set_io_mode")
+        _check(self._l.nsb_set_io_mode(self._h, 1 if direct else 0), "nsb_set_io_mode")
 
     def io_mode(self) -> str:
-        return "direct" if lib().nsb_io_mode(self._h) == 1 else "staged"
+        return "direct" if self._l.nsb_io_mode(self._h) == 1 else "staged"
 
     def stream(self, slot=0) -> int:
-        return lib().nsb_stream(self._h, slot) or 0
+        return self._l.nsb_stream(self._h, slot) or 0
 
     def set_timing(self, on: bool):
-        _check(lib().nsb_set_timing(self._h, int(on)), "nsb_set_timing")
+        _check(self._l.nsb_set_timing(self._h, int(on)), "nsb_set_timing")
 
     def trunk_time(self):
         s, n = C.c_double(0), C.c_uint64(0)
-        _check(lib().nsb_trunk_time(self._h, C.byref(s), C.byref(n)), "nsb_trunk_time")
+        _check(self._l.nsb_trunk_time(self._h, C.byref(s), C.byref(n)), "nsb_trunk_time")
         return float(s.value), int(n.value)
 
     def trunk_time_reset(self):
-        _check(lib().nsb_trunk_time_reset(self._h), "nsb_trunk_time_reset")
+        _check(self._l.nsb_trunk_time_reset(self._h), "nsb_trunk_time_reset")
 
     def trunk_kernel_name(self) -> str:
-        return lib().nsb_trunk_kernel_name(self._h).decode()
+        return self._l.nsb_trunk_kernel_name(self._h).decode()
 
     def launch_count(self) -> int:
-        return int(lib().nsb_launch_count(self._h))
+        return int(self._l.nsb_launch_count(self._h))

@@ -19,6 +19,9 @@
 #include <vector>
 
 #include "nsb_internal.h"
+#ifdef NSB_DIAG
+#include "../../include/nsb_diag.h"
+#endif
 
 namespace nsb {
 
@@ -88,6 +91,9 @@ struct nsb_ctx {
     bool duo_always = false;   // every launch uses it (multi-slot pipeline, or forced); otherwise it is chosen per batch size
     nsb::DeviceNet net_duo{};  // the same net with the weight stream in trunk_duo.cu's order (when both kernels are loaded)
     void* d_duo_tiles = nullptr;
+    // launch durations (ms) that use_duo() chooses by; calibrated on this device / net at nsb_load_weights
+    double t_classic_wave = 0.129, t_duo_single = 0.157, t_duo_pair = 0.215;
+    bool calibrated = false;
     nsb::DeviceCache cache{};  // device-resident evaluation cache (nsb_cache_create / nsb_cache_attach)
     bool cache_owned = false;  // false: the table belongs to another ctx of the same device (nsb_cache_attach)
     nsb_net_desc desc{};
@@ -166,7 +172,11 @@ static bool dense_outputs_mapped(size_t n, const float* policy, const float* win
 extern "C" {
 
 const char* nsb_last_error(void) { return g_err; }
-const char* nsb_version(void) { return "nsb 0.2 (sm_100a: tcgen05 position-stationary trunk, cta_group::2 pair trunk, device-resident eval cache)"; }
+const char* nsb_version(void) { return "nsb 0.3 (sm_100a: tcgen05 position-stationary trunk, cta_group::2 pair trunk, device-resident eval cache)"
+#ifdef NSB_DIAG
+           " [diagnostic build]"
+#endif
+        ; }
 
 int nsb_device_count(void) {
     int n = 0;
@@ -210,8 +220,15 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     int rc = trunk_fused_prepare(net->channels);
     if (rc) return rc;
     int max_pairs = 0;
-    // NSB_TRUNK256=single keeps the one-CTA kernel for A/B measurements (diagnostics only)
+    // NSB_TRUNK256=single keeps the one-CTA kernel for A/B measurements (diagnostic build only)
     const char* t256 = getenv("NSB_TRUNK256");
+    const char* t128 = getenv("NSB_TRUNK128");
+#ifndef NSB_DIAG
+    if ((t256 && strcmp(t256, "single") == 0) || (t128 && strcmp(t128, "ts") == 0)) {
+        set_error("nsb_create: NSB_TRUNK256=single / NSB_TRUNK128=ts exist in the diagnostic build only (libnsb_diag.so)");
+        return NSB_ERR_INVALID;
+    }
+#endif
     if (net->channels == 256 && !(t256 && strcmp(t256, "single") == 0)) {
         if ((rc = trunk_pair_prepare(&max_pairs))) return rc;
         if (max_pairs > prop.multiProcessorCount / 2) max_pairs = prop.multiProcessorCount / 2;
@@ -220,7 +237,6 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     // several streams) and gets the two-CTAs-per-SM kernel (trunk_duo.cu: +6 % throughput, measured);
     // a one-slot context evaluates one batch at a time and gets the kernel with the shorter launch
     // (trunk_fused.cu).  NSB_TRUNK128 = classic | duo | ts forces one (ts: experimental trunk_ts.cu).
-    const char* t128 = getenv("NSB_TRUNK128");
     const bool is128 = net->channels == 128;
     const bool use_ts = is128 && t128 && strcmp(t128, "ts") == 0;
     // Unforced, a 128-channel context loads BOTH kernels: a multi-slot pipeline always launches the duo kernel; a
@@ -228,7 +244,9 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     // launch), trunk_duo.cu (two co-resident CTAs per SM share the tensor pipe) where that is faster (use_duo()).
     const bool want_duo = is128 && !use_ts && (t128 ? strcmp(t128, "duo") == 0 : true);
     const bool duo_always = want_duo && (t128 ? true : slots >= 2);
+#ifdef NSB_DIAG
     if (use_ts && (rc = trunk_ts_prepare())) return rc;
+#endif
     int duo_ctas = 0;
     if (want_duo && (rc = trunk_duo_prepare(&duo_ctas))) return rc;
     nsb_ctx* c = new (std::nothrow) nsb_ctx();
@@ -316,6 +334,8 @@ int nsb_weight_blob_random(const nsb_net_desc* net, uint64_t seed, float* blob) 
     return 0;
 }
 
+static int calibrate_kernel_choice(nsb_ctx* c);
+
 int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
     if (!c || !blob) {
         set_error("nsb_load_weights: null argument");
@@ -382,20 +402,63 @@ int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
         c->net_duo = n;
     }
     c->loaded = true;
-    return 0;
+    return calibrate_kernel_choice(c);
 }
 
-// One-slot 128-channel contexts hold both trunk kernels and choose per batch.  Launch durations measured on B200
-// (tools/residency.py, tools/sweep.py): trunk_fused.cu 0.129 ms per wave of 148 CTAs (2 positions each);
-// trunk_duo.cu 0.157 ms while at most one CTA per SM is resident, 0.215 ms per wave of 296 co-resident CTAs.
+// One-slot 128-channel contexts hold both trunk kernels and choose per batch from three launch durations: trunk_fused.cu
+// per wave of one CTA per SM (2 positions each), trunk_duo.cu while at most one CTA per SM is resident, and trunk_duo.cu
+// per wave of two co-resident CTAs per SM.  The durations are measured at nsb_load_weights on this device with this net
+// (calibrate_kernel_choice); the initial values (10 x 128 on a B200 at full clocks) only serve contexts whose batch_max
+// is too small for the choice to exist.
 static bool use_duo(const nsb_ctx* c, int n) {
     if (c->duo_ctas <= 0) return false;
     if (c->duo_always) return true;
     const int groups = (n + 1) / 2, sms = c->num_sms;
-    const double classic = 0.129 * ((groups + sms - 1) / sms);
+    const double classic = c->t_classic_wave * ((groups + sms - 1) / sms);
     const int full = groups / (2 * sms), rest = groups % (2 * sms);  // waves of co-resident pairs, then the remainder
-    const double duo = 0.215 * full + (rest == 0 ? 0.0 : rest <= sms ? 0.157 : 0.215);
+    const double duo = c->t_duo_pair * full + (rest == 0 ? 0.0 : rest <= sms ? c->t_duo_single : c->t_duo_pair);
     return duo < classic;  // in effect: more than one CTA per SM worth of position pairs
+}
+
+// Times the two 128-channel kernels on empty boards (the kernels' duration does not depend on the data): best of three
+// launches after a warm-up each, CUDA events on slot 0's stream.  ~12 launches, once per nsb_load_weights.
+static int calibrate_kernel_choice(nsb_ctx* c) {
+    const int sms = c->num_sms;
+    if (c->duo_ctas <= 0 || c->duo_always || c->batch_max <= 2 * sms) return 0;  // one wave of trunk_fused.cu: no choice to make
+    Slot& s = c->slots[0];
+    const int n_wave = 2 * sms, n_pair = c->batch_max < 4 * sms ? c->batch_max : 4 * sms;
+    NSB_CUDA(cudaMemsetAsync(s.d_feat, 0, (size_t)n_pair * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard), s.stream));
+    cudaEvent_t e0, e1;
+    NSB_CUDA(cudaEventCreate(&e0));
+    NSB_CUDA(cudaEventCreate(&e1));
+    auto best_of = [&](bool duo, int n, double* out) -> int {
+        EvalArgs a{};
+        a.features = s.d_feat;
+        a.n = n;
+        a.win = s.d_win;
+        a.draw = s.d_draw;
+        float best = 1e30f;
+        for (int it = 0; it < 4; ++it) {
+            NSB_CUDA(cudaEventRecord(e0, s.stream));
+            const int k = duo ? launch_trunk_duo(c->net_duo, a, sms, c->duo_ctas, s.stream) : launch_trunk_fused(c->net, a, sms, s.stream);
+            if (k < 0) return k;
+            NSB_CUDA(cudaGetLastError());
+            NSB_CUDA(cudaEventRecord(e1, s.stream));
+            NSB_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            NSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (it > 0 && ms < best) best = ms;
+        }
+        *out = best;
+        return 0;
+    };
+    int rc = best_of(false, n_wave, &c->t_classic_wave);
+    if (!rc) rc = best_of(true, n_wave, &c->t_duo_single);
+    if (!rc) rc = best_of(true, n_pair, &c->t_duo_pair);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->calibrated = rc == 0;
+    return rc;
 }
 
 /* ---- shared launch helper ------------------------------------------------------------------ */
@@ -411,7 +474,9 @@ static int run_trunk(nsb_ctx* c, Slot& s, const EvalArgs& a) {
     }
     int k = c->max_pairs > 0 ? launch_trunk_pair(c->net, a, c->max_pairs, s.stream)
             : use_duo(c, a.n) ? launch_trunk_duo(c->net_duo, a, c->num_sms, c->duo_ctas, s.stream)
+#ifdef NSB_DIAG
             : c->use_ts      ? launch_trunk_ts(c->net, a, c->num_sms, s.stream)
+#endif
                              : launch_trunk_fused(c->net, a, c->num_sms, s.stream);
     if (k < 0) return k;
     NSB_CUDA(cudaGetLastError());
@@ -996,6 +1061,7 @@ static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const
     return 0;
 }
 
+#ifdef NSB_DIAG
 static int debug_timeline(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, const nsb_position* d_positions,
                           size_t n, uint64_t* host_stamps, size_t max_stamps) {
     int rc = check_ctx(c, slot);
@@ -1049,6 +1115,8 @@ int nsb_debug_trunk_timeline_positions(nsb_ctx* c, int slot, const nsb_position*
                                        uint64_t* host_stamps, size_t max_stamps) {
     return debug_timeline(c, slot, nullptr, d_positions, n, host_stamps, max_stamps);
 }
+
+#endif  // NSB_DIAG
 
 int nsb_extract_device(nsb_ctx* c, int slot, const nsb_feature_bitboard* d_features, size_t n, int channels,
                        int channels_first, float* d_planes) {
@@ -1258,6 +1326,7 @@ int nsb_umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* m
     return umma_selftest(gpu, n_cols, k_elems, shift_rows, max_err, epi_err);
 }
 
+#ifdef NSB_DIAG
 int nsb_debug_umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int layout, int iters, float* max_err,
                          double* cycles_per_mma) {
     return umma_probe(gpu, n_cols, k_elems, shift_rows, layout, iters, max_err, cycles_per_mma);
@@ -1266,6 +1335,8 @@ int nsb_debug_umma_probe(int gpu, int n_cols, int k_elems, int shift_rows, int l
 int nsb_debug_bulk_rate_probe(int gpu, int ctas, int tile_bytes, int stages, int split, double* bytes_per_cycle) {
     return bulk_rate_probe(gpu, ctas, tile_bytes, stages, split, bytes_per_cycle);
 }
+
+#endif  // NSB_DIAG
 
 int nsb_event_create(void** out) {
     if (!out) return NSB_ERR_INVALID;

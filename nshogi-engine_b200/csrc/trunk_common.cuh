@@ -41,6 +41,18 @@ __device__ __forceinline__ uint4 plane_bits(uint4 f) {
     return make_uint4(s0, s1, s2, (uint32_t)f32_to_bf16_bits(__uint_as_float(f.w)));
 }
 
+// Diagnostics (tools/timeline.py, tools/residency.py): the clock64 stamps exist only in the diagnostic build of the
+// library (libnsb_diag.so, -DNSB_DIAG); in the product build the pointer is a compile-time null and every stamp
+// and its predicate fold away.
+__device__ __forceinline__ unsigned long long* eval_timeline(const EvalArgs& a) {
+#ifdef NSB_DIAG
+    return a.timeline;
+#else
+    (void)a;
+    return nullptr;
+#endif
+}
+
 // A launch works on n positions, or - behind a cache probe - on the *count misses listed in index[].
 __device__ __forceinline__ int eval_count(const EvalArgs& a) { return a.count ? __ldg(a.count) : a.n; }
 // batch index of work-list entry li, -1 past the end

@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
     const int my_passes =
         (int)blockIdx.x < groups ? (groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int NL = net.num_layers;
-    const bool stamp = a.timeline && blockIdx.x == 0;  // diagnostics: tools/timeline.py
+    const bool stamp = eval_timeline(a) && blockIdx.x == 0;  // diagnostics: tools/timeline.py
     // diagnostics: where and when every CTA ran (co-residency of the two CTAs of an SM: tools/residency.py)
-    unsigned long long* cta_rec = (a.timeline && blockIdx.x < 1024) ? a.timeline + 4 * NL + 16 + 3 * blockIdx.x : nullptr;
+    unsigned long long* cta_rec = (eval_timeline(a) && blockIdx.x < 1024) ? eval_timeline(a) + 4 * NL + 16 + 3 * blockIdx.x : nullptr;
     if (cta_rec && threadIdx.x == 0) {
         unsigned smid;
         unsigned long long t;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                     mbar_wait(bar_act, act_phase);
                     act_phase ^= 1u;
                     tc_fence_after();
-                    if (stamp && p == 0 && lane == 0) a.timeline[4 * L + 0] = clock64();
+                    if (stamp && p == 0 && lane == 0) eval_timeline(a)[4 * L + 0] = clock64();
                     const bool head = (L == NL - 1);
                     const uint32_t in_buf = (L & 1) ? bufA : bufB;
                     const int ntaps = head ? 1 : 9;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                     }
                     if (elect_one()) umma_commit(bar_acc);
                     __syncwarp();
-                    if (stamp && p == 0 && lane == 0) a.timeline[4 * L + 1] = clock64();
+                    if (stamp && p == 0 && lane == 0) eval_timeline(a)[4 * L + 1] = clock64();
                 }
             }
         }
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                 mbar_wait(bar_acc, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                if (stamp && p == 0 && et == 0) a.timeline[4 * L + 2] = clock64();
+                if (stamp && p == 0 && et == 0) eval_timeline(a)[4 * L + 2] = clock64();
                 const uint32_t out_buf = ((L & 1) ? bufB : bufA) + G::GUARD * 16;
                 const bool residual = (L >= 2) && ((L & 1) == 0);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_act);
-                if (stamp && p == 0 && et == 0) a.timeline[4 * L + 3] = clock64();
+                if (stamp && p == 0 && et == 0) eval_timeline(a)[4 * L + 3] = clock64();
             }
 
             // -- heads: row 32*(h/7) + h%7 of the accumulator holds head channel h

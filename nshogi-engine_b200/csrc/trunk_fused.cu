@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
         (int)blockIdx.x < groups ? (groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int NL = net.num_layers;
 
-    if (a.timeline && blockIdx.x == 0 && threadIdx.x == 128) a.timeline[4 * NL + 0] = clock64();
+    if (eval_timeline(a) && blockIdx.x == 0 && threadIdx.x == 128) eval_timeline(a)[4 * NL + 0] = clock64();
     // ---- one-time setup ---------------------------------------------------------------------
     for (int i = threadIdx.x; i < 2 * G::BUF_BYTES / 16; i += kThreads)
         reinterpret_cast<uint4*>(smem + G::OFF_BUF_A)[i] = make_uint4(0, 0, 0, 0);
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    if (a.timeline && blockIdx.x == 0 && threadIdx.x == 128) a.timeline[4 * NL + 1] = clock64();
+    if (eval_timeline(a) && blockIdx.x == 0 && threadIdx.x == 128) eval_timeline(a)[4 * NL + 1] = clock64();
 
     if (warp == 0 || warp == 2) {
         // ===== weight producers: linear stream of 16 KB tiles, re-walked once per pass ==========
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
                 mbar_wait(bar_act, act_phase);
                 act_phase ^= 1u;
                 tc_fence_after();
-                if (a.timeline && blockIdx.x == 0 && p == 0 && lane == 0) a.timeline[4 * L + 0] = clock64();
+                if (eval_timeline(a) && blockIdx.x == 0 && p == 0 && lane == 0) eval_timeline(a)[4 * L + 0] = clock64();
                 const bool head = (L == NL - 1);
                 const uint32_t in_buf = (L & 1) ? bufA : bufB;
                 const int ntaps = head ? 1 : 9;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
                 }
                 if (elect_one()) umma_commit(bar_acc);  // accumulator(s) of layer L complete
                 __syncwarp();
-                if (a.timeline && blockIdx.x == 0 && p == 0 && lane == 0) a.timeline[4 * L + 1] = clock64();
+                if (eval_timeline(a) && blockIdx.x == 0 && p == 0 && lane == 0) eval_timeline(a)[4 * L + 1] = clock64();
             }
         }
     } else if (warp >= 4) {
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
         const int part = ew >> 2;          // C=128: column half (= position); C=256: Cout half
         const int e_col0 = (C == 128) ? 96 * part : 0;
         const int e_half = (C == 128) ? 0 : part;
-        if (a.timeline && blockIdx.x == 0 && et == 0) a.timeline[4 * NL + 11] = clock64();
+        if (eval_timeline(a) && blockIdx.x == 0 && et == 0) eval_timeline(a)[4 * NL + 11] = clock64();
         EpilogueMask<3> realmask;
         realmask.init(e_col0, lane);
         uint32_t acc_phase = 0;
@@ -160,13 +160,13 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
             const int b0 = ((int)blockIdx.x + p * (int)gridDim.x) * G::NPOS;
 
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
-            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 8] = clock64();
-            unsigned long long* tl = (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) ? a.timeline + 4 * NL : nullptr;
+            if (eval_timeline(a) && blockIdx.x == 0 && p == 0 && et == 0) eval_timeline(a)[4 * NL + 8] = clock64();
+            unsigned long long* tl = (eval_timeline(a) && blockIdx.x == 0 && p == 0 && et == 0) ? eval_timeline(a) + 4 * NL : nullptr;
             expand_features<G::NPOS, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_act);
-            if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * NL + 2] = clock64();
+            if (eval_timeline(a) && blockIdx.x == 0 && p == 0 && et == 0) eval_timeline(a)[4 * NL + 2] = clock64();
 
             // -- conv layers: TMEM -> +bias (+skip) -> ReLU -> bf16 -> next layer's B operand ----
             for (int L = 0; L < NL - 1; ++L) {
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
                 mbar_wait(bar_acc, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * L + 2] = clock64();
+                if (eval_timeline(a) && blockIdx.x == 0 && p == 0 && et == 0) eval_timeline(a)[4 * L + 2] = clock64();
                 const uint32_t out_buf = ((L & 1) ? bufB : bufA) + G::GUARD * 16;
                 const bool residual = (L >= 2) && ((L & 1) == 0);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + e_half * G::NCOLS + e_col0;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_act);
-                if (a.timeline && blockIdx.x == 0 && p == 0 && et == 0) a.timeline[4 * L + 3] = clock64();
+                if (eval_timeline(a) && blockIdx.x == 0 && p == 0 && et == 0) eval_timeline(a)[4 * L + 3] = clock64();
             }
 
             // -- heads: accumulator row 32*(h/7) + h%7 holds head channel h (0..26 policy planes,
@@ -233,8 +233,12 @@ int trunk_fused_prepare(int channels) {
         e = cudaFuncSetAttribute(trunk_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  TrunkGeom<128>::SMEM_BYTES);
     else if (channels == 256)
+#ifdef NSB_DIAG  // the one-CTA 256-channel kernel: superseded by trunk_pair.cu, kept as its bit-for-bit reference
         e = cudaFuncSetAttribute(trunk_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  TrunkGeom<256>::SMEM_BYTES);
+#else
+        e = cudaSuccess;
+#endif
     else {
         set_error("trunk: unsupported width %d (128 or 256)", channels);
         return NSB_ERR_INVALID;
@@ -254,10 +258,15 @@ int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cud
         const int grid = groups < num_sms ? groups : num_sms;
         trunk_fused_kernel<128><<<grid, kThreads, G::SMEM_BYTES, s>>>(net, a);
     } else {
+#ifdef NSB_DIAG
         using G = TrunkGeom<256>;
         const int groups = (a.n + G::NPOS - 1) / G::NPOS;
         const int grid = groups < num_sms ? groups : num_sms;
         trunk_fused_kernel<256><<<grid, kThreads, G::SMEM_BYTES, s>>>(net, a);
+#else
+        set_error("trunk: 256-channel nets run on trunk_pair.cu (the one-CTA kernel is in the diagnostic build)");
+        return NSB_ERR_INVALID;
+#endif
     }
     return 1;
 }

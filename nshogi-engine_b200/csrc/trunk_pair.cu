@@ -62,9 +62,9 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
     const int groups = (n_eff + 1) / 2;
     const int my_passes = pair < groups ? (groups - pair + npairs - 1) / npairs : 0;
     const int NL = net.num_layers;
-    const bool stamp = a.timeline && blockIdx.x == 0;
+    const bool stamp = eval_timeline(a) && blockIdx.x == 0;
 
-    if (stamp && threadIdx.x == 128) a.timeline[4 * NL + 0] = clock64();
+    if (stamp && threadIdx.x == 128) eval_timeline(a)[4 * NL + 0] = clock64();
     // ---- one-time setup ---------------------------------------------------------------------
     for (int i = threadIdx.x; i < (2 * G::BUF_BYTES + G::XBUF_BYTES) / 16; i += kThreads)
         reinterpret_cast<uint4*>(smem + G::OFF_BUF_A)[i] = make_uint4(0, 0, 0, 0);
@@ -85,7 +85,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
     cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / bulk push
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    if (stamp && threadIdx.x == 128) a.timeline[4 * NL + 1] = clock64();
+    if (stamp && threadIdx.x == 128) eval_timeline(a)[4 * NL + 1] = clock64();
 
     if (warp == 0) {
         // ===== weight producer: my Cout half of every conv tile pair, all head tiles ===========
@@ -126,7 +126,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                 mbar_wait(bar_peer_act, act_phase);
                 act_phase ^= 1u;
                 tc_fence_after();
-                if (stamp && p == 0 && lane == 0) a.timeline[4 * L + 0] = clock64();
+                if (stamp && p == 0 && lane == 0) eval_timeline(a)[4 * L + 0] = clock64();
                 const bool head = (L == NL - 1);
                 const uint32_t in_buf = (L & 1) ? bufA : bufB;
                 const int ntaps = head ? 1 : 9;
@@ -156,7 +156,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                 }
                 if (elect_one()) umma_commit_pair(bar_acc, 3);  // accumulators of layer L complete in both CTAs
                 __syncwarp();
-                if (stamp && p == 0 && lane == 0) a.timeline[4 * L + 1] = clock64();
+                if (stamp && p == 0 && lane == 0) eval_timeline(a)[4 * L + 1] = clock64();
             }
         }
     } else if (warp == 2) {
@@ -208,7 +208,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
         const int ew = warp - 4;           // 0..7
         const int q = ew & 3;              // TMEM lane quadrant (== warp % 4): 32 of my 128 Cout
         const int lbw = ew >> 2;           // the 16-lane block of that quadrant this warp owns (both positions)
-        if (stamp && et == 0) a.timeline[4 * NL + 11] = clock64();
+        if (stamp && et == 0) eval_timeline(a)[4 * NL + 11] = clock64();
         EpilogueMask<3> realmask;
         realmask.init(0, lane);
         uint32_t acc_phase = 0, skip_phase = 0;
@@ -216,7 +216,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
             const int b0 = (pair + p * npairs) * 2 + (int)rank;  // my position
 
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
-            unsigned long long* tl = (stamp && p == 0 && et == 0) ? a.timeline + 4 * NL : nullptr;
+            unsigned long long* tl = (stamp && p == 0 && et == 0) ? eval_timeline(a) + 4 * NL : nullptr;
             if (tl) tl[8] = clock64();
             expand_features<1, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
@@ -234,7 +234,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                 mbar_wait(bar_acc, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                if (stamp && p == 0 && et == 0) a.timeline[4 * L + 2] = clock64();
+                if (stamp && p == 0 && et == 0) eval_timeline(a)[4 * L + 2] = clock64();
                 const uint32_t out_base = (L & 1) ? bufB : bufA;
                 const bool residual = (L >= 2) && ((L & 1) == 0);
                 const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -264,7 +264,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_act);
-                if (stamp && p == 0 && et == 0) a.timeline[4 * L + 3] = clock64();
+                if (stamp && p == 0 && et == 0) eval_timeline(a)[4 * L + 3] = clock64();
             }
 
             // -- heads: both CTAs loaded the same head tiles, so each holds the head rows of both

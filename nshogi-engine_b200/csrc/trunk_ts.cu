@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
     const int my_passes =
         (int)blockIdx.x < groups ? (groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int NL = net.num_layers;
-    const bool stamp = a.timeline && blockIdx.x == 0;
+    const bool stamp = eval_timeline(a) && blockIdx.x == 0;
 
-    if (stamp && threadIdx.x == 128) a.timeline[4 * NL + 0] = clock64();
+    if (stamp && threadIdx.x == 128) eval_timeline(a)[4 * NL + 0] = clock64();
     // ---- one-time setup ---------------------------------------------------------------------
     for (int i = threadIdx.x; i < 2 * G::BUF_BYTES / 16; i += G::THREADS)
         reinterpret_cast<uint4*>(smem + G::OFF_BUF_A)[i] = make_uint4(0, 0, 0, 0);
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    if (stamp && threadIdx.x == 128) a.timeline[4 * NL + 1] = clock64();
+    if (stamp && threadIdx.x == 128) eval_timeline(a)[4 * NL + 1] = clock64();
 
     if (warp < 4) {
         // ===== weight producers: L2 -> registers -> tensor memory ================================
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
                     for (int kc = 0; kc < G::KC64; ++kc) {
                         mbar_wait(bar_kb(kc), kb_phase);
                         tc_fence_after();
-                        if (stamp && p == 0 && lane == 0 && kc == 0) a.timeline[4 * L + 0] = clock64();
+                        if (stamp && p == 0 && lane == 0 && kc == 0) eval_timeline(a)[4 * L + 0] = clock64();
                         const int nk = stage_steps(L, kc);
                         for (int tap = 0; tap < ntaps; ++tap) {
                             const int shift = head ? 0 : (tap / 3 - 1) * 10 + (tap % 3 - 1);
@@ -216,10 +216,10 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
                     kb_phase ^= 1u;
                     if (elect_one()) umma_commit(bar_acc);  // accumulator of layer L complete
                     __syncwarp();
-                    if (stamp && p == 0 && lane == 0) a.timeline[4 * L + 1] = clock64();
+                    if (stamp && p == 0 && lane == 0) eval_timeline(a)[4 * L + 1] = clock64();
                 }
             }
-            if (stamp && lane == 0) a.timeline[4 * NL + 12] = (unsigned long long)wait_cycles;
+            if (stamp && lane == 0) eval_timeline(a)[4 * NL + 12] = (unsigned long long)wait_cycles;
         }
     } else {
         // ===== expansion + epilogues + heads =====================================================
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
         const int q = ew & 3;              // TMEM lane quadrant (== warp % 4)
         const int part = ew >> 2;          // column half (= position)
         const int e_col0 = 96 * part;
-        if (stamp && et == 0) a.timeline[4 * NL + 11] = clock64();
+        if (stamp && et == 0) eval_timeline(a)[4 * NL + 11] = clock64();
         EpilogueMask<3> realmask;
         realmask.init(e_col0, lane);
         uint32_t acc_phase = 0;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
             const int b0 = ((int)blockIdx.x + p * (int)gridDim.x) * G::NPOS;
 
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
-            unsigned long long* tl = (stamp && p == 0 && et == 0) ? a.timeline + 4 * NL : nullptr;
+            unsigned long long* tl = (stamp && p == 0 && et == 0) ? eval_timeline(a) + 4 * NL : nullptr;
             if (tl) tl[8] = clock64();
             expand_features<G::NPOS, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
                 mbar_wait(bar_acc, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                if (stamp && p == 0 && et == 0) a.timeline[4 * L + 2] = clock64();
+                if (stamp && p == 0 && et == 0) eval_timeline(a)[4 * L + 2] = clock64();
                 const uint32_t out_buf = ((L & 1) ? bufB : bufA) + G::GUARD * 16;
                 const bool residual = (L >= 2) && ((L & 1) == 0);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(L & 1) * G::NCOLS + e_col0;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_kb(lb));
                 }
-                if (stamp && p == 0 && et == 0) a.timeline[4 * L + 3] = clock64();
+                if (stamp && p == 0 && et == 0) eval_timeline(a)[4 * L + 3] = clock64();
             }
 
             // -- heads: accumulator row 32*(h/7) + h%7 holds head channel h (0..26 policy planes,

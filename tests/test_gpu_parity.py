@@ -226,7 +226,7 @@ def test_pair_kernel_equals_single_cta_kernel(nb, orc, synth, monkeypatch):
         win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
         legal = np.zeros(int(off[-1]), dtype=np.float32)
         flag = np.zeros(n, dtype=np.uint8)
-        with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+        with nb.Context(desc, batch_max=n, blob=blob, diag=single) as ctx:   # the one-CTA kernel: libnsb_diag.so
             ctx.eval_async(0, big, n, policy, win, draw)
             ctx.await_(0)
             ctx.eval_decode_async(0, big, n, off, idx, nb.DECODE_PROBS, legal, win, draw, flag)
@@ -426,7 +426,7 @@ def test_ts_kernel_matches_oracle_and_default_kernel(nb, orc, synth, monkeypatch
         policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
         win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
         legal = np.zeros(int(off[-1]), dtype=np.float32)
-        with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+        with nb.Context(desc, batch_max=n, blob=blob, diag=ts) as ctx:   # trunk_ts.cu: libnsb_diag.so
             ctx.eval_async(0, fb, n, policy, win, draw)
             ctx.await_(0)
             ctx.eval_decode_async(0, fb, n, off, idx, nb.DECODE_PROBS, legal, win, draw, None)

@@ -257,6 +257,13 @@ def test_library_exports_every_declared_symbol(nb):
     assert declared == set(nb.SIGNATURES), (declared ^ set(nb.SIGNATURES))
     l = nb.lib()
     assert b"sm_100a" in l.nsb_version()
+    # the diagnostic build (include/nsb_diag.h): every product symbol + the nsb_debug_* entry points, nothing else
+    dhdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "nsb_diag.h")).read(), flags=re.S)
+    diag_declared = set(re.findall(r"\b(nsb_[a-z0-9_]+)\s*\(", dhdr))
+    assert diag_declared == set(nb.DIAG_SIGNATURES) and all(n.startswith("nsb_debug_") for n in diag_declared)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", nb.DIAG_LIB_PATH], text=True)
+    assert set(re.findall(r" T (nsb_[a-z0-9_]+)", out)) == declared | diag_declared
+    assert b"diagnostic build" in nb.diag_lib().nsb_version() and b"diagnostic" not in l.nsb_version()
 
 
 def test_library_is_sm100a_tcgen05_and_has_no_oracle(nb):
@@ -266,6 +273,10 @@ def test_library_is_sm100a_tcgen05_and_has_no_oracle(nb):
     if sass.returncode == 0 and sass.stdout:
         assert "sm_100a" in sass.stdout
         assert "UTCHMMA" in sass.stdout and "UBLKCP" in sass.stdout and "LDTM" in sass.stdout
+        # probes, the experimental trunk_ts.cu and the superseded one-CTA 256-channel kernel are not in the product
+        kernels = set(re.findall(r"Function : (\S+)", sass.stdout))
+        assert kernels and not any(k for k in kernels if "umma_probe" in k or "bulk_" in k or "trunk_ts" in k or "trunk_fused_kernelILi256" in k), kernels
+        assert any("trunk_duo_kernel" in k for k in kernels) and any("trunk_pair_kernel" in k for k in kernels)
     needed = subprocess.check_output(["readelf", "-d", nb.LIB_PATH], text=True)
     assert "oracle" not in needed
     pkg_dir = os.path.dirname(nb.LIB_PATH)

@@ -17,7 +17,7 @@ def run(mode):
     if mode: os.environ["NSB_TRUNK256"] = mode
     else: os.environ.pop("NSB_TRUNK256", None)
     policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32); win = np.zeros(n, dtype=np.float32); draw = np.zeros(n, dtype=np.float32)
-    with nb.Context(desc, batch_max=max(n, 8), blob=blob) as ctx:
+    with nb.Context(desc, batch_max=max(n, 8), blob=blob, diag=bool(mode)) as ctx:   # "single": diagnostic build
         ctx.eval_async(0, fb, n, policy, win, draw); ctx.await_(0)
     return policy, win, draw
 ps, ws, ds = run("single")

@@ -19,7 +19,7 @@ def run(ctx, slot):
     ctx.eval_decode_async(slot, fb, n, off, idx, nb.DECODE_LOGITS, legal, win, draw, None)
     return legal, win, draw
 os.environ["NSB_TRUNK256"] = "single"
-with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+with nb.Context(desc, batch_max=n, blob=blob, diag=True) as ctx:   # the one-CTA kernel lives in libnsb_diag.so
     ref = run(ctx, 0); ctx.await_(0)
 os.environ.pop("NSB_TRUNK256")
 bad = 0

@@ -16,7 +16,7 @@ pkg = graft.load_package()
 nb, synth = pkg.binding, pkg.synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 desc = nb.net_desc(128, 10)
-ctx = nb.Context(desc, batch_max=B, slots=2, seed=1234)
+ctx = nb.Context(desc, batch_max=B, slots=2, seed=1234, diag=True)
 fb = synth.random_feature_bitboards(B * 86, seed=1)
 d_fb = nb.DeviceBuffer.from_host(fb)
 for _ in range(3):

@@ -15,7 +15,7 @@ C = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 blocks = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 desc = nb.net_desc(C, blocks)
-ctx = nb.Context(desc, batch_max=B, seed=1234)
+ctx = nb.Context(desc, batch_max=B, seed=1234, diag=True)   # the clock64 stamps exist in libnsb_diag.so only
 POSITIONS = os.environ.get("NSB_TIMELINE_POSITIONS") == "1"   # feed packed positions: stage 1 in the prologue
 fb = synth.random_positions(B, seed=1) if POSITIONS else synth.random_feature_bitboards(B * 86, seed=1)
 d_fb = nb.DeviceBuffer.from_host(fb)
