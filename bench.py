@@ -303,6 +303,7 @@ def run_b200(args):
     if nb.device_count() < 1:
         raise SystemExit("bench: no CUDA device; the product path has no CPU fallback")
     gpu = info.local_rank
+    numa_bound = nb.numa_bind_thread(gpu)     # host buffers and this thread on the GPU's own NUMA node (evaluator.cc:39-83,127-136)
     B, C, blocks, slots, bps = args.batch, args.channels, args.blocks, args.slots, args.batches_per_step
     desc = nb.net_desc(C, blocks)
     blob = nb.random_blob(desc, args.seed)
@@ -353,17 +354,17 @@ def run_b200(args):
     # ---- e2e: host buffers through the C ABI, `slots` batches in flight ----------------------------------------------
     h_pool_n = 16
     n_moves, fb_bytes = wl.n_moves, wl.fb_bytes
-    h_fb = [nb.PinnedArray((B * 86,), nb.FEATURE_BITBOARD) for _ in range(h_pool_n)]
+    h_fb = [nb.PinnedArray((B * 86,), nb.FEATURE_BITBOARD, gpu=gpu) for _ in range(h_pool_n)]
     for k, a in enumerate(h_fb):
         a.array[:] = wl.host_pool[k % wl.pool]
-    h_off = nb.PinnedArray((B + 1,), np.uint32); h_off.array[:] = wl.off
-    h_idx = nb.PinnedArray((max(n_moves, 1),), np.uint16); h_idx.array[:n_moves] = wl.idx
-    h_legal = [nb.PinnedArray((max(n_moves, 1),), np.float32) for _ in range(slots)]
-    h_win = [nb.PinnedArray((B,), np.float32) for _ in range(slots)]
-    h_draw = [nb.PinnedArray((B,), np.float32) for _ in range(slots)]
-    h_flag = [nb.PinnedArray((B,), np.uint8) for _ in range(slots)]
-    h_policy = [nb.PinnedArray((B * 2187,), np.float32) for _ in range(slots)]
-    h_pos = [nb.PinnedArray((B,), nb.POSITION) for _ in range(h_pool_n)]
+    h_off = nb.PinnedArray((B + 1,), np.uint32, gpu=gpu); h_off.array[:] = wl.off
+    h_idx = nb.PinnedArray((max(n_moves, 1),), np.uint16, gpu=gpu); h_idx.array[:n_moves] = wl.idx
+    h_legal = [nb.PinnedArray((max(n_moves, 1),), np.float32, gpu=gpu) for _ in range(slots)]
+    h_win = [nb.PinnedArray((B,), np.float32, gpu=gpu) for _ in range(slots)]
+    h_draw = [nb.PinnedArray((B,), np.float32, gpu=gpu) for _ in range(slots)]
+    h_flag = [nb.PinnedArray((B,), np.uint8, gpu=gpu) for _ in range(slots)]
+    h_policy = [nb.PinnedArray((B * 2187,), np.float32, gpu=gpu) for _ in range(slots)]
+    h_pos = [nb.PinnedArray((B,), nb.POSITION, gpu=gpu) for _ in range(h_pool_n)]
     for a_ in h_pos:
         a_.array[:] = wl.pos[wl.rng.integers(0, len(wl.pos), size=B)]
     sink = 0.0
@@ -475,7 +476,9 @@ def run_b200(args):
                                  "api": "nsb_eval_positions_decode_async + nsb_await (packed positions in, stage 1 in the trunk prologue)",
                                  "h2d_bytes_per_step": (B * 108 + (B + 1) * 4 + n_moves * 2) * bps,
                                  "d2h_bytes_per_step": (n_moves * 4 + B * 4 * 2 + B) * bps},
-                "one_batch_in_flight": latency},
+                "one_batch_in_flight": latency,
+                "host_buffers": {"numa_node_of_gpu": nb.gpu_numa_node(gpu), "thread_bound_to_node": bool(numa_bound),
+                                 "alloc": "nsb_host_alloc_near (page-locked, on the GPU's NUMA node)"}},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "per_step_ms": [round(x, 3) for x in per_step] if per_step and len(per_step) <= 64 else None,
         "counters": counters,

@@ -60,7 +60,7 @@ typedef struct nsb_feature_bitboard {
  * canonical random-init net: stem conv3x3(in->C) ; blocks x [conv3x3, conv3x3 + skip] ;
  * policy conv1x1(C->27) ; value conv1x1(C->1) -> FC(81->hidden) -> FC(hidden->2) -> sigmoid. */
 typedef struct nsb_net_desc {
-    int32_t in_channels;  /* 86                                  */
+    int32_t in_channels;  /* feature planes per position: 86 (SimpleFeatures), 93 (CustomFeaturesV1), <= 96 */
     int32_t channels;     /* trunk width C (128 or 256)          */
     int32_t blocks;       /* residual blocks (10, 20, 40)        */
     int32_t value_hidden; /* hidden units of the value MLP (256) */
@@ -321,6 +321,16 @@ uint64_t nsb_launch_count(nsb_ctx* ctx);
  * Memory from nsb_host_alloc is page-locked AND mapped into the device's address space. */
 int nsb_host_alloc(void** out, size_t bytes);
 int nsb_host_free(void* p);
+/* The same, placed on the NUMA node of `gpu` (its PCI function's numa_node): what the reference's Evaluator does with
+ * numa_alloc_onnode in NUMA_ENABLED builds (src/evaluate/evaluator.cc:127-136) - except that the node is the GPU's own.
+ * On an 8-GPU box this keeps each GPU's D2H stream (8,756 B per sample through the Infer contract) on its own socket.
+ * Falls back to ordinary placement where the node is unknown.  Free with nsb_host_free. */
+int nsb_host_alloc_near(void** out, size_t bytes, int gpu);
+/* NUMA node of a GPU (-1: unknown / single node). */
+int nsb_gpu_numa_node(int gpu);
+/* Pin the calling thread to the CPUs of the GPU's NUMA node (== the affinity half of evaluator.cc:39-83).  0 = done,
+ * 1 = nothing to do on this machine (not an error). */
+int nsb_numa_bind_thread(int gpu);
 /* Page-lock (or adopt, if the caller already did: cudaHostRegister in evaluator.cc:95-106) a buffer the
  * caller owns, so that calls using it qualify for NSB_IO_DIRECT below.  Returns NSB_OK when this call locked the
  * range (undo with nsb_host_unregister), NSB_HOST_ALREADY_LOCKED (> 0, not an error) when it already was - by the

@@ -94,6 +94,9 @@ SIGNATURES = {
     "nsb_io_mode": (C.c_int, [_P]),
     "nsb_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "nsb_host_free": (C.c_int, [_P]),
+    "nsb_host_alloc_near": (C.c_int, [C.POINTER(_P), C.c_size_t, C.c_int]),
+    "nsb_gpu_numa_node": (C.c_int, [C.c_int]),
+    "nsb_numa_bind_thread": (C.c_int, [C.c_int]),
     "nsb_device_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "nsb_device_free": (C.c_int, [_P]),
     "nsb_memcpy_h2d": (C.c_int, [_P, _P, C.c_size_t]),
@@ -192,12 +195,16 @@ class PinnedArray:
     """numpy view over cudaHostAlloc'ed memory (reference pins with cudaHostRegister,
     src/evaluate/evaluator.cc:95-106)."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, gpu: Optional[int] = None):
+        """gpu: place the pages on that GPU's NUMA node (nsb_host_alloc_near)."""
         self.dtype = np.dtype(dtype)
         self.shape = tuple(shape) if isinstance(shape, (tuple, list)) else (int(shape),)
         nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
         p = _P()
-        _check(lib().nsb_host_alloc(C.byref(p), nbytes), "nsb_host_alloc")
+        if gpu is None:
+            _check(lib().nsb_host_alloc(C.byref(p), nbytes), "nsb_host_alloc")
+        else:
+            _check(lib().nsb_host_alloc_near(C.byref(p), nbytes, gpu), "nsb_host_alloc_near")
         self._p = p
         buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
@@ -257,6 +264,15 @@ class DeviceBuffer:
         if self.ptr:
             lib().nsb_device_free(self.ptr)
             self.ptr = None
+
+
+def gpu_numa_node(gpu: int = 0) -> int:
+    return lib().nsb_gpu_numa_node(gpu)
+
+
+def numa_bind_thread(gpu: int = 0) -> bool:
+    """Pin the calling thread to the CPUs of the GPU's NUMA node; False when there is nothing to do here."""
+    return lib().nsb_numa_bind_thread(gpu) == 0
 
 
 def device_sync():

@@ -38,11 +38,12 @@ void set_error(const char* fmt, ...) {
 // every device's address space at their host address, so a kernel can read its inputs from them and
 // write its results into them over PCIe without a copy node on the stream ("direct" I/O mode).
 static std::mutex g_host_mu;
-enum class HostKind { Alloc, Registered, Adopted };
+enum class HostKind { Alloc, NodeAlloc, Registered, Adopted };
 struct HostRange {
     size_t bytes = 0;
     bool direct = true;  // mapped at its host address: kernels may dereference the host pointer
-    // Alloc: nsb_host_alloc (cudaFreeHost in nsb_host_free); Registered: page-locked by nsb_host_register
+    // Alloc: nsb_host_alloc (cudaFreeHost in nsb_host_free); NodeAlloc: nsb_host_alloc_near (anonymous pages on the
+    // GPU's NUMA node, page-locked with cudaHostRegister; unregistered and unmapped in nsb_host_free); Registered: page-locked by nsb_host_register
     // (cudaHostUnregister is ours to call); Adopted: page-locked by the caller before we saw it (the reference's
     // Evaluator, evaluator.cc:95-106) - the caller unlocks it, we only forget it (nsb_host_unregister)
     HostKind kind = HostKind::Alloc;
@@ -164,6 +165,17 @@ static int check_offsets(const uint32_t* off, size_t n, const char* who) {
     return 0;
 }
 
+// Stage 1 on the device builds the 86 planes of preset::SimpleFeatures (pack_device.cuh); a net that takes another
+// feature set (93-channel CustomFeaturesV1: check / pawn-file / score planes need the rules library) is fed bitboards.
+static int check_positions_net(const nsb_ctx* c, const char* who) {
+    if (c->desc.in_channels != NSB_FEATURE_CHANNELS) {
+        set_error("%s: packed positions expand to the %d planes of SimpleFeatures; this net takes %d channels (feed bitboards)",
+                  who, NSB_FEATURE_CHANNELS, c->desc.in_channels);
+        return NSB_ERR_INVALID;
+    }
+    return 0;
+}
+
 static bool dense_outputs_mapped(size_t n, const float* policy, const float* win, const float* draw) {
     return host_mapped(policy, n * kPolicySize * sizeof(float)) && host_mapped(win, n * sizeof(float)) &&
            host_mapped(draw, n * sizeof(float));
@@ -193,14 +205,10 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
         return NSB_ERR_INVALID;
     }
     if ((net->channels != 128 && net->channels != 256) || net->blocks < 1 || net->blocks > 80 ||
-        net->in_channels < 1 || net->in_channels > kStemCin || net->value_hidden < 1 ||
+        net->in_channels < 1 || net->in_channels > kMaxInChannels || net->value_hidden < 1 ||
         net->value_hidden > kMaxHidden) {
         set_error("nsb_create: unsupported net (channels 128|256, blocks 1..80, in_channels<=%d, hidden<=%d)",
-                  kStemCin, kMaxHidden);
-        return NSB_ERR_INVALID;
-    }
-    if (net->in_channels != NSB_FEATURE_CHANNELS) {
-        set_error("nsb_create: in_channels must be %d (preset::SimpleFeatures)", NSB_FEATURE_CHANNELS);
+                  kMaxInChannels, kMaxHidden);
         return NSB_ERR_INVALID;
     }
     int ndev = 0;
@@ -273,7 +281,7 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     const size_t B = (size_t)batch_max;
     for (auto& s : c->slots) {
         cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);  // trt.cc:79
-        if (e == cudaSuccess) e = cudaMalloc(&s.d_feat, B * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard));
+        if (e == cudaSuccess) e = cudaMalloc(&s.d_feat, B * (size_t)net->in_channels * sizeof(nsb_feature_bitboard));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_pos, B * sizeof(nsb_position));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_policy, B * kPolicySize * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&s.d_win, B * sizeof(float));
@@ -381,6 +389,7 @@ int nsb_load_weights(nsb_ctx* c, const float* blob, size_t n_floats) {
     n.channels = C;
     n.blocks = d.blocks;
     n.in_channels = d.in_channels;
+    n.stem_steps = stem_steps(d.in_channels);
     n.hidden = H;
     n.num_layers = NL;
     n.stages_per_pass = stages;
@@ -427,7 +436,7 @@ static int calibrate_kernel_choice(nsb_ctx* c) {
     if (c->duo_ctas <= 0 || c->duo_always || c->batch_max <= 2 * sms) return 0;  // one wave of trunk_fused.cu: no choice to make
     Slot& s = c->slots[0];
     const int n_wave = 2 * sms, n_pair = c->batch_max < 4 * sms ? c->batch_max : 4 * sms;
-    NSB_CUDA(cudaMemsetAsync(s.d_feat, 0, (size_t)n_pair * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard), s.stream));
+    NSB_CUDA(cudaMemsetAsync(s.d_feat, 0, (size_t)n_pair * c->desc.in_channels * sizeof(nsb_feature_bitboard), s.stream));
     cudaEvent_t e0, e1;
     NSB_CUDA(cudaEventCreate(&e0));
     NSB_CUDA(cudaEventCreate(&e1));
@@ -512,7 +521,7 @@ int nsb_eval_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, s
     }
     if (n == 0) return 0;
     Slot& s = c->slots[slot];
-    if (c->direct_io && host_mapped(features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard)) &&
+    if (c->direct_io && host_mapped(features, n * (size_t)c->desc.in_channels * sizeof(nsb_feature_bitboard)) &&
         dense_outputs_mapped(n, policy, win, draw)) {
         EvalArgs a{};
         a.features = features;
@@ -522,7 +531,7 @@ int nsb_eval_async(nsb_ctx* c, int slot, const nsb_feature_bitboard* features, s
         a.draw = draw;
         return run_trunk(c, s, a);
     }
-    NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard),
+    NSB_CUDA(cudaMemcpyAsync(s.d_feat, features, n * (size_t)c->desc.in_channels * sizeof(nsb_feature_bitboard),
                              cudaMemcpyHostToDevice, s.stream));  // trt.cc:240-242
     EvalArgs a{};
     a.features = s.d_feat;
@@ -600,6 +609,7 @@ int nsb_eval_positions_async(nsb_ctx* c, int slot, const nsb_position* positions
         set_error("nsb_eval_positions_async: null buffer");
         return NSB_ERR_INVALID;
     }
+    if ((rc = check_positions_net(c, "nsb_eval_positions_async"))) return rc;
     if (n == 0) return 0;
     Slot& s = c->slots[slot];
     if (c->direct_io && c->fuse_pack && host_mapped(positions, n * sizeof(nsb_position)) &&
@@ -973,6 +983,7 @@ static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const
         set_error("%s: null buffer or bad mode", who);
         return NSB_ERR_INVALID;
     }
+    if (r.positions && (rc = check_positions_net(c, who))) return rc;
     if (n == 0) return 0;
     if ((rc = check_offsets(r.move_off, n, who))) return rc;
     const size_t total = r.move_off[n];
@@ -980,7 +991,7 @@ static int eval_request(nsb_ctx* c, int slot, const nsb_decode_request& r, const
     const uint8_t* row_flags = both ? r.row_flags : nullptr;  // the other modes have no per-row variants
     float* logits_out = both ? r.logits_out : nullptr;
     Slot& s = c->slots[slot];
-    const size_t in_bytes = r.features ? n * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard) : n * sizeof(nsb_position);
+    const size_t in_bytes = r.features ? n * (size_t)c->desc.in_channels * sizeof(nsb_feature_bitboard) : n * sizeof(nsb_position);
     const void* in = r.features ? (const void*)r.features : (const void*)r.positions;
 
     EvalArgs a{};
@@ -1219,10 +1230,47 @@ int nsb_host_alloc(void** out, size_t bytes) {
     g_host_allocs[(uintptr_t)*out] = HostRange{bytes ? bytes : 1, true, HostKind::Alloc};
     return 0;
 }
+int nsb_host_alloc_near(void** out, size_t bytes, int gpu) {
+    if (!out) return NSB_ERR_INVALID;
+    int node = -1;
+    void* p = alloc_near_gpu(bytes ? bytes : 1, gpu, &node);
+    if (!p) {
+        set_error("nsb_host_alloc_near: mmap of %zu bytes failed", bytes);
+        return NSB_ERR_NOMEM;
+    }
+    const cudaError_t e = cudaHostRegister(p, bytes ? bytes : 1, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        free_near_gpu(p, bytes ? bytes : 1);
+        set_error("nsb_host_alloc_near: cudaHostRegister failed: %s", cudaGetErrorString(e));
+        return NSB_ERR_CUDA;
+    }
+    void* dp = nullptr;
+    const bool direct = cudaHostGetDevicePointer(&dp, p, 0) == cudaSuccess && dp == p;
+    if (!direct) cudaGetLastError();
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    g_host_allocs[(uintptr_t)p] = HostRange{bytes ? bytes : 1, direct, HostKind::NodeAlloc};
+    *out = p;
+    return 0;
+}
+int nsb_gpu_numa_node(int gpu) { return gpu_numa_node(gpu); }
+int nsb_numa_bind_thread(int gpu) { return numa_bind_thread_to_gpu(gpu); }
 int nsb_host_free(void* p) {
+    HostRange r{};
+    bool known = false;
     {
         std::lock_guard<std::mutex> lock(g_host_mu);
-        g_host_allocs.erase((uintptr_t)p);
+        auto it = g_host_allocs.find((uintptr_t)p);
+        if (it != g_host_allocs.end()) {
+            r = it->second;
+            known = true;
+            g_host_allocs.erase(it);
+        }
+    }
+    if (known && r.kind == HostKind::NodeAlloc) {
+        NSB_CUDA(cudaHostUnregister(p));
+        free_near_gpu(p, r.bytes);
+        return 0;
     }
     NSB_CUDA(cudaFreeHost(p));
     return 0;
@@ -1279,7 +1327,7 @@ int nsb_host_unregister(void* p) {
     {
         std::lock_guard<std::mutex> lock(g_host_mu);
         auto it = g_host_allocs.find((uintptr_t)p);
-        if (it != g_host_allocs.end() && it->second.kind != HostKind::Alloc) {  // nsb_host_alloc memory goes with nsb_host_free
+        if (it != g_host_allocs.end() && it->second.kind != HostKind::Alloc && it->second.kind != HostKind::NodeAlloc) {  // nsb_host_alloc* memory goes with nsb_host_free
             ours = it->second.kind == HostKind::Registered;
             g_host_allocs.erase(it);
         }

@@ -11,7 +11,21 @@ namespace nsb {
 constexpr int kSquares = NSB_NUM_SQUARES;       // 81
 constexpr int kPolicyPlanes = NSB_POLICY_PLANES; // 27
 constexpr int kPolicySize = NSB_POLICY_SIZE;    // 2187
-constexpr int kStemCin = 128;                   // stem input channels padded 86 -> 128
+constexpr int kStemCin = 128;                   // stem input channels of the weight tiles (two K blocks of 64)
+constexpr int kMaxInChannels = 96;              // feature channels a net may take (86 SimpleFeatures, 93 CustomFeaturesV1)
+// Feature planes from this channel on carry arbitrary fp32 fill values (Progress, ProgressUnit, draw values, scores:
+// reference src/evaluate/preset.h:61-66,112-121); the planes before it are 0/1 by construction (pieces, hands, colour).
+// The stem sees each such plane twice: its value rounded to bf16, and - in a TWIN channel appended behind the real ones,
+// with the same weights - the bf16 rounding of what that rounding lost, so these inputs reach the fp32 accumulator with
+// ~16 mantissa bits instead of 8 (the reference feeds fp32 planes, src/infer/trt.cc:144-150).
+constexpr int kFirstScalarChannel = 82;
+__host__ __device__ constexpr int stem_twins(int in_channels) { return in_channels > kFirstScalarChannel ? in_channels - kFirstScalarChannel : 0; }
+// K = 16 steps of the stem per tap: 6 (96 channels: 86 + 4 twins) or 8 (128 channels: 93 + 11 twins)
+__host__ __device__ constexpr int stem_steps(int in_channels) { return in_channels + stem_twins(in_channels) <= 96 ? 6 : 8; }
+// blob channel that stem input channel ci multiplies (-1: padding)
+__host__ __device__ constexpr int stem_source_channel(int ci, int in_channels) {
+    return ci < in_channels ? ci : (ci < in_channels + stem_twins(in_channels) ? kFirstScalarChannel + (ci - in_channels) : -1);
+}
 constexpr int kStageBytes = 16384;              // one weight tile: 128 Cout x 64 Cin bf16
 constexpr int kMaxHidden = 256;
 
@@ -38,7 +52,7 @@ struct TrunkGeom {
     static constexpr int OFF_RING = OFF_BUF_B + BUF_BYTES;
     static constexpr int OFF_SCRATCH = OFF_RING + NSTAGES * kStageBytes;
     static constexpr int OFF_FEAT = OFF_SCRATCH + ((SCRATCH_FLOATS * 4 + 15) / 16) * 16;
-    static constexpr int OFF_VBUF = OFF_FEAT + NPOS * NSB_FEATURE_CHANNELS * 16;
+    static constexpr int OFF_VBUF = OFF_FEAT + NPOS * kMaxInChannels * 16;
     static constexpr int OFF_RED = OFF_VBUF + ((NPOS * 81 * 4 + 15) / 16) * 16;
     static constexpr int OFF_BARS = OFF_RED + ((8 * NPOS * 2 * 4 + NPOS * 2 * 4 + 15) / 16) * 16;
     static constexpr int SMEM_BYTES = OFF_BARS + (2 * NSTAGES + 2) * 8 + 16 + 128; // + align slack
@@ -73,7 +87,7 @@ struct PairGeom {
     static constexpr int OFF_XBUF = OFF_BUF_B + BUF_BYTES;  // also the logits scratch of the tail
     static constexpr int OFF_RING = OFF_XBUF + XBUF_BYTES;
     static constexpr int OFF_FEAT = OFF_RING + NSTAGES * kStageBytes;
-    static constexpr int OFF_VBUF = OFF_FEAT + NSB_FEATURE_CHANNELS * 16;
+    static constexpr int OFF_VBUF = OFF_FEAT + kMaxInChannels * 16;
     static constexpr int OFF_RED = OFF_VBUF + ((81 * 4 + 15) / 16) * 16;
     static constexpr int OFF_BARS = OFF_RED + ((8 * 2 * 4 + 2 * 4 + 15) / 16) * 16;
     static constexpr int SMEM_BYTES = OFF_BARS + NBARS * 8 + 16 + 128;
@@ -85,7 +99,8 @@ struct PairGeom {
 struct DeviceNet {
     int channels;      // C
     int blocks;        // residual blocks
-    int in_channels;   // 86
+    int in_channels;   // feature channels per position (86; 93 for CustomFeaturesV1), <= kMaxInChannels
+    int stem_steps;    // K = 16 steps of the stem per tap (stem_steps(in_channels))
     int hidden;        // value MLP hidden units (<= 256)
     int num_layers;    // 1 (stem) + 2*blocks + 1 (heads)
     int stages_per_pass;   // classic stream: 16 KB tiles per pass; TS stream: 4 KB K = 16 steps per pass
@@ -178,6 +193,12 @@ int bulk_rate_probe(int gpu, int ctas, int tile_bytes, int stages, int split, do
 int umma_selftest(int gpu, int n_cols, int k_elems, int shift_rows, float* max_err, float* epi_err);
 
 void set_error(const char* fmt, ...);
+
+// numa.cc: placement of host batch buffers next to a GPU (reference src/evaluate/evaluator.cc:39-83,127-136)
+int gpu_numa_node(int gpu);
+int numa_bind_thread_to_gpu(int gpu);
+void* alloc_near_gpu(size_t bytes, int gpu, int* node_out);
+void free_near_gpu(void* p, size_t bytes);
 
 // shared device code: warp-level gather + softmax over one position's legal moves
 }  // namespace nsb

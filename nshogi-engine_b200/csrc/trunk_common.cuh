@@ -21,12 +21,12 @@ constexpr int kEpiThreads = 256;
 constexpr int kEpiWarps = kEpiThreads / 32;
 constexpr uint32_t kEpiBar = 1;  // named barrier id for the 8 epilogue warps
 
-constexpr int kStemChunks = 12;  // stem K = 96 input channels (86 real), 6 K=16 steps
 constexpr int kFcPrefetch = 27;
 
 // One FeatureBitboard (reference src/cuda/extractbit.cu:20-37) -> {w0, w1, w2, value}: bit t of
 // the 81-bit string w2:w1:w0 is the plane's value at output position t (rotation applied), and
-// `value` is the fp32 fill value rounded to bf16 bits.  Squares 0..62 live in lo bits 0..62,
+// `value` holds the fp32 fill value as two bf16: low half = the value rounded to bf16, high half = the bf16 rounding
+// of the remainder (what the twin channel of a scalar plane carries, nsb_internal.h kFirstScalarChannel).  Squares 0..62 live in lo bits 0..62,
 // squares 63..80 in hi bits 0..17; every other bit of the input is ignored.
 __device__ __forceinline__ uint4 plane_bits(uint4 f) {
     uint32_t s0 = f.x;
@@ -38,7 +38,11 @@ __device__ __forceinline__ uint4 plane_bits(uint4 f) {
         s1 = __funnelshift_r(r1, r2, 15);
         s2 = r2 >> 15;
     }
-    return make_uint4(s0, s1, s2, (uint32_t)f32_to_bf16_bits(__uint_as_float(f.w)));
+    const float v = __uint_as_float(f.w);
+    const uint32_t hi = (uint32_t)f32_to_bf16_bits(v);
+    const float rest = v - __uint_as_float(hi << 16);  // exact in fp32; 0 for inf / nan inputs' sake below
+    const uint32_t lo = (rest == rest && (hi & 0x7F80u) != 0x7F80u) ? (uint32_t)f32_to_bf16_bits(rest) : 0u;
+    return make_uint4(s0, s1, s2, hi | (lo << 16));
 }
 
 // Diagnostics (tools/timeline.py, tools/residency.py): the clock64 stamps exist only in the diagnostic build of the
@@ -66,8 +70,9 @@ __device__ __forceinline__ int eval_index(const EvalArgs& a, int li, int n_eff) 
 // chunk 0 minus the guard, i.e. the buffer base).  `tl` (optional) receives clock64 stamps.
 // NT = number of threads doing the expansion (the kEpiBar named barrier is used with NT threads).
 template <int NPOS, int SPITCH, int GUARD, int NT = kEpiThreads>
-__device__ __forceinline__ void expand_features(const EvalArgs& a, int n_eff, int li0, uint4* featS, uint8_t* stem_buf,
-                                                int et, unsigned long long* tl) {
+__device__ __forceinline__ void expand_features(const DeviceNet& net, const EvalArgs& a, int n_eff, int li0, uint4* featS,
+                                                uint8_t* stem_buf, int et, unsigned long long* tl) {
+    const int IN = net.in_channels, stem_chunks = 2 * net.stem_steps;
     // Per plane: the 81 occupancy bits as one contiguous little-endian bit string with the
     // rotation (extractbit.cu:20,26) already applied, plus the fill value as bf16 bits.
     if (a.positions != nullptr) {
@@ -76,32 +81,33 @@ __device__ __forceinline__ void expand_features(const EvalArgs& a, int n_eff, in
         // first 28 featS slots (pack_device.cuh).
         const int pos = et >> 5, lane = et & 31;
         if (pos < NPOS) {
-            uint4* mine = featS + pos * NSB_FEATURE_CHANNELS;
+            uint4* mine = featS + pos * IN;  // (positions in: IN == 86, checked by the API)
             const int b = eval_index(a, li0 + pos, n_eff);
             if (b >= 0) {
                 pack_position_warp(a.positions + b, lane, mine, [&](int c, uint4 f) { mine[c] = plane_bits(f); });
             } else {
-                for (int c = lane; c < NSB_FEATURE_CHANNELS; c += 32) mine[c] = make_uint4(0, 0, 0, 0);
+                for (int c = lane; c < IN; c += 32) mine[c] = make_uint4(0, 0, 0, 0);
             }
         }
     } else {
-        for (int i = et; i < NPOS * NSB_FEATURE_CHANNELS; i += NT) {
-            const int pos = i / NSB_FEATURE_CHANNELS, c = i - pos * NSB_FEATURE_CHANNELS;
+        for (int i = et; i < NPOS * IN; i += NT) {
+            const int pos = i / IN, c = i - pos * IN;
             const int b = eval_index(a, li0 + pos, n_eff);
             uint4 f = make_uint4(0, 0, 0, 0);
-            if (b >= 0) f = __ldg(reinterpret_cast<const uint4*>(a.features) + (size_t)b * NSB_FEATURE_CHANNELS + c);
+            if (b >= 0) f = __ldg(reinterpret_cast<const uint4*>(a.features) + (size_t)b * IN + c);
             featS[i] = plane_bits(f);
         }
     }
     if (tl) tl[9] = clock64();
     named_bar_sync(kEpiBar, NT);
     if (tl) tl[3] = clock64();
-    // The stem reads 96 input channels = 12 chunks of 8 (86 real + zero padding).  One work
+    // The stem reads stem_chunks chunks of 8 input channels: the real ones, the twins of the scalar planes, zero padding
+    // (86 + 4 -> 96 channels = 12 chunks; 93 + 11 -> 128 = 16 chunks).  One work
     // item = (position, chunk, board row): the 8 planes' bit strings are loaded once, the
     // row's 9-bit field is cut out with a funnel shift, and 9 records of 16 B are written.
-    for (int item = et; item < NPOS * kStemChunks * 9; item += NT) {
-        const int pos = item / (kStemChunks * 9);
-        const int r2 = item - pos * (kStemChunks * 9);
+    for (int item = et; item < NPOS * stem_chunks * 9; item += NT) {
+        const int pos = item / (stem_chunks * 9);
+        const int r2 = item - pos * (stem_chunks * 9);
         const int j = r2 / 9, row = r2 - j * 9;
         const int bit0 = 9 * row, wi = bit0 >> 5, sh = bit0 & 31;
         uint32_t field[8], val[8];
@@ -109,11 +115,12 @@ __device__ __forceinline__ void expand_features(const EvalArgs& a, int n_eff, in
         for (int e = 0; e < 8; ++e) {
             const int c = j * 8 + e;
             uint4 f = make_uint4(0, 0, 0, 0);
-            if (c < NSB_FEATURE_CHANNELS) f = featS[pos * NSB_FEATURE_CHANNELS + c];
+            const int src = stem_source_channel(c, IN);
+            if (src >= 0) f = featS[pos * IN + src];
             const uint32_t lo = wi == 0 ? f.x : (wi == 1 ? f.y : f.z);
             const uint32_t hi = wi == 0 ? f.y : (wi == 1 ? f.z : 0u);
             field[e] = __funnelshift_r(lo, hi, sh);
-            val[e] = f.w;
+            val[e] = c < IN ? (f.w & 0xFFFFu) : (f.w >> 16);  // a twin channel carries the remainder
         }
         uint8_t* dst = stem_buf + (size_t)((j * SPITCH + GUARD + pos * 100 + row * 10) * 16);
 #pragma unroll

@@ -43,7 +43,7 @@ struct DuoGeom {
     static constexpr int EPI_WARPS = EPI_THREADS / 32;
     static constexpr int NBARS = 2 * A_STAGES + 2;  // a_full[], a_empty[], act, acc
     static constexpr int SCRATCH_BYTES = ((NPOS * kPolicySize * 4 + 15) / 16) * 16;
-    static constexpr int FEAT_BYTES = NPOS * NSB_FEATURE_CHANNELS * 16;
+    static constexpr int FEAT_BYTES = NPOS * kMaxInChannels * 16;
     // dynamic shared memory map.  The feature staging (prologue) and the logits scratch (tail) alias
     // the front of activation buffer A, which is dead in both phases.
     static constexpr int OFF_BUF_A = 0;
@@ -60,7 +60,7 @@ struct DuoGeom {
 };
 
 // K = 16 steps of (layer L, K block kc, any tap): the stem's second block holds channels 64..95 only
-__device__ __forceinline__ int block_steps(int L, int kc) { return (L == 0 && kc == 1) ? (kStemChunks - 8) / 2 : 4; }
+__device__ __forceinline__ int block_steps(const DeviceNet& net, int L, int kc) { return (L == 0 && kc == 1) ? net.stem_steps - 4 : 4; }
 
 // Tail of a pass with NT epilogue threads (the 256-thread version with its FC1 prefetch is
 // heads_tail in trunk_common.cuh): dense logits, value MLP, sigmoids, fused decode (+ cache store).
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
                     const uint32_t in_buf = (L & 1) ? bufA : bufB;
                     const int ntaps = head ? 1 : 9;
                     for (int kc = 0; kc < G::KC64; ++kc) {
-                        const int halves = block_steps(L, kc) / 2;  // ring stages per (K block, tap)
+                        const int halves = block_steps(net, L, kc) / 2;  // ring stages per (K block, tap)
                         for (int tap = 0; tap < ntaps; ++tap) {
                             const int shift = head ? 0 : (tap / 3 - 1) * 10 + (tap % 3 - 1);
                             const uint32_t b_base = in_buf + (uint32_t)((kc * 8 * G::SPITCH + G::GUARD + shift) * 16);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(DuoGeom::THREADS, 2) trunk_duo_kernel(const De
 
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB); the bit
             //    strings are staged in the (dead) front of buffer A, which is zeroed again afterwards
-            expand_features<G::NPOS, G::SPITCH, G::GUARD, G::EPI_THREADS>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, nullptr);
+            expand_features<G::NPOS, G::SPITCH, G::GUARD, G::EPI_THREADS>(net, a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, nullptr);
             named_bar_sync(kEpiBar, G::EPI_THREADS);
             for (int i = et; i < G::FEAT_BYTES / 16; i += G::EPI_THREADS) featS[i] = make_uint4(0, 0, 0, 0);
             fence_proxy_async_smem();

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
                         for (int half = 0; half < nh; ++half) {
                             mbar_wait(bar_full(stage), phase);
                             tc_fence_after();
-                            const int ksteps = (L == 0 && kc == 1) ? (kStemChunks - 8) / 2 : 4;
+                            const int ksteps = (L == 0 && kc == 1) ? net.stem_steps - 4 : 4;
                             if (elect_one()) {
                                 const uint32_t a_lo = smem_desc_lo(ring + stage * kStageBytes, 2048);
                                 const uint32_t b_lo = smem_desc_lo(b_base, b_lbo);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_fused_kernel(const DeviceNe
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
             if (eval_timeline(a) && blockIdx.x == 0 && p == 0 && et == 0) eval_timeline(a)[4 * NL + 8] = clock64();
             unsigned long long* tl = (eval_timeline(a) && blockIdx.x == 0 && p == 0 && et == 0) ? eval_timeline(a) + 4 * NL : nullptr;
-            expand_features<G::NPOS, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
+            expand_features<G::NPOS, G::SPITCH, G::GUARD>(net, a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_act);

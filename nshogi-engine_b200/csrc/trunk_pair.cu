@@ -137,7 +137,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
                         const uint32_t b_base = in_buf + (uint32_t)((kc * 8 * G::SPITCH + G::GUARD + shift) * 16);
                         mbar_wait(bar_full(stage), phase);
                         tc_fence_after();
-                        const int ksteps = (L == 0 && kc == 1) ? (kStemChunks - 8) / 2 : 4;
+                        const int ksteps = (L == 0 && kc == 1) ? net.stem_steps - 4 : 4;
                         if (elect_one()) {
                             const uint32_t a_lo = smem_desc_lo(ring + stage * kStageBytes, 2048);
                             const uint32_t b_lo = smem_desc_lo(b_base, b_lbo);
@@ -218,7 +218,7 @@ trunk_pair_kernel(const DeviceNet net, const EvalArgs a) {
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
             unsigned long long* tl = (stamp && p == 0 && et == 0) ? eval_timeline(a) + 4 * NL : nullptr;
             if (tl) tl[8] = clock64();
-            expand_features<1, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
+            expand_features<1, G::SPITCH, G::GUARD>(net, a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_act);

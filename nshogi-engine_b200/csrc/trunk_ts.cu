@@ -53,7 +53,7 @@ struct TsGeom {
     static constexpr int OFF_BUF_B = OFF_BUF_A + BUF_BYTES;
     static constexpr int OFF_SCRATCH = OFF_BUF_B + BUF_BYTES;
     static constexpr int OFF_FEAT = OFF_SCRATCH + SCRATCH_BYTES;
-    static constexpr int OFF_VBUF = OFF_FEAT + NPOS * NSB_FEATURE_CHANNELS * 16;
+    static constexpr int OFF_VBUF = OFF_FEAT + NPOS * kMaxInChannels * 16;
     static constexpr int OFF_RED = OFF_VBUF + ((NPOS * 81 * 4 + 15) / 16) * 16;
     static constexpr int OFF_BARS = OFF_RED + ((8 * NPOS * 2 * 4 + NPOS * 2 * 4 + 15) / 16) * 16;
     static constexpr int SMEM_BYTES = OFF_BARS + NBARS * 8 + 16 + 128;
@@ -62,7 +62,7 @@ struct TsGeom {
 
 // K = 16 steps of weight-stream stage (layer L, K block kc, any tap): the stem's second block holds
 // input channels 64..95 only
-__device__ __forceinline__ int stage_steps(int L, int kc) { return (L == 0 && kc == 1) ? (kStemChunks - 8) / 2 : 4; }
+__device__ __forceinline__ int stage_steps(const DeviceNet& net, int L, int kc) { return (L == 0 && kc == 1) ? net.stem_steps - 4 : 4; }
 
 __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const DeviceNet net, const EvalArgs a) {
     using G = TsGeom;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
             const uint4* src;
         };
         auto advance = [&](Cursor& c) {
-            c.src += (size_t)stage_steps(c.L, c.kc) * 256;
+            c.src += (size_t)stage_steps(net, c.L, c.kc) * 256;
             const int ntaps = (c.L == NL - 1) ? 1 : 9;
             if (++c.tap == ntaps) {
                 c.tap = 0;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
             }
         };
         auto load_stage = [&](uint4 (&dst)[8], const Cursor& c) {
-            const int nk = stage_steps(c.L, c.kc);
+            const int nk = stage_steps(net, c.L, c.kc);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (k < nk) {
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
         auto store_stage = [&](const uint4 (&buf)[8], const Cursor& c) {
             mbar_wait(bar_aempty(slot), phase ^ 1u);
             tc_fence_after();
-            if (stage_steps(c.L, c.kc) == 4) tmem_st_32x32b_x32(lane_addr + slot * G::A_STAGE_COLS, buf);
+            if (stage_steps(net, c.L, c.kc) == 4) tmem_st_32x32b_x32(lane_addr + slot * G::A_STAGE_COLS, buf);
             else tmem_st_32x32b_x16(lane_addr + slot * G::A_STAGE_COLS, buf);
             tmem_st_wait();
             tc_fence_before();
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
                         mbar_wait(bar_kb(kc), kb_phase);
                         tc_fence_after();
                         if (stamp && p == 0 && lane == 0 && kc == 0) eval_timeline(a)[4 * L + 0] = clock64();
-                        const int nk = stage_steps(L, kc);
+                        const int nk = stage_steps(net, L, kc);
                         for (int tap = 0; tap < ntaps; ++tap) {
                             const int shift = head ? 0 : (tap / 3 - 1) * 10 + (tap % 3 - 1);
                             const uint32_t b_base = in_buf + (uint32_t)((kc * 8 * G::SPITCH + G::GUARD + shift) * 16);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(TsGeom::THREADS, 1) trunk_ts_kernel(const Devi
             // -- stage 2 of feature extraction, straight into the stem's B operand (bufB) --------
             unsigned long long* tl = (stamp && p == 0 && et == 0) ? eval_timeline(a) + 4 * NL : nullptr;
             if (tl) tl[8] = clock64();
-            expand_features<G::NPOS, G::SPITCH, G::GUARD>(a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
+            expand_features<G::NPOS, G::SPITCH, G::GUARD>(net, a, n_eff, b0, featS, smem + G::OFF_BUF_B, et, tl);
             fence_proxy_async_smem();
             named_bar_sync(kEpiBar, kEpiThreads);  // the stem input has no block structure: both fire together
             if (lane == 0) {

@@ -95,7 +95,7 @@ void pack_weights(const nsb_net_desc& d, const float* blob, uint16_t* tiles, flo
     const float* w = blob;
     uint16_t* t = tiles;
     int layer = 0;
-    auto pack_conv = [&](const float* cw, int cin_real, int cin_pad) {
+    auto pack_conv = [&](const float* cw, int cin_real, int cin_pad, bool stem = false) {
         for (int tap = 0; tap < 9; ++tap)
             for (int kc = 0; kc < cin_pad / 64; ++kc)
                 for (int half = 0; half < nhalf; ++half) {
@@ -103,14 +103,15 @@ void pack_weights(const nsb_net_desc& d, const float* blob, uint16_t* tiles, flo
                         for (int row = 0; row < 128; ++row)
                             for (int e = 0; e < 8; ++e) {
                                 const int co = half * 128 + row, ci = kc * 64 + j * 8 + e;
-                                const float v =
-                                    ci < cin_real ? cw[((size_t)co * cin_real + ci) * 9 + tap] : 0.f;
+                                // the stem: twin channels repeat the weights of the scalar planes (nsb_internal.h)
+                                const int src = stem ? stem_source_channel(ci, cin_real) : (ci < cin_real ? ci : -1);
+                                const float v = src >= 0 ? cw[((size_t)co * cin_real + src) * 9 + tap] : 0.f;
                                 t[tile_index(j, row, e)] = bf16_bits_rne(v);
                             }
                     t += tile_elems;
                 }
     };
-    pack_conv(w, IN, kStemCin);
+    pack_conv(w, IN, kStemCin, true);
     w += (size_t)C * IN * 9;
     std::memcpy(bias + (size_t)layer * C, w, sizeof(float) * C);
     w += C;
@@ -167,7 +168,7 @@ void pack_weights(const nsb_net_desc& d, const float* blob, uint16_t* tiles, flo
 // layer keeps its own row assignment (head channel h in row 32*(h/7) + h%7).
 int ts_steps_per_pass(const nsb_net_desc& d) {
     const int kc64 = d.channels / 64;
-    return 9 * 6 + 2 * d.blocks * 9 * kc64 * 4 + kc64 * 4;  // stem: 96 input channels = 6 steps per tap
+    return 9 * stem_steps(d.in_channels) + 2 * d.blocks * 9 * kc64 * 4 + kc64 * 4;  // stem: 6 or 8 steps per tap
 }
 
 void pack_weights_ts(const nsb_net_desc& d, const float* blob, uint16_t* stream) {
@@ -176,20 +177,21 @@ void pack_weights_ts(const nsb_net_desc& d, const float* blob, uint16_t* stream)
     const float* w = blob;
     uint16_t* t = stream;
     auto row_channel = [](int row) { return 64 * ((row >> 4) & 1) + 16 * (row >> 5) + (row & 15); };
-    auto pack_conv = [&](const float* cw, int cin_real, int kblocks, int last_block_steps) {
+    auto pack_conv = [&](const float* cw, int cin_real, int kblocks, int last_block_steps, bool stem = false) {
         for (int kc = 0; kc < kblocks; ++kc)
             for (int tap = 0; tap < 9; ++tap)
                 for (int k = 0; k < (kc + 1 == kblocks ? last_block_steps : 4); ++k) {
                     for (int row = 0; row < 128; ++row)
                         for (int e = 0; e < 16; ++e) {
                             const int co = row_channel(row), ci = kc * 64 + k * 16 + e;
-                            const float v = ci < cin_real ? cw[((size_t)co * cin_real + ci) * 9 + tap] : 0.f;
+                            const int src = stem ? stem_source_channel(ci, cin_real) : (ci < cin_real ? ci : -1);
+                            const float v = src >= 0 ? cw[((size_t)co * cin_real + src) * 9 + tap] : 0.f;
                             t[row * 16 + e] = bf16_bits_rne(v);
                         }
                     t += 128 * 16;
                 }
     };
-    pack_conv(w, IN, 2, 2);  // stem: channels 0..63, then 64..95 (86 real)
+    pack_conv(w, IN, 2, stem_steps(IN) - 4, true);  // stem: channels 0..63, then 64..95 (86 + 4 twins) or 64..127 (93 + 11)
     w += (size_t)C * IN * 9 + C;
     for (int b = 0; b < 2 * NB; ++b) {
         pack_conv(w, C, kc64, 4);

@@ -35,8 +35,10 @@ class B200 : public Infer {
          int Slots = 1)
         : BatchSizeM(BatchSizeMax), GPUId_(GPUId), Slots_(Slots) {
         static_assert(sizeof(ml::FeatureBitboard) == sizeof(nsb_feature_bitboard), "FeatureBitboard is 16 bytes");
-        if (NumChannels != NSB_FEATURE_CHANNELS) throw std::runtime_error("B200: NumChannels must be 86");
-        Desc_ = nsb_net_desc{NSB_FEATURE_CHANNELS, NetChannels, NetBlocks, 256};
+        // 86 = preset::SimpleFeatures (globalconfig.h:19), 93 = preset::CustomFeaturesV1 (preset.h:68-122); any count the
+        // stem can take is accepted, the feature set is the caller's (FeatureBitboards in, Infer contract)
+        if (NumChannels < 1 || NumChannels > 96) throw std::runtime_error("B200: NumChannels must be in 1..96");
+        Desc_ = nsb_net_desc{NumChannels, NetChannels, NetBlocks, 256};
         check(nsb_create(&Ctx_, GPUId, BatchSizeMax, Slots, &Desc_), "nsb_create");
     }
     ~B200() override {
@@ -128,7 +130,7 @@ class B200 : public Infer {
             Seen_[2] = DstWinRate;
             Seen_[3] = DstDrawRate;
             const std::size_t B = BatchSizeM;
-            const std::size_t Bytes[4] = {B * NSB_FEATURE_CHANNELS * sizeof(nsb_feature_bitboard), B * NSB_POLICY_SIZE * sizeof(float),
+            const std::size_t Bytes[4] = {B * (std::size_t)Desc_.in_channels * sizeof(nsb_feature_bitboard), B * NSB_POLICY_SIZE * sizeof(float),
                                           B * sizeof(float), B * sizeof(float)};
             // Every range the library now knows - locked by this call OR adopted from the caller's Evaluator - is
             // remembered and forgotten again in ~B200 (nsb_host_unregister unlocks only what the library locked and
@@ -152,6 +154,15 @@ class B200 : public Infer {
         const int R = nsb_is_computing(Ctx_, 0);
         if (R < 0) check(R, "nsb_is_computing");
         return R == 1;
+    }
+
+    // Pin the calling (evaluator) thread to the CPUs of this GPU's NUMA node: the affinity half of the reference's
+    // NUMA_ENABLED Evaluator (src/evaluate/evaluator.cc:39-83); LeafPipeline places its pinned slots on that node.
+    bool bindThreadToGpuNode() {
+        return nsb_numa_bind_thread(GPUId_) == 0;
+    }
+    int gpu() const {
+        return GPUId_;
     }
 
     nsb_ctx* context() {

@@ -141,7 +141,8 @@ class LeafPipeline {
     template <typename T>
     void alloc(T*& P, std::size_t N) {
         void* Raw = nullptr;
-        infer::B200::check(nsb_host_alloc(&Raw, N * sizeof(T)), "nsb_host_alloc");  // evaluator.cc:95-106
+        // page-locked (evaluator.cc:95-106) on the GPU's own NUMA node (evaluator.cc:127-136 numa_alloc_onnode)
+        infer::B200::check(nsb_host_alloc_near(&Raw, N * sizeof(T), Ex->gpu()), "nsb_host_alloc_near");
         Pinned.push_back(Raw);
         P = static_cast<T*>(Raw);
     }

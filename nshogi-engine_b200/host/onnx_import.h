@@ -249,8 +249,14 @@ inline Tensor parseTensor(Span S) {
         break;
     default: throw Error("onnx: tensor '" + T.Name + "': unsupported data type " + std::to_string(DType));
     }
+    // an initializer of this model family has small positive dims (a scalar: none); anything else - zero, negative, or a
+    // product that would wrap - is a damaged file, not a shape to reinterpret
     std::size_t Count = 1;
-    for (int64_t D : T.Dims) Count *= (std::size_t)D;
+    for (int64_t D : T.Dims) {
+        if (D <= 0 || D > (int64_t(1) << 24) || Count > (std::size_t(1) << 40) / (std::size_t)D)
+            throw Error("onnx: tensor '" + T.Name + "': dimension " + std::to_string(D) + " out of range");
+        Count *= (std::size_t)D;
+    }
     if (T.Data.size() != Count) throw Error("onnx: tensor '" + T.Name + "': value count does not match its shape");
     return T;
 }

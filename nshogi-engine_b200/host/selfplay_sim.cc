@@ -243,6 +243,7 @@ void searchWorker(const Options& O, FrameQueue* SearchQueue, FrameQueue* Evaluat
 void evaluationWorker(const Options& O, infer::B200* Exec, FrameQueue* EvaluationQueue, FrameQueue* SearchQueue,
                       Info* SI, std::atomic<bool>* Running) {
     Exec->resetGPU();
+    Exec->bindThreadToGpuNode();  // evaluator.cc:39-83
     evaluate::LeafPipeline Pipe(Exec, (std::size_t)O.Batch);
     const std::size_t NS = Pipe.numSlots();
     std::vector<std::vector<Frame*>> SlotTasks(NS);

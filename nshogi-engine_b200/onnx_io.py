@@ -180,7 +180,9 @@ def _parse_tensor(buf: bytes) -> Tuple[str, np.ndarray]:
         arr = np.asarray(i32, dtype=dt)
     else:  # float16 bits travel in int32_data
         arr = np.asarray(i32, dtype="<u2").view("<f2")
-    n = int(np.prod(dims)) if dims else 1
+    if any(d <= 0 or d > (1 << 24) for d in dims):
+        raise ValueError(f"tensor {name!r}: dimension out of range in shape {dims}")
+    n = int(np.prod(dims, dtype=object)) if dims else 1
     if arr.size != n:
         raise ValueError(f"tensor {name!r}: {arr.size} values for shape {dims}")
     return name, arr.reshape(dims)

@@ -281,12 +281,23 @@ static void pad_planes(const float* in /* [c][81] */, int c, float* in_pad) {
                 in_pad[(size_t)ch * PSZ + (h + 1) * PW + (x + 1)] = in[ch * 81 + h * 9 + x];
 }
 
+/* What the device does to its INPUT in bf16 mode (csrc/nsb_internal.h kFirstScalarChannel): the planes before channel
+ * 82 are 0/1 and exact in bf16; every plane from 82 on (Progress, ProgressUnit, draw values, scores - arbitrary fp32
+ * fill values) enters the stem twice: rounded to bf16, and - in a TWIN channel appended behind the real ones, with the
+ * same (bf16-exact) weights - as the bf16 rounding of the remainder.  The restatement does exactly that: `stem_w_ext`
+ * is the stem weight tensor [C][IN + T][3][3] with the twins' weights repeated. */
+#define ORACLE_FIRST_SCALAR_CHANNEL 82
+static int stem_twins(int in_channels) {
+    return in_channels > ORACLE_FIRST_SCALAR_CHANNEL ? in_channels - ORACLE_FIRST_SCALAR_CHANNEL : 0;
+}
+
 typedef struct {
     const nsb_net_desc* net;
     const float *blob, *planes;
     size_t n;
     int emulate_bf16, tid, nthreads;
     float *policy, *win, *draw;
+    const float* stem_w_ext; /* bf16 mode with twins only, else NULL */
 } fwd_job;
 
 static void* forward_worker(void* arg) {
@@ -296,7 +307,8 @@ static void* forward_worker(void* arg) {
     const int emulate_bf16 = J->emulate_bf16;
     float *policy = J->policy, *win = J->win, *draw = J->draw;
     const int IN = net->in_channels, C = net->channels, NB = net->blocks, H = net->value_hidden;
-    const int maxc = C > IN ? C : IN;
+    const int T = J->stem_w_ext ? stem_twins(IN) : 0, IN_EXT = IN + T;
+    const int maxc = C > IN_EXT ? C : IN_EXT;
     for (size_t b = (size_t)J->tid; b < J->n; b += (size_t)J->nthreads) {
         float* x = (float*)malloc(sizeof(float) * (size_t)maxc * 81);
         float* t = (float*)malloc(sizeof(float) * (size_t)maxc * 81);
@@ -307,9 +319,15 @@ static void* forward_worker(void* arg) {
             const float v = planes[(size_t)b * IN * 81 + i];
             x[i] = emulate_bf16 ? nsb_oracle_bf16_round(v) : v;
         }
+        for (int k = 0; k < T; ++k) /* twin of channel 82 + k: bf16 of what the rounding above lost */
+            for (int i = 0; i < 81; ++i) {
+                const int src = (ORACLE_FIRST_SCALAR_CHANNEL + k) * 81 + i;
+                const float v = planes[(size_t)b * IN * 81 + src];
+                x[(IN + k) * 81 + i] = isfinite(v) ? nsb_oracle_bf16_round(v - x[src]) : 0.0f;
+            }
         /* stem */
-        pad_planes(x, IN, pad);
-        conv3x3(pad, IN, w, w + (size_t)C * IN * 9, C, t);
+        pad_planes(x, IN_EXT, pad);
+        conv3x3(pad, IN_EXT, T ? J->stem_w_ext : w, w + (size_t)C * IN * 9, C, t);
         w += (size_t)C * IN * 9 + C;
         for (int i = 0; i < C * 81; ++i) {
             float v = t[i] > 0.f ? t[i] : 0.f;
@@ -384,11 +402,22 @@ void nsb_oracle_forward(const nsb_net_desc* net, const float* blob, const float*
     if ((size_t)nt > n) nt = (long)(n ? n : 1);
     pthread_t th[64];
     fwd_job jobs[64];
+    float* stem_ext = NULL;
+    const int IN = net->in_channels, C = net->channels, T = stem_twins(IN);
+    if (emulate_bf16 && T > 0) {
+        stem_ext = (float*)malloc(sizeof(float) * (size_t)C * (IN + T) * 9);
+        for (int co = 0; co < C; ++co)
+            for (int ci = 0; ci < IN + T; ++ci) {
+                const int src = ci < IN ? ci : ORACLE_FIRST_SCALAR_CHANNEL + (ci - IN);
+                memcpy(stem_ext + ((size_t)co * (IN + T) + ci) * 9, blob + ((size_t)co * IN + src) * 9, 9 * sizeof(float));
+            }
+    }
     for (long t = 0; t < nt; ++t) {
-        jobs[t] = (fwd_job){net, blob, planes, n, emulate_bf16, (int)t, (int)nt, policy, win, draw};
+        jobs[t] = (fwd_job){net, blob, planes, n, emulate_bf16, (int)t, (int)nt, policy, win, draw, stem_ext};
         pthread_create(&th[t], NULL, forward_worker, &jobs[t]);
     }
     for (long t = 0; t < nt; ++t) pthread_join(th[t], NULL);
+    free(stem_ext);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -869,6 +869,48 @@ def test_selfplay_decode_in_one_launch(nb, orc, synth, monkeypatch):
             a.free()
 
 
+@pytest.mark.parametrize("channels,slots", [(128, 1), (128, 2), (256, 1)])
+def test_custom_features_v1_93_channels(nb, orc, synth, monkeypatch, channels, slots):
+    """preset::CustomFeaturesV1 (reference src/evaluate/preset.h:68-122): 93 planes, eleven of them (82..92) with
+    arbitrary fp32 fill values.  The executor takes any feature count up to 96 as bitboards (the Infer contract); the
+    stem then runs 8 K-steps per tap (93 + 11 twin channels).  Against the oracle on every trunk kernel; the fused
+    expansion equals the standalone extract kernel's planes fed to the oracle; packed positions are refused (stage 1
+    on the device builds SimpleFeatures)."""
+    monkeypatch.delenv("NSB_TRUNK128", raising=False)
+    monkeypatch.delenv("NSB_IO", raising=False)
+    IN = 93
+    desc = nb.net_desc(channels, 2, in_channels=IN)
+    blob = nb.random_blob(desc, 31)
+    n = 37
+    fb = synth.random_feature_bitboards(n * IN, seed=93)
+    # planes 0..81 are 0/1 planes in the real feature set: give them the fill value 1.0 (bits 32..63 of hi)
+    hi = fb["hi"].reshape(n, IN)
+    hi[:, :82] = (hi[:, :82] & np.uint64(0xFFFFFFFF)) | (np.uint64(0x3F800000) << np.uint64(32))
+    fb["hi"] = hi.reshape(-1)
+    off, idx = synth.random_legal_moves(n, seed=4)
+    policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+    win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    legal = np.zeros(int(off[-1]), dtype=np.float32)
+    w2, d2 = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    with nb.Context(desc, batch_max=n, slots=slots, blob=blob) as ctx:
+        ctx.eval_async(0, fb, n, policy, win, draw)
+        ctx.await_(0)
+        ctx.eval_decode_async(slots - 1, fb, n, off, idx, nb.DECODE_PROBS, legal, w2, d2, None)
+        ctx.await_(slots - 1)
+        with pytest.raises(nb.NsbError) as e:
+            ctx.eval_positions_async(0, synth.random_positions(n, seed=1), n, policy.copy(), win.copy(), draw.copy())
+        assert "SimpleFeatures" in str(e.value)
+    planes = orc.expand(fb, n, IN)
+    op, ow, od = orc.forward(desc, blob, planes, emulate_bf16=True)
+    assert np.max(np.abs(policy - op)) < TOL_LOGIT_VS_BF16_ORACLE
+    assert np.max(np.abs(win - ow)) < TOL_VALUE_VS_BF16_ORACLE and np.max(np.abs(draw - od)) < TOL_VALUE_VS_BF16_ORACLE
+    fp, fw, fd = orc.forward(desc, blob, planes, emulate_bf16=False)
+    pg, _ = orc.decode(policy, win, draw, off, idx, nb.DECODE_PROBS)
+    pf, _ = orc.decode(fp, fw, fd, off, idx, nb.DECODE_PROBS)
+    assert np.max(np.abs(pg - pf)) < TOL_PROB_VS_FP32 and np.max(np.abs(win - fw)) < TOL_VALUE_VS_FP32
+    assert np.allclose(legal, pg, rtol=1e-6, atol=1e-9) and np.array_equal(w2, win)
+
+
 def test_graft_entry_smoke():
     """The driver's smoke() entry point itself (it pins the launch count of the fused path)."""
     import __graft_entry__ as graft

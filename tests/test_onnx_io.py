@@ -210,3 +210,23 @@ def test_damaged_files_are_rejected_not_crashing(oi, golden_dir, tmp_path):
         loaded += py_ok
         rejected += not py_ok
     assert rejected >= 10
+
+
+def test_tensor_dims_are_validated(oi, tmp_path):
+    """A TensorProto whose dims are negative (or huge) must be rejected, not reinterpreted: dims [-1, -1] multiply to 1
+    and would otherwise pass the value-count check with a one-element payload."""
+    neg = b"\xff" * 9 + b"\x01"                                   # int64 -1 as a varint
+    def tensor(dims_bytes):
+        return dims_bytes + oi._vi(2, 1) + oi._st(8, "w") + oi._ld(9, np.float32(1.0).tobytes())
+    for dims in (b"\x08" + neg + b"\x08" + neg, b"\x08\x00", b"\x08" + oi._varint(1 << 30)):
+        with pytest.raises(ValueError):
+            oi._parse_tensor(tensor(dims))
+        model = oi._ld(7, oi._ld(5, tensor(dims)))                  # ModelProto.graph.initializer
+        with pytest.raises(ValueError):
+            oi.blob_from_bytes(model)
+        p = str(tmp_path / "dims.onnx")
+        open(p, "wb").write(model)
+        rc, out, _, _ = _cpp_blob(p, tmp_path)
+        assert rc == 3 and "out of range" in out, (rc, out)
+    name, arr = oi._parse_tensor(tensor(b"\x08\x01"))              # a well-formed [1] tensor still parses
+    assert name == "w" and arr.shape == (1,) and arr[0] == 1.0
