@@ -1,0 +1,389 @@
+// rules/shogi.h — a self-contained shogi rules core for the CALLERS of the leaf-evaluation path:
+// position, legal move generation, make / unmake, check / mate / repetition, Zobrist hash, hirate start position.
+//
+// In the reference all of this is libnshogi (core::State, core::MoveGenerator, core::Position; linked from outside
+// the tree): src/mcts/searchworker.cc:164-173 (expandLeaf -> generateLegalMoves), :475-538 (terminal /
+// repetition / max-ply checks), src/selfplay/worker.cc:82-110 (phases), :349-358.  The library is not available to
+// this build, so the search and self-play harnesses of this repo (host/mcts_search.h, host/selfplay_real.cc,
+// host/usi_go_bench.cc) run on this restatement of the RULES OF SHOGI instead.  What pins it: the perft counts of the
+// start position (30, 900, 25470, 719731, 19861490 - public known answers for shogi move generators) and hand-made
+// positions for every special rule (nsb_host_unit --rules).  What it does not have: libnshogi's df-pn mate solver
+// (searchworker.cc:220-240) and declaration win (27-point rule, searchworker.cc:500-520); games end by mate, by
+// four-fold repetition (draw; a perpetual check is scored as a draw too) or at max ply (draw).
+//
+// Squares, piece codes and hand order are those of nsb_position (include/nsb.h), so a position is handed to stage 1 of
+// the executor by copying the board: square s = 9 * (file - 1) + (rank - 1); board[s] = 0 or 1 + type + 14 * colour,
+// type in {P, L, N, S, G, K, B, R, +P, +L, +N, +S, +B, +R}; hands[colour][{P, L, N, S, G, B, R}].  Black (colour 0,
+// sente) moves toward rank 1.
+#ifndef NSHOGI_ENGINE_B200_RULES_SHOGI_H
+#define NSHOGI_ENGINE_B200_RULES_SHOGI_H
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../move_index.h"
+#include "nsb.h"
+
+namespace nshogi {
+namespace engine {
+namespace b200 {
+namespace rules {
+
+enum PieceType : uint8_t {
+    Pawn = 0, Lance, Knight, Silver, Gold, King, Bishop, Rook,
+    ProPawn, ProLance, ProKnight, ProSilver, ProBishop, ProRook, NumPieceTypes
+};
+constexpr int kMaxMoves = NSB_MAX_LEGAL_MOVES;  // 593
+
+// hand slot {P, L, N, S, G, B, R} of a (possibly promoted) piece type; -1 for the king
+constexpr int kHandSlot[NumPieceTypes] = {0, 1, 2, 3, 4, -1, 5, 6, 0, 1, 2, 3, 5, 6};
+constexpr PieceType kHandPiece[7] = {Pawn, Lance, Knight, Silver, Gold, Bishop, Rook};
+constexpr int kPromoted[NumPieceTypes] = {ProPawn, ProLance, ProKnight, ProSilver, -1, -1, ProBishop, ProRook, -1, -1, -1, -1, -1, -1};
+constexpr int kDemoted[NumPieceTypes] = {Pawn, Lance, Knight, Silver, Gold, King, Bishop, Rook, Pawn, Lance, Knight, Silver, Bishop, Rook};
+
+struct Move {
+    uint8_t From;     // 0..80; 81 + hand slot for a drop
+    uint8_t To;       // 0..80
+    uint8_t Promote;  // 1: the piece promotes on this move
+    uint8_t Piece;    // type of the moving piece before the move (a drop: the dropped type)
+    bool isDrop() const { return From >= 81; }
+    int dropSlot() const { return From - 81; }
+    bool operator==(const Move& O) const { return From == O.From && To == O.To && Promote == O.Promote; }
+};
+
+inline int fileOf(int S) { return S / 9; }  // 0..8 (file - 1)
+inline int rankOf(int S) { return S % 9; }  // 0..8 (rank - 1); black's camp is ranks 7..9 (6..8 here)
+inline bool onBoard(int F, int R) { return F >= 0 && F < 9 && R >= 0 && R < 9; }
+
+struct ZobristKeys {
+    uint64_t Piece[81][29];
+    uint64_t Hand[2][7][19];
+    uint64_t Side;
+    ZobristKeys() {
+        uint64_t S = 0x9E3779B97F4A7C15ull;
+        auto next = [&S]() {  // splitmix64
+            uint64_t Z = (S += 0x9E3779B97F4A7C15ull);
+            Z = (Z ^ (Z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            Z = (Z ^ (Z >> 27)) * 0x94D049BB133111EBull;
+            return Z ^ (Z >> 31);
+        };
+        for (auto& Sq : Piece)
+            for (auto& K : Sq) K = next();
+        for (auto& C : Hand)
+            for (auto& P : C)
+                for (auto& K : P) K = next();
+        Side = next();
+        for (auto& Sq : Piece) Sq[0] = 0;       // empty square
+        for (auto& C : Hand)
+            for (auto& P : C) P[0] = 0;         // nothing in hand
+    }
+};
+inline const ZobristKeys& zobrist() {
+    static const ZobristKeys K;
+    return K;
+}
+
+class Position {
+ public:
+    uint8_t Board[81];
+    uint8_t Hands[2][7];
+    uint8_t Side = 0;     // 0 = black to move
+    uint16_t Ply = 0;
+    uint8_t KingSq[2] = {0, 0};
+    uint64_t Hash = 0;
+
+    static int code(int Type, int Colour) { return 1 + Type + 14 * Colour; }
+    static int typeOf(int Code) { return (Code - 1) % 14; }
+    static int colourOf(int Code) { return (Code - 1) / 14; }
+
+    Position() { setHirate(); }
+
+    void clear() {
+        std::memset(Board, 0, sizeof Board);
+        std::memset(Hands, 0, sizeof Hands);
+        Side = 0;
+        Ply = 0;
+        KingSq[0] = KingSq[1] = 255;
+        Hash = 0;
+    }
+    void put(int File, int Rank, int Type, int Colour) {  // 1-based file / rank
+        const int S = 9 * (File - 1) + (Rank - 1);
+        Board[S] = (uint8_t)code(Type, Colour);
+        if (Type == King) KingSq[Colour] = (uint8_t)S;
+    }
+    void setHirate() {
+        clear();
+        const int Back[9] = {Lance, Knight, Silver, Gold, King, Gold, Silver, Knight, Lance};
+        for (int F = 1; F <= 9; ++F) {
+            put(F, 9, Back[F - 1], 0);
+            put(F, 1, Back[9 - F], 1);
+            put(F, 7, Pawn, 0);
+            put(F, 3, Pawn, 1);
+        }
+        put(8, 8, Bishop, 0);
+        put(2, 8, Rook, 0);
+        put(2, 2, Bishop, 1);
+        put(8, 2, Rook, 1);
+        rehash();
+    }
+    void rehash() {
+        const ZobristKeys& Z = zobrist();
+        Hash = Side ? Z.Side : 0;
+        for (int S = 0; S < 81; ++S) Hash ^= Z.Piece[S][Board[S]];
+        for (int C = 0; C < 2; ++C)
+            for (int K = 0; K < 7; ++K) Hash ^= Z.Hand[C][K][Hands[C][K]];
+        for (int S = 0; S < 81; ++S)
+            if (Board[S] && typeOf(Board[S]) == King) KingSq[colourOf(Board[S])] = (uint8_t)S;
+    }
+
+    // ---- attacks -------------------------------------------------------------------------------------------------
+    // step / slide tables in BLACK's orientation (forward = rank - 1); white's are the same with the rank step negated
+    static bool stepsTo(int Type, int Df, int Dr) {  // can a black piece of Type step by (Df, Dr)?
+        const bool Fwd = Dr == -1, Back = Dr == 1, Side_ = Dr == 0;
+        const int Af = Df < 0 ? -Df : Df;
+        switch (Type) {
+        case Pawn: return Df == 0 && Fwd;
+        case Knight: return Af == 1 && Dr == -2;
+        case Silver: return (Fwd && Af <= 1) || (Back && Af == 1);
+        case Gold: case ProPawn: case ProLance: case ProKnight: case ProSilver:
+            return (Fwd && Af <= 1) || (Side_ && Af == 1) || (Back && Df == 0);
+        case King: return Af <= 1 && Dr >= -1 && Dr <= 1 && (Df != 0 || Dr != 0);
+        case ProBishop: return Af + (Dr < 0 ? -Dr : Dr) == 1;  // orthogonal king steps (the diagonals slide)
+        case ProRook: return Af == 1 && (Dr == 1 || Dr == -1);  // diagonal king steps (the orthogonals slide)
+        default: return false;
+        }
+    }
+    static bool slidesAlong(int Type, int Df, int Dr) {  // black orientation, unit direction
+        switch (Type) {
+        case Lance: return Df == 0 && Dr == -1;
+        case Bishop: case ProBishop: return Df != 0 && Dr != 0;
+        case Rook: case ProRook: return (Df == 0) != (Dr == 0);
+        default: return false;
+        }
+    }
+
+    // Is square S attacked by a piece of colour By?
+    bool attacked(int S, int By) const {
+        const int F = fileOf(S), R = rankOf(S);
+        const int Sign = By == 0 ? 1 : -1;  // an attacker of colour By at T steps (Df, Sign * Dr_black) to reach S
+        // steps (including the knight's)
+        static const int8_t Steps[10][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {-1, -2}, {1, -2}};
+        for (const auto& D : Steps) {
+            // the attacker moves by (D0, Sign * D1): it stands at S - that
+            const int Af = F - D[0], Ar = R - Sign * D[1];
+            if (!onBoard(Af, Ar)) continue;
+            const int C = Board[9 * Af + Ar];
+            if (C && colourOf(C) == By && stepsTo(typeOf(C), D[0], D[1])) return true;
+        }
+        // slides
+        static const int8_t Dirs[8][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}};
+        for (const auto& D : Dirs) {
+            int Af = F - D[0], Ar = R - Sign * D[1];
+            while (onBoard(Af, Ar)) {
+                const int C = Board[9 * Af + Ar];
+                if (C) {
+                    if (colourOf(C) == By && slidesAlong(typeOf(C), D[0], D[1])) return true;
+                    break;
+                }
+                Af -= D[0];
+                Ar -= Sign * D[1];
+            }
+        }
+        return false;
+    }
+    bool inCheck(int Colour) const { return KingSq[Colour] != 255 && attacked(KingSq[Colour], Colour ^ 1); }
+
+    // ---- make / unmake -------------------------------------------------------------------------------------------
+    struct Undo {
+        uint8_t Captured;
+        uint64_t Hash;
+    };
+    void make(const Move& M, Undo* U) {
+        const ZobristKeys& Z = zobrist();
+        U->Hash = Hash;
+        const int Me = Side;
+        if (M.isDrop()) {
+            const int K = M.dropSlot();
+            U->Captured = 0;
+            Hash ^= Z.Hand[Me][K][Hands[Me][K]];
+            --Hands[Me][K];
+            Hash ^= Z.Hand[Me][K][Hands[Me][K]];
+            Board[M.To] = (uint8_t)code(kHandPiece[K], Me);
+            Hash ^= Z.Piece[M.To][Board[M.To]];
+        } else {
+            const int Cap = Board[M.To];
+            U->Captured = (uint8_t)Cap;
+            if (Cap) {
+                Hash ^= Z.Piece[M.To][Cap];
+                const int K = kHandSlot[typeOf(Cap)];
+                if (K >= 0) {
+                    Hash ^= Z.Hand[Me][K][Hands[Me][K]];
+                    ++Hands[Me][K];
+                    Hash ^= Z.Hand[Me][K][Hands[Me][K]];
+                } else {
+                    KingSq[Me ^ 1] = 255;  // (never happens in legal play)
+                }
+            }
+            const int Moving = Board[M.From];
+            Hash ^= Z.Piece[M.From][Moving];
+            Board[M.From] = 0;
+            const int NewType = M.Promote ? kPromoted[typeOf(Moving)] : typeOf(Moving);
+            Board[M.To] = (uint8_t)code(NewType, Me);
+            Hash ^= Z.Piece[M.To][Board[M.To]];
+            if (NewType == King) KingSq[Me] = M.To;
+        }
+        Side ^= 1;
+        Hash ^= Z.Side;
+        ++Ply;
+    }
+    void unmake(const Move& M, const Undo& U) {
+        Side ^= 1;
+        --Ply;
+        const int Me = Side;
+        if (M.isDrop()) {
+            Board[M.To] = 0;
+            ++Hands[Me][M.dropSlot()];
+        } else {
+            Board[M.From] = (uint8_t)code(M.Piece, Me);
+            Board[M.To] = U.Captured;
+            if (U.Captured) {
+                const int K = kHandSlot[typeOf(U.Captured)];
+                if (K >= 0) --Hands[Me][K];
+                else KingSq[Me ^ 1] = M.To;
+            }
+            if (M.Piece == King) KingSq[Me] = M.From;
+        }
+        Hash = U.Hash;
+    }
+
+    // ---- move generation -----------------------------------------------------------------------------------------
+    static bool inPromotionZone(int Colour, int R) { return Colour == 0 ? R <= 2 : R >= 6; }
+    static bool canStay(int Type, int Colour, int R) {  // may an UNPROMOTED piece of Type stand on rank R?
+        const int Rel = Colour == 0 ? R : 8 - R;  // 0 = the far rank
+        if (Type == Pawn || Type == Lance) return Rel >= 1;
+        if (Type == Knight) return Rel >= 2;
+        return true;
+    }
+
+    // Pseudo-legal moves of the side to move (king safety not yet checked).  Returns the count.
+    int generatePseudoLegal(Move* Out) const {
+        int N = 0;
+        const int Me = Side, Sign = Me == 0 ? 1 : -1;
+        static const int8_t Steps[10][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {-1, -2}, {1, -2}};
+        static const int8_t Dirs[8][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}};
+        auto emit = [&](int From, int To, int Type) {
+            const int Rf = rankOf(From), Rt = rankOf(To);
+            const bool Promotable = kPromoted[Type] >= 0 && (inPromotionZone(Me, Rf) || inPromotionZone(Me, Rt));
+            if (Promotable) Out[N++] = Move{(uint8_t)From, (uint8_t)To, 1, (uint8_t)Type};
+            if (canStay(Type, Me, Rt)) Out[N++] = Move{(uint8_t)From, (uint8_t)To, 0, (uint8_t)Type};
+        };
+        bool PawnOnFile[9] = {false, false, false, false, false, false, false, false, false};
+        for (int S = 0; S < 81; ++S) {
+            const int C = Board[S];
+            if (!C || colourOf(C) != Me) continue;
+            const int Type = typeOf(C), F = fileOf(S), R = rankOf(S);
+            if (Type == Pawn) PawnOnFile[F] = true;
+            for (const auto& D : Steps) {
+                if (!stepsTo(Type, D[0], D[1])) continue;
+                const int Tf = F + D[0], Tr = R + Sign * D[1];
+                if (!onBoard(Tf, Tr)) continue;
+                const int T = Board[9 * Tf + Tr];
+                if (T && colourOf(T) == Me) continue;
+                emit(S, 9 * Tf + Tr, Type);
+            }
+            for (const auto& D : Dirs) {
+                if (!slidesAlong(Type, D[0], D[1])) continue;
+                int Tf = F + D[0], Tr = R + Sign * D[1];
+                while (onBoard(Tf, Tr)) {
+                    const int T = Board[9 * Tf + Tr];
+                    if (T && colourOf(T) == Me) break;
+                    emit(S, 9 * Tf + Tr, Type);
+                    if (T) break;
+                    Tf += D[0];
+                    Tr += Sign * D[1];
+                }
+            }
+        }
+        for (int K = 0; K < 7; ++K) {
+            if (!Hands[Me][K]) continue;
+            const int Type = kHandPiece[K];
+            for (int S = 0; S < 81; ++S) {
+                if (Board[S]) continue;
+                if (!canStay(Type, Me, rankOf(S))) continue;
+                if (Type == Pawn && PawnOnFile[fileOf(S)]) continue;  // nifu
+                Out[N++] = Move{(uint8_t)(81 + K), (uint8_t)S, 0, (uint8_t)Type};
+            }
+        }
+        return N;
+    }
+
+    // Legal moves: the mover's king is not left in check; a pawn drop that mates is illegal (uchifuzume).
+    int generateLegal(Move* Out) {
+        Move Tmp[kMaxMoves + 64];
+        const int NP = generatePseudoLegal(Tmp);
+        const int Me = Side;
+        int N = 0;
+        for (int I = 0; I < NP; ++I) {
+            Undo U;
+            make(Tmp[I], &U);
+            bool Ok = !inCheck(Me);
+            if (Ok && Tmp[I].isDrop() && Tmp[I].Piece == Pawn && inCheck(Me ^ 1)) Ok = hasLegalMove();  // uchifuzume
+            unmake(Tmp[I], U);
+            if (Ok && N < kMaxMoves) Out[N++] = Tmp[I];
+        }
+        return N;
+    }
+    bool hasLegalMove() {
+        Move Tmp[kMaxMoves + 64];
+        const int NP = generatePseudoLegal(Tmp);
+        const int Me = Side;
+        for (int I = 0; I < NP; ++I) {
+            Undo U;
+            make(Tmp[I], &U);
+            bool Ok = !inCheck(Me);
+            if (Ok && Tmp[I].isDrop() && Tmp[I].Piece == Pawn && inCheck(Me ^ 1)) Ok = hasLegalMove();
+            unmake(Tmp[I], U);
+            if (Ok) return true;
+        }
+        return false;
+    }
+
+    uint64_t perft(int Depth) {
+        if (Depth == 0) return 1;
+        Move Ms[kMaxMoves];
+        const int N = generateLegal(Ms);
+        if (Depth == 1) return (uint64_t)N;
+        uint64_t Sum = 0;
+        for (int I = 0; I < N; ++I) {
+            Undo U;
+            make(Ms[I], &U);
+            Sum += perft(Depth - 1);
+            unmake(Ms[I], U);
+        }
+        return Sum;
+    }
+
+    // ---- hand-over to the executor ---------------------------------------------------------------------------------
+    // Stage-1 record of this position (include/nsb.h nsb_position; the board codes are the same by construction).
+    void toRecord(nsb_position* P, uint16_t MaxPly, float BlackDraw, float WhiteDraw) const {
+        std::memcpy(P->board, Board, 81);
+        P->side = Side;
+        std::memcpy(P->hands, Hands, 14);
+        P->ply = Ply;
+        P->max_ply = MaxPly;
+        P->black_draw_value = BlackDraw;
+        P->white_draw_value = WhiteDraw;
+    }
+    // Policy slot of a legal move of the side to move (host/move_index.h == ml::getMoveIndex's role).
+    int policyIndex(const Move& M) const {
+        return getMoveIndex(Side, MoveSpec{M.isDrop() ? 0 : (int)M.From, (int)M.To, M.Promote != 0, M.isDrop() ? M.dropSlot() : -1});
+    }
+};
+
+} // namespace rules
+} // namespace b200
+} // namespace engine
+} // namespace nshogi
+
+#endif
