@@ -28,6 +28,7 @@
 #include "selfplay_feed.h"
 #include "move_index.h"
 #include "onnx_import.h"
+#include "selfplay_game.h"
 
 using namespace nshogi::engine;
 
@@ -253,7 +254,167 @@ static int selfplayFeedChecks() {
     return 0;
 }
 
+
+// ---- rules/shogi.h: known-answer perft counts and one hand-made position per special rule ------------------------
+static int rulesChecks(int PerftDepth) {
+    using namespace b200::rules;
+    {
+        Position P;
+        const unsigned long long Want[6] = {1ull, 30ull, 900ull, 25470ull, 719731ull, 19861490ull};  // public perft values of hirate
+        for (int D = 1; D <= PerftDepth && D <= 5; ++D) CHECK(P.perft(D) == Want[D]);
+        const uint64_t H0 = P.Hash;
+        Move Ms[kMaxMoves];
+        const int N = P.generateLegal(Ms);
+        CHECK(N == 30);
+        for (int I = 0; I < N; ++I) {  // make / unmake restores everything, the hash is incremental == recomputed
+            Position Q = P;
+            Position::Undo U;
+            Q.make(Ms[I], &U);
+            const uint64_t Inc = Q.Hash;
+            Q.rehash();
+            CHECK(Inc == Q.Hash && Q.Hash != H0);
+            Q.unmake(Ms[I], U);
+            CHECK(Q.Hash == H0 && std::memcmp(Q.Board, P.Board, 81) == 0 && Q.Side == 0 && Q.Ply == 0);
+            const int Slot = P.policyIndex(Ms[I]);
+            CHECK(Slot >= 0 && Slot < NSB_POLICY_SIZE);
+        }
+        std::set<int> Slots;                 // distinct policy slots for distinct legal moves
+        for (int I = 0; I < N; ++I) Slots.insert(P.policyIndex(Ms[I]));
+        CHECK((int)Slots.size() == N);
+    }
+    auto has = [](Position& P, int From, int To, int Promote) {
+        Move Ms[kMaxMoves];
+        const int N = P.generateLegal(Ms);
+        for (int I = 0; I < N; ++I)
+            if (Ms[I].From == From && Ms[I].To == To && Ms[I].Promote == Promote) return true;
+        return false;
+    };
+    auto sq = [](int F, int R) { return 9 * (F - 1) + (R - 1); };
+    {   // nifu, drop ranks, mandatory promotion
+        Position P;
+        P.clear();
+        P.put(5, 9, King, 0); P.put(5, 1, King, 1);
+        P.put(3, 5, Pawn, 0);                 // black pawn on file 3
+        P.put(7, 2, Pawn, 0);                 // a pawn one step from the far rank
+        P.put(8, 3, Knight, 0);               // a knight that can only jump to the far rank
+        P.Hands[0][0] = 1; P.Hands[0][1] = 1; P.Hands[0][2] = 1;   // pawn, lance, knight in hand
+        P.rehash();
+        CHECK(!has(P, 81 + 0, sq(3, 4), 0) && has(P, 81 + 0, sq(4, 4), 0));      // nifu on file 3 only
+        CHECK(!has(P, 81 + 0, sq(4, 1), 0) && !has(P, 81 + 1, sq(4, 1), 0));     // pawn / lance never on the far rank
+        CHECK(has(P, 81 + 1, sq(4, 2), 0));
+        CHECK(!has(P, 81 + 2, sq(4, 2), 0) && !has(P, 81 + 2, sq(4, 1), 0) && has(P, 81 + 2, sq(4, 3), 0));  // knight: not on the far two
+        CHECK(has(P, sq(7, 2), sq(7, 1), 1) && !has(P, sq(7, 2), sq(7, 1), 0));  // the pawn must promote
+        CHECK(has(P, sq(8, 3), sq(7, 1), 1) && !has(P, sq(8, 3), sq(7, 1), 0) && has(P, sq(8, 3), sq(9, 1), 1));
+    }
+    {   // pawn-drop mate is illegal; the same drop is legal as soon as the king has a flight square
+        Position P;
+        P.clear();
+        P.put(5, 9, King, 0); P.put(1, 1, King, 1);
+        P.put(2, 1, Knight, 1); P.put(2, 2, Pawn, 1);   // the king's neighbours are its own pieces
+        P.put(1, 9, Lance, 0);                            // guards the whole first file
+        P.Hands[0][0] = 1;
+        P.rehash();
+        CHECK(!has(P, 81 + 0, sq(1, 2), 0));
+        CHECK(has(P, 81 + 0, sq(1, 3), 0));               // a pawn drop that is no check is fine
+        P.Board[sq(2, 2)] = 0;                            // open a flight square
+        P.rehash();
+        CHECK(has(P, 81 + 0, sq(1, 2), 0));
+    }
+    {   // pins and check evasions
+        Position P;
+        P.clear();
+        P.put(5, 9, King, 0); P.put(5, 8, Gold, 0); P.put(5, 1, Rook, 1); P.put(1, 1, King, 1);
+        P.rehash();
+        CHECK(has(P, sq(5, 8), sq(5, 7), 0) && !has(P, sq(5, 8), sq(4, 8), 0) && !has(P, sq(5, 8), sq(6, 7), 0));   // pinned on the file
+        P.Board[sq(5, 8)] = 0;
+        P.put(9, 9, Gold, 0);
+        P.rehash();
+        CHECK(P.inCheck(0));
+        Move Ms[kMaxMoves];
+        const int N = P.generateLegal(Ms);
+        for (int I = 0; I < N; ++I) CHECK(Ms[I].Piece == King && fileOf(Ms[I].To) != 4);   // only king moves off the file
+        CHECK(N == 4);                                                                       // 4i, 6i, 4h, 6h ... (5h stays attacked)
+    }
+    {   // promoted sliders keep sliding and gain the king's other steps; captures go to the hand unpromoted
+        Position P;
+        P.clear();
+        P.put(5, 9, King, 0); P.put(1, 1, King, 1); P.put(5, 5, ProBishop, 0); P.put(7, 3, ProRook, 1);
+        P.rehash();
+        CHECK(has(P, sq(5, 5), sq(5, 4), 0) && has(P, sq(5, 5), sq(1, 9), 0) && has(P, sq(5, 5), sq(7, 3), 0) && !has(P, sq(5, 5), sq(9, 1), 0));
+        Move Ms[kMaxMoves];
+        const int N = P.generateLegal(Ms);
+        for (int I = 0; I < N; ++I)
+            if (Ms[I].From == sq(5, 5) && Ms[I].To == sq(7, 3)) {
+                Position::Undo U;
+                P.make(Ms[I], &U);
+                CHECK(P.Hands[0][6] == 1 && P.Board[sq(7, 3)] == Position::code(ProBishop, 0));   // a ROOK in hand
+                P.unmake(Ms[I], U);
+                CHECK(P.Hands[0][6] == 0 && P.Board[sq(7, 3)] == Position::code(ProRook, 1));
+            }
+    }
+    return 0;
+}
+
+// ---- selfplay_game.h + mcts_search.h: whole games against a mock evaluator (no GPU) -----------------------------------
+static int selfplayMock(int Games, int Playouts) {
+    using namespace b200;
+    game::GameOptions O;
+    O.Playouts = Playouts;
+    O.FullSearchRatio = 0.5;
+    game::Info SI;
+    game::Frame F;
+    F.MT.seed(42);
+    game::newGame(O, F);
+    F.MaxPly = 60;
+    game::prepareRoot(O, F);
+    uint64_t Evals = 0;
+    while ((int)SI.Games.load() < Games) {
+        const uint64_t GamesBefore = SI.Games.load(), RecordsBefore = SI.Records.load();
+        const uint32_t RootVisitsBefore = F.Tree.Nodes[0].Visits;
+        game::advance(O, F, &SI);
+        if (SI.Games.load() != GamesBefore) F.MaxPly = 60;  // (newGame drew a long one)
+        if (SI.Records.load() == RecordsBefore && F.LeafNode != 0) CHECK(F.Tree.Nodes[0].Visits >= RootVisitsBefore);
+        // the frame now waits for an evaluation of F.Leaf with F.NumLeafMoves legal moves
+        CHECK(F.NumLeafMoves >= 1 && F.NumLeafMoves <= rules::kMaxMoves && F.LeafNode >= 0);
+        rules::Move Check[rules::kMaxMoves];
+        rules::Position L = F.Leaf;
+        CHECK(L.generateLegal(Check) == F.NumLeafMoves);
+        std::vector<float> Row((size_t)F.NumLeafMoves);
+        double Sum = 0.0;
+        uint64_t H = F.Leaf.Hash;
+        for (int J = 0; J < F.NumLeafMoves; ++J) {
+            CHECK(F.LeafSlots[J] < NSB_POLICY_SIZE);
+            H = H * 6364136223846793005ull + F.LeafSlots[J];
+            Sum += (Row[(size_t)J] = 1.0f + (float)((H >> 40) % 1000) / 250.0f);
+        }
+        for (auto& X : Row) X = (float)(X / Sum);
+        std::vector<uint16_t> Order((size_t)F.NumLeafMoves);
+        for (int J = 0; J < F.NumLeafMoves; ++J) Order[(size_t)J] = (uint16_t)J;
+        std::stable_sort(Order.begin(), Order.end(), [&](uint16_t A, uint16_t B) { return Row[A] > Row[B]; });
+        const float Win = 0.3f + 0.4f * (float)((F.Leaf.Hash >> 20) % 1000) / 1000.0f, Draw = 0.05f;
+        game::applyEvaluation(O, F, Row.data(), Order.data(), Win, Draw);
+        ++Evals;
+        // tree invariants after the back-propagation
+        const search::Node& R = F.Tree.Nodes[0];
+        uint64_t ChildVisits = 0;
+        for (int I = 0; I < R.NumEdges; ++I) {
+            const search::Edge& E = F.Tree.Edges[(size_t)R.EdgeBegin + (size_t)I];
+            if (I > 0) CHECK(E.P <= F.Tree.Edges[(size_t)R.EdgeBegin + (size_t)I - 1].P);   // sorted by prior
+            if (E.Child >= 0) ChildVisits += F.Tree.Nodes[(size_t)E.Child].Visits;
+        }
+        CHECK(R.Evaluated && R.Visits == ChildVisits + 1 && R.VirtualLoss == 0);
+        CHECK(R.WinAcc >= 0.0 && R.WinAcc <= (double)R.Visits);
+        CHECK(R.Visits <= (uint32_t)Playouts + 1);
+    }
+    std::printf("selfplay mock: %d games, %llu records, %llu evaluations, %llu terminal leaves; ended by mate %llu / repetition %llu / max ply %llu\n",
+                Games, (unsigned long long)SI.Records.load(), (unsigned long long)Evals, (unsigned long long)SI.Terminals.load(),
+                (unsigned long long)SI.Mates.load(), (unsigned long long)SI.Repetitions.load(), (unsigned long long)SI.MaxPlies.load());
+    CHECK(SI.Records.load() >= (uint64_t)Games * 10 && Evals > SI.Records.load());
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 3 && std::strcmp(argv[1], "--perft") == 0) return rulesChecks(std::atoi(argv[2]));
     if (argc >= 4 && std::strcmp(argv[1], "--queue-stress") == 0) return queueStress(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]));
     if (argc >= 4 && std::strcmp(argv[1], "--onnx-blob") == 0) return onnxBlob(argv[2], argv[3]);
     if (argc >= 3 && std::strcmp(argv[1], "--cache-trace") == 0) return cacheTrace((std::size_t)std::atoi(argv[2]));
@@ -316,6 +477,8 @@ int main(int argc, char** argv) {
     }
     if (feedChecks()) return 1;  // mcts_feed.h == setEvaluation + sort + updateAncestors of the reference
     if (selfplayFeedChecks()) return 1;
+    if (rulesChecks(4)) return 1;          // shogi rules: perft(1..4) of hirate + the special rules
+    if (selfplayMock(2, 24)) return 1;     // two whole games of the self-play loop against a mock evaluator
     std::printf("host_unit ok\n");
     return 0;
 }

@@ -87,6 +87,12 @@ class LeafPipeline {
         return Slots[I];
     }
 
+    // Slot `Index` itself, for callers that keep their own ring order (a slot must have been collected before it is
+    // filled again; acquire() does both for the round-robin case).
+    Slot& slotAt(std::size_t Index) {
+        return Slots[Index];
+    }
+
     // Enqueue stage 1 (if FromPositions) + expansion + forward + fused decode, with the copies around them or, in
     // a one-slot executor, directly on these page-locked arrays (NSB_IO_DIRECT).  With UseCache (executor built
     // with enableCache) the batch goes through the device-resident cache: hits are served from HBM, only the

@@ -1,0 +1,181 @@
+// selfplay_game.h — one self-play game ("frame") and the search side of its phase machine, shared by the GPU harness
+// (selfplay_real.cc) and the CPU unit test that plays whole games against a mock evaluator (host_unit.cc --selfplay).
+// Reference: src/selfplay/frame.h (Frame), src/selfplay/worker.cc:55-110 (phases), :112-156 (initialize), :159-206
+// (prepareRoot), :330-372 (terminal checks), :415-430 (playout budget), :520-640 (transition), :476-518 (judge),
+// src/selfplay/frame.cc:93-136 (setEvaluation).  Rules: rules/shogi.h; tree: mcts_search.h.
+#ifndef NSHOGI_ENGINE_B200_SELFPLAY_GAME_H
+#define NSHOGI_ENGINE_B200_SELFPLAY_GAME_H
+
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <random>
+#include <vector>
+
+#include "mcts_search.h"
+#include "rules/shogi.h"
+
+namespace nshogi {
+namespace engine {
+namespace b200 {
+namespace game {
+
+struct GameOptions {
+    int Playouts = 200;
+    bool Gumbel = false;
+    double FullSearchRatio = 0.25;
+};
+
+struct Frame {  // reference src/selfplay/frame.h: one game in flight
+    rules::Position Root, Leaf;
+    std::vector<uint64_t> History, Path;
+    search::Tree Tree;
+    int LeafNode = -1;
+    rules::Move LeafMoves[rules::kMaxMoves];
+    uint16_t LeafSlots[rules::kMaxMoves];
+    int NumLeafMoves = 0;
+    uint16_t MaxPly = 320;
+    float BlackDraw = 0.5f, WhiteDraw = 0.5f;
+    uint32_t Playouts = 0;
+    bool FullSearch = true;
+    double Noise[600];
+    std::mt19937_64 MT;
+};
+
+struct Info {  // reference src/selfplay/selfplayinfo.h
+    std::atomic<uint64_t> Evals{0}, Batches{0}, Records{0}, Games{0}, NanRows{0}, CacheHits{0};
+    std::atomic<uint64_t> Mates{0}, Repetitions{0}, MaxPlies{0}, Terminals{0}, PliesPlayed{0}, LegalMoves{0};
+};
+
+// Worker::initialize, worker.cc:112-156
+inline void newGame(const GameOptions& O, Frame& F) {
+    F.Root.setHirate();
+    F.History.clear();
+    F.History.push_back(F.Root.Hash);
+    std::uniform_int_distribution<int> MaxPlyD(160 + 64, 512 + 128);
+    std::uniform_real_distribution<float> DrawD(0.0f, 1.0f);
+    F.MaxPly = (uint16_t)MaxPlyD(F.MT);
+    if (F.MT() % 4 < 2) {
+        F.BlackDraw = F.WhiteDraw = 0.5f;
+    } else {
+        F.BlackDraw = DrawD(F.MT);
+        F.WhiteDraw = 1.0f - F.BlackDraw;
+    }
+    (void)O;
+}
+
+// Worker::prepareRoot, worker.cc:159-206
+inline void prepareRoot(const GameOptions& O, Frame& F) {
+    F.Tree.reset();
+    if (O.Gumbel) {
+        std::uniform_real_distribution<double> D(std::numeric_limits<double>::min(), 1.0);
+        for (double& X : F.Noise) X = -std::log(-std::log(D(F.MT)));
+    } else {
+        std::gamma_distribution<double> D(0.15, 1.0);
+        double Sum = 0.0;
+        for (double& X : F.Noise) Sum += (X = D(F.MT));
+        for (double& X : F.Noise) X /= Sum;
+    }
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    F.FullSearch = U(F.MT) <= O.FullSearchRatio;
+    F.Playouts = F.FullSearch ? (uint32_t)O.Playouts : (uint32_t)std::max(1, O.Playouts / 4);
+}
+
+// Worker::transition + judge, worker.cc:520-640,476-518: play the most visited move; true when the game is over.
+inline bool transition(Frame& F, Info* SI) {
+    const int Best = F.Tree.bestRootEdge();
+    const search::Node& R = F.Tree.Nodes[0];
+    const rules::Move M = F.Tree.Edges[R.EdgeBegin + Best].M;
+    rules::Position::Undo U;
+    F.Root.make(M, &U);
+    F.History.push_back(F.Root.Hash);
+    SI->Records.fetch_add(1, std::memory_order_relaxed);  // one teacher record per played position (saveworker.cc:160-182)
+    SI->PliesPlayed.fetch_add(1, std::memory_order_relaxed);
+    int Seen = 0;
+    for (uint64_t H : F.History) Seen += H == F.Root.Hash;
+    if (Seen >= 4) {
+        SI->Repetitions.fetch_add(1, std::memory_order_relaxed);
+        return true;
+    }
+    if (F.Root.Ply >= F.MaxPly) {
+        SI->MaxPlies.fetch_add(1, std::memory_order_relaxed);
+        return true;
+    }
+    if (!F.Root.hasLegalMove()) {
+        SI->Mates.fetch_add(1, std::memory_order_relaxed);
+        return true;
+    }
+    return false;
+}
+
+// One frame until it needs the network: selectLeaf / checkTerminal / backpropagate / transition (worker.cc:82-106).
+inline void advance(const GameOptions& O, Frame& F, Info* SI) {
+    for (;;) {
+        search::Node& Root = F.Tree.Nodes[0];
+        if (Root.Evaluated && (Root.NumEdges == 1 || Root.Visits >= F.Playouts + 1)) {  // worker.cc:415-430 (+1: the root's own evaluation)
+            if (transition(F, SI)) {
+                SI->Games.fetch_add(1, std::memory_order_relaxed);
+                newGame(O, F);
+            }
+            prepareRoot(O, F);
+            continue;
+        }
+        F.Leaf = F.Root;
+        F.Path.clear();
+        const int Node = F.Tree.selectLeaf(F.Leaf, F.BlackDraw, F.WhiteDraw, &F.Path);
+        search::Node& N = F.Tree.Nodes[Node];
+        if (N.Term == search::Mated) {
+            F.Tree.backup(Node, 0.0f, 0.0f);
+            continue;
+        }
+        if (N.Term == search::DrawnGame) {
+            F.Tree.backup(Node, 0.5f, 1.0f);
+            continue;
+        }
+        // a new leaf: terminal checks first (searchworker.cc:475-538, selfplay/worker.cc:330-372)
+        const int NumMoves = F.Leaf.generateLegal(F.LeafMoves);
+        if (NumMoves == 0) {
+            N.Term = search::Mated;
+            N.Evaluated = true;
+            SI->Terminals.fetch_add(1, std::memory_order_relaxed);
+            F.Tree.backup(Node, 0.0f, 0.0f);
+            continue;
+        }
+        if (Node != 0 && (search::isFourfold(F.Leaf.Hash, F.History, F.Path) || F.Leaf.Ply >= F.MaxPly)) {
+            N.Term = search::DrawnGame;
+            N.Evaluated = true;
+            SI->Terminals.fetch_add(1, std::memory_order_relaxed);
+            F.Tree.backup(Node, 0.5f, 1.0f);
+            continue;
+        }
+        F.Tree.expand(Node, F.LeafMoves, NumMoves);
+        for (int J = 0; J < NumMoves; ++J) F.LeafSlots[J] = (uint16_t)F.Leaf.policyIndex(F.LeafMoves[J]);  // ml::getMoveIndex
+        F.NumLeafMoves = NumMoves;
+        F.LeafNode = Node;
+        return;
+    }
+}
+
+// Frame::setEvaluation's consumer side (frame.cc:93-136) for a row the executor decoded (NSB_DECODE_BOTH + order_out):
+// priors in rank order (Node::setEvaluation + Node::sort in one pass), the Dirichlet mix of a full-search AlphaZero
+// root (frame.cc:121-133; the noise is i.i.d., so mixing it after the sort draws from the same distribution), then
+// Node::updateAncestors.
+inline void applyEvaluation(const GameOptions& O, Frame& F, const float* Row, const uint16_t* Order, float WinRate, float DrawRate) {
+    F.Tree.setPriors(F.LeafNode, Row, Order);
+    if (!O.Gumbel && F.LeafNode == 0 && F.FullSearch) {
+        search::Node& R = F.Tree.Nodes[0];
+        search::Edge* E = F.Tree.Edges.data() + R.EdgeBegin;
+        const double EPS = 0.25;
+        for (int J = 0; J < R.NumEdges; ++J) E[J].P = (float)((1 - EPS) * (double)E[J].P + EPS * F.Noise[J]);
+        F.Tree.sortEdges(0);
+    }
+    F.Tree.backup(F.LeafNode, WinRate, DrawRate);
+}
+
+} // namespace game
+} // namespace b200
+} // namespace engine
+} // namespace nshogi
+
+#endif

@@ -1,0 +1,257 @@
+// selfplay_real.cc — self-play data generation with REAL shogi rules and a REAL MCTS, driving infer::B200 through the
+// pinned multi-slot LeafPipeline: BASELINE.json configs[3] ("self-play data generation, 20x256 ResNet, 1024 concurrent
+// games per GPU") and its metric "self-play positions/sec" (SURVEY.md §8 f1).
+//
+// Structure = the reference's src/selfplay/: a pool of frames (games, main.cc:100-110), search workers that run the
+// phase machine of worker.cc:55-110 on one frame at a time (initialize -> prepareRoot -> selectLeaf -> checkTerminal ->
+// [evaluation] -> backpropagate -> transition -> judge), ONE evaluation worker per GPU (evaluationworker.cc:69-117), two
+// frame queues between them (framequeue.cc).  What differs from the reference, on purpose:
+//   - rules, move generation, repetition: host/rules/shogi.h (libnshogi is not available; perft-pinned);
+//   - tree: host/mcts_search.h (PUCT with the reference's constants; no df-pn, no tree reuse between moves);
+//   - the evaluation worker does not build features and does not block per batch: it copies 108-byte position records
+//     and the legal moves' policy slots into the next pinned slot, submits (stage 1, forward, gather, cache store of the
+//     raw logits, softmax and the edges' rank order all happen in ONE launch: NSB_DECODE_BOTH + order_out) and waits
+//     only for the oldest batch;
+//   - teacher records are counted, not written (the record format is libnshogi's io::file::simple_teacher,
+//     saveworker.cc:160-182).
+// Games start from hirate; per game MaxPly ~ U[224, 640] and the draw values of worker.cc:135-150; per move a full
+// search (--num-playouts) with probability --full-search-ratio, else a quarter of it (worker.cc:184-197); AlphaZero
+// style: Dirichlet(0.15) noise mixed into the root priors of full searches (frame.cc:121-133), the most visited move is
+// played (worker.cc:555-590).  A game ends by mate, four-fold repetition (draw) or at MaxPly (draw).
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <mutex>
+#include <random>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "infer_b200.h"
+#include "leaf_pipeline.h"
+#include "selfplay_feed.h"
+#include "selfplay_game.h"
+
+using namespace nshogi::engine;
+using namespace nshogi::engine::b200;
+using Clock = std::chrono::steady_clock;
+
+namespace {
+
+struct Options : b200::game::GameOptions {
+    int Channels = 256, Blocks = 20, Batch = 512, Frames = 1024, SearchWorkers = 4, Slots = 3, GPU = 0;
+    int CacheMiB = 0;
+    double Seconds = 5.0, Warmup = 1.0;
+    uint64_t Seed = 1234;
+};
+using b200::game::Frame;
+using b200::game::Info;
+
+class FrameQueue {  // reference src/selfplay/framequeue.h
+ public:
+    void add(std::vector<Frame*>& Fs) {
+        if (Fs.empty()) return;
+        {
+            std::lock_guard<std::mutex> L(M);
+            for (Frame* F : Fs) Q.push_back(F);
+        }
+        CV.notify_all();
+        Fs.clear();
+    }
+    void get(std::size_t Max, bool Wait, std::vector<Frame*>& Out) {
+        std::unique_lock<std::mutex> L(M);
+        if (Wait) CV.wait_for(L, std::chrono::milliseconds(2), [&] { return !Q.empty() || Closed; });
+        while (!Q.empty() && Out.size() < Max) {
+            Out.push_back(Q.front());
+            Q.pop_front();
+        }
+    }
+    void close() {
+        {
+            std::lock_guard<std::mutex> L(M);
+            Closed = true;
+        }
+        CV.notify_all();
+    }
+
+ private:
+    std::deque<Frame*> Q;
+    std::mutex M;
+    std::condition_variable CV;
+    bool Closed = false;
+};
+
+void searchWorker(const Options& O, FrameQueue* SearchQueue, FrameQueue* EvaluationQueue, Info* SI, std::atomic<bool>* Running) {
+    std::vector<Frame*> In, Out;
+    while (Running->load(std::memory_order_relaxed)) {
+        In.clear();
+        SearchQueue->get(32, true, In);
+        for (Frame* F : In) {
+            b200::game::advance(O, *F, SI);
+            Out.push_back(F);
+        }
+        EvaluationQueue->add(Out);
+    }
+}
+
+// reference src/selfplay/evaluationworker.cc:69-117, restructured around the slot ring (see the file comment)
+void evaluationWorker(const Options& O, infer::B200* Exec, FrameQueue* EvaluationQueue, FrameQueue* SearchQueue, Info* SI,
+                      std::atomic<bool>* Running) {
+    Exec->resetGPU();
+    Exec->bindThreadToGpuNode();  // evaluator.cc:39-83
+    evaluate::LeafPipeline Pipe(Exec, (std::size_t)O.Batch);
+    const std::size_t NS = Pipe.numSlots();
+    std::vector<std::vector<Frame*>> SlotTasks(NS);
+    std::deque<std::size_t> InFlight;
+    std::vector<Frame*> Tasks;
+    auto deliver = [&](std::size_t Idx) {
+        evaluate::LeafPipeline::Slot& S = Pipe.collect(Idx);
+        std::vector<Frame*>& Fs = SlotTasks[Idx];
+        for (std::size_t I = 0; I < Fs.size(); ++I) {  // Frame::setEvaluation, frame.cc:93-136, consumer side
+            Frame* F = Fs[I];
+            const uint32_t B = S.MoveOffsets[I];
+            // gather, cache store of the raw logits and softmax (or its skip at a Gumbel root) happened on the GPU
+            // together with the rank order of the row; the Dirichlet mix of a full-search AlphaZero root is left
+            b200::game::applyEvaluation(O, *F, S.Legal + B, S.Order + B, S.WinRate[I], S.DrawRate[I]);
+            if (S.NanFlag[I]) SI->NanRows.fetch_add(1, std::memory_order_relaxed);
+            if (O.CacheMiB > 0 && S.HitFlag[I]) SI->CacheHits.fetch_add(1, std::memory_order_relaxed);
+        }
+        SI->Evals.fetch_add(Fs.size(), std::memory_order_relaxed);
+        SI->Batches.fetch_add(1, std::memory_order_relaxed);
+        SearchQueue->add(Fs);
+    };
+    while (Running->load(std::memory_order_relaxed)) {
+        Tasks.clear();
+        EvaluationQueue->get((std::size_t)O.Batch, InFlight.empty(), Tasks);
+        if (Tasks.empty()) {
+            if (!InFlight.empty()) {
+                deliver(InFlight.front());
+                InFlight.pop_front();
+            }
+            continue;
+        }
+        if (InFlight.size() == NS) {  // ring full: the slot acquire() hands out is the oldest one
+            deliver(InFlight.front());
+            InFlight.pop_front();
+        }
+        std::size_t Idx;
+        evaluate::LeafPipeline::Slot& S = Pipe.acquire(&Idx);
+        uint32_t Off = 0;
+        uint64_t Moves = 0;
+        for (std::size_t I = 0; I < Tasks.size(); ++I) {
+            const Frame* F = Tasks[I];
+            F->Leaf.toRecord(&S.Positions[I], F->MaxPly, F->BlackDraw, F->WhiteDraw);  // stage 1 runs on the GPU
+            S.Hashes[I] = F->Leaf.Hash;
+            S.RowFlags[I] = nshogi::engine::selfplay::rowFlags(O.Gumbel, F->LeafNode == 0);  // frame.cc:116-118
+            S.MoveOffsets[I] = Off;
+            std::memcpy(S.MoveIndices + Off, F->LeafSlots, (std::size_t)F->NumLeafMoves * sizeof(uint16_t));
+            Off += (uint32_t)F->NumLeafMoves;
+            Moves += (uint64_t)F->NumLeafMoves;
+        }
+        S.MoveOffsets[Tasks.size()] = Off;
+        SI->LegalMoves.fetch_add(Moves, std::memory_order_relaxed);
+        SlotTasks[Idx].swap(Tasks);
+        Pipe.submit(Idx, SlotTasks[Idx].size(), /*FromPositions=*/true, NSB_DECODE_BOTH, /*UseCache=*/O.CacheMiB > 0, /*Ranked=*/true);
+        InFlight.push_back(Idx);
+    }
+    while (!InFlight.empty()) {  // Worker::stop contract: drain before returning
+        deliver(InFlight.front());
+        InFlight.pop_front();
+    }
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Options O;
+    for (int I = 1; I < argc; ++I) {
+        const std::string A = argv[I];
+        auto nextI = [&]() { return I + 1 < argc ? std::atoi(argv[++I]) : 0; };
+        auto nextD = [&]() { return I + 1 < argc ? std::atof(argv[++I]) : 0.0; };
+        if (A == "--channels") O.Channels = nextI();
+        else if (A == "--blocks") O.Blocks = nextI();
+        else if (A == "--batch-size") O.Batch = nextI();
+        else if (A == "--frame-pool-size") O.Frames = nextI();
+        else if (A == "--num-search-workers") O.SearchWorkers = nextI();
+        else if (A == "--slots") O.Slots = nextI();
+        else if (A == "--gpu") O.GPU = nextI();
+        else if (A == "--num-playouts") O.Playouts = nextI();
+        else if (A == "--full-search-ratio") O.FullSearchRatio = nextD();
+        else if (A == "--cache-mb") O.CacheMiB = nextI();
+        else if (A == "--gumbel") O.Gumbel = true;
+        else if (A == "--seconds") O.Seconds = nextD();
+        else if (A == "--warmup") O.Warmup = nextD();
+        else if (A == "--seed") O.Seed = (uint64_t)nextI();
+        else {
+            std::fprintf(stderr, "unknown option %s\n", A.c_str());
+            return 2;
+        }
+    }
+    if (nsb_device_count() <= O.GPU) {
+        std::fprintf(stderr, "nsb_selfplay_real: no CUDA device %d; infer::B200 has no CPU fallback\n", O.GPU);
+        return 2;
+    }
+    infer::B200 Exec(O.GPU, (uint16_t)O.Batch, NSB_FEATURE_CHANNELS, O.Channels, O.Blocks, O.Slots);
+    Exec.load("", O.Seed);
+    if (O.CacheMiB > 0) Exec.enableCache((std::size_t)O.CacheMiB);  // Frame::setEvaluationCache, frame.cc:89
+
+    std::vector<Frame> Pool((std::size_t)O.Frames);
+    FrameQueue SearchQueue, EvaluationQueue;
+    Info SI;
+    std::vector<Frame*> Init;
+    for (std::size_t I = 0; I < Pool.size(); ++I) {
+        Pool[I].MT.seed(0x9E3779B97F4A7C15ull * (I + 1) + (uint64_t)O.GPU * 0xD1B54A32D192ED03ull);
+        b200::game::newGame(O, Pool[I]);
+        b200::game::prepareRoot(O, Pool[I]);
+        Init.push_back(&Pool[I]);
+    }
+    SearchQueue.add(Init);
+
+    std::atomic<bool> Running{true};
+    std::vector<std::thread> Threads;
+    Threads.emplace_back(evaluationWorker, std::cref(O), &Exec, &EvaluationQueue, &SearchQueue, &SI, &Running);
+    for (int W = 0; W < O.SearchWorkers; ++W)
+        Threads.emplace_back(searchWorker, std::cref(O), &SearchQueue, &EvaluationQueue, &SI, &Running);
+
+    std::this_thread::sleep_for(std::chrono::duration<double>(O.Warmup));
+    const uint64_t E0 = SI.Evals.load(), B0 = SI.Batches.load(), R0 = SI.Records.load(), G0 = SI.Games.load();
+    const uint64_t H0 = SI.CacheHits.load(), T0n = SI.Terminals.load(), L0 = SI.LegalMoves.load();
+    const auto T0 = Clock::now();
+    std::this_thread::sleep_for(std::chrono::duration<double>(O.Seconds));
+    const uint64_t E1 = SI.Evals.load(), B1 = SI.Batches.load(), R1 = SI.Records.load(), G1 = SI.Games.load();
+    const uint64_t H1 = SI.CacheHits.load(), T1n = SI.Terminals.load(), L1 = SI.LegalMoves.load();
+    const double Sec = std::chrono::duration<double>(Clock::now() - T0).count();
+    Running.store(false);
+    SearchQueue.close();
+    EvaluationQueue.close();
+    for (auto& T : Threads) T.join();
+
+    uint64_t MaxDepthPly = 0;
+    for (const Frame& F : Pool) MaxDepthPly = std::max<uint64_t>(MaxDepthPly, F.Root.Ply);
+    const double Evals = (double)(E1 - E0), Batches = (double)(B1 - B0);
+    std::printf("{\"metric\": \"selfplay_positions_per_sec\", \"value\": %.1f, \"unit\": \"positions/s\", "
+                "\"leaf_evals_per_sec\": %.1f, \"games_per_sec\": %.3f, \"avg_batch\": %.1f, \"seconds\": %.3f, "
+                "\"records\": %llu, \"evals\": %llu, \"batches\": %llu, \"games\": %llu, "
+                "\"cache_mb\": %d, \"cache_hit_rate\": %.4f, \"terminal_leaves_per_eval\": %.4f, \"avg_legal_moves\": %.1f, "
+                "\"games_ended\": {\"mate\": %llu, \"repetition\": %llu, \"max_ply\": %llu}, \"deepest_game_ply\": %llu, "
+                "\"net\": \"%dx%d\", \"batch_size\": %d, \"frame_pool\": %d, \"search_workers\": %d, \"slots\": %d, "
+                "\"num_playouts\": %d, \"full_search_ratio\": %.2f, \"nan_rows\": %llu, "
+                "\"decode\": \"NSB_DECODE_BOTH + order_out (logits cached, probabilities and rank order out; %s)\", "
+                "\"rules\": \"real: host/rules/shogi.h (perft-pinned move generation, mate, four-fold repetition, max ply), "
+                "PUCT tree host/mcts_search.h; no df-pn, no declaration win\"}\n",
+                (double)(R1 - R0) / Sec, Evals / Sec, (double)(G1 - G0) / Sec, Batches > 0 ? Evals / Batches : 0.0, Sec,
+                (unsigned long long)(R1 - R0), (unsigned long long)(E1 - E0), (unsigned long long)(B1 - B0),
+                (unsigned long long)(G1 - G0), O.CacheMiB, Evals > 0 ? (double)(H1 - H0) / Evals : 0.0,
+                Evals > 0 ? (double)(T1n - T0n) / Evals : 0.0, Evals > 0 ? (double)(L1 - L0) / Evals : 0.0,
+                (unsigned long long)SI.Mates.load(), (unsigned long long)SI.Repetitions.load(), (unsigned long long)SI.MaxPlies.load(),
+                (unsigned long long)MaxDepthPly, O.Blocks, O.Channels, O.Batch, O.Frames, O.SearchWorkers, O.Slots, O.Playouts,
+                O.FullSearchRatio, (unsigned long long)SI.NanRows.load(),
+                O.Gumbel ? "Gumbel roots skip the softmax" : "Dirichlet mix at full-search roots on the host");
+    return 0;
+}

@@ -10,6 +10,7 @@ src/infer/trt.cc:144-161 = fp32 I/O, TF32 allowed):
 and against the bf16-emulating oracle (same rounding points; only the fp32 accumulation order differs, which can flip a
 bf16 rounding once in a while, and every flip is carried through the layers that follow):
     logits                        max |l - l_bf16|      <= TOL_LOGIT_BF16_PER_RMS * max(1, rms of the fp32 logits) * layers / 21
+    win rate, draw rate           max |v - v_bf16|      <= TOL_VALUE_BF16_AT_21_LAYERS * layers / 21
 The measured values are written to gpurun_out/drift_table.json (DESIGN.md §4 quotes them).  Seeds are chosen so that the
 value head is alive (a random-init 1-channel value conv is dead for about every second seed: then win / draw are
 constants and the value tolerance would be vacuous); the test asserts it."""
@@ -30,7 +31,7 @@ TOL_PROB_VS_FP32 = 2e-2
 TOL_KL_VS_FP32 = 1e-3
 TOL_VALUE_VS_FP32 = 1e-2
 TOL_LOGIT_BF16_PER_RMS = 3e-2     # at 21 layers and logits of rms <= 1 (the bound test_full_size_batch_invariance uses)
-TOL_VALUE_VS_BF16 = 6e-3
+TOL_VALUE_BF16_AT_21_LAYERS = 3e-3   # win / draw vs the bf16-emulating oracle, scaled by layers / 21 like the logits
 
 # (channels, blocks, weight seed, n, NSB_TRUNK128, slots)
 CASES = [
@@ -62,7 +63,7 @@ def _check(m, name):
     assert m["win_vs_fp32"] <= TOL_VALUE_VS_FP32 and m["draw_vs_fp32"] <= TOL_VALUE_VS_FP32, (name, m)
     tol_logit = TOL_LOGIT_BF16_PER_RMS * max(1.0, m["logit_rms_fp32"]) * m["layers"] / 21.0
     assert m["logit_vs_bf16"] <= tol_logit, (name, tol_logit, m)
-    assert m["value_vs_bf16"] <= TOL_VALUE_VS_BF16, (name, m)
+    assert m["value_vs_bf16"] <= TOL_VALUE_BF16_AT_21_LAYERS * m["layers"] / 21.0, (name, m)
 
 
 @pytest.mark.parametrize("channels,blocks,seed,n,kernel,slots", CASES)

@@ -130,3 +130,48 @@ def test_infer_contract_on_plain_buffers_is_page_locked_by_the_executor(built):
         assert line["ok"] and line["io_mode"] == "direct"
         rates[bool(flag)] = line["infer_blocking_evals_per_s"]
     assert rates[True] > 0.9 * rates[False]      # page-locked by the executor == allocated page-locked
+
+
+def test_real_rules_harnesses_fail_loudly_without_gpu(built, nb):
+    if nb.device_count() > 0:
+        pytest.skip("GPU present")
+    for exe in ("nsb_selfplay_real", "nsb_usi_go_bench"):
+        out = subprocess.run([os.path.join(built, exe)], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 2 and "no CPU fallback" in out.stderr
+
+
+def test_shogi_rules_perft5_cpu(built):
+    """host/rules/shogi.h against the public perft counts of the start position up to depth 5 (19,861,490 leaves) -
+    the known answers that pin the move generator the search / self-play harnesses run on."""
+    out = subprocess.run([os.path.join(built, "nsb_host_unit"), "--perft", "5"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_selfplay_real_rules_gpu(built):
+    """Self-play with real rules and a real MCTS (host/selfplay_real.cc) on a small net: records are produced, every
+    evaluated leaf has a plausible number of legal moves, no NaN rows, games progress; and with the device cache
+    (raw logits stored, probabilities served: NSB_DECODE_BOTH) transpositions hit."""
+    base = [os.path.join(built, "nsb_selfplay_real"), "--channels", "128", "--blocks", "2", "--batch-size", "128",
+            "--frame-pool-size", "256", "--num-search-workers", "2", "--num-playouts", "16", "--seconds", "1.5", "--warmup", "0.5"]
+    out = subprocess.run(base, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["nan_rows"] == 0 and rec["evals"] > 5000 and rec["records"] > 300
+    assert 15.0 <= rec["avg_legal_moves"] <= 200.0 and rec["rules"].startswith("real")
+    assert 2.0 <= rec["evals"] / rec["records"] <= 20.0          # 16 playouts on full searches, 4 otherwise, + the root
+    out = subprocess.run(base + ["--cache-mb", "64"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["nan_rows"] == 0 and rec["cache_hit_rate"] > 0.02   # early-game transpositions across 256 games from hirate
+
+
+@pytest.mark.gpu
+def test_usi_go_bench_gpu(built):
+    """One search tree from the start position with batched leaves under virtual loss (host/usi_go_bench.cc)."""
+    out = subprocess.run([os.path.join(built, "nsb_usi_go_bench"), "--channels", "128", "--blocks", "2", "--batch-size", "128",
+                          "--seconds", "1.0"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["nodes"] > 5000 and rec["value"] > 5000 and rec["avg_batch"] > 8 and len(rec["pv"].split()) >= 2
+    assert 0.0 < rec["root_win_rate"] < 1.0 and 20.0 <= rec["avg_legal_moves"] <= 120.0
