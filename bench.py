@@ -483,11 +483,8 @@ def run_b200(args):
         "per_step_ms": [round(x, 3) for x in per_step] if per_step and len(per_step) <= 64 else None,
         "counters": counters,
     }
-    if args.config == 3 and latency:
-        # USI nps (src/protocol/usilogger.cc:46) = visited nodes / s; the executor bounds it from above by
-        # evals/s / (1 - cache-hit fraction - terminal fraction); the search needs libnshogi
-        line["usi_nps_estimate"] = {"leaf_evals_per_s": round(value, 1), "one_batch_in_flight_evals_per_s": latency["evals_per_s_one_in_flight"],
-                                    "formula": "nps ~= evals/s / (1 - cache_hit - terminal); not measured: no rules library"}
+    if args.config == 3 and world == 1 and not args.no_selfplay:
+        line["usi_go"] = usi_leg(args, info)   # measured nodes/s of a real search from the start position
     if selfplay is not None:
         line["selfplay"] = selfplay
     if info.rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -525,13 +522,13 @@ def batch_sweep(args, nb, synth, rep, desc, blob, gpu, info, tf_burst, tf_sust):
 
 def selfplay_leg(args, info, rep, device):
     """BASELINE.json's second metric, "self-play positions/sec" (configs[3]: 20x256 net, 1024 concurrent
-    games per GPU): the C++ self-play loop of nshogi-engine_b200/host/selfplay_sim.cc (frame pool, search
-    workers, pinned multi-slot evaluation worker) against infer::B200, one process per GPU, counters
-    summed over ranks.  Rules are synthetic (libnshogi is not available); the GPU path is the real one."""
-    exe = os.path.join(ROOT, "nshogi-engine_b200", "host", "nsb_selfplay_sim")
+    games per GPU): the C++ self-play loop of nshogi-engine_b200/host/selfplay_real.cc (frame pool, search
+    workers running a PUCT search on real shogi rules - host/rules/shogi.h, perft-pinned -, pinned multi-slot
+    evaluation worker) against infer::B200, one process per GPU, counters summed over ranks."""
+    exe = os.path.join(ROOT, "nshogi-engine_b200", "host", "nsb_selfplay_real")
     if not os.path.exists(exe):
-        return {"unavailable": "nsb_selfplay_sim not built"}
-    workers = max(2, min(8, (os.cpu_count() or 4) // max(1, info.world) - 1))
+        return {"unavailable": "nsb_selfplay_real not built"}
+    workers = max(2, min(14, (os.cpu_count() or 4) // max(1, info.world) - 2))
     cmd = [exe, "--gpu", str(info.local_rank), "--channels", "256", "--blocks", "20", "--batch-size", "512",
            "--frame-pool-size", "1024", "--num-search-workers", str(workers), "--seconds", str(args.selfplay_seconds),
            "--warmup", "1.5"]
@@ -558,7 +555,28 @@ def selfplay_leg(args, info, rep, device):
             "config": {"workload": "self-play data generation, 20x256 ResNet, 1024 concurrent games per GPU",
                        "batch_size": 512, "num_playouts": rec["num_playouts"], "full_search_ratio": rec["full_search_ratio"],
                        "search_workers_per_gpu": workers, "slots": rec["slots"], "rules": rec["rules"],
-                       "decode": rec.get("decode")}}
+                       "decode": rec.get("decode"), "avg_legal_moves": rec.get("avg_legal_moves"),
+                       "terminal_leaves_per_eval": rec.get("terminal_leaves_per_eval")}}
+
+
+def usi_leg(args, info):
+    """BASELINE configs[2], "USI go from hirate startpos, 20-block 256-ch ResNet, batch 512, 1xB200 nodes/sec": one
+    search tree from the start position (host/usi_go_bench.cc: real rules, PUCT with virtual loss, search threads
+    filling the pinned batch in place, fused MCTS decode with rank order).  nps as src/protocol/usilogger.cc:46."""
+    exe = os.path.join(ROOT, "nshogi-engine_b200", "host", "nsb_usi_go_bench")
+    if not os.path.exists(exe) or info.rank != 0:
+        return None
+    threads = max(1, min(8, (os.cpu_count() or 4) - 2))
+    out = {}
+    for name, extra in (("search_threads_2_reference_default", ["--num-search-threads", "2"]),
+                        (f"search_threads_{threads}", ["--num-search-threads", str(threads)])):
+        try:
+            r = subprocess.run([exe, "--gpu", str(info.local_rank), "--channels", str(args.channels), "--blocks", str(args.blocks),
+                                "--batch-size", str(args.batch), "--seconds", "4"] + extra, capture_output=True, text=True, timeout=120)
+            out[name] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"unavailable": r.stderr.strip()[-200:]}
+        except (OSError, subprocess.SubprocessError, ValueError, IndexError) as e:
+            out[name] = {"unavailable": repr(e)}
+    return out
 
 
 def cpu_path_rate(orc, synth, B, threads, seconds):

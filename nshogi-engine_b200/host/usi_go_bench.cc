@@ -8,20 +8,24 @@
 //
 // Reference structure: SearchWorker::doTask (src/mcts/searchworker.cc:448-609: collectOneLeaf -> terminal checks ->
 // EvalCache load -> EvaluationQueue::add), EvaluationWorker (src/mcts/evaluationworker.cc:105-199), FeedWorker
-// (src/mcts/feedworker.cc:29-137).  Here one collector thread does the three roles around the slot ring: while a batch is
-// on the GPU it descends the tree for the next one (the virtual losses of the batch in flight steer it elsewhere).  Rules:
-// host/rules/shogi.h; tree: host/mcts_search.h (no df-pn, no declaration win, no tree-parallel search threads: the
-// number printed is one collector thread's, and it says whether the CPU or the GPU was the limit).
+// (src/mcts/feedworker.cc:29-137).  Here: --num-search-threads search threads (default 2, context.h:74) descend the
+// shared tree under virtual loss, generate the leaf's moves and write its row IN PLACE into the open pinned batch
+// (host/leaf_queue.h: no queue of tuples, no copy); one evaluation thread seals and submits batches and feeds the
+// results of the slot it is about to reuse.  Rules: host/rules/shogi.h; tree: host/mcts_search.h behind one mutex (no
+// df-pn, no declaration win).
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "infer_b200.h"
 #include "leaf_pipeline.h"
+#include "leaf_queue.h"
 #include "mcts_search.h"
 #include "rules/shogi.h"
 
@@ -30,7 +34,7 @@ using namespace nshogi::engine::b200;
 using Clock = std::chrono::steady_clock;
 
 int main(int argc, char** argv) {
-    int Channels = 256, Blocks = 20, Batch = 512, Slots = 3, GPU = 0, CacheMiB = 0, MaxCollisions = 64;
+    int Channels = 256, Blocks = 20, Batch = 512, Slots = 3, GPU = 0, CacheMiB = 0, SearchThreads = 2;
     double Seconds = 5.0;
     uint64_t Seed = 1234;
     for (int I = 1; I < argc; ++I) {
@@ -42,7 +46,7 @@ int main(int argc, char** argv) {
         else if (A == "--slots") Slots = nextI();
         else if (A == "--gpu") GPU = nextI();
         else if (A == "--cache-mb") CacheMiB = nextI();
-        else if (A == "--max-collisions") MaxCollisions = nextI();
+        else if (A == "--num-search-threads") SearchThreads = nextI();  // context.h:74 default 2
         else if (A == "--seed") Seed = (uint64_t)nextI();
         else if (A == "--seconds") Seconds = I + 1 < argc ? std::atof(argv[++I]) : 0.0;
         else {
@@ -54,114 +58,124 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "nsb_usi_go_bench: no CUDA device %d; infer::B200 has no CPU fallback\n", GPU);
         return 2;
     }
+    if (SearchThreads < 1) SearchThreads = 1;
     infer::B200 Exec(GPU, (uint16_t)Batch, NSB_FEATURE_CHANNELS, Channels, Blocks, Slots);
     Exec.load("", Seed);
     if (CacheMiB > 0) Exec.enableCache((std::size_t)CacheMiB);  // Manager's EvalCache, manager.cc:202-206
     Exec.resetGPU();
     Exec.bindThreadToGpuNode();
     evaluate::LeafPipeline Pipe(&Exec, (std::size_t)Batch);
+    evaluate::LeafQueue Queue(&Pipe);  // lock-free in-place batch assembly by the search threads (EvaluationQueue + getBatch)
     const std::size_t NS = Pipe.numSlots();
 
-    rules::Position Root;  // hirate
-    std::vector<uint64_t> History{Root.Hash}, Path;
-    search::Tree T;
+    const rules::Position Root;  // hirate
+    const std::vector<uint64_t> History{Root.Hash};
+    search::Tree T;              // shared by the search threads and the feeding thread under TreeMu (the reference's
+    std::mutex TreeMu;           // tree is lock-free, node.h:59-100; selection and back-propagation are short)
     T.reset();
     T.Nodes.reserve(1u << 21);
     T.Edges.reserve(1u << 25);
     const uint16_t MaxPly = 320;  // StateConfig default of the USI front-end
-    std::vector<std::vector<int>> SlotNodes(NS);
-    std::deque<std::size_t> InFlight;
-    uint64_t Evals = 0, Batches = 0, Terminals = 0, Collisions = 0, CacheHits = 0, LegalMoves = 0, GpuWaitNs = 0;
+    std::atomic<uint64_t> Terminals{0}, Collisions{0}, LegalMoves{0};
+    uint64_t Evals = 0, Batches = 0, CacheHits = 0, GpuWaitNs = 0;
+    std::atomic<bool> Running{true};
 
-    auto deliver = [&](std::size_t Idx) {
-        const auto W0 = Clock::now();
-        evaluate::LeafPipeline::Slot& S = Pipe.collect(Idx);
-        GpuWaitNs += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - W0).count();
-        const std::vector<int>& Ns = SlotNodes[Idx];
-        for (std::size_t I = 0; I < Ns.size(); ++I) {  // FeedWorker::feedResult, feedworker.cc:56-137
-            const uint32_t B = S.MoveOffsets[I];
-            T.setPriors(Ns[I], S.Legal + B, S.Order + B);
-            T.backup(Ns[I], S.WinRate[I], S.DrawRate[I]);
-            if (CacheMiB > 0 && S.HitFlag[I]) ++CacheHits;
-        }
-        Evals += Ns.size();
-        ++Batches;
-        SlotNodes[Idx].clear();
+    // FeedWorker::feedResult (feedworker.cc:56-137) for one row of a collected slot: the gather, the softmax and
+    // Node::sort's permutation came back from the GPU; setEvaluation + updateAncestors are what is left
+    auto feed = [&](evaluate::LeafPipeline::Slot& S, std::size_t Row, void* User) {
+        const int Node = (int)(uintptr_t)User - 1;
+        const uint32_t B = S.MoveOffsets[Row];
+        std::lock_guard<std::mutex> L(TreeMu);
+        T.setPriors(Node, S.Legal + B, S.Order + B);
+        T.backup(Node, S.WinRate[Row], S.DrawRate[Row]);
+        if (CacheMiB > 0 && S.HitFlag[Row]) ++CacheHits;
+        ++Evals;
     };
 
-    rules::Move Moves[rules::kMaxMoves];
-    const auto T0 = Clock::now();
-    auto elapsed = [&]() { return std::chrono::duration<double>(Clock::now() - T0).count(); };
-    std::size_t NextSlot = 0;  // the ring advances only when a batch is submitted
-    while (elapsed() < Seconds) {
-        if (InFlight.size() == NS) {
-            deliver(InFlight.front());
-            InFlight.pop_front();
-        }
-        const std::size_t Idx = NextSlot;
-        evaluate::LeafPipeline::Slot& S = Pipe.slotAt(Idx);  // (free: at most NS - 1 batches are in flight here)
-        std::vector<int>& Ns = SlotNodes[Idx];
-        uint32_t Off = 0;
-        int Failed = 0;
-        while ((int)Ns.size() < Batch && Failed < MaxCollisions) {
+    // SearchWorker::doTask (searchworker.cc:448-609)
+    auto searchThread = [&]() {
+        rules::Move Moves[rules::kMaxMoves];
+        uint16_t Slots_[rules::kMaxMoves];
+        std::vector<uint64_t> Path;
+        while (Running.load(std::memory_order_relaxed)) {
             rules::Position Pos = Root;
             Path.clear();
-            const int Node = T.selectLeaf(Pos, 0.5f, 0.5f, &Path);  // SearchWorker::collectOneLeaf
-            if (Node < 0) {                                         // ran into a leaf that is being evaluated
-                ++Failed;
-                ++Collisions;
+            int Node;
+            {
+                std::lock_guard<std::mutex> L(TreeMu);
+                Node = T.selectLeaf(Pos, 0.5f, 0.5f, &Path);  // collectOneLeaf; leaves a virtual loss on the path
+                if (Node >= 0) {
+                    const search::Node& N = T.Nodes[(std::size_t)Node];
+                    if (N.Term == search::Mated) {
+                        T.backup(Node, 0.0f, 0.0f);
+                        continue;
+                    }
+                    if (N.Term == search::DrawnGame) {
+                        T.backup(Node, 0.5f, 1.0f);
+                        continue;
+                    }
+                }
+            }
+            if (Node < 0) {  // ran into a leaf that is being evaluated (searchworker.cc:349-357)
+                Collisions.fetch_add(1, std::memory_order_relaxed);
+                std::this_thread::yield();
                 continue;
             }
-            search::Node& N = T.Nodes[(std::size_t)Node];
-            if (N.Term == search::Mated) {
-                T.backup(Node, 0.0f, 0.0f);
-                continue;
-            }
-            if (N.Term == search::DrawnGame) {
-                T.backup(Node, 0.5f, 1.0f);
-                continue;
-            }
-            const int NumMoves = Pos.generateLegal(Moves);          // expandLeaf, searchworker.cc:164-173
-            if (NumMoves == 0) {                                    // terminal checks, :475-538
-                N.Term = search::Mated;
+            const int NumMoves = Pos.generateLegal(Moves);  // expandLeaf, :164-173 - outside the lock
+            const bool Mated = NumMoves == 0;
+            const bool Drawn = !Mated && Node != 0 && (search::isFourfold(Pos.Hash, History, Path) || Pos.Ply >= MaxPly);
+            if (Mated || Drawn) {  // terminal checks, :475-538
+                std::lock_guard<std::mutex> L(TreeMu);
+                search::Node& N = T.Nodes[(std::size_t)Node];
+                N.Term = Mated ? search::Mated : search::DrawnGame;
                 N.Evaluated = true;
-                ++Terminals;
-                T.backup(Node, 0.0f, 0.0f);
+                T.backup(Node, Mated ? 0.0f : 0.5f, Mated ? 0.0f : 1.0f);
+                Terminals.fetch_add(1, std::memory_order_relaxed);
                 continue;
             }
-            if (Node != 0 && (search::isFourfold(Pos.Hash, History, Path) || Pos.Ply >= MaxPly)) {
-                N.Term = search::DrawnGame;
-                N.Evaluated = true;
-                ++Terminals;
-                T.backup(Node, 0.5f, 1.0f);
-                continue;
+            for (int J = 0; J < NumMoves; ++J) Slots_[J] = (uint16_t)Pos.policyIndex(Moves[J]);  // ml::getMoveIndex
+            {
+                std::lock_guard<std::mutex> L(TreeMu);
+                T.expand(Node, Moves, NumMoves);
             }
-            T.expand(Node, Moves, NumMoves);
-            const std::size_t Row = Ns.size();
-            Pos.toRecord(&S.Positions[Row], MaxPly, 0.5f, 0.5f);    // stage 1 runs on the GPU
-            S.Hashes[Row] = Pos.Hash;
-            S.MoveOffsets[Row] = Off;
-            for (int J = 0; J < NumMoves; ++J) S.MoveIndices[Off + (uint32_t)J] = (uint16_t)Pos.policyIndex(Moves[J]);
-            Off += (uint32_t)NumMoves;
-            LegalMoves += (uint64_t)NumMoves;
-            Ns.push_back(Node);
-        }
-        if (Ns.empty()) {  // everything reachable is in flight: wait for the oldest batch
-            if (!InFlight.empty()) {
-                deliver(InFlight.front());
-                InFlight.pop_front();
+            evaluate::LeafQueue::Ticket Tk;
+            while (!Queue.reserve((uint16_t)NumMoves, (void*)(uintptr_t)(Node + 1), &Tk)) {  // EvaluationQueue::add, evaluationqueue.cc:45-60
+                if (!Running.load(std::memory_order_relaxed)) break;
+                std::this_thread::yield();
             }
-            continue;
+            if (Tk.S == nullptr) break;  // shutting down with the leaf unqueued: its virtual loss dies with the tree
+            Pos.toRecord(&Tk.S->Positions[Tk.Row], MaxPly, 0.5f, 0.5f);  // stage 1 runs on the GPU
+            Tk.S->Hashes[Tk.Row] = Pos.Hash;
+            std::memcpy(Tk.S->MoveIndices + Tk.MoveBegin, Slots_, (std::size_t)NumMoves * sizeof(uint16_t));
+            LegalMoves.fetch_add((uint64_t)NumMoves, std::memory_order_relaxed);
+            Queue.publish(Tk);
         }
-        S.MoveOffsets[Ns.size()] = Off;
-        Pipe.submit(Idx, Ns.size(), /*FromPositions=*/true, NSB_DECODE_PROBS, /*UseCache=*/CacheMiB > 0, /*Ranked=*/true);
-        InFlight.push_back(Idx);
-        NextSlot = (NextSlot + 1) % NS;
+    };
+
+    Queue.open(feed);
+    std::vector<std::thread> Threads;
+    const auto T0 = Clock::now();
+    auto elapsed = [&]() { return std::chrono::duration<double>(Clock::now() - T0).count(); };
+    for (int I = 0; I < SearchThreads; ++I) Threads.emplace_back(searchThread);
+    // EvaluationWorker::doTask (evaluationworker.cc:105-199): a batch goes out when it is full, or - like the
+    // reference's "whatever is queued" - when rows are waiting and nothing has been submitted for a moment
+    auto LastSubmit = Clock::now();
+    while (elapsed() < Seconds) {
+        const std::size_t Rows = Queue.openRows();
+        const double IdleUs = std::chrono::duration<double, std::micro>(Clock::now() - LastSubmit).count();
+        if (Rows >= (std::size_t)Batch || (Rows > 0 && IdleUs > 150.0)) {
+            const auto W0 = Clock::now();
+            Queue.submitOpen(/*FromPositions=*/true, NSB_DECODE_PROBS, /*UseCache=*/CacheMiB > 0, /*Ranked=*/true, feed);
+            GpuWaitNs += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - W0).count();
+            ++Batches;
+            LastSubmit = Clock::now();
+        } else {
+            std::this_thread::yield();
+        }
     }
-    while (!InFlight.empty()) {
-        deliver(InFlight.front());
-        InFlight.pop_front();
-    }
+    Running.store(false);
+    for (auto& Th : Threads) Th.join();
+    Queue.drain(true, NSB_DECODE_PROBS, CacheMiB > 0, true, feed);
     const double Sec = elapsed();
 
     // usilogger.cc:29-65: nodes = visits of the root, nps, pv by most-visited edges
@@ -196,13 +210,13 @@ int main(int argc, char** argv) {
     const double RootWin = Nodes ? T.Nodes[0].WinAcc / (double)Nodes : 0.0;
     std::printf("{\"metric\": \"usi_go_nodes_per_sec\", \"value\": %.1f, \"unit\": \"nodes/s\", \"nodes\": %llu, \"time_ms\": %.0f, "
                 "\"leaf_evals_per_sec\": %.1f, \"avg_batch\": %.1f, \"batches\": %llu, \"terminal_leaves\": %llu, \"collisions\": %llu, "
-                "\"cache_mb\": %d, \"cache_hit_rate\": %.4f, \"avg_legal_moves\": %.1f, \"tree_nodes\": %zu, \"gpu_wait_fraction\": %.3f, "
+                "\"cache_mb\": %d, \"cache_hit_rate\": %.4f, \"avg_legal_moves\": %.1f, \"tree_nodes\": %zu, \"submit_and_feed_fraction\": %.3f, "
                 "\"root_win_rate\": %.4f, \"pv\": \"%s\", \"net\": \"%dx%d\", \"batch_size\": %d, \"slots\": %d, "
-                "\"position\": \"hirate startpos\", \"search_threads\": 1, "
+                "\"position\": \"hirate startpos\", \"search_threads\": %d, "
                 "\"rules\": \"real: host/rules/shogi.h + host/mcts_search.h (PUCT, virtual loss); no df-pn, no declaration win\"}\n",
                 (double)Nodes / Sec, (unsigned long long)Nodes, Sec * 1e3, (double)Evals / Sec, Batches ? (double)Evals / (double)Batches : 0.0,
-                (unsigned long long)Batches, (unsigned long long)Terminals, (unsigned long long)Collisions, CacheMiB,
-                Evals ? (double)CacheHits / (double)Evals : 0.0, Evals ? (double)LegalMoves / (double)Evals : 0.0, T.Nodes.size(),
-                (double)GpuWaitNs * 1e-9 / Sec, RootWin, PV.c_str(), Blocks, Channels, Batch, (int)NS);
+                (unsigned long long)Batches, (unsigned long long)Terminals.load(), (unsigned long long)Collisions.load(), CacheMiB,
+                Evals ? (double)CacheHits / (double)Evals : 0.0, Evals ? (double)LegalMoves.load() / (double)Evals : 0.0, T.Nodes.size(),
+                (double)GpuWaitNs * 1e-9 / Sec, RootWin, PV.c_str(), Blocks, Channels, Batch, (int)NS, SearchThreads);
     return 0;
 }
