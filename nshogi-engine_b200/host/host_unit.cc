@@ -133,6 +133,7 @@ struct FakePipeline {
     Slot& acquire(std::size_t* K) { *K = Next; Next = (Next + 1) % Slots.size(); return Slots[*K]; }
     void submit(std::size_t K, std::size_t Rows, bool, int, bool, bool) { Slots[K].Count = Rows; ++Batches; }
     Slot& collect(std::size_t K) { return Slots[K]; }
+    bool ready(std::size_t) const { return true; }
 };
 
 static int queueStress(int Threads, std::size_t Leaves) {

@@ -101,6 +101,21 @@ class BasicLeafQueue {
         return Rows;
     }
 
+    // Evaluation thread: feed every submitted batch whose results have arrived, without waiting for the ring to come
+    // round to its slot.  A tree search needs this - its next leaves depend on the results (the reference's FeedWorkers
+    // run as soon as a batch is done, feedworker.cc:29-39); independent leaves (self-play frames) can do without.
+    // Returns the number of rows fed.
+    template <typename Feed>
+    std::size_t pollFeed(Feed&& FeedRow) {
+        std::size_t Fed = 0;
+        for (std::size_t K = 0; K < Pipe->numSlots(); ++K) {
+            if (K == OpenIndex || Counts[K] == 0 || !Pipe->ready(K)) continue;
+            Fed += Counts[K];
+            feedSlot(K, FeedRow);
+        }
+        return Fed;
+    }
+
     // Evaluation thread, after the search threads have stopped: submit what is open, collect and feed everything.
     template <typename Feed>
     void drain(bool FromPositions, int DecodeMode, bool UseCache, bool Ranked, Feed&& FeedRow) {

@@ -14,7 +14,8 @@
 //   - back-propagation: updateAncestors, the win rate flips at every level, the draw rate does not (node.h:170-202).
 // What it leaves out: mate-distance propagation / df-pn (searchworker.cc:220-240,361-424), tree reuse between moves
 // and the garbage collector (tree.cc:31-94), lock-free sharing of one tree by several threads (a tree here belongs
-// to one thread at a time: a self-play frame, or the single collector thread of the USI-style harness).
+// to one thread at a time - a self-play frame - or is shared under one mutex: the USI-style harness, whose search
+// threads hold it for the descent and the back-propagation only, not for move generation).
 #ifndef NSHOGI_ENGINE_B200_MCTS_SEARCH_H
 #define NSHOGI_ENGINE_B200_MCTS_SEARCH_H
 
@@ -73,7 +74,7 @@ class Tree {
         for (;;) {
             Node& N = Nodes[Cur];
             if (!N.Evaluated || N.Term != Open) {
-                if (!N.Evaluated && N.VirtualLoss > 0 && N.Visits == 0 && Cur != 0) return abandon();  // in flight
+                if (!N.Evaluated && N.VirtualLoss > 0) return abandon();  // its evaluation is in flight (the root's too)
                 break;
             }
             const float DrawValue = Pos.Side == 0 ? BlackDraw : WhiteDraw;

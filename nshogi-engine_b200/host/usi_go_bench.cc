@@ -169,7 +169,7 @@ int main(int argc, char** argv) {
             GpuWaitNs += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - W0).count();
             ++Batches;
             LastSubmit = Clock::now();
-        } else {
+        } else if (Queue.pollFeed(feed) == 0) {  // FeedWorker::doTask: results go back into the tree as soon as they exist
             std::this_thread::yield();
         }
     }
