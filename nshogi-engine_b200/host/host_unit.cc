@@ -371,10 +371,10 @@ static int selfplayMock(int Games, int Playouts) {
     uint64_t Evals = 0;
     while ((int)SI.Games.load() < Games) {
         const uint64_t GamesBefore = SI.Games.load(), RecordsBefore = SI.Records.load();
-        const uint32_t RootVisitsBefore = F.Tree.Nodes[0].Visits;
+        const uint32_t RootVisitsBefore = F.Tree.node(0).Visits;
         game::advance(O, F, &SI);
         if (SI.Games.load() != GamesBefore) F.MaxPly = 60;  // (newGame drew a long one)
-        if (SI.Records.load() == RecordsBefore && F.LeafNode != 0) CHECK(F.Tree.Nodes[0].Visits >= RootVisitsBefore);
+        if (SI.Records.load() == RecordsBefore && F.LeafNode != 0) CHECK(F.Tree.node(0).Visits >= RootVisitsBefore);
         // the frame now waits for an evaluation of F.Leaf with F.NumLeafMoves legal moves
         CHECK(F.NumLeafMoves >= 1 && F.NumLeafMoves <= rules::kMaxMoves && F.LeafNode >= 0);
         rules::Move Check[rules::kMaxMoves];
@@ -396,14 +396,17 @@ static int selfplayMock(int Games, int Playouts) {
         game::applyEvaluation(O, F, Row.data(), Order.data(), Win, Draw);
         ++Evals;
         // tree invariants after the back-propagation
-        const search::Node& R = F.Tree.Nodes[0];
+        const search::Node& R = F.Tree.node(0);
         uint64_t ChildVisits = 0;
         for (int I = 0; I < R.NumEdges; ++I) {
-            const search::Edge& E = F.Tree.Edges[(size_t)R.EdgeBegin + (size_t)I];
-            if (I > 0) CHECK(E.P <= F.Tree.Edges[(size_t)R.EdgeBegin + (size_t)I - 1].P);   // sorted by prior
-            if (E.Child >= 0) ChildVisits += F.Tree.Nodes[(size_t)E.Child].Visits;
+            const search::Edge& E = F.Tree.edgesOf(0)[I];
+            if (I > 0) CHECK(E.P <= F.Tree.edgesOf(0)[I - 1].P);   // sorted by prior
+            if (E.Child >= 0) {
+                CHECK(E.CVisits == F.Tree.node(E.Child).Visits && E.CVirtualLoss == 0);   // the edge mirrors its child
+                ChildVisits += F.Tree.node(E.Child).Visits;
+            }
         }
-        CHECK(R.Evaluated && R.Visits == ChildVisits + 1 && R.VirtualLoss == 0);
+        CHECK(R.evaluated() && R.Visits == ChildVisits + 1 && R.VirtualLoss == 0);
         CHECK(R.WinAcc >= 0.0 && R.WinAcc <= (double)R.Visits);
         CHECK(R.Visits <= (uint32_t)Playouts + 1);
     }
@@ -414,7 +417,85 @@ static int selfplayMock(int Games, int Playouts) {
     return 0;
 }
 
+// ---- mcts_search.h shared tree: `--tree-stress THREADS NODES` (also built with -fsanitize=thread by the tests) ------
+// Search threads descend, claim, expand, "evaluate" (a hash of the position), publish and back-propagate concurrently on
+// one lock-free tree of real shogi positions.  Afterwards: no virtual loss is left anywhere, the root's visits are its
+// children's + 1, every edge mirrors its child exactly, every evaluated node has sorted priors.
+static int treeStress(int Threads, std::size_t Nodes) {
+    using namespace b200;
+    const std::size_t Cap = Nodes + Nodes / 2 + 64 * (std::size_t)Threads + 1024;  // (terminal nodes and children created twice take slots too)
+    search::Tree T(Cap, Cap * 64);
+    const rules::Position Root;
+    const std::vector<uint64_t> History{Root.Hash};
+    std::atomic<uint64_t> Done{0}, Collisions{0};
+    std::atomic<bool> Full{false};
+    std::vector<std::thread> Th;
+    for (int Id = 0; Id < Threads; ++Id)
+        Th.emplace_back([&]() {
+            rules::Move Moves[rules::kMaxMoves];
+            std::vector<uint64_t> Path;
+            std::vector<int> Trail;
+            std::vector<float> Row(rules::kMaxMoves);
+            std::vector<uint16_t> Order(rules::kMaxMoves);
+            while (Done.load(std::memory_order_relaxed) < Nodes && !Full.load(std::memory_order_relaxed)) {
+                rules::Position Pos = Root;
+                Path.clear();
+                const int Node = T.selectLeaf(Pos, 0.5f, 0.5f, &Path, &Trail);
+                if (Node == search::Tree::OutOfMemory) { Full.store(true); break; }
+                if (Node < 0) { Collisions.fetch_add(1, std::memory_order_relaxed); std::this_thread::yield(); continue; }
+                if (T.node(Node).Term != search::Open) { T.backup(Node, T.node(Node).Term == search::Mated ? 0.f : 0.5f, T.node(Node).Term == search::Mated ? 0.f : 1.f); continue; }
+                const int N = Pos.generateLegal(Moves);
+                if (N == 0 || (Node != 0 && (search::isFourfold(Pos.Hash, History, Path) || Pos.Ply >= 60))) {
+                    T.setTerminal(Node, N == 0 ? search::Mated : search::DrawnGame);
+                    T.backup(Node, N == 0 ? 0.f : 0.5f, N == 0 ? 0.f : 1.f);
+                    continue;
+                }
+                if (!T.expand(Node, Moves, N)) { Full.store(true); break; }
+                double Sum = 0.0;
+                uint64_t H = Pos.Hash;
+                for (int J = 0; J < N; ++J) {
+                    H = H * 6364136223846793005ull + (uint64_t)J;
+                    Sum += (Row[(size_t)J] = 1.0f + (float)((H >> 40) % 1000) / 250.0f);
+                    Order[(size_t)J] = (uint16_t)J;
+                }
+                for (int J = 0; J < N; ++J) Row[(size_t)J] = (float)(Row[(size_t)J] / Sum);
+                std::stable_sort(Order.begin(), Order.begin() + N, [&](uint16_t A, uint16_t B) { return Row[A] > Row[B]; });
+                T.setPriors(Node, Row.data(), Order.data());
+                T.backup(Node, 0.3f + 0.4f * (float)((Pos.Hash >> 20) % 1000) / 1000.0f, 0.05f);
+                Done.fetch_add(1, std::memory_order_relaxed);
+            }
+        });
+    for (auto& X : Th) X.join();
+    bool Ok = !Full.load();
+    uint64_t Evaluated = 0, ChildVisits = 0;
+    for (std::size_t I = 0; I < T.numNodes() && Ok; ++I) {
+        const search::Node& N = T.node((int)I);
+        Ok = Ok && N.VirtualLoss == 0;
+        if (!N.evaluated()) { Ok = Ok && N.Visits == 0; continue; }   // a child another thread created first and nobody used
+        ++Evaluated;
+        uint64_t Sum = 0;
+        for (int J = 0; J < N.NumEdges && Ok; ++J) {
+            const search::Edge& E = T.edgesOf((int)I)[J];
+            if (J > 0) Ok = Ok && E.P <= T.edgesOf((int)I)[J - 1].P;
+            if (E.Child >= 0) {
+                const search::Node& C = T.node(E.Child);
+                Ok = Ok && C.Parent == (int)I && E.CVisits == C.Visits && E.CVirtualLoss == 0 && std::fabs((double)E.CWinAcc - C.WinAcc) < 1e-2 * (1.0 + C.WinAcc);
+                Sum += C.Visits;
+            } else {
+                Ok = Ok && E.CVisits == 0;
+            }
+        }
+        if (N.Term == search::Open) Ok = Ok && N.Visits == Sum + 1;
+        if (I == 0) ChildVisits = Sum;
+    }
+    std::printf("tree stress: %llu evaluations by %d threads, %zu nodes (%llu evaluated), root visits %u = %llu + 1, %llu collisions: %s\n",
+                (unsigned long long)Done.load(), Threads, T.numNodes(), (unsigned long long)Evaluated, T.node(0).Visits,
+                (unsigned long long)ChildVisits, (unsigned long long)Collisions.load(), Ok ? "ok" : "FAIL");
+    return Ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 4 && std::strcmp(argv[1], "--tree-stress") == 0) return treeStress(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]));
     if (argc >= 3 && std::strcmp(argv[1], "--perft") == 0) return rulesChecks(std::atoi(argv[2]));
     if (argc >= 4 && std::strcmp(argv[1], "--queue-stress") == 0) return queueStress(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]));
     if (argc >= 4 && std::strcmp(argv[1], "--onnx-blob") == 0) return onnxBlob(argv[2], argv[3]);

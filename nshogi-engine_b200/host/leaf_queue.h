@@ -82,6 +82,13 @@ class BasicLeafQueue {
         Published.fetch_add(1, std::memory_order_release);
     }
 
+    // Evaluation thread: submitted batches whose rows have not been fed yet.
+    std::size_t inFlight() const {
+        std::size_t N = 0;
+        for (std::size_t K = 0; K < Counts.size(); ++K) N += (K != OpenIndex && Counts[K] > 0) ? 1 : 0;
+        return N;
+    }
+
     std::size_t openRows() const {
         return (std::size_t)((Cursor.load(std::memory_order_relaxed) >> 32) & 0xFFFF);
     }

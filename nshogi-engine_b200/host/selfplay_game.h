@@ -85,8 +85,7 @@ inline void prepareRoot(const GameOptions& O, Frame& F) {
 // Worker::transition + judge, worker.cc:520-640,476-518: play the most visited move; true when the game is over.
 inline bool transition(Frame& F, Info* SI) {
     const int Best = F.Tree.bestRootEdge();
-    const search::Node& R = F.Tree.Nodes[0];
-    const rules::Move M = F.Tree.Edges[R.EdgeBegin + Best].M;
+    const rules::Move M = F.Tree.edgesOf(0)[Best].M;
     rules::Position::Undo U;
     F.Root.make(M, &U);
     F.History.push_back(F.Root.Hash);
@@ -112,8 +111,8 @@ inline bool transition(Frame& F, Info* SI) {
 // One frame until it needs the network: selectLeaf / checkTerminal / backpropagate / transition (worker.cc:82-106).
 inline void advance(const GameOptions& O, Frame& F, Info* SI) {
     for (;;) {
-        search::Node& Root = F.Tree.Nodes[0];
-        if (Root.Evaluated && (Root.NumEdges == 1 || Root.Visits >= F.Playouts + 1)) {  // worker.cc:415-430 (+1: the root's own evaluation)
+        const search::Node& Root = F.Tree.node(0);
+        if (Root.evaluated() && (Root.NumEdges == 1 || Root.Visits >= F.Playouts + 1)) {  // worker.cc:415-430 (+1: the root's own evaluation)
             if (transition(F, SI)) {
                 SI->Games.fetch_add(1, std::memory_order_relaxed);
                 newGame(O, F);
@@ -124,7 +123,7 @@ inline void advance(const GameOptions& O, Frame& F, Info* SI) {
         F.Leaf = F.Root;
         F.Path.clear();
         const int Node = F.Tree.selectLeaf(F.Leaf, F.BlackDraw, F.WhiteDraw, &F.Path);
-        search::Node& N = F.Tree.Nodes[Node];
+        const search::Node& N = F.Tree.node(Node);
         if (N.Term == search::Mated) {
             F.Tree.backup(Node, 0.0f, 0.0f);
             continue;
@@ -136,15 +135,13 @@ inline void advance(const GameOptions& O, Frame& F, Info* SI) {
         // a new leaf: terminal checks first (searchworker.cc:475-538, selfplay/worker.cc:330-372)
         const int NumMoves = F.Leaf.generateLegal(F.LeafMoves);
         if (NumMoves == 0) {
-            N.Term = search::Mated;
-            N.Evaluated = true;
+            F.Tree.setTerminal(Node, search::Mated);
             SI->Terminals.fetch_add(1, std::memory_order_relaxed);
             F.Tree.backup(Node, 0.0f, 0.0f);
             continue;
         }
         if (Node != 0 && (search::isFourfold(F.Leaf.Hash, F.History, F.Path) || F.Leaf.Ply >= F.MaxPly)) {
-            N.Term = search::DrawnGame;
-            N.Evaluated = true;
+            F.Tree.setTerminal(Node, search::DrawnGame);
             SI->Terminals.fetch_add(1, std::memory_order_relaxed);
             F.Tree.backup(Node, 0.5f, 1.0f);
             continue;
@@ -162,14 +159,15 @@ inline void advance(const GameOptions& O, Frame& F, Info* SI) {
 // root (frame.cc:121-133; the noise is i.i.d., so mixing it after the sort draws from the same distribution), then
 // Node::updateAncestors.
 inline void applyEvaluation(const GameOptions& O, Frame& F, const float* Row, const uint16_t* Order, float WinRate, float DrawRate) {
-    F.Tree.setPriors(F.LeafNode, Row, Order);
+    F.Tree.setPriors(F.LeafNode, Row, Order, /*Publish=*/false);
     if (!O.Gumbel && F.LeafNode == 0 && F.FullSearch) {
-        search::Node& R = F.Tree.Nodes[0];
-        search::Edge* E = F.Tree.Edges.data() + R.EdgeBegin;
+        search::Edge* E = F.Tree.edgesOf(0);
+        const int NumEdges = F.Tree.node(0).NumEdges;
         const double EPS = 0.25;
-        for (int J = 0; J < R.NumEdges; ++J) E[J].P = (float)((1 - EPS) * (double)E[J].P + EPS * F.Noise[J]);
+        for (int J = 0; J < NumEdges; ++J) E[J].P = (float)((1 - EPS) * (double)E[J].P + EPS * F.Noise[J]);
         F.Tree.sortEdges(0);
     }
+    F.Tree.publish(F.LeafNode);
     F.Tree.backup(F.LeafNode, WinRate, DrawRate);
 }
 

@@ -11,14 +11,13 @@
 // (src/mcts/feedworker.cc:29-137).  Here: --num-search-threads search threads (default 2, context.h:74) descend the
 // shared tree under virtual loss, generate the leaf's moves and write its row IN PLACE into the open pinned batch
 // (host/leaf_queue.h: no queue of tuples, no copy); one evaluation thread seals and submits batches and feeds the
-// results of the slot it is about to reuse.  Rules: host/rules/shogi.h; tree: host/mcts_search.h behind one mutex (no
-// df-pn, no declaration win).
+// results as soon as a batch is done.  Rules: host/rules/shogi.h; tree: host/mcts_search.h, shared lock-free (no df-pn,
+// no declaration win).
 #include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -70,22 +69,20 @@ int main(int argc, char** argv) {
 
     const rules::Position Root;  // hirate
     const std::vector<uint64_t> History{Root.Hash};
-    search::Tree T;              // shared by the search threads and the feeding thread under TreeMu (the reference's
-    std::mutex TreeMu;           // tree is lock-free, node.h:59-100; selection and back-propagation are short)
-    T.reset();
-    T.Nodes.reserve(1u << 21);
-    T.Edges.reserve(1u << 25);
+    // shared by the search threads and the feeding thread without a lock, like the reference's tree (node.h:59-100);
+    // arenas sized for the run: ~350 k nodes/s at ~40 legal moves each
+    const std::size_t MaxNodes = (std::size_t)(6.0e5 * (Seconds + 1.0)) + (1u << 16);
+    search::Tree T(MaxNodes, MaxNodes * 48);
     const uint16_t MaxPly = 320;  // StateConfig default of the USI front-end
     std::atomic<uint64_t> Terminals{0}, Collisions{0}, LegalMoves{0};
     uint64_t Evals = 0, Batches = 0, CacheHits = 0, GpuWaitNs = 0;
-    std::atomic<bool> Running{true};
+    std::atomic<bool> Running{true}, TreeFull{false};
 
     // FeedWorker::feedResult (feedworker.cc:56-137) for one row of a collected slot: the gather, the softmax and
     // Node::sort's permutation came back from the GPU; setEvaluation + updateAncestors are what is left
     auto feed = [&](evaluate::LeafPipeline::Slot& S, std::size_t Row, void* User) {
         const int Node = (int)(uintptr_t)User - 1;
         const uint32_t B = S.MoveOffsets[Row];
-        std::lock_guard<std::mutex> L(TreeMu);
         T.setPriors(Node, S.Legal + B, S.Order + B);
         T.backup(Node, S.WinRate[Row], S.DrawRate[Row]);
         if (CacheMiB > 0 && S.HitFlag[Row]) ++CacheHits;
@@ -97,46 +94,44 @@ int main(int argc, char** argv) {
         rules::Move Moves[rules::kMaxMoves];
         uint16_t Slots_[rules::kMaxMoves];
         std::vector<uint64_t> Path;
+        std::vector<int> Trail;
         while (Running.load(std::memory_order_relaxed)) {
             rules::Position Pos = Root;
             Path.clear();
-            int Node;
-            {
-                std::lock_guard<std::mutex> L(TreeMu);
-                Node = T.selectLeaf(Pos, 0.5f, 0.5f, &Path);  // collectOneLeaf; leaves a virtual loss on the path
-                if (Node >= 0) {
-                    const search::Node& N = T.Nodes[(std::size_t)Node];
-                    if (N.Term == search::Mated) {
-                        T.backup(Node, 0.0f, 0.0f);
-                        continue;
-                    }
-                    if (N.Term == search::DrawnGame) {
-                        T.backup(Node, 0.5f, 1.0f);
-                        continue;
-                    }
-                }
+            const int Node = T.selectLeaf(Pos, 0.5f, 0.5f, &Path, &Trail);  // collectOneLeaf; leaves a virtual loss on the path
+            if (Node == search::Tree::OutOfMemory) {
+                TreeFull.store(true, std::memory_order_relaxed);
+                break;
             }
             if (Node < 0) {  // ran into a leaf that is being evaluated (searchworker.cc:349-357)
                 Collisions.fetch_add(1, std::memory_order_relaxed);
                 std::this_thread::yield();
                 continue;
             }
+            {
+                const search::Node& N = T.node(Node);
+                if (N.Term == search::Mated) {
+                    T.backup(Node, 0.0f, 0.0f);
+                    continue;
+                }
+                if (N.Term == search::DrawnGame) {
+                    T.backup(Node, 0.5f, 1.0f);
+                    continue;
+                }
+            }
             const int NumMoves = Pos.generateLegal(Moves);  // expandLeaf, :164-173 - outside the lock
             const bool Mated = NumMoves == 0;
             const bool Drawn = !Mated && Node != 0 && (search::isFourfold(Pos.Hash, History, Path) || Pos.Ply >= MaxPly);
             if (Mated || Drawn) {  // terminal checks, :475-538
-                std::lock_guard<std::mutex> L(TreeMu);
-                search::Node& N = T.Nodes[(std::size_t)Node];
-                N.Term = Mated ? search::Mated : search::DrawnGame;
-                N.Evaluated = true;
+                T.setTerminal(Node, Mated ? search::Mated : search::DrawnGame);
                 T.backup(Node, Mated ? 0.0f : 0.5f, Mated ? 0.0f : 1.0f);
                 Terminals.fetch_add(1, std::memory_order_relaxed);
                 continue;
             }
             for (int J = 0; J < NumMoves; ++J) Slots_[J] = (uint16_t)Pos.policyIndex(Moves[J]);  // ml::getMoveIndex
-            {
-                std::lock_guard<std::mutex> L(TreeMu);
-                T.expand(Node, Moves, NumMoves);
+            if (!T.expand(Node, Moves, NumMoves)) {
+                TreeFull.store(true, std::memory_order_relaxed);
+                break;
             }
             evaluate::LeafQueue::Ticket Tk;
             while (!Queue.reserve((uint16_t)NumMoves, (void*)(uintptr_t)(Node + 1), &Tk)) {  // EvaluationQueue::add, evaluationqueue.cc:45-60
@@ -157,18 +152,17 @@ int main(int argc, char** argv) {
     const auto T0 = Clock::now();
     auto elapsed = [&]() { return std::chrono::duration<double>(Clock::now() - T0).count(); };
     for (int I = 0; I < SearchThreads; ++I) Threads.emplace_back(searchThread);
-    // EvaluationWorker::doTask (evaluationworker.cc:105-199): a batch goes out when it is full, or - like the
-    // reference's "whatever is queued" - when rows are waiting and nothing has been submitted for a moment
-    auto LastSubmit = Clock::now();
-    while (elapsed() < Seconds) {
-        const std::size_t Rows = Queue.openRows();
-        const double IdleUs = std::chrono::duration<double, std::micro>(Clock::now() - LastSubmit).count();
-        if (Rows >= (std::size_t)Batch || (Rows > 0 && IdleUs > 150.0)) {
+    // EvaluationWorker::doTask (evaluationworker.cc:105-199).  The reference submits "whatever is queued"; with the
+    // batch assembled in place the rule is: a full batch goes out at once; a partial one goes out when the GPU would
+    // otherwise idle (nothing in flight), or at half size when only one batch is in flight - so the open batch keeps
+    // filling while the GPU is busy and its size follows the parallelism the tree offers.
+    while (elapsed() < Seconds && !TreeFull.load(std::memory_order_relaxed)) {
+        const std::size_t Rows = Queue.openRows(), Busy = Queue.inFlight();
+        if (Rows >= (std::size_t)Batch || (Rows > 0 && Busy == 0) || (Rows >= (std::size_t)Batch / 2 && Busy == 1 && NS > 2)) {
             const auto W0 = Clock::now();
             Queue.submitOpen(/*FromPositions=*/true, NSB_DECODE_PROBS, /*UseCache=*/CacheMiB > 0, /*Ranked=*/true, feed);
             GpuWaitNs += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - W0).count();
             ++Batches;
-            LastSubmit = Clock::now();
         } else if (Queue.pollFeed(feed) == 0) {  // FeedWorker::doTask: results go back into the tree as soon as they exist
             std::this_thread::yield();
         }
@@ -179,35 +173,26 @@ int main(int argc, char** argv) {
     const double Sec = elapsed();
 
     // usilogger.cc:29-65: nodes = visits of the root, nps, pv by most-visited edges
-    const uint64_t Nodes = T.Nodes[0].Visits;
+    const uint64_t Nodes = T.node(0).Visits;
     std::string PV;
     int Cur = 0, Depth = 0;
     while (Depth < 12) {
-        const search::Node& N = T.Nodes[(std::size_t)Cur];
-        if (!N.Evaluated || N.NumEdges == 0) break;
-        int Best = -1;
-        uint32_t BestV = 0;
-        for (int I = 0; I < N.NumEdges; ++I) {
-            const search::Edge& E = T.Edges[(std::size_t)N.EdgeBegin + (std::size_t)I];
-            const uint32_t V = E.Child >= 0 ? T.Nodes[(std::size_t)E.Child].Visits : 0;
-            if (V > BestV) {
-                BestV = V;
-                Best = I;
-            }
-        }
-        if (Best < 0) break;
-        const rules::Move& M = T.Edges[(std::size_t)N.EdgeBegin + (std::size_t)Best].M;
+        const search::Node& N = T.node(Cur);
+        if (!N.evaluated() || N.NumEdges == 0 || N.Term != search::Open) break;
+        const int Best = T.bestEdge(Cur);
+        if (Best < 0 || T.edgesOf(Cur)[Best].CVisits == 0) break;
+        const rules::Move& M = T.edgesOf(Cur)[Best].M;
         char Buf[16];
         if (M.isDrop())
             std::snprintf(Buf, sizeof Buf, "%c*%d%c ", "PLNSGBR"[M.dropSlot()], M.To / 9 + 1, 'a' + M.To % 9);
         else
             std::snprintf(Buf, sizeof Buf, "%d%c%d%c%s ", M.From / 9 + 1, 'a' + M.From % 9, M.To / 9 + 1, 'a' + M.To % 9, M.Promote ? "+" : "");
         PV += Buf;
-        Cur = T.Edges[(std::size_t)N.EdgeBegin + (std::size_t)Best].Child;
+        Cur = T.edgesOf(Cur)[Best].Child;
         ++Depth;
     }
     if (!PV.empty()) PV.pop_back();
-    const double RootWin = Nodes ? T.Nodes[0].WinAcc / (double)Nodes : 0.0;
+    const double RootWin = Nodes ? T.node(0).WinAcc / (double)Nodes : 0.0;
     std::printf("{\"metric\": \"usi_go_nodes_per_sec\", \"value\": %.1f, \"unit\": \"nodes/s\", \"nodes\": %llu, \"time_ms\": %.0f, "
                 "\"leaf_evals_per_sec\": %.1f, \"avg_batch\": %.1f, \"batches\": %llu, \"terminal_leaves\": %llu, \"collisions\": %llu, "
                 "\"cache_mb\": %d, \"cache_hit_rate\": %.4f, \"avg_legal_moves\": %.1f, \"tree_nodes\": %zu, \"submit_and_feed_fraction\": %.3f, "
@@ -216,7 +201,7 @@ int main(int argc, char** argv) {
                 "\"rules\": \"real: host/rules/shogi.h + host/mcts_search.h (PUCT, virtual loss); no df-pn, no declaration win\"}\n",
                 (double)Nodes / Sec, (unsigned long long)Nodes, Sec * 1e3, (double)Evals / Sec, Batches ? (double)Evals / (double)Batches : 0.0,
                 (unsigned long long)Batches, (unsigned long long)Terminals.load(), (unsigned long long)Collisions.load(), CacheMiB,
-                Evals ? (double)CacheHits / (double)Evals : 0.0, Evals ? (double)LegalMoves.load() / (double)Evals : 0.0, T.Nodes.size(),
+                Evals ? (double)CacheHits / (double)Evals : 0.0, Evals ? (double)LegalMoves.load() / (double)Evals : 0.0, T.numNodes(),
                 (double)GpuWaitNs * 1e-9 / Sec, RootWin, PV.c_str(), Blocks, Channels, Batch, (int)NS, SearchThreads);
     return 0;
 }

@@ -114,6 +114,14 @@ def test_leaf_queue_protocol_under_thread_sanitizer(built, tmp_path):
     out = subprocess.run([os.path.join(built, "nsb_host_unit"), "--queue-stress", "8", "300000"], capture_output=True,
                          text=True, timeout=300)
     assert out.returncode == 0 and ": ok" in out.stdout
+    # the lock-free search tree (mcts_search.h: relaxed counters, claim by compare-and-swap, edges published by a release
+    # store) under the same sanitizer: 6 threads grow one tree of real shogi positions, then every invariant is checked
+    out = subprocess.run([exe, "--tree-stress", "6", "6000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and ": ok" in out.stdout, out.stdout + out.stderr
+    assert "ThreadSanitizer" not in out.stderr
+    out = subprocess.run([os.path.join(built, "nsb_host_unit"), "--tree-stress", "8", "200000"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0 and ": ok" in out.stdout, out.stdout + out.stderr
 
 
 @pytest.mark.gpu
