@@ -149,8 +149,8 @@ class Tree {
         Trail->push_back(Cur);
         for (int I : *Trail) {
             Node& X = NodesP[I];
-            std::atomic_ref<uint32_t>(X.VirtualLoss).fetch_add(1, std::memory_order_relaxed);
-            if (X.ParentEdge >= 0) std::atomic_ref<uint32_t>(EdgesP[X.ParentEdge].CVirtualLoss).fetch_add(1, std::memory_order_relaxed);
+            add(X.VirtualLoss, 1u);
+            if (X.ParentEdge >= 0) add(EdgesP[X.ParentEdge].CVirtualLoss, 1u);
         }
         return Cur;
     }
@@ -216,16 +216,17 @@ class Tree {
         float W = WinRate;
         for (int Cur = Leaf; Cur >= 0; Cur = NodesP[Cur].Parent) {
             Node& N = NodesP[Cur];
-            std::atomic_ref<double>(N.WinAcc).fetch_add((double)W, std::memory_order_relaxed);
-            std::atomic_ref<double>(N.DrawAcc).fetch_add((double)DrawRate, std::memory_order_relaxed);
-            std::atomic_ref<uint32_t>(N.Visits).fetch_add(1, std::memory_order_relaxed);
-            std::atomic_ref<uint32_t>(N.VirtualLoss).fetch_sub(1, std::memory_order_relaxed);
+            add(N.WinAcc, (double)W);
+            add(N.DrawAcc, (double)DrawRate);
+            add(N.Visits, 1u);
+            add(N.VirtualLoss, ~0u);  // - 1
             if (N.ParentEdge >= 0) {
                 Edge& E = EdgesP[N.ParentEdge];
-                std::atomic_ref<float>(E.CWinAcc).fetch_add(W, std::memory_order_relaxed);
-                std::atomic_ref<float>(E.CDrawAcc).fetch_add(DrawRate, std::memory_order_relaxed);
-                std::atomic_ref<uint32_t>(E.CVirtualLoss).fetch_sub(1, std::memory_order_relaxed);
-                std::atomic_ref<uint32_t>(E.CVisits).fetch_add(1, std::memory_order_release);  // last: the sums are there
+                add(E.CWinAcc, W);
+                add(E.CDrawAcc, DrawRate);
+                add(E.CVirtualLoss, ~0u);
+                if (Shared) std::atomic_ref<uint32_t>(E.CVisits).fetch_add(1, std::memory_order_release);  // last: the sums are there
+                else ++E.CVisits;
             }
             W = 1.0f - W;
         }
@@ -256,6 +257,13 @@ class Tree {
     std::atomic<uint32_t> NumNodes{0};
     std::atomic<uint64_t> NumEdgesUsed{0};
     std::vector<int> OwnTrail;
+
+    // counters: relaxed atomic read-modify-writes on a shared tree, plain arithmetic on a private one
+    template <typename T>
+    void add(T& X, T V) {
+        if (Shared) std::atomic_ref<T>(X).fetch_add(V, std::memory_order_relaxed);
+        else X += V;
+    }
 
     void initNode(int I, int Parent, int ParentEdge) {
         NodesP[I] = Node{Parent, ParentEdge, 0, 0, Open, Fresh, 0u, 0u, 0.0, 0.0};
