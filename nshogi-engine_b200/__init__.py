@@ -8,4 +8,4 @@ for tests and benchmarks: ``binding`` (ctypes), ``infer`` (Python twin of the In
 ``onnx_io`` (the reference's ONNX model files <-> canonical blob, no `onnx` package needed).  There is no
 CPU fallback anywhere in this package.
 """
-from . import binding, infer, onnx_io, replica, synth, weights_io  # noqa: F401
+from . import binding, infer, onnx_io, replica, synth, teacher_io, weights_io  # noqa: F401

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <set>
+#include <sstream>
 #include <vector>
 
 #include <fstream>
@@ -369,10 +370,44 @@ static int selfplayMock(int Games, int Playouts) {
     F.MaxPly = 60;
     game::prepareRoot(O, F);
     uint64_t Evals = 0;
+    std::size_t SavedRecords = 0;
+    bool SaveOk = true;
     while ((int)SI.Games.load() < Games) {
         const uint64_t GamesBefore = SI.Games.load(), RecordsBefore = SI.Records.load();
         const uint32_t RootVisitsBefore = F.Tree.node(0).Visits;
-        game::advance(O, F, &SI);
+        game::advance(O, F, &SI, [&](const game::Frame& Done) {   // SelfplayPhase::Save: the finished game as teacher records
+            const teacher::FinishedGame G = game::finishedGame(Done);
+            std::ostringstream Out;
+            teacher::writeHeader(Out);
+            const std::size_t N = teacher::saveGame(&Out, G);
+            SavedRecords += N;
+            const std::string Bytes = Out.str();
+            SaveOk = SaveOk && Bytes.size() == 12 + N * sizeof(teacher::TeacherRecord) && G.Moves.size() == G.DidFullSearch.size();
+            std::size_t Full = 0;
+            for (uint8_t B : G.DidFullSearch) Full += B;
+            SaveOk = SaveOk && Full == N && G.Winner <= teacher::WinnerNone;
+            rules::Position Replay;   // every record holds the position BEFORE its move, and the move is legal there
+            std::size_t K = 0;
+            for (std::size_t Ply = 0; Ply < G.Moves.size(); ++Ply) {
+                rules::Move Ms[rules::kMaxMoves];
+                const int NM = Replay.generateLegal(Ms);
+                bool Legal = false;
+                for (int J = 0; J < NM; ++J) Legal = Legal || Ms[J] == G.Moves[Ply];
+                SaveOk = SaveOk && Legal;
+                if (G.DidFullSearch[Ply]) {
+                    teacher::TeacherRecord R;
+                    std::memcpy(&R, Bytes.data() + 12 + K * sizeof R, sizeof R);
+                    nsb_position Want;
+                    Replay.toRecord(&Want, G.MaxPly, G.BlackDraw, G.WhiteDraw);
+                    SaveOk = SaveOk && std::memcmp(&R.Position, &Want, sizeof Want) == 0 && R.From == G.Moves[Ply].From &&
+                             R.To == G.Moves[Ply].To && R.Promote == G.Moves[Ply].Promote && R.Winner == G.Winner;
+                    ++K;
+                }
+                rules::Position::Undo U;
+                Replay.make(G.Moves[Ply], &U);
+            }
+            SaveOk = SaveOk && K == N && Replay.Hash == Done.Root.Hash;
+        });
         if (SI.Games.load() != GamesBefore) F.MaxPly = 60;  // (newGame drew a long one)
         if (SI.Records.load() == RecordsBefore && F.LeafNode != 0) CHECK(F.Tree.node(0).Visits >= RootVisitsBefore);
         // the frame now waits for an evaluation of F.Leaf with F.NumLeafMoves legal moves
@@ -414,6 +449,7 @@ static int selfplayMock(int Games, int Playouts) {
                 Games, (unsigned long long)SI.Records.load(), (unsigned long long)Evals, (unsigned long long)SI.Terminals.load(),
                 (unsigned long long)SI.Mates.load(), (unsigned long long)SI.Repetitions.load(), (unsigned long long)SI.MaxPlies.load());
     CHECK(SI.Records.load() >= (uint64_t)Games * 10 && Evals > SI.Records.load());
+    CHECK(SaveOk && SavedRecords > 0 && SavedRecords < SI.Records.load());   // teacher records: full-search plies only
     return 0;
 }
 

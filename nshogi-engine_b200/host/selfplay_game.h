@@ -15,6 +15,7 @@
 
 #include "mcts_search.h"
 #include "rules/shogi.h"
+#include "teacher_io.h"
 
 namespace nshogi {
 namespace engine {
@@ -41,6 +42,9 @@ struct Frame {  // reference src/selfplay/frame.h: one game in flight
     bool FullSearch = true;
     double Noise[600];
     std::mt19937_64 MT;
+    std::vector<rules::Move> GameMoves;      // the game so far (State::getHistoryMove)
+    std::vector<uint8_t> DidFullSearch;      // per ply (Frame::getDidFullSearch, frame.h)
+    uint8_t Winner = teacher::WinnerNone;
 };
 
 struct Info {  // reference src/selfplay/selfplayinfo.h
@@ -53,6 +57,9 @@ inline void newGame(const GameOptions& O, Frame& F) {
     F.Root.setHirate();
     F.History.clear();
     F.History.push_back(F.Root.Hash);
+    F.GameMoves.clear();
+    F.DidFullSearch.clear();
+    F.Winner = teacher::WinnerNone;
     std::uniform_int_distribution<int> MaxPlyD(160 + 64, 512 + 128);
     std::uniform_real_distribution<float> DrawD(0.0f, 1.0f);
     F.MaxPly = (uint16_t)MaxPlyD(F.MT);
@@ -89,7 +96,9 @@ inline bool transition(Frame& F, Info* SI) {
     rules::Position::Undo U;
     F.Root.make(M, &U);
     F.History.push_back(F.Root.Hash);
-    SI->Records.fetch_add(1, std::memory_order_relaxed);  // one teacher record per played position (saveworker.cc:160-182)
+    F.GameMoves.push_back(M);
+    F.DidFullSearch.push_back(F.FullSearch ? 1 : 0);      // Frame::pushDidFullSearch
+    SI->Records.fetch_add(1, std::memory_order_relaxed);  // positions played (teacher records: full-search plies only, teacher_io.h)
     SI->PliesPlayed.fetch_add(1, std::memory_order_relaxed);
     int Seen = 0;
     for (uint64_t H : F.History) Seen += H == F.Root.Hash;
@@ -103,18 +112,34 @@ inline bool transition(Frame& F, Info* SI) {
     }
     if (!F.Root.hasLegalMove()) {
         SI->Mates.fetch_add(1, std::memory_order_relaxed);
+        F.Winner = F.Root.Side == 0 ? teacher::WinnerWhite : teacher::WinnerBlack;  // the side to move is mated
         return true;
     }
     return false;
 }
 
+// A finished game for the save worker (SelfplayPhase::Save, worker.cc:98-99; saveworker.cc:56-88).
+inline teacher::FinishedGame finishedGame(const Frame& F) {
+    teacher::FinishedGame G;
+    G.Moves = F.GameMoves;
+    G.DidFullSearch = F.DidFullSearch;
+    G.MaxPly = F.MaxPly;
+    G.BlackDraw = F.BlackDraw;
+    G.WhiteDraw = F.WhiteDraw;
+    G.Winner = F.Winner;
+    return G;
+}
+
 // One frame until it needs the network: selectLeaf / checkTerminal / backpropagate / transition (worker.cc:82-106).
-inline void advance(const GameOptions& O, Frame& F, Info* SI) {
+// OnGameEnd(const Frame&) is called when a game is over, before the frame starts its next one.
+template <typename GameEnd>
+inline void advance(const GameOptions& O, Frame& F, Info* SI, GameEnd&& OnGameEnd) {
     for (;;) {
         const search::Node& Root = F.Tree.node(0);
         if (Root.evaluated() && (Root.NumEdges == 1 || Root.Visits >= F.Playouts + 1)) {  // worker.cc:415-430 (+1: the root's own evaluation)
             if (transition(F, SI)) {
                 SI->Games.fetch_add(1, std::memory_order_relaxed);
+                OnGameEnd(F);
                 newGame(O, F);
             }
             prepareRoot(O, F);
@@ -152,6 +177,10 @@ inline void advance(const GameOptions& O, Frame& F, Info* SI) {
         F.LeafNode = Node;
         return;
     }
+}
+
+inline void advance(const GameOptions& O, Frame& F, Info* SI) {
+    advance(O, F, SI, [](const Frame&) {});
 }
 
 // Frame::setEvaluation's consumer side (frame.cc:93-136) for a row the executor decoded (NSB_DECODE_BOTH + order_out):

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <fstream>
 #include <limits>
 #include <mutex>
 #include <random>
@@ -49,6 +50,7 @@ struct Options : b200::game::GameOptions {
     int CacheMiB = 0;
     double Seconds = 5.0, Warmup = 1.0;
     uint64_t Seed = 1234;
+    std::string Out;  // main.cc -o / --out: the teacher file ("" = records are counted, not written)
 };
 using b200::game::Frame;
 using b200::game::Info;
@@ -87,13 +89,71 @@ class FrameQueue {  // reference src/selfplay/framequeue.h
     bool Closed = false;
 };
 
-void searchWorker(const Options& O, FrameQueue* SearchQueue, FrameQueue* EvaluationQueue, Info* SI, std::atomic<bool>* Running) {
+// reference src/selfplay/saveworker.cc: finished games are replayed and their full-search positions written as teacher
+// records (host/teacher_io.h), off the search threads
+class SaveQueue {
+ public:
+    void add(teacher::FinishedGame&& G) {
+        {
+            std::lock_guard<std::mutex> L(M);
+            Q.push_back(std::move(G));
+        }
+        CV.notify_one();
+    }
+    bool get(teacher::FinishedGame* G) {
+        std::unique_lock<std::mutex> L(M);
+        CV.wait_for(L, std::chrono::milliseconds(5), [&] { return !Q.empty() || Closed; });
+        if (Q.empty()) return false;
+        *G = std::move(Q.front());
+        Q.pop_front();
+        return true;
+    }
+    void close() {
+        {
+            std::lock_guard<std::mutex> L(M);
+            Closed = true;
+        }
+        CV.notify_all();
+    }
+    bool drained() {
+        std::lock_guard<std::mutex> L(M);
+        return Q.empty();
+    }
+
+ private:
+    std::deque<teacher::FinishedGame> Q;
+    std::mutex M;
+    std::condition_variable CV;
+    bool Closed = false;
+};
+
+struct SaveStats {
+    std::atomic<uint64_t> Games{0}, Records{0}, Winners[3] = {{0}, {0}, {0}};
+};
+
+void saveWorker(const Options& O, SaveQueue* Queue, SaveStats* Stats, std::atomic<bool>* Running) {
+    std::ofstream File;
+    if (!O.Out.empty()) {
+        File.open(O.Out, std::ios::binary | std::ios::trunc);
+        teacher::writeHeader(File);
+    }
+    teacher::FinishedGame G;
+    while (Running->load(std::memory_order_relaxed) || !Queue->drained()) {
+        if (!Queue->get(&G)) continue;
+        Stats->Records.fetch_add(teacher::saveGame(O.Out.empty() ? nullptr : &File, G), std::memory_order_relaxed);
+        Stats->Games.fetch_add(1, std::memory_order_relaxed);
+        Stats->Winners[G.Winner].fetch_add(1, std::memory_order_relaxed);  // SaveWorker::updateStatistics
+    }
+}
+
+void searchWorker(const Options& O, FrameQueue* SearchQueue, FrameQueue* EvaluationQueue, SaveQueue* Saves, Info* SI,
+                  std::atomic<bool>* Running) {
     std::vector<Frame*> In, Out;
     while (Running->load(std::memory_order_relaxed)) {
         In.clear();
         SearchQueue->get(32, true, In);
         for (Frame* F : In) {
-            b200::game::advance(O, *F, SI);
+            b200::game::advance(O, *F, SI, [&](const Frame& Done) { Saves->add(b200::game::finishedGame(Done)); });
             Out.push_back(F);
         }
         EvaluationQueue->add(Out);
@@ -188,6 +248,7 @@ int main(int argc, char** argv) {
         else if (A == "--seconds") O.Seconds = nextD();
         else if (A == "--warmup") O.Warmup = nextD();
         else if (A == "--seed") O.Seed = (uint64_t)nextI();
+        else if (A == "--out" || A == "-o") O.Out = I + 1 < argc ? argv[++I] : "";
         else {
             std::fprintf(stderr, "unknown option %s\n", A.c_str());
             return 2;
@@ -216,8 +277,12 @@ int main(int argc, char** argv) {
     std::atomic<bool> Running{true};
     std::vector<std::thread> Threads;
     Threads.emplace_back(evaluationWorker, std::cref(O), &Exec, &EvaluationQueue, &SearchQueue, &SI, &Running);
+    SaveQueue Saves;
+    SaveStats Saved;
+    std::atomic<bool> Saving{true};
+    std::thread Saver(saveWorker, std::cref(O), &Saves, &Saved, &Saving);
     for (int W = 0; W < O.SearchWorkers; ++W)
-        Threads.emplace_back(searchWorker, std::cref(O), &SearchQueue, &EvaluationQueue, &SI, &Running);
+        Threads.emplace_back(searchWorker, std::cref(O), &SearchQueue, &EvaluationQueue, &Saves, &SI, &Running);
 
     std::this_thread::sleep_for(std::chrono::duration<double>(O.Warmup));
     const uint64_t E0 = SI.Evals.load(), B0 = SI.Batches.load(), R0 = SI.Records.load(), G0 = SI.Games.load();
@@ -231,6 +296,9 @@ int main(int argc, char** argv) {
     SearchQueue.close();
     EvaluationQueue.close();
     for (auto& T : Threads) T.join();
+    Saving.store(false);
+    Saves.close();
+    Saver.join();
 
     uint64_t MaxDepthPly = 0;
     for (const Frame& F : Pool) MaxDepthPly = std::max<uint64_t>(MaxDepthPly, F.Root.Ply);
@@ -240,6 +308,8 @@ int main(int argc, char** argv) {
                 "\"records\": %llu, \"evals\": %llu, \"batches\": %llu, \"games\": %llu, "
                 "\"cache_mb\": %d, \"cache_hit_rate\": %.4f, \"terminal_leaves_per_eval\": %.4f, \"avg_legal_moves\": %.1f, "
                 "\"games_ended\": {\"mate\": %llu, \"repetition\": %llu, \"max_ply\": %llu}, \"deepest_game_ply\": %llu, "
+                "\"teacher\": {\"games_saved\": %llu, \"records_saved\": %llu, \"black_wins\": %llu, \"white_wins\": %llu, \"draws\": %llu, "
+                "\"file\": \"%s\", \"what\": \"full-search positions of finished games (saveworker.cc:160-182), NSBT format\"}, "
                 "\"net\": \"%dx%d\", \"batch_size\": %d, \"frame_pool\": %d, \"search_workers\": %d, \"slots\": %d, "
                 "\"num_playouts\": %d, \"full_search_ratio\": %.2f, \"nan_rows\": %llu, "
                 "\"decode\": \"NSB_DECODE_BOTH + order_out (logits cached, probabilities and rank order out; %s)\", "
@@ -250,7 +320,9 @@ int main(int argc, char** argv) {
                 (unsigned long long)(G1 - G0), O.CacheMiB, Evals > 0 ? (double)(H1 - H0) / Evals : 0.0,
                 Evals > 0 ? (double)(T1n - T0n) / Evals : 0.0, Evals > 0 ? (double)(L1 - L0) / Evals : 0.0,
                 (unsigned long long)SI.Mates.load(), (unsigned long long)SI.Repetitions.load(), (unsigned long long)SI.MaxPlies.load(),
-                (unsigned long long)MaxDepthPly, O.Blocks, O.Channels, O.Batch, O.Frames, O.SearchWorkers, O.Slots, O.Playouts,
+                (unsigned long long)MaxDepthPly, (unsigned long long)Saved.Games.load(), (unsigned long long)Saved.Records.load(),
+                (unsigned long long)Saved.Winners[0].load(), (unsigned long long)Saved.Winners[1].load(),
+                (unsigned long long)Saved.Winners[2].load(), O.Out.c_str(), O.Blocks, O.Channels, O.Batch, O.Frames, O.SearchWorkers, O.Slots, O.Playouts,
                 O.FullSearchRatio, (unsigned long long)SI.NanRows.load(),
                 O.Gumbel ? "Gumbel roots skip the softmax" : "Dirichlet mix at full-search roots on the host");
     return 0;

@@ -4,6 +4,7 @@ import json
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -172,6 +173,33 @@ def test_selfplay_real_rules_gpu(built):
     assert out.returncode == 0, out.stdout + out.stderr
     rec = json.loads(out.stdout.strip().splitlines()[-1])
     assert rec["nan_rows"] == 0 and rec["cache_hit_rate"] > 0.02   # early-game transpositions across 256 games from hirate
+
+
+@pytest.mark.gpu
+def test_selfplay_writes_teacher_records_gpu(built, pkg, nb, tmp_path):
+    """SaveWorker (reference src/selfplay/saveworker.cc:160-182): finished games are replayed and their full-search
+    positions written as teacher records.  Tiny playout budget so that games finish within the run; the file must hold
+    exactly the records the harness reports, each a shogi position with both kings, the mover's move and a winner."""
+    path = str(tmp_path / "teacher.nsbt")
+    out = subprocess.run([os.path.join(built, "nsb_selfplay_real"), "--channels", "128", "--blocks", "1", "--batch-size", "256",
+                          "--frame-pool-size", "512", "--num-search-workers", "4", "--num-playouts", "4", "--full-search-ratio", "0.5",
+                          "--seconds", "3.0", "--warmup", "0.2", "--out", path], capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    t = rec["teacher"]
+    assert t["games_saved"] > 0 and t["records_saved"] > 0, rec
+    assert t["black_wins"] + t["white_wins"] + t["draws"] == t["games_saved"]
+    recs = pkg.teacher_io.read_nsbt(path)
+    assert len(recs) == t["records_saved"]
+    assert set(np.unique(recs["winner"])) <= {0, 1, 2}
+    board = recs["position"]["board"]
+    assert np.all((board == 6).sum(axis=1) == 1) and np.all((board == 20).sum(axis=1) == 1)      # both kings (K = type 5)
+    assert np.all(recs["position"]["side"] == recs["position"]["ply"] % 2)                        # black moves on even plies
+    src = recs["from"]
+    on_board = src < 81
+    mover = (board[np.arange(len(recs)), np.minimum(src, 80)] - 1) // 14
+    assert np.all(mover[on_board] == recs["position"]["side"][on_board])                           # the mover's own piece moves
+    assert np.all(board[np.arange(len(recs)), recs["to"]][~on_board] == 0)                         # drops land on empty squares
 
 
 @pytest.mark.gpu
