@@ -552,6 +552,7 @@ def selfplay_leg(args, info, rep, device):
             "unit": "positions/s", "leaf_evals_per_sec": round(rep.whole_job_rate(counters["evals"], ms_max), 1),
             "games_per_sec": round(rep.whole_job_rate(counters["games"], ms_max), 2),
             "avg_batch": round(counters["evals"] / max(counters["batches"], 1), 1), "seconds": rec["seconds"],
+            "teacher_rank0": rec.get("teacher"),
             "config": {"workload": "self-play data generation, 20x256 ResNet, 1024 concurrent games per GPU",
                        "batch_size": 512, "num_playouts": rec["num_playouts"], "full_search_ratio": rec["full_search_ratio"],
                        "search_workers_per_gpu": workers, "slots": rec["slots"], "rules": rec["rules"],
