@@ -337,6 +337,42 @@ static int rulesChecks(int PerftDepth) {
         for (int I = 0; I < N; ++I) CHECK(Ms[I].Piece == King && fileOf(Ms[I].To) != 4);   // only king moves off the file
         CHECK(N == 4);                                                                       // 4i, 6i, 4h, 6h ... (5h stays attacked)
     }
+    {   // the pin-aware generator against the brute-force definition (make every pseudo-legal move, test the king) on
+        // 30,000 positions of random playouts - captures, drops, promotions, checks, pins, perpetuals
+        std::mt19937_64 Rng(2024);
+        std::size_t Positions = 0, InCheck = 0, WithPins = 0;
+        for (int Game = 0; Game < 300; ++Game) {
+            Position P;
+            for (int Ply = 0; Ply < 100; ++Ply) {
+                Move Fast[kMaxMoves], Pseudo[kMaxMoves + 64];
+                const int NF = P.generateLegal(Fast);
+                const int NP = P.generatePseudoLegal(Pseudo);
+                int NS = 0;
+                const int Me = P.Side;
+                for (int I = 0; I < NP; ++I) {
+                    Position::Undo U;
+                    P.make(Pseudo[I], &U);
+                    bool Ok = !P.inCheck(Me);
+                    if (Ok && Pseudo[I].isDrop() && Pseudo[I].Piece == Pawn && P.inCheck(Me ^ 1)) Ok = P.hasLegalMove();
+                    P.unmake(Pseudo[I], U);
+                    if (Ok) {
+                        CHECK(NS < NF && Fast[NS] == Pseudo[I]);   // same moves in the same order
+                        ++NS;
+                    }
+                }
+                CHECK(NS == NF);
+                ++Positions;
+                const Position::KingSafety KS = P.kingSafety(Me);
+                InCheck += KS.InCheck;
+                WithPins += (KS.PinnedLo | KS.PinnedHi) != 0;
+                if (NF == 0) break;
+                Position::Undo U;
+                P.make(Fast[Rng() % (uint64_t)NF], &U);
+            }
+        }
+        std::printf("rules: %zu random-playout positions, %zu in check, %zu with pinned pieces: generators agree\n", Positions, InCheck, WithPins);
+        CHECK(Positions >= 20000 && InCheck > 300 && WithPins > 300);
+    }
     {   // promoted sliders keep sliding and gain the king's other steps; captures go to the hand unpromoted
         Position P;
         P.clear();

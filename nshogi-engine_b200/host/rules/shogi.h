@@ -318,19 +318,68 @@ class Position {
         return N;
     }
 
-    // Legal moves: the mover's king is not left in check; a pawn drop that mates is illegal (uchifuzume).
+    // Squares of the mover's pieces that are pinned to its king (bit per square), and whether the king is in check.
+    // A piece is pinned when it is the only piece between its king and an enemy slider that moves along that ray.
+    struct KingSafety {
+        uint64_t PinnedLo = 0;   // squares 0..63
+        uint32_t PinnedHi = 0;   // squares 64..80
+        bool InCheck = false;
+        bool pinned(int S) const { return S < 64 ? (PinnedLo >> S) & 1u : (PinnedHi >> (S - 64)) & 1u; }
+    };
+    KingSafety kingSafety(int Colour) const {
+        KingSafety K;
+        const int Ks = KingSq[Colour];
+        if (Ks == 255) return K;
+        K.InCheck = attacked(Ks, Colour ^ 1);
+        const int F = fileOf(Ks), R = rankOf(Ks), Enemy = Colour ^ 1;
+        const int Sign = Enemy == 0 ? 1 : -1;  // an enemy slider that moves by (D0, Sign * D1) towards the king
+        static const int8_t Dirs[8][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}};
+        for (const auto& D : Dirs) {
+            int Af = F - D[0], Ar = R - Sign * D[1], Own = -1;
+            while (onBoard(Af, Ar)) {
+                const int Sq = 9 * Af + Ar, C = Board[Sq];
+                if (C) {
+                    if (colourOf(C) == Colour) {
+                        if (Own >= 0) break;  // two own pieces in the way
+                        Own = Sq;
+                    } else {
+                        if (Own >= 0 && slidesAlong(typeOf(C), D[0], D[1])) {
+                            if (Own < 64) K.PinnedLo |= 1ull << Own;
+                            else K.PinnedHi |= 1u << (Own - 64);
+                        }
+                        break;
+                    }
+                }
+                Af -= D[0];
+                Ar -= Sign * D[1];
+            }
+        }
+        return K;
+    }
+
+    // Legal moves: the mover's king is not left in check; a pawn drop that mates is illegal (uchifuzume).  When the
+    // mover is not in check, a move of a piece that is neither the king nor pinned, and any drop, cannot expose the
+    // king and is legal as generated; only king moves, moves of pinned pieces and every move of a side in check are
+    // verified by making them.
     int generateLegal(Move* Out) {
         Move Tmp[kMaxMoves + 64];
         const int NP = generatePseudoLegal(Tmp);
         const int Me = Side;
+        const KingSafety KS = kingSafety(Me);
         int N = 0;
         for (int I = 0; I < NP; ++I) {
-            Undo U;
-            make(Tmp[I], &U);
-            bool Ok = !inCheck(Me);
-            if (Ok && Tmp[I].isDrop() && Tmp[I].Piece == Pawn && inCheck(Me ^ 1)) Ok = hasLegalMove();  // uchifuzume
-            unmake(Tmp[I], U);
-            if (Ok && N < kMaxMoves) Out[N++] = Tmp[I];
+            const Move& M = Tmp[I];
+            const bool PawnDrop = M.isDrop() && M.Piece == Pawn;
+            const bool NeedsCheck = KS.InCheck || PawnDrop || (!M.isDrop() && (M.Piece == King || KS.pinned(M.From)));
+            bool Ok = true;
+            if (NeedsCheck) {
+                Undo U;
+                make(M, &U);
+                Ok = !inCheck(Me);
+                if (Ok && PawnDrop && inCheck(Me ^ 1)) Ok = hasLegalMove();  // uchifuzume
+                unmake(M, U);
+            }
+            if (Ok && N < kMaxMoves) Out[N++] = M;
         }
         return N;
     }
@@ -338,12 +387,16 @@ class Position {
         Move Tmp[kMaxMoves + 64];
         const int NP = generatePseudoLegal(Tmp);
         const int Me = Side;
+        const KingSafety KS = kingSafety(Me);
         for (int I = 0; I < NP; ++I) {
+            const Move& M = Tmp[I];
+            const bool PawnDrop = M.isDrop() && M.Piece == Pawn;
+            if (!(KS.InCheck || PawnDrop || (!M.isDrop() && (M.Piece == King || KS.pinned(M.From))))) return true;
             Undo U;
-            make(Tmp[I], &U);
+            make(M, &U);
             bool Ok = !inCheck(Me);
-            if (Ok && Tmp[I].isDrop() && Tmp[I].Piece == Pawn && inCheck(Me ^ 1)) Ok = hasLegalMove();
-            unmake(Tmp[I], U);
+            if (Ok && PawnDrop && inCheck(Me ^ 1)) Ok = hasLegalMove();
+            unmake(M, U);
             if (Ok) return true;
         }
         return false;
