@@ -32,10 +32,12 @@ def worker(name, channels, blocks, slots, n, cached_with=None, own_cache=False, 
         ctx.cache_attach(cached_with)
     handles[name] = ctx
     ready.wait()
-    pos = synth.random_positions(n, seed=hash(name) % 1000)
+    pos = synth.random_positions(n, seed=100 + sorted(NAMES).index(name))
     off, idx = synth.random_legal_moves(n, seed=3, edge_rows=False)
     total = int(off[-1])
-    hashes = (np.arange(n, dtype=np.uint64) + np.uint64(hash(name) % 977)) * np.uint64(0x9E3779B97F4A7C15)
+    # distinct key ranges per worker: two workers that share the cache must not collide by construction (a collision
+    # with an equal move count is, as in the reference, served as a hit - and would fail the bit-for-bit comparison)
+    hashes = (np.arange(n, dtype=np.uint64) + np.uint64(1_000_003 * (1 + sorted(NAMES).index(name)))) * np.uint64(0x9E3779B97F4A7C15)
     bufs = []
     for s in range(slots):
         b = dict(pos=P((n,), nb.POSITION), off=P((n + 1,), np.uint32), idx=P((total,), np.uint16), legal=P((total,), np.float32),
@@ -73,6 +75,7 @@ def worker(name, channels, blocks, slots, n, cached_with=None, own_cache=False, 
     counts[name] = it
 
 
+NAMES = ["classic+cache", "classic+attached", "duo", "pair"]
 handles, ready = {}, threading.Event()
 t1 = threading.Thread(target=worker, args=("classic+cache", 128, 10, 1, 200), kwargs=dict(own_cache=True, ranked=True))
 t1.start()
