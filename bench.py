@@ -570,7 +570,8 @@ def usi_leg(args, info):
     threads = max(1, min(8, (os.cpu_count() or 4) - 2))
     out = {}
     for name, extra in (("search_threads_2_reference_default", ["--num-search-threads", "2"]),
-                        (f"search_threads_{threads}", ["--num-search-threads", str(threads)])):
+                        (f"search_threads_{threads}", ["--num-search-threads", str(threads)]),
+                        (f"search_threads_{threads}_device_cache_4GiB", ["--num-search-threads", str(threads), "--cache-mb", "4096"])):
         try:
             r = subprocess.run([exe, "--gpu", str(info.local_rank), "--channels", str(args.channels), "--blocks", str(args.blocks),
                                 "--batch-size", str(args.batch), "--seconds", "4"] + extra, capture_output=True, text=True, timeout=120)
