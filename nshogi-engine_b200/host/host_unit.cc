@@ -295,6 +295,29 @@ static int rulesChecks(int PerftDepth) {
         return false;
     };
     auto sq = [](int F, int R) { return 9 * (F - 1) + (R - 1); };
+    {   // the position with the most legal moves known in shogi: 593 (sfen R8/2K1S1SSk/4B4/9/9/9/9/9/1L1L1L3 b RBGSNLP3g3n17p 1),
+        // the bound NSB_MAX_LEGAL_MOVES comes from; 469 of them are drops, 52 promotions
+        Position P;
+        P.clear();
+        P.put(9, 1, Rook, 0);
+        P.put(7, 2, King, 0); P.put(5, 2, Silver, 0); P.put(3, 2, Silver, 0); P.put(2, 2, Silver, 0); P.put(1, 2, King, 1);
+        P.put(5, 3, Bishop, 0);
+        P.put(8, 9, Lance, 0); P.put(6, 9, Lance, 0); P.put(4, 9, Lance, 0);
+        for (int K = 0; K < 7; ++K) P.Hands[0][K] = 1;
+        P.Hands[1][0] = 17; P.Hands[1][2] = 3; P.Hands[1][4] = 3;
+        P.rehash();
+        Move Ms[kMaxMoves];
+        const int N = P.generateLegal(Ms);
+        int Drops = 0, Promotions = 0;
+        std::set<int> Slots;
+        for (int I = 0; I < N; ++I) {
+            Drops += Ms[I].isDrop();
+            Promotions += Ms[I].Promote;
+            Slots.insert(P.policyIndex(Ms[I]));
+        }
+        CHECK(N == NSB_MAX_LEGAL_MOVES && Drops == 469 && Promotions == 52);
+        CHECK((int)Slots.size() == N);   // the move-index adaptor gives every legal move its own policy slot
+    }
     {   // nifu, drop ranks, mandatory promotion
         Position P;
         P.clear();

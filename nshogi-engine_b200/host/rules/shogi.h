@@ -6,8 +6,9 @@
 // repetition / max-ply checks), src/selfplay/worker.cc:82-110 (phases), :349-358.  The library is not available to
 // this build, so the search and self-play harnesses of this repo (host/mcts_search.h, host/selfplay_real.cc,
 // host/usi_go_bench.cc) run on this restatement of the RULES OF SHOGI instead.  What pins it: the perft counts of the
-// start position (30, 900, 25470, 719731, 19861490 - public known answers for shogi move generators) and hand-made
-// positions for every special rule (nsb_host_unit --rules).  What it does not have: libnshogi's df-pn mate solver
+// start position (30, 900, 25470, 719731, 19861490 - public known answers for shogi move generators), the 593 legal
+// moves of the known maximum position, hand-made positions for every special rule, and the brute-force legality filter
+// on random playouts (nsb_host_unit).  What it does not have: libnshogi's df-pn mate solver
 // (searchworker.cc:220-240) and declaration win (27-point rule, searchworker.cc:500-520); games end by mate, by
 // four-fold repetition (draw; a perpetual check is scored as a draw too) or at max ply (draw).
 //
