@@ -653,6 +653,58 @@ def test_direct_io_on_caller_registered_buffers(nb, orc, synth, monkeypatch):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_adopted_host_ranges_are_revalidated_and_forgotten(nb, orc, synth, monkeypatch):
+    """the reference's Evaluator pins its arrays itself (cudaHostRegister, evaluator.cc:95-106) and
+    unpins + frees them BEFORE the executor is destroyed.  An adopted range must not survive that: (1) while the caller's
+    registration stands, nsb_host_register adopts it and direct I/O works on it; (2) after the caller has unregistered
+    it, registering the same address again must not trust the stale entry - the library locks the range itself;
+    (3) nsb_host_unregister forgets an adopted range without unlocking it, and leaves nsb_host_alloc memory alone."""
+    import torch
+    monkeypatch.delenv("NSB_IO", raising=False)
+    rt = torch.cuda.cudart()
+    desc = nb.net_desc(128, 1)
+    blob = nb.random_blob(desc, 3)
+    n = 32
+    fb = orc.pack(synth.random_positions(n, seed=2))
+    feat = np.zeros(n * 86 + 512, dtype=nb.FEATURE_BITBOARD)[:n * 86]
+    feat[:] = fb
+    policy = np.zeros((n, nb.POLICY_SIZE), dtype=np.float32)
+    win, draw = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    bufs = (feat, policy, win, draw)
+    with nb.Context(desc, batch_max=n, blob=blob) as ctx:
+        ctx.eval_async(0, feat, n, policy, win, draw)            # pageable: staged
+        ctx.await_(0)
+        want = policy.copy()
+        for a in bufs:                                            # the caller pins (what Evaluator does)
+            assert int(rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0
+        assert [nb.host_register(a) for a in bufs] == [False] * 4     # adopted: NSB_HOST_ALREADY_LOCKED
+        policy[...] = 0
+        l0 = ctx.launch_count()
+        ctx.eval_async(0, feat, n, policy, win, draw)            # direct I/O on the adopted ranges
+        ctx.await_(0)
+        assert ctx.launch_count() - l0 == 1 and np.array_equal(policy.view(np.uint32), want.view(np.uint32))
+        for a in bufs:                                            # ~Evaluator: the caller unpins; the entries are stale now
+            assert int(rt.cudaHostUnregister(a.ctypes.data)) == 0
+        assert [nb.host_register(a) for a in bufs] == [True] * 4      # NOT trusted: re-validated, locked by the library
+        policy[...] = 0
+        ctx.eval_async(0, feat, n, policy, win, draw)
+        ctx.await_(0)
+        assert np.array_equal(policy.view(np.uint32), want.view(np.uint32))
+        for a in bufs:
+            nb.host_unregister(a)                                 # unlocks what the library locked
+        for a in bufs:                                            # forgotten: pageable again -> staged path, same bits
+            assert int(rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0
+            assert int(rt.cudaHostUnregister(a.ctypes.data)) == 0
+        policy[...] = 0
+        ctx.eval_async(0, feat, n, policy, win, draw)
+        ctx.await_(0)
+        assert np.array_equal(policy.view(np.uint32), want.view(np.uint32))
+        pinned = nb.PinnedArray((16,), np.float32)               # nsb_host_alloc memory is not nsb_host_unregister's to forget
+        nb.host_unregister(pinned.array)
+        assert nb.host_register(pinned.array) is False
+        pinned.free()
+
+
 @pytest.mark.parametrize("channels,slots", [(128, 1), (128, 2), (256, 1)])
 def test_rank_order_of_decoded_rows(nb, orc, synth, monkeypatch, channels, slots):
     """order_out of nsb_eval_request_async: per position the permutation that sorts its decoded row by decreasing
