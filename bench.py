@@ -528,7 +528,8 @@ def selfplay_leg(args, info, rep, device):
     exe = os.path.join(ROOT, "nshogi-engine_b200", "host", "nsb_selfplay_real")
     if not os.path.exists(exe):
         return {"unavailable": "nsb_selfplay_real not built"}
-    workers = max(2, min(14, (os.cpu_count() or 4) // max(1, info.world) - 2))
+    # threads per rank: W search workers + the evaluation worker (the save worker and the main thread sleep almost always)
+    workers = max(2, min(14, (os.cpu_count() or 4) // max(1, info.world) - 1))
     cmd = [exe, "--gpu", str(info.local_rank), "--channels", "256", "--blocks", "20", "--batch-size", "512",
            "--frame-pool-size", "1024", "--num-search-workers", str(workers), "--seconds", str(args.selfplay_seconds),
            "--warmup", "1.5"]
