@@ -1,0 +1,122 @@
+// evaluation_worker_b200.h — the pipelined evaluation worker as a `worker::Worker`: the shape
+// src/selfplay/evaluationworker.{h,cc} (and, with a LeafQueue in front, src/mcts/evaluationworker.{h,cc}) take on this
+// executor, inside the reference's own threading contract (src/worker/worker.h: initializationTask() once on the worker
+// thread, then doTask() in a loop between start() and stop(); a worker is only stopped while doTask() reports idle).
+//
+// Reference doTask() (src/selfplay/evaluationworker.cc:69-117): pop up to BatchSize frames, construct 1,376 B of
+// features per frame on this thread, computeBlocking(), setEvaluation per frame, hand the frames back - the GPU idles
+// while the thread builds features and decodes, the thread idles while the GPU runs.  Here doTask() is one turn of a
+// slot ring: take what is queued, write each task's row (108-byte position record or bitboards, policy slots of its
+// legal moves, hash, row flag) into the next pinned slot, submit it (stage 1, forward, decode, cache, rank order: one
+// launch), and deliver the OLDEST slot's rows only when the ring is full or nothing is queued.  doTask() returns false
+// only when nothing is queued AND nothing is in flight, so the Worker contract's "stopped while idle" means "stopped
+// while drained": no result can arrive after await() returns.
+//
+// What a task IS stays with the caller (a selfplay::Frame, a Node* + State, ...): EvaluationClient is the four things the
+// worker needs to do with it.  PipelineT = evaluate::LeafPipeline, or anything with its surface (the CPU tests run the
+// worker on plain memory, against this repo's Worker stand-in and against the reference's own worker.cc).
+#ifndef NSHOGI_ENGINE_EVALUATION_WORKER_B200_H
+#define NSHOGI_ENGINE_EVALUATION_WORKER_B200_H
+
+#include <cstddef>
+#include <cstdint>
+#include <deque>
+#include <vector>
+
+#include "worker/worker.h"  // the reference's header when built in-tree, host/shim otherwise
+
+namespace nshogi {
+namespace engine {
+namespace evaluate {
+
+template <typename SlotT>
+class EvaluationClient {
+ public:
+    virtual ~EvaluationClient() = default;
+    // Pop up to Max queued tasks into Out (FrameQueue::get, framequeue.cc:48-84).  Wait: block briefly if none is queued.
+    virtual void take(std::size_t Max, bool Wait, std::vector<void*>& Out) = 0;
+    // Write the task's inputs into row Row of slot S; its legal moves' policy slots go to S.MoveIndices[MoveBegin ..).
+    // Returns the number of legal moves.  (evaluationworker.cc:87-92 constructAt + frame.cc:96-107 getMoveIndex)
+    virtual uint32_t fill(void* Task, SlotT& S, std::size_t Row, uint32_t MoveBegin) = 0;
+    // Row Row of the collected slot S holds the task's result (Frame::setEvaluation, evaluationworker.cc:106-108).
+    virtual void deliver(void* Task, SlotT& S, std::size_t Row) = 0;
+    // The delivered tasks go back to the search side (SearchQueue->add, evaluationworker.cc:114); clears Tasks.
+    virtual void release(std::vector<void*>& Tasks) = 0;
+};
+
+template <typename PipelineT>
+class PipelinedEvaluationWorker : public worker::Worker {
+ public:
+    using Slot = typename PipelineT::Slot;
+
+    // The pipeline is created by the caller; Bind (optional) runs once on the worker thread before the first task
+    // (the reference binds the executor's device there: selfplay/evaluationworker.cc:62-67).
+    PipelinedEvaluationWorker(PipelineT* Pipeline, EvaluationClient<Slot>* Client_, bool FromPositions, int DecodeMode,
+                              bool UseCache, bool Ranked, void (*Bind)(void*) = nullptr, void* BindArg = nullptr)
+        : worker::Worker(true), Pipe(Pipeline), Client(Client_), Positions(FromPositions), Mode(DecodeMode), Cache(UseCache),
+          Rank(Ranked), BindFn(Bind), BindArgument(BindArg), SlotTasks(Pipeline->numSlots()) {
+        spawnThread();
+    }
+
+    uint64_t batches() const { return Batches; }
+    uint64_t rows() const { return Rows; }
+
+ protected:
+    void initializationTask() override {
+        if (BindFn) BindFn(BindArgument);
+    }
+
+    bool doTask() override {
+        Tasks.clear();
+        Client->take(Pipe->batchMax(), InFlight.empty(), Tasks);
+        if (Tasks.empty()) {
+            if (InFlight.empty()) return false;  // idle AND drained: the only state in which the worker can be stopped
+            deliverOldest();
+            return true;
+        }
+        if (InFlight.size() == Pipe->numSlots()) deliverOldest();  // ring full: acquire() hands out the oldest slot
+        std::size_t K;
+        Slot& S = Pipe->acquire(&K);
+        uint32_t Off = 0;
+        for (std::size_t I = 0; I < Tasks.size(); ++I) {
+            S.MoveOffsets[I] = Off;
+            Off += Client->fill(Tasks[I], S, I, Off);
+        }
+        S.MoveOffsets[Tasks.size()] = Off;
+        SlotTasks[K].swap(Tasks);
+        Pipe->submit(K, SlotTasks[K].size(), Positions, Mode, Cache, Rank);
+        InFlight.push_back(K);
+        return true;
+    }
+
+ private:
+    void deliverOldest() {
+        const std::size_t K = InFlight.front();
+        InFlight.pop_front();
+        Slot& S = Pipe->collect(K);
+        std::vector<void*>& Ts = SlotTasks[K];
+        for (std::size_t I = 0; I < Ts.size(); ++I) Client->deliver(Ts[I], S, I);
+        Rows += Ts.size();
+        ++Batches;
+        Client->release(Ts);
+        Ts.clear();
+    }
+
+    PipelineT* Pipe;
+    EvaluationClient<Slot>* Client;
+    const bool Positions;
+    const int Mode;
+    const bool Cache, Rank;
+    void (*BindFn)(void*);
+    void* BindArgument;
+    std::vector<std::vector<void*>> SlotTasks;
+    std::deque<std::size_t> InFlight;
+    std::vector<void*> Tasks;
+    uint64_t Batches = 0, Rows = 0;
+};
+
+} // namespace evaluate
+} // namespace engine
+} // namespace nshogi
+
+#endif

@@ -7,6 +7,9 @@
 // i32 in_channels, channels, blocks, hidden + the canonical fp32 blob (tests/test_onnx_io.py compares it with
 // the Python reader bit for bit); a graph it rejects prints the reason and exits 3.
 #include <cstdio>
+#include <chrono>
+#include <mutex>
+#include <deque>
 #include <cstdlib>
 #include <cstring>
 #include <set>
@@ -24,6 +27,7 @@
 #include <thread>
 
 #include "eval_cache.h"
+#include "evaluation_worker_b200.h"
 #include "leaf_queue.h"
 #include "mcts_feed.h"
 #include "selfplay_feed.h"
@@ -592,7 +596,89 @@ static int treeStress(int Threads, std::size_t Nodes) {
     return Ok ? 0 : 1;
 }
 
+// ---- evaluation_worker_b200.h: the pipelined evaluation worker inside the worker::Worker contract, on plain memory ----
+// `--worker-cycles TASKS`: built against this repo's Worker stand-in (host/shim/worker) by the Makefile and against the
+// REFERENCE's own src/worker/worker.{h,cc} by tests/test_host_cpp.py.  Three start() / stop() / await() cycles; after
+// every await() each task pushed so far has been filled once and delivered once (a stopped worker is a drained worker).
+struct CycleTask {
+    uint32_t Id = 0;
+    std::atomic<int> Filled{0}, Delivered{0};
+    bool RowOk = true;
+};
+struct CycleClient : evaluate::EvaluationClient<FakePipeline::Slot> {
+    std::mutex M;
+    std::deque<CycleTask*> Queue;
+    std::atomic<uint64_t> Released{0};
+    void push(CycleTask* T) {
+        std::lock_guard<std::mutex> L(M);
+        Queue.push_back(T);
+    }
+    void take(std::size_t Max, bool Wait, std::vector<void*>& Out) override {
+        {
+            std::lock_guard<std::mutex> L(M);
+            while (!Queue.empty() && Out.size() < Max) {
+                Out.push_back(Queue.front());
+                Queue.pop_front();
+            }
+        }
+        if (Out.empty() && Wait) std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+    uint32_t fill(void* Task, FakePipeline::Slot& S, std::size_t Row, uint32_t MoveBegin) override {
+        CycleTask* T = static_cast<CycleTask*>(Task);
+        const uint32_t N = 1 + T->Id % 5;
+        for (uint32_t J = 0; J < N; ++J) S.MoveIndices[MoveBegin + J] = (uint16_t)(T->Id + J);
+        S.Hashes[Row] = T->Id * 2654435761ull;
+        T->Filled.fetch_add(1);
+        return N;
+    }
+    void deliver(void* Task, FakePipeline::Slot& S, std::size_t Row) override {
+        CycleTask* T = static_cast<CycleTask*>(Task);
+        const uint32_t B = S.MoveOffsets[Row], E = S.MoveOffsets[Row + 1];
+        T->RowOk = S.Hashes[Row] == T->Id * 2654435761ull && E - B == 1 + T->Id % 5 && S.MoveIndices[B] == (uint16_t)T->Id;
+        T->Delivered.fetch_add(1);
+    }
+    void release(std::vector<void*>& Tasks) override {
+        Released.fetch_add(Tasks.size());
+        Tasks.clear();
+    }
+};
+
+static int workerCycles(std::size_t Tasks) {
+    FakePipeline Pipe(3, 64);
+    CycleClient Client;
+    std::vector<CycleTask> Pool(Tasks * 3);
+    for (std::size_t I = 0; I < Pool.size(); ++I) Pool[I].Id = (uint32_t)I;
+    int Bound = 0;
+    {
+        evaluate::PipelinedEvaluationWorker<FakePipeline> W(&Pipe, &Client, true, 0, false, true,
+                                                            [](void* P) { ++*static_cast<int*>(P); }, &Bound);
+        CHECK(Bound == 1 && !W.isRunning());   // initializationTask ran on the worker thread before spawnThread returned
+        std::size_t Pushed = 0;
+        for (int Cycle = 0; Cycle < 3; ++Cycle) {
+            W.start();
+            std::thread Producer([&]() {
+                for (std::size_t I = 0; I < Tasks; ++I) {
+                    Client.push(&Pool[Pushed + I]);
+                    if ((I & 255) == 255) std::this_thread::yield();
+                }
+            });
+            Producer.join();
+            Pushed += Tasks;
+            while (Client.Released.load() < Pushed) std::this_thread::yield();
+            W.stop();
+            W.await();
+            CHECK(!W.isRunning());
+            for (std::size_t I = 0; I < Pushed; ++I) CHECK(Pool[I].Filled.load() == 1 && Pool[I].Delivered.load() == 1 && Pool[I].RowOk);
+            for (std::size_t I = Pushed; I < Pool.size(); ++I) CHECK(Pool[I].Filled.load() == 0);
+            CHECK(W.rows() == Pushed);
+        }
+        std::printf("worker cycles: %zu tasks in %llu batches over 3 start/stop/await cycles: ok\n", Pushed, (unsigned long long)W.batches());
+    }   // ~Worker joins the thread
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 3 && std::strcmp(argv[1], "--worker-cycles") == 0) return workerCycles((std::size_t)std::atol(argv[2]));
     if (argc >= 4 && std::strcmp(argv[1], "--tree-stress") == 0) return treeStress(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]));
     if (argc >= 3 && std::strcmp(argv[1], "--perft") == 0) return rulesChecks(std::atoi(argv[2]));
     if (argc >= 4 && std::strcmp(argv[1], "--queue-stress") == 0) return queueStress(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]));
@@ -658,7 +744,8 @@ int main(int argc, char** argv) {
     if (feedChecks()) return 1;  // mcts_feed.h == setEvaluation + sort + updateAncestors of the reference
     if (selfplayFeedChecks()) return 1;
     if (rulesChecks(4)) return 1;          // shogi rules: perft(1..4) of hirate + the special rules
-    if (selfplayMock(2, 24)) return 1;     // two whole games of the self-play loop against a mock evaluator
+    if (selfplayMock(2, 24)) return 1;
+    if (workerCycles(5000)) return 1;      // the pipelined evaluation worker inside the worker::Worker contract     // two whole games of the self-play loop against a mock evaluator
     std::printf("host_unit ok\n");
     return 0;
 }

@@ -8,7 +8,8 @@
 // frame queues between them (framequeue.cc).  What differs from the reference, on purpose:
 //   - rules, move generation, repetition: host/rules/shogi.h (libnshogi is not available; perft-pinned);
 //   - tree: host/mcts_search.h (PUCT with the reference's constants; no df-pn, no tree reuse between moves);
-//   - the evaluation worker does not build features and does not block per batch: it copies 108-byte position records
+//   - the evaluation worker (host/evaluation_worker_b200.h, a worker::Worker like the reference's) does not build
+//     features and does not block per batch: it copies 108-byte position records
 //     and the legal moves' policy slots into the next pinned slot, submits (stage 1, forward, gather, cache store of the
 //     raw logits, softmax and the edges' rank order all happen in ONE launch: NSB_DECODE_BOTH + order_out) and waits
 //     only for the oldest batch;
@@ -28,6 +29,7 @@
 #include <deque>
 #include <fstream>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <random>
 #include <string>
@@ -35,6 +37,7 @@
 #include <vector>
 
 #include "infer_b200.h"
+#include "evaluation_worker_b200.h"
 #include "leaf_pipeline.h"
 #include "selfplay_feed.h"
 #include "selfplay_game.h"
@@ -146,85 +149,83 @@ void saveWorker(const Options& O, SaveQueue* Queue, SaveStats* Stats, std::atomi
     }
 }
 
-void searchWorker(const Options& O, FrameQueue* SearchQueue, FrameQueue* EvaluationQueue, SaveQueue* Saves, Info* SI,
-                  std::atomic<bool>* Running) {
-    std::vector<Frame*> In, Out;
-    while (Running->load(std::memory_order_relaxed)) {
+// reference src/selfplay/worker.{h,cc}: a search worker is a worker::Worker whose doTask() takes frames off the search
+// queue, runs each one's phase machine until it needs the network, and hands them to the evaluation queue
+class SearchWorker : public worker::Worker {
+ public:
+    SearchWorker(const Options& Opt, FrameQueue* Search, FrameQueue* Evaluation, SaveQueue* Save, Info* I)
+        : worker::Worker(true), O(Opt), SearchQueue(Search), EvaluationQueue(Evaluation), Saves(Save), SI(I) {
+        spawnThread();
+    }
+
+ protected:
+    bool doTask() override {
         In.clear();
         SearchQueue->get(32, true, In);
+        if (In.empty()) return false;
         for (Frame* F : In) {
             b200::game::advance(O, *F, SI, [&](const Frame& Done) { Saves->add(b200::game::finishedGame(Done)); });
             Out.push_back(F);
         }
         EvaluationQueue->add(Out);
+        return true;
     }
-}
 
-// reference src/selfplay/evaluationworker.cc:69-117, restructured around the slot ring (see the file comment)
-void evaluationWorker(const Options& O, infer::B200* Exec, FrameQueue* EvaluationQueue, FrameQueue* SearchQueue, Info* SI,
-                      std::atomic<bool>* Running) {
-    Exec->resetGPU();
-    Exec->bindThreadToGpuNode();  // evaluator.cc:39-83
-    evaluate::LeafPipeline Pipe(Exec, (std::size_t)O.Batch);
-    const std::size_t NS = Pipe.numSlots();
-    std::vector<std::vector<Frame*>> SlotTasks(NS);
-    std::deque<std::size_t> InFlight;
-    std::vector<Frame*> Tasks;
-    auto deliver = [&](std::size_t Idx) {
-        evaluate::LeafPipeline::Slot& S = Pipe.collect(Idx);
-        std::vector<Frame*>& Fs = SlotTasks[Idx];
-        for (std::size_t I = 0; I < Fs.size(); ++I) {  // Frame::setEvaluation, frame.cc:93-136, consumer side
-            Frame* F = Fs[I];
-            const uint32_t B = S.MoveOffsets[I];
-            // gather, cache store of the raw logits and softmax (or its skip at a Gumbel root) happened on the GPU
-            // together with the rank order of the row; the Dirichlet mix of a full-search AlphaZero root is left
-            b200::game::applyEvaluation(O, *F, S.Legal + B, S.Order + B, S.WinRate[I], S.DrawRate[I]);
-            if (S.NanFlag[I]) SI->NanRows.fetch_add(1, std::memory_order_relaxed);
-            if (O.CacheMiB > 0 && S.HitFlag[I]) SI->CacheHits.fetch_add(1, std::memory_order_relaxed);
-        }
-        SI->Evals.fetch_add(Fs.size(), std::memory_order_relaxed);
+ private:
+    const Options& O;
+    FrameQueue* SearchQueue;
+    FrameQueue* EvaluationQueue;
+    SaveQueue* Saves;
+    Info* SI;
+    std::vector<Frame*> In, Out;
+};
+
+// What the pipelined evaluation worker (host/evaluation_worker_b200.h, a worker::Worker) needs to know about a frame:
+// the four steps of reference src/selfplay/evaluationworker.cc:69-117 that touch one.
+class FrameClient : public evaluate::EvaluationClient<evaluate::LeafPipeline::Slot> {
+ public:
+    FrameClient(const Options& Opt, FrameQueue* Evaluation, FrameQueue* Search, Info* I)
+        : O(Opt), EvaluationQueue(Evaluation), SearchQueue(Search), SI(I) {}
+
+    void take(std::size_t Max, bool Wait, std::vector<void*>& Out) override {  // :70-81
+        Frames.clear();
+        EvaluationQueue->get(Max, Wait, Frames);
+        for (Frame* F : Frames) Out.push_back(F);
+    }
+    uint32_t fill(void* Task, evaluate::LeafPipeline::Slot& S, std::size_t Row, uint32_t MoveBegin) override {  // :87-92
+        const Frame* F = static_cast<const Frame*>(Task);
+        F->Leaf.toRecord(&S.Positions[Row], F->MaxPly, F->BlackDraw, F->WhiteDraw);  // stage 1 runs on the GPU
+        S.Hashes[Row] = F->Leaf.Hash;
+        S.RowFlags[Row] = nshogi::engine::selfplay::rowFlags(O.Gumbel, F->LeafNode == 0);  // frame.cc:116-118
+        std::memcpy(S.MoveIndices + MoveBegin, F->LeafSlots, (std::size_t)F->NumLeafMoves * sizeof(uint16_t));
+        SI->LegalMoves.fetch_add((uint64_t)F->NumLeafMoves, std::memory_order_relaxed);
+        return (uint32_t)F->NumLeafMoves;
+    }
+    void deliver(void* Task, evaluate::LeafPipeline::Slot& S, std::size_t Row) override {  // :106-108, frame.cc:93-136
+        Frame* F = static_cast<Frame*>(Task);
+        const uint32_t B = S.MoveOffsets[Row];
+        // gather, cache store of the raw logits and softmax (or its skip at a Gumbel root) happened on the GPU
+        // together with the rank order of the row; the Dirichlet mix of a full-search AlphaZero root is left
+        b200::game::applyEvaluation(O, *F, S.Legal + B, S.Order + B, S.WinRate[Row], S.DrawRate[Row]);
+        if (S.NanFlag[Row]) SI->NanRows.fetch_add(1, std::memory_order_relaxed);
+        if (O.CacheMiB > 0 && S.HitFlag[Row]) SI->CacheHits.fetch_add(1, std::memory_order_relaxed);
+    }
+    void release(std::vector<void*>& Tasks) override {  // :114
+        SI->Evals.fetch_add(Tasks.size(), std::memory_order_relaxed);
         SI->Batches.fetch_add(1, std::memory_order_relaxed);
-        SearchQueue->add(Fs);
-    };
-    while (Running->load(std::memory_order_relaxed)) {
+        Frames.clear();
+        for (void* T : Tasks) Frames.push_back(static_cast<Frame*>(T));
+        SearchQueue->add(Frames);
         Tasks.clear();
-        EvaluationQueue->get((std::size_t)O.Batch, InFlight.empty(), Tasks);
-        if (Tasks.empty()) {
-            if (!InFlight.empty()) {
-                deliver(InFlight.front());
-                InFlight.pop_front();
-            }
-            continue;
-        }
-        if (InFlight.size() == NS) {  // ring full: the slot acquire() hands out is the oldest one
-            deliver(InFlight.front());
-            InFlight.pop_front();
-        }
-        std::size_t Idx;
-        evaluate::LeafPipeline::Slot& S = Pipe.acquire(&Idx);
-        uint32_t Off = 0;
-        uint64_t Moves = 0;
-        for (std::size_t I = 0; I < Tasks.size(); ++I) {
-            const Frame* F = Tasks[I];
-            F->Leaf.toRecord(&S.Positions[I], F->MaxPly, F->BlackDraw, F->WhiteDraw);  // stage 1 runs on the GPU
-            S.Hashes[I] = F->Leaf.Hash;
-            S.RowFlags[I] = nshogi::engine::selfplay::rowFlags(O.Gumbel, F->LeafNode == 0);  // frame.cc:116-118
-            S.MoveOffsets[I] = Off;
-            std::memcpy(S.MoveIndices + Off, F->LeafSlots, (std::size_t)F->NumLeafMoves * sizeof(uint16_t));
-            Off += (uint32_t)F->NumLeafMoves;
-            Moves += (uint64_t)F->NumLeafMoves;
-        }
-        S.MoveOffsets[Tasks.size()] = Off;
-        SI->LegalMoves.fetch_add(Moves, std::memory_order_relaxed);
-        SlotTasks[Idx].swap(Tasks);
-        Pipe.submit(Idx, SlotTasks[Idx].size(), /*FromPositions=*/true, NSB_DECODE_BOTH, /*UseCache=*/O.CacheMiB > 0, /*Ranked=*/true);
-        InFlight.push_back(Idx);
     }
-    while (!InFlight.empty()) {  // Worker::stop contract: drain before returning
-        deliver(InFlight.front());
-        InFlight.pop_front();
-    }
-}
+
+ private:
+    const Options& O;
+    FrameQueue* EvaluationQueue;
+    FrameQueue* SearchQueue;
+    Info* SI;
+    std::vector<Frame*> Frames;
+};
 
 }  // namespace
 
@@ -274,15 +275,25 @@ int main(int argc, char** argv) {
     }
     SearchQueue.add(Init);
 
-    std::atomic<bool> Running{true};
-    std::vector<std::thread> Threads;
-    Threads.emplace_back(evaluationWorker, std::cref(O), &Exec, &EvaluationQueue, &SearchQueue, &SI, &Running);
+    // reference src/selfplay/main.cc:181-211: workers are constructed (their threads initialise and wait), then started
     SaveQueue Saves;
     SaveStats Saved;
     std::atomic<bool> Saving{true};
     std::thread Saver(saveWorker, std::cref(O), &Saves, &Saved, &Saving);
+    evaluate::LeafPipeline Pipe(&Exec, (std::size_t)O.Batch);
+    FrameClient Client(O, &EvaluationQueue, &SearchQueue, &SI);
+    evaluate::PipelinedEvaluationWorker<evaluate::LeafPipeline> Evaluation(
+        &Pipe, &Client, /*FromPositions=*/true, NSB_DECODE_BOTH, /*UseCache=*/O.CacheMiB > 0, /*Ranked=*/true,
+        [](void* E) {  // on the worker thread, as selfplay/evaluationworker.cc:62-67 binds its executor
+            static_cast<infer::B200*>(E)->resetGPU();
+            static_cast<infer::B200*>(E)->bindThreadToGpuNode();  // evaluator.cc:39-83
+        },
+        &Exec);
+    std::vector<std::unique_ptr<SearchWorker>> Searchers;
     for (int W = 0; W < O.SearchWorkers; ++W)
-        Threads.emplace_back(searchWorker, std::cref(O), &SearchQueue, &EvaluationQueue, &Saves, &SI, &Running);
+        Searchers.push_back(std::make_unique<SearchWorker>(O, &SearchQueue, &EvaluationQueue, &Saves, &SI));
+    Evaluation.start();
+    for (auto& W : Searchers) W->start();
 
     std::this_thread::sleep_for(std::chrono::duration<double>(O.Warmup));
     const uint64_t E0 = SI.Evals.load(), B0 = SI.Batches.load(), R0 = SI.Records.load(), G0 = SI.Games.load();
@@ -292,10 +303,13 @@ int main(int argc, char** argv) {
     const uint64_t E1 = SI.Evals.load(), B1 = SI.Batches.load(), R1 = SI.Records.load(), G1 = SI.Games.load();
     const uint64_t H1 = SI.CacheHits.load(), T1n = SI.Terminals.load(), L1 = SI.LegalMoves.load();
     const double Sec = std::chrono::duration<double>(Clock::now() - T0).count();
-    Running.store(false);
-    SearchQueue.close();
-    EvaluationQueue.close();
-    for (auto& T : Threads) T.join();
+    // stop the search side first, then the evaluation worker: it leaves its loop only when nothing is queued and
+    // nothing is in flight (worker::Worker stops a worker while doTask() reports idle)
+    for (auto& W : Searchers) W->stop();
+    for (auto& W : Searchers) W->await();
+    Evaluation.stop();
+    Evaluation.await();
+    Searchers.clear();
     Saving.store(false);
     Saves.close();
     Saver.join();

@@ -141,6 +141,25 @@ def test_infer_contract_on_plain_buffers_is_page_locked_by_the_executor(built):
     assert rates[True] > 0.9 * rates[False]      # page-locked by the executor == allocated page-locked
 
 
+def test_pipelined_evaluation_worker_inside_the_reference_worker_contract(built, tmp_path):
+    """host/evaluation_worker_b200.h derives from worker::Worker.  Built here against the REFERENCE's own
+    src/worker/worker.{h,cc} (compiled in place, nothing copied) and run on plain memory: three start / stop / await
+    cycles, after each of which every task pushed so far has been filled once and delivered once - a stopped worker is a
+    drained worker.  (The in-tree build runs the same check against this repo's stand-in, host/shim/worker/worker.h.)"""
+    out = subprocess.run([os.path.join(built, "nsb_host_unit"), "--worker-cycles", "20000"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "cycles: ok" in out.stdout, out.stdout + out.stderr
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present on this box")
+    exe = str(tmp_path / "unit_refworker")
+    r = subprocess.run(["g++", "-std=c++20", "-O2", f"-I{ref}", f"-I{HOST}", f"-I{os.path.join(HOST, 'shim')}",
+                        f"-I{os.path.join(ROOT, 'include')}", "-o", exe, os.path.join(HOST, "host_unit.cc"),
+                        os.path.join(ref, "worker", "worker.cc"), "-lpthread"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe, "--worker-cycles", "20000"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "cycles: ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_real_rules_harnesses_fail_loudly_without_gpu(built, nb):
     if nb.device_count() > 0:
         pytest.skip("GPU present")
