@@ -34,6 +34,7 @@
 #include "move_index.h"
 #include "onnx_import.h"
 #include "selfplay_game.h"
+#include "selfplay_workers.h"
 
 using namespace nshogi::engine;
 
@@ -677,7 +678,125 @@ static int workerCycles(std::size_t Tasks) {
     return 0;
 }
 
+// ---- the whole self-play harness (host/selfplay_workers.h: search workers, pipelined evaluation worker, save worker;
+//      start-up and wind-down exactly as host/selfplay_real.cc runs them) against a mock pipeline whose collect() invents
+//      the evaluations: `--selfplay-loop WORKERS FRAMES MILLISECONDS`.  The program must END - a worker::Worker is only
+//      stopped while it reports idle - and every frame must be back in one of the two queues afterwards.
+struct MockEvalPipeline {
+    struct Slot {
+        std::vector<nsb_position> PositionsV;
+        std::vector<uint32_t> MoveOffsetsV;
+        std::vector<uint16_t> MoveIndicesV, OrderV;
+        std::vector<uint64_t> HashesV;
+        std::vector<uint8_t> RowFlagsV, NanFlagV, HitFlagV;
+        std::vector<float> LegalV, WinRateV, DrawRateV;
+        nsb_position* Positions;
+        uint32_t* MoveOffsets;
+        uint16_t *MoveIndices, *Order;
+        uint64_t* Hashes;
+        uint8_t *RowFlags, *NanFlag, *HitFlag;
+        float *Legal, *WinRate, *DrawRate;
+        std::size_t Count = 0;
+    };
+    std::vector<Slot> Slots;
+    std::size_t BatchMax, Next = 0;
+    MockEvalPipeline(std::size_t NumSlots, std::size_t B) : Slots(NumSlots), BatchMax(B) {
+        for (auto& S : Slots) {
+            S.PositionsV.resize(B); S.MoveOffsetsV.resize(B + 1); S.MoveIndicesV.resize(B * NSB_MAX_LEGAL_MOVES);
+            S.OrderV.resize(B * NSB_MAX_LEGAL_MOVES); S.HashesV.resize(B); S.RowFlagsV.resize(B); S.NanFlagV.assign(B, 0);
+            S.HitFlagV.assign(B, 0); S.LegalV.resize(B * NSB_MAX_LEGAL_MOVES); S.WinRateV.resize(B); S.DrawRateV.resize(B);
+            S.Positions = S.PositionsV.data(); S.MoveOffsets = S.MoveOffsetsV.data(); S.MoveIndices = S.MoveIndicesV.data();
+            S.Order = S.OrderV.data(); S.Hashes = S.HashesV.data(); S.RowFlags = S.RowFlagsV.data(); S.NanFlag = S.NanFlagV.data();
+            S.HitFlag = S.HitFlagV.data(); S.Legal = S.LegalV.data(); S.WinRate = S.WinRateV.data(); S.DrawRate = S.DrawRateV.data();
+        }
+    }
+    std::size_t numSlots() const { return Slots.size(); }
+    std::size_t batchMax() const { return BatchMax; }
+    Slot& acquire(std::size_t* K) { *K = Next; Next = (Next + 1) % Slots.size(); return Slots[*K]; }
+    void submit(std::size_t K, std::size_t Rows, bool, int, bool, bool) { Slots[K].Count = Rows; }
+    Slot& collect(std::size_t K) {
+        Slot& S = Slots[K];
+        for (std::size_t R = 0; R < S.Count; ++R) {
+            const uint32_t B = S.MoveOffsets[R], N = S.MoveOffsets[R + 1] - B;
+            uint64_t H = S.Hashes[R];
+            double Sum = 0.0;
+            for (uint32_t J = 0; J < N; ++J) {
+                H = H * 6364136223846793005ull + S.MoveIndices[B + J];
+                Sum += (S.Legal[B + J] = 1.0f + (float)((H >> 40) % 1000) / 250.0f);
+            }
+            for (uint32_t J = 0; J < N; ++J) {
+                S.Legal[B + J] = (float)(S.Legal[B + J] / Sum);
+                S.Order[B + J] = (uint16_t)J;
+            }
+            std::stable_sort(S.Order + B, S.Order + B + N, [&](uint16_t X, uint16_t Y) { return S.Legal[B + X] > S.Legal[B + Y]; });
+            S.WinRate[R] = 0.3f + 0.4f * (float)((S.Hashes[R] >> 20) % 1000) / 1000.0f;
+            S.DrawRate[R] = 0.05f;
+        }
+        return S;
+    }
+};
+
+static int selfplayLoop(int Workers, std::size_t Frames, int Milliseconds) {
+    using namespace b200::game;
+    HarnessOptions O;
+    O.Playouts = 12;
+    O.FullSearchRatio = 0.5;
+    std::vector<Frame> Pool(Frames);
+    FrameQueue SearchQueue, EvaluationQueue;
+    Info SI;
+    std::vector<Frame*> Init;
+    for (std::size_t I = 0; I < Pool.size(); ++I) {
+        Pool[I].MT.seed(77 * (I + 1));
+        newGame(O, Pool[I]);
+        Pool[I].MaxPly = 40;   // short games: the save path runs too
+        prepareRoot(O, Pool[I]);
+        Init.push_back(&Pool[I]);
+    }
+    SearchQueue.add(Init);
+    SaveQueue Saves;
+    SaveStats Saved;
+    std::atomic<bool> Saving{true};
+    std::thread Saver(saveWorker, std::cref(O), &Saves, &Saved, &Saving);
+    MockEvalPipeline Pipe(3, 32);
+    FrameClient<MockEvalPipeline::Slot> Client(O, &EvaluationQueue, &SearchQueue, &SI);
+    std::atomic<bool> Closing{false};
+    {
+        evaluate::PipelinedEvaluationWorker<MockEvalPipeline> Evaluation(&Pipe, &Client, true, 2, false, true);
+        std::vector<std::unique_ptr<SearchWorker>> Searchers;
+        for (int W = 0; W < Workers; ++W)
+            Searchers.push_back(std::make_unique<SearchWorker>(O, &SearchQueue, &EvaluationQueue, &Saves, &SI, &Closing));
+        Evaluation.start();
+        for (auto& W : Searchers) W->start();
+        std::this_thread::sleep_for(std::chrono::milliseconds(Milliseconds));
+        Closing.store(true);
+        for (auto& W : Searchers) W->stop();
+        for (auto& W : Searchers) W->await();
+        Evaluation.stop();
+        Evaluation.await();   // drained: nothing queued for evaluation, nothing in flight
+        CHECK(Evaluation.rows() == SI.Evals.load());
+    }
+    Saving.store(false);
+    Saves.close();
+    Saver.join();
+    // every frame is in the search queue again (the evaluation queue is empty), none lost, none twice
+    std::vector<Frame*> Left, LeftEval;
+    SearchQueue.get(Frames + 1, false, Left);
+    EvaluationQueue.get(Frames + 1, false, LeftEval);
+    CHECK(LeftEval.empty() && Left.size() == Frames);
+    std::set<Frame*> Distinct(Left.begin(), Left.end());
+    CHECK(Distinct.size() == Frames);
+    CHECK(SI.Evals.load() > Frames && SI.Records.load() > 0);
+    CHECK(Saved.Games.load() == SI.Games.load() && Saves.drained());
+    std::printf("selfplay loop: %d search workers, %zu frames, %d ms: %llu evals in %llu batches, %llu positions, %llu games saved "
+                "(%llu records): wound down, all frames accounted for: ok\n",
+                Workers, Frames, Milliseconds, (unsigned long long)SI.Evals.load(), (unsigned long long)SI.Batches.load(),
+                (unsigned long long)SI.Records.load(), (unsigned long long)Saved.Games.load(), (unsigned long long)Saved.Records.load());
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 5 && std::strcmp(argv[1], "--selfplay-loop") == 0)
+        return selfplayLoop(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]), std::atoi(argv[4]));
     if (argc >= 3 && std::strcmp(argv[1], "--worker-cycles") == 0) return workerCycles((std::size_t)std::atol(argv[2]));
     if (argc >= 4 && std::strcmp(argv[1], "--tree-stress") == 0) return treeStress(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]));
     if (argc >= 3 && std::strcmp(argv[1], "--perft") == 0) return rulesChecks(std::atoi(argv[2]));
@@ -744,8 +863,9 @@ int main(int argc, char** argv) {
     if (feedChecks()) return 1;  // mcts_feed.h == setEvaluation + sort + updateAncestors of the reference
     if (selfplayFeedChecks()) return 1;
     if (rulesChecks(4)) return 1;          // shogi rules: perft(1..4) of hirate + the special rules
-    if (selfplayMock(2, 24)) return 1;
-    if (workerCycles(5000)) return 1;      // the pipelined evaluation worker inside the worker::Worker contract     // two whole games of the self-play loop against a mock evaluator
+    if (selfplayMock(2, 24)) return 1;     // two whole games of the self-play loop against a mock evaluator
+    if (workerCycles(5000)) return 1;      // the pipelined evaluation worker inside the worker::Worker contract
+    if (selfplayLoop(2, 48, 300)) return 1; // the whole harness: starts, plays, winds down
     std::printf("host_unit ok\n");
     return 0;
 }

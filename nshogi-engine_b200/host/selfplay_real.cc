@@ -39,8 +39,7 @@
 #include "infer_b200.h"
 #include "evaluation_worker_b200.h"
 #include "leaf_pipeline.h"
-#include "selfplay_feed.h"
-#include "selfplay_game.h"
+#include "selfplay_workers.h"
 
 using namespace nshogi::engine;
 using namespace nshogi::engine::b200;
@@ -48,189 +47,21 @@ using Clock = std::chrono::steady_clock;
 
 namespace {
 
-struct Options : b200::game::GameOptions {
+struct Options : b200::game::HarnessOptions {
     int Channels = 256, Blocks = 20, Batch = 512, Frames = 1024, SearchWorkers = 4, Slots = 3, GPU = 0;
-    int CacheMiB = 0;
     double Seconds = 5.0, Warmup = 1.0;
     uint64_t Seed = 1234;
-    std::string Out;  // main.cc -o / --out: the teacher file ("" = records are counted, not written)
 };
-using b200::game::Frame;
-using b200::game::Info;
-
-class FrameQueue {  // reference src/selfplay/framequeue.h
- public:
-    void add(std::vector<Frame*>& Fs) {
-        if (Fs.empty()) return;
-        {
-            std::lock_guard<std::mutex> L(M);
-            for (Frame* F : Fs) Q.push_back(F);
-        }
-        CV.notify_all();
-        Fs.clear();
-    }
-    void get(std::size_t Max, bool Wait, std::vector<Frame*>& Out) {
-        std::unique_lock<std::mutex> L(M);
-        if (Wait) CV.wait_for(L, std::chrono::milliseconds(2), [&] { return !Q.empty() || Closed; });
-        while (!Q.empty() && Out.size() < Max) {
-            Out.push_back(Q.front());
-            Q.pop_front();
-        }
-    }
-    void close() {
-        {
-            std::lock_guard<std::mutex> L(M);
-            Closed = true;
-        }
-        CV.notify_all();
-    }
-
- private:
-    std::deque<Frame*> Q;
-    std::mutex M;
-    std::condition_variable CV;
-    bool Closed = false;
-};
-
-// reference src/selfplay/saveworker.cc: finished games are replayed and their full-search positions written as teacher
-// records (host/teacher_io.h), off the search threads
-class SaveQueue {
- public:
-    void add(teacher::FinishedGame&& G) {
-        {
-            std::lock_guard<std::mutex> L(M);
-            Q.push_back(std::move(G));
-        }
-        CV.notify_one();
-    }
-    bool get(teacher::FinishedGame* G) {
-        std::unique_lock<std::mutex> L(M);
-        CV.wait_for(L, std::chrono::milliseconds(5), [&] { return !Q.empty() || Closed; });
-        if (Q.empty()) return false;
-        *G = std::move(Q.front());
-        Q.pop_front();
-        return true;
-    }
-    void close() {
-        {
-            std::lock_guard<std::mutex> L(M);
-            Closed = true;
-        }
-        CV.notify_all();
-    }
-    bool drained() {
-        std::lock_guard<std::mutex> L(M);
-        return Q.empty();
-    }
-
- private:
-    std::deque<teacher::FinishedGame> Q;
-    std::mutex M;
-    std::condition_variable CV;
-    bool Closed = false;
-};
-
-struct SaveStats {
-    std::atomic<uint64_t> Games{0}, Records{0}, Winners[3] = {{0}, {0}, {0}};
-};
-
-void saveWorker(const Options& O, SaveQueue* Queue, SaveStats* Stats, std::atomic<bool>* Running) {
-    std::ofstream File;
-    if (!O.Out.empty()) {
-        File.open(O.Out, std::ios::binary | std::ios::trunc);
-        teacher::writeHeader(File);
-    }
-    teacher::FinishedGame G;
-    while (Running->load(std::memory_order_relaxed) || !Queue->drained()) {
-        if (!Queue->get(&G)) continue;
-        Stats->Records.fetch_add(teacher::saveGame(O.Out.empty() ? nullptr : &File, G), std::memory_order_relaxed);
-        Stats->Games.fetch_add(1, std::memory_order_relaxed);
-        Stats->Winners[G.Winner].fetch_add(1, std::memory_order_relaxed);  // SaveWorker::updateStatistics
-    }
-}
-
-// reference src/selfplay/worker.{h,cc}: a search worker is a worker::Worker whose doTask() takes frames off the search
-// queue, runs each one's phase machine until it needs the network, and hands them to the evaluation queue
-class SearchWorker : public worker::Worker {
- public:
-    SearchWorker(const Options& Opt, FrameQueue* Search, FrameQueue* Evaluation, SaveQueue* Save, Info* I)
-        : worker::Worker(true), O(Opt), SearchQueue(Search), EvaluationQueue(Evaluation), Saves(Save), SI(I) {
-        spawnThread();
-    }
-
- protected:
-    bool doTask() override {
-        In.clear();
-        SearchQueue->get(32, true, In);
-        if (In.empty()) return false;
-        for (Frame* F : In) {
-            b200::game::advance(O, *F, SI, [&](const Frame& Done) { Saves->add(b200::game::finishedGame(Done)); });
-            Out.push_back(F);
-        }
-        EvaluationQueue->add(Out);
-        return true;
-    }
-
- private:
-    const Options& O;
-    FrameQueue* SearchQueue;
-    FrameQueue* EvaluationQueue;
-    SaveQueue* Saves;
-    Info* SI;
-    std::vector<Frame*> In, Out;
-};
-
-// What the pipelined evaluation worker (host/evaluation_worker_b200.h, a worker::Worker) needs to know about a frame:
-// the four steps of reference src/selfplay/evaluationworker.cc:69-117 that touch one.
-class FrameClient : public evaluate::EvaluationClient<evaluate::LeafPipeline::Slot> {
- public:
-    FrameClient(const Options& Opt, FrameQueue* Evaluation, FrameQueue* Search, Info* I)
-        : O(Opt), EvaluationQueue(Evaluation), SearchQueue(Search), SI(I) {}
-
-    void take(std::size_t Max, bool Wait, std::vector<void*>& Out) override {  // :70-81
-        Frames.clear();
-        EvaluationQueue->get(Max, Wait, Frames);
-        for (Frame* F : Frames) Out.push_back(F);
-    }
-    uint32_t fill(void* Task, evaluate::LeafPipeline::Slot& S, std::size_t Row, uint32_t MoveBegin) override {  // :87-92
-        const Frame* F = static_cast<const Frame*>(Task);
-        F->Leaf.toRecord(&S.Positions[Row], F->MaxPly, F->BlackDraw, F->WhiteDraw);  // stage 1 runs on the GPU
-        S.Hashes[Row] = F->Leaf.Hash;
-        S.RowFlags[Row] = nshogi::engine::selfplay::rowFlags(O.Gumbel, F->LeafNode == 0);  // frame.cc:116-118
-        std::memcpy(S.MoveIndices + MoveBegin, F->LeafSlots, (std::size_t)F->NumLeafMoves * sizeof(uint16_t));
-        SI->LegalMoves.fetch_add((uint64_t)F->NumLeafMoves, std::memory_order_relaxed);
-        return (uint32_t)F->NumLeafMoves;
-    }
-    void deliver(void* Task, evaluate::LeafPipeline::Slot& S, std::size_t Row) override {  // :106-108, frame.cc:93-136
-        Frame* F = static_cast<Frame*>(Task);
-        const uint32_t B = S.MoveOffsets[Row];
-        // gather, cache store of the raw logits and softmax (or its skip at a Gumbel root) happened on the GPU
-        // together with the rank order of the row; the Dirichlet mix of a full-search AlphaZero root is left
-        b200::game::applyEvaluation(O, *F, S.Legal + B, S.Order + B, S.WinRate[Row], S.DrawRate[Row]);
-        if (S.NanFlag[Row]) SI->NanRows.fetch_add(1, std::memory_order_relaxed);
-        if (O.CacheMiB > 0 && S.HitFlag[Row]) SI->CacheHits.fetch_add(1, std::memory_order_relaxed);
-    }
-    void release(std::vector<void*>& Tasks) override {  // :114
-        SI->Evals.fetch_add(Tasks.size(), std::memory_order_relaxed);
-        SI->Batches.fetch_add(1, std::memory_order_relaxed);
-        Frames.clear();
-        for (void* T : Tasks) Frames.push_back(static_cast<Frame*>(T));
-        SearchQueue->add(Frames);
-        Tasks.clear();
-    }
-
- private:
-    const Options& O;
-    FrameQueue* EvaluationQueue;
-    FrameQueue* SearchQueue;
-    Info* SI;
-    std::vector<Frame*> Frames;
-};
+using namespace b200::game;
 
 }  // namespace
 
 int main(int argc, char** argv) {
     Options O;
+    bool Verbose = false;
+    auto stage = [&](const char* What) {
+        if (Verbose) std::fprintf(stderr, "nsb_selfplay_real: %s\n", What);
+    };
     for (int I = 1; I < argc; ++I) {
         const std::string A = argv[I];
         auto nextI = [&]() { return I + 1 < argc ? std::atoi(argv[++I]) : 0; };
@@ -250,6 +81,7 @@ int main(int argc, char** argv) {
         else if (A == "--warmup") O.Warmup = nextD();
         else if (A == "--seed") O.Seed = (uint64_t)nextI();
         else if (A == "--out" || A == "-o") O.Out = I + 1 < argc ? argv[++I] : "";
+        else if (A == "--verbose") Verbose = true;
         else {
             std::fprintf(stderr, "unknown option %s\n", A.c_str());
             return 2;
@@ -281,7 +113,7 @@ int main(int argc, char** argv) {
     std::atomic<bool> Saving{true};
     std::thread Saver(saveWorker, std::cref(O), &Saves, &Saved, &Saving);
     evaluate::LeafPipeline Pipe(&Exec, (std::size_t)O.Batch);
-    FrameClient Client(O, &EvaluationQueue, &SearchQueue, &SI);
+    FrameClient<evaluate::LeafPipeline::Slot> Client(O, &EvaluationQueue, &SearchQueue, &SI);
     evaluate::PipelinedEvaluationWorker<evaluate::LeafPipeline> Evaluation(
         &Pipe, &Client, /*FromPositions=*/true, NSB_DECODE_BOTH, /*UseCache=*/O.CacheMiB > 0, /*Ranked=*/true,
         [](void* E) {  // on the worker thread, as selfplay/evaluationworker.cc:62-67 binds its executor
@@ -289,11 +121,14 @@ int main(int argc, char** argv) {
             static_cast<infer::B200*>(E)->bindThreadToGpuNode();  // evaluator.cc:39-83
         },
         &Exec);
+    std::atomic<bool> Closing{false};
     std::vector<std::unique_ptr<SearchWorker>> Searchers;
     for (int W = 0; W < O.SearchWorkers; ++W)
-        Searchers.push_back(std::make_unique<SearchWorker>(O, &SearchQueue, &EvaluationQueue, &Saves, &SI));
+        Searchers.push_back(std::make_unique<SearchWorker>(O, &SearchQueue, &EvaluationQueue, &Saves, &SI, &Closing));
+    stage("workers constructed");
     Evaluation.start();
     for (auto& W : Searchers) W->start();
+    stage("workers started");
 
     std::this_thread::sleep_for(std::chrono::duration<double>(O.Warmup));
     const uint64_t E0 = SI.Evals.load(), B0 = SI.Batches.load(), R0 = SI.Records.load(), G0 = SI.Games.load();
@@ -305,10 +140,14 @@ int main(int argc, char** argv) {
     const double Sec = std::chrono::duration<double>(Clock::now() - T0).count();
     // stop the search side first, then the evaluation worker: it leaves its loop only when nothing is queued and
     // nothing is in flight (worker::Worker stops a worker while doTask() reports idle)
+    stage("measured; winding down");
+    Closing.store(true);
     for (auto& W : Searchers) W->stop();
     for (auto& W : Searchers) W->await();
+    stage("search workers idle");
     Evaluation.stop();
     Evaluation.await();
+    stage("evaluation worker drained");
     Searchers.clear();
     Saving.store(false);
     Saves.close();

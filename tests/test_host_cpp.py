@@ -158,6 +158,30 @@ def test_pipelined_evaluation_worker_inside_the_reference_worker_contract(built,
     assert r.returncode == 0, r.stderr
     out = subprocess.run([exe, "--worker-cycles", "20000"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "cycles: ok" in out.stdout, out.stdout + out.stderr
+    # the whole self-play harness on the reference's Worker: it must wind down (search workers never run dry on their own)
+    out = subprocess.run([exe, "--selfplay-loop", "3", "96", "500"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "all frames accounted for: ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_selfplay_harness_starts_plays_and_winds_down_cpu(built, tmp_path):
+    """host/selfplay_workers.h - the search workers, the pipelined evaluation worker and the save worker of
+    nsb_selfplay_real, started and stopped exactly as its main() does - on a mock pipeline that invents the evaluations:
+    real rules, real trees, real teacher records.  The run must END within the timeout (a worker::Worker is only
+    stopped while its doTask() reports idle; a pool of games never goes idle by itself), with every frame back in the
+    search queue exactly once and every finished game saved.  Also under -fsanitize=thread."""
+    out = subprocess.run([os.path.join(built, "nsb_host_unit"), "--selfplay-loop", "4", "128", "800"], capture_output=True,
+                         text=True, timeout=60)
+    assert out.returncode == 0 and "all frames accounted for: ok" in out.stdout, out.stdout + out.stderr
+    inc = ["-I" + HOST, "-I" + os.path.join(HOST, "shim"), "-I" + os.path.join(ROOT, "include")]
+    exe = str(tmp_path / "loop_tsan")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", *inc, "-o", exe,
+                        os.path.join(HOST, "host_unit.cc"), "-lpthread"], capture_output=True, text=True, timeout=300)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe, "--selfplay-loop", "3", "48", "400"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "all frames accounted for: ok" in out.stdout, out.stdout + out.stderr
+    assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
 
 
 def test_real_rules_harnesses_fail_loudly_without_gpu(built, nb):
