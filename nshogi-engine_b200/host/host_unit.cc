@@ -404,6 +404,95 @@ static int rulesChecks(int PerftDepth) {
         std::printf("rules: %zu random-playout positions, %zu in check, %zu with pinned pieces: generators agree\n", Positions, InCheck, WithPins);
         CHECK(Positions >= 20000 && InCheck > 300 && WithPins > 300);
     }
+    {   // declaration win, 27-point rule: king in the camp, not in check, 10 other pieces there, 28 points (black) / 27 (white)
+        Position P;
+        P.clear();
+        P.put(5, 2, King, 0); P.put(5, 9, King, 1);
+        P.put(9, 1, ProRook, 0); P.put(8, 1, Bishop, 0);                       // 5 + 5
+        for (int F = 1; F <= 7; ++F) P.put(F, 3, ProPawn, 0);                  // 7
+        P.put(1, 1, Gold, 0);                                                  // 1: 10 pieces, 18 points on the board
+        P.Hands[0][0] = 5; P.Hands[0][6] = 1;                                  // 5 pawns + a rook in hand: 10
+        P.rehash();
+        CHECK(P.canDeclare());
+        P.Hands[0][0] = 4;
+        CHECK(!P.canDeclare());                                                // 27 points are not enough for black
+        P.Hands[0][0] = 5;
+        P.Board[sq(1, 1)] = 0;
+        P.Hands[0][4] = 1;                                                     // the gold in hand instead: 28 points, 9 pieces
+        CHECK(!P.canDeclare());
+        P.Hands[0][4] = 0;
+        P.put(1, 1, Gold, 0);
+        P.put(5, 1, Gold, 1);                                                  // a white gold in front of the king
+        CHECK(P.inCheck(0) && !P.canDeclare());                                // not while in check
+        P.Board[sq(5, 1)] = 0;
+        P.Board[sq(5, 2)] = 0; P.put(5, 4, King, 0);
+        CHECK(!P.canDeclare());                                                // the king must stand inside the camp
+        // white: the mirrored position needs 27
+        Position W;
+        W.clear();
+        W.put(5, 8, King, 1); W.put(5, 1, King, 0);
+        W.put(1, 9, ProRook, 1); W.put(2, 9, Bishop, 1);
+        for (int F = 3; F <= 9; ++F) W.put(F, 7, ProPawn, 1);
+        W.put(9, 9, Gold, 1);
+        W.Hands[1][0] = 4; W.Hands[1][6] = 1;                                  // 18 + 9 = 27
+        W.Side = 1;
+        W.rehash();
+        CHECK(W.canDeclare());
+        W.Hands[1][0] = 3;
+        CHECK(!W.canDeclare());
+        W.Hands[1][0] = 4;
+        W.Side = 0;
+        CHECK(!W.canDeclare());                                                // black to move: black's king is not in white's camp
+    }
+    {   // four-fold repetition: a draw, but lost by a side that checked with every move of the cycle
+        using b200::game::Repetition;
+        using b200::game::repetitionStatus;
+        Position P;
+        P.clear();
+        P.put(5, 9, King, 0); P.put(1, 1, King, 1); P.put(1, 5, Rook, 0); P.put(9, 9, Gold, 1);
+        P.Side = 1;                                   // white to move, in check from the rook on its file
+        P.Ply = 1;
+        P.rehash();
+        std::vector<uint64_t> History{0x1234u, P.Hash};                       // (ply 0: anything)
+        std::vector<uint8_t> InCheck{0, (uint8_t)P.inCheck(1)};
+        CHECK(InCheck[1] == 1);
+        auto play = [&](int From, int To) {
+            Move Ms[kMaxMoves];
+            const int N = P.generateLegal(Ms);
+            for (int I = 0; I < N; ++I)
+                if (Ms[I].From == From && Ms[I].To == To && !Ms[I].Promote) {
+                    Position::Undo U;
+                    P.make(Ms[I], &U);
+                    History.push_back(P.Hash);
+                    InCheck.push_back(P.inCheck(P.Side) ? 1 : 0);
+                    return true;
+                }
+            return false;
+        };
+        Repetition R = Repetition::None;
+        for (int Cycle = 0; Cycle < 3; ++Cycle) {      // king 1a-2a, rook 1e-2e+, king 2a-1a, rook 2e-1e+ : black checks every time
+            CHECK(R == Repetition::None);
+            CHECK(play(sq(1, 1), sq(2, 1)) && repetitionStatus(History, InCheck) == Repetition::None);
+            CHECK(play(sq(1, 5), sq(2, 5)) && repetitionStatus(History, InCheck) == Repetition::None);
+            CHECK(play(sq(2, 1), sq(1, 1)) && repetitionStatus(History, InCheck) == Repetition::None);
+            CHECK(play(sq(2, 5), sq(1, 5)));
+            R = repetitionStatus(History, InCheck);
+        }
+        CHECK(R == Repetition::BlackLoses);            // the fourth occurrence of the start of the cycle
+        // the same cycle with one quiet move in it is an ordinary draw
+        std::vector<uint8_t> Quiet = InCheck;
+        Quiet[5] = 0;
+        CHECK(repetitionStatus(History, Quiet) == Repetition::Draw);
+        // and with the colours swapped (white's replies are the checks) white loses
+        std::vector<uint64_t> H2{1, 2, 3, 4, 5, 2, 3, 4, 5, 2, 3, 4, 5, 2};  // position "2" (ply 1, 5, 9, 13)
+        std::vector<uint8_t> C2(H2.size(), 0);
+        for (std::size_t I = 2; I < H2.size(); I += 2) C2[I] = 1;              // black to move at even plies, always in check
+        CHECK(repetitionStatus(H2, C2) == Repetition::WhiteLoses);
+        C2.assign(H2.size(), 0);
+        CHECK(repetitionStatus(H2, C2) == Repetition::Draw);
+        H2.pop_back();
+        CHECK(repetitionStatus(H2, C2) == Repetition::None);
+    }
     {   // promoted sliders keep sliding and gain the king's other steps; captures go to the hand unpromoted
         Position P;
         P.clear();
@@ -794,7 +883,65 @@ static int selfplayLoop(int Workers, std::size_t Frames, int Milliseconds) {
     return 0;
 }
 
+// ---- host cost of one self-play leaf, single thread, no GPU: `--host-cost FRAMES LEAVES`.  The three things a leaf costs
+//      the host in nsb_selfplay_real - advance() on a search worker, fill() and deliver() on the evaluation worker - timed
+//      around a free mock evaluation over a pool of games as large as the harness's (cache footprint included).
+static int hostCost(std::size_t Frames, std::size_t Leaves) {
+    using namespace b200::game;
+    using Clk = std::chrono::steady_clock;
+    HarnessOptions O;
+    std::vector<Frame> Pool(Frames);
+    Info SI;
+    for (std::size_t I = 0; I < Pool.size(); ++I) {
+        Pool[I].MT.seed(77 * (I + 1));
+        newGame(O, Pool[I]);
+        prepareRoot(O, Pool[I]);
+    }
+    std::vector<float> Row(NSB_MAX_LEGAL_MOVES);
+    std::vector<uint16_t> Order(NSB_MAX_LEGAL_MOVES), Slots(NSB_MAX_LEGAL_MOVES);
+    nsb_position Rec;
+    double TAdvance = 0, TFill = 0, TDeliver = 0;
+    uint64_t Moves = 0, Sink = 0;
+    for (std::size_t L = 0; L < Leaves; ++L) {
+        Frame& F = Pool[L % Frames];
+        const auto T0 = Clk::now();
+        advance(O, F, &SI);
+        const auto T1 = Clk::now();
+        F.Leaf.toRecord(&Rec, F.MaxPly, F.BlackDraw, F.WhiteDraw);
+        std::memcpy(Slots.data(), F.LeafSlots, (std::size_t)F.NumLeafMoves * sizeof(uint16_t));
+        const auto T2 = Clk::now();
+        Sink += Rec.board[40] + Slots[0];
+        const int N = F.NumLeafMoves;
+        uint64_t H = F.Leaf.Hash;
+        float Sum = 0.f;
+        for (int J = 0; J < N; ++J) {
+            H = H * 6364136223846793005ull + 1442695040888963407ull;
+            Sum += (Row[(size_t)J] = 1.0f + (float)(H >> 54) / 256.0f);
+        }
+        for (int J = 0; J < N; ++J) {
+            Row[(size_t)J] /= Sum;
+            Order[(size_t)J] = (uint16_t)J;
+        }
+        std::stable_sort(Order.begin(), Order.begin() + N, [&](uint16_t A, uint16_t B) { return Row[A] > Row[B]; });
+        const float Win = 0.3f + 0.4f * (float)((F.Leaf.Hash >> 20) % 1000) / 1000.0f;
+        const auto T3 = Clk::now();
+        applyEvaluation(O, F, Row.data(), Order.data(), Win, 0.05f);
+        const auto T4 = Clk::now();
+        TAdvance += std::chrono::duration<double>(T1 - T0).count();
+        TFill += std::chrono::duration<double>(T2 - T1).count();
+        TDeliver += std::chrono::duration<double>(T4 - T3).count();
+        Moves += (uint64_t)N;
+    }
+    std::printf("{\"host_cost_us_per_leaf\": {\"advance\": %.3f, \"fill\": %.3f, \"deliver\": %.3f}, \"frames\": %zu, \"leaves\": %zu, "
+                "\"avg_legal_moves\": %.1f, \"positions_played\": %llu, \"games\": %llu, \"terminals\": %llu, \"sink\": %llu}\n",
+                1e6 * TAdvance / (double)Leaves, 1e6 * TFill / (double)Leaves, 1e6 * TDeliver / (double)Leaves, Frames, Leaves,
+                (double)Moves / (double)Leaves, (unsigned long long)SI.Records.load(), (unsigned long long)SI.Games.load(),
+                (unsigned long long)SI.Terminals.load(), (unsigned long long)(Sink & 1));
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 4 && std::strcmp(argv[1], "--host-cost") == 0) return hostCost((std::size_t)std::atol(argv[2]), (std::size_t)std::atol(argv[3]));
     if (argc >= 5 && std::strcmp(argv[1], "--selfplay-loop") == 0)
         return selfplayLoop(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]), std::atoi(argv[4]));
     if (argc >= 3 && std::strcmp(argv[1], "--worker-cycles") == 0) return workerCycles((std::size_t)std::atol(argv[2]));

@@ -44,7 +44,7 @@ namespace search {
 constexpr int32_t CBase = 19652;  // searchworker.h:46
 constexpr double CInit = 1.25;    // searchworker.h:47
 
-enum Terminal : uint8_t { Open = 0, Mated = 1, DrawnGame = 2 };
+enum Terminal : uint8_t { Open = 0, Mated = 1, DrawnGame = 2, Declared = 3 };  // Declared: the side to move wins (27-point rule)
 enum NodeState : uint8_t { Fresh = 0, Claimed = 1, Ready = 2 };  // Claimed: its evaluation is in flight
 
 struct Edge {

@@ -8,9 +8,9 @@
 // host/usi_go_bench.cc) run on this restatement of the RULES OF SHOGI instead.  What pins it: the perft counts of the
 // start position (30, 900, 25470, 719731, 19861490 - public known answers for shogi move generators), the 593 legal
 // moves of the known maximum position, hand-made positions for every special rule, and the brute-force legality filter
-// on random playouts (nsb_host_unit).  What it does not have: libnshogi's df-pn mate solver
-// (searchworker.cc:220-240) and declaration win (27-point rule, searchworker.cc:500-520); games end by mate, by
-// four-fold repetition (draw; a perpetual check is scored as a draw too) or at max ply (draw).
+// on random playouts (nsb_host_unit).  What it does not have: libnshogi's mate solvers (df-pn at the root of a finished
+// game, the 3-ply search at leaves: selfplay/worker.cc:352-362,517).  Games end by mate, by declaration (27-point rule),
+// by four-fold repetition (draw; lost by a side whose every move of the cycle gave check) or at max ply (draw).
 //
 // Squares, piece codes and hand order are those of nsb_position (include/nsb.h), so a position is handed to stage 1 of
 // the executor by copying the board: square s = 9 * (file - 1) + (rank - 1); board[s] = 0 or 1 + type + 14 * colour,
@@ -401,6 +401,31 @@ class Position {
             if (Ok) return true;
         }
         return false;
+    }
+
+    // Declaration win, 27-point rule (the reference plays self-play with core::EndingRule::ER_Declare27,
+    // src/selfplay/worker.cc:143,299-317; State::canDeclare is libnshogi's).  The side to move may declare when its
+    // king stands in the opponent's camp and is not in check, at least 10 of its other pieces stand there too, and those
+    // pieces plus its hand are worth 28 points (black) / 27 (white) with rook and bishop - promoted or not - 5 and
+    // everything else 1.
+    bool canDeclare() const {
+        const int Me = Side;
+        const int K = KingSq[Me];
+        if (K == 255 || !inPromotionZone(Me, rankOf(K))) return false;
+        int Pieces = 0, Points = 0;
+        for (int F = 0; F < 9; ++F)
+            for (int R = Me == 0 ? 0 : 6; R < (Me == 0 ? 3 : 9); ++R) {
+                const int C = Board[9 * F + R];
+                if (C == 0 || colourOf(C) != Me) continue;
+                const int T = typeOf(C);
+                if (T == King) continue;
+                ++Pieces;
+                Points += (kDemoted[T] == Bishop || kDemoted[T] == Rook) ? 5 : 1;
+            }
+        if (Pieces < 10) return false;
+        for (int Slot = 0; Slot < 7; ++Slot) Points += Hands[Me][Slot] * (Slot >= 5 ? 5 : 1);
+        if (Points < (Me == 0 ? 28 : 27)) return false;
+        return !inCheck(Me);
     }
 
     uint64_t perft(int Depth) {

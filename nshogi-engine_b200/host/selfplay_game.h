@@ -6,6 +6,7 @@
 #ifndef NSHOGI_ENGINE_B200_SELFPLAY_GAME_H
 #define NSHOGI_ENGINE_B200_SELFPLAY_GAME_H
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -31,6 +32,7 @@ struct GameOptions {
 struct Frame {  // reference src/selfplay/frame.h: one game in flight
     rules::Position Root, Leaf;
     std::vector<uint64_t> History, Path;
+    std::vector<uint8_t> InCheck;            // per History entry: is the side to move in check there?
     search::Tree Tree;
     int LeafNode = -1;
     rules::Move LeafMoves[rules::kMaxMoves];
@@ -50,6 +52,7 @@ struct Frame {  // reference src/selfplay/frame.h: one game in flight
 struct Info {  // reference src/selfplay/selfplayinfo.h
     std::atomic<uint64_t> Evals{0}, Batches{0}, Records{0}, Games{0}, NanRows{0}, CacheHits{0};
     std::atomic<uint64_t> Mates{0}, Repetitions{0}, MaxPlies{0}, Terminals{0}, PliesPlayed{0}, LegalMoves{0};
+    std::atomic<uint64_t> Declarations{0}, PerpetualChecks{0};
 };
 
 // Worker::initialize, worker.cc:112-156
@@ -57,6 +60,7 @@ inline void newGame(const GameOptions& O, Frame& F) {
     F.Root.setHirate();
     F.History.clear();
     F.History.push_back(F.Root.Hash);
+    F.InCheck.assign(1, 0);
     F.GameMoves.clear();
     F.DidFullSearch.clear();
     F.Winner = teacher::WinnerNone;
@@ -89,6 +93,34 @@ inline void prepareRoot(const GameOptions& O, Frame& F) {
     F.Playouts = F.FullSearch ? (uint32_t)O.Playouts : (uint32_t)std::max(1, O.Playouts / 4);
 }
 
+// judge, worker.cc:477-488 (State::getRepetitionStatus is libnshogi's): the position that was just reached - the last
+// entry of History - has now occurred four times: a draw, unless one side gave check with every move since the first
+// occurrence (RepetitionStatus::WinRepetition / LossRepetition): that side loses.  History[I] is the position at ply I of
+// a game from hirate, so its side to move is I & 1, and InCheck[I] says whether that side is in check; "X always checked"
+// == every position after the first occurrence with X's opponent to move is a check.
+enum class Repetition { None, Draw, BlackLoses, WhiteLoses };
+inline Repetition repetitionStatus(const std::vector<uint64_t>& History, const std::vector<uint8_t>& InCheck) {
+    const uint64_t Hash = History.back();
+    int Seen = 0;
+    std::size_t First = History.size();
+    for (std::size_t I = 0; I < History.size(); ++I)
+        if (History[I] == Hash) {
+            ++Seen;
+            First = std::min(First, I);
+        }
+    if (Seen < 4) return Repetition::None;
+    for (int X = 0; X < 2; ++X) {
+        int Replies = 0, Checked = 0;
+        for (std::size_t I = First + 1; I < History.size(); ++I)
+            if ((int)(I & 1) != X) {
+                ++Replies;
+                Checked += InCheck[I];
+            }
+        if (Replies > 0 && Checked == Replies) return X == 0 ? Repetition::BlackLoses : Repetition::WhiteLoses;
+    }
+    return Repetition::Draw;
+}
+
 // Worker::transition + judge, worker.cc:520-640,476-518: play the most visited move; true when the game is over.
 inline bool transition(Frame& F, Info* SI) {
     const int Best = F.Tree.bestRootEdge();
@@ -100,10 +132,19 @@ inline bool transition(Frame& F, Info* SI) {
     F.DidFullSearch.push_back(F.FullSearch ? 1 : 0);      // Frame::pushDidFullSearch
     SI->Records.fetch_add(1, std::memory_order_relaxed);  // positions played (teacher records: full-search plies only, teacher_io.h)
     SI->PliesPlayed.fetch_add(1, std::memory_order_relaxed);
-    int Seen = 0;
-    for (uint64_t H : F.History) Seen += H == F.Root.Hash;
-    if (Seen >= 4) {
+    F.InCheck.push_back(F.Root.inCheck(F.Root.Side) ? 1 : 0);
+    const Repetition Rep = repetitionStatus(F.History, F.InCheck);
+    if (Rep != Repetition::None) {
+        if (Rep != Repetition::Draw) {
+            F.Winner = Rep == Repetition::BlackLoses ? teacher::WinnerWhite : teacher::WinnerBlack;
+            SI->PerpetualChecks.fetch_add(1, std::memory_order_relaxed);
+        }
         SI->Repetitions.fetch_add(1, std::memory_order_relaxed);
+        return true;
+    }
+    if (F.Root.canDeclare()) {  // worker.cc:490-494
+        F.Winner = F.Root.Side == 0 ? teacher::WinnerBlack : teacher::WinnerWhite;
+        SI->Declarations.fetch_add(1, std::memory_order_relaxed);
         return true;
     }
     if (F.Root.Ply >= F.MaxPly) {
@@ -157,7 +198,17 @@ inline void advance(const GameOptions& O, Frame& F, Info* SI, GameEnd&& OnGameEn
             F.Tree.backup(Node, 0.5f, 1.0f);
             continue;
         }
-        // a new leaf: terminal checks first (searchworker.cc:475-538, selfplay/worker.cc:330-372)
+        if (N.Term == search::Declared) {
+            F.Tree.backup(Node, 1.0f, 0.0f);
+            continue;
+        }
+        // a new leaf: terminal checks first (searchworker.cc:475-538, selfplay/worker.cc:270-372)
+        if (Node != 0 && F.Leaf.canDeclare()) {  // worker.cc:299-317: the side to move declares and wins
+            F.Tree.setTerminal(Node, search::Declared);
+            SI->Terminals.fetch_add(1, std::memory_order_relaxed);
+            F.Tree.backup(Node, 1.0f, 0.0f);
+            continue;
+        }
         const int NumMoves = F.Leaf.generateLegal(F.LeafMoves);
         if (NumMoves == 0) {
             F.Tree.setTerminal(Node, search::Mated);

@@ -11,8 +11,8 @@
 // (src/mcts/feedworker.cc:29-137).  Here: --num-search-threads search threads (default 2, context.h:74) descend the
 // shared tree under virtual loss, generate the leaf's moves and write its row IN PLACE into the open pinned batch
 // (host/leaf_queue.h: no queue of tuples, no copy); one evaluation thread seals and submits batches and feeds the
-// results as soon as a batch is done.  Rules: host/rules/shogi.h; tree: host/mcts_search.h, shared lock-free (no df-pn,
-// no declaration win).
+// results as soon as a batch is done.  Rules: host/rules/shogi.h; tree: host/mcts_search.h, shared lock-free (27-point declaration;
+// no mate solver).
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -118,6 +118,16 @@ int main(int argc, char** argv) {
                     T.backup(Node, 0.5f, 1.0f);
                     continue;
                 }
+                if (N.Term == search::Declared) {
+                    T.backup(Node, 1.0f, 0.0f);
+                    continue;
+                }
+            }
+            if (Node != 0 && Pos.canDeclare()) {  // 27-point declaration: the side to move wins
+                T.setTerminal(Node, search::Declared);
+                T.backup(Node, 1.0f, 0.0f);
+                Terminals.fetch_add(1, std::memory_order_relaxed);
+                continue;
             }
             const int NumMoves = Pos.generateLegal(Moves);  // expandLeaf, :164-173 - outside the lock
             const bool Mated = NumMoves == 0;
@@ -198,7 +208,7 @@ int main(int argc, char** argv) {
                 "\"cache_mb\": %d, \"cache_hit_rate\": %.4f, \"avg_legal_moves\": %.1f, \"tree_nodes\": %zu, \"submit_and_feed_fraction\": %.3f, "
                 "\"root_win_rate\": %.4f, \"pv\": \"%s\", \"net\": \"%dx%d\", \"batch_size\": %d, \"slots\": %d, "
                 "\"position\": \"hirate startpos\", \"search_threads\": %d, "
-                "\"rules\": \"real: host/rules/shogi.h + host/mcts_search.h (PUCT, virtual loss); no df-pn, no declaration win\"}\n",
+                "\"rules\": \"real: host/rules/shogi.h + host/mcts_search.h (PUCT, virtual loss, 27-point declaration); no mate solver\"}\n",
                 (double)Nodes / Sec, (unsigned long long)Nodes, Sec * 1e3, (double)Evals / Sec, Batches ? (double)Evals / (double)Batches : 0.0,
                 (unsigned long long)Batches, (unsigned long long)Terminals.load(), (unsigned long long)Collisions.load(), CacheMiB,
                 Evals ? (double)CacheHits / (double)Evals : 0.0, Evals ? (double)LegalMoves.load() / (double)Evals : 0.0, T.numNodes(),
