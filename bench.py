@@ -533,32 +533,47 @@ def selfplay_leg(args, info, rep, device):
     cmd = [exe, "--gpu", str(info.local_rank), "--channels", "256", "--blocks", "20", "--batch-size", "512",
            "--frame-pool-size", "1024", "--num-search-workers", str(workers), "--seconds", str(args.selfplay_seconds),
            "--warmup", "1.5"]
-    rep.barrier()
-    rec, err = None, None
-    try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=120 + args.selfplay_seconds)
-        if out.returncode == 0:
-            rec = json.loads(out.stdout.strip().splitlines()[-1])
-        else:
-            err = out.stderr.strip()[-300:] or f"exit code {out.returncode}"
-    except (OSError, subprocess.SubprocessError, ValueError, IndexError) as e:
-        err = repr(e)
-    # every rank takes part in the reduction, also one whose harness failed (it contributes zeros)
-    mine = {"records": rec["records"], "games": rec["games"], "evals": rec["evals"], "batches": rec["batches"],
-            "nan_rows": 0 if rec else 1} if rec else {"nan_rows": 1}
-    counters, ms_max = rep.aggregate(mine, rec["seconds"] * 1e3 if rec else 0.0, device=device)
-    if counters["nan_rows"] or rec is None:      # "nan_rows" doubles as the count of failed ranks in this reduction
-        return {"unavailable": f"self-play harness failed on {counters['nan_rows']} rank(s): {err}"}
-    return {"metric": "selfplay_positions_per_sec", "value": round(rep.whole_job_rate(counters["records"], ms_max), 1),
-            "unit": "positions/s", "leaf_evals_per_sec": round(rep.whole_job_rate(counters["evals"], ms_max), 1),
-            "games_per_sec": round(rep.whole_job_rate(counters["games"], ms_max), 2),
-            "avg_batch": round(counters["evals"] / max(counters["batches"], 1), 1), "seconds": rec["seconds"],
-            "teacher_rank0": rec.get("teacher"),
-            "config": {"workload": "self-play data generation, 20x256 ResNet, 1024 concurrent games per GPU",
-                       "batch_size": 512, "num_playouts": rec["num_playouts"], "full_search_ratio": rec["full_search_ratio"],
-                       "search_workers_per_gpu": workers, "slots": rec["slots"], "rules": rec["rules"],
-                       "decode": rec.get("decode"), "avg_legal_moves": rec.get("avg_legal_moves"),
-                       "terminal_leaves_per_eval": rec.get("terminal_leaves_per_eval")}}
+    def one_run(extra):
+        rep.barrier()
+        rec, err = None, None
+        try:
+            out = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=120 + args.selfplay_seconds)
+            if out.returncode == 0:
+                rec = json.loads(out.stdout.strip().splitlines()[-1])
+            else:
+                err = out.stderr.strip()[-300:] or f"exit code {out.returncode}"
+        except (OSError, subprocess.SubprocessError, ValueError, IndexError) as e:
+            err = repr(e)
+        # every rank takes part in the reduction, also one whose harness failed (it contributes zeros)
+        mine = {"records": rec["records"], "games": rec["games"], "evals": rec["evals"], "batches": rec["batches"],
+                "nan_rows": 0 if rec else 1} if rec else {"nan_rows": 1}
+        counters, ms_max = rep.aggregate(mine, rec["seconds"] * 1e3 if rec else 0.0, device=device)
+        if counters["nan_rows"] or rec is None:      # "nan_rows" doubles as the count of failed ranks in this reduction
+            return None, {"unavailable": f"self-play harness failed on {counters['nan_rows']} rank(s): {err}"}
+        return rec, {"metric": "selfplay_positions_per_sec", "value": round(rep.whole_job_rate(counters["records"], ms_max), 1),
+                     "unit": "positions/s", "leaf_evals_per_sec": round(rep.whole_job_rate(counters["evals"], ms_max), 1),
+                     "games_per_sec": round(rep.whole_job_rate(counters["games"], ms_max), 2),
+                     "avg_batch": round(counters["evals"] / max(counters["batches"], 1), 1), "seconds": rec["seconds"]}
+
+    rec, line = one_run([])
+    if rec is None:
+        return line
+    line["teacher_rank0"] = rec.get("teacher")
+    line["config"] = {"workload": "self-play data generation, 20x256 ResNet, 1024 concurrent games per GPU",
+                      "batch_size": 512, "num_playouts": rec["num_playouts"], "full_search_ratio": rec["full_search_ratio"],
+                      "search_workers_per_gpu": workers, "slots": rec["slots"], "rules": rec["rules"],
+                      "decode": rec.get("decode"), "avg_legal_moves": rec.get("avg_legal_moves"),
+                      "terminal_leaves_per_eval": rec.get("terminal_leaves_per_eval"), "eval_cache": "off: every leaf runs the network"}
+    # the reference's self-play runs with an evaluation cache, 1,024 MB by default (src/selfplay/main.cc:39-40,93-106):
+    # here the device-resident cache (probe kernel + store in the decode tail) of the same size
+    rec_c, line_c = one_run(["--cache-mb", "1024"])
+    if rec_c is not None:
+        line_c["cache_mb"] = 1024
+        line_c["cache_hit_rate_rank0"] = rec_c.get("cache_hit_rate")
+        line_c["what"] = ("same run with the reference's default evaluation cache size (device-resident); transpositions among the "
+                          "1,024 games of one random-init net are served by the probe kernel instead of the network")
+    line["with_eval_cache_1GiB"] = line_c
+    return line
 
 
 def usi_leg(args, info):
