@@ -19,6 +19,7 @@
 #define NSHOGI_ENGINE_EVALUATION_WORKER_B200_H
 
 #include <cstddef>
+#include <chrono>
 #include <cstdint>
 #include <deque>
 #include <vector>
@@ -60,6 +61,12 @@ class PipelinedEvaluationWorker : public worker::Worker {
 
     uint64_t batches() const { return Batches; }
     uint64_t rows() const { return Rows; }
+    // where the worker thread's time went (seconds; read after await()): writing rows, waiting for the oldest slot,
+    // handing rows back, waiting for work
+    double secondsFilling() const { return TFill; }
+    double secondsCollecting() const { return TCollect; }
+    double secondsDelivering() const { return TDeliver; }
+    double secondsTaking() const { return TTake; }
 
  protected:
     void initializationTask() override {
@@ -68,7 +75,9 @@ class PipelinedEvaluationWorker : public worker::Worker {
 
     bool doTask() override {
         Tasks.clear();
+        const auto T0 = Clock::now();
         Client->take(Pipe->batchMax(), InFlight.empty(), Tasks);
+        TTake += seconds(T0);
         if (Tasks.empty()) {
             if (InFlight.empty()) return false;  // idle AND drained: the only state in which the worker can be stopped
             deliverOldest();
@@ -76,6 +85,7 @@ class PipelinedEvaluationWorker : public worker::Worker {
         }
         if (InFlight.size() == Pipe->numSlots()) deliverOldest();  // ring full: acquire() hands out the oldest slot
         std::size_t K;
+        const auto T1 = Clock::now();
         Slot& S = Pipe->acquire(&K);
         uint32_t Off = 0;
         for (std::size_t I = 0; I < Tasks.size(); ++I) {
@@ -86,6 +96,7 @@ class PipelinedEvaluationWorker : public worker::Worker {
         SlotTasks[K].swap(Tasks);
         Pipe->submit(K, SlotTasks[K].size(), Positions, Mode, Cache, Rank);
         InFlight.push_back(K);
+        TFill += seconds(T1);
         return true;
     }
 
@@ -93,14 +104,21 @@ class PipelinedEvaluationWorker : public worker::Worker {
     void deliverOldest() {
         const std::size_t K = InFlight.front();
         InFlight.pop_front();
+        const auto T0 = Clock::now();
         Slot& S = Pipe->collect(K);
+        TCollect += seconds(T0);
+        const auto T1 = Clock::now();
         std::vector<void*>& Ts = SlotTasks[K];
         for (std::size_t I = 0; I < Ts.size(); ++I) Client->deliver(Ts[I], S, I);
         Rows += Ts.size();
         ++Batches;
         Client->release(Ts);
         Ts.clear();
+        TDeliver += seconds(T1);
     }
+
+    using Clock = std::chrono::steady_clock;
+    static double seconds(Clock::time_point Since) { return std::chrono::duration<double>(Clock::now() - Since).count(); }
 
     PipelineT* Pipe;
     EvaluationClient<Slot>* Client;
@@ -113,6 +131,7 @@ class PipelinedEvaluationWorker : public worker::Worker {
     std::deque<std::size_t> InFlight;
     std::vector<void*> Tasks;
     uint64_t Batches = 0, Rows = 0;
+    double TFill = 0, TCollect = 0, TDeliver = 0, TTake = 0;
 };
 
 } // namespace evaluate

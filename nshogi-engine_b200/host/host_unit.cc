@@ -395,7 +395,7 @@ static int rulesChecks(int PerftDepth) {
                 ++Positions;
                 const Position::KingSafety KS = P.kingSafety(Me);
                 InCheck += KS.InCheck;
-                WithPins += (KS.PinnedLo | KS.PinnedHi) != 0;
+                WithPins += KS.Pinned.any();
                 if (NF == 0) break;
                 Position::Undo U;
                 P.make(Fast[Rng() % (uint64_t)NF], &U);
@@ -863,6 +863,9 @@ static int selfplayLoop(int Workers, std::size_t Frames, int Milliseconds) {
         Evaluation.stop();
         Evaluation.await();   // drained: nothing queued for evaluation, nothing in flight
         CHECK(Evaluation.rows() == SI.Evals.load());
+        std::printf("evaluation worker: %.2f us per row filling, %.2f delivering; %.0f %% of its time waiting for frames\n",
+                    1e6 * Evaluation.secondsFilling() / (double)Evaluation.rows(), 1e6 * Evaluation.secondsDelivering() / (double)Evaluation.rows(),
+                    100.0 * Evaluation.secondsTaking() / (Evaluation.secondsTaking() + Evaluation.secondsFilling() + Evaluation.secondsDelivering() + Evaluation.secondsCollecting()));
     }
     Saving.store(false);
     Saves.close();
@@ -884,9 +887,9 @@ static int selfplayLoop(int Workers, std::size_t Frames, int Milliseconds) {
 }
 
 // ---- host cost of one self-play leaf, single thread, no GPU: `--host-cost FRAMES LEAVES`.  The three things a leaf costs
-//      the host in nsb_selfplay_real - advance() on a search worker, fill() and deliver() on the evaluation worker - timed
+//      (`--host-cost FRAMES LEAVES WARMUP_LEAVES` measures after the games have left the opening.)  The host in nsb_selfplay_real - advance() on a search worker, fill() and deliver() on the evaluation worker - timed
 //      around a free mock evaluation over a pool of games as large as the harness's (cache footprint included).
-static int hostCost(std::size_t Frames, std::size_t Leaves) {
+static int hostCost(std::size_t Frames, std::size_t Leaves, std::size_t Warmup) {
     using namespace b200::game;
     using Clk = std::chrono::steady_clock;
     HarnessOptions O;
@@ -902,8 +905,12 @@ static int hostCost(std::size_t Frames, std::size_t Leaves) {
     nsb_position Rec;
     double TAdvance = 0, TFill = 0, TDeliver = 0;
     uint64_t Moves = 0, Sink = 0;
-    for (std::size_t L = 0; L < Leaves; ++L) {
+    for (std::size_t L = 0; L < Leaves + Warmup; ++L) {
         Frame& F = Pool[L % Frames];
+        if (L == Warmup) {  // (the first plies of every game are opening positions: few drops, no checks)
+            TAdvance = TFill = TDeliver = 0;
+            Moves = 0;
+        }
         const auto T0 = Clk::now();
         advance(O, F, &SI);
         const auto T1 = Clk::now();
@@ -937,11 +944,54 @@ static int hostCost(std::size_t Frames, std::size_t Leaves) {
                 1e6 * TAdvance / (double)Leaves, 1e6 * TFill / (double)Leaves, 1e6 * TDeliver / (double)Leaves, Frames, Leaves,
                 (double)Moves / (double)Leaves, (unsigned long long)SI.Records.load(), (unsigned long long)SI.Games.load(),
                 (unsigned long long)SI.Terminals.load(), (unsigned long long)(Sink & 1));
+#ifdef NSB_PHASE_TIMING
+    const PhaseCycles& PC = phaseCycles();   // (includes the warm-up leaves)
+    const double Per = 1.0 / (double)(Leaves + Warmup);
+    std::printf("cycles per leaf: select %.0f, generate %.0f, terminal checks %.0f, expand %.0f, policy slots %.0f, transition + prepareRoot %.0f, apply staged evaluation %.0f\n",
+                PC.Select * Per, PC.Generate * Per, PC.Terminal * Per, PC.Expand * Per, PC.Slots * Per, PC.Root * Per, PC.Apply * Per);
+#endif
+    return 0;
+}
+
+// ---- `--movegen-bench`: ns per generateLegal over mid-game positions of random playouts (drops, checks, pins) -------
+static int movegenBench() {
+    using namespace b200::rules;
+    std::mt19937_64 Rng(7);
+    std::vector<Position> Sample;
+    while (Sample.size() < 4000) {
+        Position P;
+        for (int Ply = 0; Ply < 140; ++Ply) {
+            Move Ms[kMaxMoves];
+            const int N = P.generateLegal(Ms);
+            if (N == 0) break;
+            if (Ply >= 30 && Ply % 5 == 0) Sample.push_back(P);
+            Position::Undo U;
+            P.make(Ms[Rng() % (uint64_t)N], &U);
+        }
+    }
+    uint64_t Moves = 0, InCheck = 0;
+    double Best = 1e30;
+    for (int Rep = 0; Rep < 7; ++Rep) {
+        Moves = InCheck = 0;
+        const auto T0 = std::chrono::steady_clock::now();
+        for (int K = 0; K < 25; ++K)
+            for (Position& P : Sample) {
+                Move Ms[kMaxMoves];
+                Moves += (uint64_t)P.generateLegal(Ms);
+            }
+        Best = std::min(Best, std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());
+    }
+    for (Position& P : Sample) InCheck += P.inCheck(P.Side);
+    const double Calls = 25.0 * (double)Sample.size();
+    std::printf("{\"movegen_ns_per_position\": %.1f, \"ns_per_legal_move\": %.2f, \"avg_legal_moves\": %.1f, \"positions\": %zu, \"in_check\": %.3f}\n",
+                1e9 * Best / Calls, 1e9 * Best / (double)Moves, (double)Moves / Calls, Sample.size(), (double)InCheck / (double)Sample.size());
     return 0;
 }
 
 int main(int argc, char** argv) {
-    if (argc >= 4 && std::strcmp(argv[1], "--host-cost") == 0) return hostCost((std::size_t)std::atol(argv[2]), (std::size_t)std::atol(argv[3]));
+    if (argc >= 2 && std::strcmp(argv[1], "--movegen-bench") == 0) return movegenBench();
+    if (argc >= 4 && std::strcmp(argv[1], "--host-cost") == 0)
+        return hostCost((std::size_t)std::atol(argv[2]), (std::size_t)std::atol(argv[3]), argc >= 5 ? (std::size_t)std::atol(argv[4]) : 0);
     if (argc >= 5 && std::strcmp(argv[1], "--selfplay-loop") == 0)
         return selfplayLoop(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]), std::atoi(argv[4]));
     if (argc >= 3 && std::strcmp(argv[1], "--worker-cycles") == 0) return workerCycles((std::size_t)std::atol(argv[2]));

@@ -53,6 +53,7 @@ struct Edge {
     int32_t Child;  // -1: not created yet
     uint32_t CVisits, CVirtualLoss;
     float CWinAcc, CDrawAcc;
+    int32_t ChildEdges;  // hint: EdgeBegin of the child once it has been expanded (-1 before); only ever used to prefetch
 };
 
 struct Node {
@@ -141,6 +142,14 @@ class Tree {
                 if (Ref2.compare_exchange_strong(Child, NewIdx, std::memory_order_acq_rel)) Child = NewIdx;
                 // else: another thread created the child first (Child now holds its index); ours stays unused
             }
+            // A descent is a chain of dependent cache misses - node, its edges, the next node ... - through trees that
+            // do not fit any cache (1,024 games per GPU): ask for the child's node and its edges together, now.
+            __builtin_prefetch(&NodesP[Child]);
+            const int32_t Hint = relaxed(EdgesP[EdgeIdx].ChildEdges);
+            if (Hint >= 0) {
+                __builtin_prefetch(&EdgesP[Hint]);
+                __builtin_prefetch(reinterpret_cast<const char*>(&EdgesP[Hint]) + 64);
+            }
             rules::Position::Undo U;
             Pos.make(EdgesP[EdgeIdx].M, &U);
             if (Path) Path->push_back(Pos.Hash);
@@ -167,7 +176,8 @@ class Tree {
         L.EdgeBegin = (int32_t)Begin;
         L.NumEdges = (uint16_t)N;
         Edge* E = EdgesP + Begin;
-        for (int I = 0; I < N; ++I) E[I] = Edge{Moves[I], 0.f, -1, 0u, 0u, 0.f, 0.f};
+        for (int I = 0; I < N; ++I) E[I] = Edge{Moves[I], 0.f, -1, 0u, 0u, 0.f, 0.f, -1};
+        if (L.ParentEdge >= 0) std::atomic_ref<int32_t>(EdgesP[L.ParentEdge].ChildEdges).store((int32_t)Begin, std::memory_order_relaxed);
         return true;
     }
 

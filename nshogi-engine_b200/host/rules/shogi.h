@@ -53,8 +53,25 @@ struct Move {
     bool operator==(const Move& O) const { return From == O.From && To == O.To && Promote == O.Promote; }
 };
 
-inline int fileOf(int S) { return S / 9; }  // 0..8 (file - 1)
-inline int rankOf(int S) { return S % 9; }  // 0..8 (rank - 1); black's camp is ranks 7..9 (6..8 here)
+struct SquareTables {
+    uint8_t File[81], Rank[81];
+    uint8_t Type[32], Colour[32];  // of a board code 1 + type + 14 * colour (entry 0: empty)
+};
+constexpr SquareTables makeSquareTables() {
+    SquareTables T{};
+    for (int S = 0; S < 81; ++S) {
+        T.File[S] = (uint8_t)(S / 9);
+        T.Rank[S] = (uint8_t)(S % 9);
+    }
+    for (int C = 0; C < 32; ++C) {
+        T.Type[C] = C ? (uint8_t)((C - 1) % 14) : 0;
+        T.Colour[C] = C ? (uint8_t)((C - 1) / 14) : 0;
+    }
+    return T;
+}
+constexpr SquareTables kSq = makeSquareTables();
+inline int fileOf(int S) { return kSq.File[S]; }  // 0..8 (file - 1)
+inline int rankOf(int S) { return kSq.Rank[S]; }  // 0..8 (rank - 1); black's camp is ranks 7..9 (6..8 here)
 inline bool onBoard(int F, int R) { return F >= 0 && F < 9 && R >= 0 && R < 9; }
 
 struct ZobristKeys {
@@ -85,6 +102,53 @@ inline const ZobristKeys& zobrist() {
     return K;
 }
 
+// step / slide tables in BLACK's orientation (forward = rank - 1); white's are the same with the rank step negated
+constexpr bool stepsTo(int Type, int Df, int Dr) {  // can a black piece of Type step by (Df, Dr)?
+    const bool Fwd = Dr == -1, Back = Dr == 1, Side_ = Dr == 0;
+    const int Af = Df < 0 ? -Df : Df;
+    switch (Type) {
+    case Pawn: return Df == 0 && Fwd;
+    case Knight: return Af == 1 && Dr == -2;
+    case Silver: return (Fwd && Af <= 1) || (Back && Af == 1);
+    case Gold: case ProPawn: case ProLance: case ProKnight: case ProSilver:
+        return (Fwd && Af <= 1) || (Side_ && Af == 1) || (Back && Df == 0);
+    case King: return Af <= 1 && Dr >= -1 && Dr <= 1 && (Df != 0 || Dr != 0);
+    case ProBishop: return Af + (Dr < 0 ? -Dr : Dr) == 1;  // orthogonal king steps (the diagonals slide)
+    case ProRook: return Af == 1 && (Dr == 1 || Dr == -1);  // diagonal king steps (the orthogonals slide)
+    default: return false;
+    }
+}
+constexpr bool slidesAlong(int Type, int Df, int Dr) {  // black orientation, unit direction
+    switch (Type) {
+    case Lance: return Df == 0 && Dr == -1;
+    case Bishop: case ProBishop: return Df != 0 && Dr != 0;
+    case Rook: case ProRook: return (Df == 0) != (Dr == 0);
+    default: return false;
+    }
+}
+
+// The 10 steps (8 neighbours + the two knight jumps) and the 8 slide directions, black's orientation; which of them
+// a piece type uses is a bit mask computed once from stepsTo / slidesAlong.
+constexpr int8_t kSteps[10][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {-1, -2}, {1, -2}};
+constexpr int8_t kDirs[8][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}};
+struct TypeDirs {
+    uint16_t Step[NumPieceTypes];
+    uint8_t Slide[NumPieceTypes];
+};
+constexpr TypeDirs makeTypeDirs() {
+    TypeDirs T{};
+    for (int Type = 0; Type < NumPieceTypes; ++Type) {
+        T.Step[Type] = 0;
+        T.Slide[Type] = 0;
+        for (int D = 0; D < 10; ++D)
+            if (stepsTo(Type, kSteps[D][0], kSteps[D][1])) T.Step[Type] |= (uint16_t)(1u << D);
+        for (int D = 0; D < 8; ++D)
+            if (slidesAlong(Type, kDirs[D][0], kDirs[D][1])) T.Slide[Type] |= (uint8_t)(1u << D);
+    }
+    return T;
+}
+constexpr TypeDirs kTypeDirs = makeTypeDirs();
+
 class Position {
  public:
     uint8_t Board[81];
@@ -95,8 +159,8 @@ class Position {
     uint64_t Hash = 0;
 
     static int code(int Type, int Colour) { return 1 + Type + 14 * Colour; }
-    static int typeOf(int Code) { return (Code - 1) % 14; }
-    static int colourOf(int Code) { return (Code - 1) / 14; }
+    static int typeOf(int Code) { return kSq.Type[Code]; }
+    static int colourOf(int Code) { return kSq.Colour[Code]; }
 
     Position() { setHirate(); }
 
@@ -139,56 +203,27 @@ class Position {
     }
 
     // ---- attacks -------------------------------------------------------------------------------------------------
-    // step / slide tables in BLACK's orientation (forward = rank - 1); white's are the same with the rank step negated
-    static bool stepsTo(int Type, int Df, int Dr) {  // can a black piece of Type step by (Df, Dr)?
-        const bool Fwd = Dr == -1, Back = Dr == 1, Side_ = Dr == 0;
-        const int Af = Df < 0 ? -Df : Df;
-        switch (Type) {
-        case Pawn: return Df == 0 && Fwd;
-        case Knight: return Af == 1 && Dr == -2;
-        case Silver: return (Fwd && Af <= 1) || (Back && Af == 1);
-        case Gold: case ProPawn: case ProLance: case ProKnight: case ProSilver:
-            return (Fwd && Af <= 1) || (Side_ && Af == 1) || (Back && Df == 0);
-        case King: return Af <= 1 && Dr >= -1 && Dr <= 1 && (Df != 0 || Dr != 0);
-        case ProBishop: return Af + (Dr < 0 ? -Dr : Dr) == 1;  // orthogonal king steps (the diagonals slide)
-        case ProRook: return Af == 1 && (Dr == 1 || Dr == -1);  // diagonal king steps (the orthogonals slide)
-        default: return false;
-        }
-    }
-    static bool slidesAlong(int Type, int Df, int Dr) {  // black orientation, unit direction
-        switch (Type) {
-        case Lance: return Df == 0 && Dr == -1;
-        case Bishop: case ProBishop: return Df != 0 && Dr != 0;
-        case Rook: case ProRook: return (Df == 0) != (Dr == 0);
-        default: return false;
-        }
-    }
-
     // Is square S attacked by a piece of colour By?
     bool attacked(int S, int By) const {
         const int F = fileOf(S), R = rankOf(S);
-        const int Sign = By == 0 ? 1 : -1;  // an attacker of colour By at T steps (Df, Sign * Dr_black) to reach S
-        // steps (including the knight's)
-        static const int8_t Steps[10][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {-1, -2}, {1, -2}};
-        for (const auto& D : Steps) {
-            // the attacker moves by (D0, Sign * D1): it stands at S - that
-            const int Af = F - D[0], Ar = R - Sign * D[1];
+        const int Sign = By == 0 ? 1 : -1;  // an attacker of colour By moves by (D0, Sign * D1): it stands at S - that
+        for (int D = 0; D < 10; ++D) {
+            const int Af = F - kSteps[D][0], Ar = R - Sign * kSteps[D][1];
             if (!onBoard(Af, Ar)) continue;
             const int C = Board[9 * Af + Ar];
-            if (C && colourOf(C) == By && stepsTo(typeOf(C), D[0], D[1])) return true;
+            if (C && colourOf(C) == By && ((kTypeDirs.Step[typeOf(C)] >> D) & 1u)) return true;
         }
-        // slides
-        static const int8_t Dirs[8][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}};
-        for (const auto& D : Dirs) {
-            int Af = F - D[0], Ar = R - Sign * D[1];
+        for (int D = 0; D < 8; ++D) {
+            const int Df = kDirs[D][0], Dr = Sign * kDirs[D][1];
+            int Af = F - Df, Ar = R - Dr;
             while (onBoard(Af, Ar)) {
                 const int C = Board[9 * Af + Ar];
                 if (C) {
-                    if (colourOf(C) == By && slidesAlong(typeOf(C), D[0], D[1])) return true;
+                    if (colourOf(C) == By && ((kTypeDirs.Slide[typeOf(C)] >> D) & 1u)) return true;
                     break;
                 }
-                Af -= D[0];
-                Ar -= Sign * D[1];
+                Af -= Df;
+                Ar -= Dr;
             }
         }
         return false;
@@ -271,47 +306,54 @@ class Position {
     int generatePseudoLegal(Move* Out) const {
         int N = 0;
         const int Me = Side, Sign = Me == 0 ? 1 : -1;
-        static const int8_t Steps[10][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}, {-1, -2}, {1, -2}};
-        static const int8_t Dirs[8][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}};
-        auto emit = [&](int From, int To, int Type) {
-            const int Rf = rankOf(From), Rt = rankOf(To);
-            const bool Promotable = kPromoted[Type] >= 0 && (inPromotionZone(Me, Rf) || inPromotionZone(Me, Rt));
-            if (Promotable) Out[N++] = Move{(uint8_t)From, (uint8_t)To, 1, (uint8_t)Type};
+        // a move from rank Rf to rank Rt (0 = black's far rank): promotion where the piece can, staying unpromoted where it may
+        auto emit = [&](int From, int To, int Type, int Rf, int Rt) {
+            if (kPromoted[Type] >= 0 && (inPromotionZone(Me, Rf) || inPromotionZone(Me, Rt))) Out[N++] = Move{(uint8_t)From, (uint8_t)To, 1, (uint8_t)Type};
             if (canStay(Type, Me, Rt)) Out[N++] = Move{(uint8_t)From, (uint8_t)To, 0, (uint8_t)Type};
         };
         bool PawnOnFile[9] = {false, false, false, false, false, false, false, false, false};
-        for (int S = 0; S < 81; ++S) {
-            const int C = Board[S];
-            if (!C || colourOf(C) != Me) continue;
-            const int Type = typeOf(C), F = fileOf(S), R = rankOf(S);
-            if (Type == Pawn) PawnOnFile[F] = true;
-            for (const auto& D : Steps) {
-                if (!stepsTo(Type, D[0], D[1])) continue;
-                const int Tf = F + D[0], Tr = R + Sign * D[1];
-                if (!onBoard(Tf, Tr)) continue;
-                const int T = Board[9 * Tf + Tr];
-                if (T && colourOf(T) == Me) continue;
-                emit(S, 9 * Tf + Tr, Type);
-            }
-            for (const auto& D : Dirs) {
-                if (!slidesAlong(Type, D[0], D[1])) continue;
-                int Tf = F + D[0], Tr = R + Sign * D[1];
-                while (onBoard(Tf, Tr)) {
-                    const int T = Board[9 * Tf + Tr];
-                    if (T && colourOf(T) == Me) break;
-                    emit(S, 9 * Tf + Tr, Type);
-                    if (T) break;
-                    Tf += D[0];
-                    Tr += Sign * D[1];
+        uint8_t Empty[81];
+        int NumEmpty = 0;
+        for (int F = 0, S = 0; F < 9; ++F)
+            for (int R = 0; R < 9; ++R, ++S) {
+                const int C = Board[S];
+                if (!C) {
+                    Empty[NumEmpty++] = (uint8_t)S;
+                    continue;
+                }
+                if (colourOf(C) != Me) continue;
+                const int Type = typeOf(C);
+                if (Type == Pawn) PawnOnFile[F] = true;
+                for (unsigned Mask = kTypeDirs.Step[Type]; Mask; Mask &= Mask - 1) {
+                    const int D = __builtin_ctz(Mask);
+                    const int Tf = F + kSteps[D][0], Tr = R + Sign * kSteps[D][1];
+                    if (!onBoard(Tf, Tr)) continue;
+                    const int To = 9 * Tf + Tr, T = Board[To];
+                    if (T && colourOf(T) == Me) continue;
+                    emit(S, To, Type, R, Tr);
+                }
+                for (unsigned Mask = kTypeDirs.Slide[Type]; Mask; Mask &= Mask - 1) {
+                    const int D = __builtin_ctz(Mask);
+                    const int Df = kDirs[D][0], Dr = Sign * kDirs[D][1], Step = 9 * Df + Dr;
+                    int Tf = F + Df, Tr = R + Dr, To = S + Step;
+                    while (onBoard(Tf, Tr)) {
+                        const int T = Board[To];
+                        if (T && colourOf(T) == Me) break;
+                        emit(S, To, Type, R, Tr);
+                        if (T) break;
+                        Tf += Df;
+                        Tr += Dr;
+                        To += Step;
+                    }
                 }
             }
-        }
         for (int K = 0; K < 7; ++K) {
             if (!Hands[Me][K]) continue;
             const int Type = kHandPiece[K];
-            for (int S = 0; S < 81; ++S) {
-                if (Board[S]) continue;
-                if (!canStay(Type, Me, rankOf(S))) continue;
+            const int MinRel = Type == Knight ? 2 : (Type == Pawn || Type == Lance) ? 1 : 0;  // canStay
+            for (int J = 0; J < NumEmpty; ++J) {
+                const int S = Empty[J], R = rankOf(S);
+                if ((Me == 0 ? R : 8 - R) < MinRel) continue;
                 if (Type == Pawn && PawnOnFile[fileOf(S)]) continue;  // nifu
                 Out[N++] = Move{(uint8_t)(81 + K), (uint8_t)S, 0, (uint8_t)Type};
             }
@@ -319,89 +361,111 @@ class Position {
         return N;
     }
 
-    // Squares of the mover's pieces that are pinned to its king (bit per square), and whether the king is in check.
-    // A piece is pinned when it is the only piece between its king and an enemy slider that moves along that ray.
+    // King safety of one side: the squares of its pieces that are pinned to its king (a piece is pinned when it is the
+    // only piece between its king and an enemy slider that moves along that ray), the pieces that give check, and - for
+    // a single check - the squares on which a move of another piece answers it: the checker's own square and, for a
+    // slider, the squares between it and the king.
+    struct SquareSet {
+        uint64_t Lo = 0;   // squares 0..63
+        uint32_t Hi = 0;   // squares 64..80
+        void add(int S) {
+            if (S < 64) Lo |= 1ull << S;
+            else Hi |= 1u << (S - 64);
+        }
+        bool has(int S) const { return S < 64 ? (Lo >> S) & 1u : (Hi >> (S - 64)) & 1u; }
+        bool any() const { return (Lo | Hi) != 0; }
+    };
     struct KingSafety {
-        uint64_t PinnedLo = 0;   // squares 0..63
-        uint32_t PinnedHi = 0;   // squares 64..80
+        SquareSet Pinned, Answer;
+        int NumCheckers = 0;
         bool InCheck = false;
-        bool pinned(int S) const { return S < 64 ? (PinnedLo >> S) & 1u : (PinnedHi >> (S - 64)) & 1u; }
+        bool pinned(int S) const { return Pinned.has(S); }
     };
     KingSafety kingSafety(int Colour) const {
         KingSafety K;
         const int Ks = KingSq[Colour];
         if (Ks == 255) return K;
-        K.InCheck = attacked(Ks, Colour ^ 1);
         const int F = fileOf(Ks), R = rankOf(Ks), Enemy = Colour ^ 1;
-        const int Sign = Enemy == 0 ? 1 : -1;  // an enemy slider that moves by (D0, Sign * D1) towards the king
-        static const int8_t Dirs[8][2] = {{0, -1}, {1, -1}, {1, 0}, {1, 1}, {0, 1}, {-1, 1}, {-1, 0}, {-1, -1}};
-        for (const auto& D : Dirs) {
-            int Af = F - D[0], Ar = R - Sign * D[1], Own = -1;
+        const int Sign = Enemy == 0 ? 1 : -1;  // an enemy piece that moves by (D0, Sign * D1) towards the king
+        for (int D = 0; D < 10; ++D) {
+            const int Af = F - kSteps[D][0], Ar = R - Sign * kSteps[D][1];
+            if (!onBoard(Af, Ar)) continue;
+            const int C = Board[9 * Af + Ar];
+            if (C && colourOf(C) == Enemy && ((kTypeDirs.Step[typeOf(C)] >> D) & 1u)) {
+                if (K.NumCheckers++ == 0) K.Answer.add(9 * Af + Ar);
+            }
+        }
+        for (int D = 0; D < 8; ++D) {
+            const int Df = kDirs[D][0], Dr = Sign * kDirs[D][1];
+            int Af = F - Df, Ar = R - Dr, Own = -1;
+            SquareSet Ray;
             while (onBoard(Af, Ar)) {
                 const int Sq = 9 * Af + Ar, C = Board[Sq];
+                Ray.add(Sq);
                 if (C) {
                     if (colourOf(C) == Colour) {
                         if (Own >= 0) break;  // two own pieces in the way
                         Own = Sq;
                     } else {
-                        if (Own >= 0 && slidesAlong(typeOf(C), D[0], D[1])) {
-                            if (Own < 64) K.PinnedLo |= 1ull << Own;
-                            else K.PinnedHi |= 1u << (Own - 64);
+                        if ((kTypeDirs.Slide[typeOf(C)] >> D) & 1u) {
+                            if (Own >= 0) K.Pinned.add(Own);
+                            else if (K.NumCheckers++ == 0) K.Answer = Ray;
                         }
                         break;
                     }
                 }
-                Af -= D[0];
-                Ar -= Sign * D[1];
+                Af -= Df;
+                Ar -= Dr;
             }
         }
+        K.InCheck = K.NumCheckers > 0;
         return K;
     }
 
-    // Legal moves: the mover's king is not left in check; a pawn drop that mates is illegal (uchifuzume).  When the
-    // mover is not in check, a move of a piece that is neither the king nor pinned, and any drop, cannot expose the
-    // king and is legal as generated; only king moves, moves of pinned pieces and every move of a side in check are
-    // verified by making them.
-    int generateLegal(Move* Out) {
+    // Legal moves: the mover's king is not left in check; a pawn drop that mates is illegal (uchifuzume).  Most moves
+    // are decided without touching the board: not in check, a move of a piece that is neither the king nor pinned, and
+    // any drop, cannot expose the king; in a single check a non-king move must land on an answering square (capture the
+    // checker or interpose), in a double check only the king moves.  A king move asks whether its target is attacked with
+    // the king off the board; moves of pinned pieces and the one pawn drop that gives check (the square in front of the
+    // enemy king) are verified by making them.
+    template <bool FirstOnly>
+    int legalMoves(Move* Out) {
         Move Tmp[kMaxMoves + 64];
         const int NP = generatePseudoLegal(Tmp);
         const int Me = Side;
         const KingSafety KS = kingSafety(Me);
+        const int EnemyKing = KingSq[Me ^ 1];
+        // the square from which a pawn of the mover attacks the enemy king (same file, one rank behind it from the mover's view)
+        const int PawnCheckSq = EnemyKing == 255 ? -1
+                                : Me == 0 ? (rankOf(EnemyKing) < 8 ? EnemyKing + 1 : -1)
+                                          : (rankOf(EnemyKing) > 0 ? EnemyKing - 1 : -1);
         int N = 0;
         for (int I = 0; I < NP; ++I) {
             const Move& M = Tmp[I];
-            const bool PawnDrop = M.isDrop() && M.Piece == Pawn;
-            const bool NeedsCheck = KS.InCheck || PawnDrop || (!M.isDrop() && (M.Piece == King || KS.pinned(M.From)));
+            const bool Drop = M.isDrop(), KingMove = !Drop && M.Piece == King;
+            if (KS.InCheck && !KingMove && (KS.NumCheckers > 1 || !KS.Answer.has(M.To))) continue;
+            const bool MatingDrop = Drop && M.Piece == Pawn && M.To == PawnCheckSq;
             bool Ok = true;
-            if (NeedsCheck) {
+            if (KingMove) {  // is the target attacked once the king has left its square (it may have shielded the target)?
+                const uint8_t KingCode = Board[M.From];
+                Board[M.From] = 0;
+                Ok = !attacked(M.To, Me ^ 1);
+                Board[M.From] = KingCode;
+            } else if (MatingDrop || (!Drop && KS.pinned(M.From))) {
                 Undo U;
                 make(M, &U);
                 Ok = !inCheck(Me);
-                if (Ok && PawnDrop && inCheck(Me ^ 1)) Ok = hasLegalMove();  // uchifuzume
+                if (Ok && MatingDrop) Ok = hasLegalMove();  // uchifuzume
                 unmake(M, U);
             }
-            if (Ok && N < kMaxMoves) Out[N++] = M;
+            if (!Ok) continue;
+            if (FirstOnly) return 1;
+            if (N < kMaxMoves) Out[N++] = M;
         }
         return N;
     }
-    bool hasLegalMove() {
-        Move Tmp[kMaxMoves + 64];
-        const int NP = generatePseudoLegal(Tmp);
-        const int Me = Side;
-        const KingSafety KS = kingSafety(Me);
-        for (int I = 0; I < NP; ++I) {
-            const Move& M = Tmp[I];
-            const bool PawnDrop = M.isDrop() && M.Piece == Pawn;
-            if (!(KS.InCheck || PawnDrop || (!M.isDrop() && (M.Piece == King || KS.pinned(M.From))))) return true;
-            Undo U;
-            make(M, &U);
-            bool Ok = !inCheck(Me);
-            if (Ok && PawnDrop && inCheck(Me ^ 1)) Ok = hasLegalMove();
-            unmake(M, U);
-            if (Ok) return true;
-        }
-        return false;
-    }
+    int generateLegal(Move* Out) { return legalMoves<false>(Out); }
+    bool hasLegalMove() { return legalMoves<true>(nullptr) != 0; }
 
     // Declaration win, 27-point rule (the reference plays self-play with core::EndingRule::ER_Declare27,
     // src/selfplay/worker.cc:143,299-317; State::canDeclare is libnshogi's).  The side to move may declare when its

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <limits>
 #include <random>
 #include <vector>
@@ -47,6 +48,12 @@ struct Frame {  // reference src/selfplay/frame.h: one game in flight
     std::vector<rules::Move> GameMoves;      // the game so far (State::getHistoryMove)
     std::vector<uint8_t> DidFullSearch;      // per ply (Frame::getDidFullSearch, frame.h)
     uint8_t Winner = teacher::WinnerNone;
+    // the leaf's evaluation as the evaluation worker left it (stageEvaluation), applied by the search worker that takes
+    // the frame next (SelfplayPhase::Backpropagation runs on the search workers in the reference too, worker.cc:94-96)
+    bool EvalPending = false;
+    float EvalWin = 0.f, EvalDraw = 0.f;
+    float EvalRow[rules::kMaxMoves];
+    uint16_t EvalOrder[rules::kMaxMoves];
 };
 
 struct Info {  // reference src/selfplay/selfplayinfo.h
@@ -82,12 +89,8 @@ inline void prepareRoot(const GameOptions& O, Frame& F) {
     if (O.Gumbel) {
         std::uniform_real_distribution<double> D(std::numeric_limits<double>::min(), 1.0);
         for (double& X : F.Noise) X = -std::log(-std::log(D(F.MT)));
-    } else {
-        std::gamma_distribution<double> D(0.15, 1.0);
-        double Sum = 0.0;
-        for (double& X : F.Noise) Sum += (X = D(F.MT));
-        for (double& X : F.Noise) X /= Sum;
     }
+    // (the Dirichlet noise of an AlphaZero root is drawn when the root's evaluation arrives: drawRootNoise)
     std::uniform_real_distribution<double> U(0.0, 1.0);
     F.FullSearch = U(F.MT) <= O.FullSearchRatio;
     F.Playouts = F.FullSearch ? (uint32_t)O.Playouts : (uint32_t)std::max(1, O.Playouts / 4);
@@ -171,24 +174,57 @@ inline teacher::FinishedGame finishedGame(const Frame& F) {
     return G;
 }
 
+// -DNSB_PHASE_TIMING: cycles per phase of advance() (host_unit --host-cost prints them); compiled out otherwise.
+#ifdef NSB_PHASE_TIMING
+struct PhaseCycles {
+    uint64_t Select = 0, Generate = 0, Terminal = 0, Expand = 0, Slots = 0, Root = 0, Apply = 0;
+};
+inline PhaseCycles& phaseCycles() {
+    static thread_local PhaseCycles P;
+    return P;
+}
+#define NSB_PHASE(Field, Stmt)                                      \
+    do {                                                            \
+        const uint64_t T_ = __builtin_ia32_rdtsc();                 \
+        Stmt;                                                       \
+        phaseCycles().Field += __builtin_ia32_rdtsc() - T_;         \
+    } while (0)
+#else
+#define NSB_PHASE(Field, Stmt) \
+    do {                       \
+        Stmt;                  \
+    } while (0)
+#endif
+
 // One frame until it needs the network: selectLeaf / checkTerminal / backpropagate / transition (worker.cc:82-106).
 // OnGameEnd(const Frame&) is called when a game is over, before the frame starts its next one.
+inline void applyEvaluation(const GameOptions& O, Frame& F, const float* Row, const uint16_t* Order, float WinRate, float DrawRate);
+
 template <typename GameEnd>
 inline void advance(const GameOptions& O, Frame& F, Info* SI, GameEnd&& OnGameEnd) {
+    if (F.EvalPending) {
+        F.EvalPending = false;
+        NSB_PHASE(Apply, applyEvaluation(O, F, F.EvalRow, F.EvalOrder, F.EvalWin, F.EvalDraw));
+    }
     for (;;) {
         const search::Node& Root = F.Tree.node(0);
         if (Root.evaluated() && (Root.NumEdges == 1 || Root.Visits >= F.Playouts + 1)) {  // worker.cc:415-430 (+1: the root's own evaluation)
-            if (transition(F, SI)) {
-                SI->Games.fetch_add(1, std::memory_order_relaxed);
-                OnGameEnd(F);
-                newGame(O, F);
-            }
-            prepareRoot(O, F);
+            NSB_PHASE(Root, {
+                if (transition(F, SI)) {
+                    SI->Games.fetch_add(1, std::memory_order_relaxed);
+                    OnGameEnd(F);
+                    newGame(O, F);
+                }
+                prepareRoot(O, F);
+            });
             continue;
         }
-        F.Leaf = F.Root;
-        F.Path.clear();
-        const int Node = F.Tree.selectLeaf(F.Leaf, F.BlackDraw, F.WhiteDraw, &F.Path);
+        int Node;
+        NSB_PHASE(Select, {
+            F.Leaf = F.Root;
+            F.Path.clear();
+            Node = F.Tree.selectLeaf(F.Leaf, F.BlackDraw, F.WhiteDraw, &F.Path);
+        });
         const search::Node& N = F.Tree.node(Node);
         if (N.Term == search::Mated) {
             F.Tree.backup(Node, 0.0f, 0.0f);
@@ -203,27 +239,32 @@ inline void advance(const GameOptions& O, Frame& F, Info* SI, GameEnd&& OnGameEn
             continue;
         }
         // a new leaf: terminal checks first (searchworker.cc:475-538, selfplay/worker.cc:270-372)
-        if (Node != 0 && F.Leaf.canDeclare()) {  // worker.cc:299-317: the side to move declares and wins
+        bool Declares;
+        NSB_PHASE(Terminal, Declares = Node != 0 && F.Leaf.canDeclare());
+        if (Declares) {  // worker.cc:299-317: the side to move declares and wins
             F.Tree.setTerminal(Node, search::Declared);
             SI->Terminals.fetch_add(1, std::memory_order_relaxed);
             F.Tree.backup(Node, 1.0f, 0.0f);
             continue;
         }
-        const int NumMoves = F.Leaf.generateLegal(F.LeafMoves);
+        int NumMoves;
+        NSB_PHASE(Generate, NumMoves = F.Leaf.generateLegal(F.LeafMoves));
         if (NumMoves == 0) {
             F.Tree.setTerminal(Node, search::Mated);
             SI->Terminals.fetch_add(1, std::memory_order_relaxed);
             F.Tree.backup(Node, 0.0f, 0.0f);
             continue;
         }
-        if (Node != 0 && (search::isFourfold(F.Leaf.Hash, F.History, F.Path) || F.Leaf.Ply >= F.MaxPly)) {
+        bool Drawn;
+        NSB_PHASE(Terminal, Drawn = Node != 0 && (search::isFourfold(F.Leaf.Hash, F.History, F.Path) || F.Leaf.Ply >= F.MaxPly));
+        if (Drawn) {
             F.Tree.setTerminal(Node, search::DrawnGame);
             SI->Terminals.fetch_add(1, std::memory_order_relaxed);
             F.Tree.backup(Node, 0.5f, 1.0f);
             continue;
         }
-        F.Tree.expand(Node, F.LeafMoves, NumMoves);
-        for (int J = 0; J < NumMoves; ++J) F.LeafSlots[J] = (uint16_t)F.Leaf.policyIndex(F.LeafMoves[J]);  // ml::getMoveIndex
+        NSB_PHASE(Expand, F.Tree.expand(Node, F.LeafMoves, NumMoves));
+        NSB_PHASE(Slots, for (int J = 0; J < NumMoves; ++J) F.LeafSlots[J] = (uint16_t)F.Leaf.policyIndex(F.LeafMoves[J]));  // ml::getMoveIndex
         F.NumLeafMoves = NumMoves;
         F.LeafNode = Node;
         return;
@@ -232,6 +273,18 @@ inline void advance(const GameOptions& O, Frame& F, Info* SI, GameEnd&& OnGameEn
 
 inline void advance(const GameOptions& O, Frame& F, Info* SI) {
     advance(O, F, SI, [](const Frame&) {});
+}
+
+// The reference draws 600 Gamma(0.15) samples at every root and divides them by their sum (worker.cc:165-177), of which
+// the root's NumEdges first are used - and only at a full-search root (frame.cc:121).  Same joint distribution, drawn
+// when needed: NumEdges samples + one Gamma(0.15 * (600 - NumEdges)) sample for the sum of the ones nobody looks at.
+inline void drawRootNoise(Frame& F, int NumEdges) {
+    constexpr int Total = (int)(sizeof(F.Noise) / sizeof(F.Noise[0]));
+    std::gamma_distribution<double> D(0.15, 1.0);
+    double Sum = 0.0;
+    for (int J = 0; J < NumEdges; ++J) Sum += (F.Noise[J] = D(F.MT));
+    if (NumEdges < Total) Sum += std::gamma_distribution<double>(0.15 * (double)(Total - NumEdges), 1.0)(F.MT);
+    for (int J = 0; J < NumEdges; ++J) F.Noise[J] /= Sum;
 }
 
 // Frame::setEvaluation's consumer side (frame.cc:93-136) for a row the executor decoded (NSB_DECODE_BOTH + order_out):
@@ -244,11 +297,23 @@ inline void applyEvaluation(const GameOptions& O, Frame& F, const float* Row, co
         search::Edge* E = F.Tree.edgesOf(0);
         const int NumEdges = F.Tree.node(0).NumEdges;
         const double EPS = 0.25;
+        drawRootNoise(F, NumEdges);
         for (int J = 0; J < NumEdges; ++J) E[J].P = (float)((1 - EPS) * (double)E[J].P + EPS * F.Noise[J]);
         F.Tree.sortEdges(0);
     }
     F.Tree.publish(F.LeafNode);
     F.Tree.backup(F.LeafNode, WinRate, DrawRate);
+}
+
+// What the evaluation worker does with a decoded row: leave it with the frame.  Walking the tree (setPriors over the
+// leaf's edges, backup along ~15 ancestors: dependent cache misses in memory another core wrote last) is the search
+// workers' job - many of them, one evaluation thread.
+inline void stageEvaluation(Frame& F, const float* Row, const uint16_t* Order, float WinRate, float DrawRate) {
+    std::memcpy(F.EvalRow, Row, (std::size_t)F.NumLeafMoves * sizeof(float));
+    std::memcpy(F.EvalOrder, Order, (std::size_t)F.NumLeafMoves * sizeof(uint16_t));
+    F.EvalWin = WinRate;
+    F.EvalDraw = DrawRate;
+    F.EvalPending = true;
 }
 
 } // namespace game

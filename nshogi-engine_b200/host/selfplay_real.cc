@@ -153,6 +153,8 @@ int main(int argc, char** argv) {
     Saves.close();
     Saver.join();
 
+    const double EvalTotal = std::max(1e-9, Evaluation.secondsFilling() + Evaluation.secondsDelivering() + Evaluation.secondsCollecting() +
+                                                Evaluation.secondsTaking());
     uint64_t MaxDepthPly = 0;
     for (const Frame& F : Pool) MaxDepthPly = std::max<uint64_t>(MaxDepthPly, F.Root.Ply);
     const double Evals = (double)(E1 - E0), Batches = (double)(B1 - B0);
@@ -165,6 +167,8 @@ int main(int argc, char** argv) {
                 "\"file\": \"%s\", \"what\": \"full-search positions of finished games (saveworker.cc:160-182), NSBT format\"}, "
                 "\"net\": \"%dx%d\", \"batch_size\": %d, \"frame_pool\": %d, \"search_workers\": %d, \"slots\": %d, "
                 "\"num_playouts\": %d, \"full_search_ratio\": %.2f, \"nan_rows\": %llu, "
+                "\"evaluation_worker\": {\"us_per_row_filling\": %.3f, \"us_per_row_delivering\": %.3f, \"share_waiting_for_gpu\": %.3f, "
+                "\"share_waiting_for_frames\": %.3f}, "
                 "\"decode\": \"NSB_DECODE_BOTH + order_out (logits cached, probabilities and rank order out; %s)\", "
                 "\"rules\": \"real: host/rules/shogi.h (perft-pinned move generation, mate, four-fold repetition, "
                 "perpetual check, 27-point declaration, max ply), PUCT tree host/mcts_search.h; no mate solver\"}\n",
@@ -178,6 +182,9 @@ int main(int argc, char** argv) {
                 (unsigned long long)Saved.Winners[0].load(), (unsigned long long)Saved.Winners[1].load(),
                 (unsigned long long)Saved.Winners[2].load(), O.Out.c_str(), O.Blocks, O.Channels, O.Batch, O.Frames, O.SearchWorkers, O.Slots, O.Playouts,
                 O.FullSearchRatio, (unsigned long long)SI.NanRows.load(),
+                1e6 * Evaluation.secondsFilling() / std::max<double>(1.0, (double)Evaluation.rows()),
+                1e6 * Evaluation.secondsDelivering() / std::max<double>(1.0, (double)Evaluation.rows()),
+                Evaluation.secondsCollecting() / EvalTotal, Evaluation.secondsTaking() / EvalTotal,
                 O.Gumbel ? "Gumbel roots skip the softmax" : "Dirichlet mix at full-search roots on the host");
     return 0;
 }

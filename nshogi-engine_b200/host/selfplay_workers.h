@@ -184,8 +184,9 @@ class FrameClient : public evaluate::EvaluationClient<SlotT> {
         Frame* F = static_cast<Frame*>(Task);
         const uint32_t B = S.MoveOffsets[Row];
         // gather, cache store of the raw logits and softmax (or its skip at a Gumbel root) happened on the GPU
-        // together with the rank order of the row; the Dirichlet mix of a full-search AlphaZero root is left
-        applyEvaluation(O, *F, S.Legal + B, S.Order + B, S.WinRate[Row], S.DrawRate[Row]);
+        // together with the rank order of the row; what is left - priors into the edges in rank order, the Dirichlet mix
+        // of a full-search AlphaZero root, back-propagation - is done by the search worker that takes the frame next
+        stageEvaluation(*F, S.Legal + B, S.Order + B, S.WinRate[Row], S.DrawRate[Row]);
         if (S.NanFlag[Row]) SI->NanRows.fetch_add(1, std::memory_order_relaxed);
         if (O.CacheMiB > 0 && S.HitFlag[Row]) SI->CacheHits.fetch_add(1, std::memory_order_relaxed);
     }
