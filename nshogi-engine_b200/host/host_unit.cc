@@ -900,48 +900,56 @@ static int hostCost(std::size_t Frames, std::size_t Leaves, std::size_t Warmup) 
         newGame(O, Pool[I]);
         prepareRoot(O, Pool[I]);
     }
+    // the search worker's pattern (selfplay_workers.h): frames in groups of 32; per group the trail prefetch, then per
+    // frame advance() - which first applies the evaluation staged on the last visit - and the row hand-over
     std::vector<float> Row(NSB_MAX_LEGAL_MOVES);
     std::vector<uint16_t> Order(NSB_MAX_LEGAL_MOVES), Slots(NSB_MAX_LEGAL_MOVES);
     nsb_position Rec;
-    double TAdvance = 0, TFill = 0, TDeliver = 0;
+    const bool Prefetch = std::getenv("NSB_NO_TRAIL_PREFETCH") == nullptr;
+    double TSearch = 0, TFill = 0;
     uint64_t Moves = 0, Sink = 0;
-    for (std::size_t L = 0; L < Leaves + Warmup; ++L) {
-        Frame& F = Pool[L % Frames];
-        if (L == Warmup) {  // (the first plies of every game are opening positions: few drops, no checks)
-            TAdvance = TFill = TDeliver = 0;
+    constexpr std::size_t Group = 32;
+    for (std::size_t L = 0; L < Leaves + Warmup; L += Group) {
+        if (L >= Warmup && L < Warmup + Group) {  // (the first plies of every game are opening positions: few drops, no checks)
+            TSearch = TFill = 0;
             Moves = 0;
         }
+        const std::size_t First = L % Frames;
         const auto T0 = Clk::now();
-        advance(O, F, &SI);
+        if (Prefetch)
+            for (std::size_t G = 0; G < Group; ++G) Pool[(First + G) % Frames].Tree.prefetchLastTrail();
+        for (std::size_t G = 0; G < Group; ++G) advance(O, Pool[(First + G) % Frames], &SI);
         const auto T1 = Clk::now();
-        F.Leaf.toRecord(&Rec, F.MaxPly, F.BlackDraw, F.WhiteDraw);
-        std::memcpy(Slots.data(), F.LeafSlots, (std::size_t)F.NumLeafMoves * sizeof(uint16_t));
-        const auto T2 = Clk::now();
-        Sink += Rec.board[40] + Slots[0];
-        const int N = F.NumLeafMoves;
-        uint64_t H = F.Leaf.Hash;
-        float Sum = 0.f;
-        for (int J = 0; J < N; ++J) {
-            H = H * 6364136223846793005ull + 1442695040888963407ull;
-            Sum += (Row[(size_t)J] = 1.0f + (float)(H >> 54) / 256.0f);
+        TSearch += std::chrono::duration<double>(T1 - T0).count();
+        for (std::size_t G = 0; G < Group; ++G) {
+            Frame& F = Pool[(First + G) % Frames];
+            const auto T2 = Clk::now();
+            F.Leaf.toRecord(&Rec, F.MaxPly, F.BlackDraw, F.WhiteDraw);
+            std::memcpy(Slots.data(), F.LeafSlots, (std::size_t)F.NumLeafMoves * sizeof(uint16_t));
+            Sink += Rec.board[40] + Slots[0];
+            const int N = F.NumLeafMoves;
+            uint64_t H = F.Leaf.Hash;
+            float Sum = 0.f;
+            for (int J = 0; J < N; ++J) {
+                H = H * 6364136223846793005ull + 1442695040888963407ull;
+                Sum += (Row[(size_t)J] = 1.0f + (float)(H >> 54) / 256.0f);
+            }
+            for (int J = 0; J < N; ++J) {
+                Row[(size_t)J] /= Sum;
+                Order[(size_t)J] = (uint16_t)J;
+            }
+            const auto T3 = Clk::now();   // (the rank order is the executor's work)
+            std::stable_sort(Order.begin(), Order.begin() + N, [&](uint16_t A, uint16_t B) { return Row[A] > Row[B]; });
+            const auto T4 = Clk::now();
+            stageEvaluation(F, Row.data(), Order.data(), 0.3f + 0.4f * (float)((F.Leaf.Hash >> 20) % 1000) / 1000.0f, 0.05f);
+            TFill += std::chrono::duration<double>(T3 - T2).count() + std::chrono::duration<double>(Clk::now() - T4).count();
+            Moves += (uint64_t)N;
         }
-        for (int J = 0; J < N; ++J) {
-            Row[(size_t)J] /= Sum;
-            Order[(size_t)J] = (uint16_t)J;
-        }
-        std::stable_sort(Order.begin(), Order.begin() + N, [&](uint16_t A, uint16_t B) { return Row[A] > Row[B]; });
-        const float Win = 0.3f + 0.4f * (float)((F.Leaf.Hash >> 20) % 1000) / 1000.0f;
-        const auto T3 = Clk::now();
-        applyEvaluation(O, F, Row.data(), Order.data(), Win, 0.05f);
-        const auto T4 = Clk::now();
-        TAdvance += std::chrono::duration<double>(T1 - T0).count();
-        TFill += std::chrono::duration<double>(T2 - T1).count();
-        TDeliver += std::chrono::duration<double>(T4 - T3).count();
-        Moves += (uint64_t)N;
     }
-    std::printf("{\"host_cost_us_per_leaf\": {\"advance\": %.3f, \"fill\": %.3f, \"deliver\": %.3f}, \"frames\": %zu, \"leaves\": %zu, "
-                "\"avg_legal_moves\": %.1f, \"positions_played\": %llu, \"games\": %llu, \"terminals\": %llu, \"sink\": %llu}\n",
-                1e6 * TAdvance / (double)Leaves, 1e6 * TFill / (double)Leaves, 1e6 * TDeliver / (double)Leaves, Frames, Leaves,
+    std::printf("{\"host_cost_us_per_leaf\": {\"search_worker\": %.3f, \"evaluation_worker_incl_mock_network\": %.3f}, \"trail_prefetch\": %s, "
+                "\"frames\": %zu, \"leaves\": %zu, \"avg_legal_moves\": %.1f, \"positions_played\": %llu, \"games\": %llu, "
+                "\"terminals\": %llu, \"sink\": %llu}\n",
+                1e6 * TSearch / (double)Leaves, 1e6 * TFill / (double)Leaves, Prefetch ? "true" : "false", Frames, Leaves,
                 (double)Moves / (double)Leaves, (unsigned long long)SI.Records.load(), (unsigned long long)SI.Games.load(),
                 (unsigned long long)SI.Terminals.load(), (unsigned long long)(Sink & 1));
 #ifdef NSB_PHASE_TIMING
