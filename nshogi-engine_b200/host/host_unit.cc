@@ -900,12 +900,11 @@ static int hostCost(std::size_t Frames, std::size_t Leaves, std::size_t Warmup) 
         newGame(O, Pool[I]);
         prepareRoot(O, Pool[I]);
     }
-    // the search worker's pattern (selfplay_workers.h): frames in groups of 32; per group the trail prefetch, then per
+    // the search worker's pattern (selfplay_workers.h): frames in groups of 32; per
     // frame advance() - which first applies the evaluation staged on the last visit - and the row hand-over
     std::vector<float> Row(NSB_MAX_LEGAL_MOVES);
     std::vector<uint16_t> Order(NSB_MAX_LEGAL_MOVES), Slots(NSB_MAX_LEGAL_MOVES);
     nsb_position Rec;
-    const bool Prefetch = std::getenv("NSB_NO_TRAIL_PREFETCH") == nullptr;
     double TSearch = 0, TFill = 0;
     uint64_t Moves = 0, Sink = 0;
     constexpr std::size_t Group = 32;
@@ -916,8 +915,6 @@ static int hostCost(std::size_t Frames, std::size_t Leaves, std::size_t Warmup) 
         }
         const std::size_t First = L % Frames;
         const auto T0 = Clk::now();
-        if (Prefetch)
-            for (std::size_t G = 0; G < Group; ++G) Pool[(First + G) % Frames].Tree.prefetchLastTrail();
         for (std::size_t G = 0; G < Group; ++G) advance(O, Pool[(First + G) % Frames], &SI);
         const auto T1 = Clk::now();
         TSearch += std::chrono::duration<double>(T1 - T0).count();
@@ -946,10 +943,10 @@ static int hostCost(std::size_t Frames, std::size_t Leaves, std::size_t Warmup) 
             Moves += (uint64_t)N;
         }
     }
-    std::printf("{\"host_cost_us_per_leaf\": {\"search_worker\": %.3f, \"evaluation_worker_incl_mock_network\": %.3f}, \"trail_prefetch\": %s, "
+    std::printf("{\"host_cost_us_per_leaf\": {\"search_worker\": %.3f, \"evaluation_worker_incl_mock_network\": %.3f}, "
                 "\"frames\": %zu, \"leaves\": %zu, \"avg_legal_moves\": %.1f, \"positions_played\": %llu, \"games\": %llu, "
                 "\"terminals\": %llu, \"sink\": %llu}\n",
-                1e6 * TSearch / (double)Leaves, 1e6 * TFill / (double)Leaves, Prefetch ? "true" : "false", Frames, Leaves,
+                1e6 * TSearch / (double)Leaves, 1e6 * TFill / (double)Leaves, Frames, Leaves,
                 (double)Moves / (double)Leaves, (unsigned long long)SI.Records.load(), (unsigned long long)SI.Games.load(),
                 (unsigned long long)SI.Terminals.load(), (unsigned long long)(Sink & 1));
 #ifdef NSB_PHASE_TIMING

@@ -164,20 +164,7 @@ class Tree {
         return Cur;
     }
     int selectLeaf(rules::Position& Pos, float BlackDraw, float WhiteDraw, std::vector<uint64_t>* Path) {  // private tree
-        const int Leaf = selectLeaf(Pos, BlackDraw, WhiteDraw, Path, &OwnTrail);
-        OwnTrailEdges.clear();
-        for (int I : OwnTrail) OwnTrailEdges.push_back(NodesP[I].EdgeBegin);
-        return Leaf;
-    }
-    // Private tree: ask for the nodes and the first edges along the last descent.  The back-propagation of that
-    // descent walks exactly these, and the next descent mostly does (PUCT moves away from a line slowly): issued for a
-    // batch of games before any of them is touched, the misses of all of them overlap instead of forming one chain of
-    // dependent misses per game (a pool of 1,024 trees does not fit any cache).
-    void prefetchLastTrail() const {
-        for (std::size_t I = 0; I < OwnTrail.size(); ++I) {
-            __builtin_prefetch(&NodesP[OwnTrail[I]]);
-            __builtin_prefetch(&EdgesP[OwnTrailEdges[I]]);
-        }
+        return selectLeaf(Pos, BlackDraw, WhiteDraw, Path, &OwnTrail);
     }
 
     // expandLeaf (searchworker.cc:164-173): the claimed leaf's legal moves become its edges (priors follow with
@@ -280,7 +267,6 @@ class Tree {
     std::atomic<uint32_t> NumNodes{0};
     std::atomic<uint64_t> NumEdgesUsed{0};
     std::vector<int> OwnTrail;
-    std::vector<int32_t> OwnTrailEdges;
 
     // counters: relaxed atomic read-modify-writes on a shared tree, plain arithmetic on a private one
     template <typename T>

@@ -149,6 +149,86 @@ constexpr TypeDirs makeTypeDirs() {
 }
 constexpr TypeDirs kTypeDirs = makeTypeDirs();
 
+// Move-generation tables, per colour (white's directions are black's with the rank step negated): the step targets of
+// every (type, square) in direction order, the length of every ray, which codes are the mover's own pieces, and for a
+// move of a type from rank Rf to rank Rt whether it may promote (bit 0) and whether it may stay unpromoted (bit 1).
+struct StepList {
+    uint8_t N;
+    uint8_t To[8];
+};
+struct MoveTables {
+    StepList Steps[2][NumPieceTypes][81];
+    uint8_t RayLen[2][81][8];
+    int8_t RayStep[2][8];
+    uint8_t Own[2][32];
+    uint8_t Flags[2][NumPieceTypes][9][9];
+    // for "is S attacked by colour By": the squares a By piece would step FROM to reach S with the step it would use,
+    // and per board code the steps / slides a piece of colour By has (0 for the other colour and for empty)
+    struct StepSource {
+        uint8_t N;
+        uint8_t From[10], D[10];
+    } StepFrom[2][81];
+    uint16_t StepsOf[2][32];
+    uint8_t SlidesOf[2][32];
+};
+constexpr MoveTables makeMoveTables() {
+    MoveTables T{};
+    for (int Me = 0; Me < 2; ++Me) {
+        const int Sign = Me == 0 ? 1 : -1;
+        for (int Type = 0; Type < NumPieceTypes; ++Type)
+            for (int S = 0; S < 81; ++S) {
+                StepList& L = T.Steps[Me][Type][S];
+                L.N = 0;
+                for (int D = 0; D < 10; ++D) {
+                    if (!((kTypeDirs.Step[Type] >> D) & 1u)) continue;
+                    const int Tf = S / 9 + kSteps[D][0], Tr = S % 9 + Sign * kSteps[D][1];
+                    if (Tf < 0 || Tf > 8 || Tr < 0 || Tr > 8) continue;
+                    L.To[L.N++] = (uint8_t)(9 * Tf + Tr);
+                }
+            }
+        for (int D = 0; D < 8; ++D) T.RayStep[Me][D] = (int8_t)(9 * kDirs[D][0] + Sign * kDirs[D][1]);
+        for (int S = 0; S < 81; ++S)
+            for (int D = 0; D < 8; ++D) {
+                int Tf = S / 9 + kDirs[D][0], Tr = S % 9 + Sign * kDirs[D][1], Len = 0;
+                while (Tf >= 0 && Tf <= 8 && Tr >= 0 && Tr <= 8) {
+                    ++Len;
+                    Tf += kDirs[D][0];
+                    Tr += Sign * kDirs[D][1];
+                }
+                T.RayLen[Me][S][D] = (uint8_t)Len;
+            }
+        for (int C = 0; C < 32; ++C) {
+            const bool Mine = C >= 1 && C <= 28 && (C - 1) / 14 == Me;
+            T.Own[Me][C] = Mine ? 1 : 0;
+            T.StepsOf[Me][C] = Mine ? kTypeDirs.Step[(C - 1) % 14] : (uint16_t)0;
+            T.SlidesOf[Me][C] = Mine ? kTypeDirs.Slide[(C - 1) % 14] : (uint8_t)0;
+        }
+        for (int S = 0; S < 81; ++S) {
+            MoveTables::StepSource& A = T.StepFrom[Me][S];
+            A.N = 0;
+            for (int D = 0; D < 10; ++D) {
+                const int Af = S / 9 - kSteps[D][0], Ar = S % 9 - Sign * kSteps[D][1];
+                if (Af < 0 || Af > 8 || Ar < 0 || Ar > 8) continue;
+                A.From[A.N] = (uint8_t)(9 * Af + Ar);
+                A.D[A.N++] = (uint8_t)D;
+            }
+        }
+        for (int Type = 0; Type < NumPieceTypes; ++Type)
+            for (int Rf = 0; Rf < 9; ++Rf)
+                for (int Rt = 0; Rt < 9; ++Rt) {
+                    const bool ZoneF = Me == 0 ? Rf <= 2 : Rf >= 6, ZoneT = Me == 0 ? Rt <= 2 : Rt >= 6;
+                    const int Rel = Me == 0 ? Rt : 8 - Rt;  // 0 = the far rank
+                    const bool Stay = (Type == Pawn || Type == Lance) ? Rel >= 1 : Type == Knight ? Rel >= 2 : true;
+                    T.Flags[Me][Type][Rf][Rt] = (uint8_t)(((kPromoted[Type] >= 0 && (ZoneF || ZoneT)) ? 1 : 0) | (Stay ? 2 : 0));
+                }
+    }
+    return T;
+}
+inline const MoveTables& moveTables() {
+    static const MoveTables T = makeMoveTables();
+    return T;
+}
+
 class Position {
  public:
     uint8_t Board[81];
@@ -205,25 +285,21 @@ class Position {
     // ---- attacks -------------------------------------------------------------------------------------------------
     // Is square S attacked by a piece of colour By?
     bool attacked(int S, int By) const {
-        const int F = fileOf(S), R = rankOf(S);
-        const int Sign = By == 0 ? 1 : -1;  // an attacker of colour By moves by (D0, Sign * D1): it stands at S - that
-        for (int D = 0; D < 10; ++D) {
-            const int Af = F - kSteps[D][0], Ar = R - Sign * kSteps[D][1];
-            if (!onBoard(Af, Ar)) continue;
-            const int C = Board[9 * Af + Ar];
-            if (C && colourOf(C) == By && ((kTypeDirs.Step[typeOf(C)] >> D) & 1u)) return true;
-        }
-        for (int D = 0; D < 8; ++D) {
-            const int Df = kDirs[D][0], Dr = Sign * kDirs[D][1];
-            int Af = F - Df, Ar = R - Dr;
-            while (onBoard(Af, Ar)) {
-                const int C = Board[9 * Af + Ar];
+        const MoveTables& T = moveTables();
+        const MoveTables::StepSource& A = T.StepFrom[By][S];
+        unsigned Hit = 0;
+        for (int K = 0; K < A.N; ++K) Hit |= (unsigned)(T.StepsOf[By][Board[A.From[K]]] >> A.D[K]) & 1u;
+        if (Hit) return true;
+        for (int D = 0; D < 8; ++D) {  // a By slider moving along D comes from the opposite direction
+            const int Back = (D + 4) & 7, Step = T.RayStep[By][Back];
+            int Sq = S;
+            for (int Len = T.RayLen[By][S][Back]; Len > 0; --Len) {
+                Sq += Step;
+                const int C = Board[Sq];
                 if (C) {
-                    if (colourOf(C) == By && ((kTypeDirs.Slide[typeOf(C)] >> D) & 1u)) return true;
+                    if ((T.SlidesOf[By][C] >> D) & 1u) return true;
                     break;
                 }
-                Af -= Df;
-                Ar -= Dr;
             }
         }
         return false;
@@ -304,12 +380,18 @@ class Position {
 
     // Pseudo-legal moves of the side to move (king safety not yet checked).  Returns the count.
     int generatePseudoLegal(Move* Out) const {
+        static_assert(sizeof(Move) == 4, "a move is stored as one 32-bit word: From | To << 8 | Promote << 16 | Piece << 24");
+        const MoveTables& T = moveTables();
         int N = 0;
-        const int Me = Side, Sign = Me == 0 ? 1 : -1;
-        // a move from rank Rf to rank Rt (0 = black's far rank): promotion where the piece can, staying unpromoted where it may
-        auto emit = [&](int From, int To, int Type, int Rf, int Rt) {
-            if (kPromoted[Type] >= 0 && (inPromotionZone(Me, Rf) || inPromotionZone(Me, Rt))) Out[N++] = Move{(uint8_t)From, (uint8_t)To, 1, (uint8_t)Type};
-            if (canStay(Type, Me, Rt)) Out[N++] = Move{(uint8_t)From, (uint8_t)To, 0, (uint8_t)Type};
+        const int Me = Side;
+        const uint8_t* Own = T.Own[Me];
+        // Both forms of a move are always written; N only advances over the ones that exist (no branch on the board).
+        auto emit = [&](uint32_t Word, unsigned Flags, unsigned Ok) {
+            const uint32_t Promoting = Word | (1u << 16);
+            std::memcpy(static_cast<void*>(Out + N), &Promoting, 4);
+            N += (int)(Ok & Flags & 1u);
+            std::memcpy(static_cast<void*>(Out + N), &Word, 4);
+            N += (int)(Ok & (Flags >> 1) & 1u);
         };
         bool PawnOnFile[9] = {false, false, false, false, false, false, false, false, false};
         uint8_t Empty[81];
@@ -321,29 +403,26 @@ class Position {
                     Empty[NumEmpty++] = (uint8_t)S;
                     continue;
                 }
-                if (colourOf(C) != Me) continue;
+                if (!Own[C]) continue;
                 const int Type = typeOf(C);
                 if (Type == Pawn) PawnOnFile[F] = true;
-                for (unsigned Mask = kTypeDirs.Step[Type]; Mask; Mask &= Mask - 1) {
-                    const int D = __builtin_ctz(Mask);
-                    const int Tf = F + kSteps[D][0], Tr = R + Sign * kSteps[D][1];
-                    if (!onBoard(Tf, Tr)) continue;
-                    const int To = 9 * Tf + Tr, T = Board[To];
-                    if (T && colourOf(T) == Me) continue;
-                    emit(S, To, Type, R, Tr);
+                const uint32_t Base = (uint32_t)S | ((uint32_t)Type << 24);
+                const uint8_t* FlagsFrom = T.Flags[Me][Type][R];
+                const StepList& L = T.Steps[Me][Type][S];
+                for (int K = 0; K < L.N; ++K) {
+                    const int To = L.To[K];
+                    emit(Base | ((uint32_t)To << 8), FlagsFrom[rankOf(To)], 1u ^ Own[Board[To]]);
                 }
                 for (unsigned Mask = kTypeDirs.Slide[Type]; Mask; Mask &= Mask - 1) {
                     const int D = __builtin_ctz(Mask);
-                    const int Df = kDirs[D][0], Dr = Sign * kDirs[D][1], Step = 9 * Df + Dr;
-                    int Tf = F + Df, Tr = R + Dr, To = S + Step;
-                    while (onBoard(Tf, Tr)) {
-                        const int T = Board[To];
-                        if (T && colourOf(T) == Me) break;
-                        emit(S, To, Type, R, Tr);
-                        if (T) break;
-                        Tf += Df;
-                        Tr += Dr;
+                    const int Step = T.RayStep[Me][D];
+                    int To = S;
+                    for (int Len = T.RayLen[Me][S][D]; Len > 0; --Len) {
                         To += Step;
+                        const int Target = Board[To];
+                        if (Own[Target]) break;
+                        emit(Base | ((uint32_t)To << 8), FlagsFrom[rankOf(To)], 1u);
+                        if (Target) break;
                     }
                 }
             }
@@ -351,11 +430,13 @@ class Position {
             if (!Hands[Me][K]) continue;
             const int Type = kHandPiece[K];
             const int MinRel = Type == Knight ? 2 : (Type == Pawn || Type == Lance) ? 1 : 0;  // canStay
+            const uint32_t Base = (uint32_t)(81 + K) | ((uint32_t)Type << 24);
             for (int J = 0; J < NumEmpty; ++J) {
                 const int S = Empty[J], R = rankOf(S);
-                if ((Me == 0 ? R : 8 - R) < MinRel) continue;
-                if (Type == Pawn && PawnOnFile[fileOf(S)]) continue;  // nifu
-                Out[N++] = Move{(uint8_t)(81 + K), (uint8_t)S, 0, (uint8_t)Type};
+                const unsigned Ok = (unsigned)((Me == 0 ? R : 8 - R) >= MinRel) & (unsigned)!(Type == Pawn && PawnOnFile[fileOf(S)]);  // nifu
+                const uint32_t Word = Base | ((uint32_t)S << 8);
+                std::memcpy(static_cast<void*>(Out + N), &Word, 4);
+                N += (int)Ok;
             }
         }
         return N;
@@ -385,37 +466,32 @@ class Position {
         KingSafety K;
         const int Ks = KingSq[Colour];
         if (Ks == 255) return K;
-        const int F = fileOf(Ks), R = rankOf(Ks), Enemy = Colour ^ 1;
-        const int Sign = Enemy == 0 ? 1 : -1;  // an enemy piece that moves by (D0, Sign * D1) towards the king
-        for (int D = 0; D < 10; ++D) {
-            const int Af = F - kSteps[D][0], Ar = R - Sign * kSteps[D][1];
-            if (!onBoard(Af, Ar)) continue;
-            const int C = Board[9 * Af + Ar];
-            if (C && colourOf(C) == Enemy && ((kTypeDirs.Step[typeOf(C)] >> D) & 1u)) {
-                if (K.NumCheckers++ == 0) K.Answer.add(9 * Af + Ar);
+        const MoveTables& T = moveTables();
+        const int Enemy = Colour ^ 1;
+        const MoveTables::StepSource& A = T.StepFrom[Enemy][Ks];
+        for (int I = 0; I < A.N; ++I)
+            if ((T.StepsOf[Enemy][Board[A.From[I]]] >> A.D[I]) & 1u) {
+                if (K.NumCheckers++ == 0) K.Answer.add(A.From[I]);
             }
-        }
-        for (int D = 0; D < 8; ++D) {
-            const int Df = kDirs[D][0], Dr = Sign * kDirs[D][1];
-            int Af = F - Df, Ar = R - Dr, Own = -1;
+        for (int D = 0; D < 8; ++D) {  // an enemy slider moving along D towards the king comes from the opposite direction
+            const int Back = (D + 4) & 7, Step = T.RayStep[Enemy][Back];
+            int Sq = Ks, Own = -1;
             SquareSet Ray;
-            while (onBoard(Af, Ar)) {
-                const int Sq = 9 * Af + Ar, C = Board[Sq];
+            for (int Len = T.RayLen[Enemy][Ks][Back]; Len > 0; --Len) {
+                Sq += Step;
+                const int C = Board[Sq];
                 Ray.add(Sq);
-                if (C) {
-                    if (colourOf(C) == Colour) {
-                        if (Own >= 0) break;  // two own pieces in the way
-                        Own = Sq;
-                    } else {
-                        if ((kTypeDirs.Slide[typeOf(C)] >> D) & 1u) {
-                            if (Own >= 0) K.Pinned.add(Own);
-                            else if (K.NumCheckers++ == 0) K.Answer = Ray;
-                        }
-                        break;
+                if (!C) continue;
+                if (T.Own[Colour][C]) {
+                    if (Own >= 0) break;  // two own pieces in the way
+                    Own = Sq;
+                } else {
+                    if ((T.SlidesOf[Enemy][C] >> D) & 1u) {
+                        if (Own >= 0) K.Pinned.add(Own);
+                        else if (K.NumCheckers++ == 0) K.Answer = Ray;
                     }
+                    break;
                 }
-                Af -= Df;
-                Ar -= Dr;
             }
         }
         K.InCheck = K.NumCheckers > 0;

@@ -140,7 +140,6 @@ class SearchWorker : public worker::Worker {
         In.clear();
         SearchQueue->get(32, true, In);
         if (In.empty()) return false;
-        for (Frame* F : In) F->Tree.prefetchLastTrail();
         for (Frame* F : In) {
             advance(O, *F, SI, [&](const Frame& Done) { Saves->add(finishedGame(Done)); });
             Out.push_back(F);
