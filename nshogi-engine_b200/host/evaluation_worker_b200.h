@@ -52,10 +52,14 @@ class PipelinedEvaluationWorker : public worker::Worker {
 
     // The pipeline is created by the caller; Bind (optional) runs once on the worker thread before the first task
     // (the reference binds the executor's device there: selfplay/evaluationworker.cc:62-67).
+    // MinFill: while batches are in flight, a batch is only submitted once it has this many rows - fewer tasks stay
+    // with the worker and wait for the ones the next delivery sets free (slots are the scarce resource: a slot that
+    // carries 20 rows is in flight as long as one that carries 500).  With nothing in flight whatever is there goes out.
     PipelinedEvaluationWorker(PipelineT* Pipeline, EvaluationClient<Slot>* Client_, bool FromPositions, int DecodeMode,
-                              bool UseCache, bool Ranked, void (*Bind)(void*) = nullptr, void* BindArg = nullptr)
+                              bool UseCache, bool Ranked, void (*Bind)(void*) = nullptr, void* BindArg = nullptr,
+                              std::size_t MinFill_ = 1)
         : worker::Worker(true), Pipe(Pipeline), Client(Client_), Positions(FromPositions), Mode(DecodeMode), Cache(UseCache),
-          Rank(Ranked), BindFn(Bind), BindArgument(BindArg), SlotTasks(Pipeline->numSlots()) {
+          Rank(Ranked), BindFn(Bind), BindArgument(BindArg), MinFill(MinFill_ < 1 ? 1 : MinFill_), SlotTasks(Pipeline->numSlots()) {
         spawnThread();
     }
 
@@ -74,12 +78,15 @@ class PipelinedEvaluationWorker : public worker::Worker {
     }
 
     bool doTask() override {
-        Tasks.clear();
         const auto T0 = Clock::now();
-        Client->take(Pipe->batchMax(), InFlight.empty(), Tasks);
+        if (Tasks.size() < Pipe->batchMax()) Client->take(Pipe->batchMax() - Tasks.size(), InFlight.empty() && Tasks.empty(), Tasks);
         TTake += seconds(T0);
         if (Tasks.empty()) {
             if (InFlight.empty()) return false;  // idle AND drained: the only state in which the worker can be stopped
+            deliverOldest();
+            return true;
+        }
+        if (Tasks.size() < MinFill && !InFlight.empty()) {  // wait for a fuller batch: the next delivery frees more tasks
             deliverOldest();
             return true;
         }
@@ -94,6 +101,7 @@ class PipelinedEvaluationWorker : public worker::Worker {
         }
         S.MoveOffsets[Tasks.size()] = Off;
         SlotTasks[K].swap(Tasks);
+        Tasks.clear();
         Pipe->submit(K, SlotTasks[K].size(), Positions, Mode, Cache, Rank);
         InFlight.push_back(K);
         TFill += seconds(T1);
@@ -127,6 +135,7 @@ class PipelinedEvaluationWorker : public worker::Worker {
     const bool Cache, Rank;
     void (*BindFn)(void*);
     void* BindArgument;
+    const std::size_t MinFill;
     std::vector<std::vector<void*>> SlotTasks;
     std::deque<std::size_t> InFlight;
     std::vector<void*> Tasks;

@@ -733,7 +733,7 @@ struct CycleClient : evaluate::EvaluationClient<FakePipeline::Slot> {
     }
 };
 
-static int workerCycles(std::size_t Tasks) {
+static int workerCycles(std::size_t Tasks, std::size_t MinFill = 1) {
     FakePipeline Pipe(3, 64);
     CycleClient Client;
     std::vector<CycleTask> Pool(Tasks * 3);
@@ -741,7 +741,7 @@ static int workerCycles(std::size_t Tasks) {
     int Bound = 0;
     {
         evaluate::PipelinedEvaluationWorker<FakePipeline> W(&Pipe, &Client, true, 0, false, true,
-                                                            [](void* P) { ++*static_cast<int*>(P); }, &Bound);
+                                                            [](void* P) { ++*static_cast<int*>(P); }, &Bound, MinFill);
         CHECK(Bound == 1 && !W.isRunning());   // initializationTask ran on the worker thread before spawnThread returned
         std::size_t Pushed = 0;
         for (int Cycle = 0; Cycle < 3; ++Cycle) {
@@ -762,7 +762,7 @@ static int workerCycles(std::size_t Tasks) {
             for (std::size_t I = Pushed; I < Pool.size(); ++I) CHECK(Pool[I].Filled.load() == 0);
             CHECK(W.rows() == Pushed);
         }
-        std::printf("worker cycles: %zu tasks in %llu batches over 3 start/stop/await cycles: ok\n", Pushed, (unsigned long long)W.batches());
+        std::printf("worker cycles (min fill %zu): %zu tasks in %llu batches over 3 start/stop/await cycles: ok\n", MinFill, Pushed, (unsigned long long)W.batches());
     }   // ~Worker joins the thread
     return 0;
 }
@@ -999,7 +999,8 @@ int main(int argc, char** argv) {
         return hostCost((std::size_t)std::atol(argv[2]), (std::size_t)std::atol(argv[3]), argc >= 5 ? (std::size_t)std::atol(argv[4]) : 0);
     if (argc >= 5 && std::strcmp(argv[1], "--selfplay-loop") == 0)
         return selfplayLoop(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]), std::atoi(argv[4]));
-    if (argc >= 3 && std::strcmp(argv[1], "--worker-cycles") == 0) return workerCycles((std::size_t)std::atol(argv[2]));
+    if (argc >= 3 && std::strcmp(argv[1], "--worker-cycles") == 0)
+        return workerCycles((std::size_t)std::atol(argv[2])) || workerCycles((std::size_t)std::atol(argv[2]), 48);
     if (argc >= 4 && std::strcmp(argv[1], "--tree-stress") == 0) return treeStress(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]));
     if (argc >= 3 && std::strcmp(argv[1], "--perft") == 0) return rulesChecks(std::atoi(argv[2]));
     if (argc >= 4 && std::strcmp(argv[1], "--queue-stress") == 0) return queueStress(std::atoi(argv[2]), (std::size_t)std::atol(argv[3]));
@@ -1066,7 +1067,7 @@ int main(int argc, char** argv) {
     if (selfplayFeedChecks()) return 1;
     if (rulesChecks(4)) return 1;          // shogi rules: perft(1..4) of hirate + the special rules
     if (selfplayMock(2, 24)) return 1;     // two whole games of the self-play loop against a mock evaluator
-    if (workerCycles(5000)) return 1;      // the pipelined evaluation worker inside the worker::Worker contract
+    if (workerCycles(5000) || workerCycles(5000, 48)) return 1;  // the pipelined evaluation worker inside the worker::Worker contract
     if (selfplayLoop(2, 48, 300)) return 1; // the whole harness: starts, plays, winds down
     std::printf("host_unit ok\n");
     return 0;

@@ -48,7 +48,7 @@ using Clock = std::chrono::steady_clock;
 namespace {
 
 struct Options : b200::game::HarnessOptions {
-    int Channels = 256, Blocks = 20, Batch = 512, Frames = 1024, SearchWorkers = 4, Slots = 3, GPU = 0;
+    int Channels = 256, Blocks = 20, Batch = 512, Frames = 1024, SearchWorkers = 4, Slots = 3, GPU = 0, MinFill = 1;
     double Seconds = 5.0, Warmup = 1.0;
     uint64_t Seed = 1234;
 };
@@ -72,6 +72,7 @@ int main(int argc, char** argv) {
         else if (A == "--frame-pool-size") O.Frames = nextI();
         else if (A == "--num-search-workers") O.SearchWorkers = nextI();
         else if (A == "--slots") O.Slots = nextI();
+        else if (A == "--min-fill") O.MinFill = nextI();
         else if (A == "--gpu") O.GPU = nextI();
         else if (A == "--num-playouts") O.Playouts = nextI();
         else if (A == "--full-search-ratio") O.FullSearchRatio = nextD();
@@ -120,7 +121,7 @@ int main(int argc, char** argv) {
             static_cast<infer::B200*>(E)->resetGPU();
             static_cast<infer::B200*>(E)->bindThreadToGpuNode();  // evaluator.cc:39-83
         },
-        &Exec);
+        &Exec, (std::size_t)O.MinFill);
     std::atomic<bool> Closing{false};
     std::vector<std::unique_ptr<SearchWorker>> Searchers;
     for (int W = 0; W < O.SearchWorkers; ++W)
@@ -165,7 +166,7 @@ int main(int argc, char** argv) {
                 "\"games_ended\": {\"mate\": %llu, \"repetition\": %llu, \"of_which_perpetual_check\": %llu, \"declaration\": %llu, \"max_ply\": %llu}, \"deepest_game_ply\": %llu, "
                 "\"teacher\": {\"games_saved\": %llu, \"records_saved\": %llu, \"black_wins\": %llu, \"white_wins\": %llu, \"draws\": %llu, "
                 "\"file\": \"%s\", \"what\": \"full-search positions of finished games (saveworker.cc:160-182), NSBT format\"}, "
-                "\"net\": \"%dx%d\", \"batch_size\": %d, \"frame_pool\": %d, \"search_workers\": %d, \"slots\": %d, "
+                "\"net\": \"%dx%d\", \"batch_size\": %d, \"frame_pool\": %d, \"search_workers\": %d, \"slots\": %d, \"min_fill\": %d, "
                 "\"num_playouts\": %d, \"full_search_ratio\": %.2f, \"nan_rows\": %llu, "
                 "\"evaluation_worker\": {\"us_per_row_filling\": %.3f, \"us_per_row_delivering\": %.3f, \"share_waiting_for_gpu\": %.3f, "
                 "\"share_waiting_for_frames\": %.3f}, "
@@ -180,7 +181,7 @@ int main(int argc, char** argv) {
                 (unsigned long long)SI.Declarations.load(), (unsigned long long)SI.MaxPlies.load(),
                 (unsigned long long)MaxDepthPly, (unsigned long long)Saved.Games.load(), (unsigned long long)Saved.Records.load(),
                 (unsigned long long)Saved.Winners[0].load(), (unsigned long long)Saved.Winners[1].load(),
-                (unsigned long long)Saved.Winners[2].load(), O.Out.c_str(), O.Blocks, O.Channels, O.Batch, O.Frames, O.SearchWorkers, O.Slots, O.Playouts,
+                (unsigned long long)Saved.Winners[2].load(), O.Out.c_str(), O.Blocks, O.Channels, O.Batch, O.Frames, O.SearchWorkers, O.Slots, O.MinFill, O.Playouts,
                 O.FullSearchRatio, (unsigned long long)SI.NanRows.load(),
                 1e6 * Evaluation.secondsFilling() / std::max<double>(1.0, (double)Evaluation.rows()),
                 1e6 * Evaluation.secondsDelivering() / std::max<double>(1.0, (double)Evaluation.rows()),
