@@ -530,7 +530,7 @@ def selfplay_leg(args, info, rep, device):
         return {"unavailable": "nsb_selfplay_real not built"}
     # threads per rank: W search workers + the evaluation worker (the save worker and the main thread sleep almost always)
     workers = max(2, min(14, (os.cpu_count() or 4) // max(1, info.world) - 1))
-    cmd = [exe, "--gpu", str(info.local_rank), "--channels", "256", "--blocks", "20", "--batch-size", "512",
+    cmd = [exe, "--gpu", str(info.local_rank), "--channels", "256", "--blocks", "20", "--batch-size", "256", "--slots", "4",
            "--frame-pool-size", "1024", "--num-search-workers", str(workers), "--seconds", str(args.selfplay_seconds),
            "--warmup", "1.5"]
     def one_run(extra):
@@ -560,7 +560,7 @@ def selfplay_leg(args, info, rep, device):
         return line
     line["teacher_rank0"] = rec.get("teacher")
     line["config"] = {"workload": "self-play data generation, 20x256 ResNet, 1024 concurrent games per GPU",
-                      "batch_size": 512, "num_playouts": rec["num_playouts"], "full_search_ratio": rec["full_search_ratio"],
+                      "batch_size": rec["batch_size"], "num_playouts": rec["num_playouts"], "full_search_ratio": rec["full_search_ratio"],
                       "search_workers_per_gpu": workers, "slots": rec["slots"], "rules": rec["rules"],
                       "decode": rec.get("decode"), "avg_legal_moves": rec.get("avg_legal_moves"),
                       "terminal_leaves_per_eval": rec.get("terminal_leaves_per_eval"), "eval_cache": "off: every leaf runs the network"}

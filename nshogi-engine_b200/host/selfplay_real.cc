@@ -48,7 +48,7 @@ using Clock = std::chrono::steady_clock;
 namespace {
 
 struct Options : b200::game::HarnessOptions {
-    int Channels = 256, Blocks = 20, Batch = 512, Frames = 1024, SearchWorkers = 4, Slots = 3, GPU = 0, MinFill = 1;
+    int Channels = 256, Blocks = 20, Batch = 256, Frames = 1024, SearchWorkers = 4, Slots = 4, GPU = 0, MinFill = 1;
     double Seconds = 5.0, Warmup = 1.0;
     uint64_t Seed = 1234;
 };
