@@ -119,8 +119,12 @@ class ClockSampler:
             def loop():
                 while not self._stop.is_set():
                     try:
+                        try:
+                            mj = float(pynvml.nvmlDeviceGetTotalEnergyConsumption(h))   # the board's own energy counter, mJ
+                        except pynvml.NVMLError:
+                            mj = None
                         self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
-                                             pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons_fn(h))))
+                                             pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons_fn(h)), mj))
                     except pynvml.NVMLError:
                         pass
                     self._stop.wait(0.02)
@@ -173,11 +177,19 @@ class ClockSampler:
             return None
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
         reasons = sorted({nm for s in inside for bit, nm in names.items() if s[3] & bit})
-        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_mhz_min": min(s[1] for s in inside),
-                "sm_max_mhz": self.max_mhz, "power_w_max": round(max(s[2] for s in inside), 1),
-                "power_w_median": round(statistics.median(s[2] for s in inside), 1), "samples": len(inside),
-                "reasons": reasons, "window_s": round(t1 - t0, 3), "source": self.source,
-                "window": "the timed region of `value` only"}
+        out = {"sm_mhz": statistics.median(s[1] for s in inside), "sm_mhz_min": min(s[1] for s in inside),
+               "sm_max_mhz": self.max_mhz, "power_w_max": round(max(s[2] for s in inside), 1),
+               "power_w_median": round(statistics.median(s[2] for s in inside), 1), "samples": len(inside),
+               "reasons": reasons, "window_s": round(t1 - t0, 3), "source": self.source,
+               "window": "the timed region of `value` only"}
+        # energy from the board's counter between the first and the last sample inside the window (the counter's own
+        # average power over that span; the instantaneous power readings above lag by NVML's averaging window)
+        counted = [s for s in inside if len(s) > 4 and s[4] is not None]
+        if len(counted) >= 2 and counted[-1][0] > counted[0][0]:
+            joules = (counted[-1][4] - counted[0][4]) / 1000.0
+            out["energy_counter"] = {"joules": round(joules, 2), "span_s": round(counted[-1][0] - counted[0][0], 3),
+                                     "avg_power_w": round(joules / (counted[-1][0] - counted[0][0]), 1)}
+        return out
 
 
 class Workload:
@@ -457,6 +469,14 @@ def run_b200(args):
                 "best_step": {"avg_launch_ms": round(best_step_ms / bps, 5),
                               "frac": round(flops_batch / (best_step_ms / bps * 1e-3) / 1e12 / tf_burst, 4)},
                 "isolated_launch": isolated, "one_slot_executor_launch": one_slot, "traffic": traffic}
+    if clocks and clocks.get("energy_counter"):
+        # joules are what the steady state is bounded by: the board's energy counter over the timed region
+        # of this rank, per evaluation and per FLOP (useful FLOPs: the net's; the kernels execute 192 / 162 of them)
+        watts = clocks["energy_counter"]["avg_power_w"]
+        rate = B / (batch_ms * 1e-3)
+        roofline["energy"] = {"avg_power_w": watts, "uj_per_eval": round(watts / rate * 1e6, 1),
+                              "pj_per_useful_flop": round(watts / (achieved_ss * 1e12) * 1e12, 4),
+                              "source": "nvmlDeviceGetTotalEnergyConsumption over the timed region, rank 0's GPU"}
     if sweep is not None:
         roofline["sweep"] = sweep
 
