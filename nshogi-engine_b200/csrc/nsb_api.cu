@@ -89,6 +89,7 @@ struct nsb_ctx {
     bool direct_io = false;    // kernels read / write the caller's page-locked buffers themselves (no copy nodes)
     bool fuse_pack = true;     // packed positions are expanded in the trunk prologue (NSB_FUSE_PACK=0: separate pack kernel)
     int duo_ctas = 0;          // > 0: the two-CTAs-per-SM 128-channel trunk (trunk_duo.cu) is available, co-resident CTAs per SM
+    int cluster128 = 1;        // NSB_TRUNK128=mc2 / mc4: trunk_fused.cu in clusters of 2 / 4 CTAs that share the weight stream by multicast
     bool duo_always = false;   // every launch uses it (multi-slot pipeline, or forced); otherwise it is chosen per batch size
     nsb::DeviceNet net_duo{};  // the same net with the weight stream in trunk_duo.cu's order (when both kernels are loaded)
     void* d_duo_tiles = nullptr;
@@ -244,12 +245,14 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     // 128 channels: a context with several slots is a throughput pipeline (batches in flight on
     // several streams) and gets the two-CTAs-per-SM kernel (trunk_duo.cu: +6 % throughput, measured);
     // a one-slot context evaluates one batch at a time and gets the kernel with the shorter launch
-    // (trunk_fused.cu).  NSB_TRUNK128 = classic | duo | ts forces one (ts: experimental trunk_ts.cu).
+    // (trunk_fused.cu).  NSB_TRUNK128 = classic | duo | mc2 | mc4 | ts forces one (mc2 / mc4: trunk_fused.cu in clusters that share the
+    // weight stream by multicast; ts: experimental trunk_ts.cu, diagnostic build).
     const bool is128 = net->channels == 128;
     const bool use_ts = is128 && t128 && strcmp(t128, "ts") == 0;
     // Unforced, a 128-channel context loads BOTH kernels: a multi-slot pipeline always launches the duo kernel; a
     // one-slot context picks per batch - trunk_fused.cu while the batch fits one wave of one CTA per SM (shortest
     // launch), trunk_duo.cu (two co-resident CTAs per SM share the tensor pipe) where that is faster (use_duo()).
+    const int cluster128 = (is128 && t128 && strcmp(t128, "mc2") == 0) ? 2 : (is128 && t128 && strcmp(t128, "mc4") == 0) ? 4 : 1;
     const bool want_duo = is128 && !use_ts && (t128 ? strcmp(t128, "duo") == 0 : true);
     const bool duo_always = want_duo && (t128 ? true : slots >= 2);
 #ifdef NSB_DIAG
@@ -269,6 +272,7 @@ int nsb_create(nsb_ctx** out, int gpu, int batch_max, int slots, const nsb_net_d
     c->use_ts = use_ts;
     c->duo_ctas = duo_ctas;
     c->duo_always = duo_always;
+    c->cluster128 = cluster128;
     if (const char* dc = getenv("NSB_DUO_CTAS")) c->duo_ctas = duo_ctas > 0 ? atoi(dc) : 0;  // diagnostics: force the grid cap
     if (const char* fp = getenv("NSB_FUSE_PACK")) c->fuse_pack = strcmp(fp, "0") != 0;
     // A one-slot context is the latency configuration (one batch at a time: every copy node is serial
@@ -486,7 +490,7 @@ static int run_trunk(nsb_ctx* c, Slot& s, const EvalArgs& a) {
 #ifdef NSB_DIAG
             : c->use_ts      ? launch_trunk_ts(c->net, a, c->num_sms, s.stream)
 #endif
-                             : launch_trunk_fused(c->net, a, c->num_sms, s.stream);
+                             : launch_trunk_fused(c->net, a, c->num_sms, s.stream, c->cluster128);
     if (k < 0) return k;
     NSB_CUDA(cudaGetLastError());
     c->launches += (uint64_t)k;

@@ -171,7 +171,7 @@ int launch_pack_positions(const nsb_position* d_pos, size_t n, nsb_feature_bitbo
 int launch_decode(const float* d_policy, const float* d_win, const float* d_draw, size_t n,
                   const uint32_t* d_off, const uint16_t* d_idx, int mode, float* d_out,
                   uint8_t* d_flag, cudaStream_t s, const uint8_t* d_row_flags = nullptr, float* d_logits_out = nullptr);
-int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s);
+int launch_trunk_fused(const DeviceNet& net, const EvalArgs& a, int num_sms, cudaStream_t s, int cluster = 1);
 int launch_cache_probe(const DeviceCache& c, const uint64_t* d_hashes, size_t n, const uint32_t* d_off, float* d_legal,
                        float* d_win, float* d_draw, uint8_t* d_hit, uint8_t* d_nan_flag, int* d_miss_idx, int* d_miss_count,
                        cudaStream_t s, uint16_t* d_order = nullptr, int mode = 0, const uint8_t* d_row_flags = nullptr,

@@ -82,6 +82,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
         : "memory");
 }
 
+// The same copy delivered to the same shared-memory offset - and completing on the mbarrier at the same offset - in
+// every CTA of the cluster whose bit is set in cta_mask.
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                                   uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+        : "memory");
+}
+
 // ---- TMEM -----------------------------------------------------------------------------------
 // One full warp allocates `ncols` (power of two >= 32) columns; base address lands in smem.
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -116,7 +126,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // so (addr >> 4) needs no mask, and consecutive K steps differ by a constant in the low word only -
 // one integer add per descriptor instead of a shift and two logic ops on the (narrow) uniform datapath.
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
-    return (smem_addr >> 4) | ((lbo_bytes >> 4) << 16);
+    // matrix-descriptor-encode(x) = (x & 0x3FFFF) >> 4: in a cluster launch the shared-window address of a CTA of rank > 0
+    // carries its rank above bit 18, which must not spill into the LBO field
+    return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
 }
 __device__ __forceinline__ uint64_t smem_desc_from(uint32_t lo, uint32_t sbo_bytes) {
     return ((uint64_t)(((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14)) << 32) | lo;
@@ -357,6 +369,12 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc,
 }
 // arrive (once) on the mbarrier at this offset in every CTA of `cta_mask` when all MMAs issued so
 // far by this thread have retired
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {  // MMAs of cta_group::1
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(cta_mask)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"

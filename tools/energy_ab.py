@@ -20,7 +20,7 @@ def bench_line(env, steps):
     if out.returncode != 0:
         return {"error": out.stderr[-400:]}
     d = json.loads(out.stdout.strip().splitlines()[-1])
-    return {"kernel": d["roofline"]["kernel"], "evals_per_s": d["value"], "clocks": d["clocks"], "energy": d["roofline"].get("energy"),
+    return {"kernel": d["roofline"]["kernel"], "mode": env.get("NSB_TRUNK128"), "evals_per_s": d["value"], "clocks": d["clocks"], "energy": d["roofline"].get("energy"),
             "frac_of_burst": d["roofline"]["frac"]}
 
 
@@ -60,8 +60,10 @@ def main():
     args = ap.parse_args()
     steps = max(20, int(args.seconds / 0.053))
     out = {"one_cta_kernel": bench_line({"NSB_TRUNK128": "classic"}, steps), "duo_kernel": bench_line({"NSB_TRUNK128": "duo"}, steps),
+           "one_cta_kernel_clusters_of_2": bench_line({"NSB_TRUNK128": "mc2"}, steps),
+           "one_cta_kernel_clusters_of_4": bench_line({"NSB_TRUNK128": "mc4"}, steps),
            "cublas": matmul_energy(args.seconds)}
-    for k in ("one_cta_kernel", "duo_kernel"):
+    for k in ("one_cta_kernel", "duo_kernel", "one_cta_kernel_clusters_of_2", "one_cta_kernel_clusters_of_4"):
         e = out[k].get("energy")
         if e:
             e["pj_per_executed_flop"] = round(e["pj_per_useful_flop"] * 162.0 / 192.0, 4)
