@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "trunk_common.cuh"
 
 namespace nsb {
@@ -271,7 +273,10 @@ int launch_cluster128(const DeviceNet& net, const EvalArgs& a, int num_sms, cuda
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    static int resident = 0;  // clusters of CL one-CTA-per-SM blocks the device holds at once (GPC boundaries cost a few SMs)
+    // clusters of CL one-CTA-per-SM blocks the device holds at once (GPC boundaries cost a few SMs); asked once - several
+    // host threads may race to ask, they get the same answer
+    static std::atomic<int> resident_cached{0};
+    int resident = resident_cached.load(std::memory_order_relaxed);
     if (resident == 0) {
         cfg.gridDim = dim3((unsigned)(num_sms / CL * CL));
         int clusters = 0;
@@ -280,6 +285,7 @@ int launch_cluster128(const DeviceNet& net, const EvalArgs& a, int num_sms, cuda
             return NSB_ERR_NO_DEVICE;
         }
         resident = clusters * CL < num_sms ? clusters * CL : num_sms / CL * CL;
+        resident_cached.store(resident, std::memory_order_relaxed);
     }
     int grid = (groups + CL - 1) / CL * CL;
     if (grid > resident) grid = resident;
