@@ -17,6 +17,7 @@
 #include <vector>
 
 #include <fstream>
+#include <functional>
 #include <iterator>
 
 #include <algorithm>
@@ -493,6 +494,66 @@ static int rulesChecks(int PerftDepth) {
         H2.pop_back();
         CHECK(repetitionStatus(H2, C2) == Repetition::None);
     }
+    {   // shallow mate search against the exhaustive definition on random-playout positions
+        std::function<bool(Position&, int)> brute = [&](Position& P, int Plies) -> bool {   // side to move mates within Plies (odd)
+            Move Ms[kMaxMoves];
+            const int N = P.generateLegal(Ms);
+            const int Me = P.Side;
+            for (int I = 0; I < N; ++I) {
+                Position::Undo U;
+                P.make(Ms[I], &U);
+                bool Wins = false;
+                if (P.inCheck(Me ^ 1)) {
+                    Move Ev[kMaxMoves];
+                    const int NE = P.generateLegal(Ev);
+                    if (NE == 0) Wins = true;
+                    else if (Plies >= 3) {
+                        Wins = true;
+                        for (int J = 0; J < NE && Wins; ++J) {
+                            Position::Undo V;
+                            P.make(Ev[J], &V);
+                            Wins = brute(P, Plies - 2);
+                            P.unmake(Ev[J], V);
+                        }
+                    }
+                }
+                P.unmake(Ms[I], U);
+                if (Wins) return true;
+            }
+            return false;
+        };
+        std::mt19937_64 Rng(31);
+        std::size_t Checked = 0, Mates1 = 0, Mates3 = 0;
+        for (int Game = 0; Game < 400 && Checked < 12000; ++Game) {
+            Position P;
+            for (int Ply = 0; Ply < 160; ++Ply) {
+                Move Ms[kMaxMoves];
+                const int N = P.generateLegal(Ms);
+                if (N == 0) break;
+                if (Ply >= 20) {
+                    Position Q = P;
+                    const bool B1 = brute(Q, 1), B3 = brute(Q, 3);
+                    Move M1, M3;
+                    const bool F1 = Q.mateIn1(&M1), F3 = Q.mateIn3(&M3);
+                    CHECK(B1 == F1 && B3 == F3 && (!F1 || F3));
+                    CHECK(Q.Hash == P.Hash && std::memcmp(Q.Board, P.Board, 81) == 0);   // the search leaves the position as it was
+                    if (F1) {   // the move it reports mates
+                        Position::Undo U;
+                        Q.make(M1, &U);
+                        CHECK(Q.inCheck(Q.Side) && !Q.hasLegalMove());
+                        Q.unmake(M1, U);
+                    }
+                    Mates1 += F1;
+                    Mates3 += F3;
+                    ++Checked;
+                }
+                Position::Undo U;
+                P.make(Ms[Rng() % (uint64_t)N], &U);
+            }
+        }
+        std::printf("rules: mate search == exhaustive search on %zu random-playout positions (%zu mates in 1, %zu within 3 plies)\n", Checked, Mates1, Mates3);
+        CHECK(Checked >= 5000 && Mates1 > 20 && Mates3 > Mates1);
+    }
     {   // promoted sliders keep sliding and gain the king's other steps; captures go to the hand unpromoted
         Position P;
         P.clear();
@@ -514,11 +575,12 @@ static int rulesChecks(int PerftDepth) {
 }
 
 // ---- selfplay_game.h + mcts_search.h: whole games against a mock evaluator (no GPU) -----------------------------------
-static int selfplayMock(int Games, int Playouts) {
+static int selfplayMock(int Games, int Playouts, int MatePlies = 0) {
     using namespace b200;
     game::GameOptions O;
     O.Playouts = Playouts;
     O.FullSearchRatio = 0.5;
+    O.MatePlies = MatePlies;
     game::Info SI;
     game::Frame F;
     F.MT.seed(42);
@@ -986,6 +1048,16 @@ static int movegenBench() {
             }
         Best = std::min(Best, std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());
     }
+    double BestMate = 1e30;
+    uint64_t Found = 0;
+    for (int Rep = 0; Rep < 5; ++Rep) {
+        Found = 0;
+        const auto T0 = std::chrono::steady_clock::now();
+        for (Position& P : Sample) Found += P.mateIn3() ? 1 : 0;
+        BestMate = std::min(BestMate, std::chrono::duration<double>(std::chrono::steady_clock::now() - T0).count());
+    }
+    std::printf("{\"mate_in_3_ns_per_position\": %.1f, \"found\": %llu, \"positions\": %zu}\n", 1e9 * BestMate / (double)Sample.size(),
+                (unsigned long long)Found, Sample.size());
     for (Position& P : Sample) InCheck += P.inCheck(P.Side);
     const double Calls = 25.0 * (double)Sample.size();
     std::printf("{\"movegen_ns_per_position\": %.1f, \"ns_per_legal_move\": %.2f, \"avg_legal_moves\": %.1f, \"positions\": %zu, \"in_check\": %.3f}\n",
@@ -1067,6 +1139,7 @@ int main(int argc, char** argv) {
     if (selfplayFeedChecks()) return 1;
     if (rulesChecks(4)) return 1;          // shogi rules: perft(1..4) of hirate + the special rules
     if (selfplayMock(2, 24)) return 1;     // two whole games of the self-play loop against a mock evaluator
+    if (selfplayMock(1, 24, 3)) return 1;  // one more with the shallow mate search at leaves and roots
     if (workerCycles(5000) || workerCycles(5000, 48)) return 1;  // the pipelined evaluation worker inside the worker::Worker contract
     if (selfplayLoop(2, 48, 300)) return 1; // the whole harness: starts, plays, winds down
     std::printf("host_unit ok\n");

@@ -8,8 +8,8 @@
 // host/usi_go_bench.cc) run on this restatement of the RULES OF SHOGI instead.  What pins it: the perft counts of the
 // start position (30, 900, 25470, 719731, 19861490 - public known answers for shogi move generators), the 593 legal
 // moves of the known maximum position, hand-made positions for every special rule, and the brute-force legality filter
-// on random playouts (nsb_host_unit).  What it does not have: libnshogi's mate solvers (df-pn at the root of a finished
-// game, the 3-ply search at leaves: selfplay/worker.cc:352-362,517).  Games end by mate, by declaration (27-point rule),
+// on random playouts (nsb_host_unit).  Mate search: mateIn3() stands in for the 3-ply solver::dfs::solve the reference asks at every
+// self-play leaf (selfplay/worker.cc:352-362); libnshogi's df-pn solver (100,000 nodes at a finished game's root, :517) has no equivalent.  Games end by mate, by declaration (27-point rule),
 // by four-fold repetition (draw; lost by a side whose every move of the cycle gave check) or at max ply (draw).
 //
 // Squares, piece codes and hand order are those of nsb_position (include/nsb.h), so a position is handed to stage 1 of
@@ -226,6 +226,25 @@ constexpr MoveTables makeMoveTables() {
 }
 inline const MoveTables& moveTables() {
     static const MoveTables T = makeMoveTables();
+    return T;
+}
+
+// Could a piece on square A give check to a king on square B at all?  True when B is a neighbour of A, a knight's jump
+// away (either colour) or on the same file, rank or diagonal - the cheap filter in front of "make the move and look".
+struct LineTable {
+    uint8_t Aligned[81][81];
+};
+inline const LineTable& lineTable() {
+    static const LineTable T = [] {
+        LineTable L{};
+        for (int A = 0; A < 81; ++A)
+            for (int B = 0; B < 81; ++B) {
+                const int Df = B / 9 - A / 9, Dr = B % 9 - A % 9;
+                const int Af = Df < 0 ? -Df : Df, Ar = Dr < 0 ? -Dr : Dr;
+                L.Aligned[A][B] = (A != B) && (Df == 0 || Dr == 0 || Af == Ar || (Af == 1 && Ar == 2));
+            }
+        return L;
+    }();
     return T;
 }
 
@@ -566,6 +585,64 @@ class Position {
         for (int Slot = 0; Slot < 7; ++Slot) Points += Hands[Me][Slot] * (Slot >= 5 ? 5 : 1);
         if (Points < (Me == 0 ? 28 : 27)) return false;
         return !inCheck(Me);
+    }
+
+    // ---- shallow mate search (the reference asks libnshogi's solver::dfs::solve(State, 3) at every self-play leaf,
+    //      src/selfplay/worker.cc:352-362) ------------------------------------------------------------------------------
+    // A move can only give check if its target is aligned with the enemy king (direct check) or its origin is (a
+    // discovered check); only those are made and looked at.
+    bool mayGiveCheck(const Move& M) const {
+        const int K = KingSq[Side ^ 1];
+        if (K == 255) return false;
+        const LineTable& L = lineTable();
+        return L.Aligned[M.To][K] || (!M.isDrop() && L.Aligned[M.From][K]);
+    }
+    // Has the side to move a move that checkmates?  (A mating pawn drop is not a legal move, so it is never found.)
+    bool mateIn1(Move* Mate = nullptr) {
+        Move Ms[kMaxMoves];
+        const int N = generateLegal(Ms);
+        const int Me = Side;
+        for (int I = 0; I < N; ++I) {
+            if (!mayGiveCheck(Ms[I])) continue;
+            Undo U;
+            make(Ms[I], &U);
+            const bool Mated = inCheck(Me ^ 1) && !hasLegalMove();
+            unmake(Ms[I], U);
+            if (Mated) {
+                if (Mate) *Mate = Ms[I];
+                return true;
+            }
+        }
+        return false;
+    }
+    // Mate in at most three plies: a check to which every answer allows a mate in one (or to which there is none).
+    bool mateIn3(Move* First = nullptr) {
+        Move Ms[kMaxMoves];
+        const int N = generateLegal(Ms);
+        const int Me = Side;
+        for (int I = 0; I < N; ++I) {
+            if (!mayGiveCheck(Ms[I])) continue;
+            Undo U;
+            make(Ms[I], &U);
+            bool Wins = false;
+            if (inCheck(Me ^ 1)) {
+                Move Ev[kMaxMoves];
+                const int NE = generateLegal(Ev);
+                Wins = true;  // no evasion: mate in one
+                for (int J = 0; J < NE && Wins; ++J) {
+                    Undo V;
+                    make(Ev[J], &V);
+                    Wins = mateIn1();
+                    unmake(Ev[J], V);
+                }
+            }
+            unmake(Ms[I], U);
+            if (Wins) {
+                if (First) *First = Ms[I];
+                return true;
+            }
+        }
+        return false;
     }
 
     uint64_t perft(int Depth) {

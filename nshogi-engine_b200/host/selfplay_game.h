@@ -28,6 +28,10 @@ struct GameOptions {
     int Playouts = 200;
     bool Gumbel = false;
     double FullSearchRatio = 0.25;
+    // 0 / 1 / 3: shallow mate search at every new leaf and at the root of a position just reached (the reference asks
+    // libnshogi's solver::dfs::solve(State, 3) at leaves, worker.cc:352-362, and its df-pn solver in judge, :517).  Off by
+    // default: rules/shogi.h's search costs 4-7x a move generation; a build against libnshogi uses its solvers.
+    int MatePlies = 0;
 };
 
 struct Frame {  // reference src/selfplay/frame.h: one game in flight
@@ -59,7 +63,7 @@ struct Frame {  // reference src/selfplay/frame.h: one game in flight
 struct Info {  // reference src/selfplay/selfplayinfo.h
     std::atomic<uint64_t> Evals{0}, Batches{0}, Records{0}, Games{0}, NanRows{0}, CacheHits{0};
     std::atomic<uint64_t> Mates{0}, Repetitions{0}, MaxPlies{0}, Terminals{0}, PliesPlayed{0}, LegalMoves{0};
-    std::atomic<uint64_t> Declarations{0}, PerpetualChecks{0};
+    std::atomic<uint64_t> Declarations{0}, PerpetualChecks{0}, MatesBySearch{0}, LeafMatesBySearch{0};
 };
 
 // Worker::initialize, worker.cc:112-156
@@ -125,7 +129,7 @@ inline Repetition repetitionStatus(const std::vector<uint64_t>& History, const s
 }
 
 // Worker::transition + judge, worker.cc:520-640,476-518: play the most visited move; true when the game is over.
-inline bool transition(Frame& F, Info* SI) {
+inline bool transition(const GameOptions& O, Frame& F, Info* SI) {
     const int Best = F.Tree.bestRootEdge();
     const rules::Move M = F.Tree.edgesOf(0)[Best].M;
     rules::Position::Undo U;
@@ -157,6 +161,11 @@ inline bool transition(Frame& F, Info* SI) {
     if (!F.Root.hasLegalMove()) {
         SI->Mates.fetch_add(1, std::memory_order_relaxed);
         F.Winner = F.Root.Side == 0 ? teacher::WinnerWhite : teacher::WinnerBlack;  // the side to move is mated
+        return true;
+    }
+    if (O.MatePlies > 0 && (O.MatePlies >= 3 ? F.Root.mateIn3() : F.Root.mateIn1())) {  // judge, worker.cc:517-523: a forced mate ends the game
+        SI->MatesBySearch.fetch_add(1, std::memory_order_relaxed);
+        F.Winner = F.Root.Side == 0 ? teacher::WinnerBlack : teacher::WinnerWhite;
         return true;
     }
     return false;
@@ -210,7 +219,7 @@ inline void advance(const GameOptions& O, Frame& F, Info* SI, GameEnd&& OnGameEn
         const search::Node& Root = F.Tree.node(0);
         if (Root.evaluated() && (Root.NumEdges == 1 || Root.Visits >= F.Playouts + 1)) {  // worker.cc:415-430 (+1: the root's own evaluation)
             NSB_PHASE(Root, {
-                if (transition(F, SI)) {
+                if (transition(O, F, SI)) {
                     SI->Games.fetch_add(1, std::memory_order_relaxed);
                     OnGameEnd(F);
                     newGame(O, F);
@@ -261,6 +270,13 @@ inline void advance(const GameOptions& O, Frame& F, Info* SI, GameEnd&& OnGameEn
             F.Tree.setTerminal(Node, search::DrawnGame);
             SI->Terminals.fetch_add(1, std::memory_order_relaxed);
             F.Tree.backup(Node, 0.5f, 1.0f);
+            continue;
+        }
+        if (O.MatePlies > 0 && Node != 0 && (O.MatePlies >= 3 ? F.Leaf.mateIn3() : F.Leaf.mateIn1())) {  // worker.cc:352-362
+            F.Tree.setTerminal(Node, search::Declared);  // (the same terminal kind: the side to move wins)
+            SI->Terminals.fetch_add(1, std::memory_order_relaxed);
+            SI->LeafMatesBySearch.fetch_add(1, std::memory_order_relaxed);
+            F.Tree.backup(Node, 1.0f, 0.0f);
             continue;
         }
         NSB_PHASE(Expand, F.Tree.expand(Node, F.LeafMoves, NumMoves));

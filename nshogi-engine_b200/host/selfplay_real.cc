@@ -78,6 +78,7 @@ int main(int argc, char** argv) {
         else if (A == "--full-search-ratio") O.FullSearchRatio = nextD();
         else if (A == "--cache-mb") O.CacheMiB = nextI();
         else if (A == "--gumbel") O.Gumbel = true;
+        else if (A == "--leaf-mate-plies") O.MatePlies = nextI();
         else if (A == "--seconds") O.Seconds = nextD();
         else if (A == "--warmup") O.Warmup = nextD();
         else if (A == "--seed") O.Seed = (uint64_t)nextI();
@@ -163,7 +164,7 @@ int main(int argc, char** argv) {
                 "\"leaf_evals_per_sec\": %.1f, \"games_per_sec\": %.3f, \"avg_batch\": %.1f, \"seconds\": %.3f, "
                 "\"records\": %llu, \"evals\": %llu, \"batches\": %llu, \"games\": %llu, "
                 "\"cache_mb\": %d, \"cache_hit_rate\": %.4f, \"terminal_leaves_per_eval\": %.4f, \"avg_legal_moves\": %.1f, "
-                "\"games_ended\": {\"mate\": %llu, \"repetition\": %llu, \"of_which_perpetual_check\": %llu, \"declaration\": %llu, \"max_ply\": %llu}, \"deepest_game_ply\": %llu, "
+                "\"games_ended\": {\"mate\": %llu, \"repetition\": %llu, \"of_which_perpetual_check\": %llu, \"declaration\": %llu, \"max_ply\": %llu, \"mate_found_by_search\": %llu}, \"leaf_mate_plies\": %d, \"leaf_mates_by_search\": %llu, \"deepest_game_ply\": %llu, "
                 "\"teacher\": {\"games_saved\": %llu, \"records_saved\": %llu, \"black_wins\": %llu, \"white_wins\": %llu, \"draws\": %llu, "
                 "\"file\": \"%s\", \"what\": \"full-search positions of finished games (saveworker.cc:160-182), NSBT format\"}, "
                 "\"net\": \"%dx%d\", \"batch_size\": %d, \"frame_pool\": %d, \"search_workers\": %d, \"slots\": %d, \"min_fill\": %d, "
@@ -172,13 +173,14 @@ int main(int argc, char** argv) {
                 "\"share_waiting_for_frames\": %.3f}, "
                 "\"decode\": \"NSB_DECODE_BOTH + order_out (logits cached, probabilities and rank order out; %s)\", "
                 "\"rules\": \"real: host/rules/shogi.h (perft-pinned move generation, mate, four-fold repetition, "
-                "perpetual check, 27-point declaration, max ply), PUCT tree host/mcts_search.h; no mate solver\"}\n",
+                "perpetual check, 27-point declaration, max ply), PUCT tree host/mcts_search.h; shallow mate search optional (--leaf-mate-plies)\"}\n",
                 (double)(R1 - R0) / Sec, Evals / Sec, (double)(G1 - G0) / Sec, Batches > 0 ? Evals / Batches : 0.0, Sec,
                 (unsigned long long)(R1 - R0), (unsigned long long)(E1 - E0), (unsigned long long)(B1 - B0),
                 (unsigned long long)(G1 - G0), O.CacheMiB, Evals > 0 ? (double)(H1 - H0) / Evals : 0.0,
                 Evals > 0 ? (double)(T1n - T0n) / Evals : 0.0, Evals > 0 ? (double)(L1 - L0) / Evals : 0.0,
                 (unsigned long long)SI.Mates.load(), (unsigned long long)SI.Repetitions.load(), (unsigned long long)SI.PerpetualChecks.load(),
-                (unsigned long long)SI.Declarations.load(), (unsigned long long)SI.MaxPlies.load(),
+                (unsigned long long)SI.Declarations.load(), (unsigned long long)SI.MaxPlies.load(), (unsigned long long)SI.MatesBySearch.load(),
+                O.MatePlies, (unsigned long long)SI.LeafMatesBySearch.load(),
                 (unsigned long long)MaxDepthPly, (unsigned long long)Saved.Games.load(), (unsigned long long)Saved.Records.load(),
                 (unsigned long long)Saved.Winners[0].load(), (unsigned long long)Saved.Winners[1].load(),
                 (unsigned long long)Saved.Winners[2].load(), O.Out.c_str(), O.Blocks, O.Channels, O.Batch, O.Frames, O.SearchWorkers, O.Slots, O.MinFill, O.Playouts,
