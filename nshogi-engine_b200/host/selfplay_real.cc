@@ -7,18 +7,21 @@
 // [evaluation] -> backpropagate -> transition -> judge), ONE evaluation worker per GPU (evaluationworker.cc:69-117), two
 // frame queues between them (framequeue.cc).  What differs from the reference, on purpose:
 //   - rules, move generation, repetition: host/rules/shogi.h (libnshogi is not available; perft-pinned);
-//   - tree: host/mcts_search.h (PUCT with the reference's constants; no mate solver, no tree reuse between moves);
+//   - tree: host/mcts_search.h (PUCT with the reference's constants; no tree reuse between moves); the 3-ply mate search
+//     the reference asks at every leaf is optional here (--leaf-mate-plies 3: rules/shogi.h mateIn3), its df-pn solver absent;
 //   - the evaluation worker (host/evaluation_worker_b200.h, a worker::Worker like the reference's) does not build
-//     features and does not block per batch: it copies 108-byte position records
-//     and the legal moves' policy slots into the next pinned slot, submits (stage 1, forward, gather, cache store of the
-//     raw logits, softmax and the edges' rank order all happen in ONE launch: NSB_DECODE_BOTH + order_out) and waits
-//     only for the oldest batch;
-//   - teacher records are counted, not written (the record format is libnshogi's io::file::simple_teacher,
-//     saveworker.cc:160-182).
+//     features and does not block per batch: it copies 108-byte position records and the legal moves' policy slots into
+//     the next pinned slot, submits (stage 1, forward, gather, cache store of the raw logits, softmax and the edges' rank
+//     order all happen in ONE launch: NSB_DECODE_BOTH + order_out), waits only for the oldest batch and leaves each
+//     decoded row with its frame; the search worker that takes the frame next writes the priors and back-propagates
+//     (host/selfplay_workers.h, host/selfplay_game.h);
+//   - finished games are written by a save worker as NSBT teacher records (host/teacher_io.h; --out FILE), not in
+//     libnshogi's io::file::simple_teacher layout (saveworker.cc:160-182), which is defined outside the reference tree.
 // Games start from hirate; per game MaxPly ~ U[224, 640] and the draw values of worker.cc:135-150; per move a full
 // search (--num-playouts) with probability --full-search-ratio, else a quarter of it (worker.cc:184-197); AlphaZero
 // style: Dirichlet(0.15) noise mixed into the root priors of full searches (frame.cc:121-133), the most visited move is
-// played (worker.cc:555-590).  A game ends by mate, four-fold repetition (draw) or at MaxPly (draw).
+// played (worker.cc:555-590).  A game ends by mate, 27-point declaration, four-fold repetition (a draw, or lost by the
+// side whose every move of the cycle gave check) or at MaxPly (draw).
 #include <atomic>
 #include <chrono>
 #include <cmath>

@@ -27,7 +27,7 @@ namespace game {
 
 struct HarnessOptions : GameOptions {
     int CacheMiB = 0;
-    std::string Out;  // main.cc -o / --out: the teacher file ("" = records are counted, not written)
+    std::string Out;  // main.cc -o / --out: the teacher file ("" = the records are built and counted, not written)
 };
 
 class FrameQueue {  // reference src/selfplay/framequeue.h
