@@ -43,6 +43,9 @@ class EvaluationClient {
     virtual void deliver(void* Task, SlotT& S, std::size_t Row) = 0;
     // The delivered tasks go back to the search side (SearchQueue->add, evaluationworker.cc:114); clears Tasks.
     virtual void release(std::vector<void*>& Tasks) = 0;
+    // Called while the worker would otherwise block on the GPU (the oldest slot is not done yet): do a SMALL piece of
+    // useful work - a few microseconds - and return true, or return false to let the worker block.  Default: block.
+    virtual bool help() { return false; }
 };
 
 template <typename PipelineT>
@@ -71,6 +74,7 @@ class PipelinedEvaluationWorker : public worker::Worker {
     double secondsCollecting() const { return TCollect; }
     double secondsDelivering() const { return TDeliver; }
     double secondsTaking() const { return TTake; }
+    double secondsHelping() const { return THelp; }  // part of secondsCollecting(): spent in EvaluationClient::help()
 
  protected:
     void initializationTask() override {
@@ -113,6 +117,9 @@ class PipelinedEvaluationWorker : public worker::Worker {
         const std::size_t K = InFlight.front();
         InFlight.pop_front();
         const auto T0 = Clock::now();
+        const auto TH = Clock::now();
+        while (!Pipe->ready(K) && Client->help()) {}  // a thread that waits for the GPU can run a search step meanwhile
+        THelp += seconds(TH);
         Slot& S = Pipe->collect(K);
         TCollect += seconds(T0);
         const auto T1 = Clock::now();
@@ -140,7 +147,7 @@ class PipelinedEvaluationWorker : public worker::Worker {
     std::deque<std::size_t> InFlight;
     std::vector<void*> Tasks;
     uint64_t Batches = 0, Rows = 0;
-    double TFill = 0, TCollect = 0, TDeliver = 0, TTake = 0;
+    double TFill = 0, TCollect = 0, TDeliver = 0, TTake = 0, THelp = 0;
 };
 
 } // namespace evaluate

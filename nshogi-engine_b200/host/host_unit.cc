@@ -864,7 +864,9 @@ struct MockEvalPipeline {
     std::size_t numSlots() const { return Slots.size(); }
     std::size_t batchMax() const { return BatchMax; }
     Slot& acquire(std::size_t* K) { *K = Next; Next = (Next + 1) % Slots.size(); return Slots[*K]; }
-    void submit(std::size_t K, std::size_t Rows, bool, int, bool, bool) { Slots[K].Count = Rows; }
+    void submit(std::size_t K, std::size_t Rows, bool, int, bool, bool) { Slots[K].Count = Rows; Polls = 0; }
+    bool ready(std::size_t) { return ++Polls > 2; }   // (a batch is "done" on the third look: the worker's help() path runs)
+    std::size_t Polls = 0;
     Slot& collect(std::size_t K) {
         Slot& S = Slots[K];
         for (std::size_t R = 0; R < S.Count; ++R) {
@@ -909,8 +911,8 @@ static int selfplayLoop(int Workers, std::size_t Frames, int Milliseconds) {
     std::atomic<bool> Saving{true};
     std::thread Saver(saveWorker, std::cref(O), &Saves, &Saved, &Saving);
     MockEvalPipeline Pipe(3, 32);
-    FrameClient<MockEvalPipeline::Slot> Client(O, &EvaluationQueue, &SearchQueue, &SI);
     std::atomic<bool> Closing{false};
+    FrameClient<MockEvalPipeline::Slot> Client(O, &EvaluationQueue, &SearchQueue, &SI, &Saves, &Closing);
     {
         evaluate::PipelinedEvaluationWorker<MockEvalPipeline> Evaluation(&Pipe, &Client, true, 2, false, true);
         std::vector<std::unique_ptr<SearchWorker>> Searchers;

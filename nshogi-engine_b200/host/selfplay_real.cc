@@ -61,7 +61,7 @@ using namespace b200::game;
 
 int main(int argc, char** argv) {
     Options O;
-    bool Verbose = false;
+    bool Verbose = false, NoHelp = false;
     auto stage = [&](const char* What) {
         if (Verbose) std::fprintf(stderr, "nsb_selfplay_real: %s\n", What);
     };
@@ -87,6 +87,7 @@ int main(int argc, char** argv) {
         else if (A == "--seed") O.Seed = (uint64_t)nextI();
         else if (A == "--out" || A == "-o") O.Out = I + 1 < argc ? argv[++I] : "";
         else if (A == "--verbose") Verbose = true;
+        else if (A == "--no-help") NoHelp = true;  // the evaluation thread blocks on the GPU instead of running search steps meanwhile
         else {
             std::fprintf(stderr, "unknown option %s\n", A.c_str());
             return 2;
@@ -118,7 +119,8 @@ int main(int argc, char** argv) {
     std::atomic<bool> Saving{true};
     std::thread Saver(saveWorker, std::cref(O), &Saves, &Saved, &Saving);
     evaluate::LeafPipeline Pipe(&Exec, (std::size_t)O.Batch);
-    FrameClient<evaluate::LeafPipeline::Slot> Client(O, &EvaluationQueue, &SearchQueue, &SI);
+    std::atomic<bool> Closing{false};
+    FrameClient<evaluate::LeafPipeline::Slot> Client(O, &EvaluationQueue, &SearchQueue, &SI, NoHelp ? nullptr : &Saves, &Closing);
     evaluate::PipelinedEvaluationWorker<evaluate::LeafPipeline> Evaluation(
         &Pipe, &Client, /*FromPositions=*/true, NSB_DECODE_BOTH, /*UseCache=*/O.CacheMiB > 0, /*Ranked=*/true,
         [](void* E) {  // on the worker thread, as selfplay/evaluationworker.cc:62-67 binds its executor
@@ -126,7 +128,6 @@ int main(int argc, char** argv) {
             static_cast<infer::B200*>(E)->bindThreadToGpuNode();  // evaluator.cc:39-83
         },
         &Exec, (std::size_t)O.MinFill);
-    std::atomic<bool> Closing{false};
     std::vector<std::unique_ptr<SearchWorker>> Searchers;
     for (int W = 0; W < O.SearchWorkers; ++W)
         Searchers.push_back(std::make_unique<SearchWorker>(O, &SearchQueue, &EvaluationQueue, &Saves, &SI, &Closing));
@@ -173,7 +174,7 @@ int main(int argc, char** argv) {
                 "\"net\": \"%dx%d\", \"batch_size\": %d, \"frame_pool\": %d, \"search_workers\": %d, \"slots\": %d, \"min_fill\": %d, "
                 "\"num_playouts\": %d, \"full_search_ratio\": %.2f, \"nan_rows\": %llu, "
                 "\"evaluation_worker\": {\"us_per_row_filling\": %.3f, \"us_per_row_delivering\": %.3f, \"share_waiting_for_gpu\": %.3f, "
-                "\"share_waiting_for_frames\": %.3f}, "
+                "\"share_waiting_for_frames\": %.3f, \"share_helping_search\": %.3f}, "
                 "\"decode\": \"NSB_DECODE_BOTH + order_out (logits cached, probabilities and rank order out; %s)\", "
                 "\"rules\": \"real: host/rules/shogi.h (perft-pinned move generation, mate, four-fold repetition, "
                 "perpetual check, 27-point declaration, max ply), PUCT tree host/mcts_search.h; shallow mate search optional (--leaf-mate-plies)\"}\n",
@@ -190,7 +191,8 @@ int main(int argc, char** argv) {
                 O.FullSearchRatio, (unsigned long long)SI.NanRows.load(),
                 1e6 * Evaluation.secondsFilling() / std::max<double>(1.0, (double)Evaluation.rows()),
                 1e6 * Evaluation.secondsDelivering() / std::max<double>(1.0, (double)Evaluation.rows()),
-                Evaluation.secondsCollecting() / EvalTotal, Evaluation.secondsTaking() / EvalTotal,
+                (Evaluation.secondsCollecting() - Evaluation.secondsHelping()) / EvalTotal, Evaluation.secondsTaking() / EvalTotal,
+                Evaluation.secondsHelping() / EvalTotal,
                 O.Gumbel ? "Gumbel roots skip the softmax" : "Dirichlet mix at full-search roots on the host");
     return 0;
 }

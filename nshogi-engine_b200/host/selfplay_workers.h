@@ -163,8 +163,21 @@ class SearchWorker : public worker::Worker {
 template <typename SlotT>
 class FrameClient : public evaluate::EvaluationClient<SlotT> {
  public:
-    FrameClient(const HarnessOptions& Opt, FrameQueue* Evaluation, FrameQueue* Search, Info* I)
-        : O(Opt), EvaluationQueue(Evaluation), SearchQueue(Search), SI(I) {}
+    // Helper: with a save queue the evaluation thread runs search steps while it waits for the GPU (help()).
+    // (Like the search workers it stops taking frames once the harness is closing: the pool must run dry.)
+    FrameClient(const HarnessOptions& Opt, FrameQueue* Evaluation, FrameQueue* Search, Info* I, SaveQueue* Helper = nullptr,
+                const std::atomic<bool>* WindDown = nullptr)
+        : O(Opt), EvaluationQueue(Evaluation), SearchQueue(Search), SI(I), Saves(Helper), Closing(WindDown) {}
+
+    bool help() override {  // four frames' worth of a search worker's doTask()
+        if (Saves == nullptr || (Closing && Closing->load(std::memory_order_relaxed))) return false;
+        HelpIn.clear();
+        SearchQueue->get(4, false, HelpIn);
+        if (HelpIn.empty()) return false;
+        for (Frame* F : HelpIn) advance(O, *F, SI, [&](const Frame& Done) { Saves->add(finishedGame(Done)); });
+        EvaluationQueue->add(HelpIn);
+        return true;
+    }
 
     void take(std::size_t Max, bool Wait, std::vector<void*>& Out) override {  // :70-81
         Frames.clear();
@@ -204,7 +217,9 @@ class FrameClient : public evaluate::EvaluationClient<SlotT> {
     FrameQueue* EvaluationQueue;
     FrameQueue* SearchQueue;
     Info* SI;
-    std::vector<Frame*> Frames;
+    SaveQueue* Saves;
+    const std::atomic<bool>* Closing;
+    std::vector<Frame*> Frames, HelpIn;
 };
 
 } // namespace game
