@@ -87,6 +87,14 @@ class PipelinedEvaluationWorker : public worker::Worker {
         TTake += seconds(T0);
         if (Tasks.empty()) {
             if (InFlight.empty()) return false;  // idle AND drained: the only state in which the worker can be stopped
+            // nothing to submit, a slot free, the oldest batch still running: a search step may produce work for that slot
+            if (InFlight.size() < Pipe->numSlots() && !Pipe->ready(InFlight.front())) {
+                const auto TH = Clock::now();
+                const bool Helped = Client->help();
+                THelp += seconds(TH);
+                TCollect += seconds(TH);
+                if (Helped) return true;
+            }
             deliverOldest();
             return true;
         }
