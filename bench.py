@@ -607,6 +607,7 @@ def usi_leg(args, info):
     out = {}
     for name, extra in (("search_threads_2_reference_default", ["--num-search-threads", "2"]),
                         (f"search_threads_{threads}", ["--num-search-threads", str(threads)]),
+                        ("search_threads_2_device_cache_4GiB", ["--num-search-threads", "2", "--cache-mb", "4096"]),
                         (f"search_threads_{threads}_device_cache_4GiB", ["--num-search-threads", str(threads), "--cache-mb", "4096"])):
         try:
             r = subprocess.run([exe, "--gpu", str(info.local_rank), "--channels", str(args.channels), "--blocks", str(args.blocks),

@@ -14,6 +14,7 @@
 // results as soon as a batch is done.  Rules: host/rules/shogi.h; tree: host/mcts_search.h, shared lock-free (27-point declaration;
 // no mate solver).
 #include <atomic>
+#include <memory>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +35,7 @@ using Clock = std::chrono::steady_clock;
 
 int main(int argc, char** argv) {
     int Channels = 256, Blocks = 20, Batch = 512, Slots = 3, GPU = 0, CacheMiB = 0, SearchThreads = 2;
+    bool NoHelp = false;
     double Seconds = 5.0;
     uint64_t Seed = 1234;
     for (int I = 1; I < argc; ++I) {
@@ -47,6 +49,7 @@ int main(int argc, char** argv) {
         else if (A == "--cache-mb") CacheMiB = nextI();
         else if (A == "--num-search-threads") SearchThreads = nextI();  // context.h:74 default 2
         else if (A == "--seed") Seed = (uint64_t)nextI();
+        else if (A == "--no-help") NoHelp = true;  // the evaluation thread idles instead of collecting leaves between its duties
         else if (A == "--seconds") Seconds = I + 1 < argc ? std::atof(argv[++I]) : 0.0;
         else {
             std::fprintf(stderr, "unknown option %s\n", A.c_str());
@@ -89,74 +92,94 @@ int main(int argc, char** argv) {
         ++Evals;
     };
 
-    // SearchWorker::doTask (searchworker.cc:448-609)
-    auto searchThread = [&]() {
-        rules::Move Moves[rules::kMaxMoves];
-        uint16_t Slots_[rules::kMaxMoves];
-        std::vector<uint64_t> Path;
-        std::vector<int> Trail;
-        while (Running.load(std::memory_order_relaxed)) {
-            rules::Position Pos = Root;
-            Path.clear();
-            const int Node = T.selectLeaf(Pos, 0.5f, 0.5f, &Path, &Trail);  // collectOneLeaf; leaves a virtual loss on the path
-            if (Node == search::Tree::OutOfMemory) {
-                TreeFull.store(true, std::memory_order_relaxed);
-                break;
-            }
-            if (Node < 0) {  // ran into a leaf that is being evaluated (searchworker.cc:349-357)
-                Collisions.fetch_add(1, std::memory_order_relaxed);
-                std::this_thread::yield();
-                continue;
-            }
-            {
-                const search::Node& N = T.node(Node);
-                if (N.Term == search::Mated) {
-                    T.backup(Node, 0.0f, 0.0f);
-                    continue;
-                }
-                if (N.Term == search::DrawnGame) {
-                    T.backup(Node, 0.5f, 1.0f);
-                    continue;
-                }
-                if (N.Term == search::Declared) {
-                    T.backup(Node, 1.0f, 0.0f);
-                    continue;
-                }
-            }
-            if (Node != 0 && Pos.canDeclare()) {  // 27-point declaration: the side to move wins
-                T.setTerminal(Node, search::Declared);
-                T.backup(Node, 1.0f, 0.0f);
-                Terminals.fetch_add(1, std::memory_order_relaxed);
-                continue;
-            }
-            const int NumMoves = Pos.generateLegal(Moves);  // expandLeaf, :164-173 - outside the lock
-            const bool Mated = NumMoves == 0;
-            const bool Drawn = !Mated && Node != 0 && (search::isFourfold(Pos.Hash, History, Path) || Pos.Ply >= MaxPly);
-            if (Mated || Drawn) {  // terminal checks, :475-538
-                T.setTerminal(Node, Mated ? search::Mated : search::DrawnGame);
-                T.backup(Node, Mated ? 0.0f : 0.5f, Mated ? 0.0f : 1.0f);
-                Terminals.fetch_add(1, std::memory_order_relaxed);
-                continue;
-            }
-            for (int J = 0; J < NumMoves; ++J) Slots_[J] = (uint16_t)Pos.policyIndex(Moves[J]);  // ml::getMoveIndex
-            if (!T.expand(Node, Moves, NumMoves)) {
-                TreeFull.store(true, std::memory_order_relaxed);
-                break;
-            }
-            evaluate::LeafQueue::Ticket Tk;
-            while (!Queue.reserve((uint16_t)NumMoves, (void*)(uintptr_t)(Node + 1), &Tk)) {  // EvaluationQueue::add, evaluationqueue.cc:45-60
-                if (!Running.load(std::memory_order_relaxed)) break;
-                std::this_thread::yield();
-            }
-            if (Tk.S == nullptr) break;  // shutting down with the leaf unqueued: its virtual loss dies with the tree
-            Pos.toRecord(&Tk.S->Positions[Tk.Row], MaxPly, 0.5f, 0.5f);  // stage 1 runs on the GPU
-            Tk.S->Hashes[Tk.Row] = Pos.Hash;
-            std::memcpy(Tk.S->MoveIndices + Tk.MoveBegin, Slots_, (std::size_t)NumMoves * sizeof(uint16_t));
-            LegalMoves.fetch_add((uint64_t)NumMoves, std::memory_order_relaxed);
-            Queue.publish(Tk);
-        }
+    auto submitOpen = [&]() {
+        const auto W0 = Clock::now();
+        Queue.submitOpen(/*FromPositions=*/true, NSB_DECODE_PROBS, /*UseCache=*/CacheMiB > 0, /*Ranked=*/true, feed);
+        GpuWaitNs += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - W0).count();
+        ++Batches;
     };
 
+    // SearchWorker::doTask (searchworker.cc:448-609): one leaf.  Returns false when the search is over for this thread.
+    // Helper = the evaluation thread between its own duties (--no-help switches that off): it must never wait for a row
+    // of the open batch - nobody else would submit the full one - so it submits it itself.
+    struct Scratch {
+        rules::Move Moves[rules::kMaxMoves];
+        uint16_t Slots[rules::kMaxMoves];
+        std::vector<uint64_t> Path;
+        std::vector<int> Trail;
+    };
+    auto searchStep = [&](Scratch& C, bool Helper) -> bool {
+        rules::Position Pos = Root;
+        C.Path.clear();
+        const int Node = T.selectLeaf(Pos, 0.5f, 0.5f, &C.Path, &C.Trail);  // collectOneLeaf; leaves a virtual loss on the path
+        if (Node == search::Tree::OutOfMemory) {
+            TreeFull.store(true, std::memory_order_relaxed);
+            return false;
+        }
+        if (Node < 0) {  // ran into a leaf that is being evaluated (searchworker.cc:349-357)
+            Collisions.fetch_add(1, std::memory_order_relaxed);
+            if (!Helper) std::this_thread::yield();
+            return true;
+        }
+        {
+            const search::Node& N = T.node(Node);
+            if (N.Term == search::Mated) {
+                T.backup(Node, 0.0f, 0.0f);
+                return true;
+            }
+            if (N.Term == search::DrawnGame) {
+                T.backup(Node, 0.5f, 1.0f);
+                return true;
+            }
+            if (N.Term == search::Declared) {
+                T.backup(Node, 1.0f, 0.0f);
+                return true;
+            }
+        }
+        if (Node != 0 && Pos.canDeclare()) {  // 27-point declaration: the side to move wins
+            T.setTerminal(Node, search::Declared);
+            T.backup(Node, 1.0f, 0.0f);
+            Terminals.fetch_add(1, std::memory_order_relaxed);
+            return true;
+        }
+        const int NumMoves = Pos.generateLegal(C.Moves);  // expandLeaf, :164-173 - outside the lock
+        const bool Mated = NumMoves == 0;
+        const bool Drawn = !Mated && Node != 0 && (search::isFourfold(Pos.Hash, History, C.Path) || Pos.Ply >= MaxPly);
+        if (Mated || Drawn) {  // terminal checks, :475-538
+            T.setTerminal(Node, Mated ? search::Mated : search::DrawnGame);
+            T.backup(Node, Mated ? 0.0f : 0.5f, Mated ? 0.0f : 1.0f);
+            Terminals.fetch_add(1, std::memory_order_relaxed);
+            return true;
+        }
+        for (int J = 0; J < NumMoves; ++J) C.Slots[J] = (uint16_t)Pos.policyIndex(C.Moves[J]);  // ml::getMoveIndex
+        if (!T.expand(Node, C.Moves, NumMoves)) {
+            TreeFull.store(true, std::memory_order_relaxed);
+            return false;
+        }
+        evaluate::LeafQueue::Ticket Tk;
+        while (!Queue.reserve((uint16_t)NumMoves, (void*)(uintptr_t)(Node + 1), &Tk)) {  // EvaluationQueue::add, evaluationqueue.cc:45-60
+            if (Helper) {
+                submitOpen();  // the open batch is full: sending it is this thread's own job
+                continue;
+            }
+            if (!Running.load(std::memory_order_relaxed)) break;
+            std::this_thread::yield();
+        }
+        if (Tk.S == nullptr) return false;  // shutting down with the leaf unqueued: its virtual loss dies with the tree
+        Pos.toRecord(&Tk.S->Positions[Tk.Row], MaxPly, 0.5f, 0.5f);  // stage 1 runs on the GPU
+        Tk.S->Hashes[Tk.Row] = Pos.Hash;
+        std::memcpy(Tk.S->MoveIndices + Tk.MoveBegin, C.Slots, (std::size_t)NumMoves * sizeof(uint16_t));
+        LegalMoves.fetch_add((uint64_t)NumMoves, std::memory_order_relaxed);
+        Queue.publish(Tk);
+        return true;
+    };
+    auto searchThread = [&]() {
+        auto C = std::make_unique<Scratch>();
+        while (Running.load(std::memory_order_relaxed) && searchStep(*C, false)) {}
+    };
+
+    auto EvalScratch = std::make_unique<Scratch>();
+    uint64_t HelpedLeaves = 0;
     Queue.open(feed);
     std::vector<std::thread> Threads;
     const auto T0 = Clock::now();
@@ -169,12 +192,11 @@ int main(int argc, char** argv) {
     while (elapsed() < Seconds && !TreeFull.load(std::memory_order_relaxed)) {
         const std::size_t Rows = Queue.openRows(), Busy = Queue.inFlight();
         if (Rows >= (std::size_t)Batch || (Rows > 0 && Busy == 0) || (Rows >= (std::size_t)Batch / 2 && Busy == 1 && NS > 2)) {
-            const auto W0 = Clock::now();
-            Queue.submitOpen(/*FromPositions=*/true, NSB_DECODE_PROBS, /*UseCache=*/CacheMiB > 0, /*Ranked=*/true, feed);
-            GpuWaitNs += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - W0).count();
-            ++Batches;
+            submitOpen();
         } else if (Queue.pollFeed(feed) == 0) {  // FeedWorker::doTask: results go back into the tree as soon as they exist
-            std::this_thread::yield();
+            // nothing to send, nothing to feed: collect a leaf like a search thread instead of idling
+            if (NoHelp || !searchStep(*EvalScratch, true)) std::this_thread::yield();
+            else ++HelpedLeaves;
         }
     }
     Running.store(false);
@@ -207,11 +229,11 @@ int main(int argc, char** argv) {
                 "\"leaf_evals_per_sec\": %.1f, \"avg_batch\": %.1f, \"batches\": %llu, \"terminal_leaves\": %llu, \"collisions\": %llu, "
                 "\"cache_mb\": %d, \"cache_hit_rate\": %.4f, \"avg_legal_moves\": %.1f, \"tree_nodes\": %zu, \"submit_and_feed_fraction\": %.3f, "
                 "\"root_win_rate\": %.4f, \"pv\": \"%s\", \"net\": \"%dx%d\", \"batch_size\": %d, \"slots\": %d, "
-                "\"position\": \"hirate startpos\", \"search_threads\": %d, "
+                "\"position\": \"hirate startpos\", \"search_threads\": %d, \"leaves_collected_by_the_evaluation_thread\": %llu, "
                 "\"rules\": \"real: host/rules/shogi.h + host/mcts_search.h (PUCT, virtual loss, 27-point declaration); no mate solver\"}\n",
                 (double)Nodes / Sec, (unsigned long long)Nodes, Sec * 1e3, (double)Evals / Sec, Batches ? (double)Evals / (double)Batches : 0.0,
                 (unsigned long long)Batches, (unsigned long long)Terminals.load(), (unsigned long long)Collisions.load(), CacheMiB,
                 Evals ? (double)CacheHits / (double)Evals : 0.0, Evals ? (double)LegalMoves.load() / (double)Evals : 0.0, T.numNodes(),
-                (double)GpuWaitNs * 1e-9 / Sec, RootWin, PV.c_str(), Blocks, Channels, Batch, (int)NS, SearchThreads);
+                (double)GpuWaitNs * 1e-9 / Sec, RootWin, PV.c_str(), Blocks, Channels, Batch, (int)NS, SearchThreads, (unsigned long long)HelpedLeaves);
     return 0;
 }
