@@ -36,6 +36,7 @@
 #include "onnx_import.h"
 #include "selfplay_game.h"
 #include "selfplay_workers.h"
+#include "usi_search.h"
 
 using namespace nshogi::engine;
 
@@ -1067,7 +1068,55 @@ static int movegenBench() {
     return 0;
 }
 
+// ---- the USI-style search (host/usi_search.h: search threads filling pinned batches in place, the evaluation thread
+//      submitting, feeding and collecting leaves between its duties) on the mock pipeline: `--usi-loop THREADS MILLISECONDS
+//      [nohelp]`.  Must END; afterwards the tree's invariants hold (no virtual loss left but the abandoned leaves', every edge mirrors its child).
+static int usiLoop(int Threads, int Milliseconds, bool Help) {
+    using namespace b200;
+    MockEvalPipeline Pipe(3, 64);
+    const std::size_t Cap = 400000;
+    search::Tree T(Cap, Cap * 48);
+    const rules::Position Root;
+    UsiSearch<MockEvalPipeline> Search(&T, &Pipe, Root, 320, 0, false);
+    const double Sec = Search.run(Milliseconds * 1e-3, Threads, Help);
+    const search::Node& R = T.node(0);
+    // (a search thread that is stopped while it waits for a row abandons its claimed leaf: at most one virtual loss per
+    //  search thread is left on the paths, usi_search.h searchStep)
+    const uint32_t Slack = (uint32_t)Threads;
+    CHECK(R.evaluated() && R.Visits > 100 && R.VirtualLoss <= Slack);
+    CHECK(Search.Evals > 100 && Search.Batches > 2);
+    if (Help && Threads <= 1) CHECK(Search.HelpedLeaves > 0);
+    if (!Help) CHECK(Search.HelpedLeaves == 0);
+    bool Ok = true;
+    uint64_t Evaluated = 0;
+    for (std::size_t I = 0; I < T.numNodes(); ++I) {
+        const search::Node& N = T.node((int)I);
+        Ok = Ok && N.VirtualLoss <= Slack;
+        if (!N.evaluated()) continue;
+        ++Evaluated;
+        uint64_t Sum = 0;
+        for (int J = 0; J < N.NumEdges; ++J) {
+            const search::Edge& E = T.edgesOf((int)I)[J];
+            if (J > 0 && N.Term == search::Open) Ok = Ok && E.P <= T.edgesOf((int)I)[J - 1].P;
+            if (E.Child >= 0) {
+                Ok = Ok && E.CVisits == T.node(E.Child).Visits && E.CVirtualLoss <= Slack;
+                Sum += T.node(E.Child).Visits;
+            }
+        }
+        if (N.Term == search::Open) Ok = Ok && N.Visits == Sum + 1;
+    }
+    CHECK(Ok);
+    std::printf("usi loop: %d search threads%s, %.0f ms: %u root visits, %llu evaluations in %llu batches, %llu leaves collected by the evaluation "
+                "thread, %llu collisions, %llu evaluated nodes: invariants hold: ok\n",
+                Threads, Help ? " + helping evaluation thread" : "", Sec * 1e3, R.Visits, (unsigned long long)Search.Evals,
+                (unsigned long long)Search.Batches, (unsigned long long)Search.HelpedLeaves, (unsigned long long)Search.Collisions.load(),
+                (unsigned long long)Evaluated);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 4 && std::strcmp(argv[1], "--usi-loop") == 0)
+        return usiLoop(std::atoi(argv[2]), std::atoi(argv[3]), !(argc >= 5 && std::strcmp(argv[4], "nohelp") == 0));
     if (argc >= 2 && std::strcmp(argv[1], "--movegen-bench") == 0) return movegenBench();
     if (argc >= 4 && std::strcmp(argv[1], "--host-cost") == 0)
         return hostCost((std::size_t)std::atol(argv[2]), (std::size_t)std::atol(argv[3]), argc >= 5 ? (std::size_t)std::atol(argv[4]) : 0);
@@ -1144,6 +1193,7 @@ int main(int argc, char** argv) {
     if (selfplayMock(1, 24, 3)) return 1;  // one more with the shallow mate search at leaves and roots
     if (workerCycles(5000) || workerCycles(5000, 48)) return 1;  // the pipelined evaluation worker inside the worker::Worker contract
     if (selfplayLoop(2, 48, 300)) return 1; // the whole harness: starts, plays, winds down
+    if (usiLoop(2, 300, true) || usiLoop(1, 200, true) || usiLoop(2, 200, false)) return 1;  // the USI-style search on the mock pipeline
     std::printf("host_unit ok\n");
     return 0;
 }

@@ -25,9 +25,7 @@
 
 #include "infer_b200.h"
 #include "leaf_pipeline.h"
-#include "leaf_queue.h"
-#include "mcts_search.h"
-#include "rules/shogi.h"
+#include "usi_search.h"
 
 using namespace nshogi::engine;
 using namespace nshogi::engine::b200;
@@ -66,143 +64,21 @@ int main(int argc, char** argv) {
     if (CacheMiB > 0) Exec.enableCache((std::size_t)CacheMiB);  // Manager's EvalCache, manager.cc:202-206
     Exec.resetGPU();
     Exec.bindThreadToGpuNode();
-    evaluate::LeafPipeline Pipe(&Exec, (std::size_t)Batch);
-    evaluate::LeafQueue Queue(&Pipe);  // lock-free in-place batch assembly by the search threads (EvaluationQueue + getBatch)
+    evaluate::LeafPipeline Pipe(&Exec, (std::size_t)Batch);  // search threads assemble batches in place in its pinned slots (host/leaf_queue.h)
     const std::size_t NS = Pipe.numSlots();
 
     const rules::Position Root;  // hirate
-    const std::vector<uint64_t> History{Root.Hash};
     // shared by the search threads and the feeding thread without a lock, like the reference's tree (node.h:59-100);
     // arenas sized for the run: ~350 k nodes/s at ~40 legal moves each
     const std::size_t MaxNodes = (std::size_t)(6.0e5 * (Seconds + 1.0)) + (1u << 16);
     search::Tree T(MaxNodes, MaxNodes * 48);
     const uint16_t MaxPly = 320;  // StateConfig default of the USI front-end
-    std::atomic<uint64_t> Terminals{0}, Collisions{0}, LegalMoves{0};
-    uint64_t Evals = 0, Batches = 0, CacheHits = 0, GpuWaitNs = 0;
-    std::atomic<bool> Running{true}, TreeFull{false};
-
-    // FeedWorker::feedResult (feedworker.cc:56-137) for one row of a collected slot: the gather, the softmax and
-    // Node::sort's permutation came back from the GPU; setEvaluation + updateAncestors are what is left
-    auto feed = [&](evaluate::LeafPipeline::Slot& S, std::size_t Row, void* User) {
-        const int Node = (int)(uintptr_t)User - 1;
-        const uint32_t B = S.MoveOffsets[Row];
-        T.setPriors(Node, S.Legal + B, S.Order + B);
-        T.backup(Node, S.WinRate[Row], S.DrawRate[Row]);
-        if (CacheMiB > 0 && S.HitFlag[Row]) ++CacheHits;
-        ++Evals;
-    };
-
-    auto submitOpen = [&]() {
-        const auto W0 = Clock::now();
-        Queue.submitOpen(/*FromPositions=*/true, NSB_DECODE_PROBS, /*UseCache=*/CacheMiB > 0, /*Ranked=*/true, feed);
-        GpuWaitNs += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - W0).count();
-        ++Batches;
-    };
-
-    // SearchWorker::doTask (searchworker.cc:448-609): one leaf.  Returns false when the search is over for this thread.
-    // Helper = the evaluation thread between its own duties (--no-help switches that off): it must never wait for a row
-    // of the open batch - nobody else would submit the full one - so it submits it itself.
-    struct Scratch {
-        rules::Move Moves[rules::kMaxMoves];
-        uint16_t Slots[rules::kMaxMoves];
-        std::vector<uint64_t> Path;
-        std::vector<int> Trail;
-    };
-    auto searchStep = [&](Scratch& C, bool Helper) -> bool {
-        rules::Position Pos = Root;
-        C.Path.clear();
-        const int Node = T.selectLeaf(Pos, 0.5f, 0.5f, &C.Path, &C.Trail);  // collectOneLeaf; leaves a virtual loss on the path
-        if (Node == search::Tree::OutOfMemory) {
-            TreeFull.store(true, std::memory_order_relaxed);
-            return false;
-        }
-        if (Node < 0) {  // ran into a leaf that is being evaluated (searchworker.cc:349-357)
-            Collisions.fetch_add(1, std::memory_order_relaxed);
-            if (!Helper) std::this_thread::yield();
-            return true;
-        }
-        {
-            const search::Node& N = T.node(Node);
-            if (N.Term == search::Mated) {
-                T.backup(Node, 0.0f, 0.0f);
-                return true;
-            }
-            if (N.Term == search::DrawnGame) {
-                T.backup(Node, 0.5f, 1.0f);
-                return true;
-            }
-            if (N.Term == search::Declared) {
-                T.backup(Node, 1.0f, 0.0f);
-                return true;
-            }
-        }
-        if (Node != 0 && Pos.canDeclare()) {  // 27-point declaration: the side to move wins
-            T.setTerminal(Node, search::Declared);
-            T.backup(Node, 1.0f, 0.0f);
-            Terminals.fetch_add(1, std::memory_order_relaxed);
-            return true;
-        }
-        const int NumMoves = Pos.generateLegal(C.Moves);  // expandLeaf, :164-173 - outside the lock
-        const bool Mated = NumMoves == 0;
-        const bool Drawn = !Mated && Node != 0 && (search::isFourfold(Pos.Hash, History, C.Path) || Pos.Ply >= MaxPly);
-        if (Mated || Drawn) {  // terminal checks, :475-538
-            T.setTerminal(Node, Mated ? search::Mated : search::DrawnGame);
-            T.backup(Node, Mated ? 0.0f : 0.5f, Mated ? 0.0f : 1.0f);
-            Terminals.fetch_add(1, std::memory_order_relaxed);
-            return true;
-        }
-        for (int J = 0; J < NumMoves; ++J) C.Slots[J] = (uint16_t)Pos.policyIndex(C.Moves[J]);  // ml::getMoveIndex
-        if (!T.expand(Node, C.Moves, NumMoves)) {
-            TreeFull.store(true, std::memory_order_relaxed);
-            return false;
-        }
-        evaluate::LeafQueue::Ticket Tk;
-        while (!Queue.reserve((uint16_t)NumMoves, (void*)(uintptr_t)(Node + 1), &Tk)) {  // EvaluationQueue::add, evaluationqueue.cc:45-60
-            if (Helper) {
-                submitOpen();  // the open batch is full: sending it is this thread's own job
-                continue;
-            }
-            if (!Running.load(std::memory_order_relaxed)) break;
-            std::this_thread::yield();
-        }
-        if (Tk.S == nullptr) return false;  // shutting down with the leaf unqueued: its virtual loss dies with the tree
-        Pos.toRecord(&Tk.S->Positions[Tk.Row], MaxPly, 0.5f, 0.5f);  // stage 1 runs on the GPU
-        Tk.S->Hashes[Tk.Row] = Pos.Hash;
-        std::memcpy(Tk.S->MoveIndices + Tk.MoveBegin, C.Slots, (std::size_t)NumMoves * sizeof(uint16_t));
-        LegalMoves.fetch_add((uint64_t)NumMoves, std::memory_order_relaxed);
-        Queue.publish(Tk);
-        return true;
-    };
-    auto searchThread = [&]() {
-        auto C = std::make_unique<Scratch>();
-        while (Running.load(std::memory_order_relaxed) && searchStep(*C, false)) {}
-    };
-
-    auto EvalScratch = std::make_unique<Scratch>();
-    uint64_t HelpedLeaves = 0;
-    Queue.open(feed);
-    std::vector<std::thread> Threads;
-    const auto T0 = Clock::now();
-    auto elapsed = [&]() { return std::chrono::duration<double>(Clock::now() - T0).count(); };
-    for (int I = 0; I < SearchThreads; ++I) Threads.emplace_back(searchThread);
-    // EvaluationWorker::doTask (evaluationworker.cc:105-199).  The reference submits "whatever is queued"; with the
-    // batch assembled in place the rule is: a full batch goes out at once; a partial one goes out when the GPU would
-    // otherwise idle (nothing in flight), or at half size when only one batch is in flight - so the open batch keeps
-    // filling while the GPU is busy and its size follows the parallelism the tree offers.
-    while (elapsed() < Seconds && !TreeFull.load(std::memory_order_relaxed)) {
-        const std::size_t Rows = Queue.openRows(), Busy = Queue.inFlight();
-        if (Rows >= (std::size_t)Batch || (Rows > 0 && Busy == 0) || (Rows >= (std::size_t)Batch / 2 && Busy == 1 && NS > 2)) {
-            submitOpen();
-        } else if (Queue.pollFeed(feed) == 0) {  // FeedWorker::doTask: results go back into the tree as soon as they exist
-            // nothing to send, nothing to feed: collect a leaf like a search thread instead of idling
-            if (NoHelp || !searchStep(*EvalScratch, true)) std::this_thread::yield();
-            else ++HelpedLeaves;
-        }
-    }
-    Running.store(false);
-    for (auto& Th : Threads) Th.join();
-    Queue.drain(true, NSB_DECODE_PROBS, CacheMiB > 0, true, feed);
-    const double Sec = elapsed();
+    // MCTS flavour of the decode: NSB_DECODE_PROBS + order_out (host/usi_search.h holds the search itself)
+    UsiSearch<evaluate::LeafPipeline> Search(&T, &Pipe, Root, MaxPly, NSB_DECODE_PROBS, CacheMiB > 0);
+    const double Sec = Search.run(Seconds, SearchThreads, !NoHelp);
+    const uint64_t Evals = Search.Evals, Batches = Search.Batches, CacheHits = Search.CacheHits, GpuWaitNs = Search.GpuWaitNs;
+    const uint64_t HelpedLeaves = Search.HelpedLeaves;
+    const std::atomic<uint64_t>&Terminals = Search.Terminals, &Collisions = Search.Collisions, &LegalMoves = Search.LegalMoves;
 
     // usilogger.cc:29-65: nodes = visits of the root, nps, pv by most-visited edges
     const uint64_t Nodes = T.node(0).Visits;

@@ -163,7 +163,7 @@ def test_pipelined_evaluation_worker_inside_the_reference_worker_contract(built,
     assert out.returncode == 0 and "all frames accounted for: ok" in out.stdout, out.stdout + out.stderr
 
 
-def test_selfplay_harness_starts_plays_and_winds_down_cpu(built, tmp_path):
+def test_selfplay_and_usi_harnesses_start_play_and_wind_down_cpu(built, tmp_path):
     """host/selfplay_workers.h - the search workers, the pipelined evaluation worker and the save worker of
     nsb_selfplay_real, started and stopped exactly as its main() does - on a mock pipeline that invents the evaluations:
     real rules, real trees, real teacher records.  The run must END within the timeout (a worker::Worker is only
@@ -182,6 +182,14 @@ def test_selfplay_harness_starts_plays_and_winds_down_cpu(built, tmp_path):
     out = subprocess.run([exe, "--selfplay-loop", "3", "48", "400"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "all frames accounted for: ok" in out.stdout, out.stdout + out.stderr
     assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
+    # the USI-style search (host/usi_search.h) on the mock pipeline: search threads filling batches in place, the
+    # evaluation thread submitting, feeding and collecting leaves itself; must end, tree invariants hold, TSAN silent
+    for args in (["3", "400"], ["1", "300"], ["2", "300", "nohelp"]):
+        out = subprocess.run([exe, "--usi-loop", *args], capture_output=True, text=True, timeout=180)
+        assert out.returncode == 0 and "invariants hold: ok" in out.stdout, out.stdout + out.stderr
+        assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
+    out = subprocess.run([os.path.join(built, "nsb_host_unit"), "--usi-loop", "6", "1500"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "invariants hold: ok" in out.stdout, out.stdout + out.stderr
 
 
 def test_real_rules_harnesses_fail_loudly_without_gpu(built, nb):
