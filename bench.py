@@ -460,6 +460,9 @@ def run_b200(args):
     roofline = {"bound": "tensor", "kernel": ctx.trunk_kernel_name(), "achieved": round(achieved_ss, 2),
                 "peak": tf_burst, "unit": "TFLOP/s", "frac": round(achieved_ss / tf_burst, 4),
                 "frac_of_sustained_peak": round(achieved_ss / tf_sust, 4), "peak_source": which,
+                "peak_sustained": tf_sust,
+                "peak_note": "frac is against the BURST bf16 peak of MEASURED_PEAKS.json (conservative); this kernel is timed inside a "
+                             "~1 s step, for which the sustained figure is the applicable denominator: frac_of_sustained_peak",
                 "flops_per_launch": flops_batch, "avg_launch_ms": round(batch_ms, 5),
                 "timing": f"timed region: {K * bps} launches over {slots} streams, CUDA events on the streams, "
                           "duration per launch = elapsed / launches (launches overlap); per GPU",
